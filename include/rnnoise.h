@@ -1,0 +1,148 @@
+/* rnnoise.h -- public C ABI of the B200-native batched denoise engine (librnnoise_b200.so).
+ *
+ * Drop-in surface of xiph/rnnoise's include/rnnoise.h (reference file:line cited per entry point)
+ * plus the batched entry points the B200 engine adds.  Plain C linkage, plain pointers and sizes,
+ * no CUDA or torch types in any signature.  Every entry point that computes runs on the GPU; there
+ * is no CPU fallback: creation fails (NULL / -1) when no CUDA device is usable.
+ *
+ * Data conventions (unchanged from the reference, examples/rnnoise_demo.c:52-61): mono 48 kHz,
+ * 480 samples per frame, float samples in int16 units (+-32768, not +-1); `out` may alias `in`.
+ */
+#ifndef RNNOISE_H
+#define RNNOISE_H 1
+
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef RNNOISE_EXPORT
+# if defined(__GNUC__) && defined(RNNOISE_BUILD)
+#  define RNNOISE_EXPORT __attribute__ ((visibility ("default")))
+# else
+#  define RNNOISE_EXPORT
+# endif
+#endif
+
+typedef struct DenoiseState DenoiseState;
+typedef struct RNNModel RNNModel;
+typedef struct RNNoiseBatch RNNoiseBatch;
+
+/* ------------------------------------------------------------------------------------------ */
+/* Reference surface (single stream).  Each DenoiseState is one stream of a private batch of 1, */
+/* driven through exactly the same kernels as the batched path.                                  */
+/* ------------------------------------------------------------------------------------------ */
+
+/** Size of DenoiseState in bytes.  Replaces reference include/rnnoise.h:57 (src/denoise.c:277). */
+RNNOISE_EXPORT int rnnoise_get_size(void);
+
+/** Samples per rnnoise_process_frame() call (480).  Replaces rnnoise.h:62 (denoise.c:281). */
+RNNOISE_EXPORT int rnnoise_get_frame_size(void);
+
+/** Initialise caller-provided memory of rnnoise_get_size() bytes.  Returns 0, or -1 when the model
+ *  blob lacks/mis-sizes an array (same rule as src/parse_lpcnet_weights.c:123-176) or no GPU is
+ *  usable.  Replaces rnnoise.h:71 (denoise.c:285).  Device resources attached to a state
+ *  initialised this way are released by rnnoise_destroy_inplace() (or at process exit).
+ *  model == NULL selects the built-in model; this build has no built-in weights (the reference
+ *  downloads them, download_model.sh:4-31), so the blob named by $RNNOISE_B200_DEFAULT_MODEL is
+ *  loaded instead and -1 is returned when that is unset or unreadable. */
+RNNOISE_EXPORT int rnnoise_init(DenoiseState *st, RNNModel *model);
+
+/** Allocate + initialise.  NULL on failure.  Replaces rnnoise.h:80 (denoise.c:311). */
+RNNOISE_EXPORT DenoiseState *rnnoise_create(RNNModel *model);
+
+/** Free a state made by rnnoise_create().  Replaces rnnoise.h:87 (denoise.c:323). */
+RNNOISE_EXPORT void rnnoise_destroy(DenoiseState *st);
+
+/** Release the device side of a state set up with rnnoise_init() on caller memory (new). */
+RNNOISE_EXPORT void rnnoise_destroy_inplace(DenoiseState *st);
+
+/** Denoise one 480-sample frame; returns the VAD probability (0 on a silent frame).
+ *  Replaces rnnoise.h:94 (denoise.c:457). */
+RNNOISE_EXPORT float rnnoise_process_frame(DenoiseState *st, float *out, const float *in);
+
+/** Model from a memory buffer (borrowed; must outlive the model).  NULL when the buffer is not a
+ *  well-formed weight blob.  Replaces rnnoise.h:102 (denoise.c:235). */
+RNNOISE_EXPORT RNNModel *rnnoise_model_from_buffer(const void *ptr, int len);
+
+/** Model from an open FILE (contents are copied; the FILE stays the caller's).
+ *  Replaces rnnoise.h:111 (denoise.c:252). */
+RNNOISE_EXPORT RNNModel *rnnoise_model_from_file(FILE *f);
+
+/** Model from a file name; NULL when it cannot be opened (the reference dereferences the failed
+ *  fopen, denoise.c:246-248).  Replaces rnnoise.h:118 (denoise.c:244). */
+RNNOISE_EXPORT RNNModel *rnnoise_model_from_filename(const char *filename);
+
+/** Free a model (after every state/batch using it).  Replaces rnnoise.h:125 (denoise.c:271). */
+RNNOISE_EXPORT void rnnoise_model_free(RNNModel *model);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Batched surface (new; named by the north star).  One RNNoiseBatch = nb_streams independent     */
+/* DenoiseStates resident in the HBM of ONE device, advanced in lock-step: one call = one 10 ms   */
+/* frame of every stream.  Streams never interact; multi-GPU use is one batch per device.        */
+/* ------------------------------------------------------------------------------------------ */
+
+/** Create nb_streams zero-initialised stream states on CUDA device `device` (>= 0).
+ *  NULL on failure (bad model, nb_streams < 1, no such device, out of memory). */
+RNNOISE_EXPORT RNNoiseBatch *rnnoise_batch_create(RNNModel *model, int nb_streams, int device);
+
+RNNOISE_EXPORT void rnnoise_batch_destroy(RNNoiseBatch *b);
+
+RNNOISE_EXPORT int rnnoise_batch_get_streams(const RNNoiseBatch *b);
+
+/** Host-buffer call: in/out are [nb_streams][480] floats in host memory (pinned memory makes the
+ *  copies asynchronous DMA), vad is [nb_streams] (may be NULL).  Copies in, runs the frame, copies
+ *  out, and returns after the results are in `out`/`vad`.  0 on success, -1 on a CUDA error. */
+RNNOISE_EXPORT int rnnoise_process_frame_batch(RNNoiseBatch *b, float *out, const float *in, float *vad);
+
+/** Device-buffer call: d_in/d_out/d_vad are device pointers on the batch's device (d_out may alias
+ *  d_in; d_vad may be NULL).  Enqueues the frame on the batch's stream and returns without
+ *  synchronising.  0 on success, -1 on a launch error. */
+RNNOISE_EXPORT int rnnoise_process_frame_batch_device(RNNoiseBatch *b, float *d_out, const float *d_in, float *d_vad);
+
+/** Block until everything enqueued on the batch's stream has finished.  0 / -1. */
+RNNOISE_EXPORT int rnnoise_batch_sync(RNNoiseBatch *b);
+
+/** Use an existing CUDA stream (a cudaStream_t passed as void*) for all subsequent work of this
+ *  batch, so callers can time with events on their own stream.  NULL restores the private stream. */
+RNNOISE_EXPORT int rnnoise_batch_set_stream(RNNoiseBatch *b, void *cuda_stream);
+
+/** Re-zero the state of one stream (what rnnoise_init() does to a DenoiseState).  0 / -1. */
+RNNOISE_EXPORT int rnnoise_batch_reset_stream(RNNoiseBatch *b, int stream);
+
+/** Number of kernel launches one rnnoise_process_frame_batch_device() call issues. */
+RNNOISE_EXPORT int rnnoise_batch_launches_per_frame(const RNNoiseBatch *b);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Introspection for parity tests (device -> host copies of per-stream intermediates of the last */
+/* processed frame).  Not needed by applications.                                                */
+/* ------------------------------------------------------------------------------------------ */
+enum {
+  RNNOISE_DBG_FEATURES = 0,   /* [65]  features fed to the network (denoise.c:347 output)        */
+  RNNOISE_DBG_X = 1,          /* [962] analysis spectrum X, interleaved re/im                    */
+  RNNOISE_DBG_P = 2,          /* [962] pitch spectrum P                                          */
+  RNNOISE_DBG_EX = 3,         /* [32]  band energies of X                                        */
+  RNNOISE_DBG_EP = 4,         /* [32]                                                            */
+  RNNOISE_DBG_EXP = 5,        /* [32]  normalised band correlation                               */
+  RNNOISE_DBG_GAINS = 6,      /* [32]  raw network gains g (before denoise.c:483)               */
+  RNNOISE_DBG_LASTG = 7,      /* [32]  st->lastg                                                 */
+  RNNOISE_DBG_XB = 8,         /* [480] input after the high-pass biquad                          */
+  RNNOISE_DBG_GRU1 = 9,       /* [gru] GRU states after the frame                               */
+  RNNOISE_DBG_GRU2 = 10,
+  RNNOISE_DBG_GRU3 = 11,
+  RNNOISE_DBG_CONV1_STATE = 12, /* [130] */
+  RNNOISE_DBG_CONV2_STATE = 13, /* [2*cond] */
+  RNNOISE_DBG_PITCH = 14,     /* [2]   {last_period (as float), last_gain}                       */
+  RNNOISE_DBG_SILENCE = 15,   /* [1]   1.0 when the frame was classified silent                  */
+  RNNOISE_DBG_CONV2_OUT = 16  /* [gru] conv2 output of the frame                                */
+};
+/** Copies item `what` of stream `stream` into dst (capacity in floats); returns the number of
+ *  floats written or -1. */
+RNNOISE_EXPORT int rnnoise_batch_debug_read(RNNoiseBatch *b, int what, int stream, float *dst, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,131 @@
+"""rnnoise_b200 -- host-side mirror of the C ABI in include/rnnoise.h (ctypes, no compute in Python).
+
+The product is rnnoise_b200/librnnoise_b200.so (C host code + sm_100a CUDA kernels).  This module
+only loads it and forwards calls with plain pointers, the way the reference's own callers
+(examples/rnnoise_demo.c:40-66) use librnnoise.  It never falls back to a CPU path: importing works
+without a GPU (so the ABI can be inspected), but creating a batch raises if the engine cannot come up.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librnnoise_b200.so")
+FRAME_SIZE = 480
+
+# debug-read selectors (include/rnnoise.h)
+DBG = dict(features=0, X=1, P=2, Ex=3, Ep=4, Exp=5, gains=6, lastg=7, xb=8, gru1=9, gru2=10, gru3=11,
+           conv1_state=12, conv2_state=13, pitch=14, silence=15, conv2_out=16)
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (building is __graft_entry__.build()'s / build.py's job)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing -- run `python rnnoise_b200/build.py` (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        vp, ip, fp = C.c_void_p, C.c_int, C.POINTER(C.c_float)
+        L.rnnoise_get_size.restype = ip
+        L.rnnoise_get_frame_size.restype = ip
+        L.rnnoise_model_from_filename.restype = vp; L.rnnoise_model_from_filename.argtypes = [C.c_char_p]
+        L.rnnoise_model_from_buffer.restype = vp; L.rnnoise_model_from_buffer.argtypes = [vp, ip]
+        L.rnnoise_model_free.argtypes = [vp]
+        L.rnnoise_create.restype = vp; L.rnnoise_create.argtypes = [vp]
+        L.rnnoise_destroy.argtypes = [vp]
+        L.rnnoise_process_frame.restype = C.c_float; L.rnnoise_process_frame.argtypes = [vp, fp, fp]
+        L.rnnoise_batch_create.restype = vp; L.rnnoise_batch_create.argtypes = [vp, ip, ip]
+        L.rnnoise_batch_destroy.argtypes = [vp]
+        L.rnnoise_batch_get_streams.restype = ip; L.rnnoise_batch_get_streams.argtypes = [vp]
+        L.rnnoise_process_frame_batch.restype = ip; L.rnnoise_process_frame_batch.argtypes = [vp, vp, vp, vp]
+        L.rnnoise_process_frame_batch_device.restype = ip; L.rnnoise_process_frame_batch_device.argtypes = [vp, vp, vp, vp]
+        L.rnnoise_batch_sync.restype = ip; L.rnnoise_batch_sync.argtypes = [vp]
+        L.rnnoise_batch_set_stream.restype = ip; L.rnnoise_batch_set_stream.argtypes = [vp, vp]
+        L.rnnoise_batch_reset_stream.restype = ip; L.rnnoise_batch_reset_stream.argtypes = [vp, ip]
+        L.rnnoise_batch_launches_per_frame.restype = ip; L.rnnoise_batch_launches_per_frame.argtypes = [vp]
+        L.rnnoise_batch_debug_read.restype = ip; L.rnnoise_batch_debug_read.argtypes = [vp, ip, ip, fp, ip]
+        _lib = L
+    return _lib
+
+
+class Model:
+    """RNNModel* (rnnoise_model_from_filename / rnnoise_model_from_buffer)."""
+
+    def __init__(self, path=None, buffer=None):
+        L = lib()
+        self._buf = None
+        if path is not None:
+            self.handle = L.rnnoise_model_from_filename(os.fsencode(path))
+        else:
+            self._buf = bytes(buffer)  # must outlive the model (borrowed, like the reference)
+            self.handle = L.rnnoise_model_from_buffer(self._buf, len(self._buf))
+        if not self.handle:
+            raise ValueError("not a valid RNNoise weight blob")
+
+    def free(self):
+        if self.handle:
+            lib().rnnoise_model_free(self.handle)
+            self.handle = None
+
+
+class Batch:
+    """RNNoiseBatch*: nb_streams independent denoiser states resident on one GPU."""
+
+    def __init__(self, model, nb_streams, device=0):
+        self.model = model
+        self.nb_streams = nb_streams
+        self.handle = lib().rnnoise_batch_create(model.handle, nb_streams, device)
+        if not self.handle:
+            raise RuntimeError("rnnoise_batch_create failed (no usable CUDA device, bad model or out of memory)")
+
+    def process(self, pcm, want_vad=True):
+        """pcm: float32 [nb_streams][480] host array -> (out [nb_streams][480], vad [nb_streams])."""
+        x = np.ascontiguousarray(pcm, np.float32)
+        assert x.shape == (self.nb_streams, FRAME_SIZE)
+        out = np.empty_like(x)
+        vad = np.empty(self.nb_streams, np.float32)
+        rc = lib().rnnoise_process_frame_batch(self.handle, out.ctypes.data, x.ctypes.data, vad.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("rnnoise_process_frame_batch failed")
+        return out, vad
+
+    def process_ptr(self, out_ptr, in_ptr, vad_ptr=None):
+        """Host-buffer call on raw addresses (e.g. pinned torch tensors)."""
+        if lib().rnnoise_process_frame_batch(self.handle, out_ptr, in_ptr, vad_ptr) != 0:
+            raise RuntimeError("rnnoise_process_frame_batch failed")
+
+    def process_device(self, d_out, d_in, d_vad=None):
+        """Device pointers (ints); asynchronous on the batch's stream."""
+        if lib().rnnoise_process_frame_batch_device(self.handle, d_out, d_in, d_vad) != 0:
+            raise RuntimeError("rnnoise_process_frame_batch_device failed")
+
+    def set_stream(self, cuda_stream):
+        if lib().rnnoise_batch_set_stream(self.handle, cuda_stream) != 0:
+            raise RuntimeError("rnnoise_batch_set_stream failed")
+
+    def sync(self):
+        if lib().rnnoise_batch_sync(self.handle) != 0:
+            raise RuntimeError("rnnoise_batch_sync failed")
+
+    def reset_stream(self, s):
+        if lib().rnnoise_batch_reset_stream(self.handle, s) != 0:
+            raise RuntimeError("rnnoise_batch_reset_stream failed")
+
+    @property
+    def launches_per_frame(self):
+        return lib().rnnoise_batch_launches_per_frame(self.handle)
+
+    def debug(self, what, stream):
+        buf = np.empty(2048, np.float32)
+        n = lib().rnnoise_batch_debug_read(self.handle, DBG[what], stream, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size)
+        if n < 0:
+            raise RuntimeError("debug_read failed")
+        return buf[:n].copy()
+
+    def destroy(self):
+        if self.handle:
+            lib().rnnoise_batch_destroy(self.handle)
+            self.handle = None

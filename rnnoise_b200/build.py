@@ -1,0 +1,59 @@
+"""Builds rnnoise_b200/librnnoise_b200.so in-tree: host C (gcc) + CUDA for sm_100a (nvcc).
+
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo --fmad=false ...
+--fmad=false is part of the arithmetic contract (DESIGN.md "Numerics"): the reference's DSP code is
+compiled without FMA contraction; every FMA the kernels execute is an explicit fmaf().
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "librnnoise_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def sources():
+    out = []
+    for d in (CSRC, os.path.join(HERE, "..", "include")):
+        for f in sorted(os.listdir(d)):
+            if f.endswith((".c", ".cu", ".cuh", ".h", ".hpp")):
+                out.append(os.path.join(d, f))
+    return out
+
+
+def build(force=False, verbose=False):
+    if not force and not _newer(SO, sources() + [os.path.abspath(__file__)]):
+        return SO
+    obj = os.path.join(HERE, "build")
+    os.makedirs(obj, exist_ok=True)
+    cmds = []
+    cobjs = []
+    for c in ("rnnoise_api.c", "model_blob.c"):
+        o = os.path.join(obj, c + ".o")
+        cmds.append(["gcc", "-O2", "-fPIC", "-Wall", "-fvisibility=hidden", "-DRNNOISE_BUILD", "-c", os.path.join(CSRC, c), "-o", o])
+        cobjs.append(o)
+    eo = os.path.join(obj, "engine.cu.o")
+    cmds.append([NVCC, *ARCH, "-O3", "-lineinfo", "--fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-DRNNOISE_BUILD",
+                 "-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, "engine.cu"), "-o", eo])
+    cmds.append([NVCC, *ARCH, "-shared", "-o", SO, *cobjs, eo, "-cudart", "static"])
+    for cmd in cmds:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError("build of librnnoise_b200.so failed")
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,353 @@
+// dsp_core.cuh -- per-stream DSP stages of rnnoise_process_frame() for the B200 engine.
+//
+// One CTA of DSP_THREADS threads owns one stream for one frame; every stage below is written as
+// a barrier-separated PHASE so that (a) on the GPU the 4 warps cooperate through shared memory and
+// (b) the very same source can be executed thread-by-thread on the host by tests/emu (PHASE loops
+// over tid) to check indexing and arithmetic without a GPU.  It is NOT a CPU fallback: nothing in
+// the library's API reaches the host instantiation.
+//
+// Arithmetic contract: every float operation of the reference's scalar SSE2 DSP code
+// (src/denoise.c, src/pitch.c, src/celt_lpc.c, src/kiss_fft.c) is performed in the same order
+// with the same rounding -- the translation unit is compiled with --fmad=false and no fast-math,
+// so X, P, band energies, pitch period and the 65 features are bit-identical to the reference.
+// Parallelism comes only from operations the reference leaves independent: butterflies of one FFT
+// stage, different lags of a correlation, different bands.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define HD __host__ __device__ __forceinline__
+#else
+#define HD static inline
+#endif
+
+#define DSP_THREADS 128
+#define FRAME_SIZE 480
+#define WINDOW_SIZE 960
+#define FREQ_SIZE 481
+#define NB_BANDS 32
+#define NB_FEATURES 65
+#define PITCH_MIN_PERIOD 60
+#define PITCH_MAX_PERIOD 768
+#define PITCH_FRAME_SIZE 960
+#define PITCH_BUF_SIZE 1728
+#define LP_SIZE 864
+
+// Same operand orientation as the reference's MAX16/MIN16/MAX32 macros (src/arch.h:72-75).
+#define RMAX(a, b) ((a) > (b) ? (a) : (b))
+#define RMIN(a, b) ((a) < (b) ? (a) : (b))
+
+struct cpx { float r, i; };
+
+// Tables, generated on the host from the reference's closed forms (dsp_tables.c) and kept in
+// global memory (lane-divergent indices would serialise in __constant__).
+struct DspTables {
+  float half_window[FRAME_SIZE];   // src/dump_rnnoise_tables.c:85
+  float dct[NB_BANDS * NB_BANDS];  // :92-97
+  cpx tw[WINDOW_SIZE];             // src/kiss_fft.c:406-420
+  short bitrev[WINDOW_SIZE];       // digit reversal for radices 5,3,4,4,4
+  short eband[NB_BANDS + 2];       // src/denoise.c:63-65
+  unsigned char bin_band[400];     // band whose interpolation segment holds bin k (1..31 inner)
+  float bin_frac[400];             // (float)j / band_size for that bin
+  float fft_scale;                 // rnnoise_tables.c:562 literal
+};
+
+// ------------------------------------------------------------------------------------------------
+// Shared-memory plan of one stream (floats).  Pitch scratch and FFT scratch overlay each other.
+// ------------------------------------------------------------------------------------------------
+#define SM_PB 0                          // [1728] linearised pitch history incl. the new frame
+#define SM_U (SM_PB + PITCH_BUF_SIZE)    // union region
+//   pitch phase
+#define SM_LP (SM_U)                     // [864] whitened half-rate signal
+#define SM_LP0 (SM_LP + LP_SIZE)         // [864] decimated signal before whitening (dies after FIR)
+#define SM_X4 (SM_LP0)                   // [240]   (reuses LP0 once the FIR is done)
+#define SM_Y4 (SM_X4 + 240)              // [388]
+#define SM_XC (SM_Y4 + 388)              // [296] coarse / fine correlations
+#define SM_SYY (SM_XC + 296)             // [296] running energies seen by find_best_pitch
+#define SM_YYL (SM_SYY + 296)            // [392] yy_lookup
+#define SM_DOT (SM_YYL + 392)            // [64]  remove_doubling dot products
+#define SM_PITCH_END (SM_DOT + 64)
+//   spectrum phase
+#define SM_F (SM_U)                      // [1920] FFT work buffer (interleaved complex)
+#define SM_XS (SM_F + 2 * WINDOW_SIZE)   // [962] X kept for the X.P correlation
+#define SM_SPEC_END (SM_XS + 2 * FREQ_SIZE)
+#define SM_UNION_END (SM_PITCH_END > SM_SPEC_END ? SM_PITCH_END : SM_SPEC_END)
+#define SM_MISC (SM_UNION_END)           // [288] small per-stream scalars / band vectors
+#define SM_TOTAL (SM_MISC + 288)
+// misc slots (float indices relative to SM_MISC)
+#define MI_AC 0     // [5] autocorrelation
+#define MI_NUM 8    // [5] whitening FIR taps
+#define MI_INT 16   // ints: [0]=best0 [1]=best1 [2]=T (pitch index) [3]=silence [4]=T0 half-rate
+#define MI_BAND 32  // [3][34] band sums (X, P, X.P)
+#define MI_E 136    // [3][32] Ex, Ep, Exp
+#define MI_LY 232   // [32] log band energies
+static_assert(SM_LP0 + LP_SIZE <= SM_UNION_END, "lp0 overlay");
+
+// ------------------------------------------------------------------------------------------------
+// 960-point forward FFT stages (src/kiss_fft.c:101-316; stage order rnn_fft_impl:518-564).
+// ------------------------------------------------------------------------------------------------
+HD cpx cmul(cpx a, cpx b) {
+  cpx m;
+  m.r = a.r * b.r - a.i * b.i;
+  m.i = a.r * b.i + a.i * b.r;
+  return m;
+}
+HD cpx cadd(cpx a, cpx b) { cpx m; m.r = a.r + b.r; m.i = a.i + b.i; return m; }
+HD cpx csub(cpx a, cpx b) { cpx m; m.r = a.r - b.r; m.i = a.i - b.i; return m; }
+
+// Stage 1 (radix 4, m = 1) fused with the bit-reversed, scaled, windowed load: group g gathers
+// its four inputs straight from `src` (kiss_fft.c:577-584 + kf_bfly4 m==1 branch :112-130).
+// Input element i of the transform is win(i) * src[i] (imag 0) when `herm` is null, or the
+// Hermitian extension of herm[0..480] (inverse_transform, denoise.c:200-211).
+HD void fft_stage1(cpx *F, const float *src, const cpx *herm, const DspTables *T, int tid, int nthr) {
+  for (int g = tid; g < 240; g += nthr) {
+    int j0 = g / 48, j1 = (g / 16) % 3, j2 = (g / 4) % 4, j3 = g % 4;
+    int base = j0 + 5 * j1 + 15 * j2 + 60 * j3;
+    cpx a[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      int i = base + 240 * q;
+      cpx v;
+      if (herm) {
+        if (i < FREQ_SIZE) v = herm[i];
+        else { v.r = herm[WINDOW_SIZE - i].r; v.i = -herm[WINDOW_SIZE - i].i; }
+      } else {
+        int wi = i < FRAME_SIZE ? i : WINDOW_SIZE - 1 - i;
+        v.r = src[i] * T->half_window[wi];
+        v.i = 0.f;
+      }
+      a[q].r = T->fft_scale * v.r;
+      a[q].i = T->fft_scale * v.i;
+    }
+    cpx s0 = csub(a[0], a[2]);
+    a[0] = cadd(a[0], a[2]);
+    cpx s1 = cadd(a[1], a[3]);
+    a[2] = csub(a[0], s1);
+    a[0] = cadd(a[0], s1);
+    s1 = csub(a[1], a[3]);
+    a[1].r = s0.r + s1.i; a[1].i = s0.i - s1.r;
+    a[3].r = s0.r - s1.i; a[3].i = s0.i + s1.r;
+    F[4 * g + 0] = a[0]; F[4 * g + 1] = a[1]; F[4 * g + 2] = a[2]; F[4 * g + 3] = a[3];
+  }
+}
+// generic radix-4 stage: `m` butterflies per group, groups `gstride` apart, twiddle stride fs
+HD void fft_radix4(cpx *F0, int m, int gstride, int fs, const DspTables *T, int tid, int nthr) {
+  for (int b = tid; b < 240; b += nthr) {
+    int g = b / m, j = b % m;
+    cpx *F = F0 + g * gstride + j;
+    cpx s0 = cmul(F[m], T->tw[j * fs]);
+    cpx s1 = cmul(F[2 * m], T->tw[2 * j * fs]);
+    cpx s2 = cmul(F[3 * m], T->tw[3 * j * fs]);
+    cpx f0 = F[0];
+    cpx s5 = csub(f0, s1);
+    f0 = cadd(f0, s1);
+    cpx s3 = cadd(s0, s2);
+    cpx s4 = csub(s0, s2);
+    F[2 * m] = csub(f0, s3);
+    F[0] = cadd(f0, s3);
+    cpx o1, o3;
+    o1.r = s5.r + s4.i; o1.i = s5.i - s4.r;
+    o3.r = s5.r - s4.i; o3.i = s5.i + s4.r;
+    F[m] = o1; F[3 * m] = o3;
+  }
+}
+HD void fft_radix3(cpx *F0, const DspTables *T, int tid, int nthr) { // m = 64, 5 groups of 192
+  const int m = 64, fs = 5;
+  const float epi3 = T->tw[fs * m].i;
+  for (int b = tid; b < 320; b += nthr) {
+    int g = b / m, j = b % m;
+    cpx *F = F0 + g * 192 + j;
+    cpx s1 = cmul(F[m], T->tw[j * fs]);
+    cpx s2 = cmul(F[2 * m], T->tw[2 * j * fs]);
+    cpx s3 = cadd(s1, s2);
+    cpx s0 = csub(s1, s2);
+    cpx f0 = F[0], f1;
+    f1.r = f0.r - s3.r * .5f;
+    f1.i = f0.i - s3.i * .5f;
+    s0.r *= epi3; s0.i *= epi3;
+    F[0] = cadd(f0, s3);
+    cpx o2, o1;
+    o2.r = f1.r + s0.i; o2.i = f1.i - s0.r;
+    o1.r = f1.r - s0.i; o1.i = f1.i + s0.r;
+    F[2 * m] = o2; F[m] = o1;
+  }
+}
+HD void fft_radix5(cpx *F, const DspTables *T, int tid, int nthr) { // m = 192, one group
+  const int m = 192;
+  const cpx ya = T->tw[m], yb = T->tw[2 * m];
+  for (int u = tid; u < m; u += nthr) {
+    cpx s0 = F[u];
+    cpx s1 = cmul(F[u + m], T->tw[u]);
+    cpx s2 = cmul(F[u + 2 * m], T->tw[2 * u]);
+    cpx s3 = cmul(F[u + 3 * m], T->tw[3 * u]);
+    cpx s4 = cmul(F[u + 4 * m], T->tw[4 * u]);
+    cpx s7 = cadd(s1, s4), s10 = csub(s1, s4), s8 = cadd(s2, s3), s9 = csub(s2, s3);
+    cpx o0;
+    o0.r = s0.r + (s7.r + s8.r);
+    o0.i = s0.i + (s7.i + s8.i);
+    F[u] = o0;
+    cpx s5, s6, s11, s12;
+    s5.r = s0.r + (s7.r * ya.r + s8.r * yb.r);
+    s5.i = s0.i + (s7.i * ya.r + s8.i * yb.r);
+    s6.r = s10.i * ya.i + s9.i * yb.i;
+    s6.i = -(s10.r * ya.i + s9.r * yb.i);
+    F[u + m] = csub(s5, s6);
+    F[u + 4 * m] = cadd(s5, s6);
+    s11.r = s0.r + (s7.r * yb.r + s8.r * ya.r);
+    s11.i = s0.i + (s7.i * yb.r + s8.i * ya.r);
+    s12.r = s9.i * ya.i - s10.i * yb.i;
+    s12.i = s10.r * yb.i - s9.r * ya.i;
+    F[u + 2 * m] = cadd(s11, s12);
+    F[u + 3 * m] = csub(s11, s12);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Band sums (compute_band_energy / compute_band_corr, src/denoise.c:90-138).  Thread b owns
+// sum[b] (b = 0..33) and adds its terms in the reference's order: first the frac*t terms of band
+// b-1, then the (1-frac)*t terms of band b.  which: 0 -> |A|^2, 1 -> Re(A conj B).
+// ------------------------------------------------------------------------------------------------
+HD float band_sum_one(int b, const cpx *A, const cpx *B, const DspTables *T) {
+  float sum = 0.f;
+  if (b >= 1) {
+    int e0 = T->eband[b - 1], bs = T->eband[b] - e0;
+    for (int j = 0; j < bs; j++) {
+      float frac = (float)j / bs;
+      cpx a = A[e0 + j], c = B[e0 + j];
+      float t = a.r * c.r;
+      t += a.i * c.i;
+      sum += frac * t;
+    }
+  }
+  if (b <= NB_BANDS) {
+    int e0 = T->eband[b], bs = T->eband[b + 1] - e0;
+    for (int j = 0; j < bs; j++) {
+      float frac = (float)j / bs;
+      cpx a = A[e0 + j], c = B[e0 + j];
+      float t = a.r * c.r;
+      t += a.i * c.i;
+      sum += (1 - frac) * t;
+    }
+  }
+  return sum;
+}
+// sum[34] -> E[32] with the edge-band fix-up (denoise.c:107-112)
+HD float band_finish(const float *sum, int b) {
+  if (b == 0) return (sum[0] + sum[1]) * 2 / 3;
+  if (b == NB_BANDS - 1) return (sum[NB_BANDS] + sum[NB_BANDS + 1]) * 2 / 3;
+  return sum[b + 1];
+}
+
+// interp_band_gain (denoise.c:140-154) evaluated per bin; bins >= 400 are 0 (callers zero-init).
+HD float interp_bin(const float *band, int k, const DspTables *T) {
+  if (k >= 400) return 0.f;
+  if (k < 2) return band[0];
+  if (k >= 356) return band[NB_BANDS - 1];
+  int b = T->bin_band[k];
+  float frac = T->bin_frac[k];
+  return (1 - frac) * band[b - 1] + frac * band[b];
+}
+
+// dct (denoise.c:160-170): output i, sequential over j
+HD float dct_one(const float *in, int i, const DspTables *T) {
+  float sum = 0.f;
+  for (int j = 0; j < NB_BANDS; j++) sum += in[j] * T->dct[j * NB_BANDS + i];
+  return (float)(sum * sqrt(2. / 22));
+}
+
+// one biquad step (rnn_biquad, denoise.c:409-419; b = {-2, 1}, a = {-1.99599, 0.996} :469-470)
+HD float biquad_step(float xi, float &m0, float &m1) {
+  const float b0 = -2.f, b1 = 1.f, a0 = -1.99599f, a1 = 0.99600f;
+  float yi = xi + m0;
+  m0 = (float)((double)m1 + ((double)b0 * (double)xi - (double)a0 * (double)yi));
+  m1 = (float)((double)b1 * (double)xi - (double)a1 * (double)yi);
+  return yi;
+}
+
+// compute_pitch_gain (src/pitch.c:416-419)
+HD float pitch_gain(float xy, float xx, float yy) { return (float)(xy / sqrt((double)(1 + xx * yy))); }
+
+// find_best_pitch's selection scan (src/pitch.c:61-101) over precomputed running energies syy[i]
+// (= the value of Syy when lag i is examined).
+HD void best_two_scan(const float *xcorr, const float *syy, int max_pitch, int *best) {
+  float bnum0 = -1, bnum1 = -1, bden0 = 0, bden1 = 0;
+  int b0 = 0, b1 = 1;
+  for (int i = 0; i < max_pitch; i++) {
+    if (xcorr[i] > 0) {
+      float x16 = xcorr[i];
+      x16 *= 1e-12f;
+      float num = x16 * x16;
+      float Syy = syy[i];
+      if (num * bden1 > bnum1 * Syy) {
+        if (num * bden0 > bnum0 * Syy) {
+          bnum1 = bnum0; bden1 = bden0; b1 = b0;
+          bnum0 = num; bden0 = Syy; b0 = i;
+        } else {
+          bnum1 = num; bden1 = Syy; b1 = i;
+        }
+      }
+    }
+  }
+  best[0] = b0; best[1] = b1;
+}
+// running energy chain of find_best_pitch: syy[0] = 1 + sum_{j<len} y[j]^2 (sequential),
+// syy[i+1] = max(1, syy[i] + (y[i+len]^2 - y[i]^2))   (pitch.c:67-68, 99-100)
+HD void syy_chain(float *syy, const float *y, int len, int max_pitch) {
+  float S = 1;
+  for (int j = 0; j < len; j++) S = S + y[j] * y[j];
+  for (int i = 0; i < max_pitch; i++) {
+    syy[i] = S;
+    S += y[i + len] * y[i + len] - y[i] * y[i];
+    S = RMAX(1, S);
+  }
+}
+
+// Order-4 whitening filter design (src/pitch.c:181-212, src/celt_lpc.c:38-89): ac[5] -> taps[5]
+HD void lpc_taps(const float *ac_in, float *num) {
+  float ac[5];
+  for (int k = 0; k < 5; k++) ac[k] = ac_in[k];
+  ac[0] *= 1.0001f;
+  for (int i = 1; i <= 4; i++) ac[i] -= ac[i] * (.008f * i) * (.008f * i);
+  float lpc[4] = {0, 0, 0, 0};
+  float error = ac[0];
+  if (ac[0] != 0) {
+    for (int i = 0; i < 4; i++) {
+      float rr = 0;
+      for (int j = 0; j < i; j++) rr += lpc[j] * ac[i - j];
+      rr += ac[i + 1];
+      float r = -rr / error;
+      lpc[i] = r;
+      for (int j = 0; j < (i + 1) >> 1; j++) {
+        float t1 = lpc[j], t2 = lpc[i - 1 - j];
+        lpc[j] = t1 + r * t2;
+        lpc[i - 1 - j] = t2 + r * t1;
+      }
+      error = error - (r * r) * error;
+      if (error < .001f * ac[0]) break;
+    }
+  }
+  float tmp = 1.f;
+  for (int i = 0; i < 4; i++) {
+    tmp = .9f * tmp;
+    lpc[i] = lpc[i] * tmp;
+  }
+  const float c1 = .8f;
+  num[0] = lpc[0] + .8f;
+  num[1] = lpc[1] + c1 * lpc[0];
+  num[2] = lpc[2] + c1 * lpc[1];
+  num[3] = lpc[3] + c1 * lpc[2];
+  num[4] = c1 * lpc[3];
+}
+
+// Candidate geometry of rnn_remove_doubling (src/pitch.c:462-481), half-rate domain.
+// k = 1 stands for the initial candidate T0 itself.
+HD void rd_candidate(int k, int T0, int *T1, int *T1b) {
+  const int maxperiod = PITCH_MAX_PERIOD / 2;
+  const int second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};
+  if (k == 1) { *T1 = T0; *T1b = T0; return; }
+  int t1 = (2 * T0 + k) / (2 * k);
+  *T1 = t1;
+  if (k == 2) *T1b = (t1 + T0 > maxperiod) ? T0 : T0 + t1;
+  else *T1b = (2 * second_check[k] * T0 + k) / (2 * k);
+}

@@ -1,0 +1,409 @@
+// dsp_stream.cuh -- the two per-stream DSP bodies (analysis before the network, synthesis after).
+// See dsp_core.cuh for the execution model (PHASE = barrier-separated step of a 128-thread CTA,
+// or a loop over tid in the host emulation used by tests/emu).
+#pragma once
+#include "dsp_core.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define PHASE_BEGIN { const int tid = threadIdx.x; const int nthr = DSP_THREADS; (void)nthr;
+#define PHASE_END } __syncthreads();
+#else
+#define PHASE_BEGIN for (int tid = 0; tid < DSP_THREADS; ++tid) { const int nthr = DSP_THREADS; (void)nthr;
+#define PHASE_END }
+#endif
+
+struct AnalysisArgs {
+  const float *xb;      // [480]  this stream's frame after the high-pass biquad
+  float *ring;          // [1728] pitch-history ring of this stream
+  int ring_base;        // physical index of logical sample 0 AFTER this frame's 480-sample shift
+  float *spec_out;      // [2][962] X then P of this frame (becomes "delayed" next frame)
+  float *band_out;      // [3][32]  Ex, Ep, Exp
+  float *features;      // [65]
+  int *silence;         // [1]
+  float *pitch_state;   // [2] {last_period as int bits, last_gain}
+};
+
+// rnn_compute_frame_features (src/denoise.c:347-398) incl. rnn_frame_analysis (:332-345),
+// rnn_pitch_downsample / rnn_pitch_search / rnn_remove_doubling (src/pitch.c:146,281,423).
+HD void analysis_stream(float *sm, const AnalysisArgs a, const DspTables *T) {
+  float *pb = sm + SM_PB, *lp = sm + SM_LP, *lp0 = sm + SM_LP0, *x4 = sm + SM_X4, *y4 = sm + SM_Y4;
+  float *xc = sm + SM_XC, *syy = sm + SM_SYY, *yyl = sm + SM_YYL, *dot = sm + SM_DOT;
+  float *misc = sm + SM_MISC;
+  int *mi = (int *)(misc + MI_INT);
+  cpx *F = (cpx *)(sm + SM_F), *XS = (cpx *)(sm + SM_XS);
+
+  // -- load the shifted history, append the new frame (denoise.c:359-360; ring instead of memmove)
+  PHASE_BEGIN
+    for (int i = tid; i < PITCH_BUF_SIZE - FRAME_SIZE; i += nthr) {
+      int p = a.ring_base + i; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
+      pb[i] = a.ring[p];
+    }
+    for (int j = tid; j < FRAME_SIZE; j += nthr) {
+      float v = a.xb[j];
+      int p = a.ring_base + PITCH_BUF_SIZE - FRAME_SIZE + j; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
+      pb[PITCH_BUF_SIZE - FRAME_SIZE + j] = v;
+      a.ring[p] = v;
+    }
+  PHASE_END
+  // -- 2x decimation (pitch.c:171-173)
+  PHASE_BEGIN
+    for (int i = tid; i < LP_SIZE; i += nthr)
+      lp0[i] = i ? .5f * (.5f * (pb[2 * i - 1] + pb[2 * i + 1]) + pb[2 * i]) : .5f * (.5f * pb[1] + pb[0]);
+  PHASE_END
+  // -- autocorrelation lags 0..4 (celt_lpc.c:92-174: first n-4 samples, then the tail)
+  PHASE_BEGIN
+    if (tid < 5) {
+      const int k = tid, fastN = LP_SIZE - 4;
+      float s = 0.f;
+      for (int j = 0; j < fastN; j++) s = s + lp0[j] * lp0[j + k];
+      float d = 0.f;
+      for (int i = k + fastN; i < LP_SIZE; i++) d = d + lp0[i] * lp0[i - k];
+      misc[MI_AC + k] = s + d;
+    }
+  PHASE_END
+  PHASE_BEGIN
+    if (tid == 0) lpc_taps(misc + MI_AC, misc + MI_NUM);
+  PHASE_END
+  // -- 5-tap whitening FIR with zero history (celt_fir5, pitch.c:104-143)
+  PHASE_BEGIN
+    for (int i = tid; i < LP_SIZE; i += nthr) {
+      float sum = lp0[i];
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        float m = (i - 1 - k >= 0) ? lp0[i - 1 - k] : 0.f;
+        sum = sum + misc[MI_NUM + k] * m;
+      }
+      lp[i] = sum;
+    }
+  PHASE_END
+  // -- second 2x decimation (pitch.c:305-308)
+  PHASE_BEGIN
+    for (int j = tid; j < 240; j += nthr) x4[j] = lp[384 + 2 * j];
+    for (int j = tid; j < 388; j += nthr) y4[j] = j < 387 ? lp[2 * j] : 0.f;
+  PHASE_END
+  // -- coarse search: 147 lags x 240 (rnn_pitch_xcorr pitch.c:216; each lag summed in order);
+  //    one other lane runs find_best_pitch's running-energy chain concurrently.
+  PHASE_BEGIN
+    if (tid < 30) {
+      const int l0 = 5 * tid;
+      float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < 240; j++) {
+        float xv = x4[j];
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+          int idx = l0 + q + j;
+          float yv = idx < 388 ? y4[idx] : 0.f;
+          acc[q] = acc[q] + xv * yv;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 5; q++) if (l0 + q < 147) xc[l0 + q] = acc[q];
+    } else if (tid == 32) {
+      syy_chain(syy, y4, 240, 147);
+    }
+  PHASE_END
+  PHASE_BEGIN
+    if (tid == 0) best_two_scan(xc, syy, 147, mi);
+  PHASE_END
+  PHASE_BEGIN
+    for (int i = tid; i < 294; i += nthr) xc[i] = 0.f;
+  PHASE_END
+  // -- fine search around the two coarse winners (pitch.c:344-361) + its energy chain
+  PHASE_BEGIN
+    if (tid < 10) {
+      const int c0 = 2 * mi[0], c1 = 2 * mi[1];
+      int i = tid < 5 ? c0 - 2 + tid : c1 - 2 + (tid - 5);
+      bool ok = i >= 0 && i < 294;
+      if (tid >= 5) { int d = i - c0; if (d < 0) d = -d; if (d <= 2) ok = false; }
+      if (ok) {
+        const float *xl = lp + 384, *y = lp + i;
+        float sum = 0.f;
+        for (int j = 0; j < 480; j++) sum = sum + xl[j] * y[j];
+        xc[i] = RMAX(-1, sum);
+      }
+    } else if (tid == 32) {
+      syy_chain(syy, lp, 480, 294);
+    }
+  PHASE_END
+  // -- pick the winner, pseudo-interpolate (pitch.c:362-384), enter the half-rate domain
+  PHASE_BEGIN
+    if (tid == 0) {
+      int best[2];
+      best_two_scan(xc, syy, 294, best);
+      int offset = 0;
+      if (best[0] > 0 && best[0] < 293) {
+        float aa = xc[best[0] - 1], bb = xc[best[0]], cc = xc[best[0] + 1];
+        if ((cc - aa) > .7f * (bb - aa)) offset = 1;
+        else if ((aa - cc) > .7f * (bb - cc)) offset = -1;
+      }
+      int pitch_index = PITCH_MAX_PERIOD - (2 * best[0] - offset);   // denoise.c:365
+      int T0 = pitch_index / 2;                                       // pitch.c:441
+      if (T0 >= PITCH_MAX_PERIOD / 2) T0 = PITCH_MAX_PERIOD / 2 - 1;  // :445-446
+      mi[4] = T0;
+    }
+  PHASE_END
+  // -- all dot products rnn_remove_doubling can need, in parallel lanes (each one sequential):
+  //    warp 0: xx, xy(T0), and xy(T1), xy(T1b) for k = 2..15      (pitch.c:449, 482)
+  //    warp 1: speculative refinement lags T-1, T+1 of every candidate (pitch.c:513-514)
+  //    warp 2: the yy_lookup energy chain                           (pitch.c:450-456)
+  PHASE_BEGIN
+    const float *x = lp + PITCH_MAX_PERIOD / 2;
+    const int N = PITCH_FRAME_SIZE / 2, T0 = mi[4];
+    if (tid < 30) {
+      int off, ok = 1;
+      if (tid == 0) off = 0;
+      else if (tid == 1) off = T0;
+      else {
+        int k = 2 + (tid - 2) / 2, T1, T1b;
+        rd_candidate(k, T0, &T1, &T1b);
+        ok = T1 >= PITCH_MIN_PERIOD / 2;
+        off = ((tid - 2) & 1) ? T1b : T1;
+      }
+      if (ok) {
+        float s = 0.f;
+        for (int i = 0; i < N; i++) s = s + x[i] * x[i - off];
+        dot[tid] = s;
+      }
+    } else if (tid >= 32 && tid < 62) {
+      int c = (tid - 32) / 2, k = c + 1, T1, T1b;
+      rd_candidate(k, T0, &T1, &T1b);
+      if (k == 1 || T1 >= PITCH_MIN_PERIOD / 2) {
+        int off = ((tid - 32) & 1) ? T1 + 1 : T1 - 1;
+        float s = 0.f;
+        for (int i = 0; i < N; i++) s = s + x[i] * x[i - off];
+        dot[tid] = s;
+      }
+    } else if (tid == 64) {
+      float yy = 0.f;
+      for (int i = 0; i < N; i++) yy = yy + x[i] * x[i];   // == xx, summed in the same order
+      yyl[0] = yy;
+      for (int i = 1; i <= PITCH_MAX_PERIOD / 2; i++) {
+        yy = yy + x[-i] * x[-i] - x[N - i] * x[N - i];
+        yyl[i] = RMAX(0, yy);
+      }
+    }
+  PHASE_END
+  // -- decision logic of rnn_remove_doubling (pitch.c:457-527) + state update (denoise.c:369-370)
+  PHASE_BEGIN
+    if (tid == 0) {
+      const int T0 = mi[4], minperiod = PITCH_MIN_PERIOD / 2;
+      int prev_period = ((const int *)a.pitch_state)[0] / 2;
+      const float prev_gain = a.pitch_state[1];
+      const float xx = dot[0];
+      float xy = dot[1];
+      float yy = yyl[T0];
+      float best_xy = xy, best_yy = yy;
+      const float g0 = pitch_gain(xy, xx, yy);
+      float g = g0;
+      int T = T0, kbest = 1;
+      for (int k = 2; k <= 15; k++) {
+        int T1, T1b;
+        rd_candidate(k, T0, &T1, &T1b);
+        if (T1 < minperiod) break;
+        xy = .5f * (dot[2 + 2 * (k - 2)] + dot[3 + 2 * (k - 2)]);
+        yy = .5f * (yyl[T1] + yyl[T1b]);
+        float g1 = pitch_gain(xy, xx, yy);
+        int d = T1 - prev_period; if (d < 0) d = -d;
+        float cont;
+        if (d <= 1) cont = prev_gain;
+        else if (d <= 2 && 5 * k * k < T0) cont = .5f * prev_gain;
+        else cont = 0;
+        float thresh = RMAX(.3f, .7f * g0 - cont);
+        if (T1 < 3 * minperiod) thresh = RMAX(.4f, .85f * g0 - cont);
+        else if (T1 < 2 * minperiod) thresh = RMAX(.5f, .9f * g0 - cont);
+        if (g1 > thresh) { best_xy = xy; best_yy = yy; T = T1; g = g1; kbest = k; }
+      }
+      best_xy = RMAX(0, best_xy);
+      float pg;
+      if (best_yy <= best_xy) pg = 1.f;
+      else pg = best_xy / (best_yy + 1);
+      // xcorr[k] = <x, x-(T+k-1)>, k = 0..2; the centre lag was summed above in the same order
+      float xc0 = dot[32 + 2 * (kbest - 1)], xc2 = dot[33 + 2 * (kbest - 1)];
+      float xc1 = kbest == 1 ? dot[1] : dot[2 + 2 * (kbest - 2)];
+      int offset;
+      if ((xc2 - xc0) > .7f * (xc1 - xc0)) offset = 1;
+      else if ((xc0 - xc2) > .7f * (xc1 - xc2)) offset = -1;
+      else offset = 0;
+      if (pg > g) pg = g;
+      int Tout = 2 * T + offset;
+      if (Tout < PITCH_MIN_PERIOD) Tout = PITCH_MIN_PERIOD;
+      mi[2] = Tout;
+      ((int *)a.pitch_state)[0] = Tout;
+      a.pitch_state[1] = pg;
+    }
+  PHASE_END
+  // -- X = FFT(window * [previous frame | this frame]) (denoise.c:332-339); the analysis window
+  //    is the last 960 samples of the updated pitch history.
+  PHASE_BEGIN fft_stage1(F, pb + PITCH_BUF_SIZE - WINDOW_SIZE, nullptr, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix5(F, T, tid, nthr); PHASE_END
+  PHASE_BEGIN
+    for (int i = tid; i < FREQ_SIZE; i += nthr) {
+      cpx v = F[i];
+      XS[i] = v;
+      ((cpx *)a.spec_out)[i] = v;
+    }
+    if (tid < NB_BANDS + 2) misc[MI_BAND + tid] = band_sum_one(tid, F, F, T);
+  PHASE_END
+  // -- P = FFT(window * pitch_buf[768-T .. 768-T+960)) (denoise.c:371-374)
+  PHASE_BEGIN fft_stage1(F, pb + PITCH_BUF_SIZE - WINDOW_SIZE - mi[2], nullptr, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix5(F, T, tid, nthr); PHASE_END
+  PHASE_BEGIN
+    for (int i = tid; i < FREQ_SIZE; i += nthr) ((cpx *)a.spec_out)[FREQ_SIZE + i] = F[i];
+    if (tid < NB_BANDS + 2) misc[MI_BAND + 34 + tid] = band_sum_one(tid, F, F, T);
+    else if (tid >= 64 && tid < 64 + NB_BANDS + 2) misc[MI_BAND + 68 + tid - 64] = band_sum_one(tid - 64, XS, F, T);
+  PHASE_END
+  // -- Ex, Ep, Exp (denoise.c:344,375-377)
+  PHASE_BEGIN
+    if (tid < NB_BANDS) {
+      float ex = band_finish(misc + MI_BAND, tid);
+      float ep = band_finish(misc + MI_BAND + 34, tid);
+      float exp_ = band_finish(misc + MI_BAND + 68, tid);
+      exp_ = (float)(exp_ / sqrt(.001 + ex * ep));
+      misc[MI_E + tid] = ex; misc[MI_E + 32 + tid] = ep; misc[MI_E + 64 + tid] = exp_;
+      a.band_out[tid] = ex; a.band_out[32 + tid] = ep; a.band_out[64 + tid] = exp_;
+    }
+  PHASE_END
+  // -- log-energy floor follower + silence test (denoise.c:380-393)
+  PHASE_BEGIN
+    if (tid == 0) {
+      float logMax = -2, follow = -2, E = 0;
+      for (int i = 0; i < NB_BANDS; i++) {
+        float ex = misc[MI_E + i];
+        float ly = (float)log10(1e-2 + ex);
+        double f15 = follow - 1.5;
+        double m1 = RMAX(f15, ly);
+        float lm7 = logMax - 7;
+        ly = (float)RMAX(lm7, m1);
+        logMax = RMAX(logMax, ly);
+        follow = (float)RMAX(f15, ly);
+        misc[MI_LY + i] = ly;
+        E += ex;
+      }
+      int silent = E < 0.04;
+      mi[3] = silent;
+      a.silence[0] = silent;
+    }
+  PHASE_END
+  // -- features (denoise.c:378-379, 391, 394-396)
+  PHASE_BEGIN
+    const int silent = mi[3];
+    if (tid < NB_BANDS) {
+      float v = dct_one(misc + MI_LY, tid, T);
+      if (tid == 0) v -= 12;
+      if (tid == 1) v -= 4;
+      a.features[tid] = silent ? 0.f : v;
+    } else if (tid < 2 * NB_BANDS) {
+      float v = dct_one(misc + MI_E + 64, tid - NB_BANDS, T);
+      a.features[tid] = silent ? 0.f : v;
+    } else if (tid == 2 * NB_BANDS) {
+      a.features[tid] = silent ? 0.f : (float)(.01 * (mi[2] - 300));
+    }
+  PHASE_END
+}
+
+struct SynthesisArgs {
+  float *spec_delayed;      // [2][962] X and P of the PREVIOUS frame (modified in place, then dead)
+  const float *band_delayed;// [3][32]  Ex, Ep, Exp of the previous frame
+  const float *band_cur;    // [3][32]  Ex of this frame is [0..32)
+  const float *gains;       // [32] network output of this frame
+  const int *silence;       // [1]
+  float *lastg;             // [32]
+  float *synthesis_mem;     // [480]
+  float *out;               // [480]
+};
+
+// shared-memory plan of the synthesis CTA (floats)
+#define SS_X 0                        // [962] delayed X
+#define SS_P (SS_X + 2 * FREQ_SIZE)   // [962] delayed P
+#define SS_F (SS_P + 2 * FREQ_SIZE)   // [1920] FFT buffer
+#define SS_V (SS_F + 2 * WINDOW_SIZE) // [6][34] band vectors: r, norm, g, sums...
+#define SS_TOTAL (SS_V + 6 * 34)
+
+// rnn_pitch_filter (denoise.c:421-455), gain smoothing + interpolation (:479-493),
+// frame_synthesis (:400-407) with inverse_transform (:200-217).
+HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
+  cpx *X = (cpx *)(sm + SS_X), *P = (cpx *)(sm + SS_P), *F = (cpx *)(sm + SS_F);
+  float *r = sm + SS_V, *sums = sm + SS_V + 34, *norm = sm + SS_V + 68, *g = sm + SS_V + 102;
+  const int silent = a.silence[0];
+  PHASE_BEGIN
+    for (int i = tid; i < FREQ_SIZE; i += nthr) {
+      X[i] = ((const cpx *)a.spec_delayed)[i];
+      P[i] = ((const cpx *)a.spec_delayed)[FREQ_SIZE + i];
+    }
+    if (!silent && tid < NB_BANDS) {
+      const float Ex = a.band_delayed[tid], Ep = a.band_delayed[32 + tid], Exp = a.band_delayed[64 + tid];
+      const float gg = a.gains[tid];
+      float rr;
+      if (Exp > gg) rr = 1;
+      else {
+        float e2 = Exp * Exp, g2 = gg * gg;
+        rr = (float)((e2 * (1 - g2)) / (.001 + g2 * (1 - e2)));
+      }
+      float c = RMAX(0, rr);
+      c = RMIN(1, c);
+      rr = (float)sqrt((double)c);
+      rr = (float)(rr * sqrt(Ex / (1e-8 + Ep)));
+      r[tid] = rr;
+    }
+  PHASE_END
+  if (!silent) {
+    PHASE_BEGIN
+      for (int i = tid; i < FREQ_SIZE; i += nthr) {
+        float rf = interp_bin(r, i, T);
+        cpx x = X[i], p = P[i];
+        x.r += rf * p.r;
+        x.i += rf * p.i;
+        X[i] = x;
+      }
+    PHASE_END
+    PHASE_BEGIN
+      if (tid < NB_BANDS + 2) sums[tid] = band_sum_one(tid, X, X, T);
+    PHASE_END
+    PHASE_BEGIN
+      if (tid < NB_BANDS) {
+        float newE = band_finish(sums, tid);
+        norm[tid] = (float)sqrt(a.band_delayed[tid] / (1e-8 + newE));
+        // gain smoothing (denoise.c:479-487)
+        float gg = a.gains[tid];
+        float lg = a.lastg[tid];
+        float al = .6f * lg;
+        gg = RMAX(gg, al);
+        double t = gg * (a.band_delayed[tid] + 1e-3) / (a.band_cur[tid] + 1e-3);
+        a.lastg[tid] = (float)RMIN(1.f, t);
+        g[tid] = gg;
+      }
+    PHASE_END
+    PHASE_BEGIN
+      for (int i = tid; i < FREQ_SIZE; i += nthr) {
+        float nf = interp_bin(norm, i, T);
+        float gf = interp_bin(g, i, T);
+        cpx x = X[i];
+        x.r *= nf; x.i *= nf;
+        x.r *= gf; x.i *= gf;
+        X[i] = x;
+      }
+    PHASE_END
+  }
+  PHASE_BEGIN fft_stage1(F, nullptr, X, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix5(F, T, tid, nthr); PHASE_END
+  PHASE_BEGIN
+    for (int i = tid; i < FRAME_SIZE; i += nthr) {
+      // t[i] = 960 * y[(960 - i) % 960].re, windowed; out = first half + overlap memory
+      float t0 = WINDOW_SIZE * F[i ? WINDOW_SIZE - i : 0].r;
+      float t1 = WINDOW_SIZE * F[WINDOW_SIZE - (FRAME_SIZE + i)].r;   // index 480+i -> y[480-i]
+      t0 *= T->half_window[i];
+      t1 *= T->half_window[FRAME_SIZE - 1 - i];
+      a.out[i] = t0 + a.synthesis_mem[i];
+      a.synthesis_mem[i] = t1;
+    }
+  PHASE_END
+}

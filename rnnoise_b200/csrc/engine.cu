@@ -1,0 +1,355 @@
+// engine.cu -- device arena, model upload and the per-frame kernel sequence of the B200 engine.
+//
+// One frame of every stream =
+//   k_biquad (thread/stream)  -> k_analysis (CTA/stream) -> k_conv1 -> k_conv2 -> k_gru x3 -> k_heads
+//   -> k_synthesis (CTA/stream)
+// all on one CUDA stream; state lives in HBM between frames (layout: DESIGN.md "Data layout").
+// A device-side frame counter selects the ping-pong halves and the pitch-ring base, so the launch
+// arguments never change from frame to frame (CUDA-graph friendly).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/rnnoise.h"
+#include "dsp_stream.cuh"
+#include "dsp_tables.hpp"
+#include "engine.h"
+#include "rnn_kernels.cuh"
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      fprintf(stderr, "[rnnoise_b200] %s failed: %s (%s:%d)\n", #call, cudaGetErrorString(e_), \
+              __FILE__, __LINE__);                                                        \
+      return -1;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Per-stream state in HBM (all [S][len], stream-major so one CTA reads its stream contiguously)
+// ------------------------------------------------------------------------------------------------
+struct Arena {
+  int S, cond, gru;
+  int *ctr;            // frames started so far (incremented by k_biquad)
+  // DSP state
+  float *ring;         // [S][1728] pitch history ring (analysis_mem is its newest 480 samples)
+  float *synth_mem;    // [S][480]
+  float *hp_mem;       // [S][2]
+  float *spec;         // [2][S][2][962] ping-pong: X and P of the current / previous frame
+  float *band;         // [2][S][96]     ping-pong: Ex, Ep, Exp
+  float *lastg;        // [S][32]
+  float *pitch_state;  // [S][2] {last_period (int bits), last_gain}
+  // network state
+  float *conv1_state;  // [S][130]
+  float *conv2_state;  // [S][2*cond]
+  float *hbuf;         // [2][3][S][gru] ping-pong GRU states
+  // per-frame scratch
+  float *xb;           // [S][480]
+  float *features;     // [S][65]
+  int *silence;        // [S]
+  float *conv1_out;    // [S][cond]
+  float *conv2_out;    // [S][gru]
+  float *gains;        // [S][32]
+  float *vad;          // [S]
+};
+
+// ------------------------------------------------------------------------------------------------
+// DSP kernels
+// ------------------------------------------------------------------------------------------------
+
+// High-pass biquad (rnn_biquad, denoise.c:409-419): strictly serial per stream (each step rounds
+// the state to float), so one THREAD owns one stream; a warp transposes 32x32 tiles through shared
+// memory so that global traffic stays coalesced.  grid = ceil(S/32), block = 32.
+__global__ void __launch_bounds__(32) k_biquad(Arena a, const float *__restrict__ in) {
+  __shared__ float tile[32][33];
+  const int lane = threadIdx.x, s0 = blockIdx.x * 32, s = s0 + lane;
+  if (blockIdx.x == 0 && lane == 0) a.ctr[0] += 1;   // nobody reads ctr inside this kernel
+  float m0 = 0.f, m1 = 0.f;
+  if (s < a.S) { m0 = a.hp_mem[2 * s]; m1 = a.hp_mem[2 * s + 1]; }
+  const int rows = min(32, a.S - s0);
+  for (int c = 0; c < FRAME_SIZE / 32; c++) {
+    for (int r = 0; r < rows; r++) tile[r][lane] = in[(size_t)(s0 + r) * FRAME_SIZE + c * 32 + lane];
+    __syncwarp();
+    if (s < a.S) {
+#pragma unroll 4
+      for (int t = 0; t < 32; t++) tile[lane][t] = biquad_step(tile[lane][t], m0, m1);
+    }
+    __syncwarp();
+    for (int r = 0; r < rows; r++) a.xb[(size_t)(s0 + r) * FRAME_SIZE + c * 32 + lane] = tile[r][lane];
+    __syncwarp();
+  }
+  if (s < a.S) { a.hp_mem[2 * s] = m0; a.hp_mem[2 * s + 1] = m1; }
+}
+
+__global__ void __launch_bounds__(DSP_THREADS) k_analysis(Arena a, const DspTables *__restrict__ T) {
+  extern __shared__ float sm[];
+  const int s = blockIdx.x;
+  const int f = a.ctr[0] - 1, par = f & 1;
+  AnalysisArgs g;
+  g.xb = a.xb + (size_t)s * FRAME_SIZE;
+  g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
+  g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+  g.spec_out = a.spec + ((size_t)par * a.S + s) * (4 * FREQ_SIZE);
+  g.band_out = a.band + ((size_t)par * a.S + s) * 96;
+  g.features = a.features + (size_t)s * NB_FEATURES;
+  g.silence = a.silence + s;
+  g.pitch_state = a.pitch_state + 2 * (size_t)s;
+  analysis_stream(sm, g, T);
+}
+
+__global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTables *__restrict__ T,
+                                                           float *__restrict__ out) {
+  extern __shared__ float sm[];
+  const int s = blockIdx.x;
+  const int f = a.ctr[0] - 1, par = f & 1;
+  SynthesisArgs g;
+  g.spec_delayed = a.spec + ((size_t)(par ^ 1) * a.S + s) * (4 * FREQ_SIZE);
+  g.band_delayed = a.band + ((size_t)(par ^ 1) * a.S + s) * 96;
+  g.band_cur = a.band + ((size_t)par * a.S + s) * 96;
+  g.gains = a.gains + (size_t)s * NB_BANDS;
+  g.silence = a.silence + s;
+  g.lastg = a.lastg + (size_t)s * NB_BANDS;
+  g.synthesis_mem = a.synth_mem + (size_t)s * FRAME_SIZE;
+  g.out = out + (size_t)s * FRAME_SIZE;
+  synthesis_stream(sm, g, T);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct B200Engine {
+  int device;
+  Arena a;
+  DevModel dm;
+  DspTables *d_tables;
+  cudaStream_t own_stream, stream;
+  long long frames;                 // host mirror of the device frame counter
+  std::vector<void *> allocs;
+  float *stage_in, *stage_out, *stage_vad;   // device staging for the host-buffer call
+};
+
+template <typename T>
+static T *dalloc(B200Engine *e, size_t n, bool zero = true) {
+  void *p = nullptr;
+  if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+  if (zero && cudaMemset(p, 0, n * sizeof(T)) != cudaSuccess) return nullptr;
+  e->allocs.push_back(p);
+  return (T *)p;
+}
+template <typename T>
+static const T *upload(B200Engine *e, const T *h, size_t n) {
+  T *d = dalloc<T>(e, n, false);
+  if (!d) return nullptr;
+  if (cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  return d;
+}
+
+// dense s8 [out][in] -> packed [in/4][out] int32 (4 consecutive inputs of one output per word)
+static const int *upload_packed(B200Engine *e, const B200Layer *l) {
+  const int K4 = l->nb_in / 4, N = l->nb_out;
+  std::vector<int> p((size_t)K4 * N);
+  for (int k4 = 0; k4 < K4; k4++)
+    for (int o = 0; o < N; o++) {
+      const signed char *w = l->w8 + (size_t)o * l->nb_in + 4 * k4;
+      unsigned v = (unsigned)(unsigned char)w[0] | ((unsigned)(unsigned char)w[1] << 8) |
+                   ((unsigned)(unsigned char)w[2] << 16) | ((unsigned)(unsigned char)w[3] << 24);
+      p[(size_t)k4 * N + o] = (int)v;
+    }
+  return upload<int>(e, p.data(), p.size());
+}
+static int upload_q(B200Engine *e, DevLayerQ *d, const B200Layer *l) {
+  d->wp = upload_packed(e, l);
+  d->scale = upload<float>(e, l->scale, l->nb_out);
+  d->subias = upload<float>(e, l->subias, l->nb_out);
+  d->diag = l->diag ? upload<float>(e, l->diag, l->nb_out) : nullptr;
+  return (d->wp && d->scale && d->subias && (!l->diag || d->diag)) ? 0 : -1;
+}
+static int upload_f(B200Engine *e, DevLayerF *d, const B200Layer *l) {
+  d->w = upload<float>(e, l->wf, (size_t)l->nb_in * l->nb_out);
+  d->bias = upload<float>(e, l->bias, l->nb_out);
+  return (d->w && d->bias) ? 0 : -1;
+}
+
+extern "C" void b200_engine_destroy(B200Engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->own_stream) { cudaStreamSynchronize(e->own_stream); cudaStreamDestroy(e->own_stream); }
+  for (void *p : e->allocs) cudaFree(p);
+  delete e;
+}
+
+extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    fprintf(stderr, "[rnnoise_b200] no CUDA device available -- this library has no CPU path\n");
+    return nullptr;
+  }
+  if (!m || S < 1 || device < 0 || device >= ndev) return nullptr;
+  if (m->gru % 128 || m->cond % 4 || m->gru > 1024 || m->cond > 512) {
+    fprintf(stderr, "[rnnoise_b200] unsupported model dims cond=%d gru=%d (need gru %% 128 == 0)\n", m->cond, m->gru);
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  B200Engine *e = new B200Engine();
+  e->device = device;
+  e->frames = 0;
+  e->own_stream = nullptr;
+  if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return nullptr; }
+  e->stream = e->own_stream;
+  Arena &a = e->a;
+  a.S = S; a.cond = m->cond; a.gru = m->gru;
+  const size_t Ss = (size_t)S;
+  bool ok = true;
+  ok &= !!(a.ctr = dalloc<int>(e, 4));
+  ok &= !!(a.ring = dalloc<float>(e, Ss * PITCH_BUF_SIZE));
+  ok &= !!(a.synth_mem = dalloc<float>(e, Ss * FRAME_SIZE));
+  ok &= !!(a.hp_mem = dalloc<float>(e, Ss * 2));
+  ok &= !!(a.spec = dalloc<float>(e, 2 * Ss * 4 * FREQ_SIZE));
+  ok &= !!(a.band = dalloc<float>(e, 2 * Ss * 96));
+  ok &= !!(a.lastg = dalloc<float>(e, Ss * NB_BANDS));
+  ok &= !!(a.pitch_state = dalloc<float>(e, Ss * 2));
+  ok &= !!(a.conv1_state = dalloc<float>(e, Ss * 2 * NB_FEATURES));
+  ok &= !!(a.conv2_state = dalloc<float>(e, Ss * 2 * m->cond));
+  ok &= !!(a.hbuf = dalloc<float>(e, 2 * 3 * Ss * m->gru));
+  ok &= !!(a.xb = dalloc<float>(e, Ss * FRAME_SIZE));
+  ok &= !!(a.features = dalloc<float>(e, Ss * NB_FEATURES));
+  ok &= !!(a.silence = dalloc<int>(e, Ss));
+  ok &= !!(a.conv1_out = dalloc<float>(e, Ss * m->cond));
+  ok &= !!(a.conv2_out = dalloc<float>(e, Ss * m->gru));
+  ok &= !!(a.gains = dalloc<float>(e, Ss * NB_BANDS));
+  ok &= !!(a.vad = dalloc<float>(e, Ss));
+  ok &= !!(e->stage_in = dalloc<float>(e, Ss * FRAME_SIZE));
+  ok &= !!(e->stage_out = dalloc<float>(e, Ss * FRAME_SIZE));
+  ok &= !!(e->stage_vad = dalloc<float>(e, Ss));
+  DspTables *ht = new DspTables();
+  b200_fill_dsp_tables(ht);
+  e->d_tables = (DspTables *)upload<DspTables>(e, ht, 1);
+  delete ht;
+  ok &= !!e->d_tables;
+  DevModel &dm = e->dm;
+  dm.cond = m->cond; dm.gru = m->gru;
+  ok = ok && upload_f(e, &dm.conv1, &m->conv1) == 0 && upload_f(e, &dm.dense_out, &m->dense_out) == 0 &&
+       upload_f(e, &dm.vad_dense, &m->vad_dense) == 0 && upload_q(e, &dm.conv2, &m->conv2) == 0;
+  for (int k = 0; k < 3 && ok; k++)
+    ok = upload_q(e, &dm.gru_in[k], &m->gru_in[k]) == 0 && upload_q(e, &dm.gru_rec[k], &m->gru_rec[k]) == 0;
+  if (!ok || cudaDeviceSynchronize() != cudaSuccess) {
+    fprintf(stderr, "[rnnoise_b200] engine allocation/upload failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+    b200_engine_destroy(e);
+    return nullptr;
+  }
+  return e;
+}
+
+extern "C" int b200_engine_streams(const B200Engine *e) { return e ? e->a.S : 0; }
+extern "C" int b200_engine_launches_per_frame(const B200Engine *) { return 9; }
+
+extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float *d_in, float *d_vad) {
+  if (!e || !d_out || !d_in) return -1;
+  CK(cudaSetDevice(e->device));
+  const Arena &a = e->a;
+  const int S = a.S, gru = a.gru, cond = a.cond;
+  cudaStream_t st = e->stream;
+  const int par = (int)(e->frames & 1);
+  const size_t hstride = (size_t)S * gru;
+  float *h_new[3], *h_old[3];
+  for (int l = 0; l < 3; l++) {
+    h_new[l] = a.hbuf + ((size_t)par * 3 + l) * hstride;
+    h_old[l] = a.hbuf + ((size_t)(par ^ 1) * 3 + l) * hstride;
+  }
+  k_biquad<<<(S + 31) / 32, 32, 0, st>>>(a, d_in);
+  k_analysis<<<S, DSP_THREADS, SM_TOTAL * sizeof(float), st>>>(a, e->d_tables);
+  const int gts = (S + RNN_TS - 1) / RNN_TS;
+  k_conv1<<<gts, 128, 0, st>>>(S, e->dm, a.features, a.conv1_state, a.silence, a.conv1_out);
+  k_conv2<<<gts, 128, RNN_TS * 2 * cond * sizeof(uint32_t), st>>>(S, e->dm, a.conv1_out, a.conv2_state, a.silence, a.conv2_out);
+  const size_t gsm = 2 * RNN_TS * (gru / 4) * sizeof(uint32_t);
+  for (int l = 0; l < 3; l++) {
+    const float *x = l == 0 ? a.conv2_out : h_new[l - 1];
+    k_gru<<<dim3(gts, gru / 128), 128, gsm, st>>>(S, gru, e->dm.gru_in[l], e->dm.gru_rec[l], x, h_old[l], h_new[l], a.silence);
+  }
+  k_heads<<<(S + HEAD_TS - 1) / HEAD_TS, 160, 0, st>>>(S, e->dm, a.conv2_out, h_new[0], h_new[1], h_new[2], a.silence,
+                                                      a.gains, a.vad, d_vad);
+  k_synthesis<<<S, DSP_THREADS, SS_TOTAL * sizeof(float), st>>>(a, e->d_tables, d_out);
+  CK(cudaGetLastError());
+  e->frames++;
+  return 0;
+}
+
+extern "C" int b200_engine_frame_host(B200Engine *e, float *out, const float *in, float *vad) {
+  if (!e || !out || !in) return -1;
+  CK(cudaSetDevice(e->device));
+  const size_t n = (size_t)e->a.S * FRAME_SIZE * sizeof(float);
+  CK(cudaMemcpyAsync(e->stage_in, in, n, cudaMemcpyHostToDevice, e->stream));
+  if (b200_engine_frame_device(e, e->stage_out, e->stage_in, e->stage_vad)) return -1;
+  CK(cudaMemcpyAsync(out, e->stage_out, n, cudaMemcpyDeviceToHost, e->stream));
+  if (vad) CK(cudaMemcpyAsync(vad, e->stage_vad, (size_t)e->a.S * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+extern "C" int b200_engine_sync(B200Engine *e) {
+  if (!e) return -1;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+extern "C" int b200_engine_set_stream(B200Engine *e, void *cuda_stream) {
+  if (!e) return -1;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+  return 0;
+}
+
+extern "C" int b200_engine_reset_stream(B200Engine *e, int s) {
+  if (!e || s < 0 || s >= e->a.S) return -1;
+  CK(cudaSetDevice(e->device));
+  const Arena &a = e->a;
+  const size_t S = a.S;
+  cudaStream_t st = e->stream;
+#define ZERO(ptr, per, copies)                                                                          \
+  for (int c_ = 0; c_ < (copies); c_++)                                                                 \
+    CK(cudaMemsetAsync((ptr) + ((size_t)c_ * S + s) * (per), 0, (size_t)(per) * sizeof(*(ptr)), st));
+  ZERO(a.ring, PITCH_BUF_SIZE, 1) ZERO(a.synth_mem, FRAME_SIZE, 1) ZERO(a.hp_mem, 2, 1)
+  ZERO(a.spec, 4 * FREQ_SIZE, 2) ZERO(a.band, 96, 2) ZERO(a.lastg, NB_BANDS, 1) ZERO(a.pitch_state, 2, 1)
+  ZERO(a.conv1_state, 2 * NB_FEATURES, 1) ZERO(a.conv2_state, 2 * a.cond, 1) ZERO(a.hbuf, a.gru, 6)
+#undef ZERO
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst, int cap) {
+  if (!e || !dst || s < 0 || s >= e->a.S || e->frames < 1) return -1;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  const Arena &a = e->a;
+  const size_t S = a.S;
+  const int par = (int)((e->frames - 1) & 1);
+  const float *src = nullptr;
+  int n = 0;
+  switch (what) {
+    case RNNOISE_DBG_FEATURES: src = a.features + (size_t)s * NB_FEATURES; n = NB_FEATURES; break;
+    case RNNOISE_DBG_X: src = a.spec + ((size_t)par * S + s) * 4 * FREQ_SIZE; n = 2 * FREQ_SIZE; break;
+    case RNNOISE_DBG_P: src = a.spec + ((size_t)par * S + s) * 4 * FREQ_SIZE + 2 * FREQ_SIZE; n = 2 * FREQ_SIZE; break;
+    case RNNOISE_DBG_EX: src = a.band + ((size_t)par * S + s) * 96; n = 32; break;
+    case RNNOISE_DBG_EP: src = a.band + ((size_t)par * S + s) * 96 + 32; n = 32; break;
+    case RNNOISE_DBG_EXP: src = a.band + ((size_t)par * S + s) * 96 + 64; n = 32; break;
+    case RNNOISE_DBG_GAINS: src = a.gains + (size_t)s * NB_BANDS; n = NB_BANDS; break;
+    case RNNOISE_DBG_LASTG: src = a.lastg + (size_t)s * NB_BANDS; n = NB_BANDS; break;
+    case RNNOISE_DBG_XB: src = a.xb + (size_t)s * FRAME_SIZE; n = FRAME_SIZE; break;
+    case RNNOISE_DBG_GRU1: case RNNOISE_DBG_GRU2: case RNNOISE_DBG_GRU3:
+      src = a.hbuf + (((size_t)par * 3 + (what - RNNOISE_DBG_GRU1)) * S + s) * a.gru; n = a.gru; break;
+    case RNNOISE_DBG_CONV1_STATE: src = a.conv1_state + (size_t)s * 2 * NB_FEATURES; n = 2 * NB_FEATURES; break;
+    case RNNOISE_DBG_CONV2_STATE: src = a.conv2_state + (size_t)s * 2 * a.cond; n = 2 * a.cond; break;
+    case RNNOISE_DBG_PITCH: src = a.pitch_state + 2 * (size_t)s; n = 2; break;
+    case RNNOISE_DBG_SILENCE: src = (const float *)(a.silence + s); n = 1; break;
+    case RNNOISE_DBG_CONV2_OUT: src = a.conv2_out + (size_t)s * a.gru; n = a.gru; break;
+    default: return -1;
+  }
+  if (cap < n) return -1;
+  CK(cudaMemcpy(dst, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (what == RNNOISE_DBG_PITCH) { int p; memcpy(&p, dst, 4); dst[0] = (float)p; }
+  if (what == RNNOISE_DBG_SILENCE) { int p; memcpy(&p, dst, 4); dst[0] = (float)p; }
+  return n;
+}

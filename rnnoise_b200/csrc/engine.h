@@ -1,0 +1,31 @@
+/* engine.h -- internal C interface between the host API (rnnoise_api.c, plain C) and the CUDA
+ * engine (engine.cu).  Plain pointers and ints only. */
+#ifndef RNNOISE_B200_ENGINE_H
+#define RNNOISE_B200_ENGINE_H
+
+#include "model_blob.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct B200Engine B200Engine;
+
+/* Creates device state for nb_streams streams on `device`; uploads the model. NULL on failure. */
+B200Engine *b200_engine_create(const B200HostModel *m, int nb_streams, int device);
+void b200_engine_destroy(B200Engine *e);
+int b200_engine_streams(const B200Engine *e);
+/* One frame for every stream, device pointers, asynchronous on the engine's stream. */
+int b200_engine_frame_device(B200Engine *e, float *d_out, const float *d_in, float *d_vad);
+/* One frame, host pointers (copies in, runs, copies out, synchronises). */
+int b200_engine_frame_host(B200Engine *e, float *out, const float *in, float *vad);
+int b200_engine_sync(B200Engine *e);
+int b200_engine_set_stream(B200Engine *e, void *cuda_stream);
+int b200_engine_reset_stream(B200Engine *e, int stream);
+int b200_engine_launches_per_frame(const B200Engine *e);
+int b200_engine_debug_read(B200Engine *e, int what, int stream, float *dst, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

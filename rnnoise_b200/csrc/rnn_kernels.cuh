@@ -1,0 +1,292 @@
+// rnn_kernels.cuh -- compute_rnn() (reference src/rnn.c:44-60) batched over the stream dimension.
+//
+// Arithmetic contract (oracle/rnnoise_port.c is the executable statement of it): identical to the
+// reference's AVX2 kernels (src/vec_avx.h, src/nnet_arch.h) -- u8 = sat(rne(fma(x,127,127)))
+// activations, exact s32 accumulation of u8 x s8 products, (float)acc*scale + subias, FMA'd
+// recurrent diagonal, float layers as a sequential FMA chain over the inputs, Pade tanh/sigmoid --
+// with the single substitution of a correctly rounded reciprocal for _mm256_rcp_ps.
+// The translation unit is compiled with --fmad=false: every FMA below is explicit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define RNN_TS 8          // streams per CTA in the CUDA-core kernels
+#define NB_FEAT 65
+#define NB_GAINS 32
+
+__device__ __forceinline__ float act_tanh(float x) {   // tanh8_approx, vec_avx.h:398-416
+  const float N0 = 952.52801514f, N1 = 96.39235687f, N2 = 0.60863042f;
+  const float D0 = 952.72399902f, D1 = 413.36801147f, D2 = 11.88600922f;
+  float x2 = x * x;
+  float num = fmaf(fmaf(N2, x2, N1), x2, N0);
+  float den = fmaf(fmaf(D2, x2, D1), x2, D0);
+  num = num * x;
+  den = __frcp_rn(den);
+  num = num * den;
+  num = num < 1.f ? num : 1.f;
+  return num > -1.f ? num : -1.f;
+}
+__device__ __forceinline__ float act_sigmoid(float x) { // sigmoid8_approx, vec_avx.h:426-445
+  const float N0 = 238.13200378f, N1 = 6.02452230f, N2 = 0.00950985f;
+  const float D0 = 952.72399902f, D1 = 103.34200287f, D2 = 0.74287558f;
+  float x2 = x * x;
+  float num = fmaf(fmaf(N2, x2, N1), x2, N0);
+  float den = fmaf(fmaf(D2, x2, D1), x2, D0);
+  num = num * x;
+  den = __frcp_rn(den);
+  num = fmaf(num, den, .5f);
+  num = num < 1.f ? num : 1.f;
+  return num > 0.f ? num : 0.f;
+}
+__device__ __forceinline__ uint32_t quant_u8(float x) { // vector_ps_to_epi8, vec_avx.h:326-341
+  int v = __float2int_rn(fmaf(x, 127.f, 127.f));
+  v = v < 0 ? 0 : v;
+  return (uint32_t)(v > 255 ? 255 : v);
+}
+__device__ __forceinline__ uint32_t quant4(float a, float b, float c, float d) {
+  return quant_u8(a) | (quant_u8(b) << 8) | (quant_u8(c) << 16) | (quant_u8(d) << 24);
+}
+__device__ __forceinline__ int dp4a_us(uint32_t u, int w, int acc) { // 4 x (u8 * s8) + s32, exact
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(u), "r"(w), "r"(acc));
+  return d;
+}
+
+// Device-resident model (built by engine.cu from the parsed blob).
+struct DevLayerF { const float *w, *bias; };                               // w[in][out]
+struct DevLayerQ { const int *wp; const float *scale, *subias, *diag; };   // wp[in/4][out] packed s8x4
+struct DevModel {
+  int cond, gru;
+  DevLayerF conv1, dense_out, vad_dense;
+  DevLayerQ conv2, gru_in[3], gru_rec[3];
+};
+
+// ------------------------------------------------------------------------------------------------
+// conv1: [mem(2 frames) | features] (195) -> cond, fp32, tanh   (nnet.c:113-123, sgemv vec_avx.h:672)
+// grid = ceil(S / RNN_TS), block = 128
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *__restrict__ features,
+                                               float *conv1_state, const int *__restrict__ silence,
+                                               float *__restrict__ conv1_out) {
+  __shared__ float tmp[RNN_TS][3 * NB_FEAT + 1];
+  const int s0 = blockIdx.x * RNN_TS, tid = threadIdx.x;
+  for (int idx = tid; idx < RNN_TS * 3 * NB_FEAT; idx += 128) {
+    int s = idx / (3 * NB_FEAT), j = idx % (3 * NB_FEAT);
+    float v = 0.f;
+    if (s0 + s < S) v = j < 2 * NB_FEAT ? conv1_state[(size_t)(s0 + s) * 2 * NB_FEAT + j]
+                                         : features[(size_t)(s0 + s) * NB_FEAT + j - 2 * NB_FEAT];
+    tmp[s][j] = v;
+  }
+  __syncthreads();
+  for (int o = tid; o < m.cond; o += 128) {
+    float acc[RNN_TS];
+#pragma unroll
+    for (int s = 0; s < RNN_TS; s++) acc[s] = 0.f;
+    for (int j = 0; j < 3 * NB_FEAT; j++) {
+      float w = __ldg(&m.conv1.w[(size_t)j * m.cond + o]);
+#pragma unroll
+      for (int s = 0; s < RNN_TS; s++) acc[s] = fmaf(w, tmp[s][j], acc[s]);
+    }
+    const float b = m.conv1.bias[o];
+#pragma unroll
+    for (int s = 0; s < RNN_TS; s++)
+      if (s0 + s < S) conv1_out[(size_t)(s0 + s) * m.cond + o] = act_tanh(acc[s] + b);
+  }
+  // memory update: mem = tmp[65:195]; silent frames leave the state untouched (denoise.c:474)
+  for (int idx = tid; idx < RNN_TS * 2 * NB_FEAT; idx += 128) {
+    int s = idx / (2 * NB_FEAT), j = idx % (2 * NB_FEAT);
+    if (s0 + s < S && !silence[s0 + s]) conv1_state[(size_t)(s0 + s) * 2 * NB_FEAT + j] = tmp[s][NB_FEAT + j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv2: [mem(2 x cond) | conv1_out] (3*cond) -> gru, int8, tanh   (cgemv8x4 vec_avx.h:829)
+// grid = ceil(S / RNN_TS), block = 128, dynamic smem = RNN_TS * 2*cond * 4 bytes (operands, then
+// staging of the memory rotate)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_conv2(int S, DevModel m, const float *__restrict__ conv1_out,
+                                               float *conv2_state, const int *__restrict__ silence,
+                                               float *__restrict__ conv2_out) {
+  extern __shared__ uint32_t u_sm[];   // [RNN_TS][K/4]
+  const int K = 3 * m.cond, K4 = K / 4, s0 = blockIdx.x * RNN_TS, tid = threadIdx.x;
+  for (int idx = tid; idx < RNN_TS * K4; idx += 128) {
+    int s = idx / K4, k = 4 * (idx % K4);
+    uint32_t q = 0;
+    if (s0 + s < S) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        int kk = k + e;
+        v[e] = kk < 2 * m.cond ? conv2_state[(size_t)(s0 + s) * 2 * m.cond + kk]
+                               : conv1_out[(size_t)(s0 + s) * m.cond + kk - 2 * m.cond];
+      }
+      q = quant4(v[0], v[1], v[2], v[3]);
+    }
+    u_sm[idx] = q;
+  }
+  __syncthreads();
+  for (int o = tid; o < m.gru; o += 128) {
+    int acc[RNN_TS];
+#pragma unroll
+    for (int s = 0; s < RNN_TS; s++) acc[s] = 0;
+    for (int k4 = 0; k4 < K4; k4++) {
+      int w = __ldg(&m.conv2.wp[(size_t)k4 * m.gru + o]);
+#pragma unroll
+      for (int s = 0; s < RNN_TS; s++) acc[s] = dp4a_us(u_sm[s * K4 + k4], w, acc[s]);
+    }
+    const float sc = m.conv2.scale[o], sb = m.conv2.subias[o];
+#pragma unroll
+    for (int s = 0; s < RNN_TS; s++)
+      if (s0 + s < S) conv2_out[(size_t)(s0 + s) * m.gru + o] = act_tanh((float)acc[s] * sc + sb);
+  }
+  __syncthreads();
+  // mem = [mem[cond:2cond] | conv1_out]
+  for (int idx = tid; idx < RNN_TS * 2 * m.cond; idx += 128) {
+    int s = idx / (2 * m.cond), j = idx % (2 * m.cond);
+    if (s0 + s < S && !silence[s0 + s]) {
+      float v = j < m.cond ? conv2_state[(size_t)(s0 + s) * 2 * m.cond + m.cond + j]
+                           : conv1_out[(size_t)(s0 + s) * m.cond + j - m.cond];
+      // staged through shared memory: the rotate reads columns other threads overwrite
+      u_sm[idx] = __float_as_uint(v);
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < RNN_TS * 2 * m.cond; idx += 128) {
+    int s = idx / (2 * m.cond), j = idx % (2 * m.cond);
+    if (s0 + s < S && !silence[s0 + s]) conv2_state[(size_t)(s0 + s) * 2 * m.cond + j] = __uint_as_float(u_sm[idx]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One GRU layer (compute_generic_gru nnet.c:65-94; sparse_cgemv8x4 vec_avx.h:778 executed dense:
+// the zero blocks contribute exact zeros).  Thread = hidden unit, RNN_TS streams per CTA.
+// grid = (ceil(S / RNN_TS), gru / 128), block = 128, dynamic smem = 2 * RNN_TS * (gru/4) * 4 bytes
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_gru(int S, int gru, DevLayerQ wi, DevLayerQ wr,
+                                             const float *__restrict__ x, const float *__restrict__ h_old,
+                                             float *__restrict__ h_new, const int *__restrict__ silence) {
+  extern __shared__ uint32_t u_sm[];
+  const int K4 = gru / 4, s0 = blockIdx.x * RNN_TS, tid = threadIdx.x;
+  uint32_t *xu = u_sm, *hu = u_sm + RNN_TS * K4;
+  for (int idx = tid; idx < RNN_TS * K4; idx += 128) {
+    int s = idx / K4, k4 = idx % K4;
+    uint32_t qx = 0, qh = 0;
+    if (s0 + s < S) {
+      float4 a = *(const float4 *)&x[(size_t)(s0 + s) * gru + 4 * k4];
+      float4 b = *(const float4 *)&h_old[(size_t)(s0 + s) * gru + 4 * k4];
+      qx = quant4(a.x, a.y, a.z, a.w);
+      qh = quant4(b.x, b.y, b.z, b.w);
+    }
+    xu[idx] = qx; hu[idx] = qh;
+  }
+  __syncthreads();
+  const int j = blockIdx.y * 128 + tid;
+  if (j >= gru) return;
+  int ai[3][RNN_TS], ar[3][RNN_TS];
+#pragma unroll
+  for (int g = 0; g < 3; g++)
+#pragma unroll
+    for (int s = 0; s < RNN_TS; s++) { ai[g][s] = 0; ar[g][s] = 0; }
+  for (int k4 = 0; k4 < K4; k4++) {
+    int wiz = __ldg(&wi.wp[(size_t)k4 * 3 * gru + j]), wir = __ldg(&wi.wp[(size_t)k4 * 3 * gru + gru + j]),
+        win = __ldg(&wi.wp[(size_t)k4 * 3 * gru + 2 * gru + j]);
+    int wrz = __ldg(&wr.wp[(size_t)k4 * 3 * gru + j]), wrr = __ldg(&wr.wp[(size_t)k4 * 3 * gru + gru + j]),
+        wrn = __ldg(&wr.wp[(size_t)k4 * 3 * gru + 2 * gru + j]);
+#pragma unroll
+    for (int s = 0; s < RNN_TS; s++) {
+      uint32_t xv = xu[s * K4 + k4], hv = hu[s * K4 + k4];
+      ai[0][s] = dp4a_us(xv, wiz, ai[0][s]);
+      ai[1][s] = dp4a_us(xv, wir, ai[1][s]);
+      ai[2][s] = dp4a_us(xv, win, ai[2][s]);
+      ar[0][s] = dp4a_us(hv, wrz, ar[0][s]);
+      ar[1][s] = dp4a_us(hv, wrr, ar[1][s]);
+      ar[2][s] = dp4a_us(hv, wrn, ar[2][s]);
+    }
+  }
+  float sci[3], sbi[3], scr[3], sbr[3], dg[3];
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+    sci[g] = wi.scale[g * gru + j]; sbi[g] = wi.subias[g * gru + j];
+    scr[g] = wr.scale[g * gru + j]; sbr[g] = wr.subias[g * gru + j];
+    dg[g] = wr.diag[g * gru + j];
+  }
+#pragma unroll
+  for (int s = 0; s < RNN_TS; s++) {
+    if (s0 + s >= S) continue;
+    const float h = h_old[(size_t)(s0 + s) * gru + j];
+    float out = h;
+    if (!silence[s0 + s]) {
+      float zi = (float)ai[0][s] * sci[0] + sbi[0];
+      float ri = (float)ai[1][s] * sci[1] + sbi[1];
+      float ni = (float)ai[2][s] * sci[2] + sbi[2];
+      float zr = fmaf(dg[0], h, (float)ar[0][s] * scr[0] + sbr[0]);
+      float rr = fmaf(dg[1], h, (float)ar[1][s] * scr[1] + sbr[1]);
+      float nr = fmaf(dg[2], h, (float)ar[2][s] * scr[2] + sbr[2]);
+      float z = act_sigmoid(zi + zr);
+      float r = act_sigmoid(ri + rr);
+      float n = act_tanh(ni + nr * r);
+      out = z * h + (1 - z) * n;
+    }
+    h_new[(size_t)(s0 + s) * gru + j] = out;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output heads on cat = [conv2_out | gru1 | gru2 | gru3] (rnn.c:53-57): dense_out (32, sigmoid;
+// sequential FMA chain) and vad_dense (1, sigmoid; the reference's scalar tail multiplies and adds
+// separately, vec_avx.h:731-735).  grid = ceil(S / 32), block = 160 (4 warps dense + 1 warp vad).
+// ------------------------------------------------------------------------------------------------
+#define HEAD_TS 32
+#define HEAD_KC 128
+__global__ void __launch_bounds__(160) k_heads(int S, DevModel m, const float *__restrict__ c2,
+                                               const float *__restrict__ g1, const float *__restrict__ g2,
+                                               const float *__restrict__ g3, const int *__restrict__ silence,
+                                               float *__restrict__ gains, float *__restrict__ vad,
+                                               float *__restrict__ vad_user) {
+  __shared__ float xs[HEAD_TS][HEAD_KC + 1];
+  const int s0 = blockIdx.x * HEAD_TS, tid = threadIdx.x, gru = m.gru, K = 4 * gru;
+  const int o = tid & 31, sg = tid >> 5;
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) acc[q] = 0.f;
+  float y = 0.f;
+  for (int c0 = 0; c0 < K; c0 += HEAD_KC) {
+    __syncthreads();
+    for (int idx = tid; idx < HEAD_TS * HEAD_KC; idx += 160) {
+      int s = idx / HEAD_KC, kk = c0 + idx % HEAD_KC;
+      float v = 0.f;
+      if (s0 + s < S && kk < K) {
+        int src = kk / gru, off = kk % gru;
+        const float *p = src == 0 ? c2 : src == 1 ? g1 : src == 2 ? g2 : g3;
+        v = p[(size_t)(s0 + s) * gru + off];
+      }
+      xs[s][idx % HEAD_KC] = v;
+    }
+    __syncthreads();
+    const int kn = min(HEAD_KC, K - c0);
+    if (sg < 4) {
+      for (int kk = 0; kk < kn; kk++) {
+        float w = __ldg(&m.dense_out.w[(size_t)(c0 + kk) * NB_GAINS + o]);
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = fmaf(w, xs[sg * 8 + q][kk], acc[q]);
+      }
+    } else {
+      for (int kk = 0; kk < kn; kk++) y = y + __ldg(&m.vad_dense.w[c0 + kk]) * xs[o][kk];
+    }
+  }
+  if (sg < 4) {
+    const float b = m.dense_out.bias[o];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      int s = s0 + sg * 8 + q;
+      if (s < S) gains[(size_t)s * NB_GAINS + o] = act_sigmoid(acc[q] + b);
+    }
+  } else {
+    int s = s0 + o;
+    if (s < S) {
+      float v = silence[s] ? 0.f : act_sigmoid(y + m.vad_dense.bias[0]);
+      vad[s] = v;
+      if (vad_user) vad_user[s] = v;
+    }
+  }
+}
