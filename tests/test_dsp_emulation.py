@@ -1,0 +1,52 @@
+"""The GPU's per-stream DSP source (rnnoise_b200/csrc/dsp_stream.cuh) executed on the host, thread id
+by thread id, must be BIT-IDENTICAL to the oracle port (hence to the reference build): checks the
+indexing, work partitioning and arithmetic of the exact code the GPU runs, without a GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.portbind import Port, fptr
+from rnnoise_b200.synth_pcm import stream_pcm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_SRC = os.path.join(ROOT, "tests", "emu", "emu_dsp.cpp")
+EMU_SO = os.path.join(ROOT, "tests", "emu", "libemu_dsp.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    deps = [EMU_SRC] + [os.path.join(ROOT, "rnnoise_b200", "csrc", f) for f in ("dsp_core.cuh", "dsp_stream.cuh", "dsp_tables.hpp")]
+    if not os.path.exists(EMU_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMU_SO) for d in deps):
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                        "-I", os.path.join(ROOT, "rnnoise_b200", "csrc"), EMU_SRC, "-o", EMU_SO], check=True)
+    E = C.CDLL(EMU_SO)
+    E.emu_create.restype = C.c_void_p
+    E.emu_destroy.argtypes = [C.c_void_p]
+    E.emu_analysis.argtypes = [C.c_void_p] + [C.POINTER(C.c_float)] * 7
+    E.emu_synthesis.argtypes = [C.c_void_p] + [C.POINTER(C.c_float)] * 3
+    return E
+
+
+@pytest.mark.parametrize("stream,frames", [(0, 80), (15, 60), (7, 50)])
+def test_device_dsp_source_is_bit_identical_to_port(emu, port_default, stream, frames):
+    pcm = stream_pcm(stream, frames)
+    st, e = port_default.create(), emu.emu_create()
+    for f in range(frames):
+        b = port_default.process_frame(st, pcm[f])
+        xb = np.zeros(480, np.float32); feat = np.zeros(65, np.float32)
+        X = np.zeros(962, np.float32); P = np.zeros(962, np.float32)
+        bands = np.zeros(96, np.float32); pitch = np.zeros(2, np.float32)
+        sil = emu.emu_analysis(e, fptr(pcm[f].copy()), fptr(xb), fptr(feat), fptr(X), fptr(P), fptr(bands), fptr(pitch))
+        out = np.zeros(480, np.float32); lastg = np.zeros(32, np.float32)
+        emu.emu_synthesis(e, fptr(b["g_raw"]), fptr(out), fptr(lastg))
+        for k, u, v in (("xb", xb, b["xb"]), ("features", feat, b["features"]), ("X", X, b["X"]), ("P", P, b["P"]),
+                        ("Ex", bands[:32], b["Ex"]), ("Ep", bands[32:64], b["Ep"]), ("Exp", bands[64:], b["Exp"]),
+                        ("out", out, b["out"]), ("lastg", lastg, b["lastg"])):
+            assert u.tobytes() == v.tobytes(), (k, f)
+        assert sil == b["silence"] and int(pitch[0]) == b["pitch"]
+        assert pitch[1:].tobytes() == np.float32(b["pitch_gain"]).tobytes()
+    emu.emu_destroy(e)
+    port_default.destroy(st)

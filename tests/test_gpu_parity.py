@@ -1,0 +1,200 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+include/rnnoise.h (ctypes); the checker is the oracle port (bit-pinned to the reference build by
+tests/test_oracle_port.py) plus the committed reference goldens.
+
+Bars (DESIGN.md "Parity"):
+  * DSP quantities (biquad output, X, P, Ex, Ep, Exp, features, pitch period, silence flag): bit-exact.
+  * int8 accumulators: exact by construction; network outputs (gains, VAD, states) and PCM: the CUDA
+    path implements the port's arithmetic operation for operation, so they are compared bit-exact
+    against the port as well, and against the REFERENCE goldens within the reference's own
+    cross-build envelope: err <= 2 * E_ref + floor, E_ref = |AVX2 build - generic-C build|.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from rnnoise_b200.synth_pcm import batch_pcm, stream_pcm
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import rnnoise_b200
+    if not os.path.exists(rnnoise_b200.LIB_PATH):
+        from rnnoise_b200 import build
+        build.build()
+    rnnoise_b200.lib()
+    return rnnoise_b200
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def compare_with_port(rb, port, model_path, stream_ids, frames, exact_nn=True):
+    model = rb.Model(model_path)
+    S = len(stream_ids)
+    batch = rb.Batch(model, S)
+    pcm = np.stack([stream_pcm(s, frames) for s in stream_ids], axis=1)  # [frames][S][480]
+    states = [port.create() for _ in stream_ids]
+    worst = {}
+    for f in range(frames):
+        out, vad = batch.process(pcm[f])
+        for i in range(S):
+            r = port.process_frame(states[i], pcm[f, i])
+            tag = f"frame {f} stream {stream_ids[i]}"
+            assert int(batch.debug("silence", i)[0]) == r["silence"], tag
+            assert int(batch.debug("pitch", i)[0]) == r["pitch"], tag
+            for key, pk in (("xb", "xb"), ("X", "X"), ("P", "P"), ("Ex", "Ex"), ("Ep", "Ep"), ("Exp", "Exp"),
+                            ("features", "features")):
+                assert np.array_equal(bits(batch.debug(key, i)), bits(r[pk])), f"{key} not bit-exact, {tag}"
+            nn = dict(out=(out[i], r["out"]), vad=(vad[i:i + 1], np.float32([r["vad"]])), lastg=(batch.debug("lastg", i), r["lastg"]))
+            if not r["silence"]:
+                nn["gains"] = (batch.debug("gains", i), r["g_raw"])
+            for k, (u, v) in nn.items():
+                d = float(np.abs(np.asarray(u, np.float64) - np.asarray(v, np.float64)).max())
+                worst[k] = max(worst.get(k, 0.0), d)
+                if exact_nn:
+                    assert np.array_equal(bits(u), bits(v)), f"{k} differs from the port by {d}, {tag}"
+            st = states[i].contents
+            for li, k in enumerate(("gru1", "gru2", "gru3")):
+                g = np.array(st.gru_state[li][:len(batch.debug(k, i))], np.float32)
+                if exact_nn:
+                    assert np.array_equal(bits(batch.debug(k, i)), bits(g)), f"{k} state, {tag}"
+    for st in states:
+        port.destroy(st)
+    batch.destroy()
+    model.free()
+    return worst
+
+
+def test_default_model_bit_exact_vs_port(rb, port_default, models_dir):
+    ids = [0, 1, 2, 3, 15, 7, 31, 100, 47]
+    worst = compare_with_port(rb, port_default, os.path.join(models_dir, "default.bin"), ids, 70)
+    print("max |gpu - port|:", worst)
+
+
+@pytest.mark.parametrize("name", ["hot", "little"])
+def test_other_models_bit_exact_vs_port(rb, models_dir, name):
+    from oracle.portbind import Port
+    port = Port(os.path.join(models_dir, name + ".bin"))
+    worst = compare_with_port(rb, port, os.path.join(models_dir, name + ".bin"), [0, 15, 5], 50)
+    print(name, "max |gpu - port|:", worst)
+
+
+@pytest.mark.parametrize("name", ["default", "hot", "little"])
+def test_against_reference_goldens(rb, models_dir, name):
+    """Committed outputs of the unmodified reference (AVX2 path): DSP bit-exact, network/PCM inside
+    2x the reference's own AVX2-vs-generic-C envelope."""
+    g = np.load(os.path.join(GOLD, f"ref_{name}.npz"))
+    frames, ids = int(g["frames"]), [int(s) for s in g["streams"]]
+    model = rb.Model(os.path.join(models_dir, name + ".bin"))
+    batch = rb.Batch(model, len(ids))
+    pcm = np.stack([stream_pcm(s, frames) for s in ids], axis=1)
+    got = {k: np.zeros((frames, len(ids)) + shp, np.float32) for k, shp in
+           (("features", (65,)), ("Ex", (32,)), ("g_raw", (32,)), ("out", (480,)), ("lastg", (32,)), ("vad", ()), ("pitch", ()), ("silence", ()))}
+    for f in range(frames):
+        out, vad = batch.process(pcm[f])
+        got["out"][f], got["vad"][f] = out, vad
+        for i in range(len(ids)):
+            got["features"][f, i] = batch.debug("features", i); got["Ex"][f, i] = batch.debug("Ex", i)
+            got["lastg"][f, i] = batch.debug("lastg", i)
+            got["pitch"][f, i] = batch.debug("pitch", i)[0]; got["silence"][f, i] = batch.debug("silence", i)[0]
+            got["g_raw"][f, i] = 0 if got["silence"][f, i] else batch.debug("gains", i)
+    for i, s in enumerate(ids):
+        assert np.array_equal(bits(got["features"][:, i]), bits(g[f"s{s}_features"])), f"features vs reference, stream {s}"
+        assert np.array_equal(bits(got["Ex"][:, i]), bits(g[f"s{s}_Ex"]))
+        assert np.array_equal(got["pitch"][:, i].astype(int), g[f"s{s}_pitch"])
+        assert np.array_equal(got["silence"][:, i].astype(int), g[f"s{s}_silence"])
+        for key, floor in (("g_raw", 2e-4), ("vad", 2e-4), ("lastg", 2e-4), ("out", 0.25)):
+            ref = g[f"s{s}_{key}"].reshape(got[key][:, i].shape)
+            e_ref = float(np.abs(g[f"s{s}_generic_{key}"].reshape(ref.shape) - ref).max())
+            err = float(np.abs(got[key][:, i] - ref).max())
+            assert err <= 2 * e_ref + floor, (name, s, key, err, e_ref)
+    batch.destroy(); model.free()
+
+
+def test_single_stream_api_equals_batch(rb, models_dir):
+    """rnnoise_create()/rnnoise_process_frame() (reference surface, in == out aliasing as in
+    examples/rnnoise_demo.c:57) gives exactly what the batched call gives for the same stream."""
+    import ctypes as C
+    L = rb.lib()
+    mp = os.path.join(models_dir, "default.bin")
+    model = rb.Model(mp)
+    st = L.rnnoise_create(model.handle)
+    assert st
+    batch = rb.Batch(model, 3)
+    frames = 25
+    pcm = np.stack([stream_pcm(s, frames) for s in (4, 5, 6)], axis=1)
+    for f in range(frames):
+        out, vad = batch.process(pcm[f])
+        x = pcm[f, 1].copy()
+        p = x.ctypes.data_as(C.POINTER(C.c_float))
+        v = L.rnnoise_process_frame(st, p, p)
+        assert np.array_equal(bits(x), bits(out[1])) and np.float32(v) == vad[1]
+    L.rnnoise_destroy(st)
+    batch.destroy(); model.free()
+
+
+def test_streams_are_independent_and_reset_works(rb, models_dir):
+    """Same input on every stream -> identical output on every stream (no cross-stream term), and a
+    reset stream restarts exactly like a fresh state."""
+    model = rb.Model(os.path.join(models_dir, "default.bin"))
+    S, frames = 300, 12   # S not a multiple of any tile size used by the kernels
+    batch = rb.Batch(model, S)
+    one = stream_pcm(9, 2 * frames)
+    first = []
+    for f in range(frames):
+        out, vad = batch.process(np.repeat(one[f][None], S, 0))
+        assert np.array_equal(bits(out), np.repeat(bits(out[:1]), S, 0)) and np.all(vad == vad[0])
+        first.append(out[0].copy())
+    batch.reset_stream(137)
+    for f in range(frames):   # replay the same frames on the reset stream only
+        x = np.repeat(one[frames + f][None], S, 0)
+        x[137] = one[f]
+        out, _ = batch.process(x)
+        assert np.array_equal(bits(out[137]), bits(first[f])), f
+    batch.destroy(); model.free()
+
+
+def test_device_pointer_call_in_place(rb, models_dir):
+    """Device-buffer entry point with d_out aliasing d_in, driven from torch-allocated memory."""
+    import torch
+    model = rb.Model(os.path.join(models_dir, "default.bin"))
+    S, frames = 64, 6
+    a, b = rb.Batch(model, S), rb.Batch(model, S)
+    pcm = batch_pcm(S, frames)
+    for f in range(frames):
+        ref_out, ref_vad = a.process(pcm[f])
+        d = torch.from_numpy(pcm[f]).cuda()
+        dv = torch.empty(S, device="cuda")
+        torch.cuda.synchronize()
+        b.process_device(d.data_ptr(), d.data_ptr(), dv.data_ptr())
+        b.sync()
+        assert np.array_equal(bits(d.cpu().numpy()), bits(ref_out)) and np.array_equal(dv.cpu().numpy(), ref_vad)
+    a.destroy(); b.destroy(); model.free()
+
+
+def test_full_size_properties_4096_streams(rb, models_dir):
+    """BASELINE config[1] size: 4096 streams.  Size-independent properties: streams fed zeros stay
+    exactly silent (VAD 0, output 0), duplicated streams stay bit-identical, and a spot-checked
+    stream equals the port."""
+    from oracle.portbind import Port
+    S, frames = 4096, 8
+    mp = os.path.join(models_dir, "default.bin")
+    model = rb.Model(mp)
+    batch = rb.Batch(model, S)
+    base = batch_pcm(64, frames)                       # 64 distinct streams, tiled 64x
+    port = Port(mp); st = port.create()
+    for f in range(frames):
+        x = np.tile(base[f], (S // 64, 1))
+        x[1::128] = 0.0                                # some all-zero streams
+        out, vad = batch.process(x)
+        assert np.array_equal(bits(out[:64][2::2]), bits(out[64 * 17:64 * 18][2::2]))
+        assert not out[1::128].any() and not vad[1::128].any()
+        r = port.process_frame(st, base[f, 5])
+        assert np.array_equal(bits(out[64 * 40 + 5]), bits(r["out"])) and np.float32(r["vad"]) == vad[64 * 40 + 5]
+    batch.destroy(); model.free()
