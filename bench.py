@@ -1,0 +1,296 @@
+#!/usr/bin/env python3
+"""bench.py -- 10 ms frames/sec of the batched denoise hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--streams S] [--impl b200|reference]
+  (N > 1: launched by torchrun, one rank per GPU; streams shard with no collective -> "weak")
+
+One "step" = one call of the hot path = one 480-sample frame for each of S streams resident on a
+GPU (default S = 4096 = BASELINE configs[1], default synthetic model).  Prints ONE JSON line:
+  value      whole-job frames/s, PCM already resident in HBM (rnnoise_process_frame_batch_device)
+  e2e        same metric through the host-buffer C-ABI call rnnoise_process_frame_batch():
+             pinned host in -> H2D -> kernels -> D2H -> pinned host out, all inside the timed region
+  roofline   dominant kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline  the unmodified reference (oracle/_ref, AVX2 RTCD build) on this box's host cores
+--impl reference times that CPU reference arm alone on the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FRAME = 480
+POOL_FRAMES = 32          # distinct frames per pooled stream (device-resident input rotates through them)
+POOL_STREAMS = 128        # distinct synthetic streams, tiled over S
+MODEL = os.path.join(ROOT, "tests", "golden", "models", "default.bin")
+# Algorithmic HBM bytes per stream-frame (DESIGN.md "Kernels"): whole pipeline 43 344;
+# per kernel, counting each array the kernel must read or write once:
+KERNEL_BYTES = {
+    "k_biquad": 480 * 4 * 2 + 16,                                   # in -> xb, hp state
+    "k_analysis": (480 + 1248 + 480 + 2 * 962 + 96 + 65 + 1 + 4) * 4,  # xb, ring old/new, X+P, bands, features
+    "k_synthesis": (2 * 962 + 96 + 32 + 32 + 2 * 32 + 2 * 480 + 480) * 4,
+}
+
+
+def world():
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def make_pool(S):
+    """float32 [POOL_FRAMES][S][480]: POOL_STREAMS distinct synthetic streams tiled to S."""
+    from rnnoise_b200.synth_pcm import batch_pcm
+    base = batch_pcm(min(POOL_STREAMS, S), POOL_FRAMES)
+    reps = (S + base.shape[1] - 1) // base.shape[1]
+    return np.ascontiguousarray(np.tile(base, (1, reps, 1))[:, :S])
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop.set()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_reference(S, steps, warmup, threads=None):
+    """Times the unmodified reference (oracle/_ref) on the host cores; returns dict or None."""
+    from oracle import refbind
+    exe = refbind.bench_path()
+    if not os.path.exists(exe):
+        return None
+    threads = threads or len(os.sched_getaffinity(0))
+    r = subprocess.run([exe, MODEL, str(S), str(steps), str(warmup), str(threads)], capture_output=True, text=True, timeout=1500)
+    if r.returncode != 0:
+        return None
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    d["threads"] = min(threads, S)
+    return d
+
+
+def best_reference_threads(S):
+    """Quick sweep: containers often expose more logical CPUs than their CPU quota; pick the thread
+    count that gives the reference its best throughput on this box."""
+    n = len(os.sched_getaffinity(0))
+    best, best_t = None, n
+    for t in sorted({n, max(1, n // 2), max(1, n // 4), max(1, n // 8)}, reverse=True):
+        r = run_reference(min(S, 8 * t), 12, 3, threads=t)
+        if r and (best is None or r["frames_per_s"] > best):
+            best, best_t = r["frames_per_s"], t
+    return best_t, best
+
+
+def cpu_model():
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    W, rank, local = world()
+    S, K, Wm = a.streams, a.steps, max(a.warmup, 3)
+    cfg = {"workload": f"{S} concurrent 48 kHz mono streams per GPU, default synthetic model (cond128/GRU384 int8 block-sparse), "
+                       f"one 480-sample frame per stream per step", "streams_per_gpu": S, "frame": FRAME,
+           "model": "tests/golden/models/default.bin",
+           "l2": f"per-step state+I/O working set {S * 43344 / 1e6:.0f} MB vs 126 MB L2; input rotates through a "
+                 f"{POOL_FRAMES}-frame device pool ({POOL_FRAMES * S * FRAME * 4 / 1e6:.0f} MB)"}
+
+    if a.impl == "reference":
+        # CPU arm: rank 0 alone runs it; other ranks exit quietly.
+        if rank != 0:
+            return
+        total_S = S * max(a.gpus, 1)
+        threads, _ = best_reference_threads(total_S)
+        ref = run_reference(total_S, K, Wm, threads=threads)
+        if ref is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_bench not built (needs /root/reference at build time)"}))
+            return
+        v = ref["frames_per_s"]
+        print(json.dumps({"impl": "reference", "metric": "10ms frames/sec", "value": v, "unit": "frames/s", "n_gpus": a.gpus,
+                          "steps": K, "warmup": Wm, "ms_per_step": 1e3 * ref["elapsed_s"] / K, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "int8+fp32 (AVX2)", "data": "synthetic",
+                          "config": dict(cfg, streams_total=total_S),
+                          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": ref["threads"], "kind": "reference",
+                                           "sample": f"{total_S} streams x {K} frames, unmodified xiph/rnnoise RTCD/AVX2 build, {cpu_model()}"},
+                          "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import rnnoise_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    if W > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if not os.path.exists(rnnoise_b200.LIB_PATH):
+        from rnnoise_b200 import build
+        build.build()
+    model = rnnoise_b200.Model(MODEL)
+    batch = rnnoise_b200.Batch(model, S, local)
+    pool_h = torch.from_numpy(make_pool(S)).pin_memory()           # [POOL][S][480] pinned host
+    pool_d = pool_h.to(dev)                                        # device-resident inputs
+    out_d = torch.empty(S, FRAME, device=dev)
+    vad_d = torch.empty(S, device=dev)
+    # a dedicated non-default stream: handle 0 (the legacy default stream) means "private stream" to
+    # rnnoise_batch_set_stream(), and events must be recorded on the stream the kernels run on.
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    batch.set_stream(stream.cuda_stream)
+
+    def step_device(i):
+        batch.process_device(out_d.data_ptr(), pool_d[i % POOL_FRAMES].data_ptr(), vad_d.data_ptr())
+
+    def barrier():
+        if W > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput (value) ----
+    for i in range(Wm):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e0.record(stream)
+    for i in range(K):
+        step_device(Wm + i)
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    # the device-event time must explain the wall clock of the same region (guards against timing
+    # the wrong stream): allow launch/sync slack only
+    assert ms > 0.7 * wall_ms - 2.0, f"event time {ms:.2f} ms does not cover wall time {wall_ms:.2f} ms"
+    if W > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = W * S * K / (ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer C-ABI call (e2e) ----
+    out_h = torch.empty(S, FRAME).pin_memory()
+    vad_h = torch.empty(S).pin_memory()
+    Ke = max(10, min(K, 100))
+    for i in range(3):
+        batch.process_ptr(out_h.data_ptr(), pool_h[i % POOL_FRAMES].data_ptr(), vad_h.data_ptr())
+    barrier()
+    e0.record(stream)
+    for i in range(Ke):
+        batch.process_ptr(out_h.data_ptr(), pool_h[(3 + i) % POOL_FRAMES].data_ptr(), vad_h.data_ptr())
+    e1.record(stream)
+    barrier()
+    ms_e = e0.elapsed_time(e1)
+    if W > 1:
+        t = torch.tensor([ms_e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e = float(t.item())
+    e2e = {"value": W * S * Ke / (ms_e * 1e-3), "unit": "frames/s", "steps": Ke, "ms_per_step": ms_e / Ke,
+           "h2d_bytes_per_step": S * FRAME * 4, "d2h_bytes_per_step": S * FRAME * 4 + S * 4,
+           "api": "rnnoise_process_frame_batch (pinned host buffers, copies inside the timed region)"}
+
+    # ---- per-kernel CUDA-event timing for the roofline (separate pass, same workload) ----
+    batch.profile(True)
+    Kp = max(5, min(K, 50))
+    for i in range(Kp):
+        step_device(i)
+    times, nprof = batch.profile_read()
+    batch.profile(False)
+    kernels = {k: v / nprof for k, v in times.items()}             # ms per launch
+    top = max(kernels, key=kernels.get)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    top_bytes = KERNEL_BYTES.get(top, 43344) * S
+    achieved = top_bytes / (kernels[top] * 1e-3) / 1e9
+    roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+            "algorithmic_bytes_per_launch": top_bytes, "ms_per_launch": kernels[top], "traffic": None,
+            "kernel_ms_per_step": kernels, "kernel_share": {k: v / sum(kernels.values()) for k, v in kernels.items()},
+            "pipeline": {"algorithmic_bytes_per_stream_frame": 43344,
+                         "achieved_GBps": 43344 * S * K / (ms * 1e-3) / 1e9 / 1.0,
+                         "frac": 43344 * S * K / (ms * 1e-3) / 1e9 / hbm}}
+
+    if rank == 0:
+        cpu = None
+        if W == 1 and not a.no_cpu_baseline:
+            try:
+                threads, rate = best_reference_threads(S)           # calibration ~ a second
+                if rate:
+                    steps_cpu = int(max(10, min(400, 15.0 * rate / S)))
+                    ref = run_reference(S, steps_cpu, 5, threads=threads)
+                    cpu = {"value": ref["frames_per_s"], "unit": "frames/s", "cores": ref["threads"], "kind": "reference",
+                           "sample": f"{S} streams x {steps_cpu} frames, unmodified xiph/rnnoise RTCD/AVX2 build via oracle/_ref, {cpu_model()}"}
+            except Exception as ex:  # noqa: BLE001
+                cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+        line = {"metric": "10ms frames/sec", "value": value, "unit": "frames/s", "n_gpus": W, "steps": K, "warmup": Wm,
+                "ms_per_step": ms / K, "wall_ms_per_step": wall_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int8 (u8 x s8 -> s32) + fp32", "data": "synthetic", "config": dict(cfg, streams_total=W * S),
+                "realtime_streams_per_gpu": value / W / 100.0, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": K * batch.launches_per_frame, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    batch.destroy()
+    model.free()
+    if W > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

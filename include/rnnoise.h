@@ -114,6 +114,16 @@ RNNOISE_EXPORT int rnnoise_batch_reset_stream(RNNoiseBatch *b, int stream);
 /** Number of kernel launches one rnnoise_process_frame_batch_device() call issues. */
 RNNOISE_EXPORT int rnnoise_batch_launches_per_frame(const RNNoiseBatch *b);
 
+/** Per-kernel timing for roofline reports.  enable != 0: every following frame records CUDA events
+ *  around each kernel launch on the batch's stream and accumulates the elapsed times (the call then
+ *  synchronises after each frame).  enable == 0 stops.  Accumulators reset on every enable. */
+RNNOISE_EXPORT int rnnoise_batch_profile(RNNoiseBatch *b, int enable);
+
+/** Reads the accumulators: ms[i] = total milliseconds spent in kernel i over *frames frames,
+ *  i < rnnoise_batch_launches_per_frame().  names[i] (optional) receives static strings.
+ *  Returns the number of kernels or -1. */
+RNNOISE_EXPORT int rnnoise_batch_profile_read(RNNoiseBatch *b, float *ms, const char **names, int capacity, int *frames);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Introspection for parity tests (device -> host copies of per-stream intermediates of the last */
 /* processed frame).  Not needed by applications.                                                */

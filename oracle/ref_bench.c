@@ -31,6 +31,7 @@
 typedef struct {
   int tid, nthreads, s0, s1, steps, warmup, in_frames;
   DenoiseState **st;
+  RNNModel *model;
   const float *pcm; /* [streams][in_frames][480] */
   pthread_barrier_t *bar;
   double checksum;
@@ -63,6 +64,11 @@ static void *work(void *arg) {
   CPU_ZERO(&set);
   CPU_SET(w->tid % (int)sysconf(_SC_NPROCESSORS_ONLN), &set);
   pthread_setaffinity_np(pthread_self(), sizeof(set), &set); /* best effort */
+  /* each worker creates (first-touches) its own states so they are NUMA-local to it */
+  for (int s = w->s0; s < w->s1; s++) {
+    w->st[s] = rnnoise_create(w->model);
+    if (!w->st[s]) { fprintf(stderr, "rnnoise_create failed (model dims mismatch?)\n"); exit(1); }
+  }
   for (int f = 0; f < w->warmup; f++)
     for (int s = w->s0; s < w->s1; s++)
       rnnoise_process_frame(w->st[s], out, w->pcm + ((size_t)s * w->in_frames + f % w->in_frames) * FRAME);
@@ -90,11 +96,7 @@ int main(int argc, char **argv) {
   if (T > S) T = S;
   RNNModel *model = rnnoise_model_from_filename(argv[1]);
   if (!model) { fprintf(stderr, "cannot load model\n"); return 1; }
-  DenoiseState **st = malloc(sizeof(*st) * S);
-  for (int s = 0; s < S; s++) {
-    st[s] = rnnoise_create(model);
-    if (!st[s]) { fprintf(stderr, "rnnoise_create failed (model dims mismatch?)\n"); return 1; }
-  }
+  DenoiseState **st = calloc(S, sizeof(*st));
   int in_frames;
   float *pcm;
   if (argc > 6) {
@@ -116,7 +118,7 @@ int main(int argc, char **argv) {
   Worker *w = calloc(T, sizeof(*w));
   for (int t = 0; t < T; t++) {
     w[t] = (Worker){.tid = t, .nthreads = T, .s0 = (int)((long)S * t / T), .s1 = (int)((long)S * (t + 1) / T),
-                    .steps = steps, .warmup = warmup, .in_frames = in_frames, .st = st, .pcm = pcm, .bar = &bar};
+                    .steps = steps, .warmup = warmup, .in_frames = in_frames, .st = st, .model = model, .pcm = pcm, .bar = &bar};
     pthread_create(&th[t], NULL, work, &w[t]);
   }
   double cs = 0, tmin = 1e300, tmax = -1e300;

@@ -46,6 +46,9 @@ def lib():
         L.rnnoise_batch_set_stream.restype = ip; L.rnnoise_batch_set_stream.argtypes = [vp, vp]
         L.rnnoise_batch_reset_stream.restype = ip; L.rnnoise_batch_reset_stream.argtypes = [vp, ip]
         L.rnnoise_batch_launches_per_frame.restype = ip; L.rnnoise_batch_launches_per_frame.argtypes = [vp]
+        L.rnnoise_batch_profile.restype = ip; L.rnnoise_batch_profile.argtypes = [vp, ip]
+        L.rnnoise_batch_profile_read.restype = ip
+        L.rnnoise_batch_profile_read.argtypes = [vp, fp, C.POINTER(C.c_char_p), ip, C.POINTER(ip)]
         L.rnnoise_batch_debug_read.restype = ip; L.rnnoise_batch_debug_read.argtypes = [vp, ip, ip, fp, ip]
         _lib = L
     return _lib
@@ -117,6 +120,18 @@ class Batch:
     @property
     def launches_per_frame(self):
         return lib().rnnoise_batch_launches_per_frame(self.handle)
+
+    def profile(self, enable):
+        if lib().rnnoise_batch_profile(self.handle, 1 if enable else 0) != 0:
+            raise RuntimeError("rnnoise_batch_profile failed")
+
+    def profile_read(self):
+        """-> (dict kernel name -> total ms, frames profiled)"""
+        n = self.launches_per_frame
+        ms = (C.c_float * n)(); names = (C.c_char_p * n)(); frames = C.c_int(0)
+        if lib().rnnoise_batch_profile_read(self.handle, ms, names, n, C.byref(frames)) != n:
+            raise RuntimeError("rnnoise_batch_profile_read failed")
+        return {names[i].decode(): float(ms[i]) for i in range(n)}, frames.value
 
     def debug(self, what, stream):
         buf = np.empty(2048, np.float32)

@@ -269,13 +269,16 @@ HD void analysis_stream(float *sm, const AnalysisArgs a, const DspTables *T) {
       a.band_out[tid] = ex; a.band_out[32 + tid] = ep; a.band_out[64 + tid] = exp_;
     }
   PHASE_END
-  // -- log-energy floor follower + silence test (denoise.c:380-393)
+  // -- log-energy floor follower + silence test (denoise.c:380-393): the 32 log10() are independent
+  //    (one lane each); only the follower itself is a serial chain.
+  PHASE_BEGIN
+    if (tid < NB_BANDS) misc[MI_LY + tid] = (float)log10(1e-2 + misc[MI_E + tid]);
+  PHASE_END
   PHASE_BEGIN
     if (tid == 0) {
       float logMax = -2, follow = -2, E = 0;
       for (int i = 0; i < NB_BANDS; i++) {
-        float ex = misc[MI_E + i];
-        float ly = (float)log10(1e-2 + ex);
+        float ly = misc[MI_LY + i];
         double f15 = follow - 1.5;
         double m1 = RMAX(f15, ly);
         float lm7 = logMax - 7;
@@ -283,7 +286,7 @@ HD void analysis_stream(float *sm, const AnalysisArgs a, const DspTables *T) {
         logMax = RMAX(logMax, ly);
         follow = (float)RMAX(f15, ly);
         misc[MI_LY + i] = ly;
-        E += ex;
+        E += misc[MI_E + i];
       }
       int silent = E < 0.04;
       mi[3] = silent;

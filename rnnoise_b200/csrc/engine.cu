@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTab
 }
 
 // ------------------------------------------------------------------------------------------------
+#define NKERNELS 9
 struct B200Engine {
   int device;
   Arena a;
@@ -127,7 +128,13 @@ struct B200Engine {
   long long frames;                 // host mirror of the device frame counter
   std::vector<void *> allocs;
   float *stage_in, *stage_out, *stage_vad;   // device staging for the host-buffer call
+  // optional per-kernel timing (rnnoise_batch_profile)
+  int profiling, prof_frames;
+  cudaEvent_t ev[NKERNELS + 1];
+  double prof_ms[NKERNELS];
 };
+static const char *const kKernelNames[NKERNELS] = {"k_biquad", "k_analysis", "k_conv1", "k_conv2", "k_gru[0]",
+                                                   "k_gru[1]", "k_gru[2]", "k_heads", "k_synthesis"};
 
 template <typename T>
 static T *dalloc(B200Engine *e, size_t n, bool zero = true) {
@@ -175,6 +182,7 @@ extern "C" void b200_engine_destroy(B200Engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->own_stream) { cudaStreamSynchronize(e->own_stream); cudaStreamDestroy(e->own_stream); }
+  for (int i = 0; i <= NKERNELS; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   for (void *p : e->allocs) cudaFree(p);
   delete e;
 }
@@ -195,6 +203,8 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   e->device = device;
   e->frames = 0;
   e->own_stream = nullptr;
+  e->profiling = 0; e->prof_frames = 0;
+  for (int i = 0; i <= NKERNELS; i++) e->ev[i] = nullptr;
   if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return nullptr; }
   e->stream = e->own_stream;
   Arena &a = e->a;
@@ -242,7 +252,7 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
 }
 
 extern "C" int b200_engine_streams(const B200Engine *e) { return e ? e->a.S : 0; }
-extern "C" int b200_engine_launches_per_frame(const B200Engine *) { return 9; }
+extern "C" int b200_engine_launches_per_frame(const B200Engine *) { return NKERNELS; }
 
 extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float *d_in, float *d_vad) {
   if (!e || !d_out || !d_in) return -1;
@@ -257,21 +267,41 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
     h_new[l] = a.hbuf + ((size_t)par * 3 + l) * hstride;
     h_old[l] = a.hbuf + ((size_t)(par ^ 1) * 3 + l) * hstride;
   }
+  int ki = 0;
+#define MARK() do { if (e->profiling) cudaEventRecord(e->ev[ki++], st); } while (0)
+  MARK();
   k_biquad<<<(S + 31) / 32, 32, 0, st>>>(a, d_in);
+  MARK();
   k_analysis<<<S, DSP_THREADS, SM_TOTAL * sizeof(float), st>>>(a, e->d_tables);
+  MARK();
   const int gts = (S + RNN_TS - 1) / RNN_TS;
   k_conv1<<<gts, 128, 0, st>>>(S, e->dm, a.features, a.conv1_state, a.silence, a.conv1_out);
+  MARK();
   k_conv2<<<gts, 128, RNN_TS * 2 * cond * sizeof(uint32_t), st>>>(S, e->dm, a.conv1_out, a.conv2_state, a.silence, a.conv2_out);
+  MARK();
   const size_t gsm = 2 * RNN_TS * (gru / 4) * sizeof(uint32_t);
   for (int l = 0; l < 3; l++) {
     const float *x = l == 0 ? a.conv2_out : h_new[l - 1];
     k_gru<<<dim3(gts, gru / 128), 128, gsm, st>>>(S, gru, e->dm.gru_in[l], e->dm.gru_rec[l], x, h_old[l], h_new[l], a.silence);
+    MARK();
   }
   k_heads<<<(S + HEAD_TS - 1) / HEAD_TS, 160, 0, st>>>(S, e->dm, a.conv2_out, h_new[0], h_new[1], h_new[2], a.silence,
                                                       a.gains, a.vad, d_vad);
+  MARK();
   k_synthesis<<<S, DSP_THREADS, SS_TOTAL * sizeof(float), st>>>(a, e->d_tables, d_out);
+  MARK();
+#undef MARK
   CK(cudaGetLastError());
   e->frames++;
+  if (e->profiling) {
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < NKERNELS; i++) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]));
+      e->prof_ms[i] += ms;
+    }
+    e->prof_frames++;
+  }
   return 0;
 }
 
@@ -300,6 +330,29 @@ extern "C" int b200_engine_set_stream(B200Engine *e, void *cuda_stream) {
   CK(cudaStreamSynchronize(e->stream));
   e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
   return 0;
+}
+
+extern "C" int b200_engine_profile(B200Engine *e, int enable) {
+  if (!e) return -1;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  if (enable) {
+    for (int i = 0; i <= NKERNELS; i++) if (!e->ev[i]) CK(cudaEventCreate(&e->ev[i]));
+    for (int i = 0; i < NKERNELS; i++) e->prof_ms[i] = 0.0;
+    e->prof_frames = 0;
+  }
+  e->profiling = enable ? 1 : 0;
+  return 0;
+}
+
+extern "C" int b200_engine_profile_read(B200Engine *e, float *ms, const char **names, int capacity, int *frames) {
+  if (!e || !ms || capacity < NKERNELS) return -1;
+  for (int i = 0; i < NKERNELS; i++) {
+    ms[i] = (float)e->prof_ms[i];
+    if (names) names[i] = kKernelNames[i];
+  }
+  if (frames) *frames = e->prof_frames;
+  return NKERNELS;
 }
 
 extern "C" int b200_engine_reset_stream(B200Engine *e, int s) {

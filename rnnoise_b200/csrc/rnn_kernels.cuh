@@ -233,55 +233,65 @@ __global__ void __launch_bounds__(128) k_gru(int S, int gru, DevLayerQ wi, DevLa
 
 // ------------------------------------------------------------------------------------------------
 // Output heads on cat = [conv2_out | gru1 | gru2 | gru3] (rnn.c:53-57): dense_out (32, sigmoid;
-// sequential FMA chain) and vad_dense (1, sigmoid; the reference's scalar tail multiplies and adds
-// separately, vec_avx.h:731-735).  grid = ceil(S / 32), block = 160 (4 warps dense + 1 warp vad).
+// sequential FMA chain over the 4*gru inputs) and vad_dense (1, sigmoid; the reference's scalar
+// tail multiplies and adds separately, vec_avx.h:731-735).
+// grid = ceil(S / 16), block = 160: warps 0..3 own 4 streams each (lane = output, 4 accumulator
+// chains per thread), warp 4 runs the 16 VAD chains (lane = stream).  Activations and weights are
+// staged through shared memory in chunks of 128 inputs so the FMA chains only wait on LDS.
 // ------------------------------------------------------------------------------------------------
-#define HEAD_TS 32
+#define HEAD_TS 16
 #define HEAD_KC 128
+#define HEAD_XS (HEAD_KC + 4)
 __global__ void __launch_bounds__(160) k_heads(int S, DevModel m, const float *__restrict__ c2,
                                                const float *__restrict__ g1, const float *__restrict__ g2,
                                                const float *__restrict__ g3, const int *__restrict__ silence,
                                                float *__restrict__ gains, float *__restrict__ vad,
                                                float *__restrict__ vad_user) {
-  __shared__ float xs[HEAD_TS][HEAD_KC + 1];
+  __shared__ __align__(16) float xs[HEAD_TS][HEAD_XS];
+  __shared__ __align__(16) float ws[HEAD_KC][NB_GAINS];
+  __shared__ float wv[HEAD_KC];
   const int s0 = blockIdx.x * HEAD_TS, tid = threadIdx.x, gru = m.gru, K = 4 * gru;
   const int o = tid & 31, sg = tid >> 5;
-  float acc[8];
-#pragma unroll
-  for (int q = 0; q < 8; q++) acc[q] = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   float y = 0.f;
-  for (int c0 = 0; c0 < K; c0 += HEAD_KC) {
+  for (int c0 = 0; c0 < K; c0 += HEAD_KC) {   // gru % 128 == 0, so a chunk never straddles two sources
+    const int src = c0 / gru, off = c0 % gru;
+    const float *p = src == 0 ? c2 : src == 1 ? g1 : src == 2 ? g2 : g3;
     __syncthreads();
-    for (int idx = tid; idx < HEAD_TS * HEAD_KC; idx += 160) {
-      int s = idx / HEAD_KC, kk = c0 + idx % HEAD_KC;
-      float v = 0.f;
-      if (s0 + s < S && kk < K) {
-        int src = kk / gru, off = kk % gru;
-        const float *p = src == 0 ? c2 : src == 1 ? g1 : src == 2 ? g2 : g3;
-        v = p[(size_t)(s0 + s) * gru + off];
-      }
-      xs[s][idx % HEAD_KC] = v;
+    for (int idx = tid; idx < HEAD_TS * HEAD_KC / 4; idx += 160) {
+      int s = idx / (HEAD_KC / 4), k4 = idx % (HEAD_KC / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s0 + s < S) v = *(const float4 *)&p[(size_t)(s0 + s) * gru + off + 4 * k4];
+      *(float4 *)&xs[s][4 * k4] = v;
     }
+    for (int idx = tid; idx < HEAD_KC * NB_GAINS / 4; idx += 160)
+      ((float4 *)&ws[0][0])[idx] = __ldg((const float4 *)&m.dense_out.w[(size_t)c0 * NB_GAINS] + idx);
+    if (tid < HEAD_KC) wv[tid] = __ldg(&m.vad_dense.w[c0 + tid]);
     __syncthreads();
-    const int kn = min(HEAD_KC, K - c0);
     if (sg < 4) {
-      for (int kk = 0; kk < kn; kk++) {
-        float w = __ldg(&m.dense_out.w[(size_t)(c0 + kk) * NB_GAINS + o]);
-#pragma unroll
-        for (int q = 0; q < 8; q++) acc[q] = fmaf(w, xs[sg * 8 + q][kk], acc[q]);
+#pragma unroll 4
+      for (int kk = 0; kk < HEAD_KC; kk += 4) {
+        float4 x0 = *(const float4 *)&xs[sg * 4 + 0][kk], x1 = *(const float4 *)&xs[sg * 4 + 1][kk];
+        float4 x2 = *(const float4 *)&xs[sg * 4 + 2][kk], x3 = *(const float4 *)&xs[sg * 4 + 3][kk];
+        float w0 = ws[kk][o], w1 = ws[kk + 1][o], w2 = ws[kk + 2][o], w3 = ws[kk + 3][o];
+        acc[0] = fmaf(w0, x0.x, acc[0]); acc[1] = fmaf(w0, x1.x, acc[1]); acc[2] = fmaf(w0, x2.x, acc[2]); acc[3] = fmaf(w0, x3.x, acc[3]);
+        acc[0] = fmaf(w1, x0.y, acc[0]); acc[1] = fmaf(w1, x1.y, acc[1]); acc[2] = fmaf(w1, x2.y, acc[2]); acc[3] = fmaf(w1, x3.y, acc[3]);
+        acc[0] = fmaf(w2, x0.z, acc[0]); acc[1] = fmaf(w2, x1.z, acc[1]); acc[2] = fmaf(w2, x2.z, acc[2]); acc[3] = fmaf(w2, x3.z, acc[3]);
+        acc[0] = fmaf(w3, x0.w, acc[0]); acc[1] = fmaf(w3, x1.w, acc[1]); acc[2] = fmaf(w3, x2.w, acc[2]); acc[3] = fmaf(w3, x3.w, acc[3]);
       }
-    } else {
-      for (int kk = 0; kk < kn; kk++) y = y + __ldg(&m.vad_dense.w[c0 + kk]) * xs[o][kk];
+    } else if (o < HEAD_TS) {
+#pragma unroll 8
+      for (int kk = 0; kk < HEAD_KC; kk++) y = y + wv[kk] * xs[o][kk];
     }
   }
   if (sg < 4) {
     const float b = m.dense_out.bias[o];
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      int s = s0 + sg * 8 + q;
+    for (int q = 0; q < 4; q++) {
+      int s = s0 + sg * 4 + q;
       if (s < S) gains[(size_t)s * NB_GAINS + o] = act_sigmoid(acc[q] + b);
     }
-  } else {
+  } else if (o < HEAD_TS) {
     int s = s0 + o;
     if (s < S) {
       float v = silence[s] ? 0.f : act_sigmoid(y + m.vad_dense.bias[0]);

@@ -129,6 +129,10 @@ int rnnoise_batch_sync(RNNoiseBatch *b) { return b ? b200_engine_sync(b->engine)
 int rnnoise_batch_set_stream(RNNoiseBatch *b, void *s) { return b ? b200_engine_set_stream(b->engine, s) : -1; }
 int rnnoise_batch_reset_stream(RNNoiseBatch *b, int s) { return b ? b200_engine_reset_stream(b->engine, s) : -1; }
 int rnnoise_batch_launches_per_frame(const RNNoiseBatch *b) { return b ? b200_engine_launches_per_frame(b->engine) : 0; }
+int rnnoise_batch_profile(RNNoiseBatch *b, int enable) { return b ? b200_engine_profile(b->engine, enable) : -1; }
+int rnnoise_batch_profile_read(RNNoiseBatch *b, float *ms, const char **names, int capacity, int *frames) {
+  return b ? b200_engine_profile_read(b->engine, ms, names, capacity, frames) : -1;
+}
 int rnnoise_batch_debug_read(RNNoiseBatch *b, int what, int stream, float *dst, int capacity) {
   return b ? b200_engine_debug_read(b->engine, what, stream, dst, capacity) : -1;
 }
