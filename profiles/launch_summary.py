@@ -1,0 +1,25 @@
+#!/usr/bin/env python3
+"""Summarise an ncu launch list (`--metrics gpu__time_duration.sum --csv`): per-kernel mean duration
+and share of the step.  usage: python profiles/launch_summary.py launches.csv"""
+import collections
+import csv
+import sys
+
+rows = list(csv.reader(open(sys.argv[1])))
+hdr = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
+H = rows[hdr]
+ki, vi, ui = H.index('Kernel Name'), H.index('Metric Value'), H.index('Metric Unit')
+d = collections.OrderedDict()
+for r in rows[hdr + 1:]:
+    if len(r) <= vi:
+        continue
+    v = float(r[vi].replace(',', ''))
+    v = v / 1e3 if r[ui] == 'ns' else v * 1e3 if r[ui] == 'ms' else v
+    d.setdefault(r[ki].split('(')[0], []).append(v)
+per_step = {k: sum(v) / len(v) * (3 if k == 'k_gru' or k == 'k_gru_tc' else 1) for k, v in d.items() if k.startswith('k_')}
+tot = sum(per_step.values())
+print(f"{'kernel':16s} {'launches':>8s} {'mean us':>10s} {'us/step':>10s} {'share':>7s}")
+for k, v in d.items():
+    if k.startswith('k_'):
+        print(f"{k:16s} {len(v):8d} {sum(v)/len(v):10.1f} {per_step[k]:10.1f} {per_step[k]/tot:7.1%}")
+print(f"{'sum':16s} {'':8s} {'':10s} {tot:10.1f}")

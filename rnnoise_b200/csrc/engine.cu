@@ -17,6 +17,7 @@
 #include "dsp_tables.hpp"
 #include "engine.h"
 #include "rnn_kernels.cuh"
+#include "gru_tc.cuh"
 
 #define CK(call)                                                                          \
   do {                                                                                    \
@@ -46,6 +47,8 @@ struct Arena {
   float *conv1_state;  // [S][130]
   float *conv2_state;  // [S][2*cond]
   float *hbuf;         // [2][3][S][gru] ping-pong GRU states
+  uint8_t *hbuf_u8;    // [2][3][S][gru] their u8 = 127 + rne(127 h) mirrors (tensor-core A operands)
+  uint8_t *conv2_out_u8; // [S][gru]
   // per-frame scratch
   float *xb;           // [S][480]
   float *features;     // [S][65]
@@ -128,6 +131,8 @@ struct B200Engine {
   long long frames;                 // host mirror of the device frame counter
   std::vector<void *> allocs;
   float *stage_in, *stage_out, *stage_vad;   // device staging for the host-buffer call
+  int use_tc;                       // tcgen05 GRU path (default) or the dp4a cross-check kernel
+  GruTcMaps tc_maps[2][3];          // [frame parity][layer]
   // optional per-kernel timing (rnnoise_batch_profile)
   int profiling, prof_frames;
   cudaEvent_t ev[NKERNELS + 1];
@@ -178,6 +183,50 @@ static int upload_f(B200Engine *e, DevLayerF *d, const B200Layer *l) {
   return (d->w && d->bias) ? 0 : -1;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor maps for the tensor-core GRU (gru_tc.cuh).  cuTensorMapEncodeTiled is fetched through
+// the runtime (no link-time dependency on libcuda).
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// row-major bytes [rows][K], box = [box_rows][128 B], 128B swizzle
+static int make_map_u8(CUtensorMap *m, const void *base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {K, rows};
+  cuuint64_t strides[1] = {K};
+  cuuint32_t box[2] = {TC_KATOM, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -1;
+}
+// dense s8 [3*gru][K] (rows = z|r|n outputs) -> [gru/32 slices][3 gates][32 units][K]: the 96 B-operand
+// rows of one unit slice become contiguous
+static const signed char *upload_permuted(B200Engine *e, const B200Layer *l, int gru) {
+  const int K = l->nb_in;
+  std::vector<signed char> p((size_t)3 * gru * K);
+  for (int sl = 0; sl < gru / TC_UNITS; sl++)
+    for (int g = 0; g < 3; g++)
+      for (int u = 0; u < TC_UNITS; u++)
+        memcpy(&p[(((size_t)sl * 3 + g) * TC_UNITS + u) * K], l->w8 + (size_t)(g * gru + sl * TC_UNITS + u) * K, K);
+  return upload<signed char>(e, p.data(), p.size());
+}
+
 extern "C" void b200_engine_destroy(B200Engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
@@ -222,6 +271,9 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   ok &= !!(a.conv1_state = dalloc<float>(e, Ss * 2 * NB_FEATURES));
   ok &= !!(a.conv2_state = dalloc<float>(e, Ss * 2 * m->cond));
   ok &= !!(a.hbuf = dalloc<float>(e, 2 * 3 * Ss * m->gru));
+  ok &= !!(a.hbuf_u8 = dalloc<uint8_t>(e, 2 * 3 * Ss * m->gru));
+  ok &= !!(a.conv2_out_u8 = dalloc<uint8_t>(e, Ss * m->gru));
+  if (ok) ok = cudaMemset(a.hbuf_u8, 127, 2 * 3 * Ss * m->gru) == cudaSuccess;   // u8 image of h = 0
   ok &= !!(a.xb = dalloc<float>(e, Ss * FRAME_SIZE));
   ok &= !!(a.features = dalloc<float>(e, Ss * NB_FEATURES));
   ok &= !!(a.silence = dalloc<int>(e, Ss));
@@ -243,6 +295,25 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
        upload_f(e, &dm.vad_dense, &m->vad_dense) == 0 && upload_q(e, &dm.conv2, &m->conv2) == 0;
   for (int k = 0; k < 3 && ok; k++)
     ok = upload_q(e, &dm.gru_in[k], &m->gru_in[k]) == 0 && upload_q(e, &dm.gru_rec[k], &m->gru_rec[k]) == 0;
+  // tensor-core GRU path: permuted weights + TMA maps for both frame parities
+  const char *gk = getenv("RNNOISE_B200_GRU_KERNEL");
+  e->use_tc = !(gk && !strcmp(gk, "dp4a"));
+  if (ok && e->use_tc) {
+    const size_t hs = Ss * m->gru;
+    for (int l = 0; l < 3 && ok; l++) {
+      const signed char *wi = upload_permuted(e, &m->gru_in[l], m->gru), *wr = upload_permuted(e, &m->gru_rec[l], m->gru);
+      ok = wi && wr;
+      for (int par = 0; par < 2 && ok; par++) {
+        GruTcMaps &mp = e->tc_maps[par][l];
+        const uint8_t *x = l == 0 ? a.conv2_out_u8 : a.hbuf_u8 + ((size_t)par * 3 + l - 1) * hs;
+        const uint8_t *h = a.hbuf_u8 + ((size_t)(par ^ 1) * 3 + l) * hs;
+        ok = make_map_u8(&mp.x, x, S, m->gru, TC_M) == 0 && make_map_u8(&mp.h, h, S, m->gru, TC_M) == 0 &&
+             make_map_u8(&mp.wi, wi, 3 * m->gru, m->gru, TC_N) == 0 && make_map_u8(&mp.wr, wr, 3 * m->gru, m->gru, TC_N) == 0;
+      }
+    }
+    ok = ok && cudaFuncSetAttribute(k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, gru_tc_smem_bytes(m->gru)) == cudaSuccess;
+    if (!ok) fprintf(stderr, "[rnnoise_b200] tensor-core GRU setup failed\n");
+  }
   if (!ok || cudaDeviceSynchronize() != cudaSuccess) {
     fprintf(stderr, "[rnnoise_b200] engine allocation/upload failed: %s\n", cudaGetErrorString(cudaGetLastError()));
     b200_engine_destroy(e);
@@ -277,12 +348,18 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
   const int gts = (S + RNN_TS - 1) / RNN_TS;
   k_conv1<<<gts, 128, 0, st>>>(S, e->dm, a.features, a.conv1_state, a.silence, a.conv1_out);
   MARK();
-  k_conv2<<<gts, 128, RNN_TS * 2 * cond * sizeof(uint32_t), st>>>(S, e->dm, a.conv1_out, a.conv2_state, a.silence, a.conv2_out);
+  k_conv2<<<gts, 128, RNN_TS * 2 * cond * sizeof(uint32_t), st>>>(S, e->dm, a.conv1_out, a.conv2_state, a.silence, a.conv2_out, a.conv2_out_u8);
   MARK();
   const size_t gsm = 2 * RNN_TS * (gru / 4) * sizeof(uint32_t);
   for (int l = 0; l < 3; l++) {
-    const float *x = l == 0 ? a.conv2_out : h_new[l - 1];
-    k_gru<<<dim3(gts, gru / 128), 128, gsm, st>>>(S, gru, e->dm.gru_in[l], e->dm.gru_rec[l], x, h_old[l], h_new[l], a.silence);
+    uint8_t *hu8_new = a.hbuf_u8 + ((size_t)par * 3 + l) * hstride;
+    if (e->use_tc) {
+      k_gru_tc<<<dim3((S + TC_M - 1) / TC_M, gru / TC_UNITS), 160, gru_tc_smem_bytes(gru), st>>>(
+          S, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, a.silence);
+    } else {
+      const float *x = l == 0 ? a.conv2_out : h_new[l - 1];
+      k_gru<<<dim3(gts, gru / 128), 128, gsm, st>>>(S, gru, e->dm.gru_in[l], e->dm.gru_rec[l], x, h_old[l], h_new[l], hu8_new, a.silence);
+    }
     MARK();
   }
   k_heads<<<(S + HEAD_TS - 1) / HEAD_TS, 160, 0, st>>>(S, e->dm, a.conv2_out, h_new[0], h_new[1], h_new[2], a.silence,
@@ -368,6 +445,7 @@ extern "C" int b200_engine_reset_stream(B200Engine *e, int s) {
   ZERO(a.spec, 4 * FREQ_SIZE, 2) ZERO(a.band, 96, 2) ZERO(a.lastg, NB_BANDS, 1) ZERO(a.pitch_state, 2, 1)
   ZERO(a.conv1_state, 2 * NB_FEATURES, 1) ZERO(a.conv2_state, 2 * a.cond, 1) ZERO(a.hbuf, a.gru, 6)
 #undef ZERO
+  for (int c = 0; c < 6; c++) CK(cudaMemsetAsync(a.hbuf_u8 + ((size_t)c * S + s) * a.gru, 127, a.gru, st));
   CK(cudaStreamSynchronize(st));
   return 0;
 }

@@ -1,0 +1,233 @@
+// gru_tc.cuh -- one GRU layer for 128 streams x 32 hidden units per CTA on the 5th-gen tensor cores.
+//
+//   D_in [128 x 96] = Xu8[128 x K] . Wi_slice^T      (u8 x s8 -> s32, tcgen05.mma kind::i8)
+//   D_rec[128 x 96] = Hu8[128 x K] . Wr_slice^T      96 = {z, r, n} x 32 units, K = gru (384)
+//
+// Operands arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B, K-major) straight from the u8 mirrors
+// of the activations / the pre-permuted s8 weights; both accumulators live in TMEM (192 of 256
+// allocated columns); one elected thread issues the 2 x (K/32) MMAs and commits to an mbarrier;
+// the four epilogue warps read their TMEM lane quarter with tcgen05.ld and apply, in registers,
+// exactly the arithmetic of the reference (compute_linear + compute_generic_gru, src/nnet_arch.h:
+// 130-162, src/nnet.c:65-94): (float)acc*scale + subias, fma(diag,h,.), sigmoid/sigmoid/tanh,
+// h' = z*h + (1-z)*n, then store h' as fp32 AND as the u8 operand of the next consumer.
+// The integer accumulators are exact, so this kernel is bit-identical to the dp4a kernel k_gru.
+//
+// grid = (ceil(S/128), gru/32), block = 160 (warps 0..3 epilogue, warp 4 = TMA + MMA issuer),
+// dynamic smem = GRU_TC_SMEM bytes, 1 CTA / SM.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rnn_kernels.cuh"
+
+#define TC_M 128          // streams per CTA (UMMA M)
+#define TC_UNITS 32       // hidden units per CTA
+#define TC_N (3 * TC_UNITS)  // UMMA N = 96
+#define TC_KATOM 128      // bytes of K per 128B-swizzle atom
+#define TC_TMEM_COLS 256  // power of two >= 2 * TC_N
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a lost transaction (bad tensor map / byte count) becomes a trap -> CUDA error on the
+// host instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO(=1)<<16 | SBO(1024>>4)<<32 | version 1 <<46 | SW128(2)<<61)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor for kind::i8: D = S32, A = U8, B = S8, both K-major
+__device__ __forceinline__ uint32_t umma_idesc_i8(int M, int N) {
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct GruTcMaps {
+  CUtensorMap x, h, wi, wr;   // x,h: u8 [S][K]; wi,wr: s8 [(K/32 slices) * 96][K] permuted
+};
+
+// smem: A tiles (X, H): 2 x (K/128) x 16 KB ; B tiles (Wi, Wr): 2 x (K/128) x 12 KB ; params ; barriers
+#define TC_A_ATOM_BYTES (TC_M * TC_KATOM)     // 16384
+#define TC_B_ATOM_BYTES (TC_N * TC_KATOM)     // 12288
+__host__ __device__ constexpr int gru_tc_smem_bytes(int gru) {
+  return 1024 /*align slack*/ + 2 * (gru / TC_KATOM) * (TC_A_ATOM_BYTES + TC_B_ATOM_BYTES) + 15 * TC_UNITS * 4 + 64;
+}
+
+__global__ void __launch_bounds__(160, 1)
+k_gru_tc(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, DevLayerQ wr,
+         const float *__restrict__ h_old, float *__restrict__ h_new, uint8_t *__restrict__ h_new_u8,
+         const int *__restrict__ silence) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * TC_M, j0 = blockIdx.y * TC_UNITS, natoms = gru / TC_KATOM;
+  // 1024-byte aligned operand area (SWIZZLE_128B requirement)
+  uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *sAx = base, *sAh = sAx + natoms * TC_A_ATOM_BYTES;
+  uint8_t *sBi = sAh + natoms * TC_A_ATOM_BYTES, *sBr = sBi + natoms * TC_B_ATOM_BYTES;
+  float *prm = (float *)(sBr + natoms * TC_B_ATOM_BYTES);       // [15][32]
+  uint64_t *bars = (uint64_t *)(prm + 15 * TC_UNITS);           // [0] operands landed, [1] MMAs done
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2);
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+
+  if (tid == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {   // TMEM allocation is warp-wide; the same warp frees it at the end
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // epilogue parameters of this unit slice: [g] scale_i, subias_i, scale_r, subias_r, diag
+  for (int i = tid; i < 15 * TC_UNITS; i += blockDim.x) {
+    int which = i / (3 * TC_UNITS), g = (i / TC_UNITS) % 3, u = i % TC_UNITS;
+    const float *src = which == 0 ? wi.scale : which == 1 ? wi.subias : which == 2 ? wr.scale : which == 3 ? wr.subias : wr.diag;
+    prm[i] = src[g * gru + j0 + u];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- TMA producer: everything this CTA needs, one transaction barrier ----
+      mbar_expect_tx(bar_full, (uint32_t)(2 * natoms * (TC_A_ATOM_BYTES + TC_B_ATOM_BYTES)));
+      for (int a = 0; a < natoms; a++) {
+        tma_load_2d(smem_u32(sAx + a * TC_A_ATOM_BYTES), &maps.x, bar_full, a * TC_KATOM, m0);
+        tma_load_2d(smem_u32(sBi + a * TC_B_ATOM_BYTES), &maps.wi, bar_full, a * TC_KATOM, blockIdx.y * TC_N);
+      }
+      for (int a = 0; a < natoms; a++) {
+        tma_load_2d(smem_u32(sAh + a * TC_A_ATOM_BYTES), &maps.h, bar_full, a * TC_KATOM, m0);
+        tma_load_2d(smem_u32(sBr + a * TC_B_ATOM_BYTES), &maps.wr, bar_full, a * TC_KATOM, blockIdx.y * TC_N);
+      }
+      // ---- MMA issuer ----
+      mbar_wait(bar_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t idesc = umma_idesc_i8(TC_M, TC_N);
+      for (int g = 0; g < 2; g++) {
+        const uint8_t *A = g ? sAh : sAx, *B = g ? sBr : sBi;
+        for (int a = 0; a < natoms; a++) {
+          const uint64_t ad = umma_desc_sw128(smem_u32(A + a * TC_A_ATOM_BYTES));
+          const uint64_t bd = umma_desc_sw128(smem_u32(B + a * TC_B_ATOM_BYTES));
+#pragma unroll
+          for (int k = 0; k < TC_KATOM / 32; k++)   // UMMA K = 32 bytes; advance inside the swizzle atom
+            umma_i8(tmem + g * TC_N, ad + (uint64_t)(k * 32 >> 4), bd + (uint64_t)(k * 32 >> 4), idesc, (a | k) ? 1u : 0u);
+        }
+      }
+      umma_commit(bar_mma);   // implies tcgen05.fence::before_thread_sync
+    }
+  } else {
+    // ---- epilogue warps: thread = stream row (TMEM lane 32*warp + lane) ----
+    const int s = m0 + warp * 32 + lane;
+    const bool live = s < S;
+    const bool silent = live ? silence[s] != 0 : true;
+    float hrow[TC_UNITS];
+    if (live) {
+#pragma unroll
+      for (int q = 0; q < TC_UNITS / 4; q++) {
+        float4 v = *(const float4 *)&h_old[(size_t)s * gru + j0 + 4 * q];
+        hrow[4 * q] = v.x; hrow[4 * q + 1] = v.y; hrow[4 * q + 2] = v.z; hrow[4 * q + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < TC_UNITS; q++) hrow[q] = 0.f;
+    }
+    mbar_wait(bar_mma, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      int az[16], ar[16], an[16], bz[16], br[16], bn[16];
+      const int c = half * 16;
+      tmem_ld16(trow + 0 * TC_UNITS + c, az); tmem_ld16(trow + 1 * TC_UNITS + c, ar); tmem_ld16(trow + 2 * TC_UNITS + c, an);
+      tmem_ld16(trow + TC_N + 0 * TC_UNITS + c, bz); tmem_ld16(trow + TC_N + 1 * TC_UNITS + c, br); tmem_ld16(trow + TC_N + 2 * TC_UNITS + c, bn);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float outv[16];
+#pragma unroll
+      for (int q = 0; q < 16; q++) {
+        const int u = c + q;
+        const float h = hrow[u];
+        float out = h;
+        if (!silent) {
+          float zi = (float)az[q] * prm[(0 * 3 + 0) * TC_UNITS + u] + prm[(1 * 3 + 0) * TC_UNITS + u];
+          float ri = (float)ar[q] * prm[(0 * 3 + 1) * TC_UNITS + u] + prm[(1 * 3 + 1) * TC_UNITS + u];
+          float ni = (float)an[q] * prm[(0 * 3 + 2) * TC_UNITS + u] + prm[(1 * 3 + 2) * TC_UNITS + u];
+          float zr = fmaf(prm[(4 * 3 + 0) * TC_UNITS + u], h, (float)bz[q] * prm[(2 * 3 + 0) * TC_UNITS + u] + prm[(3 * 3 + 0) * TC_UNITS + u]);
+          float rr = fmaf(prm[(4 * 3 + 1) * TC_UNITS + u], h, (float)br[q] * prm[(2 * 3 + 1) * TC_UNITS + u] + prm[(3 * 3 + 1) * TC_UNITS + u]);
+          float nr = fmaf(prm[(4 * 3 + 2) * TC_UNITS + u], h, (float)bn[q] * prm[(2 * 3 + 2) * TC_UNITS + u] + prm[(3 * 3 + 2) * TC_UNITS + u]);
+          float z = act_sigmoid(zi + zr);
+          float r = act_sigmoid(ri + rr);
+          float n = act_tanh(ni + nr * r);
+          out = z * h + (1 - z) * n;
+        }
+        outv[q] = out;
+      }
+      if (live) {
+        float *dst = &h_new[(size_t)s * gru + j0 + c];
+#pragma unroll
+        for (int q = 0; q < 4; q++) *(float4 *)&dst[4 * q] = make_float4(outv[4 * q], outv[4 * q + 1], outv[4 * q + 2], outv[4 * q + 3]);
+        uint4 pk;
+        pk.x = quant4(outv[0], outv[1], outv[2], outv[3]);
+        pk.y = quant4(outv[4], outv[5], outv[6], outv[7]);
+        pk.z = quant4(outv[8], outv[9], outv[10], outv[11]);
+        pk.w = quant4(outv[12], outv[13], outv[14], outv[15]);
+        *(uint4 *)&h_new_u8[(size_t)s * gru + j0 + c] = pk;
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+  }
+}

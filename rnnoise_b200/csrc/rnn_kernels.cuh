@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *_
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_conv2(int S, DevModel m, const float *__restrict__ conv1_out,
                                                float *conv2_state, const int *__restrict__ silence,
-                                               float *__restrict__ conv2_out) {
+                                               float *__restrict__ conv2_out, uint8_t *__restrict__ conv2_out_u8) {
   extern __shared__ uint32_t u_sm[];   // [RNN_TS][K/4]
   const int K = 3 * m.cond, K4 = K / 4, s0 = blockIdx.x * RNN_TS, tid = threadIdx.x;
   for (int idx = tid; idx < RNN_TS * K4; idx += 128) {
@@ -137,7 +137,11 @@ __global__ void __launch_bounds__(128) k_conv2(int S, DevModel m, const float *_
     const float sc = m.conv2.scale[o], sb = m.conv2.subias[o];
 #pragma unroll
     for (int s = 0; s < RNN_TS; s++)
-      if (s0 + s < S) conv2_out[(size_t)(s0 + s) * m.gru + o] = act_tanh((float)acc[s] * sc + sb);
+      if (s0 + s < S) {
+        float v = act_tanh((float)acc[s] * sc + sb);
+        conv2_out[(size_t)(s0 + s) * m.gru + o] = v;
+        conv2_out_u8[(size_t)(s0 + s) * m.gru + o] = (uint8_t)quant_u8(v);   // operand of the GRU-1 tensor-core GEMM
+      }
   }
   __syncthreads();
   // mem = [mem[cond:2cond] | conv1_out]
@@ -164,7 +168,8 @@ __global__ void __launch_bounds__(128) k_conv2(int S, DevModel m, const float *_
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_gru(int S, int gru, DevLayerQ wi, DevLayerQ wr,
                                              const float *__restrict__ x, const float *__restrict__ h_old,
-                                             float *__restrict__ h_new, const int *__restrict__ silence) {
+                                             float *__restrict__ h_new, uint8_t *__restrict__ h_new_u8,
+                                             const int *__restrict__ silence) {
   extern __shared__ uint32_t u_sm[];
   const int K4 = gru / 4, s0 = blockIdx.x * RNN_TS, tid = threadIdx.x;
   uint32_t *xu = u_sm, *hu = u_sm + RNN_TS * K4;
@@ -228,6 +233,7 @@ __global__ void __launch_bounds__(128) k_gru(int S, int gru, DevLayerQ wi, DevLa
       out = z * h + (1 - z) * n;
     }
     h_new[(size_t)(s0 + s) * gru + j] = out;
+    h_new_u8[(size_t)(s0 + s) * gru + j] = (uint8_t)quant_u8(out);
   }
 }
 

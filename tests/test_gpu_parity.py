@@ -198,3 +198,24 @@ def test_full_size_properties_4096_streams(rb, models_dir):
         r = port.process_frame(st, base[f, 5])
         assert np.array_equal(bits(out[64 * 40 + 5]), bits(r["out"])) and np.float32(r["vad"]) == vad[64 * 40 + 5]
     batch.destroy(); model.free()
+
+
+def test_gru_tensor_core_path_equals_dp4a_path(rb, models_dir):
+    """The tcgen05 (u8 x s8 -> s32 in TMEM) GRU kernel and the CUDA-core dp4a kernel accumulate the same
+    exact integers, so whole-pipeline outputs and GRU states must be bit-identical; S = 300 exercises a
+    partial 128-row tile (TMA zero fill + row guards)."""
+    model = rb.Model(os.path.join(models_dir, "hot.bin"))
+    S, frames = 300, 10
+    os.environ["RNNOISE_B200_GRU_KERNEL"] = "dp4a"
+    a = rb.Batch(model, S)
+    del os.environ["RNNOISE_B200_GRU_KERNEL"]
+    b = rb.Batch(model, S)
+    pcm = batch_pcm(S, frames)
+    for f in range(frames):
+        oa, va = a.process(pcm[f])
+        ob, vb = b.process(pcm[f])
+        assert np.array_equal(bits(oa), bits(ob)) and np.array_equal(bits(va), bits(vb)), f
+        for s in (0, 127, 128, 255, 256, 299):
+            for k in ("gru1", "gru2", "gru3", "gains"):
+                assert np.array_equal(bits(a.debug(k, s)), bits(b.debug(k, s))), (k, s, f)
+    a.destroy(); b.destroy(); model.free()
