@@ -82,3 +82,18 @@ def test_product_does_not_reference_oracle():
                 if re.search(r"(#include|import|from)\s+[\"<]?\.*/?oracle", txt) or "rnnoise_port" in txt.replace("oracle/rnnoise_port.c is the executable statement", ""):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_reference_demo_links_unchanged(tmp_path):
+    """examples/rnnoise_demo.c of the reference compiles and links against our header + library
+    unmodified (build container only: needs /root/reference)."""
+    import subprocess
+    import rnnoise_b200
+    demo = "/root/reference/examples/rnnoise_demo.c"
+    if not os.path.exists(demo):
+        pytest.skip("reference tree not present")
+    exe = str(tmp_path / "rnnoise_demo")
+    r = subprocess.run(["gcc", "-DUSE_WEIGHTS_FILE", "-I", os.path.join(ROOT, "include"), demo, "-o", exe,
+                        rnnoise_b200.LIB_PATH, "-Wl,-rpath," + os.path.dirname(rnnoise_b200.LIB_PATH)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
