@@ -96,6 +96,13 @@ RNNOISE_EXPORT int rnnoise_batch_get_streams(const RNNoiseBatch *b);
  *  out, and returns after the results are in `out`/`vad`.  0 on success, -1 on a CUDA error. */
 RNNOISE_EXPORT int rnnoise_process_frame_batch(RNNoiseBatch *b, float *out, const float *in, float *vad);
 
+/** Pipelined host-buffer call: same arguments as rnnoise_process_frame_batch() but returns as soon
+ *  as the frame is enqueued.  The H2D copy, the kernels and the D2H copy of consecutive calls run on
+ *  three streams over double-buffered staging, so copy-in(n+1), compute(n) and copy-out(n-1) overlap.
+ *  `in` must stay valid and `out`/`vad` must not be read until rnnoise_batch_sync() (or a later
+ *  synchronous call) returns.  Use pinned host memory, otherwise the copies serialise. */
+RNNOISE_EXPORT int rnnoise_process_frame_batch_async(RNNoiseBatch *b, float *out, const float *in, float *vad);
+
 /** Device-buffer call: d_in/d_out/d_vad are device pointers on the batch's device (d_out may alias
  *  d_in; d_vad may be NULL).  Enqueues the frame on the batch's stream and returns without
  *  synchronising.  0 on success, -1 on a launch error. */

@@ -41,6 +41,7 @@ def lib():
         L.rnnoise_batch_destroy.argtypes = [vp]
         L.rnnoise_batch_get_streams.restype = ip; L.rnnoise_batch_get_streams.argtypes = [vp]
         L.rnnoise_process_frame_batch.restype = ip; L.rnnoise_process_frame_batch.argtypes = [vp, vp, vp, vp]
+        L.rnnoise_process_frame_batch_async.restype = ip; L.rnnoise_process_frame_batch_async.argtypes = [vp, vp, vp, vp]
         L.rnnoise_process_frame_batch_device.restype = ip; L.rnnoise_process_frame_batch_device.argtypes = [vp, vp, vp, vp]
         L.rnnoise_batch_sync.restype = ip; L.rnnoise_batch_sync.argtypes = [vp]
         L.rnnoise_batch_set_stream.restype = ip; L.rnnoise_batch_set_stream.argtypes = [vp, vp]
@@ -99,6 +100,11 @@ class Batch:
         """Host-buffer call on raw addresses (e.g. pinned torch tensors)."""
         if lib().rnnoise_process_frame_batch(self.handle, out_ptr, in_ptr, vad_ptr) != 0:
             raise RuntimeError("rnnoise_process_frame_batch failed")
+
+    def process_ptr_async(self, out_ptr, in_ptr, vad_ptr=None):
+        """Pipelined host-buffer call (pinned memory); results valid after sync()."""
+        if lib().rnnoise_process_frame_batch_async(self.handle, out_ptr, in_ptr, vad_ptr) != 0:
+            raise RuntimeError("rnnoise_process_frame_batch_async failed")
 
     def process_device(self, d_out, d_in, d_vad=None):
         """Device pointers (ints); asynchronous on the batch's stream."""

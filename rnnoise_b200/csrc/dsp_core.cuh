@@ -83,6 +83,8 @@ struct DspTables {
 #define MI_E 136    // [3][32] Ex, Ep, Exp
 #define MI_LY 232   // [32] log band energies
 static_assert(SM_LP0 + LP_SIZE <= SM_UNION_END, "lp0 overlay");
+static_assert(SM_LP % 4 == 0 && SM_X4 % 4 == 0 && SM_Y4 % 4 == 0 && SM_SYY % 4 == 0 && (SM_LP + 384) % 4 == 0,
+              "single-lane chains use 16-byte vector loads");
 
 // ------------------------------------------------------------------------------------------------
 // 960-point forward FFT stages (src/kiss_fft.c:101-316; stage order rnn_fft_impl:518-564).
@@ -270,36 +272,53 @@ HD float pitch_gain(float xy, float xx, float yy) { return (float)(xy / sqrt((do
 
 // find_best_pitch's selection scan (src/pitch.c:61-101) over precomputed running energies syy[i]
 // (= the value of Syy when lag i is examined).
-HD void best_two_scan(const float *xcorr, const float *syy, int max_pitch, int *best) {
-  float bnum0 = -1, bnum1 = -1, bden0 = 0, bden1 = 0;
-  int b0 = 0, b1 = 1;
-  for (int i = 0; i < max_pitch; i++) {
-    if (xcorr[i] > 0) {
-      float x16 = xcorr[i];
-      x16 *= 1e-12f;
-      float num = x16 * x16;
-      float Syy = syy[i];
-      if (num * bden1 > bnum1 * Syy) {
-        if (num * bden0 > bnum0 * Syy) {
-          bnum1 = bnum0; bden1 = bden0; b1 = b0;
-          bnum0 = num; bden0 = Syy; b0 = i;
-        } else {
-          bnum1 = num; bden1 = Syy; b1 = i;
-        }
+// 16-byte vector view for single-lane chains (one LDS.128 / STS.128 per four elements)
+struct alignas(16) f4 { float x, y, z, w; };
+
+// Running energy chain of find_best_pitch (pitch.c:67-68, 99-100), split so that only the truly
+// serial part runs on one lane:
+//   prefix : S = 1 + sum_{j<len} y[j]^2, added in index order (len % 4 == 0, y 16-byte aligned)
+//   running: syy[i] = S_i,  S_{i+1} = max(1, S_i + d[i]) with d[i] = y[i+len]^2 - y[i]^2 precomputed
+//            by parallel lanes into the same array (read d[i], then overwrite it with S_i).
+HD float sq_prefix(float S, const float *y, int len) {
+  for (int j = 0; j < len; j += 4) {
+    f4 v = *(const f4 *)(y + j);
+    S = S + v.x * v.x; S = S + v.y * v.y; S = S + v.z * v.z; S = S + v.w * v.w;
+  }
+  return S;
+}
+HD void syy_running_inplace(float *syy_d, float S, int max_pitch) {
+  int i = 0;
+  for (; i + 4 <= max_pitch; i += 4) {
+    f4 d = *(const f4 *)(syy_d + i), o;
+    o.x = S; S = S + d.x; S = RMAX(1, S);
+    o.y = S; S = S + d.y; S = RMAX(1, S);
+    o.z = S; S = S + d.z; S = RMAX(1, S);
+    o.w = S; S = S + d.w; S = RMAX(1, S);
+    *(f4 *)(syy_d + i) = o;
+  }
+  for (; i < max_pitch; i++) {
+    float d = syy_d[i];
+    syy_d[i] = S;
+    S = S + d; S = RMAX(1, S);
+  }
+}
+// find_best_pitch's update for one examined lag (pitch.c:71-98)
+struct Best2 { float num0, num1, den0, den1; int p0, p1; };
+HD void best2_init(Best2 &b) { b.num0 = -1; b.num1 = -1; b.den0 = 0; b.den1 = 0; b.p0 = 0; b.p1 = 1; }
+HD void best2_visit(Best2 &b, int i, float xcorr, float Syy) {
+  if (xcorr > 0) {
+    float x16 = xcorr;
+    x16 *= 1e-12f;
+    float num = x16 * x16;
+    if (num * b.den1 > b.num1 * Syy) {
+      if (num * b.den0 > b.num0 * Syy) {
+        b.num1 = b.num0; b.den1 = b.den0; b.p1 = b.p0;
+        b.num0 = num; b.den0 = Syy; b.p0 = i;
+      } else {
+        b.num1 = num; b.den1 = Syy; b.p1 = i;
       }
     }
-  }
-  best[0] = b0; best[1] = b1;
-}
-// running energy chain of find_best_pitch: syy[0] = 1 + sum_{j<len} y[j]^2 (sequential),
-// syy[i+1] = max(1, syy[i] + (y[i+len]^2 - y[i]^2))   (pitch.c:67-68, 99-100)
-HD void syy_chain(float *syy, const float *y, int len, int max_pitch) {
-  float S = 1;
-  for (int j = 0; j < len; j++) S = S + y[j] * y[j];
-  for (int i = 0; i < max_pitch; i++) {
-    syy[i] = S;
-    S += y[i + len] * y[i + len] - y[i] * y[i];
-    S = RMAX(1, S);
   }
 }
 

@@ -76,37 +76,55 @@ HD void analysis_stream(float *sm, const AnalysisArgs a, const DspTables *T) {
       lp[i] = sum;
     }
   PHASE_END
-  // -- second 2x decimation (pitch.c:305-308)
+  // -- second 2x decimation (pitch.c:305-308); the same lanes also form d[i] = y4[i+240]^2 - y4[i]^2,
+  //    the increments of find_best_pitch's running energy (pitch.c:99)
   PHASE_BEGIN
     for (int j = tid; j < 240; j += nthr) x4[j] = lp[384 + 2 * j];
     for (int j = tid; j < 388; j += nthr) y4[j] = j < 387 ? lp[2 * j] : 0.f;
+    for (int i = tid; i < 147; i += nthr) {
+      float hi = lp[2 * (i + 240)], lo = lp[2 * i];
+      syy[i] = hi * hi - lo * lo;
+    }
   PHASE_END
-  // -- coarse search: 147 lags x 240 (rnn_pitch_xcorr pitch.c:216; each lag summed in order);
-  //    one other lane runs find_best_pitch's running-energy chain concurrently.
+  // -- coarse search: 147 lags x 240 (rnn_pitch_xcorr pitch.c:216; each lag summed in order) on 30
+  //    lanes x 5 lags with a sliding register window; another warp runs the energy chain meanwhile.
   PHASE_BEGIN
     if (tid < 30) {
-      const int l0 = 5 * tid;
+      const float *yb = y4 + 5 * tid;
       float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int j = 0; j < 240; j++) {
-        float xv = x4[j];
+      float w[5];
 #pragma unroll
-        for (int q = 0; q < 5; q++) {
-          int idx = l0 + q + j;
-          float yv = idx < 388 ? y4[idx] : 0.f;
-          acc[q] = acc[q] + xv * yv;
+      for (int q = 0; q < 5; q++) w[q] = yb[q];
+      for (int j0 = 0; j0 < 240; j0 += 5) {
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          const float xv = x4[j0 + r];
+#pragma unroll
+          for (int q = 0; q < 5; q++) acc[q] = acc[q] + xv * w[(q + r) % 5];
+          const int nx = 5 * tid + j0 + r + 5;
+          w[r] = nx < 388 ? y4[nx] : 0.f;
         }
       }
 #pragma unroll
-      for (int q = 0; q < 5; q++) if (l0 + q < 147) xc[l0 + q] = acc[q];
+      for (int q = 0; q < 5; q++) if (5 * tid + q < 147) xc[5 * tid + q] = acc[q];
     } else if (tid == 32) {
-      syy_chain(syy, y4, 240, 147);
+      syy_running_inplace(syy, sq_prefix(1.f, y4, 240), 147);
     }
   PHASE_END
   PHASE_BEGIN
-    if (tid == 0) best_two_scan(xc, syy, 147, mi);
+    if (tid == 0) {
+      Best2 b2; best2_init(b2);
+      for (int i = 0; i < 147; i++) best2_visit(b2, i, xc[i], syy[i]);
+      mi[0] = b2.p0; mi[1] = b2.p1;
+    }
   PHASE_END
+  // -- xcorr := 0 (pitch.c:347) and the fine-stage increments d[i] = y[i+480]^2 - y[i]^2
   PHASE_BEGIN
-    for (int i = tid; i < 294; i += nthr) xc[i] = 0.f;
+    for (int i = tid; i < 294; i += nthr) {
+      xc[i] = 0.f;
+      float hi = lp[i + 480], lo = lp[i];
+      syy[i] = hi * hi - lo * lo;
+    }
   PHASE_END
   // -- fine search around the two coarse winners (pitch.c:344-361) + its energy chain
   PHASE_BEGIN
@@ -118,28 +136,42 @@ HD void analysis_stream(float *sm, const AnalysisArgs a, const DspTables *T) {
       if (ok) {
         const float *xl = lp + 384, *y = lp + i;
         float sum = 0.f;
+#pragma unroll 8
         for (int j = 0; j < 480; j++) sum = sum + xl[j] * y[j];
         xc[i] = RMAX(-1, sum);
       }
     } else if (tid == 32) {
-      syy_chain(syy, lp, 480, 294);
+      syy_running_inplace(syy, sq_prefix(1.f, lp, 480), 294);
     }
   PHASE_END
-  // -- pick the winner, pseudo-interpolate (pitch.c:362-384), enter the half-rate domain
+  // -- pick the winner, pseudo-interpolate (pitch.c:362-384), enter the half-rate domain.  Only lags
+  //    with xcorr > 0 can change find_best_pitch's state, and only the <= 10 searched lags are non-zero:
+  //    visit those in ascending order.  The other warps meanwhile square the samples the yy_lookup
+  //    chain of rnn_remove_doubling will need (pitch.c:454): a[i-1] = x[-i]^2, yyl[i] := x[N-i]^2.
   PHASE_BEGIN
     if (tid == 0) {
-      int best[2];
-      best_two_scan(xc, syy, 294, best);
+      const int c0 = 2 * mi[0], c1 = 2 * mi[1];
+      const int lo = c0 < c1 ? c0 : c1, hi = c0 < c1 ? c1 : c0;
+      Best2 b2; best2_init(b2);
+      for (int i = lo - 2; i <= lo + 2; i++) if (i >= 0 && i < 294) best2_visit(b2, i, xc[i], syy[i]);
+      for (int i = hi - 2; i <= hi + 2; i++) if (i > lo + 2 && i >= 0 && i < 294) best2_visit(b2, i, xc[i], syy[i]);
       int offset = 0;
-      if (best[0] > 0 && best[0] < 293) {
-        float aa = xc[best[0] - 1], bb = xc[best[0]], cc = xc[best[0] + 1];
+      if (b2.p0 > 0 && b2.p0 < 293) {
+        float aa = xc[b2.p0 - 1], bb = xc[b2.p0], cc = xc[b2.p0 + 1];
         if ((cc - aa) > .7f * (bb - aa)) offset = 1;
         else if ((aa - cc) > .7f * (bb - cc)) offset = -1;
       }
-      int pitch_index = PITCH_MAX_PERIOD - (2 * best[0] - offset);   // denoise.c:365
+      int pitch_index = PITCH_MAX_PERIOD - (2 * b2.p0 - offset);      // denoise.c:365
       int T0 = pitch_index / 2;                                       // pitch.c:441
       if (T0 >= PITCH_MAX_PERIOD / 2) T0 = PITCH_MAX_PERIOD / 2 - 1;  // :445-446
       mi[4] = T0;
+    } else if (tid >= 32) {
+      const float *x = lp + PITCH_MAX_PERIOD / 2;
+      for (int i = 1 + (tid - 32); i <= PITCH_MAX_PERIOD / 2; i += nthr - 32) {
+        float u = x[-i], v = x[PITCH_FRAME_SIZE / 2 - i];
+        x4[i - 1] = u * u;      // x4/y4 are dead after the coarse search: 384 floats fit in their 628
+        yyl[i] = v * v;
+      }
     }
   PHASE_END
   // -- all dot products rnn_remove_doubling can need, in parallel lanes (each one sequential):
@@ -174,12 +206,15 @@ HD void analysis_stream(float *sm, const AnalysisArgs a, const DspTables *T) {
         dot[tid] = s;
       }
     } else if (tid == 64) {
-      float yy = 0.f;
-      for (int i = 0; i < N; i++) yy = yy + x[i] * x[i];   // == xx, summed in the same order
+      float yy = sq_prefix(0.f, x, N);   // == xx, summed in the same order (pitch.c:449-451)
       yyl[0] = yy;
-      for (int i = 1; i <= PITCH_MAX_PERIOD / 2; i++) {
-        yy = yy + x[-i] * x[-i] - x[N - i] * x[N - i];
-        yyl[i] = RMAX(0, yy);
+      const float *a2 = x4;              // a2[i-1] = x[-i]^2, yyl[i] holds x[N-i]^2 until overwritten
+      for (int i = 1; i <= PITCH_MAX_PERIOD / 2; i += 4) {
+        f4 av = *(const f4 *)(a2 + i - 1);
+        yy = yy + av.x - yyl[i];     yyl[i] = RMAX(0, yy);
+        yy = yy + av.y - yyl[i + 1]; yyl[i + 1] = RMAX(0, yy);
+        yy = yy + av.z - yyl[i + 2]; yyl[i + 2] = RMAX(0, yy);
+        yy = yy + av.w - yyl[i + 3]; yyl[i + 3] = RMAX(0, yy);
       }
     }
   PHASE_END

@@ -130,7 +130,12 @@ struct B200Engine {
   cudaStream_t own_stream, stream;
   long long frames;                 // host mirror of the device frame counter
   std::vector<void *> allocs;
-  float *stage_in, *stage_out, *stage_vad;   // device staging for the host-buffer call
+  // host-buffer calls: double-buffered device staging, copy streams and the events that chain
+  // H2D(n) -> compute(n) -> D2H(n) while protecting slot reuse two frames later
+  float *stage_in[2], *stage_out[2], *stage_vad[2];
+  cudaStream_t s_h2d, s_d2h;
+  cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
+  long long host_frames;
   int use_tc;                       // tcgen05 GRU path (default) or the dp4a cross-check kernel
   GruTcMaps tc_maps[2][3];          // [frame parity][layer]
   // optional per-kernel timing (rnnoise_batch_profile)
@@ -232,6 +237,13 @@ extern "C" void b200_engine_destroy(B200Engine *e) {
   cudaSetDevice(e->device);
   if (e->own_stream) { cudaStreamSynchronize(e->own_stream); cudaStreamDestroy(e->own_stream); }
   for (int i = 0; i <= NKERNELS; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  if (e->s_h2d) { cudaStreamSynchronize(e->s_h2d); cudaStreamDestroy(e->s_h2d); }
+  if (e->s_d2h) { cudaStreamSynchronize(e->s_d2h); cudaStreamDestroy(e->s_d2h); }
+  for (int i = 0; i < 2; i++) {
+    if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
+    if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
+    if (e->ev_d2h[i]) cudaEventDestroy(e->ev_d2h[i]);
+  }
   for (void *p : e->allocs) cudaFree(p);
   delete e;
 }
@@ -281,9 +293,19 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   ok &= !!(a.conv2_out = dalloc<float>(e, Ss * m->gru));
   ok &= !!(a.gains = dalloc<float>(e, Ss * NB_BANDS));
   ok &= !!(a.vad = dalloc<float>(e, Ss));
-  ok &= !!(e->stage_in = dalloc<float>(e, Ss * FRAME_SIZE));
-  ok &= !!(e->stage_out = dalloc<float>(e, Ss * FRAME_SIZE));
-  ok &= !!(e->stage_vad = dalloc<float>(e, Ss));
+  e->host_frames = 0;
+  e->s_h2d = e->s_d2h = nullptr;
+  ok &= cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
+  ok &= cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2; i++) {
+    ok &= !!(e->stage_in[i] = dalloc<float>(e, Ss * FRAME_SIZE));
+    ok &= !!(e->stage_out[i] = dalloc<float>(e, Ss * FRAME_SIZE));
+    ok &= !!(e->stage_vad[i] = dalloc<float>(e, Ss));
+    e->ev_h2d[i] = e->ev_comp[i] = e->ev_d2h[i] = nullptr;
+    ok &= cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&e->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
+  }
   DspTables *ht = new DspTables();
   b200_fill_dsp_tables(ht);
   e->d_tables = (DspTables *)upload<DspTables>(e, ht, 1);
@@ -382,22 +404,41 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
   return 0;
 }
 
-extern "C" int b200_engine_frame_host(B200Engine *e, float *out, const float *in, float *vad) {
+extern "C" int b200_engine_frame_host_async(B200Engine *e, float *out, const float *in, float *vad) {
   if (!e || !out || !in) return -1;
   CK(cudaSetDevice(e->device));
   const size_t n = (size_t)e->a.S * FRAME_SIZE * sizeof(float);
-  CK(cudaMemcpyAsync(e->stage_in, in, n, cudaMemcpyHostToDevice, e->stream));
-  if (b200_engine_frame_device(e, e->stage_out, e->stage_in, e->stage_vad)) return -1;
-  CK(cudaMemcpyAsync(out, e->stage_out, n, cudaMemcpyDeviceToHost, e->stream));
-  if (vad) CK(cudaMemcpyAsync(vad, e->stage_vad, (size_t)e->a.S * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
+  const int slot = (int)(e->host_frames & 1);
+  // copy-in: the staging slot is free once frame n-2 has been computed
+  CK(cudaStreamWaitEvent(e->s_h2d, e->ev_comp[slot], 0));
+  CK(cudaMemcpyAsync(e->stage_in[slot], in, n, cudaMemcpyHostToDevice, e->s_h2d));
+  CK(cudaEventRecord(e->ev_h2d[slot], e->s_h2d));
+  // compute: needs this frame's input, and frame n-2's output staging drained
+  CK(cudaStreamWaitEvent(e->stream, e->ev_h2d[slot], 0));
+  CK(cudaStreamWaitEvent(e->stream, e->ev_d2h[slot], 0));
+  if (b200_engine_frame_device(e, e->stage_out[slot], e->stage_in[slot], e->stage_vad[slot])) return -1;
+  CK(cudaEventRecord(e->ev_comp[slot], e->stream));
+  // copy-out
+  CK(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[slot], 0));
+  CK(cudaMemcpyAsync(out, e->stage_out[slot], n, cudaMemcpyDeviceToHost, e->s_d2h));
+  if (vad) CK(cudaMemcpyAsync(vad, e->stage_vad[slot], (size_t)e->a.S * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+  CK(cudaEventRecord(e->ev_d2h[slot], e->s_d2h));
+  e->host_frames++;
+  return 0;
+}
+
+extern "C" int b200_engine_frame_host(B200Engine *e, float *out, const float *in, float *vad) {
+  if (b200_engine_frame_host_async(e, out, in, vad)) return -1;
+  CK(cudaStreamSynchronize(e->s_d2h));
   return 0;
 }
 
 extern "C" int b200_engine_sync(B200Engine *e) {
   if (!e) return -1;
   CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->s_h2d));
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->s_d2h));
   return 0;
 }
 

@@ -120,6 +120,11 @@ int rnnoise_process_frame_batch(RNNoiseBatch *b, float *out, const float *in, fl
   return b200_engine_frame_host(b->engine, out, in, vad);
 }
 
+int rnnoise_process_frame_batch_async(RNNoiseBatch *b, float *out, const float *in, float *vad) {
+  if (!b || !out || !in) return -1;
+  return b200_engine_frame_host_async(b->engine, out, in, vad);
+}
+
 int rnnoise_process_frame_batch_device(RNNoiseBatch *b, float *d_out, const float *d_in, float *d_vad) {
   if (!b || !d_out || !d_in) return -1;
   return b200_engine_frame_device(b->engine, d_out, d_in, d_vad);

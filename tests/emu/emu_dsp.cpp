@@ -18,7 +18,7 @@ struct EmuState {
   float features[NB_FEATURES], xb[FRAME_SIZE];
   int silence;
   long frames;
-  float sm[SM_TOTAL > SS_TOTAL ? SM_TOTAL : SS_TOTAL];
+  alignas(16) float sm[SM_TOTAL > SS_TOTAL ? SM_TOTAL : SS_TOTAL];
 };
 
 extern "C" {

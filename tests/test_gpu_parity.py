@@ -219,3 +219,22 @@ def test_gru_tensor_core_path_equals_dp4a_path(rb, models_dir):
             for k in ("gru1", "gru2", "gru3", "gains"):
                 assert np.array_equal(bits(a.debug(k, s)), bits(b.debug(k, s))), (k, s, f)
     a.destroy(); b.destroy(); model.free()
+
+
+def test_async_pipelined_host_call_equals_synchronous(rb, models_dir):
+    """rnnoise_process_frame_batch_async (3-stream, double-buffered H2D / compute / D2H pipeline) must
+    deliver exactly what the synchronous host call delivers, frame after frame."""
+    import torch
+    model = rb.Model(os.path.join(models_dir, "default.bin"))
+    S, frames = 500, 9
+    a, b = rb.Batch(model, S), rb.Batch(model, S)
+    pcm = torch.from_numpy(batch_pcm(S, frames)).pin_memory()
+    outs = [torch.empty(S, 480).pin_memory() for _ in range(frames)]
+    vads = [torch.empty(S).pin_memory() for _ in range(frames)]
+    for f in range(frames):
+        b.process_ptr_async(outs[f].data_ptr(), pcm[f].data_ptr(), vads[f].data_ptr())
+    b.sync()
+    for f in range(frames):
+        ro, rv = a.process(pcm[f].numpy())
+        assert np.array_equal(bits(outs[f].numpy()), bits(ro)) and np.array_equal(bits(vads[f].numpy()), bits(rv)), f
+    a.destroy(); b.destroy(); model.free()
