@@ -48,8 +48,8 @@ struct DspTables {
   cpx tw[WINDOW_SIZE];             // src/kiss_fft.c:406-420
   short bitrev[WINDOW_SIZE];       // digit reversal for radices 5,3,4,4,4
   short eband[NB_BANDS + 2];       // src/denoise.c:63-65
-  unsigned char bin_band[400];     // band whose interpolation segment holds bin k (1..31 inner)
-  float bin_frac[400];             // (float)j / band_size for that bin
+  unsigned char bin_band[400];     // triangular segment (0..32) that holds bin k
+  float bin_frac[400];             // (float)j / band_size of bin k inside its segment (denoise.c:100,148)
   float fft_scale;                 // rnnoise_tables.c:562 literal
 };
 
@@ -213,20 +213,18 @@ HD void fft_radix5(cpx *F, const DspTables *T, int tid, int nthr) { // m = 192, 
 HD float band_sum_one(int b, const cpx *A, const cpx *B, const DspTables *T) {
   float sum = 0.f;
   if (b >= 1) {
-    int e0 = T->eband[b - 1], bs = T->eband[b] - e0;
-    for (int j = 0; j < bs; j++) {
-      float frac = (float)j / bs;
-      cpx a = A[e0 + j], c = B[e0 + j];
+    for (int k = T->eband[b - 1]; k < T->eband[b]; k++) {
+      const float frac = T->bin_frac[k];      // == (float)j / band_size, tabulated (no divide in the loop)
+      cpx a = A[k], c = B[k];
       float t = a.r * c.r;
       t += a.i * c.i;
       sum += frac * t;
     }
   }
   if (b <= NB_BANDS) {
-    int e0 = T->eband[b], bs = T->eband[b + 1] - e0;
-    for (int j = 0; j < bs; j++) {
-      float frac = (float)j / bs;
-      cpx a = A[e0 + j], c = B[e0 + j];
+    for (int k = T->eband[b]; k < T->eband[b + 1]; k++) {
+      const float frac = T->bin_frac[k];
+      cpx a = A[k], c = B[k];
       float t = a.r * c.r;
       t += a.i * c.i;
       sum += (1 - frac) * t;

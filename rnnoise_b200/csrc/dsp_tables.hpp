@@ -32,7 +32,7 @@ static inline void b200_fill_dsp_tables(DspTables *t) {
     t->bitrev[i] = (short)(192 * j0 + 64 * j1 + 16 * j2 + 4 * j3 + j4);
   }
   for (int b = 0; b < NB_BANDS + 2; b++) t->eband[b] = eband[b];
-  for (int b = 1; b < NB_BANDS; b++) {
+  for (int b = 0; b < NB_BANDS + 1; b++) {   // all 33 triangular segments (interp_bin only uses 1..31)
     int bs = eband[b + 1] - eband[b];
     for (int j = 0; j < bs; j++) {
       t->bin_band[eband[b] + j] = (unsigned char)b;

@@ -136,7 +136,7 @@ struct B200Engine {
   cudaStream_t s_h2d, s_d2h;
   cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
   long long host_frames;
-  int use_tc;                       // tcgen05 GRU path (default) or the dp4a cross-check kernel
+  int use_tc;                       // GRU kernel: 2 = k_gru_tc2 (default), 1 = k_gru_tc, 0 = dp4a cross-check
   GruTcMaps tc_maps[2][3];          // [frame parity][layer]
   // optional per-kernel timing (rnnoise_batch_profile)
   int profiling, prof_frames;
@@ -222,13 +222,13 @@ static int make_map_u8(CUtensorMap *m, const void *base, uint64_t rows, uint64_t
 }
 // dense s8 [3*gru][K] (rows = z|r|n outputs) -> [gru/32 slices][3 gates][32 units][K]: the 96 B-operand
 // rows of one unit slice become contiguous
-static const signed char *upload_permuted(B200Engine *e, const B200Layer *l, int gru) {
+static const signed char *upload_permuted(B200Engine *e, const B200Layer *l, int gru, int units) {
   const int K = l->nb_in;
   std::vector<signed char> p((size_t)3 * gru * K);
-  for (int sl = 0; sl < gru / TC_UNITS; sl++)
+  for (int sl = 0; sl < gru / units; sl++)
     for (int g = 0; g < 3; g++)
-      for (int u = 0; u < TC_UNITS; u++)
-        memcpy(&p[(((size_t)sl * 3 + g) * TC_UNITS + u) * K], l->w8 + (size_t)(g * gru + sl * TC_UNITS + u) * K, K);
+      for (int u = 0; u < units; u++)
+        memcpy(&p[(((size_t)sl * 3 + g) * units + u) * K], l->w8 + (size_t)(g * gru + sl * units + u) * K, K);
   return upload<signed char>(e, p.data(), p.size());
 }
 
@@ -318,22 +318,26 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   for (int k = 0; k < 3 && ok; k++)
     ok = upload_q(e, &dm.gru_in[k], &m->gru_in[k]) == 0 && upload_q(e, &dm.gru_rec[k], &m->gru_rec[k]) == 0;
   // tensor-core GRU path: permuted weights + TMA maps for both frame parities
+  // RNNOISE_B200_GRU_KERNEL = tc2 (default: persistent pipelined tcgen05) | tc1 (one tile per CTA) |
+  // dp4a (CUDA-core cross-check); all three produce identical bits
   const char *gk = getenv("RNNOISE_B200_GRU_KERNEL");
-  e->use_tc = !(gk && !strcmp(gk, "dp4a"));
+  e->use_tc = gk && !strcmp(gk, "dp4a") ? 0 : gk && !strcmp(gk, "tc1") ? 1 : 2;
   if (ok && e->use_tc) {
     const size_t hs = Ss * m->gru;
+    const int units = e->use_tc == 1 ? TC_UNITS : P_SLICE;
     for (int l = 0; l < 3 && ok; l++) {
-      const signed char *wi = upload_permuted(e, &m->gru_in[l], m->gru), *wr = upload_permuted(e, &m->gru_rec[l], m->gru);
+      const signed char *wi = upload_permuted(e, &m->gru_in[l], m->gru, units), *wr = upload_permuted(e, &m->gru_rec[l], m->gru, units);
       ok = wi && wr;
       for (int par = 0; par < 2 && ok; par++) {
         GruTcMaps &mp = e->tc_maps[par][l];
         const uint8_t *x = l == 0 ? a.conv2_out_u8 : a.hbuf_u8 + ((size_t)par * 3 + l - 1) * hs;
         const uint8_t *h = a.hbuf_u8 + ((size_t)(par ^ 1) * 3 + l) * hs;
         ok = make_map_u8(&mp.x, x, S, m->gru, TC_M) == 0 && make_map_u8(&mp.h, h, S, m->gru, TC_M) == 0 &&
-             make_map_u8(&mp.wi, wi, 3 * m->gru, m->gru, TC_N) == 0 && make_map_u8(&mp.wr, wr, 3 * m->gru, m->gru, TC_N) == 0;
+             make_map_u8(&mp.wi, wi, 3 * m->gru, m->gru, 3 * units) == 0 && make_map_u8(&mp.wr, wr, 3 * m->gru, m->gru, 3 * units) == 0;
       }
     }
     ok = ok && cudaFuncSetAttribute(k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, gru_tc_smem_bytes(m->gru)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_gru_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, gru_tc2_smem_bytes(m->gru)) == cudaSuccess;
     if (!ok) fprintf(stderr, "[rnnoise_b200] tensor-core GRU setup failed\n");
   }
   if (!ok || cudaDeviceSynchronize() != cudaSuccess) {
@@ -375,7 +379,10 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
   const size_t gsm = 2 * RNN_TS * (gru / 4) * sizeof(uint32_t);
   for (int l = 0; l < 3; l++) {
     uint8_t *hu8_new = a.hbuf_u8 + ((size_t)par * 3 + l) * hstride;
-    if (e->use_tc) {
+    if (e->use_tc == 2) {
+      k_gru_tc2<<<dim3((S + TC_M - 1) / TC_M, 4), 288, gru_tc2_smem_bytes(gru), st>>>(
+          S, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, a.silence);
+    } else if (e->use_tc == 1) {
       k_gru_tc<<<dim3((S + TC_M - 1) / TC_M, gru / TC_UNITS), 160, gru_tc_smem_bytes(gru), st>>>(
           S, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, a.silence);
     } else {

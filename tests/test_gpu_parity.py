@@ -200,25 +200,28 @@ def test_full_size_properties_4096_streams(rb, models_dir):
     batch.destroy(); model.free()
 
 
-def test_gru_tensor_core_path_equals_dp4a_path(rb, models_dir):
-    """The tcgen05 (u8 x s8 -> s32 in TMEM) GRU kernel and the CUDA-core dp4a kernel accumulate the same
-    exact integers, so whole-pipeline outputs and GRU states must be bit-identical; S = 300 exercises a
-    partial 128-row tile (TMA zero fill + row guards)."""
+def test_gru_tensor_core_paths_equal_dp4a_path(rb, models_dir):
+    """The tcgen05 GRU kernels (u8 x s8 -> s32 in TMEM; tc2 = persistent pipelined default, tc1 = one tile
+    per CTA) and the CUDA-core dp4a kernel accumulate the same exact integers, so whole-pipeline outputs
+    and GRU states must be bit-identical; S = 300 exercises a partial 128-row tile (TMA zero fill + guards)."""
     model = rb.Model(os.path.join(models_dir, "hot.bin"))
     S, frames = 300, 10
-    os.environ["RNNOISE_B200_GRU_KERNEL"] = "dp4a"
-    a = rb.Batch(model, S)
+    batches = {}
+    for mode in ("dp4a", "tc1", "tc2"):
+        os.environ["RNNOISE_B200_GRU_KERNEL"] = mode
+        batches[mode] = rb.Batch(model, S)
     del os.environ["RNNOISE_B200_GRU_KERNEL"]
-    b = rb.Batch(model, S)
     pcm = batch_pcm(S, frames)
     for f in range(frames):
-        oa, va = a.process(pcm[f])
-        ob, vb = b.process(pcm[f])
-        assert np.array_equal(bits(oa), bits(ob)) and np.array_equal(bits(va), bits(vb)), f
-        for s in (0, 127, 128, 255, 256, 299):
-            for k in ("gru1", "gru2", "gru3", "gains"):
-                assert np.array_equal(bits(a.debug(k, s)), bits(b.debug(k, s))), (k, s, f)
-    a.destroy(); b.destroy(); model.free()
+        res = {m: b.process(pcm[f]) for m, b in batches.items()}
+        for m in ("tc1", "tc2"):
+            assert np.array_equal(bits(res[m][0]), bits(res["dp4a"][0])) and np.array_equal(bits(res[m][1]), bits(res["dp4a"][1])), (m, f)
+            for s in (0, 127, 128, 255, 256, 299):
+                for k in ("gru1", "gru2", "gru3", "gains"):
+                    assert np.array_equal(bits(batches[m].debug(k, s)), bits(batches["dp4a"].debug(k, s))), (m, k, s, f)
+    for b in batches.values():
+        b.destroy()
+    model.free()
 
 
 def test_async_pipelined_host_call_equals_synchronous(rb, models_dir):
