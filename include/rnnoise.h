@@ -149,7 +149,7 @@ enum {
   RNNOISE_DBG_GRU2 = 10,
   RNNOISE_DBG_GRU3 = 11,
   RNNOISE_DBG_CONV1_STATE = 12, /* [130] */
-  RNNOISE_DBG_CONV2_STATE = 13, /* [2*cond] */
+  RNNOISE_DBG_CONV2_STATE = 13, /* [2*cond] conv2 memory as the u8 values 127 + rne(127 x) it is kept in */
   RNNOISE_DBG_PITCH = 14,     /* [2]   {last_period (as float), last_gain}                       */
   RNNOISE_DBG_SILENCE = 15,   /* [1]   1.0 when the frame was classified silent                  */
   RNNOISE_DBG_CONV2_OUT = 16  /* [gru] conv2 output of the frame                                */

@@ -45,7 +45,7 @@ struct Arena {
   float *pitch_state;  // [S][2] {last_period (int bits), last_gain}
   // network state
   float *conv1_state;  // [S][130]
-  float *conv2_state;  // [S][2*cond]
+  uint8_t *c2in;       // [S][3*cond] u8 operand row of conv2: [memory (2 frames of conv1 output) | newest]
   float *hbuf;         // [2][3][S][gru] ping-pong GRU states
   uint8_t *hbuf_u8;    // [2][3][S][gru] their u8 = 127 + rne(127 h) mirrors (tensor-core A operands)
   uint8_t *conv2_out_u8; // [S][gru]
@@ -53,7 +53,6 @@ struct Arena {
   float *xb;           // [S][480]
   float *features;     // [S][65]
   int *silence;        // [S]
-  float *conv1_out;    // [S][cond]
   float *conv2_out;    // [S][gru]
   float *gains;        // [S][32]
   float *vad;          // [S]
@@ -136,8 +135,10 @@ struct B200Engine {
   cudaStream_t s_h2d, s_d2h;
   cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
   long long host_frames;
-  int use_tc;                       // GRU kernel: 2 = k_gru_tc2 (default), 1 = k_gru_tc, 0 = dp4a cross-check
+  int use_tc;                       // GRU kernel: 2 = k_tc2<true> (default), 1 = k_gru_tc, 0 = dp4a cross-check
+  int conv2_tc;                     // conv2 kernel: 1 = k_tc2<false> (default), 0 = dp4a cross-check
   GruTcMaps tc_maps[2][3];          // [frame parity][layer]
+  GruTcMaps conv_maps;              // x = c2in, wi = conv2 weights
   // optional per-kernel timing (rnnoise_batch_profile)
   int profiling, prof_frames;
   cudaEvent_t ev[NKERNELS + 1];
@@ -281,7 +282,8 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   ok &= !!(a.lastg = dalloc<float>(e, Ss * NB_BANDS));
   ok &= !!(a.pitch_state = dalloc<float>(e, Ss * 2));
   ok &= !!(a.conv1_state = dalloc<float>(e, Ss * 2 * NB_FEATURES));
-  ok &= !!(a.conv2_state = dalloc<float>(e, Ss * 2 * m->cond));
+  ok &= !!(a.c2in = dalloc<uint8_t>(e, Ss * 3 * m->cond));
+  if (ok) ok = cudaMemset(a.c2in, 127, Ss * 3 * m->cond) == cudaSuccess;   // u8 image of zeros
   ok &= !!(a.hbuf = dalloc<float>(e, 2 * 3 * Ss * m->gru));
   ok &= !!(a.hbuf_u8 = dalloc<uint8_t>(e, 2 * 3 * Ss * m->gru));
   ok &= !!(a.conv2_out_u8 = dalloc<uint8_t>(e, Ss * m->gru));
@@ -289,7 +291,6 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   ok &= !!(a.xb = dalloc<float>(e, Ss * FRAME_SIZE));
   ok &= !!(a.features = dalloc<float>(e, Ss * NB_FEATURES));
   ok &= !!(a.silence = dalloc<int>(e, Ss));
-  ok &= !!(a.conv1_out = dalloc<float>(e, Ss * m->cond));
   ok &= !!(a.conv2_out = dalloc<float>(e, Ss * m->gru));
   ok &= !!(a.gains = dalloc<float>(e, Ss * NB_BANDS));
   ok &= !!(a.vad = dalloc<float>(e, Ss));
@@ -337,8 +338,18 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
       }
     }
     ok = ok && cudaFuncSetAttribute(k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, gru_tc_smem_bytes(m->gru)) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_gru_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, gru_tc2_smem_bytes(m->gru)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<true>(m->gru, m->gru)) == cudaSuccess;
     if (!ok) fprintf(stderr, "[rnnoise_b200] tensor-core GRU setup failed\n");
+  }
+  // conv2 on the tensor cores needs its K = 3*cond to be whole 128-byte swizzle atoms
+  const char *ck = getenv("RNNOISE_B200_CONV2_KERNEL");
+  e->conv2_tc = !(ck && !strcmp(ck, "dp4a")) && (3 * m->cond) % TC_KATOM == 0;
+  if (ok && e->conv2_tc) {
+    const signed char *w2 = upload<signed char>(e, m->conv2.w8, (size_t)m->gru * 3 * m->cond);   // natural [unit][K]
+    ok = w2 && make_map_u8(&e->conv_maps.x, a.c2in, S, 3 * m->cond, TC_M) == 0 &&
+         make_map_u8(&e->conv_maps.wi, w2, m->gru, 3 * m->cond, P_SLICE) == 0;
+    e->conv_maps.h = e->conv_maps.x; e->conv_maps.wr = e->conv_maps.wi;
+    ok = ok && cudaFuncSetAttribute(k_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<false>(3 * m->cond, m->gru)) == cudaSuccess;
   }
   if (!ok || cudaDeviceSynchronize() != cudaSuccess) {
     fprintf(stderr, "[rnnoise_b200] engine allocation/upload failed: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -372,16 +383,20 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
   k_analysis<<<S, DSP_THREADS, SM_TOTAL * sizeof(float), st>>>(a, e->d_tables);
   MARK();
   const int gts = (S + RNN_TS - 1) / RNN_TS;
-  k_conv1<<<gts, 128, 0, st>>>(S, e->dm, a.features, a.conv1_state, a.silence, a.conv1_out);
+  k_conv1<<<gts, 128, 0, st>>>(S, e->dm, a.features, a.conv1_state, a.silence, a.c2in);
   MARK();
-  k_conv2<<<gts, 128, RNN_TS * 2 * cond * sizeof(uint32_t), st>>>(S, e->dm, a.conv1_out, a.conv2_state, a.silence, a.conv2_out, a.conv2_out_u8);
+  if (e->conv2_tc)
+    k_tc2<false><<<dim3((S + TC_M - 1) / TC_M, 4), 288, tc2_smem_bytes<false>(3 * cond, gru), st>>>(
+        S, 3 * cond, gru, e->conv_maps, e->dm.conv2, e->dm.conv2, nullptr, a.conv2_out, a.conv2_out_u8, a.silence);
+  else
+    k_conv2<<<gts, 128, RNN_TS * (3 * cond / 4) * sizeof(uint32_t), st>>>(S, e->dm, a.c2in, a.conv2_out, a.conv2_out_u8);
   MARK();
   const size_t gsm = 2 * RNN_TS * (gru / 4) * sizeof(uint32_t);
   for (int l = 0; l < 3; l++) {
     uint8_t *hu8_new = a.hbuf_u8 + ((size_t)par * 3 + l) * hstride;
     if (e->use_tc == 2) {
-      k_gru_tc2<<<dim3((S + TC_M - 1) / TC_M, 4), 288, gru_tc2_smem_bytes(gru), st>>>(
-          S, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, a.silence);
+      k_tc2<true><<<dim3((S + TC_M - 1) / TC_M, 4), 288, tc2_smem_bytes<true>(gru, gru), st>>>(
+          S, gru, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, a.silence);
     } else if (e->use_tc == 1) {
       k_gru_tc<<<dim3((S + TC_M - 1) / TC_M, gru / TC_UNITS), 160, gru_tc_smem_bytes(gru), st>>>(
           S, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, a.silence);
@@ -491,9 +506,10 @@ extern "C" int b200_engine_reset_stream(B200Engine *e, int s) {
     CK(cudaMemsetAsync((ptr) + ((size_t)c_ * S + s) * (per), 0, (size_t)(per) * sizeof(*(ptr)), st));
   ZERO(a.ring, PITCH_BUF_SIZE, 1) ZERO(a.synth_mem, FRAME_SIZE, 1) ZERO(a.hp_mem, 2, 1)
   ZERO(a.spec, 4 * FREQ_SIZE, 2) ZERO(a.band, 96, 2) ZERO(a.lastg, NB_BANDS, 1) ZERO(a.pitch_state, 2, 1)
-  ZERO(a.conv1_state, 2 * NB_FEATURES, 1) ZERO(a.conv2_state, 2 * a.cond, 1) ZERO(a.hbuf, a.gru, 6)
+  ZERO(a.conv1_state, 2 * NB_FEATURES, 1) ZERO(a.hbuf, a.gru, 6)
 #undef ZERO
   for (int c = 0; c < 6; c++) CK(cudaMemsetAsync(a.hbuf_u8 + ((size_t)c * S + s) * a.gru, 127, a.gru, st));
+  CK(cudaMemsetAsync(a.c2in + (size_t)s * 3 * a.cond, 127, 3 * a.cond, st));
   CK(cudaStreamSynchronize(st));
   return 0;
 }
@@ -520,7 +536,14 @@ extern "C" int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst
     case RNNOISE_DBG_GRU1: case RNNOISE_DBG_GRU2: case RNNOISE_DBG_GRU3:
       src = a.hbuf + (((size_t)par * 3 + (what - RNNOISE_DBG_GRU1)) * S + s) * a.gru; n = a.gru; break;
     case RNNOISE_DBG_CONV1_STATE: src = a.conv1_state + (size_t)s * 2 * NB_FEATURES; n = 2 * NB_FEATURES; break;
-    case RNNOISE_DBG_CONV2_STATE: src = a.conv2_state + (size_t)s * 2 * a.cond; n = 2 * a.cond; break;
+    case RNNOISE_DBG_CONV2_STATE: {   // kept as u8 (the only form conv2 consumes): returned as floats 0..255
+      n = 2 * a.cond;
+      if (cap < n) return -1;
+      std::vector<uint8_t> tmp(n);
+      CK(cudaMemcpy(tmp.data(), a.c2in + (size_t)s * 3 * a.cond, n, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < n; i++) dst[i] = (float)tmp[i];
+      return n;
+    }
     case RNNOISE_DBG_PITCH: src = a.pitch_state + 2 * (size_t)s; n = 2; break;
     case RNNOISE_DBG_SILENCE: src = (const float *)(a.silence + s); n = 1; break;
     case RNNOISE_DBG_CONV2_OUT: src = a.conv2_out + (size_t)s * a.gru; n = a.gru; break;

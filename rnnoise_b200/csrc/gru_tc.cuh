@@ -233,27 +233,36 @@ k_gru_tc(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, D
 }
 
 // ================================================================================================
-// k_gru_tc2 -- persistent, warp-specialised version (the default GRU path).
+// k_tc2<kGru> -- persistent, warp-specialised tensor-core kernel (the default int8 path).
 //
-// CTA = 128 streams x (gru/4) hidden units, processed as gru/64 slices of 16 units through a
-// three-deep TMA ring for the weight slices and a two-deep TMEM ring for the accumulators:
+//   kGru = true : one GRU layer (k_gru_tc2).   kGru = false: conv2 (k_conv2_tc), a single GEMM + tanh.
+//
+// CTA = 128 streams x (N/4) output units, processed as slices of 16 units through a three-deep TMA ring
+// for the weight slices and a two-deep TMEM ring for the accumulators:
 //     warp 8 (one elected thread): TMA producer + tcgen05.mma issuer
 //     warps 0..7 (256 threads)   : epilogue -- warp w reads TMEM lane quarter (w & 3), units 8*(w>>2)..+8
-// so that  TMA(slice s+2) || MMA(slice s+1) || epilogue(slice s).  The activation tiles Xu8/Hu8
-// (128 x K each) are loaded once per CTA and stay resident.  Per slice and matrix one
-// tcgen05.mma.kind::i8 M128 N48 K32 chain of K/32 instructions; accumulators: [in z|r|n (48) |
-// rec z|r|n (48)] = 96 TMEM columns per stage.  Same arithmetic as k_gru_tc / k_gru: bit-identical.
+// so that  TMA(slice s+2) || MMA(slice s+1) || epilogue(slice s).  The u8 activation tiles (128 x K;
+// GRU: Xu8 and Hu8) are loaded once per CTA and stay resident.  Per slice and matrix one
+// tcgen05.mma.kind::i8 chain of K/32 instructions, M128 x N48 (GRU: z|r|n of 16 units) or N16 (conv2);
+// accumulators: GRU [in z|r|n (48) | rec z|r|n (48)] = 96 TMEM columns per stage, conv2 16.
+// Same arithmetic as the dp4a kernels k_gru / k_conv2: bit-identical results.
 // grid = (ceil(S/128), 4), block = 288, 1 CTA / SM.
 // ================================================================================================
 #define P_SLICE 16
-#define P_N (3 * P_SLICE)                 // 48
 #define P_STAGES 3
-#define P_B_ATOM_BYTES (P_N * TC_KATOM)   // 6144
-#define P_TMEM_COLS 256                   // 2 stages x 96 columns -> next power of two
+#define P_TMEM_COLS 256                   // >= 2 stages x 96 columns, power of two
 
-__host__ __device__ constexpr int gru_tc2_smem_bytes(int gru) {
-  return 1024 + 2 * (gru / TC_KATOM) * TC_A_ATOM_BYTES + P_STAGES * 2 * (gru / TC_KATOM) * P_B_ATOM_BYTES +
-         15 * (gru / 4) * 4 + 16 * 8 + 64;
+template <bool kGru> struct TcCfg {
+  static constexpr int kMats = kGru ? 2 : 1;                 // GEMMs per slice (input, recurrent)
+  static constexpr int kN = kGru ? 3 * P_SLICE : P_SLICE;    // UMMA N: 48 / 16
+  static constexpr int kBAtom = kN * TC_KATOM;               // bytes of one weight atom: 6144 / 2048
+  static constexpr int kPrm = kGru ? 15 : 2;                 // epilogue parameter vectors per unit
+  static constexpr int kCols = kMats * kN;                   // TMEM columns per stage: 96 / 16
+};
+template <bool kGru>
+__host__ __device__ constexpr int tc2_smem_bytes(int K, int N) {
+  return 1024 + TcCfg<kGru>::kMats * (K / TC_KATOM) * TC_A_ATOM_BYTES +
+         P_STAGES * TcCfg<kGru>::kMats * (K / TC_KATOM) * TcCfg<kGru>::kBAtom + TcCfg<kGru>::kPrm * (N / 4) * 4 + 16 * 8 + 64;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -266,19 +275,25 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
                : "memory");
 }
 
+// K = contraction length (bytes of one activation row), N = number of output units (gru).
+// GRU : maps.x/h = Xu8/Hu8 [S][K]; maps.wi/wr = s8 [(N/16) x 48][K];  out = h_new (+u8), aux = h_old
+// conv: maps.x = conv2 input u8 [S][K]; maps.wi = s8 [N][K] (unit-major); out = conv2_out (+u8)
+template <bool kGru>
 __global__ void __launch_bounds__(288, 1)
-k_gru_tc2(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, DevLayerQ wr,
-          const float *__restrict__ h_old, float *__restrict__ h_new, uint8_t *__restrict__ h_new_u8,
-          const int *__restrict__ silence) {
+k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, DevLayerQ wr,
+      const float *__restrict__ h_old, float *__restrict__ out_f32, uint8_t *__restrict__ out_u8,
+      const int *__restrict__ silence) {
+  using C = TcCfg<kGru>;
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int natoms = gru / TC_KATOM, upc = gru / 4, nslice = upc / P_SLICE;   // units / slices per CTA
+  const int natoms = K / TC_KATOM, upc = N / 4, nslice = upc / P_SLICE;   // units / slices per CTA
   const int m0 = blockIdx.x * TC_M, jq = blockIdx.y * upc;
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *sAx = base, *sAh = sAx + natoms * TC_A_ATOM_BYTES, *sB = sAh + natoms * TC_A_ATOM_BYTES;
-  const int stage_bytes = 2 * natoms * P_B_ATOM_BYTES;
-  float *prm = (float *)(sB + P_STAGES * stage_bytes);            // [15][upc]
-  uint64_t *bars = (uint64_t *)(prm + 15 * upc);
+  uint8_t *sAx = base, *sAh = sAx + natoms * TC_A_ATOM_BYTES;
+  uint8_t *sB = sAx + C::kMats * natoms * TC_A_ATOM_BYTES;
+  const int stage_bytes = C::kMats * natoms * C::kBAtom;
+  float *prm = (float *)(sB + P_STAGES * stage_bytes);            // [kPrm][upc]
+  uint64_t *bars = (uint64_t *)(prm + C::kPrm * upc);
   uint32_t *tmem_slot = (uint32_t *)(bars + 16);
   const uint32_t bar_a = smem_u32(&bars[0]);
   auto bar_bfull = [&](int i) { return smem_u32(&bars[1 + i]); };
@@ -296,10 +311,14 @@ k_gru_tc2(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < 15 * upc; i += blockDim.x) {
-    int which = i / (3 * upc), g = (i / upc) % 3, u = i % upc;
-    const float *src = which == 0 ? wi.scale : which == 1 ? wi.subias : which == 2 ? wr.scale : which == 3 ? wr.subias : wr.diag;
-    prm[i] = src[g * gru + jq + u];
+  for (int i = tid; i < C::kPrm * upc; i += blockDim.x) {
+    if (kGru) {
+      int which = i / (3 * upc), g = (i / upc) % 3, u = i % upc;
+      const float *src = which == 0 ? wi.scale : which == 1 ? wi.subias : which == 2 ? wr.scale : which == 3 ? wr.subias : wr.diag;
+      prm[i] = src[g * N + jq + u];
+    } else {
+      prm[i] = (i < upc ? wi.scale : wi.subias)[jq + i % upc];
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -311,35 +330,35 @@ k_gru_tc2(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, 
       auto load_B = [&](int s) {
         const int st = s % P_STAGES;
         uint8_t *dst = sB + st * stage_bytes;
-        const int row = (blockIdx.y * nslice + s) * P_N;
+        const int row = (blockIdx.y * nslice + s) * C::kN;
         mbar_expect_tx(bar_bfull(st), (uint32_t)stage_bytes);
         for (int a = 0; a < natoms; a++) {
-          tma_load_2d(smem_u32(dst + a * P_B_ATOM_BYTES), &maps.wi, bar_bfull(st), a * TC_KATOM, row);
-          tma_load_2d(smem_u32(dst + (natoms + a) * P_B_ATOM_BYTES), &maps.wr, bar_bfull(st), a * TC_KATOM, row);
+          tma_load_2d(smem_u32(dst + a * C::kBAtom), &maps.wi, bar_bfull(st), a * TC_KATOM, row);
+          if (kGru) tma_load_2d(smem_u32(dst + (natoms + a) * C::kBAtom), &maps.wr, bar_bfull(st), a * TC_KATOM, row);
         }
       };
-      mbar_expect_tx(bar_a, (uint32_t)(2 * natoms * TC_A_ATOM_BYTES));
+      mbar_expect_tx(bar_a, (uint32_t)(C::kMats * natoms * TC_A_ATOM_BYTES));
       for (int a = 0; a < natoms; a++) {
         tma_load_2d(smem_u32(sAx + a * TC_A_ATOM_BYTES), &maps.x, bar_a, a * TC_KATOM, m0);
-        tma_load_2d(smem_u32(sAh + a * TC_A_ATOM_BYTES), &maps.h, bar_a, a * TC_KATOM, m0);
+        if (kGru) tma_load_2d(smem_u32(sAh + a * TC_A_ATOM_BYTES), &maps.h, bar_a, a * TC_KATOM, m0);
       }
       for (int s = 0; s < P_STAGES && s < nslice; s++) load_B(s);
       mbar_wait(bar_a, 0);
-      const uint32_t idesc = umma_idesc_i8(TC_M, P_N);
+      const uint32_t idesc = umma_idesc_i8(TC_M, C::kN);
       for (int s = 0; s < nslice; s++) {
         const int st = s % P_STAGES, ts = s & 1;
         mbar_wait(bar_bfull(st), (uint32_t)((s / P_STAGES) & 1));
         mbar_wait(bar_tempty(ts), (uint32_t)(((s >> 1) & 1) ^ 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint8_t *Bs = sB + st * stage_bytes;
-        for (int g = 0; g < 2; g++) {
+        for (int g = 0; g < C::kMats; g++) {
           const uint8_t *A = g ? sAh : sAx;
           for (int a = 0; a < natoms; a++) {
             const uint64_t ad = umma_desc_sw128(smem_u32(A + a * TC_A_ATOM_BYTES));
-            const uint64_t bd = umma_desc_sw128(smem_u32(Bs + (g * natoms + a) * P_B_ATOM_BYTES));
+            const uint64_t bd = umma_desc_sw128(smem_u32(Bs + (g * natoms + a) * C::kBAtom));
 #pragma unroll
             for (int k = 0; k < TC_KATOM / 32; k++)
-              umma_i8(tmem + ts * 2 * P_N + g * P_N, ad + (uint64_t)(k * 32 >> 4), bd + (uint64_t)(k * 32 >> 4), idesc, (a | k) ? 1u : 0u);
+              umma_i8(tmem + ts * C::kCols + g * C::kN, ad + (uint64_t)(k * 32 >> 4), bd + (uint64_t)(k * 32 >> 4), idesc, (a | k) ? 1u : 0u);
           }
         }
         umma_commit(bar_bempty(st));   // weight stage reusable once these MMAs retire
@@ -358,8 +377,8 @@ k_gru_tc2(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, 
     const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
     float hcur[8], hnext[8];
     auto load_h = [&](int s, float (&dst)[8]) {
-      if (live && s < nslice) {
-        const float4 *p = (const float4 *)&h_old[(size_t)srow * gru + jq + s * P_SLICE + ch * 8];
+      if (kGru && live && s < nslice) {
+        const float4 *p = (const float4 *)&h_old[(size_t)srow * N + jq + s * P_SLICE + ch * 8];
         float4 a = __ldg(p), b = __ldg(p + 1);
         dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
       } else {
@@ -373,44 +392,55 @@ k_gru_tc2(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, 
       load_h(s + 1, hnext);
       mbar_wait(bar_tfull(ts), (uint32_t)((s >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      int az[8], ar[8], an[8], bz[8], br[8], bn[8];
-      const uint32_t t0 = trow + ts * 2 * P_N + ch * 8;
-      tmem_ld8(t0 + 0 * P_SLICE, az); tmem_ld8(t0 + 1 * P_SLICE, ar); tmem_ld8(t0 + 2 * P_SLICE, an);
-      tmem_ld8(t0 + P_N + 0 * P_SLICE, bz); tmem_ld8(t0 + P_N + 1 * P_SLICE, br); tmem_ld8(t0 + P_N + 2 * P_SLICE, bn);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      // accumulators are in registers: hand the TMEM stage back to the MMA issuer
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty(ts));
+      const uint32_t t0 = trow + ts * C::kCols + ch * 8;
       const int ub = s * P_SLICE + ch * 8;     // unit index inside this CTA's quarter
       float outv[8];
+      if (kGru) {
+        int az[8], ar[8], an[8], bz[8], br[8], bn[8];
+        tmem_ld8(t0 + 0 * P_SLICE, az); tmem_ld8(t0 + 1 * P_SLICE, ar); tmem_ld8(t0 + 2 * P_SLICE, an);
+        tmem_ld8(t0 + C::kN + 0 * P_SLICE, bz); tmem_ld8(t0 + C::kN + 1 * P_SLICE, br); tmem_ld8(t0 + C::kN + 2 * P_SLICE, bn);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // accumulators are in registers: hand the TMEM stage back to the MMA issuer
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(ts));
 #pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const int u = ub + q;
-        const float h = hcur[q];
-        float out = h;
-        if (!silent) {
-          float zi = (float)az[q] * prm[(0 * 3 + 0) * upc + u] + prm[(1 * 3 + 0) * upc + u];
-          float ri = (float)ar[q] * prm[(0 * 3 + 1) * upc + u] + prm[(1 * 3 + 1) * upc + u];
-          float ni = (float)an[q] * prm[(0 * 3 + 2) * upc + u] + prm[(1 * 3 + 2) * upc + u];
-          float zr = fmaf(prm[(4 * 3 + 0) * upc + u], h, (float)bz[q] * prm[(2 * 3 + 0) * upc + u] + prm[(3 * 3 + 0) * upc + u]);
-          float rr = fmaf(prm[(4 * 3 + 1) * upc + u], h, (float)br[q] * prm[(2 * 3 + 1) * upc + u] + prm[(3 * 3 + 1) * upc + u]);
-          float nr = fmaf(prm[(4 * 3 + 2) * upc + u], h, (float)bn[q] * prm[(2 * 3 + 2) * upc + u] + prm[(3 * 3 + 2) * upc + u]);
-          float z = act_sigmoid(zi + zr);
-          float r = act_sigmoid(ri + rr);
-          float n = act_tanh(ni + nr * r);
-          out = z * h + (1 - z) * n;
+        for (int q = 0; q < 8; q++) {
+          const int u = ub + q;
+          const float h = hcur[q];
+          float out = h;
+          if (!silent) {
+            float zi = (float)az[q] * prm[(0 * 3 + 0) * upc + u] + prm[(1 * 3 + 0) * upc + u];
+            float ri = (float)ar[q] * prm[(0 * 3 + 1) * upc + u] + prm[(1 * 3 + 1) * upc + u];
+            float ni = (float)an[q] * prm[(0 * 3 + 2) * upc + u] + prm[(1 * 3 + 2) * upc + u];
+            float zr = fmaf(prm[(4 * 3 + 0) * upc + u], h, (float)bz[q] * prm[(2 * 3 + 0) * upc + u] + prm[(3 * 3 + 0) * upc + u]);
+            float rr = fmaf(prm[(4 * 3 + 1) * upc + u], h, (float)br[q] * prm[(2 * 3 + 1) * upc + u] + prm[(3 * 3 + 1) * upc + u]);
+            float nr = fmaf(prm[(4 * 3 + 2) * upc + u], h, (float)bn[q] * prm[(2 * 3 + 2) * upc + u] + prm[(3 * 3 + 2) * upc + u]);
+            float z = act_sigmoid(zi + zr);
+            float r = act_sigmoid(ri + rr);
+            float n = act_tanh(ni + nr * r);
+            out = z * h + (1 - z) * n;
+          }
+          outv[q] = out;
         }
-        outv[q] = out;
+      } else {
+        int acc[8];
+        tmem_ld8(t0, acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(ts));
+#pragma unroll
+        for (int q = 0; q < 8; q++) outv[q] = act_tanh((float)acc[q] * prm[ub + q] + prm[upc + ub + q]);
       }
       if (live) {
-        float *dst = &h_new[(size_t)srow * gru + jq + ub];
+        float *dst = &out_f32[(size_t)srow * N + jq + ub];
         *(float4 *)&dst[0] = make_float4(outv[0], outv[1], outv[2], outv[3]);
         *(float4 *)&dst[4] = make_float4(outv[4], outv[5], outv[6], outv[7]);
         uint2 pk;
         pk.x = quant4(outv[0], outv[1], outv[2], outv[3]);
         pk.y = quant4(outv[4], outv[5], outv[6], outv[7]);
-        *(uint2 *)&h_new_u8[(size_t)srow * gru + jq + ub] = pk;
+        *(uint2 *)&out_u8[(size_t)srow * N + jq + ub] = pk;
       }
 #pragma unroll
       for (int q = 0; q < 8; q++) hcur[q] = hnext[q];

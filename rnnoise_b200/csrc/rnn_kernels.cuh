@@ -63,13 +63,17 @@ struct DevModel {
 
 // ------------------------------------------------------------------------------------------------
 // conv1: [mem(2 frames) | features] (195) -> cond, fp32, tanh   (nnet.c:113-123, sgemv vec_avx.h:672)
-// grid = ceil(S / RNN_TS), block = 128
+// grid = ceil(S / RNN_TS), block = 128.
+// It also maintains conv2's operand row  c2in[s] = u8([mem2(2 x cond) | conv1_out(cond)])  (the only
+// form in which conv2 ever sees its inputs, vec_avx.h:326): on a non-silent frame the row is rotated
+// left by cond bytes (compute_generic_conv1d's memory update, nnet.c:122) and the new output appended.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *__restrict__ features,
                                                float *conv1_state, const int *__restrict__ silence,
-                                               float *__restrict__ conv1_out) {
+                                               uint8_t *c2in) {
   __shared__ float tmp[RNN_TS][3 * NB_FEAT + 1];
-  const int s0 = blockIdx.x * RNN_TS, tid = threadIdx.x;
+  __shared__ uint32_t rot[RNN_TS][128];          // 2*cond/4 words per stream (cond <= 256)
+  const int s0 = blockIdx.x * RNN_TS, tid = threadIdx.x, W = m.cond / 4;
   for (int idx = tid; idx < RNN_TS * 3 * NB_FEAT; idx += 128) {
     int s = idx / (3 * NB_FEAT), j = idx % (3 * NB_FEAT);
     float v = 0.f;
@@ -77,11 +81,20 @@ __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *_
                                          : features[(size_t)(s0 + s) * NB_FEAT + j - 2 * NB_FEAT];
     tmp[s][j] = v;
   }
+  for (int idx = tid; idx < RNN_TS * 2 * W; idx += 128) {   // words [W, 3W) of each live row
+    int s = idx / (2 * W), w = idx % (2 * W);
+    if (s0 + s < S) rot[s][w] = ((const uint32_t *)(c2in + (size_t)(s0 + s) * 3 * m.cond))[W + w];
+  }
   __syncthreads();
+  for (int idx = tid; idx < RNN_TS * 2 * W; idx += 128) {
+    int s = idx / (2 * W), w = idx % (2 * W);
+    if (s0 + s < S && !silence[s0 + s]) ((uint32_t *)(c2in + (size_t)(s0 + s) * 3 * m.cond))[w] = rot[s][w];
+  }
   for (int o = tid; o < m.cond; o += 128) {
     float acc[RNN_TS];
 #pragma unroll
     for (int s = 0; s < RNN_TS; s++) acc[s] = 0.f;
+#pragma unroll 13
     for (int j = 0; j < 3 * NB_FEAT; j++) {
       float w = __ldg(&m.conv1.w[(size_t)j * m.cond + o]);
 #pragma unroll
@@ -90,7 +103,8 @@ __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *_
     const float b = m.conv1.bias[o];
 #pragma unroll
     for (int s = 0; s < RNN_TS; s++)
-      if (s0 + s < S) conv1_out[(size_t)(s0 + s) * m.cond + o] = act_tanh(acc[s] + b);
+      if (s0 + s < S && !silence[s0 + s])
+        c2in[(size_t)(s0 + s) * 3 * m.cond + 2 * m.cond + o] = (uint8_t)quant_u8(act_tanh(acc[s] + b));
   }
   // memory update: mem = tmp[65:195]; silent frames leave the state untouched (denoise.c:474)
   for (int idx = tid; idx < RNN_TS * 2 * NB_FEAT; idx += 128) {
@@ -100,29 +114,16 @@ __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *_
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv2: [mem(2 x cond) | conv1_out] (3*cond) -> gru, int8, tanh   (cgemv8x4 vec_avx.h:829)
-// grid = ceil(S / RNN_TS), block = 128, dynamic smem = RNN_TS * 2*cond * 4 bytes (operands, then
-// staging of the memory rotate)
+// conv2 on CUDA cores (cross-check kernel for k_tc2<false>): c2in (3*cond u8) -> gru, tanh
+// (cgemv8x4 vec_avx.h:829).  grid = ceil(S / RNN_TS), block = 128, dynamic smem = RNN_TS*(3*cond/4)*4
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_conv2(int S, DevModel m, const float *__restrict__ conv1_out,
-                                               float *conv2_state, const int *__restrict__ silence,
+__global__ void __launch_bounds__(128) k_conv2(int S, DevModel m, const uint8_t *__restrict__ c2in,
                                                float *__restrict__ conv2_out, uint8_t *__restrict__ conv2_out_u8) {
   extern __shared__ uint32_t u_sm[];   // [RNN_TS][K/4]
   const int K = 3 * m.cond, K4 = K / 4, s0 = blockIdx.x * RNN_TS, tid = threadIdx.x;
   for (int idx = tid; idx < RNN_TS * K4; idx += 128) {
-    int s = idx / K4, k = 4 * (idx % K4);
-    uint32_t q = 0;
-    if (s0 + s < S) {
-      float v[4];
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        int kk = k + e;
-        v[e] = kk < 2 * m.cond ? conv2_state[(size_t)(s0 + s) * 2 * m.cond + kk]
-                               : conv1_out[(size_t)(s0 + s) * m.cond + kk - 2 * m.cond];
-      }
-      q = quant4(v[0], v[1], v[2], v[3]);
-    }
-    u_sm[idx] = q;
+    int s = idx / K4;
+    u_sm[idx] = s0 + s < S ? ((const uint32_t *)(c2in + (size_t)(s0 + s) * K))[idx % K4] : 0u;
   }
   __syncthreads();
   for (int o = tid; o < m.gru; o += 128) {
@@ -140,24 +141,8 @@ __global__ void __launch_bounds__(128) k_conv2(int S, DevModel m, const float *_
       if (s0 + s < S) {
         float v = act_tanh((float)acc[s] * sc + sb);
         conv2_out[(size_t)(s0 + s) * m.gru + o] = v;
-        conv2_out_u8[(size_t)(s0 + s) * m.gru + o] = (uint8_t)quant_u8(v);   // operand of the GRU-1 tensor-core GEMM
+        conv2_out_u8[(size_t)(s0 + s) * m.gru + o] = (uint8_t)quant_u8(v);   // operand of the GRU-1 GEMM
       }
-  }
-  __syncthreads();
-  // mem = [mem[cond:2cond] | conv1_out]
-  for (int idx = tid; idx < RNN_TS * 2 * m.cond; idx += 128) {
-    int s = idx / (2 * m.cond), j = idx % (2 * m.cond);
-    if (s0 + s < S && !silence[s0 + s]) {
-      float v = j < m.cond ? conv2_state[(size_t)(s0 + s) * 2 * m.cond + m.cond + j]
-                           : conv1_out[(size_t)(s0 + s) * m.cond + j - m.cond];
-      // staged through shared memory: the rotate reads columns other threads overwrite
-      u_sm[idx] = __float_as_uint(v);
-    }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < RNN_TS * 2 * m.cond; idx += 128) {
-    int s = idx / (2 * m.cond), j = idx % (2 * m.cond);
-    if (s0 + s < S && !silence[s0 + s]) conv2_state[(size_t)(s0 + s) * 2 * m.cond + j] = __uint_as_float(u_sm[idx]);
   }
 }
 
@@ -242,44 +227,59 @@ __global__ void __launch_bounds__(128) k_gru(int S, int gru, DevLayerQ wi, DevLa
 // sequential FMA chain over the 4*gru inputs) and vad_dense (1, sigmoid; the reference's scalar
 // tail multiplies and adds separately, vec_avx.h:731-735).
 // grid = ceil(S / 16), block = 160: warps 0..3 own 4 streams each (lane = output, 4 accumulator
-// chains per thread), warp 4 runs the 16 VAD chains (lane = stream).  Activations and weights are
-// staged through shared memory in chunks of 128 inputs so the FMA chains only wait on LDS.
+// chains per thread), warp 4 runs the 16 VAD chains (lane = stream).  Activations and weights stream
+// through a double-buffered cp.async pipeline in chunks of 64 inputs, so the FMA chains only ever
+// wait on shared memory while the next chunk is in flight.
 // ------------------------------------------------------------------------------------------------
 #define HEAD_TS 16
-#define HEAD_KC 128
+#define HEAD_KC 64
 #define HEAD_XS (HEAD_KC + 4)
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 16 : 0;   // src-size 0 -> 16 bytes of zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
 __global__ void __launch_bounds__(160) k_heads(int S, DevModel m, const float *__restrict__ c2,
                                                const float *__restrict__ g1, const float *__restrict__ g2,
                                                const float *__restrict__ g3, const int *__restrict__ silence,
                                                float *__restrict__ gains, float *__restrict__ vad,
                                                float *__restrict__ vad_user) {
-  __shared__ __align__(16) float xs[HEAD_TS][HEAD_XS];
-  __shared__ __align__(16) float ws[HEAD_KC][NB_GAINS];
-  __shared__ float wv[HEAD_KC];
-  const int s0 = blockIdx.x * HEAD_TS, tid = threadIdx.x, gru = m.gru, K = 4 * gru;
+  __shared__ __align__(16) float xs[2][HEAD_TS][HEAD_XS];
+  __shared__ __align__(16) float ws[2][HEAD_KC][NB_GAINS];
+  __shared__ __align__(16) float wv[2][HEAD_KC];
+  const int s0 = blockIdx.x * HEAD_TS, tid = threadIdx.x, gru = m.gru, K = 4 * gru, nchunk = K / HEAD_KC;
   const int o = tid & 31, sg = tid >> 5;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  float y = 0.f;
-  for (int c0 = 0; c0 < K; c0 += HEAD_KC) {   // gru % 128 == 0, so a chunk never straddles two sources
-    const int src = c0 / gru, off = c0 % gru;
+  auto stage = [&](int c, int buf) {   // gru % 64 == 0: a chunk never straddles two source arrays
+    const int c0 = c * HEAD_KC, src = c0 / gru, off = c0 % gru;
     const float *p = src == 0 ? c2 : src == 1 ? g1 : src == 2 ? g2 : g3;
-    __syncthreads();
     for (int idx = tid; idx < HEAD_TS * HEAD_KC / 4; idx += 160) {
       int s = idx / (HEAD_KC / 4), k4 = idx % (HEAD_KC / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (s0 + s < S) v = *(const float4 *)&p[(size_t)(s0 + s) * gru + off + 4 * k4];
-      *(float4 *)&xs[s][4 * k4] = v;
+      const bool live = s0 + s < S;
+      cp_async16(&xs[buf][s][4 * k4], &p[(size_t)(live ? s0 + s : 0) * gru + off + 4 * k4], live);
     }
     for (int idx = tid; idx < HEAD_KC * NB_GAINS / 4; idx += 160)
-      ((float4 *)&ws[0][0])[idx] = __ldg((const float4 *)&m.dense_out.w[(size_t)c0 * NB_GAINS] + idx);
-    if (tid < HEAD_KC) wv[tid] = __ldg(&m.vad_dense.w[c0 + tid]);
+      cp_async16(&ws[buf][0][0] + 4 * idx, &m.dense_out.w[(size_t)c0 * NB_GAINS + 4 * idx], true);
+    if (tid < HEAD_KC / 4) cp_async16(&wv[buf][4 * tid], &m.vad_dense.w[c0 + 4 * tid], true);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float y = 0.f;
+  stage(0, 0);
+  for (int c = 0; c < nchunk; c++) {
+    const int buf = c & 1;
+    if (c + 1 < nchunk) {
+      stage(c + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
     if (sg < 4) {
 #pragma unroll 4
       for (int kk = 0; kk < HEAD_KC; kk += 4) {
-        float4 x0 = *(const float4 *)&xs[sg * 4 + 0][kk], x1 = *(const float4 *)&xs[sg * 4 + 1][kk];
-        float4 x2 = *(const float4 *)&xs[sg * 4 + 2][kk], x3 = *(const float4 *)&xs[sg * 4 + 3][kk];
-        float w0 = ws[kk][o], w1 = ws[kk + 1][o], w2 = ws[kk + 2][o], w3 = ws[kk + 3][o];
+        float4 x0 = *(const float4 *)&xs[buf][sg * 4 + 0][kk], x1 = *(const float4 *)&xs[buf][sg * 4 + 1][kk];
+        float4 x2 = *(const float4 *)&xs[buf][sg * 4 + 2][kk], x3 = *(const float4 *)&xs[buf][sg * 4 + 3][kk];
+        float w0 = ws[buf][kk][o], w1 = ws[buf][kk + 1][o], w2 = ws[buf][kk + 2][o], w3 = ws[buf][kk + 3][o];
         acc[0] = fmaf(w0, x0.x, acc[0]); acc[1] = fmaf(w0, x1.x, acc[1]); acc[2] = fmaf(w0, x2.x, acc[2]); acc[3] = fmaf(w0, x3.x, acc[3]);
         acc[0] = fmaf(w1, x0.y, acc[0]); acc[1] = fmaf(w1, x1.y, acc[1]); acc[2] = fmaf(w1, x2.y, acc[2]); acc[3] = fmaf(w1, x3.y, acc[3]);
         acc[0] = fmaf(w2, x0.z, acc[0]); acc[1] = fmaf(w2, x1.z, acc[1]); acc[2] = fmaf(w2, x2.z, acc[2]); acc[3] = fmaf(w2, x3.z, acc[3]);
@@ -287,8 +287,9 @@ __global__ void __launch_bounds__(160) k_heads(int S, DevModel m, const float *_
       }
     } else if (o < HEAD_TS) {
 #pragma unroll 8
-      for (int kk = 0; kk < HEAD_KC; kk++) y = y + wv[kk] * xs[o][kk];
+      for (int kk = 0; kk < HEAD_KC; kk++) y = y + wv[buf][kk] * xs[buf][o][kk];
     }
+    __syncthreads();   // everyone is done with `buf` before chunk c+2 is staged into it
   }
   if (sg < 4) {
     const float b = m.dense_out.bias[o];

@@ -221,6 +221,18 @@ def test_gru_tensor_core_paths_equal_dp4a_path(rb, models_dir):
                     assert np.array_equal(bits(batches[m].debug(k, s)), bits(batches["dp4a"].debug(k, s))), (m, k, s, f)
     for b in batches.values():
         b.destroy()
+    # conv2: tensor-core kernel (default) vs dp4a kernel
+    os.environ["RNNOISE_B200_CONV2_KERNEL"] = "dp4a"
+    a = rb.Batch(model, S)
+    del os.environ["RNNOISE_B200_CONV2_KERNEL"]
+    b = rb.Batch(model, S)
+    for f in range(frames):
+        oa, va = a.process(pcm[f]); ob, vb = b.process(pcm[f])
+        assert np.array_equal(bits(oa), bits(ob)) and np.array_equal(bits(va), bits(vb)), f
+        for s in (0, 128, 299):
+            for k in ("conv2_out", "conv2_state", "gru3"):
+                assert np.array_equal(bits(a.debug(k, s)), bits(b.debug(k, s))), (k, s, f)
+    a.destroy(); b.destroy()
     model.free()
 
 
