@@ -108,6 +108,14 @@ RNNOISE_EXPORT int rnnoise_process_frame_batch_async(RNNoiseBatch *b, float *out
  *  synchronising.  0 on success, -1 on a launch error. */
 RNNOISE_EXPORT int rnnoise_process_frame_batch_device(RNNoiseBatch *b, float *d_out, const float *d_in, float *d_vad);
 
+/** Optional pipelining hint for the device-buffer path: d_in_next (already complete in device memory)
+ *  is the input of the next frame that has not been handed to rnnoise_process_frame_batch_device()
+ *  yet.  Its high-pass prefilter (the only stage that depends on nothing but the input and the previous
+ *  prefilter) is started right away on an internal stream, overlapping the frame in flight; the
+ *  following rnnoise_process_frame_batch_device() call must pass the same pointer.  At most two frames
+ *  ahead.  0 / -1. */
+RNNOISE_EXPORT int rnnoise_batch_prefilter_device(RNNoiseBatch *b, const float *d_in_next);
+
 /** Block until everything enqueued on the batch's stream has finished.  0 / -1. */
 RNNOISE_EXPORT int rnnoise_batch_sync(RNNoiseBatch *b);
 

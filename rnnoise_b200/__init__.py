@@ -43,6 +43,7 @@ def lib():
         L.rnnoise_process_frame_batch.restype = ip; L.rnnoise_process_frame_batch.argtypes = [vp, vp, vp, vp]
         L.rnnoise_process_frame_batch_async.restype = ip; L.rnnoise_process_frame_batch_async.argtypes = [vp, vp, vp, vp]
         L.rnnoise_process_frame_batch_device.restype = ip; L.rnnoise_process_frame_batch_device.argtypes = [vp, vp, vp, vp]
+        L.rnnoise_batch_prefilter_device.restype = ip; L.rnnoise_batch_prefilter_device.argtypes = [vp, vp]
         L.rnnoise_batch_sync.restype = ip; L.rnnoise_batch_sync.argtypes = [vp]
         L.rnnoise_batch_set_stream.restype = ip; L.rnnoise_batch_set_stream.argtypes = [vp, vp]
         L.rnnoise_batch_reset_stream.restype = ip; L.rnnoise_batch_reset_stream.argtypes = [vp, ip]
@@ -110,6 +111,11 @@ class Batch:
         """Device pointers (ints); asynchronous on the batch's stream."""
         if lib().rnnoise_process_frame_batch_device(self.handle, d_out, d_in, d_vad) != 0:
             raise RuntimeError("rnnoise_process_frame_batch_device failed")
+
+    def prefilter_device(self, d_in_next):
+        """Pipelining hint: start the next frame's high-pass prefilter now (see include/rnnoise.h)."""
+        if lib().rnnoise_batch_prefilter_device(self.handle, d_in_next) != 0:
+            raise RuntimeError("rnnoise_batch_prefilter_device failed")
 
     def set_stream(self, cuda_stream):
         if lib().rnnoise_batch_set_stream(self.handle, cuda_stream) != 0:

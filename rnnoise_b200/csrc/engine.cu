@@ -3,9 +3,10 @@
 // One frame of every stream =
 //   k_biquad (thread/stream)  -> k_analysis (CTA/stream) -> k_conv1 -> k_conv2 -> k_gru x3 -> k_heads
 //   -> k_synthesis (CTA/stream)
-// all on one CUDA stream; state lives in HBM between frames (layout: DESIGN.md "Data layout").
-// A device-side frame counter selects the ping-pong halves and the pitch-ring base, so the launch
-// arguments never change from frame to frame (CUDA-graph friendly).
+// state lives in HBM between frames (layout: DESIGN.md "Data layout"); the frame index (host-side
+// counter, passed to the kernels) selects the ping-pong halves and the pitch-ring base.  k_biquad
+// only depends on the previous k_biquad and on the frame's input, so it runs on its own stream one
+// frame ahead of the rest whenever the input is known early (pipelined host call, prefilter hint).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -34,7 +35,6 @@
 // ------------------------------------------------------------------------------------------------
 struct Arena {
   int S, cond, gru;
-  int *ctr;            // frames started so far (incremented by k_biquad)
   // DSP state
   float *ring;         // [S][1728] pitch history ring (analysis_mem is its newest 480 samples)
   float *synth_mem;    // [S][480]
@@ -50,7 +50,7 @@ struct Arena {
   uint8_t *hbuf_u8;    // [2][3][S][gru] their u8 = 127 + rne(127 h) mirrors (tensor-core A operands)
   uint8_t *conv2_out_u8; // [S][gru]
   // per-frame scratch
-  float *xb;           // [S][480]
+  float *xb;           // [2][S][480] high-passed input, double-buffered by frame parity
   float *features;     // [S][65]
   int *silence;        // [S]
   float *conv2_out;    // [S][gru]
@@ -65,10 +65,10 @@ struct Arena {
 // High-pass biquad (rnn_biquad, denoise.c:409-419): strictly serial per stream (each step rounds
 // the state to float), so one THREAD owns one stream; a warp transposes 32x32 tiles through shared
 // memory so that global traffic stays coalesced.  grid = ceil(S/32), block = 32.
-__global__ void __launch_bounds__(32) k_biquad(Arena a, const float *__restrict__ in) {
+__global__ void __launch_bounds__(32) k_biquad(Arena a, const float *__restrict__ in, int frame) {
   __shared__ float tile[32][33];
   const int lane = threadIdx.x, s0 = blockIdx.x * 32, s = s0 + lane;
-  if (blockIdx.x == 0 && lane == 0) a.ctr[0] += 1;   // nobody reads ctr inside this kernel
+  float *xb = a.xb + (size_t)(frame & 1) * a.S * FRAME_SIZE;
   float m0 = 0.f, m1 = 0.f;
   if (s < a.S) { m0 = a.hp_mem[2 * s]; m1 = a.hp_mem[2 * s + 1]; }
   const int rows = min(32, a.S - s0);
@@ -80,18 +80,18 @@ __global__ void __launch_bounds__(32) k_biquad(Arena a, const float *__restrict_
       for (int t = 0; t < 32; t++) tile[lane][t] = biquad_step(tile[lane][t], m0, m1);
     }
     __syncwarp();
-    for (int r = 0; r < rows; r++) a.xb[(size_t)(s0 + r) * FRAME_SIZE + c * 32 + lane] = tile[r][lane];
+    for (int r = 0; r < rows; r++) xb[(size_t)(s0 + r) * FRAME_SIZE + c * 32 + lane] = tile[r][lane];
     __syncwarp();
   }
   if (s < a.S) { a.hp_mem[2 * s] = m0; a.hp_mem[2 * s + 1] = m1; }
 }
 
-__global__ void __launch_bounds__(DSP_THREADS) k_analysis(Arena a, const DspTables *__restrict__ T) {
+__global__ void __launch_bounds__(DSP_THREADS) k_analysis(Arena a, const DspTables *__restrict__ T, int f) {
   extern __shared__ float sm[];
   const int s = blockIdx.x;
-  const int f = a.ctr[0] - 1, par = f & 1;
+  const int par = f & 1;
   AnalysisArgs g;
-  g.xb = a.xb + (size_t)s * FRAME_SIZE;
+  g.xb = a.xb + ((size_t)par * a.S + s) * FRAME_SIZE;
   g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
   g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
   g.spec_out = a.spec + ((size_t)par * a.S + s) * (4 * FREQ_SIZE);
@@ -103,10 +103,10 @@ __global__ void __launch_bounds__(DSP_THREADS) k_analysis(Arena a, const DspTabl
 }
 
 __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTables *__restrict__ T,
-                                                           float *__restrict__ out) {
+                                                           float *__restrict__ out, int f) {
   extern __shared__ float sm[];
   const int s = blockIdx.x;
-  const int f = a.ctr[0] - 1, par = f & 1;
+  const int par = f & 1;
   SynthesisArgs g;
   g.spec_delayed = a.spec + ((size_t)(par ^ 1) * a.S + s) * (4 * FREQ_SIZE);
   g.band_delayed = a.band + ((size_t)(par ^ 1) * a.S + s) * 96;
@@ -132,9 +132,11 @@ struct B200Engine {
   // host-buffer calls: double-buffered device staging, copy streams and the events that chain
   // H2D(n) -> compute(n) -> D2H(n) while protecting slot reuse two frames later
   float *stage_in[2], *stage_out[2], *stage_vad[2];
-  cudaStream_t s_h2d, s_d2h;
+  cudaStream_t s_h2d, s_d2h, s_bq;
   cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
+  cudaEvent_t ev_bq[2], ev_ana[2];   // biquad of frame f done / analysis of frame f done (xb slot free)
   long long host_frames;
+  long long bq_frames;               // frames whose high-pass prefilter has been issued
   int use_tc;                       // GRU kernel: 2 = k_tc2<true> (default), 1 = k_gru_tc, 0 = dp4a cross-check
   int conv2_tc;                     // conv2 kernel: 1 = k_tc2<false> (default), 0 = dp4a cross-check
   GruTcMaps tc_maps[2][3];          // [frame parity][layer]
@@ -240,10 +242,13 @@ extern "C" void b200_engine_destroy(B200Engine *e) {
   for (int i = 0; i <= NKERNELS; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->s_h2d) { cudaStreamSynchronize(e->s_h2d); cudaStreamDestroy(e->s_h2d); }
   if (e->s_d2h) { cudaStreamSynchronize(e->s_d2h); cudaStreamDestroy(e->s_d2h); }
+  if (e->s_bq) { cudaStreamSynchronize(e->s_bq); cudaStreamDestroy(e->s_bq); }
   for (int i = 0; i < 2; i++) {
     if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
     if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
     if (e->ev_d2h[i]) cudaEventDestroy(e->ev_d2h[i]);
+    if (e->ev_bq[i]) cudaEventDestroy(e->ev_bq[i]);
+    if (e->ev_ana[i]) cudaEventDestroy(e->ev_ana[i]);
   }
   for (void *p : e->allocs) cudaFree(p);
   delete e;
@@ -256,8 +261,8 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
     return nullptr;
   }
   if (!m || S < 1 || device < 0 || device >= ndev) return nullptr;
-  if (m->gru % 128 || m->cond % 4 || m->gru > 1024 || m->cond > 512) {
-    fprintf(stderr, "[rnnoise_b200] unsupported model dims cond=%d gru=%d (need gru %% 128 == 0)\n", m->cond, m->gru);
+  if (m->gru % 128 || m->cond % 4 || m->gru > 1024 || m->cond > 128) {
+    fprintf(stderr, "[rnnoise_b200] unsupported model dims cond=%d gru=%d (need gru %% 128 == 0, cond <= 128)\n", m->cond, m->gru);
     return nullptr;
   }
   if (cudaSetDevice(device) != cudaSuccess) return nullptr;
@@ -273,7 +278,6 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   a.S = S; a.cond = m->cond; a.gru = m->gru;
   const size_t Ss = (size_t)S;
   bool ok = true;
-  ok &= !!(a.ctr = dalloc<int>(e, 4));
   ok &= !!(a.ring = dalloc<float>(e, Ss * PITCH_BUF_SIZE));
   ok &= !!(a.synth_mem = dalloc<float>(e, Ss * FRAME_SIZE));
   ok &= !!(a.hp_mem = dalloc<float>(e, Ss * 2));
@@ -288,21 +292,25 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   ok &= !!(a.hbuf_u8 = dalloc<uint8_t>(e, 2 * 3 * Ss * m->gru));
   ok &= !!(a.conv2_out_u8 = dalloc<uint8_t>(e, Ss * m->gru));
   if (ok) ok = cudaMemset(a.hbuf_u8, 127, 2 * 3 * Ss * m->gru) == cudaSuccess;   // u8 image of h = 0
-  ok &= !!(a.xb = dalloc<float>(e, Ss * FRAME_SIZE));
+  ok &= !!(a.xb = dalloc<float>(e, 2 * Ss * FRAME_SIZE));
   ok &= !!(a.features = dalloc<float>(e, Ss * NB_FEATURES));
   ok &= !!(a.silence = dalloc<int>(e, Ss));
   ok &= !!(a.conv2_out = dalloc<float>(e, Ss * m->gru));
   ok &= !!(a.gains = dalloc<float>(e, Ss * NB_BANDS));
   ok &= !!(a.vad = dalloc<float>(e, Ss));
   e->host_frames = 0;
-  e->s_h2d = e->s_d2h = nullptr;
+  e->bq_frames = 0;
+  e->s_h2d = e->s_d2h = e->s_bq = nullptr;
+  ok &= cudaStreamCreateWithFlags(&e->s_bq, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 2; i++) {
     ok &= !!(e->stage_in[i] = dalloc<float>(e, Ss * FRAME_SIZE));
     ok &= !!(e->stage_out[i] = dalloc<float>(e, Ss * FRAME_SIZE));
     ok &= !!(e->stage_vad[i] = dalloc<float>(e, Ss));
-    e->ev_h2d[i] = e->ev_comp[i] = e->ev_d2h[i] = nullptr;
+    e->ev_h2d[i] = e->ev_comp[i] = e->ev_d2h[i] = e->ev_bq[i] = e->ev_ana[i] = nullptr;
+    ok &= cudaEventCreateWithFlags(&e->ev_bq[i], cudaEventDisableTiming) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&e->ev_ana[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
@@ -377,16 +385,26 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
   }
   int ki = 0;
 #define MARK() do { if (e->profiling) cudaEventRecord(e->ev[ki++], st); } while (0)
+  const int fr = (int)(e->frames & 0x3fffffff);
   MARK();
-  k_biquad<<<(S + 31) / 32, 32, 0, st>>>(a, d_in);
+  if (e->bq_frames > e->frames) {
+    // the prefilter of this frame was issued ahead on the biquad stream (prefilter hint / pipelined
+    // host call): just order the rest of the frame after it
+    CK(cudaStreamWaitEvent(st, e->ev_bq[par], 0));
+  } else {
+    k_biquad<<<(S + 31) / 32, 32, 0, st>>>(a, d_in, fr);
+    CK(cudaEventRecord(e->ev_bq[par], st));
+    e->bq_frames = e->frames + 1;
+  }
   MARK();
-  k_analysis<<<S, DSP_THREADS, SM_TOTAL * sizeof(float), st>>>(a, e->d_tables);
+  k_analysis<<<S, DSP_THREADS, SM_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr);
+  CK(cudaEventRecord(e->ev_ana[par], st));
   MARK();
   const int gts = (S + RNN_TS - 1) / RNN_TS;
   k_conv1<<<gts, 128, 0, st>>>(S, e->dm, a.features, a.conv1_state, a.silence, a.c2in);
   MARK();
   if (e->conv2_tc)
-    k_tc2<false><<<dim3((S + TC_M - 1) / TC_M, 4), 288, tc2_smem_bytes<false>(3 * cond, gru), st>>>(
+    k_tc2<false><<<dim3((S + TC_M - 1) / TC_M, 4), P_THREADS, tc2_smem_bytes<false>(3 * cond, gru), st>>>(
         S, 3 * cond, gru, e->conv_maps, e->dm.conv2, e->dm.conv2, nullptr, a.conv2_out, a.conv2_out_u8, a.silence);
   else
     k_conv2<<<gts, 128, RNN_TS * (3 * cond / 4) * sizeof(uint32_t), st>>>(S, e->dm, a.c2in, a.conv2_out, a.conv2_out_u8);
@@ -395,7 +413,7 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
   for (int l = 0; l < 3; l++) {
     uint8_t *hu8_new = a.hbuf_u8 + ((size_t)par * 3 + l) * hstride;
     if (e->use_tc == 2) {
-      k_tc2<true><<<dim3((S + TC_M - 1) / TC_M, 4), 288, tc2_smem_bytes<true>(gru, gru), st>>>(
+      k_tc2<true><<<dim3((S + TC_M - 1) / TC_M, 4), P_THREADS, tc2_smem_bytes<true>(gru, gru), st>>>(
           S, gru, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, a.silence);
     } else if (e->use_tc == 1) {
       k_gru_tc<<<dim3((S + TC_M - 1) / TC_M, gru / TC_UNITS), 160, gru_tc_smem_bytes(gru), st>>>(
@@ -409,7 +427,7 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
   k_heads<<<(S + HEAD_TS - 1) / HEAD_TS, 160, 0, st>>>(S, e->dm, a.conv2_out, h_new[0], h_new[1], h_new[2], a.silence,
                                                       a.gains, a.vad, d_vad);
   MARK();
-  k_synthesis<<<S, DSP_THREADS, SS_TOTAL * sizeof(float), st>>>(a, e->d_tables, d_out);
+  k_synthesis<<<S, DSP_THREADS, SS_TOTAL * sizeof(float), st>>>(a, e->d_tables, d_out, fr);
   MARK();
 #undef MARK
   CK(cudaGetLastError());
@@ -426,17 +444,41 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
   return 0;
 }
 
+// Issue the high-pass prefilter of the next not-yet-prefiltered frame on the biquad stream.
+// `ready` (optional) = event after which d_in is valid.  At most two frames ahead of processing.
+static int issue_prefilter(B200Engine *e, const float *d_in, cudaEvent_t ready) {
+  if (e->bq_frames >= e->frames + 2) return -1;
+  const long long f = e->bq_frames;
+  const int slot = (int)(f & 1);
+  if (ready) CK(cudaStreamWaitEvent(e->s_bq, ready, 0));
+  CK(cudaStreamWaitEvent(e->s_bq, e->ev_ana[slot], 0));       // frame f-2 no longer reads this xb half
+  CK(cudaStreamWaitEvent(e->s_bq, e->ev_bq[slot ^ 1], 0));    // biquad state: after frame f-1's filter
+  k_biquad<<<(e->a.S + 31) / 32, 32, 0, e->s_bq>>>(e->a, d_in, (int)(f & 0x3fffffff));
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e->ev_bq[slot], e->s_bq));
+  e->bq_frames = f + 1;
+  return 0;
+}
+
+extern "C" int b200_engine_prefilter_device(B200Engine *e, const float *d_in) {
+  if (!e || !d_in) return -1;
+  CK(cudaSetDevice(e->device));
+  return issue_prefilter(e, d_in, nullptr);
+}
+
 extern "C" int b200_engine_frame_host_async(B200Engine *e, float *out, const float *in, float *vad) {
   if (!e || !out || !in) return -1;
+  if (e->bq_frames != e->frames) return -1;   // a device-side prefilter hint is pending: do not mix
   CK(cudaSetDevice(e->device));
   const size_t n = (size_t)e->a.S * FRAME_SIZE * sizeof(float);
   const int slot = (int)(e->host_frames & 1);
-  // copy-in: the staging slot is free once frame n-2 has been computed
-  CK(cudaStreamWaitEvent(e->s_h2d, e->ev_comp[slot], 0));
+  // copy-in: the staging slot is free once the prefilter of frame n-2 has consumed it
+  CK(cudaStreamWaitEvent(e->s_h2d, e->ev_bq[slot], 0));
   CK(cudaMemcpyAsync(e->stage_in[slot], in, n, cudaMemcpyHostToDevice, e->s_h2d));
   CK(cudaEventRecord(e->ev_h2d[slot], e->s_h2d));
-  // compute: needs this frame's input, and frame n-2's output staging drained
-  CK(cudaStreamWaitEvent(e->stream, e->ev_h2d[slot], 0));
+  // high-pass prefilter on its own stream: overlaps the previous frame's kernels
+  if (issue_prefilter(e, e->stage_in[slot], e->ev_h2d[slot])) return -1;
+  // rest of the frame: needs frame n-2's output staging drained
   CK(cudaStreamWaitEvent(e->stream, e->ev_d2h[slot], 0));
   if (b200_engine_frame_device(e, e->stage_out[slot], e->stage_in[slot], e->stage_vad[slot])) return -1;
   CK(cudaEventRecord(e->ev_comp[slot], e->stream));
@@ -459,6 +501,7 @@ extern "C" int b200_engine_sync(B200Engine *e) {
   if (!e) return -1;
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->s_h2d));
+  CK(cudaStreamSynchronize(e->s_bq));
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaStreamSynchronize(e->s_d2h));
   return 0;
@@ -532,7 +575,7 @@ extern "C" int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst
     case RNNOISE_DBG_EXP: src = a.band + ((size_t)par * S + s) * 96 + 64; n = 32; break;
     case RNNOISE_DBG_GAINS: src = a.gains + (size_t)s * NB_BANDS; n = NB_BANDS; break;
     case RNNOISE_DBG_LASTG: src = a.lastg + (size_t)s * NB_BANDS; n = NB_BANDS; break;
-    case RNNOISE_DBG_XB: src = a.xb + (size_t)s * FRAME_SIZE; n = FRAME_SIZE; break;
+    case RNNOISE_DBG_XB: src = a.xb + ((size_t)par * S + s) * FRAME_SIZE; n = FRAME_SIZE; break;
     case RNNOISE_DBG_GRU1: case RNNOISE_DBG_GRU2: case RNNOISE_DBG_GRU3:
       src = a.hbuf + (((size_t)par * 3 + (what - RNNOISE_DBG_GRU1)) * S + s) * a.gru; n = a.gru; break;
     case RNNOISE_DBG_CONV1_STATE: src = a.conv1_state + (size_t)s * 2 * NB_FEATURES; n = 2 * NB_FEATURES; break;

@@ -20,6 +20,7 @@ int b200_engine_frame_device(B200Engine *e, float *d_out, const float *d_in, flo
 /* One frame, host pointers (copies in, runs, copies out, synchronises). */
 int b200_engine_frame_host(B200Engine *e, float *out, const float *in, float *vad);
 int b200_engine_frame_host_async(B200Engine *e, float *out, const float *in, float *vad);
+int b200_engine_prefilter_device(B200Engine *e, const float *d_in);
 int b200_engine_sync(B200Engine *e);
 int b200_engine_set_stream(B200Engine *e, void *cuda_stream);
 int b200_engine_reset_stream(B200Engine *e, int stream);

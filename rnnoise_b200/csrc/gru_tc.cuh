@@ -239,14 +239,14 @@ k_gru_tc(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, D
 //
 // CTA = 128 streams x (N/4) output units, processed as slices of 16 units through a three-deep TMA ring
 // for the weight slices and a two-deep TMEM ring for the accumulators:
-//     warp 8 (one elected thread): TMA producer + tcgen05.mma issuer
-//     warps 0..7 (256 threads)   : epilogue -- warp w reads TMEM lane quarter (w & 3), units 8*(w>>2)..+8
+//     warp 16 (one elected thread): TMA producer + tcgen05.mma issuer
+//     warps 0..15 (512 threads)   : epilogue -- warp w reads TMEM lane quarter (w & 3), units 4*(w>>2)..+4
 // so that  TMA(slice s+2) || MMA(slice s+1) || epilogue(slice s).  The u8 activation tiles (128 x K;
 // GRU: Xu8 and Hu8) are loaded once per CTA and stay resident.  Per slice and matrix one
 // tcgen05.mma.kind::i8 chain of K/32 instructions, M128 x N48 (GRU: z|r|n of 16 units) or N16 (conv2);
 // accumulators: GRU [in z|r|n (48) | rec z|r|n (48)] = 96 TMEM columns per stage, conv2 16.
 // Same arithmetic as the dp4a kernels k_gru / k_conv2: bit-identical results.
-// grid = (ceil(S/128), 4), block = 288, 1 CTA / SM.
+// grid = (ceil(S/128), 4), block = 544, 1 CTA / SM.
 // ================================================================================================
 #define P_SLICE 16
 #define P_STAGES 3
@@ -268,9 +268,12 @@ __host__ __device__ constexpr int tc2_smem_bytes(int K, int N) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+#define P_EPI_WARPS 16                    // epilogue warps: 4 per TMEM lane quarter
+#define P_UPT (P_SLICE / (P_EPI_WARPS / 4))   // units per epilogue thread and slice: 4
+#define P_THREADS (32 * (P_EPI_WARPS + 1))
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
                : "r"(taddr)
                : "memory");
 }
@@ -279,7 +282,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
 // GRU : maps.x/h = Xu8/Hu8 [S][K]; maps.wi/wr = s8 [(N/16) x 48][K];  out = h_new (+u8), aux = h_old
 // conv: maps.x = conv2 input u8 [S][K]; maps.wi = s8 [N][K] (unit-major); out = conv2_out (+u8)
 template <bool kGru>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(P_THREADS, 1)
 k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, DevLayerQ wr,
       const float *__restrict__ h_old, float *__restrict__ out_f32, uint8_t *__restrict__ out_u8,
       const int *__restrict__ silence) {
@@ -304,7 +307,7 @@ k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi,
   if (tid == 0) {
     mbar_init(bar_a, 1);
     for (int i = 0; i < P_STAGES; i++) { mbar_init(bar_bfull(i), 1); mbar_init(bar_bempty(i), 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(bar_tfull(i), 1); mbar_init(bar_tempty(i), 8); }
+    for (int i = 0; i < 2; i++) { mbar_init(bar_tfull(i), 1); mbar_init(bar_tempty(i), P_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -325,7 +328,7 @@ k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi,
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == P_EPI_WARPS) {
     if (lane == 0) {
       auto load_B = [&](int s) {
         const int st = s % P_STAGES;
@@ -375,15 +378,14 @@ k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi,
     const bool live = srow < S;
     const bool silent = live ? silence[srow] != 0 : true;
     const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
-    float hcur[8], hnext[8];
-    auto load_h = [&](int s, float (&dst)[8]) {
+    float hcur[P_UPT], hnext[P_UPT];
+    auto load_h = [&](int s, float (&dst)[P_UPT]) {
       if (kGru && live && s < nslice) {
-        const float4 *p = (const float4 *)&h_old[(size_t)srow * N + jq + s * P_SLICE + ch * 8];
-        float4 a = __ldg(p), b = __ldg(p + 1);
-        dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
+        float4 a = __ldg((const float4 *)&h_old[(size_t)srow * N + jq + s * P_SLICE + ch * P_UPT]);
+        dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
       } else {
 #pragma unroll
-        for (int q = 0; q < 8; q++) dst[q] = 0.f;
+        for (int q = 0; q < P_UPT; q++) dst[q] = 0.f;
       }
     };
     load_h(0, hcur);
@@ -392,20 +394,20 @@ k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi,
       load_h(s + 1, hnext);
       mbar_wait(bar_tfull(ts), (uint32_t)((s >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t t0 = trow + ts * C::kCols + ch * 8;
-      const int ub = s * P_SLICE + ch * 8;     // unit index inside this CTA's quarter
-      float outv[8];
+      const uint32_t t0 = trow + ts * C::kCols + ch * P_UPT;
+      const int ub = s * P_SLICE + ch * P_UPT;     // unit index inside this CTA's quarter
+      float outv[P_UPT];
       if (kGru) {
-        int az[8], ar[8], an[8], bz[8], br[8], bn[8];
-        tmem_ld8(t0 + 0 * P_SLICE, az); tmem_ld8(t0 + 1 * P_SLICE, ar); tmem_ld8(t0 + 2 * P_SLICE, an);
-        tmem_ld8(t0 + C::kN + 0 * P_SLICE, bz); tmem_ld8(t0 + C::kN + 1 * P_SLICE, br); tmem_ld8(t0 + C::kN + 2 * P_SLICE, bn);
+        int az[P_UPT], ar[P_UPT], an[P_UPT], bz[P_UPT], br[P_UPT], bn[P_UPT];
+        tmem_ld4(t0 + 0 * P_SLICE, az); tmem_ld4(t0 + 1 * P_SLICE, ar); tmem_ld4(t0 + 2 * P_SLICE, an);
+        tmem_ld4(t0 + C::kN + 0 * P_SLICE, bz); tmem_ld4(t0 + C::kN + 1 * P_SLICE, br); tmem_ld4(t0 + C::kN + 2 * P_SLICE, bn);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         // accumulators are in registers: hand the TMEM stage back to the MMA issuer
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty(ts));
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
+        for (int q = 0; q < P_UPT; q++) {
           const int u = ub + q;
           const float h = hcur[q];
           float out = h;
@@ -424,26 +426,21 @@ k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi,
           outv[q] = out;
         }
       } else {
-        int acc[8];
-        tmem_ld8(t0, acc);
+        int acc[P_UPT];
+        tmem_ld4(t0, acc);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty(ts));
 #pragma unroll
-        for (int q = 0; q < 8; q++) outv[q] = act_tanh((float)acc[q] * prm[ub + q] + prm[upc + ub + q]);
+        for (int q = 0; q < P_UPT; q++) outv[q] = act_tanh((float)acc[q] * prm[ub + q] + prm[upc + ub + q]);
       }
       if (live) {
-        float *dst = &out_f32[(size_t)srow * N + jq + ub];
-        *(float4 *)&dst[0] = make_float4(outv[0], outv[1], outv[2], outv[3]);
-        *(float4 *)&dst[4] = make_float4(outv[4], outv[5], outv[6], outv[7]);
-        uint2 pk;
-        pk.x = quant4(outv[0], outv[1], outv[2], outv[3]);
-        pk.y = quant4(outv[4], outv[5], outv[6], outv[7]);
-        *(uint2 *)&out_u8[(size_t)srow * N + jq + ub] = pk;
+        *(float4 *)&out_f32[(size_t)srow * N + jq + ub] = make_float4(outv[0], outv[1], outv[2], outv[3]);
+        *(uint32_t *)&out_u8[(size_t)srow * N + jq + ub] = quant4(outv[0], outv[1], outv[2], outv[3]);
       }
 #pragma unroll
-      for (int q = 0; q < 8; q++) hcur[q] = hnext[q];
+      for (int q = 0; q < P_UPT; q++) hcur[q] = hnext[q];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }

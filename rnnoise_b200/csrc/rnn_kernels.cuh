@@ -52,6 +52,12 @@ __device__ __forceinline__ int dp4a_us(uint32_t u, int w, int acc) { // 4 x (u8 
   return d;
 }
 
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 16 : 0;   // src-size 0 -> 16 bytes of zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
 // Device-resident model (built by engine.cu from the parsed blob).
 struct DevLayerF { const float *w, *bias; };                               // w[in][out]
 struct DevLayerQ { const int *wp; const float *scale, *subias, *diag; };   // wp[in/4][out] packed s8x4
@@ -68,14 +74,27 @@ struct DevModel {
 // form in which conv2 ever sees its inputs, vec_avx.h:326): on a non-silent frame the row is rotated
 // left by cond bytes (compute_generic_conv1d's memory update, nnet.c:122) and the new output appended.
 // ------------------------------------------------------------------------------------------------
+#define C1_KC 32
+#define C1_XS 196   // row stride of the staged inputs (195 + 1: keeps rows 16-byte aligned)
 __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *__restrict__ features,
                                                float *conv1_state, const int *__restrict__ silence,
                                                uint8_t *c2in) {
-  __shared__ float tmp[RNN_TS][3 * NB_FEAT + 1];
-  __shared__ uint32_t rot[RNN_TS][128];          // 2*cond/4 words per stream (cond <= 256)
-  const int s0 = blockIdx.x * RNN_TS, tid = threadIdx.x, W = m.cond / 4;
-  for (int idx = tid; idx < RNN_TS * 3 * NB_FEAT; idx += 128) {
-    int s = idx / (3 * NB_FEAT), j = idx % (3 * NB_FEAT);
+  __shared__ __align__(16) float tmp[RNN_TS][C1_XS];
+  __shared__ __align__(16) float wsm[2][C1_KC][128];   // weight chunks, double-buffered (cond <= 128)
+  __shared__ uint32_t rot[RNN_TS][64];                  // 2*cond/4 words per stream
+  const int s0 = blockIdx.x * RNN_TS, tid = threadIdx.x, W = m.cond / 4, cond = m.cond;
+  constexpr int KIN = 3 * NB_FEAT, NCH = (KIN + C1_KC - 1) / C1_KC;
+  auto stage = [&](int c, int buf) {
+    const int j0 = c * C1_KC, rows = min(C1_KC, KIN - j0);
+    for (int idx = tid; idx < rows * W; idx += 128) {
+      int r = idx / W, q = idx % W;
+      cp_async16(&wsm[buf][r][4 * q], &m.conv1.w[(size_t)(j0 + r) * cond + 4 * q], true);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0, 0);
+  for (int idx = tid; idx < RNN_TS * KIN; idx += 128) {
+    int s = idx / KIN, j = idx % KIN;
     float v = 0.f;
     if (s0 + s < S) v = j < 2 * NB_FEAT ? conv1_state[(size_t)(s0 + s) * 2 * NB_FEAT + j]
                                          : features[(size_t)(s0 + s) * NB_FEAT + j - 2 * NB_FEAT];
@@ -83,28 +102,51 @@ __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *_
   }
   for (int idx = tid; idx < RNN_TS * 2 * W; idx += 128) {   // words [W, 3W) of each live row
     int s = idx / (2 * W), w = idx % (2 * W);
-    if (s0 + s < S) rot[s][w] = ((const uint32_t *)(c2in + (size_t)(s0 + s) * 3 * m.cond))[W + w];
+    if (s0 + s < S) rot[s][w] = ((const uint32_t *)(c2in + (size_t)(s0 + s) * 3 * cond))[W + w];
   }
   __syncthreads();
   for (int idx = tid; idx < RNN_TS * 2 * W; idx += 128) {
     int s = idx / (2 * W), w = idx % (2 * W);
-    if (s0 + s < S && !silence[s0 + s]) ((uint32_t *)(c2in + (size_t)(s0 + s) * 3 * m.cond))[w] = rot[s][w];
+    if (s0 + s < S && !silence[s0 + s]) ((uint32_t *)(c2in + (size_t)(s0 + s) * 3 * cond))[w] = rot[s][w];
   }
-  for (int o = tid; o < m.cond; o += 128) {
-    float acc[RNN_TS];
+  const int o = tid;
+  float acc[RNN_TS];
 #pragma unroll
-    for (int s = 0; s < RNN_TS; s++) acc[s] = 0.f;
-#pragma unroll 13
-    for (int j = 0; j < 3 * NB_FEAT; j++) {
-      float w = __ldg(&m.conv1.w[(size_t)j * m.cond + o]);
-#pragma unroll
-      for (int s = 0; s < RNN_TS; s++) acc[s] = fmaf(w, tmp[s][j], acc[s]);
+  for (int s = 0; s < RNN_TS; s++) acc[s] = 0.f;
+  for (int c = 0; c < NCH; c++) {
+    const int buf = c & 1, j0 = c * C1_KC, rows = min(C1_KC, KIN - j0);
+    if (c + 1 < NCH) {
+      stage(c + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
+    __syncthreads();
+    if (o < cond) {
+      int jj = 0;
+      for (; jj + 4 <= rows; jj += 4) {   // sequential FMA chain over the inputs, 4 at a time
+        const float w0 = wsm[buf][jj][o], w1 = wsm[buf][jj + 1][o], w2 = wsm[buf][jj + 2][o], w3 = wsm[buf][jj + 3][o];
+#pragma unroll
+        for (int s = 0; s < RNN_TS; s++) {
+          const float4 x = *(const float4 *)&tmp[s][j0 + jj];
+          acc[s] = fmaf(w0, x.x, acc[s]); acc[s] = fmaf(w1, x.y, acc[s]);
+          acc[s] = fmaf(w2, x.z, acc[s]); acc[s] = fmaf(w3, x.w, acc[s]);
+        }
+      }
+      for (; jj < rows; jj++) {
+        const float w = wsm[buf][jj][o];
+#pragma unroll
+        for (int s = 0; s < RNN_TS; s++) acc[s] = fmaf(w, tmp[s][j0 + jj], acc[s]);
+      }
+    }
+    __syncthreads();
+  }
+  if (o < cond) {
     const float b = m.conv1.bias[o];
 #pragma unroll
     for (int s = 0; s < RNN_TS; s++)
       if (s0 + s < S && !silence[s0 + s])
-        c2in[(size_t)(s0 + s) * 3 * m.cond + 2 * m.cond + o] = (uint8_t)quant_u8(act_tanh(acc[s] + b));
+        c2in[(size_t)(s0 + s) * 3 * cond + 2 * cond + o] = (uint8_t)quant_u8(act_tanh(acc[s] + b));
   }
   // memory update: mem = tmp[65:195]; silent frames leave the state untouched (denoise.c:474)
   for (int idx = tid; idx < RNN_TS * 2 * NB_FEAT; idx += 128) {
@@ -234,11 +276,6 @@ __global__ void __launch_bounds__(128) k_gru(int S, int gru, DevLayerQ wi, DevLa
 #define HEAD_TS 16
 #define HEAD_KC 64
 #define HEAD_XS (HEAD_KC + 4)
-__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-  const int sz = valid ? 16 : 0;   // src-size 0 -> 16 bytes of zero fill
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
-}
 __global__ void __launch_bounds__(160) k_heads(int S, DevModel m, const float *__restrict__ c2,
                                                const float *__restrict__ g1, const float *__restrict__ g2,
                                                const float *__restrict__ g3, const int *__restrict__ silence,

@@ -130,6 +130,9 @@ int rnnoise_process_frame_batch_device(RNNoiseBatch *b, float *d_out, const floa
   return b200_engine_frame_device(b->engine, d_out, d_in, d_vad);
 }
 
+int rnnoise_batch_prefilter_device(RNNoiseBatch *b, const float *d_in_next) {
+  return b && d_in_next ? b200_engine_prefilter_device(b->engine, d_in_next) : -1;
+}
 int rnnoise_batch_sync(RNNoiseBatch *b) { return b ? b200_engine_sync(b->engine) : -1; }
 int rnnoise_batch_set_stream(RNNoiseBatch *b, void *s) { return b ? b200_engine_set_stream(b->engine, s) : -1; }
 int rnnoise_batch_reset_stream(RNNoiseBatch *b, int s) { return b ? b200_engine_reset_stream(b->engine, s) : -1; }

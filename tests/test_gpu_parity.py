@@ -253,3 +253,25 @@ def test_async_pipelined_host_call_equals_synchronous(rb, models_dir):
         ro, rv = a.process(pcm[f].numpy())
         assert np.array_equal(bits(outs[f].numpy()), bits(ro)) and np.array_equal(bits(vads[f].numpy()), bits(rv)), f
     a.destroy(); b.destroy(); model.free()
+
+
+def test_prefilter_hint_path_equals_plain_device_call(rb, models_dir):
+    """rnnoise_batch_prefilter_device() only moves the high-pass biquad of the next frame onto another
+    stream; results must not change."""
+    import torch
+    model = rb.Model(os.path.join(models_dir, "default.bin"))
+    S, frames = 200, 8
+    a, b = rb.Batch(model, S), rb.Batch(model, S)
+    pcm = torch.from_numpy(batch_pcm(S, frames)).cuda()
+    oa, ob = torch.empty(S, 480, device="cuda"), torch.empty(S, 480, device="cuda")
+    va, vb = torch.empty(S, device="cuda"), torch.empty(S, device="cuda")
+    torch.cuda.synchronize()
+    b.prefilter_device(pcm[0].data_ptr())
+    for f in range(frames):
+        a.process_device(oa.data_ptr(), pcm[f].data_ptr(), va.data_ptr())
+        if f + 1 < frames:
+            b.prefilter_device(pcm[f + 1].data_ptr())
+        b.process_device(ob.data_ptr(), pcm[f].data_ptr(), vb.data_ptr())
+        a.sync(); b.sync()
+        assert torch.equal(oa, ob) and torch.equal(va, vb), f
+    a.destroy(); b.destroy(); model.free()
