@@ -34,7 +34,8 @@ MODEL = os.path.join(ROOT, "tests", "golden", "models", "default.bin")
 # per kernel, counting each array the kernel must read or write once:
 KERNEL_BYTES = {
     "k_biquad": 480 * 4 * 2 + 16,                                   # in -> xb, hp state
-    "k_analysis": (480 + 1248 + 480 + 2 * 962 + 96 + 65 + 1 + 4) * 4,  # xb, ring old/new, X+P, bands, features
+    "k_pitch": (480 + 1248 + 480 + 4) * 4,                          # xb, ring history read, new frame appended, pitch state
+    "k_spectrum": (1728 + 2 * 962 + 96 + 65 + 1 + 2) * 4,           # ring (both windows), X+P, bands, features, flags
     "k_synthesis": (2 * 962 + 96 + 32 + 32 + 2 * 32 + 2 * 480 + 480) * 4,
 }
 

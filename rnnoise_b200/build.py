@@ -43,7 +43,8 @@ def build(force=False, verbose=False):
         cmds.append(["gcc", "-O2", "-fPIC", "-Wall", "-fvisibility=hidden", "-DRNNOISE_BUILD", "-c", os.path.join(CSRC, c), "-o", o])
         cobjs.append(o)
     eo = os.path.join(obj, "engine.cu.o")
-    cmds.append([NVCC, *ARCH, "-O3", "-lineinfo", "--fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-DRNNOISE_BUILD",
+    extra = os.environ.get("RNNOISE_B200_NVCC_FLAGS", "").split()
+    cmds.append([NVCC, *ARCH, *extra, "-O3", "-lineinfo", "--fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-DRNNOISE_BUILD",
                  "-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, "engine.cu"), "-o", eo])
     cmds.append([NVCC, *ARCH, "-shared", "-o", SO, *cobjs, eo, "-cudart", "static"])
     for cmd in cmds:

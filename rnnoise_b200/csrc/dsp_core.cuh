@@ -54,12 +54,14 @@ struct DspTables {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Shared-memory plan of one stream (floats).  Pitch scratch and FFT scratch overlay each other.
+// Shared-memory plans (floats).  The analysis of one frame is two kernels, each CTA = one stream:
+//   pitch kernel    : whitened half-rate signal + search scratch          (SM_PITCH_END + SM_MISC_SIZE)
+//   spectrum kernel : FFT work buffer + a copy of X for the X.P correlation (SM_SPEC_END + SM_MISC_SIZE)
+// The pitch history itself stays in HBM/L2 (ring): it is read once, in order, by the decimation and
+// gathered once per FFT by stage 1.
 // ------------------------------------------------------------------------------------------------
-#define SM_PB 0                          // [1728] linearised pitch history incl. the new frame
-#define SM_U (SM_PB + PITCH_BUF_SIZE)    // union region
-//   pitch phase
-#define SM_LP (SM_U)                     // [864] whitened half-rate signal
+//   pitch kernel
+#define SM_LP 0                          // [864] whitened half-rate signal
 #define SM_LP0 (SM_LP + LP_SIZE)         // [864] decimated signal before whitening (dies after FIR)
 #define SM_X4 (SM_LP0)                   // [240]   (reuses LP0 once the FIR is done)
 #define SM_Y4 (SM_X4 + 240)              // [388]
@@ -68,23 +70,30 @@ struct DspTables {
 #define SM_YYL (SM_SYY + 296)            // [392] yy_lookup
 #define SM_DOT (SM_YYL + 392)            // [64]  remove_doubling dot products
 #define SM_PITCH_END (SM_DOT + 64)
-//   spectrum phase
-#define SM_F (SM_U)                      // [1920] FFT work buffer (interleaved complex)
+//   spectrum kernel
+#define SM_F 0                           // [1920] FFT work buffer (interleaved complex)
 #define SM_XS (SM_F + 2 * WINDOW_SIZE)   // [962] X kept for the X.P correlation
 #define SM_SPEC_END (SM_XS + 2 * FREQ_SIZE)
-#define SM_UNION_END (SM_PITCH_END > SM_SPEC_END ? SM_PITCH_END : SM_SPEC_END)
-#define SM_MISC (SM_UNION_END)           // [288] small per-stream scalars / band vectors
-#define SM_TOTAL (SM_MISC + 288)
-// misc slots (float indices relative to SM_MISC)
+#define SM_MISC_SIZE 288                 // small per-stream scalars / band vectors, after either plan
+#define SM_PITCH_TOTAL (SM_PITCH_END + SM_MISC_SIZE)
+#define SM_SPEC_TOTAL (SM_SPEC_END + SM_MISC_SIZE)
+// misc slots (float indices relative to the misc base)
 #define MI_AC 0     // [5] autocorrelation
 #define MI_NUM 8    // [5] whitening FIR taps
 #define MI_INT 16   // ints: [0]=best0 [1]=best1 [2]=T (pitch index) [3]=silence [4]=T0 half-rate
 #define MI_BAND 32  // [3][34] band sums (X, P, X.P)
 #define MI_E 136    // [3][32] Ex, Ep, Exp
 #define MI_LY 232   // [32] log band energies
-static_assert(SM_LP0 + LP_SIZE <= SM_UNION_END, "lp0 overlay");
+static_assert(SM_LP0 + LP_SIZE <= SM_PITCH_END, "lp0 overlay");
 static_assert(SM_LP % 4 == 0 && SM_X4 % 4 == 0 && SM_Y4 % 4 == 0 && SM_SYY % 4 == 0 && (SM_LP + 384) % 4 == 0,
               "single-lane chains use 16-byte vector loads");
+
+// logical sample k of the updated 1728-sample pitch history (after this frame's shift)
+HD float ring_at(const float *ring, int ring_base, int k) {
+  int p = ring_base + k;
+  if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
+  return ring[p];
+}
 
 // ------------------------------------------------------------------------------------------------
 // 960-point forward FFT stages (src/kiss_fft.c:101-316; stage order rnn_fft_impl:518-564).
@@ -100,9 +109,10 @@ HD cpx csub(cpx a, cpx b) { cpx m; m.r = a.r - b.r; m.i = a.i - b.i; return m; }
 
 // Stage 1 (radix 4, m = 1) fused with the bit-reversed, scaled, windowed load: group g gathers
 // its four inputs straight from `src` (kiss_fft.c:577-584 + kf_bfly4 m==1 branch :112-130).
-// Input element i of the transform is win(i) * src[i] (imag 0) when `herm` is null, or the
-// Hermitian extension of herm[0..480] (inverse_transform, denoise.c:200-211).
-HD void fft_stage1(cpx *F, const float *src, const cpx *herm, const DspTables *T, int tid, int nthr) {
+// Input element i of the transform is win(i) * history[start + i] (imag 0) when `herm` is null
+// (history = the pitch ring, logical index start + i), or the Hermitian extension of herm[0..480]
+// (inverse_transform, denoise.c:200-211).
+HD void fft_stage1(cpx *F, const float *ring, int ring_base, int start, const cpx *herm, const DspTables *T, int tid, int nthr) {
   for (int g = tid; g < 240; g += nthr) {
     int j0 = g / 48, j1 = (g / 16) % 3, j2 = (g / 4) % 4, j3 = g % 4;
     int base = j0 + 5 * j1 + 15 * j2 + 60 * j3;
@@ -116,7 +126,7 @@ HD void fft_stage1(cpx *F, const float *src, const cpx *herm, const DspTables *T
         else { v.r = herm[WINDOW_SIZE - i].r; v.i = -herm[WINDOW_SIZE - i].i; }
       } else {
         int wi = i < FRAME_SIZE ? i : WINDOW_SIZE - 1 - i;
-        v.r = src[i] * T->half_window[wi];
+        v.r = ring_at(ring, ring_base, start + i) * T->half_window[wi];
         v.i = 0.f;
       }
       a[q].r = T->fft_scale * v.r;

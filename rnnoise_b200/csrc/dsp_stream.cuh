@@ -12,43 +12,51 @@
 #define PHASE_END }
 #endif
 
-struct AnalysisArgs {
+struct PitchArgs {
   const float *xb;      // [480]  this stream's frame after the high-pass biquad
   float *ring;          // [1728] pitch-history ring of this stream
   int ring_base;        // physical index of logical sample 0 AFTER this frame's 480-sample shift
+  float *pitch_state;   // [2] {last_period as int bits, last_gain}: read as the prior, then updated
+};
+struct SpectrumArgs {
+  const float *ring;    // [1728] ring, already holding this frame
+  int ring_base;
+  const float *pitch_state; // [2] this frame's pitch period (int bits) from the pitch kernel
   float *spec_out;      // [2][962] X then P of this frame (becomes "delayed" next frame)
   float *band_out;      // [3][32]  Ex, Ep, Exp
   float *features;      // [65]
   int *silence;         // [1]
-  float *pitch_state;   // [2] {last_period as int bits, last_gain}
 };
 
-// rnn_compute_frame_features (src/denoise.c:347-398) incl. rnn_frame_analysis (:332-345),
-// rnn_pitch_downsample / rnn_pitch_search / rnn_remove_doubling (src/pitch.c:146,281,423).
-HD void analysis_stream(float *sm, const AnalysisArgs a, const DspTables *T) {
-  float *pb = sm + SM_PB, *lp = sm + SM_LP, *lp0 = sm + SM_LP0, *x4 = sm + SM_X4, *y4 = sm + SM_Y4;
+// Pitch half of rnn_compute_frame_features (src/denoise.c:359-370): rnn_pitch_downsample /
+// rnn_pitch_search / rnn_remove_doubling (src/pitch.c:146,281,423).
+HD void pitch_stream(float *sm, const PitchArgs a, const DspTables *T) {
+  float *lp = sm + SM_LP, *lp0 = sm + SM_LP0, *x4 = sm + SM_X4, *y4 = sm + SM_Y4;
   float *xc = sm + SM_XC, *syy = sm + SM_SYY, *yyl = sm + SM_YYL, *dot = sm + SM_DOT;
-  float *misc = sm + SM_MISC;
+  float *misc = sm + SM_PITCH_END;
   int *mi = (int *)(misc + MI_INT);
-  cpx *F = (cpx *)(sm + SM_F), *XS = (cpx *)(sm + SM_XS);
+  (void)T;
 
-  // -- load the shifted history, append the new frame (denoise.c:359-360; ring instead of memmove)
+  // -- append the new frame to the history ring (denoise.c:359-360; a ring instead of the memmove) and
+  //    decimate by 2 straight from HBM/L2 (pitch.c:171-173).  The 480 ring slots being overwritten hold
+  //    the oldest samples, which the decimation never reads: no hazard inside the phase.
   PHASE_BEGIN
-    for (int i = tid; i < PITCH_BUF_SIZE - FRAME_SIZE; i += nthr) {
-      int p = a.ring_base + i; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
-      pb[i] = a.ring[p];
-    }
     for (int j = tid; j < FRAME_SIZE; j += nthr) {
-      float v = a.xb[j];
       int p = a.ring_base + PITCH_BUF_SIZE - FRAME_SIZE + j; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
-      pb[PITCH_BUF_SIZE - FRAME_SIZE + j] = v;
-      a.ring[p] = v;
+      a.ring[p] = a.xb[j];
     }
-  PHASE_END
-  // -- 2x decimation (pitch.c:171-173)
-  PHASE_BEGIN
-    for (int i = tid; i < LP_SIZE; i += nthr)
-      lp0[i] = i ? .5f * (.5f * (pb[2 * i - 1] + pb[2 * i + 1]) + pb[2 * i]) : .5f * (.5f * pb[1] + pb[0]);
+    for (int i = tid; i < LP_SIZE; i += nthr) {
+      const int k = 2 * i;
+      // sample k of the updated history: old ring part for k < 1248, this frame after that
+      const float c = k < PITCH_BUF_SIZE - FRAME_SIZE ? ring_at(a.ring, a.ring_base, k) : a.xb[k - (PITCH_BUF_SIZE - FRAME_SIZE)];
+      const float r = k + 1 < PITCH_BUF_SIZE - FRAME_SIZE ? ring_at(a.ring, a.ring_base, k + 1) : a.xb[k + 1 - (PITCH_BUF_SIZE - FRAME_SIZE)];
+      if (i) {
+        const float l = k - 1 < PITCH_BUF_SIZE - FRAME_SIZE ? ring_at(a.ring, a.ring_base, k - 1) : a.xb[k - 1 - (PITCH_BUF_SIZE - FRAME_SIZE)];
+        lp0[i] = .5f * (.5f * (l + r) + c);
+      } else {
+        lp0[i] = .5f * (.5f * r + c);
+      }
+    }
   PHASE_END
   // -- autocorrelation lags 0..4 (celt_lpc.c:92-174: first n-4 samples, then the tail)
   PHASE_BEGIN
@@ -267,9 +275,18 @@ HD void analysis_stream(float *sm, const AnalysisArgs a, const DspTables *T) {
       a.pitch_state[1] = pg;
     }
   PHASE_END
+}
+
+// Spectral half of rnn_compute_frame_features (src/denoise.c:358, 371-397) incl. rnn_frame_analysis
+// (:332-345): X, P, band energies / correlation, log-energy features, silence test.
+HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
+  float *misc = sm + SM_SPEC_END;
+  int *mi = (int *)(misc + MI_INT);
+  cpx *F = (cpx *)(sm + SM_F), *XS = (cpx *)(sm + SM_XS);
+  const int pitch_T = ((const int *)a.pitch_state)[0];
   // -- X = FFT(window * [previous frame | this frame]) (denoise.c:332-339); the analysis window
   //    is the last 960 samples of the updated pitch history.
-  PHASE_BEGIN fft_stage1(F, pb + PITCH_BUF_SIZE - WINDOW_SIZE, nullptr, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_stage1(F, a.ring, a.ring_base, PITCH_BUF_SIZE - WINDOW_SIZE, nullptr, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
@@ -283,7 +300,7 @@ HD void analysis_stream(float *sm, const AnalysisArgs a, const DspTables *T) {
     if (tid < NB_BANDS + 2) misc[MI_BAND + tid] = band_sum_one(tid, F, F, T);
   PHASE_END
   // -- P = FFT(window * pitch_buf[768-T .. 768-T+960)) (denoise.c:371-374)
-  PHASE_BEGIN fft_stage1(F, pb + PITCH_BUF_SIZE - WINDOW_SIZE - mi[2], nullptr, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_stage1(F, a.ring, a.ring_base, PITCH_BUF_SIZE - WINDOW_SIZE - pitch_T, nullptr, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
@@ -340,7 +357,7 @@ HD void analysis_stream(float *sm, const AnalysisArgs a, const DspTables *T) {
       float v = dct_one(misc + MI_E + 64, tid - NB_BANDS, T);
       a.features[tid] = silent ? 0.f : v;
     } else if (tid == 2 * NB_BANDS) {
-      a.features[tid] = silent ? 0.f : (float)(.01 * (mi[2] - 300));
+      a.features[tid] = silent ? 0.f : (float)(.01 * (pitch_T - 300));
     }
   PHASE_END
 }
@@ -428,7 +445,7 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       }
     PHASE_END
   }
-  PHASE_BEGIN fft_stage1(F, nullptr, X, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_stage1(F, nullptr, 0, 0, X, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END

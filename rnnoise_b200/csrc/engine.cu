@@ -1,7 +1,7 @@
 // engine.cu -- device arena, model upload and the per-frame kernel sequence of the B200 engine.
 //
 // One frame of every stream =
-//   k_biquad (thread/stream)  -> k_analysis (CTA/stream) -> k_conv1 -> k_conv2 -> k_gru x3 -> k_heads
+//   k_biquad (thread/stream) -> k_pitch, k_spectrum (CTA/stream) -> k_conv1 -> conv2 -> GRU x3 -> k_heads
 //   -> k_synthesis (CTA/stream)
 // state lives in HBM between frames (layout: DESIGN.md "Data layout"); the frame index (host-side
 // counter, passed to the kernels) selects the ping-pong halves and the pitch-ring base.  k_biquad
@@ -86,20 +86,33 @@ __global__ void __launch_bounds__(32) k_biquad(Arena a, const float *__restrict_
   if (s < a.S) { a.hp_mem[2 * s] = m0; a.hp_mem[2 * s + 1] = m1; }
 }
 
-__global__ void __launch_bounds__(DSP_THREADS) k_analysis(Arena a, const DspTables *__restrict__ T, int f) {
+#ifndef PITCH_MIN_BLOCKS
+#define PITCH_MIN_BLOCKS 16   // 32 registers/thread: 16 resident streams per SM hide the serial chains
+#endif
+__global__ void __launch_bounds__(DSP_THREADS, PITCH_MIN_BLOCKS) k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
+  extern __shared__ float sm[];
+  const int s = blockIdx.x;
+  PitchArgs g;
+  g.xb = a.xb + ((size_t)(f & 1) * a.S + s) * FRAME_SIZE;
+  g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
+  g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+  g.pitch_state = a.pitch_state + 2 * (size_t)s;
+  pitch_stream(sm, g, T);
+}
+
+__global__ void __launch_bounds__(DSP_THREADS) k_spectrum(Arena a, const DspTables *__restrict__ T, int f) {
   extern __shared__ float sm[];
   const int s = blockIdx.x;
   const int par = f & 1;
-  AnalysisArgs g;
-  g.xb = a.xb + ((size_t)par * a.S + s) * FRAME_SIZE;
+  SpectrumArgs g;
   g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
   g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+  g.pitch_state = a.pitch_state + 2 * (size_t)s;
   g.spec_out = a.spec + ((size_t)par * a.S + s) * (4 * FREQ_SIZE);
   g.band_out = a.band + ((size_t)par * a.S + s) * 96;
   g.features = a.features + (size_t)s * NB_FEATURES;
   g.silence = a.silence + s;
-  g.pitch_state = a.pitch_state + 2 * (size_t)s;
-  analysis_stream(sm, g, T);
+  spectrum_stream(sm, g, T);
 }
 
 __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTables *__restrict__ T,
@@ -120,7 +133,7 @@ __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTab
 }
 
 // ------------------------------------------------------------------------------------------------
-#define NKERNELS 9
+#define NKERNELS 10
 struct B200Engine {
   int device;
   Arena a;
@@ -146,7 +159,7 @@ struct B200Engine {
   cudaEvent_t ev[NKERNELS + 1];
   double prof_ms[NKERNELS];
 };
-static const char *const kKernelNames[NKERNELS] = {"k_biquad", "k_analysis", "k_conv1", "k_conv2", "k_gru[0]",
+static const char *const kKernelNames[NKERNELS] = {"k_biquad", "k_pitch", "k_spectrum", "k_conv1", "k_conv2", "k_gru[0]",
                                                    "k_gru[1]", "k_gru[2]", "k_heads", "k_synthesis"};
 
 template <typename T>
@@ -397,8 +410,10 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
     e->bq_frames = e->frames + 1;
   }
   MARK();
-  k_analysis<<<S, DSP_THREADS, SM_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr);
-  CK(cudaEventRecord(e->ev_ana[par], st));
+  k_pitch<<<S, DSP_THREADS, SM_PITCH_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr);
+  CK(cudaEventRecord(e->ev_ana[par], st));   // xb[par] is free again
+  MARK();
+  k_spectrum<<<S, DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr);
   MARK();
   const int gts = (S + RNN_TS - 1) / RNN_TS;
   k_conv1<<<gts, 128, 0, st>>>(S, e->dm, a.features, a.conv1_state, a.silence, a.c2in);

@@ -18,7 +18,7 @@ struct EmuState {
   float features[NB_FEATURES], xb[FRAME_SIZE];
   int silence;
   long frames;
-  alignas(16) float sm[SM_TOTAL > SS_TOTAL ? SM_TOTAL : SS_TOTAL];
+  alignas(16) float sm[8192];   // >= max(SM_PITCH_TOTAL, SM_SPEC_TOTAL, SS_TOTAL)
 };
 
 extern "C" {
@@ -38,16 +38,22 @@ int emu_analysis(void *p, const float *in, float *xb, float *features, float *X,
   e->hp[0] = m0; e->hp[1] = m1;
   const long f = e->frames;
   const int par = (int)(f & 1);
-  AnalysisArgs a;
-  a.xb = e->xb;
+  static_assert(SM_PITCH_TOTAL <= 8192 && SM_SPEC_TOTAL <= 8192 && SS_TOTAL <= 8192, "emu scratch");
+  PitchArgs pa;
+  pa.xb = e->xb;
+  pa.ring = e->ring;
+  pa.ring_base = (int)(((f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+  pa.pitch_state = e->pitch_state;
+  pitch_stream(e->sm, pa, &e->T);
+  SpectrumArgs a;
   a.ring = e->ring;
-  a.ring_base = (int)(((f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+  a.ring_base = pa.ring_base;
+  a.pitch_state = e->pitch_state;
   a.spec_out = e->spec[par];
   a.band_out = e->band[par];
   a.features = e->features;
   a.silence = &e->silence;
-  a.pitch_state = e->pitch_state;
-  analysis_stream(e->sm, a, &e->T);
+  spectrum_stream(e->sm, a, &e->T);
   memcpy(xb, e->xb, sizeof(e->xb));
   memcpy(features, e->features, sizeof(e->features));
   memcpy(X, e->spec[par], 2 * FREQ_SIZE * sizeof(float));
