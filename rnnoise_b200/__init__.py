@@ -21,6 +21,14 @@ DBG = dict(features=0, X=1, P=2, Ex=3, Ep=4, Exp=5, gains=6, lastg=7, xb=8, gru1
 _lib = None
 
 
+def shard(total_streams, world_size, rank):
+    """Contiguous stream shard of `rank`: streams are independent, so multi-GPU use is one batch per
+    device over [first, first + count) with no collective."""
+    base, rem = divmod(int(total_streams), int(world_size))
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
 def lib():
     """Loads the shared library (building is __graft_entry__.build()'s / build.py's job)."""
     global _lib
