@@ -171,6 +171,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     if W > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(DSP_THREADS, PITCH_MIN_BLOCKS) k_pitch(Arena a
   pitch_stream(sm, g, T);
 }
 
-__global__ void __launch_bounds__(DSP_THREADS) k_spectrum(Arena a, const DspTables *__restrict__ T, int f) {
+#ifndef SPEC_MIN_BLOCKS
+#define SPEC_MIN_BLOCKS 12
+#endif
+__global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena a, const DspTables *__restrict__ T, int f) {
   extern __shared__ float sm[];
   const int s = blockIdx.x;
   const int par = f & 1;
