@@ -98,12 +98,6 @@ HD float ring_at(const float *ring, int ring_base, int k) {
 // ------------------------------------------------------------------------------------------------
 // 960-point forward FFT stages (src/kiss_fft.c:101-316; stage order rnn_fft_impl:518-564).
 // ------------------------------------------------------------------------------------------------
-// Shared-memory slot of FFT element i.  The mixed-radix stages touch elements 16g+j+4k (m=4) and
-// 64g+j+16k (m=16): an XOR of the low four index bits with higher digits spreads every stage's
-// warp-wide 8-byte accesses over all 16 bank pairs (simulated wavefronts per transform: 1088 -> 624,
-// ideal 540) without padding.  Every reader/writer of the work buffer goes through FSW().
-#define FSW(i) ((i) ^ ((((i) >> 4) & 3) << 2) ^ (((i) >> 6) & 3))
-
 HD cpx cmul(cpx a, cpx b) {
   cpx m;
   m.r = a.r * b.r - a.i * b.i;
@@ -146,28 +140,28 @@ HD void fft_stage1(cpx *F, const float *ring, int ring_base, int start, const cp
     s1 = csub(a[1], a[3]);
     a[1].r = s0.r + s1.i; a[1].i = s0.i - s1.r;
     a[3].r = s0.r - s1.i; a[3].i = s0.i + s1.r;
-    F[FSW(4 * g + 0)] = a[0]; F[FSW(4 * g + 1)] = a[1]; F[FSW(4 * g + 2)] = a[2]; F[FSW(4 * g + 3)] = a[3];
+    F[4 * g + 0] = a[0]; F[4 * g + 1] = a[1]; F[4 * g + 2] = a[2]; F[4 * g + 3] = a[3];
   }
 }
 // generic radix-4 stage: `m` butterflies per group, groups `gstride` apart, twiddle stride fs
 HD void fft_radix4(cpx *F0, int m, int gstride, int fs, const DspTables *T, int tid, int nthr) {
   for (int b = tid; b < 240; b += nthr) {
     int g = b / m, j = b % m;
-    const int i0 = g * gstride + j, i1 = i0 + m, i2 = i0 + 2 * m, i3 = i0 + 3 * m;
-    cpx s0 = cmul(F0[FSW(i1)], T->tw[j * fs]);
-    cpx s1 = cmul(F0[FSW(i2)], T->tw[2 * j * fs]);
-    cpx s2 = cmul(F0[FSW(i3)], T->tw[3 * j * fs]);
-    cpx f0 = F0[FSW(i0)];
+    cpx *F = F0 + g * gstride + j;
+    cpx s0 = cmul(F[m], T->tw[j * fs]);
+    cpx s1 = cmul(F[2 * m], T->tw[2 * j * fs]);
+    cpx s2 = cmul(F[3 * m], T->tw[3 * j * fs]);
+    cpx f0 = F[0];
     cpx s5 = csub(f0, s1);
     f0 = cadd(f0, s1);
     cpx s3 = cadd(s0, s2);
     cpx s4 = csub(s0, s2);
-    F0[FSW(i2)] = csub(f0, s3);
-    F0[FSW(i0)] = cadd(f0, s3);
+    F[2 * m] = csub(f0, s3);
+    F[0] = cadd(f0, s3);
     cpx o1, o3;
     o1.r = s5.r + s4.i; o1.i = s5.i - s4.r;
     o3.r = s5.r - s4.i; o3.i = s5.i + s4.r;
-    F0[FSW(i1)] = o1; F0[FSW(i3)] = o3;
+    F[m] = o1; F[3 * m] = o3;
   }
 }
 HD void fft_radix3(cpx *F0, const DspTables *T, int tid, int nthr) { // m = 64, 5 groups of 192
@@ -175,49 +169,49 @@ HD void fft_radix3(cpx *F0, const DspTables *T, int tid, int nthr) { // m = 64, 
   const float epi3 = T->tw[fs * m].i;
   for (int b = tid; b < 320; b += nthr) {
     int g = b / m, j = b % m;
-    const int i0 = g * 192 + j, i1 = i0 + m, i2 = i0 + 2 * m;
-    cpx s1 = cmul(F0[FSW(i1)], T->tw[j * fs]);
-    cpx s2 = cmul(F0[FSW(i2)], T->tw[2 * j * fs]);
+    cpx *F = F0 + g * 192 + j;
+    cpx s1 = cmul(F[m], T->tw[j * fs]);
+    cpx s2 = cmul(F[2 * m], T->tw[2 * j * fs]);
     cpx s3 = cadd(s1, s2);
     cpx s0 = csub(s1, s2);
-    cpx f0 = F0[FSW(i0)], f1;
+    cpx f0 = F[0], f1;
     f1.r = f0.r - s3.r * .5f;
     f1.i = f0.i - s3.i * .5f;
     s0.r *= epi3; s0.i *= epi3;
-    F0[FSW(i0)] = cadd(f0, s3);
+    F[0] = cadd(f0, s3);
     cpx o2, o1;
     o2.r = f1.r + s0.i; o2.i = f1.i - s0.r;
     o1.r = f1.r - s0.i; o1.i = f1.i + s0.r;
-    F0[FSW(i2)] = o2; F0[FSW(i1)] = o1;
+    F[2 * m] = o2; F[m] = o1;
   }
 }
 HD void fft_radix5(cpx *F, const DspTables *T, int tid, int nthr) { // m = 192, one group
   const int m = 192;
   const cpx ya = T->tw[m], yb = T->tw[2 * m];
   for (int u = tid; u < m; u += nthr) {
-    cpx s0 = F[FSW(u)];
-    cpx s1 = cmul(F[FSW(u + m)], T->tw[u]);
-    cpx s2 = cmul(F[FSW(u + 2 * m)], T->tw[2 * u]);
-    cpx s3 = cmul(F[FSW(u + 3 * m)], T->tw[3 * u]);
-    cpx s4 = cmul(F[FSW(u + 4 * m)], T->tw[4 * u]);
+    cpx s0 = F[u];
+    cpx s1 = cmul(F[u + m], T->tw[u]);
+    cpx s2 = cmul(F[u + 2 * m], T->tw[2 * u]);
+    cpx s3 = cmul(F[u + 3 * m], T->tw[3 * u]);
+    cpx s4 = cmul(F[u + 4 * m], T->tw[4 * u]);
     cpx s7 = cadd(s1, s4), s10 = csub(s1, s4), s8 = cadd(s2, s3), s9 = csub(s2, s3);
     cpx o0;
     o0.r = s0.r + (s7.r + s8.r);
     o0.i = s0.i + (s7.i + s8.i);
-    F[FSW(u)] = o0;
+    F[u] = o0;
     cpx s5, s6, s11, s12;
     s5.r = s0.r + (s7.r * ya.r + s8.r * yb.r);
     s5.i = s0.i + (s7.i * ya.r + s8.i * yb.r);
     s6.r = s10.i * ya.i + s9.i * yb.i;
     s6.i = -(s10.r * ya.i + s9.r * yb.i);
-    F[FSW(u + m)] = csub(s5, s6);
-    F[FSW(u + 4 * m)] = cadd(s5, s6);
+    F[u + m] = csub(s5, s6);
+    F[u + 4 * m] = cadd(s5, s6);
     s11.r = s0.r + (s7.r * yb.r + s8.r * ya.r);
     s11.i = s0.i + (s7.i * yb.r + s8.i * ya.r);
     s12.r = s9.i * ya.i - s10.i * yb.i;
     s12.i = s10.r * yb.i - s9.r * ya.i;
-    F[FSW(u + 2 * m)] = cadd(s11, s12);
-    F[FSW(u + 3 * m)] = csub(s11, s12);
+    F[u + 2 * m] = cadd(s11, s12);
+    F[u + 3 * m] = csub(s11, s12);
   }
 }
 
@@ -226,13 +220,12 @@ HD void fft_radix5(cpx *F, const DspTables *T, int tid, int nthr) { // m = 192, 
 // sum[b] (b = 0..33) and adds its terms in the reference's order: first the frac*t terms of band
 // b-1, then the (1-frac)*t terms of band b.  which: 0 -> |A|^2, 1 -> Re(A conj B).
 // ------------------------------------------------------------------------------------------------
-// swA / swB: operand lives in an FFT work buffer (FSW-swizzled slots) rather than in natural order
-HD float band_sum_one(int b, const cpx *A, const cpx *B, const DspTables *T, bool swA, bool swB) {
+HD float band_sum_one(int b, const cpx *A, const cpx *B, const DspTables *T) {
   float sum = 0.f;
   if (b >= 1) {
     for (int k = T->eband[b - 1]; k < T->eband[b]; k++) {
       const float frac = T->bin_frac[k];      // == (float)j / band_size, tabulated (no divide in the loop)
-      cpx a = A[swA ? FSW(k) : k], c = B[swB ? FSW(k) : k];
+      cpx a = A[k], c = B[k];
       float t = a.r * c.r;
       t += a.i * c.i;
       sum += frac * t;
@@ -241,7 +234,7 @@ HD float band_sum_one(int b, const cpx *A, const cpx *B, const DspTables *T, boo
   if (b <= NB_BANDS) {
     for (int k = T->eband[b]; k < T->eband[b + 1]; k++) {
       const float frac = T->bin_frac[k];
-      cpx a = A[swA ? FSW(k) : k], c = B[swB ? FSW(k) : k];
+      cpx a = A[k], c = B[k];
       float t = a.r * c.r;
       t += a.i * c.i;
       sum += (1 - frac) * t;

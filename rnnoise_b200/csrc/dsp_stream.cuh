@@ -293,11 +293,11 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_BEGIN fft_radix5(F, T, tid, nthr); PHASE_END
   PHASE_BEGIN
     for (int i = tid; i < FREQ_SIZE; i += nthr) {
-      cpx v = F[FSW(i)];
+      cpx v = F[i];
       XS[i] = v;
       ((cpx *)a.spec_out)[i] = v;
     }
-    if (tid < NB_BANDS + 2) misc[MI_BAND + tid] = band_sum_one(tid, F, F, T, true, true);
+    if (tid < NB_BANDS + 2) misc[MI_BAND + tid] = band_sum_one(tid, F, F, T);
   PHASE_END
   // -- P = FFT(window * pitch_buf[768-T .. 768-T+960)) (denoise.c:371-374)
   PHASE_BEGIN fft_stage1(F, a.ring, a.ring_base, PITCH_BUF_SIZE - WINDOW_SIZE - pitch_T, nullptr, T, tid, nthr); PHASE_END
@@ -306,9 +306,9 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix5(F, T, tid, nthr); PHASE_END
   PHASE_BEGIN
-    for (int i = tid; i < FREQ_SIZE; i += nthr) ((cpx *)a.spec_out)[FREQ_SIZE + i] = F[FSW(i)];
-    if (tid < NB_BANDS + 2) misc[MI_BAND + 34 + tid] = band_sum_one(tid, F, F, T, true, true);
-    else if (tid >= 64 && tid < 64 + NB_BANDS + 2) misc[MI_BAND + 68 + tid - 64] = band_sum_one(tid - 64, XS, F, T, false, true);
+    for (int i = tid; i < FREQ_SIZE; i += nthr) ((cpx *)a.spec_out)[FREQ_SIZE + i] = F[i];
+    if (tid < NB_BANDS + 2) misc[MI_BAND + 34 + tid] = band_sum_one(tid, F, F, T);
+    else if (tid >= 64 && tid < 64 + NB_BANDS + 2) misc[MI_BAND + 68 + tid - 64] = band_sum_one(tid - 64, XS, F, T);
   PHASE_END
   // -- Ex, Ep, Exp (denoise.c:344,375-377)
   PHASE_BEGIN
@@ -418,7 +418,7 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       }
     PHASE_END
     PHASE_BEGIN
-      if (tid < NB_BANDS + 2) sums[tid] = band_sum_one(tid, X, X, T, false, false);
+      if (tid < NB_BANDS + 2) sums[tid] = band_sum_one(tid, X, X, T);
     PHASE_END
     PHASE_BEGIN
       if (tid < NB_BANDS) {
@@ -453,8 +453,8 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
   PHASE_BEGIN
     for (int i = tid; i < FRAME_SIZE; i += nthr) {
       // t[i] = 960 * y[(960 - i) % 960].re, windowed; out = first half + overlap memory
-      float t0 = WINDOW_SIZE * F[FSW(i ? WINDOW_SIZE - i : 0)].r;
-      float t1 = WINDOW_SIZE * F[FSW(WINDOW_SIZE - (FRAME_SIZE + i))].r;   // index 480+i -> y[480-i]
+      float t0 = WINDOW_SIZE * F[i ? WINDOW_SIZE - i : 0].r;
+      float t1 = WINDOW_SIZE * F[WINDOW_SIZE - (FRAME_SIZE + i)].r;   // index 480+i -> y[480-i]
       t0 *= T->half_window[i];
       t1 *= T->half_window[FRAME_SIZE - 1 - i];
       a.out[i] = t0 + a.synthesis_mem[i];
