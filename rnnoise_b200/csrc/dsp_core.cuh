@@ -50,6 +50,7 @@ struct DspTables {
   short eband[NB_BANDS + 2];       // src/denoise.c:63-65
   unsigned char bin_band[400];     // triangular segment (0..32) that holds bin k
   float bin_frac[400];             // (float)j / band_size of bin k inside its segment (denoise.c:100,148)
+  float bin_cfrac[400];            // 1 - bin_frac[k], the weight towards the lower band (denoise.c:103)
   float fft_scale;                 // rnnoise_tables.c:562 literal
 };
 
@@ -73,7 +74,8 @@ struct DspTables {
 //   spectrum kernel
 #define SM_F 0                           // [1920] FFT work buffer (interleaved complex)
 #define SM_XS (SM_F + 2 * WINDOW_SIZE)   // [962] X kept for the X.P correlation
-#define SM_SPEC_END (SM_XS + 2 * FREQ_SIZE)
+#define SM_TB (SM_XS + 2 * FREQ_SIZE)     // [3][400] per-bin terms |X|^2, |P|^2, Re(X conj P) for the band sums
+#define SM_SPEC_END (SM_TB + 3 * 400)
 #define SM_MISC_SIZE 288                 // small per-stream scalars / band vectors, after either plan
 #define SM_PITCH_TOTAL (SM_PITCH_END + SM_MISC_SIZE)
 #define SM_SPEC_TOTAL (SM_SPEC_END + SM_MISC_SIZE)
@@ -241,6 +243,21 @@ HD float band_sum_one(int b, const cpx *A, const cpx *B, const DspTables *T) {
     }
   }
   return sum;
+}
+// Same sums from per-bin terms t[k] precomputed by parallel lanes (t = a.r*c.r; t += a.i*c.i, exactly
+// as above) and tabulated weights: leaves two loads + FMUL + FADD per step on the serial lanes.
+HD float band_sum_terms(int b, const float *t, const DspTables *T) {
+  float sum = 0.f;
+  if (b >= 1)
+    for (int k = T->eband[b - 1]; k < T->eband[b]; k++) sum += T->bin_frac[k] * t[k];
+  if (b <= NB_BANDS)
+    for (int k = T->eband[b]; k < T->eband[b + 1]; k++) sum += T->bin_cfrac[k] * t[k];
+  return sum;
+}
+HD float bin_term(cpx a, cpx c) {
+  float t = a.r * c.r;
+  t += a.i * c.i;
+  return t;
 }
 // sum[34] -> E[32] with the edge-band fix-up (denoise.c:107-112)
 HD float band_finish(const float *sum, int b) {

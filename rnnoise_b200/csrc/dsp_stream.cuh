@@ -29,135 +29,185 @@ struct SpectrumArgs {
 };
 
 // Pitch half of rnn_compute_frame_features (src/denoise.c:359-370): rnn_pitch_downsample /
-// rnn_pitch_search / rnn_remove_doubling (src/pitch.c:146,281,423).
-HD void pitch_stream(float *sm, const PitchArgs a, const DspTables *T) {
-  float *lp = sm + SM_LP, *lp0 = sm + SM_LP0, *x4 = sm + SM_X4, *y4 = sm + SM_Y4;
-  float *xc = sm + SM_XC, *syy = sm + SM_SYY, *yyl = sm + SM_YYL, *dot = sm + SM_DOT;
-  float *misc = sm + SM_PITCH_END;
-  int *mi = (int *)(misc + MI_INT);
-  (void)T;
+// rnn_pitch_search / rnn_remove_doubling (src/pitch.c:146,281,423) for PITCH_NS streams per CTA.
+//
+// The pitch analysis is dominated by SERIAL float chains (each lag's dot product, the running
+// energies, the selection scans) that occupy 1..10 lanes of a warp.  A CTA therefore owns PITCH_NS
+// streams: phases whose work is wide (decimation, FIR, the 30-lane correlations) run on the 128
+// threads of each stream's own warp quartet, while the narrow chains of ALL the CTA's streams are
+// packed side by side into the lanes of one or two warps -- same instructions, PITCH_NS x the useful
+// lanes.  Thread ids: q = tid / 128 is the stream a thread belongs to, t = tid % 128 its local id;
+// packed phases use the first lanes of the CTA instead.
+#ifndef PITCH_NS
+#define PITCH_NS 4
+#endif
+#if defined(__CUDA_ARCH__)
+#define MPHASE_BEGIN { const int tid = threadIdx.x; const int q = tid >> 7, t = tid & 127; (void)q; (void)t;
+#define MPHASE_END } __syncthreads();
+#else
+#define MPHASE_BEGIN for (int tid = 0; tid < PITCH_NS * DSP_THREADS; ++tid) { const int q = tid >> 7, t = tid & 127; (void)q; (void)t;
+#define MPHASE_END }
+#endif
+#define PSM(qq) (sm + (qq) * SM_PITCH_TOTAL)
 
+// a[q].ring == nullptr marks an absent stream (batch size not a multiple of PITCH_NS)
+HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
+  (void)T;
   // -- append the new frame to the history ring (denoise.c:359-360; a ring instead of the memmove) and
   //    decimate by 2 straight from HBM/L2 (pitch.c:171-173).  The 480 ring slots being overwritten hold
   //    the oldest samples, which the decimation never reads: no hazard inside the phase.
-  PHASE_BEGIN
-    for (int j = tid; j < FRAME_SIZE; j += nthr) {
-      int p = a.ring_base + PITCH_BUF_SIZE - FRAME_SIZE + j; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
-      a.ring[p] = a.xb[j];
-    }
-    for (int i = tid; i < LP_SIZE; i += nthr) {
-      const int k = 2 * i;
-      // sample k of the updated history: old ring part for k < 1248, this frame after that
-      const float c = k < PITCH_BUF_SIZE - FRAME_SIZE ? ring_at(a.ring, a.ring_base, k) : a.xb[k - (PITCH_BUF_SIZE - FRAME_SIZE)];
-      const float r = k + 1 < PITCH_BUF_SIZE - FRAME_SIZE ? ring_at(a.ring, a.ring_base, k + 1) : a.xb[k + 1 - (PITCH_BUF_SIZE - FRAME_SIZE)];
-      if (i) {
-        const float l = k - 1 < PITCH_BUF_SIZE - FRAME_SIZE ? ring_at(a.ring, a.ring_base, k - 1) : a.xb[k - 1 - (PITCH_BUF_SIZE - FRAME_SIZE)];
-        lp0[i] = .5f * (.5f * (l + r) + c);
-      } else {
-        lp0[i] = .5f * (.5f * r + c);
+  MPHASE_BEGIN
+    if (a[q].ring) {
+      const PitchArgs A = a[q];
+      float *lp0 = PSM(q) + SM_LP0;
+      const int H = PITCH_BUF_SIZE - FRAME_SIZE;
+      for (int j = t; j < FRAME_SIZE; j += DSP_THREADS) {
+        int p = A.ring_base + H + j; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
+        A.ring[p] = A.xb[j];
+      }
+      for (int i = t; i < LP_SIZE; i += DSP_THREADS) {
+        const int k = 2 * i;
+        // sample k of the updated history: old ring part for k < 1248, this frame after that
+        const float c = k < H ? ring_at(A.ring, A.ring_base, k) : A.xb[k - H];
+        const float r = k + 1 < H ? ring_at(A.ring, A.ring_base, k + 1) : A.xb[k + 1 - H];
+        if (i) {
+          const float l = k - 1 < H ? ring_at(A.ring, A.ring_base, k - 1) : A.xb[k - 1 - H];
+          lp0[i] = .5f * (.5f * (l + r) + c);
+        } else {
+          lp0[i] = .5f * (.5f * r + c);
+        }
       }
     }
-  PHASE_END
-  // -- autocorrelation lags 0..4 (celt_lpc.c:92-174: first n-4 samples, then the tail)
-  PHASE_BEGIN
-    if (tid < 5) {
-      const int k = tid, fastN = LP_SIZE - 4;
+  MPHASE_END
+  // -- autocorrelation lags 0..4 (celt_lpc.c:92-174: first n-4 samples, then the tail): 5 lanes per
+  //    stream, all streams packed into warp 0 (lane = 8 * stream + lag)
+  MPHASE_BEGIN
+    if (tid < 8 * PITCH_NS && (tid & 7) < 5 && a[tid >> 3].ring) {
+      const int qq = tid >> 3, k = tid & 7, fastN = LP_SIZE - 4;
+      const float *lp0 = PSM(qq) + SM_LP0;
       float s = 0.f;
+#pragma unroll 4
       for (int j = 0; j < fastN; j++) s = s + lp0[j] * lp0[j + k];
       float d = 0.f;
       for (int i = k + fastN; i < LP_SIZE; i++) d = d + lp0[i] * lp0[i - k];
-      misc[MI_AC + k] = s + d;
+      PSM(qq)[SM_PITCH_END + MI_AC + k] = s + d;
     }
-  PHASE_END
-  PHASE_BEGIN
-    if (tid == 0) lpc_taps(misc + MI_AC, misc + MI_NUM);
-  PHASE_END
+  MPHASE_END
+  MPHASE_BEGIN
+    if (tid < PITCH_NS && a[tid].ring) lpc_taps(PSM(tid) + SM_PITCH_END + MI_AC, PSM(tid) + SM_PITCH_END + MI_NUM);
+  MPHASE_END
   // -- 5-tap whitening FIR with zero history (celt_fir5, pitch.c:104-143)
-  PHASE_BEGIN
-    for (int i = tid; i < LP_SIZE; i += nthr) {
-      float sum = lp0[i];
+  MPHASE_BEGIN
+    if (a[q].ring) {
+      const float *lp0 = PSM(q) + SM_LP0, *num = PSM(q) + SM_PITCH_END + MI_NUM;
+      float *lp = PSM(q) + SM_LP;
+      for (int i = t; i < LP_SIZE; i += DSP_THREADS) {
+        float sum = lp0[i];
 #pragma unroll
-      for (int k = 0; k < 5; k++) {
-        float m = (i - 1 - k >= 0) ? lp0[i - 1 - k] : 0.f;
-        sum = sum + misc[MI_NUM + k] * m;
+        for (int k = 0; k < 5; k++) {
+          float m = (i - 1 - k >= 0) ? lp0[i - 1 - k] : 0.f;
+          sum = sum + num[k] * m;
+        }
+        lp[i] = sum;
       }
-      lp[i] = sum;
     }
-  PHASE_END
+  MPHASE_END
   // -- second 2x decimation (pitch.c:305-308); the same lanes also form d[i] = y4[i+240]^2 - y4[i]^2,
   //    the increments of find_best_pitch's running energy (pitch.c:99)
-  PHASE_BEGIN
-    for (int j = tid; j < 240; j += nthr) x4[j] = lp[384 + 2 * j];
-    for (int j = tid; j < 388; j += nthr) y4[j] = j < 387 ? lp[2 * j] : 0.f;
-    for (int i = tid; i < 147; i += nthr) {
-      float hi = lp[2 * (i + 240)], lo = lp[2 * i];
-      syy[i] = hi * hi - lo * lo;
+  MPHASE_BEGIN
+    if (a[q].ring) {
+      const float *lp = PSM(q) + SM_LP;
+      float *x4 = PSM(q) + SM_X4, *y4 = PSM(q) + SM_Y4, *syy = PSM(q) + SM_SYY;
+      for (int j = t; j < 240; j += DSP_THREADS) x4[j] = lp[384 + 2 * j];
+      for (int j = t; j < 388; j += DSP_THREADS) y4[j] = j < 387 ? lp[2 * j] : 0.f;
+      for (int i = t; i < 147; i += DSP_THREADS) {
+        float hi = lp[2 * (i + 240)], lo = lp[2 * i];
+        syy[i] = hi * hi - lo * lo;
+      }
     }
-  PHASE_END
+  MPHASE_END
   // -- coarse search: 147 lags x 240 (rnn_pitch_xcorr pitch.c:216; each lag summed in order) on 30
-  //    lanes x 5 lags with a sliding register window; another warp runs the energy chain meanwhile.
-  PHASE_BEGIN
-    if (tid < 30) {
-      const float *yb = y4 + 5 * tid;
+  //    lanes x 5 lags of each stream's first warp, sliding register window; the running-energy chains
+  //    of all streams share the lanes 0..NS-1 of one other warp.
+  MPHASE_BEGIN
+    if (t < 30 && a[q].ring) {
+      const float *x4 = PSM(q) + SM_X4, *y4 = PSM(q) + SM_Y4;
+      float *xc = PSM(q) + SM_XC;
+      const float *yb = y4 + 5 * t;
       float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       float w[5];
 #pragma unroll
-      for (int q = 0; q < 5; q++) w[q] = yb[q];
+      for (int c = 0; c < 5; c++) w[c] = yb[c];
       for (int j0 = 0; j0 < 240; j0 += 5) {
 #pragma unroll
         for (int r = 0; r < 5; r++) {
           const float xv = x4[j0 + r];
 #pragma unroll
-          for (int q = 0; q < 5; q++) acc[q] = acc[q] + xv * w[(q + r) % 5];
-          const int nx = 5 * tid + j0 + r + 5;
+          for (int c = 0; c < 5; c++) acc[c] = acc[c] + xv * w[(c + r) % 5];
+          const int nx = 5 * t + j0 + r + 5;
           w[r] = nx < 388 ? y4[nx] : 0.f;
         }
       }
 #pragma unroll
-      for (int q = 0; q < 5; q++) if (5 * tid + q < 147) xc[5 * tid + q] = acc[q];
-    } else if (tid == 32) {
-      syy_running_inplace(syy, sq_prefix(1.f, y4, 240), 147);
+      for (int c = 0; c < 5; c++) if (5 * t + c < 147) xc[5 * t + c] = acc[c];
+    } else if (tid >= 32 && tid < 32 + PITCH_NS && a[tid - 32].ring) {
+      float *sq = PSM(tid - 32);
+      syy_running_inplace(sq + SM_SYY, sq_prefix(1.f, sq + SM_Y4, 240), 147);
     }
-  PHASE_END
-  PHASE_BEGIN
-    if (tid == 0) {
+  MPHASE_END
+  MPHASE_BEGIN
+    if (tid < PITCH_NS && a[tid].ring) {
+      float *sq = PSM(tid);
+      int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       Best2 b2; best2_init(b2);
-      for (int i = 0; i < 147; i++) best2_visit(b2, i, xc[i], syy[i]);
+      for (int i = 0; i < 147; i++) best2_visit(b2, i, sq[SM_XC + i], sq[SM_SYY + i]);
       mi[0] = b2.p0; mi[1] = b2.p1;
     }
-  PHASE_END
+  MPHASE_END
   // -- xcorr := 0 (pitch.c:347) and the fine-stage increments d[i] = y[i+480]^2 - y[i]^2
-  PHASE_BEGIN
-    for (int i = tid; i < 294; i += nthr) {
-      xc[i] = 0.f;
-      float hi = lp[i + 480], lo = lp[i];
-      syy[i] = hi * hi - lo * lo;
+  MPHASE_BEGIN
+    if (a[q].ring) {
+      const float *lp = PSM(q) + SM_LP;
+      float *xc = PSM(q) + SM_XC, *syy = PSM(q) + SM_SYY;
+      for (int i = t; i < 294; i += DSP_THREADS) {
+        xc[i] = 0.f;
+        float hi = lp[i + 480], lo = lp[i];
+        syy[i] = hi * hi - lo * lo;
+      }
     }
-  PHASE_END
-  // -- fine search around the two coarse winners (pitch.c:344-361) + its energy chain
-  PHASE_BEGIN
-    if (tid < 10) {
+  MPHASE_END
+  // -- fine search around the two coarse winners (pitch.c:344-361): 10 lanes per stream packed from
+  //    lane 0 on; the energy chains of all streams in the lanes of another warp
+  MPHASE_BEGIN
+    if (tid < 10 * PITCH_NS && a[tid / 10].ring) {
+      const int qq = tid / 10, c = tid % 10;
+      float *sq = PSM(qq);
+      const int *mi = (const int *)(sq + SM_PITCH_END + MI_INT);
       const int c0 = 2 * mi[0], c1 = 2 * mi[1];
-      int i = tid < 5 ? c0 - 2 + tid : c1 - 2 + (tid - 5);
+      int i = c < 5 ? c0 - 2 + c : c1 - 2 + (c - 5);
       bool ok = i >= 0 && i < 294;
-      if (tid >= 5) { int d = i - c0; if (d < 0) d = -d; if (d <= 2) ok = false; }
+      if (c >= 5) { int d = i - c0; if (d < 0) d = -d; if (d <= 2) ok = false; }
       if (ok) {
-        const float *xl = lp + 384, *y = lp + i;
+        const float *xl = sq + SM_LP + 384, *y = sq + SM_LP + i;
         float sum = 0.f;
 #pragma unroll 8
         for (int j = 0; j < 480; j++) sum = sum + xl[j] * y[j];
-        xc[i] = RMAX(-1, sum);
+        sq[SM_XC + i] = RMAX(-1, sum);
       }
-    } else if (tid == 32) {
-      syy_running_inplace(syy, sq_prefix(1.f, lp, 480), 294);
+    } else if (tid >= 64 && tid < 64 + PITCH_NS && a[tid - 64].ring) {
+      float *sq = PSM(tid - 64);
+      syy_running_inplace(sq + SM_SYY, sq_prefix(1.f, sq + SM_LP, 480), 294);
     }
-  PHASE_END
+  MPHASE_END
   // -- pick the winner, pseudo-interpolate (pitch.c:362-384), enter the half-rate domain.  Only lags
   //    with xcorr > 0 can change find_best_pitch's state, and only the <= 10 searched lags are non-zero:
-  //    visit those in ascending order.  The other warps meanwhile square the samples the yy_lookup
-  //    chain of rnn_remove_doubling will need (pitch.c:454): a[i-1] = x[-i]^2, yyl[i] := x[N-i]^2.
-  PHASE_BEGIN
-    if (tid == 0) {
+  //    visit those in ascending order.  Each stream's other warps meanwhile square the samples the
+  //    yy_lookup chain of rnn_remove_doubling will need (pitch.c:454): a[i-1] = x[-i]^2, yyl[i] := x[N-i]^2.
+  MPHASE_BEGIN
+    if (tid < PITCH_NS && a[tid].ring) {
+      float *sq = PSM(tid);
+      const float *xc = sq + SM_XC, *syy = sq + SM_SYY;
+      int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       const int c0 = 2 * mi[0], c1 = 2 * mi[1];
       const int lo = c0 < c1 ? c0 : c1, hi = c0 < c1 ? c1 : c0;
       Best2 b2; best2_init(b2);
@@ -173,72 +223,90 @@ HD void pitch_stream(float *sm, const PitchArgs a, const DspTables *T) {
       int T0 = pitch_index / 2;                                       // pitch.c:441
       if (T0 >= PITCH_MAX_PERIOD / 2) T0 = PITCH_MAX_PERIOD / 2 - 1;  // :445-446
       mi[4] = T0;
-    } else if (tid >= 32) {
-      const float *x = lp + PITCH_MAX_PERIOD / 2;
-      for (int i = 1 + (tid - 32); i <= PITCH_MAX_PERIOD / 2; i += nthr - 32) {
+    }
+    if (t >= 32 && a[q].ring) {
+      float *sq = PSM(q);
+      const float *x = sq + SM_LP + PITCH_MAX_PERIOD / 2;
+      for (int i = 1 + (t - 32); i <= PITCH_MAX_PERIOD / 2; i += DSP_THREADS - 32) {
         float u = x[-i], v = x[PITCH_FRAME_SIZE / 2 - i];
-        x4[i - 1] = u * u;      // x4/y4 are dead after the coarse search: 384 floats fit in their 628
-        yyl[i] = v * v;
+        sq[SM_X4 + i - 1] = u * u;   // x4/y4 are dead after the coarse search: 384 floats fit in their 628
+        sq[SM_YYL + i] = v * v;
       }
     }
-  PHASE_END
+  MPHASE_END
   // -- all dot products rnn_remove_doubling can need, in parallel lanes (each one sequential):
-  //    warp 0: xx, xy(T0), and xy(T1), xy(T1b) for k = 2..15      (pitch.c:449, 482)
-  //    warp 1: speculative refinement lags T-1, T+1 of every candidate (pitch.c:513-514)
-  //    warp 2: the yy_lookup energy chain                           (pitch.c:450-456)
-  PHASE_BEGIN
-    const float *x = lp + PITCH_MAX_PERIOD / 2;
-    const int N = PITCH_FRAME_SIZE / 2, T0 = mi[4];
-    if (tid < 30) {
-      int off, ok = 1;
-      if (tid == 0) off = 0;
-      else if (tid == 1) off = T0;
-      else {
-        int k = 2 + (tid - 2) / 2, T1, T1b;
+  //    stream warp 0: xx, xy(T0), and xy(T1), xy(T1b) for k = 2..15      (pitch.c:449, 482)
+  //    stream warp 1: speculative refinement lags T-1, T+1 of every candidate (pitch.c:513-514)
+  //    lanes 64..64+NS-1 of the CTA: the yy_lookup energy chains of all streams (pitch.c:450-456)
+  MPHASE_BEGIN
+    const int N = PITCH_FRAME_SIZE / 2;
+    if (tid >= 64 && tid < 64 + PITCH_NS) {
+      if (a[tid - 64].ring) {
+        float *sq = PSM(tid - 64);
+        const float *x = sq + SM_LP + PITCH_MAX_PERIOD / 2;
+        float *yyl = sq + SM_YYL;
+        float yy = sq_prefix(0.f, x, N);   // == xx, summed in the same order (pitch.c:449-451)
+        yyl[0] = yy;
+        const float *a2 = sq + SM_X4;      // a2[i-1] = x[-i]^2, yyl[i] holds x[N-i]^2 until overwritten
+        for (int i = 1; i <= PITCH_MAX_PERIOD / 2; i += 4) {
+          f4 av = *(const f4 *)(a2 + i - 1);
+          yy = yy + av.x - yyl[i];     yyl[i] = RMAX(0, yy);
+          yy = yy + av.y - yyl[i + 1]; yyl[i + 1] = RMAX(0, yy);
+          yy = yy + av.z - yyl[i + 2]; yyl[i + 2] = RMAX(0, yy);
+          yy = yy + av.w - yyl[i + 3]; yyl[i + 3] = RMAX(0, yy);
+        }
+      }
+    } else if (a[q].ring) {
+      float *sq = PSM(q);
+      const float *x = sq + SM_LP + PITCH_MAX_PERIOD / 2;
+      float *dot = sq + SM_DOT;
+      const int T0 = ((const int *)(sq + SM_PITCH_END + MI_INT))[4];
+      if (t < 30) {
+        int off, ok = 1;
+        if (t == 0) off = 0;
+        else if (t == 1) off = T0;
+        else {
+          int k = 2 + (t - 2) / 2, T1, T1b;
+          rd_candidate(k, T0, &T1, &T1b);
+          ok = T1 >= PITCH_MIN_PERIOD / 2;
+          off = ((t - 2) & 1) ? T1b : T1;
+        }
+        if (ok) {
+          float s = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < N; i++) s = s + x[i] * x[i - off];
+          dot[t] = s;
+        }
+      } else if (t >= 32 && t < 62) {
+        int c = (t - 32) / 2, k = c + 1, T1, T1b;
         rd_candidate(k, T0, &T1, &T1b);
-        ok = T1 >= PITCH_MIN_PERIOD / 2;
-        off = ((tid - 2) & 1) ? T1b : T1;
-      }
-      if (ok) {
-        float s = 0.f;
-        for (int i = 0; i < N; i++) s = s + x[i] * x[i - off];
-        dot[tid] = s;
-      }
-    } else if (tid >= 32 && tid < 62) {
-      int c = (tid - 32) / 2, k = c + 1, T1, T1b;
-      rd_candidate(k, T0, &T1, &T1b);
-      if (k == 1 || T1 >= PITCH_MIN_PERIOD / 2) {
-        int off = ((tid - 32) & 1) ? T1 + 1 : T1 - 1;
-        float s = 0.f;
-        for (int i = 0; i < N; i++) s = s + x[i] * x[i - off];
-        dot[tid] = s;
-      }
-    } else if (tid == 64) {
-      float yy = sq_prefix(0.f, x, N);   // == xx, summed in the same order (pitch.c:449-451)
-      yyl[0] = yy;
-      const float *a2 = x4;              // a2[i-1] = x[-i]^2, yyl[i] holds x[N-i]^2 until overwritten
-      for (int i = 1; i <= PITCH_MAX_PERIOD / 2; i += 4) {
-        f4 av = *(const f4 *)(a2 + i - 1);
-        yy = yy + av.x - yyl[i];     yyl[i] = RMAX(0, yy);
-        yy = yy + av.y - yyl[i + 1]; yyl[i + 1] = RMAX(0, yy);
-        yy = yy + av.z - yyl[i + 2]; yyl[i + 2] = RMAX(0, yy);
-        yy = yy + av.w - yyl[i + 3]; yyl[i + 3] = RMAX(0, yy);
+        if (k == 1 || T1 >= PITCH_MIN_PERIOD / 2) {
+          int off = ((t - 32) & 1) ? T1 + 1 : T1 - 1;
+          float s = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < N; i++) s = s + x[i] * x[i - off];
+          dot[t] = s;
+        }
       }
     }
-  PHASE_END
+  MPHASE_END
   // -- decision logic of rnn_remove_doubling (pitch.c:457-527) + state update (denoise.c:369-370)
-  PHASE_BEGIN
-    if (tid == 0) {
+  MPHASE_BEGIN
+    if (tid < PITCH_NS && a[tid].ring) {
+      const PitchArgs A = a[tid];
+      float *sq = PSM(tid);
+      const float *dot = sq + SM_DOT, *yyl = sq + SM_YYL;
+      int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       const int T0 = mi[4], minperiod = PITCH_MIN_PERIOD / 2;
-      int prev_period = ((const int *)a.pitch_state)[0] / 2;
-      const float prev_gain = a.pitch_state[1];
+      int prev_period = ((const int *)A.pitch_state)[0] / 2;
+      const float prev_gain = A.pitch_state[1];
       const float xx = dot[0];
       float xy = dot[1];
       float yy = yyl[T0];
       float best_xy = xy, best_yy = yy;
       const float g0 = pitch_gain(xy, xx, yy);
       float g = g0;
-      int T = T0, kbest = 1;
+      int Tb = T0, kbest = 1;
       for (int k = 2; k <= 15; k++) {
         int T1, T1b;
         rd_candidate(k, T0, &T1, &T1b);
@@ -254,7 +322,7 @@ HD void pitch_stream(float *sm, const PitchArgs a, const DspTables *T) {
         float thresh = RMAX(.3f, .7f * g0 - cont);
         if (T1 < 3 * minperiod) thresh = RMAX(.4f, .85f * g0 - cont);
         else if (T1 < 2 * minperiod) thresh = RMAX(.5f, .9f * g0 - cont);
-        if (g1 > thresh) { best_xy = xy; best_yy = yy; T = T1; g = g1; kbest = k; }
+        if (g1 > thresh) { best_xy = xy; best_yy = yy; Tb = T1; g = g1; kbest = k; }
       }
       best_xy = RMAX(0, best_xy);
       float pg;
@@ -268,13 +336,13 @@ HD void pitch_stream(float *sm, const PitchArgs a, const DspTables *T) {
       else if ((xc0 - xc2) > .7f * (xc1 - xc2)) offset = -1;
       else offset = 0;
       if (pg > g) pg = g;
-      int Tout = 2 * T + offset;
+      int Tout = 2 * Tb + offset;
       if (Tout < PITCH_MIN_PERIOD) Tout = PITCH_MIN_PERIOD;
       mi[2] = Tout;
-      ((int *)a.pitch_state)[0] = Tout;
-      a.pitch_state[1] = pg;
+      ((int *)A.pitch_state)[0] = Tout;
+      A.pitch_state[1] = pg;
     }
-  PHASE_END
+  MPHASE_END
 }
 
 // Spectral half of rnn_compute_frame_features (src/denoise.c:358, 371-397) incl. rnn_frame_analysis
@@ -283,6 +351,7 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   float *misc = sm + SM_SPEC_END;
   int *mi = (int *)(misc + MI_INT);
   cpx *F = (cpx *)(sm + SM_F), *XS = (cpx *)(sm + SM_XS);
+  float *tb = sm + SM_TB;
   const int pitch_T = ((const int *)a.pitch_state)[0];
   // -- X = FFT(window * [previous frame | this frame]) (denoise.c:332-339); the analysis window
   //    is the last 960 samples of the updated pitch history.
@@ -296,8 +365,8 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
       cpx v = F[i];
       XS[i] = v;
       ((cpx *)a.spec_out)[i] = v;
+      if (i < 400) tb[i] = bin_term(v, v);
     }
-    if (tid < NB_BANDS + 2) misc[MI_BAND + tid] = band_sum_one(tid, F, F, T);
   PHASE_END
   // -- P = FFT(window * pitch_buf[768-T .. 768-T+960)) (denoise.c:371-374)
   PHASE_BEGIN fft_stage1(F, a.ring, a.ring_base, PITCH_BUF_SIZE - WINDOW_SIZE - pitch_T, nullptr, T, tid, nthr); PHASE_END
@@ -306,9 +375,18 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix5(F, T, tid, nthr); PHASE_END
   PHASE_BEGIN
-    for (int i = tid; i < FREQ_SIZE; i += nthr) ((cpx *)a.spec_out)[FREQ_SIZE + i] = F[i];
-    if (tid < NB_BANDS + 2) misc[MI_BAND + 34 + tid] = band_sum_one(tid, F, F, T);
-    else if (tid >= 64 && tid < 64 + NB_BANDS + 2) misc[MI_BAND + 68 + tid - 64] = band_sum_one(tid - 64, XS, F, T);
+    for (int i = tid; i < FREQ_SIZE; i += nthr) {
+      cpx v = F[i];
+      ((cpx *)a.spec_out)[FREQ_SIZE + i] = v;
+      if (i < 400) { tb[400 + i] = bin_term(v, v); tb[800 + i] = bin_term(XS[i], v); }
+    }
+  PHASE_END
+  // -- the three sets of 34 triangular band sums (compute_band_energy / compute_band_corr), one lane each
+  PHASE_BEGIN
+    if (tid < 3 * (NB_BANDS + 2)) {
+      const int set = tid / (NB_BANDS + 2), b = tid % (NB_BANDS + 2);
+      misc[MI_BAND + 34 * set + b] = band_sum_terms(b, tb + 400 * set, T);
+    }
   PHASE_END
   // -- Ex, Ep, Exp (denoise.c:344,375-377)
   PHASE_BEGIN
@@ -378,7 +456,8 @@ struct SynthesisArgs {
 #define SS_P (SS_X + 2 * FREQ_SIZE)   // [962] delayed P
 #define SS_F (SS_P + 2 * FREQ_SIZE)   // [1920] FFT buffer
 #define SS_V (SS_F + 2 * WINDOW_SIZE) // [6][34] band vectors: r, norm, g, sums...
-#define SS_TOTAL (SS_V + 6 * 34)
+#define SS_T (SS_V + 6 * 34)           // [400] per-bin |X|^2 of the pitch-filtered spectrum
+#define SS_TOTAL (SS_T + 400)
 
 // rnn_pitch_filter (denoise.c:421-455), gain smoothing + interpolation (:479-493),
 // frame_synthesis (:400-407) with inverse_transform (:200-217).
@@ -415,10 +494,11 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
         x.r += rf * p.r;
         x.i += rf * p.i;
         X[i] = x;
+        if (i < 400) sm[SS_T + i] = bin_term(x, x);
       }
     PHASE_END
     PHASE_BEGIN
-      if (tid < NB_BANDS + 2) sums[tid] = band_sum_one(tid, X, X, T);
+      if (tid < NB_BANDS + 2) sums[tid] = band_sum_terms(tid, sm + SS_T, T);
     PHASE_END
     PHASE_BEGIN
       if (tid < NB_BANDS) {

@@ -37,6 +37,7 @@ static inline void b200_fill_dsp_tables(DspTables *t) {
     for (int j = 0; j < bs; j++) {
       t->bin_band[eband[b] + j] = (unsigned char)b;
       t->bin_frac[eband[b] + j] = (float)j / bs;
+      t->bin_cfrac[eband[b] + j] = 1 - t->bin_frac[eband[b] + j];
     }
   }
   t->fft_scale = 0.0010416667f;  // rnnoise_tables.c:562

@@ -86,18 +86,28 @@ __global__ void __launch_bounds__(32) k_biquad(Arena a, const float *__restrict_
   if (s < a.S) { a.hp_mem[2 * s] = m0; a.hp_mem[2 * s + 1] = m1; }
 }
 
-#ifndef PITCH_MIN_BLOCKS
-#define PITCH_MIN_BLOCKS 16   // 32 registers/thread: 16 resident streams per SM hide the serial chains
+// grid = ceil(S / PITCH_NS), block = PITCH_NS * 128, dynamic smem = PITCH_NS * SM_PITCH_TOTAL floats
+#ifndef PITCH_MIN_CTAS
+#define PITCH_MIN_CTAS (2048 / (PITCH_NS * DSP_THREADS))   // 32 registers/thread: 16 streams resident per SM
 #endif
-__global__ void __launch_bounds__(DSP_THREADS, PITCH_MIN_BLOCKS) k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
+__global__ void __launch_bounds__(PITCH_NS *DSP_THREADS, PITCH_MIN_CTAS)
+k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
   extern __shared__ float sm[];
-  const int s = blockIdx.x;
-  PitchArgs g;
-  g.xb = a.xb + ((size_t)(f & 1) * a.S + s) * FRAME_SIZE;
-  g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
-  g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
-  g.pitch_state = a.pitch_state + 2 * (size_t)s;
-  pitch_stream(sm, g, T);
+  __shared__ PitchArgs pa[PITCH_NS];
+  if (threadIdx.x < PITCH_NS) {
+    const int s = blockIdx.x * PITCH_NS + threadIdx.x;
+    PitchArgs g;
+    g.ring = nullptr; g.xb = nullptr; g.pitch_state = nullptr;
+    g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+    if (s < a.S) {
+      g.xb = a.xb + ((size_t)(f & 1) * a.S + s) * FRAME_SIZE;
+      g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
+      g.pitch_state = a.pitch_state + 2 * (size_t)s;
+    }
+    pa[threadIdx.x] = g;
+  }
+  __syncthreads();
+  pitch_streams(sm, pa, T);
 }
 
 #ifndef SPEC_MIN_BLOCKS
@@ -413,7 +423,7 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
     e->bq_frames = e->frames + 1;
   }
   MARK();
-  k_pitch<<<S, DSP_THREADS, SM_PITCH_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr);
+  k_pitch<<<(S + PITCH_NS - 1) / PITCH_NS, PITCH_NS * DSP_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr);
   CK(cudaEventRecord(e->ev_ana[par], st));   // xb[par] is free again
   MARK();
   k_spectrum<<<S, DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr);

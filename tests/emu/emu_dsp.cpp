@@ -11,17 +11,21 @@
 #include "dsp_stream.cuh"
 #include "dsp_tables.hpp"
 
-struct EmuState {
-  DspTables T;
+struct EmuStream {
   float ring[PITCH_BUF_SIZE], synth_mem[FRAME_SIZE], hp[2];
   float spec[2][4 * FREQ_SIZE], band[2][96], lastg[NB_BANDS], pitch_state[2];
   float features[NB_FEATURES], xb[FRAME_SIZE];
   int silence;
+};
+struct EmuState {
+  DspTables T;
+  EmuStream st[PITCH_NS];
   long frames;
-  alignas(16) float sm[8192];   // >= max(SM_PITCH_TOTAL, SM_SPEC_TOTAL, SS_TOTAL)
+  alignas(16) float sm[PITCH_NS * SM_PITCH_TOTAL > 8192 ? PITCH_NS * SM_PITCH_TOTAL : 8192];
 };
 
 extern "C" {
+int emu_streams(void) { return PITCH_NS; }
 void *emu_create(void) {
   EmuState *e = (EmuState *)calloc(1, sizeof(EmuState));
   b200_fill_dsp_tables(&e->T);
@@ -29,56 +33,70 @@ void *emu_create(void) {
 }
 void emu_destroy(void *p) { free(p); }
 
-// biquad + analysis of one frame; returns the silence flag
-int emu_analysis(void *p, const float *in, float *xb, float *features, float *X, float *P, float *bands,
-                 float *pitch) {
+// biquad + pitch + spectrum of one frame for a group of PITCH_NS streams (in: [NS][480]); nstreams < NS
+// leaves the trailing streams absent (exercises the partial-group guards)
+void emu_analysis(void *p, const float *in, int nstreams) {
   EmuState *e = (EmuState *)p;
-  float m0 = e->hp[0], m1 = e->hp[1];
-  for (int i = 0; i < FRAME_SIZE; i++) e->xb[i] = biquad_step(in[i], m0, m1);
-  e->hp[0] = m0; e->hp[1] = m1;
+  static_assert(SM_SPEC_TOTAL <= 8192 && SS_TOTAL <= 8192, "emu scratch");
   const long f = e->frames;
   const int par = (int)(f & 1);
-  static_assert(SM_PITCH_TOTAL <= 8192 && SM_SPEC_TOTAL <= 8192 && SS_TOTAL <= 8192, "emu scratch");
-  PitchArgs pa;
-  pa.xb = e->xb;
-  pa.ring = e->ring;
-  pa.ring_base = (int)(((f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
-  pa.pitch_state = e->pitch_state;
-  pitch_stream(e->sm, pa, &e->T);
-  SpectrumArgs a;
-  a.ring = e->ring;
-  a.ring_base = pa.ring_base;
-  a.pitch_state = e->pitch_state;
-  a.spec_out = e->spec[par];
-  a.band_out = e->band[par];
-  a.features = e->features;
-  a.silence = &e->silence;
-  spectrum_stream(e->sm, a, &e->T);
-  memcpy(xb, e->xb, sizeof(e->xb));
-  memcpy(features, e->features, sizeof(e->features));
-  memcpy(X, e->spec[par], 2 * FREQ_SIZE * sizeof(float));
-  memcpy(P, e->spec[par] + 2 * FREQ_SIZE, 2 * FREQ_SIZE * sizeof(float));
-  memcpy(bands, e->band[par], 96 * sizeof(float));
-  int period; memcpy(&period, &e->pitch_state[0], 4);
-  pitch[0] = (float)period; pitch[1] = e->pitch_state[1];
-  return e->silence;
+  PitchArgs pa[PITCH_NS];
+  for (int q = 0; q < PITCH_NS; q++) {
+    EmuStream &s = e->st[q];
+    pa[q].ring = nullptr;
+    if (q >= nstreams) continue;
+    float m0 = s.hp[0], m1 = s.hp[1];
+    for (int i = 0; i < FRAME_SIZE; i++) s.xb[i] = biquad_step(in[q * FRAME_SIZE + i], m0, m1);
+    s.hp[0] = m0; s.hp[1] = m1;
+    pa[q].xb = s.xb;
+    pa[q].ring = s.ring;
+    pa[q].ring_base = (int)(((f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+    pa[q].pitch_state = s.pitch_state;
+  }
+  pitch_streams(e->sm, pa, &e->T);
+  for (int q = 0; q < nstreams; q++) {
+    EmuStream &s = e->st[q];
+    SpectrumArgs a;
+    a.ring = s.ring;
+    a.ring_base = pa[q].ring_base;
+    a.pitch_state = s.pitch_state;
+    a.spec_out = s.spec[par];
+    a.band_out = s.band[par];
+    a.features = s.features;
+    a.silence = &s.silence;
+    spectrum_stream(e->sm, a, &e->T);
+  }
 }
-
-// synthesis of the same frame given the network gains; advances the frame counter
-void emu_synthesis(void *p, const float *gains, float *out, float *lastg) {
+// results of the last emu_analysis for stream q; returns the silence flag
+int emu_get(void *p, int q, float *xb, float *features, float *X, float *P, float *bands, float *pitch) {
   EmuState *e = (EmuState *)p;
+  EmuStream &s = e->st[q];
+  const int par = (int)(e->frames & 1);
+  memcpy(xb, s.xb, sizeof(s.xb));
+  memcpy(features, s.features, sizeof(s.features));
+  memcpy(X, s.spec[par], 2 * FREQ_SIZE * sizeof(float));
+  memcpy(P, s.spec[par] + 2 * FREQ_SIZE, 2 * FREQ_SIZE * sizeof(float));
+  memcpy(bands, s.band[par], 96 * sizeof(float));
+  int period; memcpy(&period, &s.pitch_state[0], 4);
+  pitch[0] = (float)period; pitch[1] = s.pitch_state[1];
+  return s.silence;
+}
+// synthesis of the same frame for stream q given the network gains
+void emu_synthesis(void *p, int q, const float *gains, float *out, float *lastg) {
+  EmuState *e = (EmuState *)p;
+  EmuStream &s = e->st[q];
   const int par = (int)(e->frames & 1);
   SynthesisArgs a;
-  a.spec_delayed = e->spec[par ^ 1];
-  a.band_delayed = e->band[par ^ 1];
-  a.band_cur = e->band[par];
+  a.spec_delayed = s.spec[par ^ 1];
+  a.band_delayed = s.band[par ^ 1];
+  a.band_cur = s.band[par];
   a.gains = gains;
-  a.silence = &e->silence;
-  a.lastg = e->lastg;
-  a.synthesis_mem = e->synth_mem;
+  a.silence = &s.silence;
+  a.lastg = s.lastg;
+  a.synthesis_mem = s.synth_mem;
   a.out = out;
   synthesis_stream(e->sm, a, &e->T);
-  memcpy(lastg, e->lastg, sizeof(e->lastg));
-  e->frames++;
+  memcpy(lastg, s.lastg, sizeof(s.lastg));
 }
+void emu_advance(void *p) { ((EmuState *)p)->frames++; }
 }

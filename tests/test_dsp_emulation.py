@@ -25,28 +25,38 @@ def emu():
     E = C.CDLL(EMU_SO)
     E.emu_create.restype = C.c_void_p
     E.emu_destroy.argtypes = [C.c_void_p]
-    E.emu_analysis.argtypes = [C.c_void_p] + [C.POINTER(C.c_float)] * 7
-    E.emu_synthesis.argtypes = [C.c_void_p] + [C.POINTER(C.c_float)] * 3
+    E.emu_analysis.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
+    E.emu_get.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_float)] * 6
+    E.emu_synthesis.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_float)] * 3
+    E.emu_advance.argtypes = [C.c_void_p]
     return E
 
 
-@pytest.mark.parametrize("stream,frames", [(0, 80), (15, 60), (7, 50)])
-def test_device_dsp_source_is_bit_identical_to_port(emu, port_default, stream, frames):
-    pcm = stream_pcm(stream, frames)
-    st, e = port_default.create(), emu.emu_create()
+@pytest.mark.parametrize("streams,frames", [((0, 15, 7, 3), 60), ((5, 31, 2), 40), ((9,), 30)])
+def test_device_dsp_source_is_bit_identical_to_port(emu, port_default, streams, frames):
+    """Groups of up to PITCH_NS streams share one emulated pitch CTA (packed serial chains); partial
+    groups exercise the absent-stream guards."""
+    assert emu.emu_streams() >= len(streams)
+    pcm = np.stack([stream_pcm(s, frames) for s in streams], axis=1)   # [frames][n][480]
+    states = [port_default.create() for _ in streams]
+    e = emu.emu_create()
     for f in range(frames):
-        b = port_default.process_frame(st, pcm[f])
-        xb = np.zeros(480, np.float32); feat = np.zeros(65, np.float32)
-        X = np.zeros(962, np.float32); P = np.zeros(962, np.float32)
-        bands = np.zeros(96, np.float32); pitch = np.zeros(2, np.float32)
-        sil = emu.emu_analysis(e, fptr(pcm[f].copy()), fptr(xb), fptr(feat), fptr(X), fptr(P), fptr(bands), fptr(pitch))
-        out = np.zeros(480, np.float32); lastg = np.zeros(32, np.float32)
-        emu.emu_synthesis(e, fptr(b["g_raw"]), fptr(out), fptr(lastg))
-        for k, u, v in (("xb", xb, b["xb"]), ("features", feat, b["features"]), ("X", X, b["X"]), ("P", P, b["P"]),
-                        ("Ex", bands[:32], b["Ex"]), ("Ep", bands[32:64], b["Ep"]), ("Exp", bands[64:], b["Exp"]),
-                        ("out", out, b["out"]), ("lastg", lastg, b["lastg"])):
-            assert u.tobytes() == v.tobytes(), (k, f)
-        assert sil == b["silence"] and int(pitch[0]) == b["pitch"]
-        assert pitch[1:].tobytes() == np.float32(b["pitch_gain"]).tobytes()
+        emu.emu_analysis(e, fptr(np.ascontiguousarray(pcm[f])), len(streams))
+        for q, s in enumerate(streams):
+            b = port_default.process_frame(states[q], pcm[f, q])
+            xb = np.zeros(480, np.float32); feat = np.zeros(65, np.float32)
+            X = np.zeros(962, np.float32); P = np.zeros(962, np.float32)
+            bands = np.zeros(96, np.float32); pitch = np.zeros(2, np.float32)
+            sil = emu.emu_get(e, q, fptr(xb), fptr(feat), fptr(X), fptr(P), fptr(bands), fptr(pitch))
+            out = np.zeros(480, np.float32); lastg = np.zeros(32, np.float32)
+            emu.emu_synthesis(e, q, fptr(b["g_raw"]), fptr(out), fptr(lastg))
+            for k, u, v in (("xb", xb, b["xb"]), ("features", feat, b["features"]), ("X", X, b["X"]), ("P", P, b["P"]),
+                            ("Ex", bands[:32], b["Ex"]), ("Ep", bands[32:64], b["Ep"]), ("Exp", bands[64:], b["Exp"]),
+                            ("out", out, b["out"]), ("lastg", lastg, b["lastg"])):
+                assert u.tobytes() == v.tobytes(), (k, f, s)
+            assert sil == b["silence"] and int(pitch[0]) == b["pitch"], (f, s)
+            assert pitch[1:].tobytes() == np.float32(b["pitch_gain"]).tobytes()
+        emu.emu_advance(e)
     emu.emu_destroy(e)
-    port_default.destroy(st)
+    for st in states:
+        port_default.destroy(st)
