@@ -38,8 +38,12 @@ struct SpectrumArgs {
 // packed side by side into the lanes of one or two warps -- same instructions, PITCH_NS x the useful
 // lanes.  Thread ids: q = tid / 128 is the stream a thread belongs to, t = tid % 128 its local id;
 // packed phases use the first lanes of the CTA instead.
+// Measured on B200 (S = 4096): PITCH_NS = 1 -> 127 us, PITCH_NS = 4 -> 145 us: with 16 streams resident
+// per SM either way, packing removes instructions but also leaves fewer warps runnable during the
+// chain phases, and the kernel is bound by the chains' latency; the default therefore stays 1 (the
+// host emulation builds with 4 to keep the packed mapping tested).
 #ifndef PITCH_NS
-#define PITCH_NS 4
+#define PITCH_NS 1
 #endif
 #if defined(__CUDA_ARCH__)
 #define MPHASE_BEGIN { const int tid = threadIdx.x; const int q = tid >> 7, t = tid & 127; (void)q; (void)t;

@@ -4,7 +4,7 @@
 // over the 128 thread ids, so indexing, work partitioning and arithmetic of the exact source the
 // GPU executes can be checked against the oracle without a GPU (tests/test_dsp_emulation.py).
 // This file is test infrastructure: nothing in the library links or calls it.
-// build: g++ -O2 -ffp-contract=off -fPIC -shared -I rnnoise_b200/csrc tests/emu/emu_dsp.cpp
+// build: g++ -O2 -ffp-contract=off -fPIC -shared -DPITCH_NS=4 -I rnnoise_b200/csrc tests/emu/emu_dsp.cpp
 #include <stdlib.h>
 #include <string.h>
 

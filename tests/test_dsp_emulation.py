@@ -20,7 +20,7 @@ EMU_SO = os.path.join(ROOT, "tests", "emu", "libemu_dsp.so")
 def emu():
     deps = [EMU_SRC] + [os.path.join(ROOT, "rnnoise_b200", "csrc", f) for f in ("dsp_core.cuh", "dsp_stream.cuh", "dsp_tables.hpp")]
     if not os.path.exists(EMU_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMU_SO) for d in deps):
-        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-DPITCH_NS=4",
                         "-I", os.path.join(ROOT, "rnnoise_b200", "csrc"), EMU_SRC, "-o", EMU_SO], check=True)
     E = C.CDLL(EMU_SO)
     E.emu_create.restype = C.c_void_p
