@@ -16,10 +16,10 @@ for r in rows[hdr + 1:]:
     v = float(r[vi].replace(',', ''))
     v = v / 1e3 if r[ui] == 'ns' else v * 1e3 if r[ui] == 'ms' else v
     d.setdefault(r[ki].split('(')[0], []).append(v)
-per_step = {k: sum(v) / len(v) * (3 if k == 'k_gru' or k == 'k_gru_tc' else 1) for k, v in d.items() if k.startswith('k_')}
+per_step = {k: sum(v) / len(v) * (3 if k in ('k_gru', 'k_gru_tc', 'void k_tc2<1>') else 1) for k, v in d.items() if 'k_' in k}
 tot = sum(per_step.values())
 print(f"{'kernel':16s} {'launches':>8s} {'mean us':>10s} {'us/step':>10s} {'share':>7s}")
 for k, v in d.items():
-    if k.startswith('k_'):
+    if 'k_' in k:
         print(f"{k:16s} {len(v):8d} {sum(v)/len(v):10.1f} {per_step[k]:10.1f} {per_step[k]/tot:7.1%}")
 print(f"{'sum':16s} {'':8s} {'':10s} {tot:10.1f}")
