@@ -282,11 +282,19 @@ def main():
     except Exception:
         pass
     hbm = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:   # dram__bytes_read+write per launch of that kernel from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "k_gru" if top.startswith("k_gru") else top
+        if S == 4096 and key in tj:
+            traffic = tj[key]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     top_bytes = KERNEL_BYTES.get(top, 43344) * S
     achieved = top_bytes / (kernels[top] * 1e-3) / 1e9
     roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-            "algorithmic_bytes_per_launch": top_bytes, "ms_per_launch": kernels[top], "traffic": None,
+            "algorithmic_bytes_per_launch": top_bytes, "ms_per_launch": kernels[top], "traffic": traffic,
             "kernel_ms_per_step": kernels, "kernel_share": {k: v / sum(kernels.values()) for k, v in kernels.items()},
             "pipeline": {"algorithmic_bytes_per_stream_frame": 43344,
                          "achieved_GBps": 43344 * S * K / (ms * 1e-3) / 1e9 / 1.0,
