@@ -39,8 +39,9 @@ struct Arena {
   float *ring;         // [S][1728] pitch history ring (analysis_mem is its newest 480 samples)
   float *synth_mem;    // [S][480]
   float *hp_mem;       // [S][2]
-  float *spec;         // [2][S][2][962] ping-pong: X and P of the current / previous frame
-  float *band;         // [2][S][96]     ping-pong: Ex, Ep, Exp
+  float *spec;         // [3][S][2][962] X and P of frame f in slot f % 3 (f-1 is the "delayed" frame; the third
+                       //                slot lets the analysis of frame f+1 overlap the synthesis of frame f)
+  float *band;         // [3][S][96]     Ex, Ep, Exp, same rotation
   float *lastg;        // [S][32]
   float *pitch_state;  // [S][2] {last_period (int bits), last_gain}
   // network state
@@ -51,8 +52,8 @@ struct Arena {
   uint8_t *conv2_out_u8; // [S][gru]
   // per-frame scratch
   float *xb;           // [2][S][480] high-passed input, double-buffered by frame parity
-  float *features;     // [S][65]
-  int *silence;        // [S]
+  float *features;     // [2][S][65] by frame parity (frame f+1's analysis overlaps frame f's network)
+  int *silence;        // [2][S]
   float *conv2_out;    // [S][gru]
   float *gains;        // [S][32]
   float *vad;          // [S]
@@ -116,15 +117,15 @@ k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
 __global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena a, const DspTables *__restrict__ T, int f) {
   extern __shared__ float sm[];
   const int s = blockIdx.x;
-  const int par = f & 1;
+  const int par = f & 1, slot = f % 3;
   SpectrumArgs g;
   g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
   g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
   g.pitch_state = a.pitch_state + 2 * (size_t)s;
-  g.spec_out = a.spec + ((size_t)par * a.S + s) * (4 * FREQ_SIZE);
-  g.band_out = a.band + ((size_t)par * a.S + s) * 96;
-  g.features = a.features + (size_t)s * NB_FEATURES;
-  g.silence = a.silence + s;
+  g.spec_out = a.spec + ((size_t)slot * a.S + s) * (4 * FREQ_SIZE);
+  g.band_out = a.band + ((size_t)slot * a.S + s) * 96;
+  g.features = a.features + ((size_t)par * a.S + s) * NB_FEATURES;
+  g.silence = a.silence + (size_t)par * a.S + s;
   spectrum_stream(sm, g, T);
 }
 
@@ -132,13 +133,13 @@ __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTab
                                                            float *__restrict__ out, int f) {
   extern __shared__ float sm[];
   const int s = blockIdx.x;
-  const int par = f & 1;
+  const int par = f & 1, slot = f % 3, dslot = (f + 2) % 3;   // dslot = (f - 1) mod 3
   SynthesisArgs g;
-  g.spec_delayed = a.spec + ((size_t)(par ^ 1) * a.S + s) * (4 * FREQ_SIZE);
-  g.band_delayed = a.band + ((size_t)(par ^ 1) * a.S + s) * 96;
-  g.band_cur = a.band + ((size_t)par * a.S + s) * 96;
+  g.spec_delayed = a.spec + ((size_t)dslot * a.S + s) * (4 * FREQ_SIZE);
+  g.band_delayed = a.band + ((size_t)dslot * a.S + s) * 96;
+  g.band_cur = a.band + ((size_t)slot * a.S + s) * 96;
   g.gains = a.gains + (size_t)s * NB_BANDS;
-  g.silence = a.silence + s;
+  g.silence = a.silence + (size_t)par * a.S + s;
   g.lastg = a.lastg + (size_t)s * NB_BANDS;
   g.synthesis_mem = a.synth_mem + (size_t)s * FRAME_SIZE;
   g.out = out + (size_t)s * FRAME_SIZE;
@@ -159,6 +160,10 @@ struct B200Engine {
   // H2D(n) -> compute(n) -> D2H(n) while protecting slot reuse two frames later
   float *stage_in[2], *stage_out[2], *stage_vad[2];
   cudaStream_t s_h2d, s_d2h, s_bq;
+  cudaStream_t s_front;              // k_pitch/k_spectrum of frame f+1 overlap network + synthesis of frame f
+  cudaEvent_t ev_front[2], ev_back[2];   // analysis of frame f done / network+synthesis of frame f done (by parity)
+  cudaEvent_t ev_in;                 // input readiness on the caller's stream (non-prefiltered frames)
+  int overlap;                       // 0: everything on one stream (RNNOISE_B200_OVERLAP=0, profiling)
   cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
   cudaEvent_t ev_bq[2], ev_ana[2];   // biquad of frame f done / analysis of frame f done (xb slot free)
   long long host_frames;
@@ -269,12 +274,16 @@ extern "C" void b200_engine_destroy(B200Engine *e) {
   if (e->s_h2d) { cudaStreamSynchronize(e->s_h2d); cudaStreamDestroy(e->s_h2d); }
   if (e->s_d2h) { cudaStreamSynchronize(e->s_d2h); cudaStreamDestroy(e->s_d2h); }
   if (e->s_bq) { cudaStreamSynchronize(e->s_bq); cudaStreamDestroy(e->s_bq); }
+  if (e->s_front) { cudaStreamSynchronize(e->s_front); cudaStreamDestroy(e->s_front); }
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
   for (int i = 0; i < 2; i++) {
     if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
     if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
     if (e->ev_d2h[i]) cudaEventDestroy(e->ev_d2h[i]);
     if (e->ev_bq[i]) cudaEventDestroy(e->ev_bq[i]);
     if (e->ev_ana[i]) cudaEventDestroy(e->ev_ana[i]);
+    if (e->ev_front[i]) cudaEventDestroy(e->ev_front[i]);
+    if (e->ev_back[i]) cudaEventDestroy(e->ev_back[i]);
   }
   for (void *p : e->allocs) cudaFree(p);
   delete e;
@@ -307,8 +316,8 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   ok &= !!(a.ring = dalloc<float>(e, Ss * PITCH_BUF_SIZE));
   ok &= !!(a.synth_mem = dalloc<float>(e, Ss * FRAME_SIZE));
   ok &= !!(a.hp_mem = dalloc<float>(e, Ss * 2));
-  ok &= !!(a.spec = dalloc<float>(e, 2 * Ss * 4 * FREQ_SIZE));
-  ok &= !!(a.band = dalloc<float>(e, 2 * Ss * 96));
+  ok &= !!(a.spec = dalloc<float>(e, 3 * Ss * 4 * FREQ_SIZE));
+  ok &= !!(a.band = dalloc<float>(e, 3 * Ss * 96));
   ok &= !!(a.lastg = dalloc<float>(e, Ss * NB_BANDS));
   ok &= !!(a.pitch_state = dalloc<float>(e, Ss * 2));
   ok &= !!(a.conv1_state = dalloc<float>(e, Ss * 2 * NB_FEATURES));
@@ -319,14 +328,19 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   ok &= !!(a.conv2_out_u8 = dalloc<uint8_t>(e, Ss * m->gru));
   if (ok) ok = cudaMemset(a.hbuf_u8, 127, 2 * 3 * Ss * m->gru) == cudaSuccess;   // u8 image of h = 0
   ok &= !!(a.xb = dalloc<float>(e, 2 * Ss * FRAME_SIZE));
-  ok &= !!(a.features = dalloc<float>(e, Ss * NB_FEATURES));
-  ok &= !!(a.silence = dalloc<int>(e, Ss));
+  ok &= !!(a.features = dalloc<float>(e, 2 * Ss * NB_FEATURES));
+  ok &= !!(a.silence = dalloc<int>(e, 2 * Ss));
   ok &= !!(a.conv2_out = dalloc<float>(e, Ss * m->gru));
   ok &= !!(a.gains = dalloc<float>(e, Ss * NB_BANDS));
   ok &= !!(a.vad = dalloc<float>(e, Ss));
   e->host_frames = 0;
   e->bq_frames = 0;
-  e->s_h2d = e->s_d2h = e->s_bq = nullptr;
+  e->s_h2d = e->s_d2h = e->s_bq = e->s_front = nullptr;
+  e->ev_in = nullptr;
+  const char *ov = getenv("RNNOISE_B200_OVERLAP");
+  e->overlap = !(ov && !strcmp(ov, "0"));
+  ok &= cudaStreamCreateWithFlags(&e->s_front, cudaStreamNonBlocking) == cudaSuccess;
+  ok &= cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags(&e->s_bq, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
@@ -334,7 +348,9 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
     ok &= !!(e->stage_in[i] = dalloc<float>(e, Ss * FRAME_SIZE));
     ok &= !!(e->stage_out[i] = dalloc<float>(e, Ss * FRAME_SIZE));
     ok &= !!(e->stage_vad[i] = dalloc<float>(e, Ss));
-    e->ev_h2d[i] = e->ev_comp[i] = e->ev_d2h[i] = e->ev_bq[i] = e->ev_ana[i] = nullptr;
+    e->ev_h2d[i] = e->ev_comp[i] = e->ev_d2h[i] = e->ev_bq[i] = e->ev_ana[i] = e->ev_front[i] = e->ev_back[i] = nullptr;
+    ok &= cudaEventCreateWithFlags(&e->ev_front[i], cudaEventDisableTiming) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&e->ev_back[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_bq[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_ana[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess;
@@ -409,31 +425,49 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
     h_new[l] = a.hbuf + ((size_t)par * 3 + l) * hstride;
     h_old[l] = a.hbuf + ((size_t)(par ^ 1) * 3 + l) * hstride;
   }
+  // Two-stream software pipeline: the analysis front (biquad -> k_pitch -> k_spectrum) of frame f runs
+  // on s_front and only waits for what it really depends on, so it overlaps the network + synthesis
+  // of frame f-1 still running on the caller's stream `st`.  Hazards: xb[par] (ev_ana), the spectrum
+  // slot f%3 and features/silence[par], last read by frame f-2's back half (ev_back[par]).
+  const bool overlap = e->overlap && !e->profiling;
+  cudaStream_t sf = overlap ? e->s_front : st;
   int ki = 0;
 #define MARK() do { if (e->profiling) cudaEventRecord(e->ev[ki++], st); } while (0)
   const int fr = (int)(e->frames & 0x3fffffff);
+  const int *sil = a.silence + (size_t)par * S;
+  const float *feat = a.features + (size_t)par * S * NB_FEATURES;
   MARK();
   if (e->bq_frames > e->frames) {
     // the prefilter of this frame was issued ahead on the biquad stream (prefilter hint / pipelined
     // host call): just order the rest of the frame after it
-    CK(cudaStreamWaitEvent(st, e->ev_bq[par], 0));
+    CK(cudaStreamWaitEvent(sf, e->ev_bq[par], 0));
   } else {
-    k_biquad<<<(S + 31) / 32, 32, 0, st>>>(a, d_in, fr);
-    CK(cudaEventRecord(e->ev_bq[par], st));
+    if (overlap) {   // the input is ordered on the caller's stream
+      CK(cudaEventRecord(e->ev_in, st));
+      CK(cudaStreamWaitEvent(sf, e->ev_in, 0));
+      CK(cudaStreamWaitEvent(sf, e->ev_bq[par ^ 1], 0));   // biquad state: after frame f-1's filter
+    }
+    k_biquad<<<(S + 31) / 32, 32, 0, sf>>>(a, d_in, fr);
+    CK(cudaEventRecord(e->ev_bq[par], sf));
     e->bq_frames = e->frames + 1;
   }
   MARK();
-  k_pitch<<<(S + PITCH_NS - 1) / PITCH_NS, PITCH_NS * DSP_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr);
-  CK(cudaEventRecord(e->ev_ana[par], st));   // xb[par] is free again
+  k_pitch<<<(S + PITCH_NS - 1) / PITCH_NS, PITCH_NS * DSP_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
+  CK(cudaEventRecord(e->ev_ana[par], sf));   // xb[par] is free again
   MARK();
-  k_spectrum<<<S, DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr);
+  if (overlap) CK(cudaStreamWaitEvent(sf, e->ev_back[par], 0));   // frame f-2 is done with slot f%3 / parity buffers
+  k_spectrum<<<S, DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
+  if (overlap) {
+    CK(cudaEventRecord(e->ev_front[par], sf));
+    CK(cudaStreamWaitEvent(st, e->ev_front[par], 0));
+  }
   MARK();
   const int gts = (S + RNN_TS - 1) / RNN_TS;
-  k_conv1<<<gts, 128, 0, st>>>(S, e->dm, a.features, a.conv1_state, a.silence, a.c2in);
+  k_conv1<<<gts, 128, 0, st>>>(S, e->dm, feat, a.conv1_state, sil, a.c2in);
   MARK();
   if (e->conv2_tc)
     k_tc2<false><<<dim3((S + TC_M - 1) / TC_M, 4), P_THREADS, tc2_smem_bytes<false>(3 * cond, gru), st>>>(
-        S, 3 * cond, gru, e->conv_maps, e->dm.conv2, e->dm.conv2, nullptr, a.conv2_out, a.conv2_out_u8, a.silence);
+        S, 3 * cond, gru, e->conv_maps, e->dm.conv2, e->dm.conv2, nullptr, a.conv2_out, a.conv2_out_u8, sil);
   else
     k_conv2<<<gts, 128, RNN_TS * (3 * cond / 4) * sizeof(uint32_t), st>>>(S, e->dm, a.c2in, a.conv2_out, a.conv2_out_u8);
   MARK();
@@ -442,20 +476,21 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
     uint8_t *hu8_new = a.hbuf_u8 + ((size_t)par * 3 + l) * hstride;
     if (e->use_tc == 2) {
       k_tc2<true><<<dim3((S + TC_M - 1) / TC_M, 4), P_THREADS, tc2_smem_bytes<true>(gru, gru), st>>>(
-          S, gru, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, a.silence);
+          S, gru, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, sil);
     } else if (e->use_tc == 1) {
       k_gru_tc<<<dim3((S + TC_M - 1) / TC_M, gru / TC_UNITS), 160, gru_tc_smem_bytes(gru), st>>>(
-          S, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, a.silence);
+          S, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, sil);
     } else {
       const float *x = l == 0 ? a.conv2_out : h_new[l - 1];
-      k_gru<<<dim3(gts, gru / 128), 128, gsm, st>>>(S, gru, e->dm.gru_in[l], e->dm.gru_rec[l], x, h_old[l], h_new[l], hu8_new, a.silence);
+      k_gru<<<dim3(gts, gru / 128), 128, gsm, st>>>(S, gru, e->dm.gru_in[l], e->dm.gru_rec[l], x, h_old[l], h_new[l], hu8_new, sil);
     }
     MARK();
   }
-  k_heads<<<(S + HEAD_TS - 1) / HEAD_TS, 160, 0, st>>>(S, e->dm, a.conv2_out, h_new[0], h_new[1], h_new[2], a.silence,
+  k_heads<<<(S + HEAD_TS - 1) / HEAD_TS, 160, 0, st>>>(S, e->dm, a.conv2_out, h_new[0], h_new[1], h_new[2], sil,
                                                       a.gains, a.vad, d_vad);
   MARK();
   k_synthesis<<<S, DSP_THREADS, SS_TOTAL * sizeof(float), st>>>(a, e->d_tables, d_out, fr);
+  CK(cudaEventRecord(e->ev_back[par], st));
   MARK();
 #undef MARK
   CK(cudaGetLastError());
@@ -530,6 +565,7 @@ extern "C" int b200_engine_sync(B200Engine *e) {
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->s_h2d));
   CK(cudaStreamSynchronize(e->s_bq));
+  CK(cudaStreamSynchronize(e->s_front));
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaStreamSynchronize(e->s_d2h));
   return 0;
@@ -576,7 +612,7 @@ extern "C" int b200_engine_reset_stream(B200Engine *e, int s) {
   for (int c_ = 0; c_ < (copies); c_++)                                                                 \
     CK(cudaMemsetAsync((ptr) + ((size_t)c_ * S + s) * (per), 0, (size_t)(per) * sizeof(*(ptr)), st));
   ZERO(a.ring, PITCH_BUF_SIZE, 1) ZERO(a.synth_mem, FRAME_SIZE, 1) ZERO(a.hp_mem, 2, 1)
-  ZERO(a.spec, 4 * FREQ_SIZE, 2) ZERO(a.band, 96, 2) ZERO(a.lastg, NB_BANDS, 1) ZERO(a.pitch_state, 2, 1)
+  ZERO(a.spec, 4 * FREQ_SIZE, 3) ZERO(a.band, 96, 3) ZERO(a.lastg, NB_BANDS, 1) ZERO(a.pitch_state, 2, 1)
   ZERO(a.conv1_state, 2 * NB_FEATURES, 1) ZERO(a.hbuf, a.gru, 6)
 #undef ZERO
   for (int c = 0; c < 6; c++) CK(cudaMemsetAsync(a.hbuf_u8 + ((size_t)c * S + s) * a.gru, 127, a.gru, st));
@@ -591,16 +627,16 @@ extern "C" int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst
   CK(cudaStreamSynchronize(e->stream));
   const Arena &a = e->a;
   const size_t S = a.S;
-  const int par = (int)((e->frames - 1) & 1);
+  const int par = (int)((e->frames - 1) & 1), slot = (int)((e->frames - 1) % 3);
   const float *src = nullptr;
   int n = 0;
   switch (what) {
-    case RNNOISE_DBG_FEATURES: src = a.features + (size_t)s * NB_FEATURES; n = NB_FEATURES; break;
-    case RNNOISE_DBG_X: src = a.spec + ((size_t)par * S + s) * 4 * FREQ_SIZE; n = 2 * FREQ_SIZE; break;
-    case RNNOISE_DBG_P: src = a.spec + ((size_t)par * S + s) * 4 * FREQ_SIZE + 2 * FREQ_SIZE; n = 2 * FREQ_SIZE; break;
-    case RNNOISE_DBG_EX: src = a.band + ((size_t)par * S + s) * 96; n = 32; break;
-    case RNNOISE_DBG_EP: src = a.band + ((size_t)par * S + s) * 96 + 32; n = 32; break;
-    case RNNOISE_DBG_EXP: src = a.band + ((size_t)par * S + s) * 96 + 64; n = 32; break;
+    case RNNOISE_DBG_FEATURES: src = a.features + ((size_t)par * S + s) * NB_FEATURES; n = NB_FEATURES; break;
+    case RNNOISE_DBG_X: src = a.spec + ((size_t)slot * S + s) * 4 * FREQ_SIZE; n = 2 * FREQ_SIZE; break;
+    case RNNOISE_DBG_P: src = a.spec + ((size_t)slot * S + s) * 4 * FREQ_SIZE + 2 * FREQ_SIZE; n = 2 * FREQ_SIZE; break;
+    case RNNOISE_DBG_EX: src = a.band + ((size_t)slot * S + s) * 96; n = 32; break;
+    case RNNOISE_DBG_EP: src = a.band + ((size_t)slot * S + s) * 96 + 32; n = 32; break;
+    case RNNOISE_DBG_EXP: src = a.band + ((size_t)slot * S + s) * 96 + 64; n = 32; break;
     case RNNOISE_DBG_GAINS: src = a.gains + (size_t)s * NB_BANDS; n = NB_BANDS; break;
     case RNNOISE_DBG_LASTG: src = a.lastg + (size_t)s * NB_BANDS; n = NB_BANDS; break;
     case RNNOISE_DBG_XB: src = a.xb + ((size_t)par * S + s) * FRAME_SIZE; n = FRAME_SIZE; break;
@@ -616,7 +652,7 @@ extern "C" int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst
       return n;
     }
     case RNNOISE_DBG_PITCH: src = a.pitch_state + 2 * (size_t)s; n = 2; break;
-    case RNNOISE_DBG_SILENCE: src = (const float *)(a.silence + s); n = 1; break;
+    case RNNOISE_DBG_SILENCE: src = (const float *)(a.silence + (size_t)par * S + s); n = 1; break;
     case RNNOISE_DBG_CONV2_OUT: src = a.conv2_out + (size_t)s * a.gru; n = a.gru; break;
     default: return -1;
   }

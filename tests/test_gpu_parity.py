@@ -275,3 +275,28 @@ def test_prefilter_hint_path_equals_plain_device_call(rb, models_dir):
         a.sync(); b.sync()
         assert torch.equal(oa, ob) and torch.equal(va, vb), f
     a.destroy(); b.destroy(); model.free()
+
+
+def test_two_stream_overlap_is_race_free(rb, models_dir):
+    """The analysis of frame f+1 overlaps network + synthesis of frame f on another stream (triple-
+    buffered spectra, double-buffered features).  A long back-to-back run through the pipelined call
+    must equal the same run with RNNOISE_B200_OVERLAP=0 bit for bit."""
+    import torch
+    model = rb.Model(os.path.join(models_dir, "default.bin"))
+    S, frames = 1500, 40
+    os.environ["RNNOISE_B200_OVERLAP"] = "0"
+    a = rb.Batch(model, S)
+    del os.environ["RNNOISE_B200_OVERLAP"]
+    b = rb.Batch(model, S)
+    pcm = torch.from_numpy(batch_pcm(S, frames)).pin_memory()
+    oa = [torch.empty(S, 480).pin_memory() for _ in range(frames)]
+    ob = [torch.empty(S, 480).pin_memory() for _ in range(frames)]
+    va = [torch.empty(S).pin_memory() for _ in range(frames)]
+    vb = [torch.empty(S).pin_memory() for _ in range(frames)]
+    for f in range(frames):
+        a.process_ptr_async(oa[f].data_ptr(), pcm[f].data_ptr(), va[f].data_ptr())
+        b.process_ptr_async(ob[f].data_ptr(), pcm[f].data_ptr(), vb[f].data_ptr())
+    a.sync(); b.sync()
+    for f in range(frames):
+        assert torch.equal(oa[f], ob[f]) and torch.equal(va[f], vb[f]), f
+    a.destroy(); b.destroy(); model.free()
