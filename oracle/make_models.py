@@ -16,6 +16,7 @@ Models:
   default : seed 1234, cond128/gru384, densities .2/.3/.5             ("gentle": gains ~0.4-0.6)
   hot     : same, GRU W x3, conv W x2, head W x8                        (saturating gates)
   little  : seed 4321, same dims, densities x0.5 (README:119-125 "little" = more sparsity)
+  g256    : seed 99, cond128/gru256 (dimension-generality check; compared against the port only)
 
 Usage: python oracle/make_models.py [names...]
 """
@@ -34,6 +35,8 @@ SPECS = {
     "default": dict(seed=1234, cond=128, gru=384, density_scale=1.0, hot=False),
     "hot": dict(seed=1234, cond=128, gru=384, density_scale=1.0, hot=True),
     "little": dict(seed=4321, cond=128, gru=384, density_scale=0.5, hot=False),
+    # other dimensions (the engine infers them from the blob): GRU 256 -> 2 swizzle atoms, 4 unit slices per CTA
+    "g256": dict(seed=99, cond=128, gru=256, density_scale=1.0, hot=False),
 }
 
 
