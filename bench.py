@@ -186,7 +186,7 @@ def main():
     vad_d = torch.empty(S, device=dev)
     # a dedicated non-default stream: handle 0 (the legacy default stream) means "private stream" to
     # rnnoise_batch_set_stream(), and events must be recorded on the stream the kernels run on.
-    stream = torch.cuda.Stream(dev)
+    stream = torch.cuda.Stream(dev, priority=int(os.environ.get("BENCH_STREAM_PRIORITY", "-1")))
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     batch.set_stream(stream.cuda_stream)

@@ -95,20 +95,24 @@ __global__ void __launch_bounds__(PITCH_NS *DSP_THREADS, PITCH_MIN_CTAS)
 k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
   extern __shared__ float sm[];
   __shared__ PitchArgs pa[PITCH_NS];
-  if (threadIdx.x < PITCH_NS) {
-    const int s = blockIdx.x * PITCH_NS + threadIdx.x;
-    PitchArgs g;
-    g.ring = nullptr; g.xb = nullptr; g.pitch_state = nullptr;
-    g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
-    if (s < a.S) {
-      g.xb = a.xb + ((size_t)(f & 1) * a.S + s) * FRAME_SIZE;
-      g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
-      g.pitch_state = a.pitch_state + 2 * (size_t)s;
+  // grid-stride over stream groups: the grid may be capped (engine: front_ctas) so that the analysis
+  // front leaves SM resources to the network kernels of the previous frame running concurrently
+  for (int grp = blockIdx.x; grp * PITCH_NS < a.S; grp += gridDim.x) {
+    if (threadIdx.x < PITCH_NS) {
+      const int s = grp * PITCH_NS + threadIdx.x;
+      PitchArgs g;
+      g.ring = nullptr; g.xb = nullptr; g.pitch_state = nullptr;
+      g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+      if (s < a.S) {
+        g.xb = a.xb + ((size_t)(f & 1) * a.S + s) * FRAME_SIZE;
+        g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
+        g.pitch_state = a.pitch_state + 2 * (size_t)s;
+      }
+      pa[threadIdx.x] = g;
     }
-    pa[threadIdx.x] = g;
+    __syncthreads();
+    pitch_streams(sm, pa, T);   // ends with a barrier
   }
-  __syncthreads();
-  pitch_streams(sm, pa, T);
 }
 
 #ifndef SPEC_MIN_BLOCKS
@@ -116,8 +120,8 @@ k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
 #endif
 __global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena a, const DspTables *__restrict__ T, int f) {
   extern __shared__ float sm[];
-  const int s = blockIdx.x;
   const int par = f & 1, slot = f % 3;
+  for (int s = blockIdx.x; s < a.S; s += gridDim.x) {   // grid-stride, see k_pitch
   SpectrumArgs g;
   g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
   g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
@@ -126,7 +130,8 @@ __global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena
   g.band_out = a.band + ((size_t)slot * a.S + s) * 96;
   g.features = a.features + ((size_t)par * a.S + s) * NB_FEATURES;
   g.silence = a.silence + (size_t)par * a.S + s;
-  spectrum_stream(sm, g, T);
+  spectrum_stream(sm, g, T);   // ends with a barrier
+  }
 }
 
 __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTables *__restrict__ T,
@@ -164,6 +169,7 @@ struct B200Engine {
   cudaEvent_t ev_front[2], ev_back[2];   // analysis of frame f done / network+synthesis of frame f done (by parity)
   cudaEvent_t ev_in;                 // input readiness on the caller's stream (non-prefiltered frames)
   int overlap;                       // 0: everything on one stream (RNNOISE_B200_OVERLAP=0, profiling)
+  int front_ctas;                    // cap on the analysis kernels' grid (0 = one CTA per stream)
   cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
   cudaEvent_t ev_bq[2], ev_ana[2];   // biquad of frame f done / analysis of frame f done (xb slot free)
   long long host_frames;
@@ -339,7 +345,18 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   e->ev_in = nullptr;
   const char *ov = getenv("RNNOISE_B200_OVERLAP");
   e->overlap = !(ov && !strcmp(ov, "0"));
-  ok &= cudaStreamCreateWithFlags(&e->s_front, cudaStreamNonBlocking) == cudaSuccess;
+  {
+    // RNNOISE_B200_FRONT_CTAS_PER_SM = r caps k_pitch / k_spectrum at r resident CTAs per SM (grid-stride
+    // over the streams) so they share each SM with the previous frame's network kernels; 0 = no cap
+    const char *fc = getenv("RNNOISE_B200_FRONT_CTAS_PER_SM");
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    e->front_ctas = fc ? atoi(fc) * sms : 0;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = lowest priority (largest value)
+    const char *pr = getenv("RNNOISE_B200_FRONT_PRIORITY");
+    ok &= cudaStreamCreateWithPriority(&e->s_front, cudaStreamNonBlocking, pr && !strcmp(pr, "high") ? hi : lo) == cudaSuccess;
+  }
   ok &= cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags(&e->s_bq, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
@@ -452,11 +469,13 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
     e->bq_frames = e->frames + 1;
   }
   MARK();
-  k_pitch<<<(S + PITCH_NS - 1) / PITCH_NS, PITCH_NS * DSP_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
+  const int pitch_grid = (S + PITCH_NS - 1) / PITCH_NS;
+  const int cap = overlap && e->front_ctas > 0 ? e->front_ctas : 0x7fffffff;
+  k_pitch<<<min(pitch_grid, cap), PITCH_NS * DSP_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
   CK(cudaEventRecord(e->ev_ana[par], sf));   // xb[par] is free again
   MARK();
   if (overlap) CK(cudaStreamWaitEvent(sf, e->ev_back[par], 0));   // frame f-2 is done with slot f%3 / parity buffers
-  k_spectrum<<<S, DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
+  k_spectrum<<<min(S, cap), DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
   if (overlap) {
     CK(cudaEventRecord(e->ev_front[par], sf));
     CK(cudaStreamWaitEvent(st, e->ev_front[par], 0));
