@@ -74,8 +74,10 @@ struct DspTables {
 //   spectrum kernel
 #define SM_F 0                           // [1920] FFT work buffer (interleaved complex)
 #define SM_XS (SM_F + 2 * WINDOW_SIZE)   // [962] X kept for the X.P correlation
-#define SM_TB (SM_XS + 2 * FREQ_SIZE)     // [3][400] per-bin terms |X|^2, |P|^2, Re(X conj P) for the band sums
-#define SM_SPEC_END (SM_TB + 3 * 400)
+#define SM_WIN (SM_XS + 2 * FREQ_SIZE)    // [960] analysis window staged from the ring (coalesced); after the P
+                                         //       transform's first stage: per-bin terms |P|^2 [0,400), Re(X conj P) [400,800)
+#define SM_TX (SM_WIN + WINDOW_SIZE)     // [400] per-bin terms |X|^2
+#define SM_SPEC_END (SM_TX + 400)
 #define SM_MISC_SIZE 288                 // small per-stream scalars / band vectors, after either plan
 #define SM_PITCH_TOTAL (SM_PITCH_END + SM_MISC_SIZE)
 #define SM_SPEC_TOTAL (SM_SPEC_END + SM_MISC_SIZE)
@@ -111,10 +113,9 @@ HD cpx csub(cpx a, cpx b) { cpx m; m.r = a.r - b.r; m.i = a.i - b.i; return m; }
 
 // Stage 1 (radix 4, m = 1) fused with the bit-reversed, scaled, windowed load: group g gathers
 // its four inputs straight from `src` (kiss_fft.c:577-584 + kf_bfly4 m==1 branch :112-130).
-// Input element i of the transform is win(i) * history[start + i] (imag 0) when `herm` is null
-// (history = the pitch ring, logical index start + i), or the Hermitian extension of herm[0..480]
-// (inverse_transform, denoise.c:200-211).
-HD void fft_stage1(cpx *F, const float *ring, int ring_base, int start, const cpx *herm, const DspTables *T, int tid, int nthr) {
+// Input element i of the transform is win(i) * src[i] (imag 0) when `herm` is null, or the
+// Hermitian extension of herm[0..480] (inverse_transform, denoise.c:200-211).
+HD void fft_stage1(cpx *F, const float *src, const cpx *herm, const DspTables *T, int tid, int nthr) {
   for (int g = tid; g < 240; g += nthr) {
     int j0 = g / 48, j1 = (g / 16) % 3, j2 = (g / 4) % 4, j3 = g % 4;
     int base = j0 + 5 * j1 + 15 * j2 + 60 * j3;
@@ -128,7 +129,7 @@ HD void fft_stage1(cpx *F, const float *ring, int ring_base, int start, const cp
         else { v.r = herm[WINDOW_SIZE - i].r; v.i = -herm[WINDOW_SIZE - i].i; }
       } else {
         int wi = i < FRAME_SIZE ? i : WINDOW_SIZE - 1 - i;
-        v.r = ring_at(ring, ring_base, start + i) * T->half_window[wi];
+        v.r = src[i] * T->half_window[wi];
         v.i = 0.f;
       }
       a[q].r = T->fft_scale * v.r;

@@ -355,11 +355,14 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   float *misc = sm + SM_SPEC_END;
   int *mi = (int *)(misc + MI_INT);
   cpx *F = (cpx *)(sm + SM_F), *XS = (cpx *)(sm + SM_XS);
-  float *tb = sm + SM_TB;
+  float *win = sm + SM_WIN, *tx = sm + SM_TX;
   const int pitch_T = ((const int *)a.pitch_state)[0];
   // -- X = FFT(window * [previous frame | this frame]) (denoise.c:332-339); the analysis window
   //    is the last 960 samples of the updated pitch history.
-  PHASE_BEGIN fft_stage1(F, a.ring, a.ring_base, PITCH_BUF_SIZE - WINDOW_SIZE, nullptr, T, tid, nthr); PHASE_END
+  PHASE_BEGIN
+    for (int i = tid; i < WINDOW_SIZE; i += nthr) win[i] = ring_at(a.ring, a.ring_base, PITCH_BUF_SIZE - WINDOW_SIZE + i);
+  PHASE_END
+  PHASE_BEGIN fft_stage1(F, win, nullptr, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
@@ -369,11 +372,13 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
       cpx v = F[i];
       XS[i] = v;
       ((cpx *)a.spec_out)[i] = v;
-      if (i < 400) tb[i] = bin_term(v, v);
+      if (i < 400) tx[i] = bin_term(v, v);
     }
+    // stage the pitch-lagged window for the second transform (coalesced read of the ring)
+    for (int i = tid; i < WINDOW_SIZE; i += nthr) win[i] = ring_at(a.ring, a.ring_base, PITCH_BUF_SIZE - WINDOW_SIZE - pitch_T + i);
   PHASE_END
   // -- P = FFT(window * pitch_buf[768-T .. 768-T+960)) (denoise.c:371-374)
-  PHASE_BEGIN fft_stage1(F, a.ring, a.ring_base, PITCH_BUF_SIZE - WINDOW_SIZE - pitch_T, nullptr, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_stage1(F, win, nullptr, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
@@ -382,14 +387,14 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
     for (int i = tid; i < FREQ_SIZE; i += nthr) {
       cpx v = F[i];
       ((cpx *)a.spec_out)[FREQ_SIZE + i] = v;
-      if (i < 400) { tb[400 + i] = bin_term(v, v); tb[800 + i] = bin_term(XS[i], v); }
+      if (i < 400) { win[i] = bin_term(v, v); win[400 + i] = bin_term(XS[i], v); }   // staging is dead by now
     }
   PHASE_END
   // -- the three sets of 34 triangular band sums (compute_band_energy / compute_band_corr), one lane each
   PHASE_BEGIN
     if (tid < 3 * (NB_BANDS + 2)) {
       const int set = tid / (NB_BANDS + 2), b = tid % (NB_BANDS + 2);
-      misc[MI_BAND + 34 * set + b] = band_sum_terms(b, tb + 400 * set, T);
+      misc[MI_BAND + 34 * set + b] = band_sum_terms(b, set == 0 ? tx : win + 400 * (set - 1), T);
     }
   PHASE_END
   // -- Ex, Ep, Exp (denoise.c:344,375-377)
@@ -529,7 +534,7 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       }
     PHASE_END
   }
-  PHASE_BEGIN fft_stage1(F, nullptr, 0, 0, X, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_stage1(F, nullptr, X, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END

@@ -249,14 +249,16 @@ k_gru_tc(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, D
 // grid = (ceil(S/128), 4), block = 544, 1 CTA / SM.
 // ================================================================================================
 #define P_SLICE 16
+#ifndef P_STAGES
 #define P_STAGES 3
+#endif
 #define P_TMEM_COLS 256                   // >= 2 stages x 96 columns, power of two
 
 template <bool kGru> struct TcCfg {
   static constexpr int kMats = kGru ? 2 : 1;                 // GEMMs per slice (input, recurrent)
   static constexpr int kN = kGru ? 3 * P_SLICE : P_SLICE;    // UMMA N: 48 / 16
   static constexpr int kBAtom = kN * TC_KATOM;               // bytes of one weight atom: 6144 / 2048
-  static constexpr int kPrm = kGru ? 15 : 2;                 // epilogue parameter vectors per unit
+  static constexpr int kPrm = kGru ? 16 : 2;                 // epilogue parameters per unit (GRU: 4 float4, see below)
   static constexpr int kCols = kMats * kN;                   // TMEM columns per stage: 96 / 16
 };
 template <bool kGru>
@@ -316,9 +318,16 @@ k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi,
   }
   for (int i = tid; i < C::kPrm * upc; i += blockDim.x) {
     if (kGru) {
-      int which = i / (3 * upc), g = (i / upc) % 3, u = i % upc;
-      const float *src = which == 0 ? wi.scale : which == 1 ? wi.subias : which == 2 ? wr.scale : which == 3 ? wr.subias : wr.diag;
-      prm[i] = src[g * N + jq + u];
+      // per unit u: {sc_i, sb_i, sc_r, sb_r} for z, r, n, then {diag_z, diag_r, diag_n, 0}: four LDS.128
+      const int u = i >> 4, c = i & 15;
+      float v = 0.f;
+      if (c < 12) {
+        const int g = c >> 2, w = c & 3;
+        v = (w == 0 ? wi.scale : w == 1 ? wi.subias : w == 2 ? wr.scale : wr.subias)[g * N + jq + u];
+      } else if (c < 15) {
+        v = wr.diag[(c - 12) * N + jq + u];
+      }
+      prm[i] = v;
     } else {
       prm[i] = (i < upc ? wi.scale : wi.subias)[jq + i % upc];
     }
@@ -412,12 +421,14 @@ k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi,
           const float h = hcur[q];
           float out = h;
           if (!silent) {
-            float zi = (float)az[q] * prm[(0 * 3 + 0) * upc + u] + prm[(1 * 3 + 0) * upc + u];
-            float ri = (float)ar[q] * prm[(0 * 3 + 1) * upc + u] + prm[(1 * 3 + 1) * upc + u];
-            float ni = (float)an[q] * prm[(0 * 3 + 2) * upc + u] + prm[(1 * 3 + 2) * upc + u];
-            float zr = fmaf(prm[(4 * 3 + 0) * upc + u], h, (float)bz[q] * prm[(2 * 3 + 0) * upc + u] + prm[(3 * 3 + 0) * upc + u]);
-            float rr = fmaf(prm[(4 * 3 + 1) * upc + u], h, (float)br[q] * prm[(2 * 3 + 1) * upc + u] + prm[(3 * 3 + 1) * upc + u]);
-            float nr = fmaf(prm[(4 * 3 + 2) * upc + u], h, (float)bn[q] * prm[(2 * 3 + 2) * upc + u] + prm[(3 * 3 + 2) * upc + u]);
+            const float4 pz = *(const float4 *)&prm[16 * u], pr = *(const float4 *)&prm[16 * u + 4];
+            const float4 pn = *(const float4 *)&prm[16 * u + 8], pd = *(const float4 *)&prm[16 * u + 12];
+            float zi = (float)az[q] * pz.x + pz.y;
+            float ri = (float)ar[q] * pr.x + pr.y;
+            float ni = (float)an[q] * pn.x + pn.y;
+            float zr = fmaf(pd.x, h, (float)bz[q] * pz.z + pz.w);
+            float rr = fmaf(pd.y, h, (float)br[q] * pr.z + pr.w);
+            float nr = fmaf(pd.z, h, (float)bn[q] * pn.z + pn.w);
             float z = act_sigmoid(zi + zr);
             float r = act_sigmoid(ri + rr);
             float n = act_tanh(ni + nr * r);
