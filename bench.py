@@ -44,10 +44,15 @@ def world():
     return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def pool_frames(S):
+    """Frames in the rotating input pool: 32, fewer for very large S (keeps pinned memory <= ~1 GB)."""
+    return int(max(4, min(POOL_FRAMES, (1 << 30) // (S * FRAME * 4))))
+
+
 def make_pool(S):
-    """float32 [POOL_FRAMES][S][480]: POOL_STREAMS distinct synthetic streams tiled to S."""
+    """float32 [pool_frames(S)][S][480]: POOL_STREAMS distinct synthetic streams tiled to S."""
     from rnnoise_b200.synth_pcm import batch_pcm
-    base = batch_pcm(min(POOL_STREAMS, S), POOL_FRAMES)
+    base = batch_pcm(min(POOL_STREAMS, S), pool_frames(S))
     reps = (S + base.shape[1] - 1) // base.shape[1]
     return np.ascontiguousarray(np.tile(base, (1, reps, 1))[:, :S])
 
@@ -129,6 +134,7 @@ def cpu_model():
 
 
 def main():
+    global POOL_FRAMES
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -143,7 +149,7 @@ def main():
                        f"one 480-sample frame per stream per step", "streams_per_gpu": S, "frame": FRAME,
            "model": "tests/golden/models/default.bin",
            "l2": f"per-step state+I/O working set {S * 43344 / 1e6:.0f} MB vs 126 MB L2; input rotates through a "
-                 f"{POOL_FRAMES}-frame device pool ({POOL_FRAMES * S * FRAME * 4 / 1e6:.0f} MB)"}
+                 f"{pool_frames(S)}-frame device pool ({pool_frames(S) * S * FRAME * 4 / 1e6:.0f} MB)"}
 
     if a.impl == "reference":
         # CPU arm: rank 0 alone runs it; other ranks exit quietly.
@@ -181,6 +187,7 @@ def main():
     model = rnnoise_b200.Model(MODEL)
     batch = rnnoise_b200.Batch(model, S, local)
     pool_h = torch.from_numpy(make_pool(S)).pin_memory()           # [POOL][S][480] pinned host
+    POOL_FRAMES = pool_h.shape[0]
     pool_d = pool_h.to(dev)                                        # device-resident inputs
     out_d = torch.empty(S, FRAME, device=dev)
     vad_d = torch.empty(S, device=dev)
