@@ -269,7 +269,20 @@ def main():
     for i in range(20):
         batch.process_ptr(out_h[0].data_ptr(), pool_h[i % POOL_FRAMES].data_ptr(), vad_h[0].data_ptr())
     ms_sync = (time.perf_counter() - t0) * 1e3 / 20
+    # same pipeline with 16-bit PCM in both directions (rnnoise_process_frame_batch_s16_async)
+    in16 = pool_h[:min(8, POOL_FRAMES)].to(torch.int16).pin_memory()
+    out16 = [torch.empty(S, FRAME, dtype=torch.int16).pin_memory() for _ in range(NBUF)]
+    for i in range(4):
+        batch.process_ptr_s16_async(out16[i % NBUF].data_ptr(), in16[i % in16.shape[0]].data_ptr(), vad_h[i % NBUF].data_ptr())
+    batch.sync()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        batch.process_ptr_s16_async(out16[i % NBUF].data_ptr(), in16[i % in16.shape[0]].data_ptr(), vad_h[i % NBUF].data_ptr())
+    batch.sync()
+    ms_16 = (time.perf_counter() - t0) * 1e3
     e2e = {"value": W * S * Ke / (ms_e * 1e-3), "unit": "frames/s", "steps": Ke, "ms_per_step": ms_e / Ke,
+           "int16_pcm": {"value": S * Ke / (ms_16 * 1e-3), "h2d_bytes_per_step": S * FRAME * 2, "d2h_bytes_per_step": S * FRAME * 2 + S * 4,
+                         "note": "this rank only"},
            "h2d_bytes_per_step": S * FRAME * 4, "d2h_bytes_per_step": S * FRAME * 4 + S * 4,
            "api": "rnnoise_process_frame_batch_async + rnnoise_batch_sync (pinned host buffers; H2D, kernels, D2H of every step inside the wall-clock region)",
            "synchronous_call_ms_per_step": ms_sync}

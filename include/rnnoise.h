@@ -103,6 +103,15 @@ RNNOISE_EXPORT int rnnoise_process_frame_batch(RNNoiseBatch *b, float *out, cons
  *  synchronous call) returns.  Use pinned host memory, otherwise the copies serialise. */
 RNNOISE_EXPORT int rnnoise_process_frame_batch_async(RNNoiseBatch *b, float *out, const float *in, float *vad);
 
+/** 16-bit PCM variants: in/out are [nb_streams][480] int16 samples, the
+ *  format examples/rnnoise_demo.c:53-58 reads and writes.  Input samples are widened to float exactly
+ *  (x = tmp[i]); output samples are narrowed like the demo's C cast (truncation toward zero, low 16
+ *  bits).  Half the PCIe bytes of the float calls; same kernels otherwise.  The _async form pipelines
+ *  like rnnoise_process_frame_batch_async(); the _device form takes device pointers. */
+RNNOISE_EXPORT int rnnoise_process_frame_batch_s16(RNNoiseBatch *b, short *out, const short *in, float *vad);
+RNNOISE_EXPORT int rnnoise_process_frame_batch_s16_async(RNNoiseBatch *b, short *out, const short *in, float *vad);
+RNNOISE_EXPORT int rnnoise_process_frame_batch_device_s16(RNNoiseBatch *b, short *d_out, const short *d_in, float *d_vad);
+
 /** Device-buffer call: d_in/d_out/d_vad are device pointers on the batch's device (d_out may alias
  *  d_in; d_vad may be NULL).  Enqueues the frame on the batch's stream and returns without
  *  synchronising.  0 on success, -1 on a launch error. */

@@ -50,6 +50,8 @@ def lib():
         L.rnnoise_batch_get_streams.restype = ip; L.rnnoise_batch_get_streams.argtypes = [vp]
         L.rnnoise_process_frame_batch.restype = ip; L.rnnoise_process_frame_batch.argtypes = [vp, vp, vp, vp]
         L.rnnoise_process_frame_batch_async.restype = ip; L.rnnoise_process_frame_batch_async.argtypes = [vp, vp, vp, vp]
+        for nm in ("rnnoise_process_frame_batch_s16", "rnnoise_process_frame_batch_s16_async", "rnnoise_process_frame_batch_device_s16"):
+            getattr(L, nm).restype = ip; getattr(L, nm).argtypes = [vp, vp, vp, vp]
         L.rnnoise_process_frame_batch_device.restype = ip; L.rnnoise_process_frame_batch_device.argtypes = [vp, vp, vp, vp]
         L.rnnoise_batch_prefilter_device.restype = ip; L.rnnoise_batch_prefilter_device.argtypes = [vp, vp]
         L.rnnoise_batch_sync.restype = ip; L.rnnoise_batch_sync.argtypes = [vp]
@@ -109,6 +111,20 @@ class Batch:
         """Host-buffer call on raw addresses (e.g. pinned torch tensors)."""
         if lib().rnnoise_process_frame_batch(self.handle, out_ptr, in_ptr, vad_ptr) != 0:
             raise RuntimeError("rnnoise_process_frame_batch failed")
+
+    def process_s16(self, pcm16):
+        """pcm16: int16 [nb_streams][480] host array -> (out int16 [nb_streams][480], vad)."""
+        x = np.ascontiguousarray(pcm16, np.int16)
+        assert x.shape == (self.nb_streams, FRAME_SIZE)
+        out = np.empty_like(x)
+        vad = np.empty(self.nb_streams, np.float32)
+        if lib().rnnoise_process_frame_batch_s16(self.handle, out.ctypes.data, x.ctypes.data, vad.ctypes.data) != 0:
+            raise RuntimeError("rnnoise_process_frame_batch_s16 failed")
+        return out, vad
+
+    def process_ptr_s16_async(self, out_ptr, in_ptr, vad_ptr=None):
+        if lib().rnnoise_process_frame_batch_s16_async(self.handle, out_ptr, in_ptr, vad_ptr) != 0:
+            raise RuntimeError("rnnoise_process_frame_batch_s16_async failed")
 
     def process_ptr_async(self, out_ptr, in_ptr, vad_ptr=None):
         """Pipelined host-buffer call (pinned memory); results valid after sync()."""

@@ -457,7 +457,8 @@ struct SynthesisArgs {
   const int *silence;       // [1]
   float *lastg;             // [32]
   float *synthesis_mem;     // [480]
-  float *out;               // [480]
+  float *out;               // [480] float PCM, or
+  short *out_s16;           // [480] 16-bit PCM (non-null selects it): the C cast of examples/rnnoise_demo.c:58
 };
 
 // shared-memory plan of the synthesis CTA (floats)
@@ -546,7 +547,9 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       float t1 = WINDOW_SIZE * F[WINDOW_SIZE - (FRAME_SIZE + i)].r;   // index 480+i -> y[480-i]
       t0 *= T->half_window[i];
       t1 *= T->half_window[FRAME_SIZE - 1 - i];
-      a.out[i] = t0 + a.synthesis_mem[i];
+      const float o = t0 + a.synthesis_mem[i];
+      if (a.out_s16) a.out_s16[i] = (short)(int)o;   // truncation toward zero, low 16 bits (x86 cvttss2si + narrowing)
+      else a.out[i] = o;
       a.synthesis_mem[i] = t1;
     }
   PHASE_END

@@ -66,7 +66,10 @@ struct Arena {
 // High-pass biquad (rnn_biquad, denoise.c:409-419): strictly serial per stream (each step rounds
 // the state to float), so one THREAD owns one stream; a warp transposes 32x32 tiles through shared
 // memory so that global traffic stays coalesced.  grid = ceil(S/32), block = 32.
-__global__ void __launch_bounds__(32) k_biquad(Arena a, const float *__restrict__ in, int frame) {
+// `in` is float PCM, or 16-bit PCM when in_s16 != 0 (widened exactly like examples/rnnoise_demo.c:56).
+__global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__ in_, int frame, int in_s16) {
+  const float *in = (const float *)in_;
+  const short *in16 = (const short *)in_;
   __shared__ float tile[32][33];
   const int lane = threadIdx.x, s0 = blockIdx.x * 32, s = s0 + lane;
   float *xb = a.xb + (size_t)(frame & 1) * a.S * FRAME_SIZE;
@@ -74,7 +77,10 @@ __global__ void __launch_bounds__(32) k_biquad(Arena a, const float *__restrict_
   if (s < a.S) { m0 = a.hp_mem[2 * s]; m1 = a.hp_mem[2 * s + 1]; }
   const int rows = min(32, a.S - s0);
   for (int c = 0; c < FRAME_SIZE / 32; c++) {
-    for (int r = 0; r < rows; r++) tile[r][lane] = in[(size_t)(s0 + r) * FRAME_SIZE + c * 32 + lane];
+    if (in_s16)
+      for (int r = 0; r < rows; r++) tile[r][lane] = (float)in16[(size_t)(s0 + r) * FRAME_SIZE + c * 32 + lane];
+    else
+      for (int r = 0; r < rows; r++) tile[r][lane] = in[(size_t)(s0 + r) * FRAME_SIZE + c * 32 + lane];
     __syncwarp();
     if (s < a.S) {
 #pragma unroll 4
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena
 }
 
 __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTables *__restrict__ T,
-                                                           float *__restrict__ out, int f) {
+                                                           void *__restrict__ out, int f, int out_s16) {
   extern __shared__ float sm[];
   const int s = blockIdx.x;
   const int par = f & 1, slot = f % 3, dslot = (f + 2) % 3;   // dslot = (f - 1) mod 3
@@ -147,7 +153,8 @@ __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTab
   g.silence = a.silence + (size_t)par * a.S + s;
   g.lastg = a.lastg + (size_t)s * NB_BANDS;
   g.synthesis_mem = a.synth_mem + (size_t)s * FRAME_SIZE;
-  g.out = out + (size_t)s * FRAME_SIZE;
+  g.out = out_s16 ? nullptr : (float *)out + (size_t)s * FRAME_SIZE;
+  g.out_s16 = out_s16 ? (short *)out + (size_t)s * FRAME_SIZE : nullptr;
   synthesis_stream(sm, g, T);
 }
 
@@ -429,7 +436,14 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
 extern "C" int b200_engine_streams(const B200Engine *e) { return e ? e->a.S : 0; }
 extern "C" int b200_engine_launches_per_frame(const B200Engine *) { return NKERNELS; }
 
+static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *d_vad, int s16);
 extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float *d_in, float *d_vad) {
+  return frame_device_io(e, d_out, d_in, d_vad, 0);
+}
+extern "C" int b200_engine_frame_device_s16(B200Engine *e, short *d_out, const short *d_in, float *d_vad) {
+  return frame_device_io(e, d_out, d_in, d_vad, 1);
+}
+static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *d_vad, int s16) {
   if (!e || !d_out || !d_in) return -1;
   CK(cudaSetDevice(e->device));
   const Arena &a = e->a;
@@ -464,7 +478,7 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
       CK(cudaStreamWaitEvent(sf, e->ev_in, 0));
       CK(cudaStreamWaitEvent(sf, e->ev_bq[par ^ 1], 0));   // biquad state: after frame f-1's filter
     }
-    k_biquad<<<(S + 31) / 32, 32, 0, sf>>>(a, d_in, fr);
+    k_biquad<<<(S + 31) / 32, 32, 0, sf>>>(a, d_in, fr, s16);
     CK(cudaEventRecord(e->ev_bq[par], sf));
     e->bq_frames = e->frames + 1;
   }
@@ -508,7 +522,7 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
   k_heads<<<(S + HEAD_TS - 1) / HEAD_TS, 160, 0, st>>>(S, e->dm, a.conv2_out, h_new[0], h_new[1], h_new[2], sil,
                                                       a.gains, a.vad, d_vad);
   MARK();
-  k_synthesis<<<S, DSP_THREADS, SS_TOTAL * sizeof(float), st>>>(a, e->d_tables, d_out, fr);
+  k_synthesis<<<S, DSP_THREADS, SS_TOTAL * sizeof(float), st>>>(a, e->d_tables, d_out, fr, s16);
   CK(cudaEventRecord(e->ev_back[par], st));
   MARK();
 #undef MARK
@@ -528,14 +542,14 @@ extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float
 
 // Issue the high-pass prefilter of the next not-yet-prefiltered frame on the biquad stream.
 // `ready` (optional) = event after which d_in is valid.  At most two frames ahead of processing.
-static int issue_prefilter(B200Engine *e, const float *d_in, cudaEvent_t ready) {
+static int issue_prefilter(B200Engine *e, const void *d_in, cudaEvent_t ready, int s16) {
   if (e->bq_frames >= e->frames + 2) return -1;
   const long long f = e->bq_frames;
   const int slot = (int)(f & 1);
   if (ready) CK(cudaStreamWaitEvent(e->s_bq, ready, 0));
   CK(cudaStreamWaitEvent(e->s_bq, e->ev_ana[slot], 0));       // frame f-2 no longer reads this xb half
   CK(cudaStreamWaitEvent(e->s_bq, e->ev_bq[slot ^ 1], 0));    // biquad state: after frame f-1's filter
-  k_biquad<<<(e->a.S + 31) / 32, 32, 0, e->s_bq>>>(e->a, d_in, (int)(f & 0x3fffffff));
+  k_biquad<<<(e->a.S + 31) / 32, 32, 0, e->s_bq>>>(e->a, d_in, (int)(f & 0x3fffffff), s16);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev_bq[slot], e->s_bq));
   e->bq_frames = f + 1;
@@ -545,24 +559,24 @@ static int issue_prefilter(B200Engine *e, const float *d_in, cudaEvent_t ready) 
 extern "C" int b200_engine_prefilter_device(B200Engine *e, const float *d_in) {
   if (!e || !d_in) return -1;
   CK(cudaSetDevice(e->device));
-  return issue_prefilter(e, d_in, nullptr);
+  return issue_prefilter(e, d_in, nullptr, 0);
 }
 
-extern "C" int b200_engine_frame_host_async(B200Engine *e, float *out, const float *in, float *vad) {
+static int frame_host_async_io(B200Engine *e, void *out, const void *in, float *vad, int s16) {
   if (!e || !out || !in) return -1;
   if (e->bq_frames != e->frames) return -1;   // a device-side prefilter hint is pending: do not mix
   CK(cudaSetDevice(e->device));
-  const size_t n = (size_t)e->a.S * FRAME_SIZE * sizeof(float);
+  const size_t n = (size_t)e->a.S * FRAME_SIZE * (s16 ? sizeof(short) : sizeof(float));
   const int slot = (int)(e->host_frames & 1);
   // copy-in: the staging slot is free once the prefilter of frame n-2 has consumed it
   CK(cudaStreamWaitEvent(e->s_h2d, e->ev_bq[slot], 0));
   CK(cudaMemcpyAsync(e->stage_in[slot], in, n, cudaMemcpyHostToDevice, e->s_h2d));
   CK(cudaEventRecord(e->ev_h2d[slot], e->s_h2d));
   // high-pass prefilter on its own stream: overlaps the previous frame's kernels
-  if (issue_prefilter(e, e->stage_in[slot], e->ev_h2d[slot])) return -1;
+  if (issue_prefilter(e, e->stage_in[slot], e->ev_h2d[slot], s16)) return -1;
   // rest of the frame: needs frame n-2's output staging drained
   CK(cudaStreamWaitEvent(e->stream, e->ev_d2h[slot], 0));
-  if (b200_engine_frame_device(e, e->stage_out[slot], e->stage_in[slot], e->stage_vad[slot])) return -1;
+  if (frame_device_io(e, e->stage_out[slot], e->stage_in[slot], e->stage_vad[slot], s16)) return -1;
   CK(cudaEventRecord(e->ev_comp[slot], e->stream));
   // copy-out
   CK(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[slot], 0));
@@ -571,6 +585,12 @@ extern "C" int b200_engine_frame_host_async(B200Engine *e, float *out, const flo
   CK(cudaEventRecord(e->ev_d2h[slot], e->s_d2h));
   e->host_frames++;
   return 0;
+}
+extern "C" int b200_engine_frame_host_async(B200Engine *e, float *out, const float *in, float *vad) {
+  return frame_host_async_io(e, out, in, vad, 0);
+}
+extern "C" int b200_engine_frame_host_async_s16(B200Engine *e, short *out, const short *in, float *vad) {
+  return frame_host_async_io(e, out, in, vad, 1);
 }
 
 extern "C" int b200_engine_frame_host(B200Engine *e, float *out, const float *in, float *vad) {

@@ -20,6 +20,8 @@ int b200_engine_frame_device(B200Engine *e, float *d_out, const float *d_in, flo
 /* One frame, host pointers (copies in, runs, copies out, synchronises). */
 int b200_engine_frame_host(B200Engine *e, float *out, const float *in, float *vad);
 int b200_engine_frame_host_async(B200Engine *e, float *out, const float *in, float *vad);
+int b200_engine_frame_device_s16(B200Engine *e, short *d_out, const short *d_in, float *d_vad);
+int b200_engine_frame_host_async_s16(B200Engine *e, short *out, const short *in, float *vad);
 int b200_engine_prefilter_device(B200Engine *e, const float *d_in);
 int b200_engine_sync(B200Engine *e);
 int b200_engine_set_stream(B200Engine *e, void *cuda_stream);

@@ -130,6 +130,19 @@ int rnnoise_process_frame_batch_device(RNNoiseBatch *b, float *d_out, const floa
   return b200_engine_frame_device(b->engine, d_out, d_in, d_vad);
 }
 
+int rnnoise_process_frame_batch_s16(RNNoiseBatch *b, short *out, const short *in, float *vad) {
+  if (!b || !out || !in) return -1;
+  if (b200_engine_frame_host_async_s16(b->engine, out, in, vad) != 0) return -1;
+  return b200_engine_sync(b->engine);
+}
+int rnnoise_process_frame_batch_s16_async(RNNoiseBatch *b, short *out, const short *in, float *vad) {
+  if (!b || !out || !in) return -1;
+  return b200_engine_frame_host_async_s16(b->engine, out, in, vad);
+}
+int rnnoise_process_frame_batch_device_s16(RNNoiseBatch *b, short *d_out, const short *d_in, float *d_vad) {
+  if (!b || !d_out || !d_in) return -1;
+  return b200_engine_frame_device_s16(b->engine, d_out, d_in, d_vad);
+}
 int rnnoise_batch_prefilter_device(RNNoiseBatch *b, const float *d_in_next) {
   return b && d_in_next ? b200_engine_prefilter_device(b->engine, d_in_next) : -1;
 }

@@ -95,6 +95,7 @@ void emu_synthesis(void *p, int q, const float *gains, float *out, float *lastg)
   a.lastg = s.lastg;
   a.synthesis_mem = s.synth_mem;
   a.out = out;
+  a.out_s16 = nullptr;
   synthesis_stream(e->sm, a, &e->T);
   memcpy(lastg, s.lastg, sizeof(s.lastg));
 }

@@ -300,3 +300,17 @@ def test_two_stream_overlap_is_race_free(rb, models_dir):
     for f in range(frames):
         assert torch.equal(oa[f], ob[f]) and torch.equal(va[f], vb[f]), f
     a.destroy(); b.destroy(); model.free()
+
+
+def test_int16_pcm_io_matches_demo_semantics(rb, models_dir):
+    """rnnoise_process_frame_batch_s16: int16 in (widened exactly) / int16 out (C cast of the float result,
+    examples/rnnoise_demo.c:56-58) must equal the float API followed by that cast."""
+    model = rb.Model(os.path.join(models_dir, "default.bin"))
+    S, frames = 130, 12
+    a, b = rb.Batch(model, S), rb.Batch(model, S)
+    pcm = batch_pcm(S, frames)                     # integer-valued floats in int16 range
+    for f in range(frames):
+        of, vf = a.process(pcm[f])
+        o16, v16 = b.process_s16(pcm[f].astype(np.int16))
+        assert np.array_equal(o16, of.astype(np.int32).astype(np.int16)) and np.array_equal(bits(vf), bits(v16)), f
+    a.destroy(); b.destroy(); model.free()
