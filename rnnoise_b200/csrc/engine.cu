@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTab
                                                            void *__restrict__ out, int f, int out_s16) {
   extern __shared__ float sm[];
   const int s = blockIdx.x;
+  pdl_wait();   // gains of this frame (k_heads)
   const int par = f & 1, slot = f % 3, dslot = (f + 2) % 3;   // dslot = (f - 1) mod 3
   SynthesisArgs g;
   g.spec_delayed = a.spec + ((size_t)dslot * a.S + s) * (4 * FREQ_SIZE);
@@ -177,6 +178,7 @@ struct B200Engine {
   cudaEvent_t ev_in;                 // input readiness on the caller's stream (non-prefiltered frames)
   int overlap;                       // 0: everything on one stream (RNNOISE_B200_OVERLAP=0, profiling)
   int front_ctas;                    // cap on the analysis kernels' grid (0 = one CTA per stream)
+  int pdl;                           // programmatic dependent launch along the network chain (RNNOISE_B200_PDL=0 disables)
   cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
   cudaEvent_t ev_bq[2], ev_ana[2];   // biquad of frame f done / analysis of frame f done (xb slot free)
   long long host_frames;
@@ -352,6 +354,7 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   e->ev_in = nullptr;
   const char *ov = getenv("RNNOISE_B200_OVERLAP");
   e->overlap = !(ov && !strcmp(ov, "0"));
+  { const char *pd = getenv("RNNOISE_B200_PDL"); e->pdl = !(pd && !strcmp(pd, "0")); }
   {
     // RNNOISE_B200_FRONT_CTAS_PER_SM = r caps k_pitch / k_spectrum at r resident CTAs per SM (grid-stride
     // over the streams) so they share each SM with the previous frame's network kernels; 0 = no cap
@@ -433,6 +436,18 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   return e;
 }
 
+// Launch with (or without) the programmatic-dependent-launch attribute (see rnn_kernels.cuh).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 extern "C" int b200_engine_streams(const B200Engine *e) { return e ? e->a.S : 0; }
 extern "C" int b200_engine_launches_per_frame(const B200Engine *) { return NKERNELS; }
 
@@ -498,9 +513,10 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   const int gts = (S + RNN_TS - 1) / RNN_TS;
   k_conv1<<<gts, 128, 0, st>>>(S, e->dm, feat, a.conv1_state, sil, a.c2in);
   MARK();
+  const bool pdl = e->pdl && !e->profiling;
   if (e->conv2_tc)
-    k_tc2<false><<<dim3((S + TC_M - 1) / TC_M, 4), P_THREADS, tc2_smem_bytes<false>(3 * cond, gru), st>>>(
-        S, 3 * cond, gru, e->conv_maps, e->dm.conv2, e->dm.conv2, nullptr, a.conv2_out, a.conv2_out_u8, sil);
+    CK(launch_pdl(k_tc2<false>, dim3((S + TC_M - 1) / TC_M, 4), dim3(P_THREADS), tc2_smem_bytes<false>(3 * cond, gru), st, pdl,
+                  S, 3 * cond, gru, e->conv_maps, e->dm.conv2, e->dm.conv2, (const float *)nullptr, a.conv2_out, a.conv2_out_u8, sil));
   else
     k_conv2<<<gts, 128, RNN_TS * (3 * cond / 4) * sizeof(uint32_t), st>>>(S, e->dm, a.c2in, a.conv2_out, a.conv2_out_u8);
   MARK();
@@ -508,8 +524,8 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   for (int l = 0; l < 3; l++) {
     uint8_t *hu8_new = a.hbuf_u8 + ((size_t)par * 3 + l) * hstride;
     if (e->use_tc == 2) {
-      k_tc2<true><<<dim3((S + TC_M - 1) / TC_M, 4), P_THREADS, tc2_smem_bytes<true>(gru, gru), st>>>(
-          S, gru, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, sil);
+      CK(launch_pdl(k_tc2<true>, dim3((S + TC_M - 1) / TC_M, 4), dim3(P_THREADS), tc2_smem_bytes<true>(gru, gru), st, pdl,
+                    S, gru, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], (const float *)h_old[l], h_new[l], hu8_new, sil));
     } else if (e->use_tc == 1) {
       k_gru_tc<<<dim3((S + TC_M - 1) / TC_M, gru / TC_UNITS), 160, gru_tc_smem_bytes(gru), st>>>(
           S, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, sil);
@@ -519,10 +535,11 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
     }
     MARK();
   }
-  k_heads<<<(S + HEAD_TS - 1) / HEAD_TS, 160, 0, st>>>(S, e->dm, a.conv2_out, h_new[0], h_new[1], h_new[2], sil,
-                                                      a.gains, a.vad, d_vad);
+  const bool pdl_heads = pdl && e->use_tc == 2;   // only the k_tc2 predecessors are PDL-aware
+  CK(launch_pdl(k_heads, dim3((S + HEAD_TS - 1) / HEAD_TS), dim3(160), 0, st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
+                (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad));
   MARK();
-  k_synthesis<<<S, DSP_THREADS, SS_TOTAL * sizeof(float), st>>>(a, e->d_tables, d_out, fr, s16);
+  CK(launch_pdl(k_synthesis, dim3(S), dim3(DSP_THREADS), SS_TOTAL * sizeof(float), st, pdl_heads, a, (const DspTables *)e->d_tables, d_out, fr, s16));
   CK(cudaEventRecord(e->ev_back[par], st));
   MARK();
 #undef MARK

@@ -306,6 +306,7 @@ k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi,
   auto bar_tfull = [&](int i) { return smem_u32(&bars[7 + i]); };
   auto bar_tempty = [&](int i) { return smem_u32(&bars[9 + i]); };
 
+  pdl_trigger();
   if (tid == 0) {
     mbar_init(bar_a, 1);
     for (int i = 0; i < P_STAGES; i++) { mbar_init(bar_bfull(i), 1); mbar_init(bar_bempty(i), 1); }
@@ -349,12 +350,13 @@ k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi,
           if (kGru) tma_load_2d(smem_u32(dst + (natoms + a) * C::kBAtom), &maps.wr, bar_bfull(st), a * TC_KATOM, row);
         }
       };
+      for (int s = 0; s < P_STAGES && s < nslice; s++) load_B(s);   // weights: independent of the previous kernel
+      pdl_wait();                                                   // activations of this frame are complete
       mbar_expect_tx(bar_a, (uint32_t)(C::kMats * natoms * TC_A_ATOM_BYTES));
       for (int a = 0; a < natoms; a++) {
         tma_load_2d(smem_u32(sAx + a * TC_A_ATOM_BYTES), &maps.x, bar_a, a * TC_KATOM, m0);
         if (kGru) tma_load_2d(smem_u32(sAh + a * TC_A_ATOM_BYTES), &maps.h, bar_a, a * TC_KATOM, m0);
       }
-      for (int s = 0; s < P_STAGES && s < nslice; s++) load_B(s);
       mbar_wait(bar_a, 0);
       const uint32_t idesc = umma_idesc_i8(TC_M, C::kN);
       for (int s = 0; s < nslice; s++) {

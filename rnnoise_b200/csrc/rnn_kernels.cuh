@@ -58,6 +58,14 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src, bool vali
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
 }
 
+// Programmatic dependent launch (PDL): the network kernels of one frame form a chain on one stream.
+// pdl_trigger() lets the next kernel's CTAs be scheduled as soon as SM resources free up (its prologue
+// -- barrier init, TMEM allocation, weight prefetch -- overlaps this kernel's tail); pdl_wait() in the
+// dependent blocks until the previous grid has completed and flushed, before any of its results is read.
+// Both are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Device-resident model (built by engine.cu from the parsed blob).
 struct DevLayerF { const float *w, *bias; };                               // w[in][out]
 struct DevLayerQ { const int *wp; const float *scale, *subias, *diag; };   // wp[in/4][out] packed s8x4
@@ -83,6 +91,7 @@ __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *_
   __shared__ __align__(16) float wsm[2][C1_KC][128];   // weight chunks, double-buffered (cond <= 128)
   __shared__ uint32_t rot[RNN_TS][64];                  // 2*cond/4 words per stream
   const int s0 = blockIdx.x * RNN_TS, tid = threadIdx.x, W = m.cond / 4, cond = m.cond;
+  pdl_trigger();
   constexpr int KIN = 3 * NB_FEAT, NCH = (KIN + C1_KC - 1) / C1_KC;
   auto stage = [&](int c, int buf) {
     const int j0 = c * C1_KC, rows = min(C1_KC, KIN - j0);
@@ -286,6 +295,8 @@ __global__ void __launch_bounds__(160) k_heads(int S, DevModel m, const float *_
   __shared__ __align__(16) float wv[2][HEAD_KC];
   const int s0 = blockIdx.x * HEAD_TS, tid = threadIdx.x, gru = m.gru, K = 4 * gru, nchunk = K / HEAD_KC;
   const int o = tid & 31, sg = tid >> 5;
+  pdl_trigger();
+  pdl_wait();   // GRU-3 state of this frame
   auto stage = [&](int c, int buf) {   // gru % 64 == 0: a chunk never straddles two source arrays
     const int c0 = c * HEAD_KC, src = c0 / gru, off = c0 % gru;
     const float *p = src == 0 ? c2 : src == 1 ? g1 : src == 2 ? g2 : g3;
