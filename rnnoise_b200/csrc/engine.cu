@@ -100,9 +100,19 @@ __global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__
 __global__ void __launch_bounds__(PITCH_NS *DSP_THREADS, PITCH_MIN_CTAS)
 k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
   extern __shared__ float sm[];
-  __shared__ PitchArgs pa[PITCH_NS];
   // grid-stride over stream groups: the grid may be capped (engine: front_ctas) so that the analysis
   // front leaves SM resources to the network kernels of the previous frame running concurrently
+#if PITCH_NS == 1
+  for (int s = blockIdx.x; s < a.S; s += gridDim.x) {
+    PitchArgs g;   // in registers: pointers keep their (global) address space
+    g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+    g.xb = a.xb + ((size_t)(f & 1) * a.S + s) * FRAME_SIZE;
+    g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
+    g.pitch_state = a.pitch_state + 2 * (size_t)s;
+    pitch_streams(sm, &g, T);   // ends with a barrier
+  }
+#else
+  __shared__ PitchArgs pa[PITCH_NS];
   for (int grp = blockIdx.x; grp * PITCH_NS < a.S; grp += gridDim.x) {
     if (threadIdx.x < PITCH_NS) {
       const int s = grp * PITCH_NS + threadIdx.x;
@@ -119,6 +129,7 @@ k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
     __syncthreads();
     pitch_streams(sm, pa, T);   // ends with a barrier
   }
+#endif
 }
 
 #ifndef SPEC_MIN_BLOCKS

@@ -108,8 +108,9 @@ k_gru_tc(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, D
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * TC_M, j0 = blockIdx.y * TC_UNITS, natoms = gru / TC_KATOM;
-  // 1024-byte aligned operand area (SWIZZLE_128B requirement)
-  uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte aligned operand area (SWIZZLE_128B requirement); plain pointer arithmetic on the shared
+  // array keeps the address space known to the compiler (LDS/STS instead of generic loads)
+  uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t *sAx = base, *sAh = sAx + natoms * TC_A_ATOM_BYTES;
   uint8_t *sBi = sAh + natoms * TC_A_ATOM_BYTES, *sBr = sBi + natoms * TC_B_ATOM_BYTES;
   float *prm = (float *)(sBr + natoms * TC_B_ATOM_BYTES);       // [15][32]
@@ -293,7 +294,9 @@ k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int natoms = K / TC_KATOM, upc = N / 4, nslice = upc / P_SLICE;   // units / slices per CTA
   const int m0 = blockIdx.x * TC_M, jq = blockIdx.y * upc;
-  uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte aligned operand area; pointer arithmetic on the shared array keeps the address space
+  // known to the compiler (LDS instead of generic loads for the epilogue parameters)
+  uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t *sAx = base, *sAh = sAx + natoms * TC_A_ATOM_BYTES;
   uint8_t *sB = sAx + C::kMats * natoms * TC_A_ATOM_BYTES;
   const int stage_bytes = C::kMats * natoms * C::kBAtom;
