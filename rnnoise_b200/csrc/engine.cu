@@ -100,20 +100,20 @@ __global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__
 __global__ void __launch_bounds__(PITCH_NS *DSP_THREADS, PITCH_MIN_CTAS)
 k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
   extern __shared__ float sm[];
-  // grid-stride over stream groups: the grid may be capped (engine: front_ctas) so that the analysis
-  // front leaves SM resources to the network kernels of the previous frame running concurrently
 #if PITCH_NS == 1
-  for (int s = blockIdx.x; s < a.S; s += gridDim.x) {
+  {
+    const int s = blockIdx.x;
     PitchArgs g;   // in registers: pointers keep their (global) address space
     g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
     g.xb = a.xb + ((size_t)(f & 1) * a.S + s) * FRAME_SIZE;
     g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
     g.pitch_state = a.pitch_state + 2 * (size_t)s;
-    pitch_streams(sm, &g, T);   // ends with a barrier
+    pitch_streams(sm, &g, T);
   }
 #else
   __shared__ PitchArgs pa[PITCH_NS];
-  for (int grp = blockIdx.x; grp * PITCH_NS < a.S; grp += gridDim.x) {
+  {
+    const int grp = blockIdx.x;
     if (threadIdx.x < PITCH_NS) {
       const int s = grp * PITCH_NS + threadIdx.x;
       PitchArgs g;
@@ -127,7 +127,7 @@ k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
       pa[threadIdx.x] = g;
     }
     __syncthreads();
-    pitch_streams(sm, pa, T);   // ends with a barrier
+    pitch_streams(sm, pa, T);
   }
 #endif
 }
@@ -138,7 +138,7 @@ k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
 __global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena a, const DspTables *__restrict__ T, int f) {
   extern __shared__ float sm[];
   const int par = f & 1, slot = f % 3;
-  for (int s = blockIdx.x; s < a.S; s += gridDim.x) {   // grid-stride, see k_pitch
+  const int s = blockIdx.x;
   SpectrumArgs g;
   g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
   g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
@@ -147,8 +147,7 @@ __global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena
   g.band_out = a.band + ((size_t)slot * a.S + s) * 96;
   g.features = a.features + ((size_t)par * a.S + s) * NB_FEATURES;
   g.silence = a.silence + (size_t)par * a.S + s;
-  spectrum_stream(sm, g, T);   // ends with a barrier
-  }
+  spectrum_stream(sm, g, T);
 }
 
 __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTables *__restrict__ T,
@@ -188,7 +187,6 @@ struct B200Engine {
   cudaEvent_t ev_front[2], ev_back[2];   // analysis of frame f done / network+synthesis of frame f done (by parity)
   cudaEvent_t ev_in;                 // input readiness on the caller's stream (non-prefiltered frames)
   int overlap;                       // 0: everything on one stream (RNNOISE_B200_OVERLAP=0, profiling)
-  int front_ctas;                    // cap on the analysis kernels' grid (0 = one CTA per stream)
   int pdl;                           // programmatic dependent launch along the network chain (RNNOISE_B200_PDL=1 enables)
   cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
   cudaEvent_t ev_bq[2], ev_ana[2];   // biquad of frame f done / analysis of frame f done (xb slot free)
@@ -369,12 +367,9 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   // kernels could use: 10.05 M frames/s without vs 9.0-9.3 M with PDL -> opt-in only
   { const char *pd = getenv("RNNOISE_B200_PDL"); e->pdl = pd && !strcmp(pd, "1"); }
   {
-    // RNNOISE_B200_FRONT_CTAS_PER_SM = r caps k_pitch / k_spectrum at r resident CTAs per SM (grid-stride
-    // over the streams) so they share each SM with the previous frame's network kernels; 0 = no cap
-    const char *fc = getenv("RNNOISE_B200_FRONT_CTAS_PER_SM");
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    e->front_ctas = fc ? atoi(fc) * sms : 0;
+    // the analysis front runs at the lowest stream priority: the network kernels of the previous frame
+    // (caller's stream) get SM slots first.  (Capping the front kernels' grid to leave room was measured
+    // and is worse than the plain one-CTA-per-stream grid: profiles/README.md.)
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = lowest priority (largest value)
     const char *pr = getenv("RNNOISE_B200_FRONT_PRIORITY");
@@ -512,12 +507,11 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   }
   MARK();
   const int pitch_grid = (S + PITCH_NS - 1) / PITCH_NS;
-  const int cap = overlap && e->front_ctas > 0 ? e->front_ctas : 0x7fffffff;
-  k_pitch<<<min(pitch_grid, cap), PITCH_NS * DSP_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
+  k_pitch<<<pitch_grid, PITCH_NS * DSP_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
   CK(cudaEventRecord(e->ev_ana[par], sf));   // xb[par] is free again
   MARK();
   if (overlap) CK(cudaStreamWaitEvent(sf, e->ev_back[par], 0));   // frame f-2 is done with slot f%3 / parity buffers
-  k_spectrum<<<min(S, cap), DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
+  k_spectrum<<<S, DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
   if (overlap) {
     CK(cudaEventRecord(e->ev_front[par], sf));
     CK(cudaStreamWaitEvent(st, e->ev_front[par], 0));
