@@ -36,7 +36,7 @@ struct SpectrumArgs {
 // streams: phases whose work is wide (decimation, FIR, the 30-lane correlations) run on the 128
 // threads of each stream's own warp quartet, while the narrow chains of ALL the CTA's streams are
 // packed side by side into the lanes of one or two warps -- same instructions, PITCH_NS x the useful
-// lanes.  Thread ids: q = tid / 128 is the stream a thread belongs to, t = tid % 128 its local id;
+// lanes.  Thread ids: q = tid / PITCH_THREADS is the stream a thread belongs to, t its local id;
 // packed phases use the first lanes of the CTA instead.
 // Measured on B200 (S = 4096): PITCH_NS = 1 -> 127 us, PITCH_NS = 4 -> 145 us: with 16 streams resident
 // per SM either way, packing removes instructions but also leaves fewer warps runnable during the
@@ -45,11 +45,18 @@ struct SpectrumArgs {
 #ifndef PITCH_NS
 #define PITCH_NS 1
 #endif
+// Threads per stream in the pitch kernel.  The chains keep one warp busy per stream, so more resident
+// streams per SM hide more latency: 96 threads (3 warps) x 20 streams fill an SM's 2048 thread slots
+// and its shared memory (20 x 11.3 KB), against 16 streams with 128 threads.
+#ifndef PITCH_THREADS
+#define PITCH_THREADS 96
+#endif
+static_assert(PITCH_THREADS >= 96 && PITCH_THREADS % 32 == 0, "phases use local thread ids up to 64 + PITCH_NS");
 #if defined(__CUDA_ARCH__)
-#define MPHASE_BEGIN { const int tid = threadIdx.x; const int q = tid >> 7, t = tid & 127; (void)q; (void)t;
+#define MPHASE_BEGIN { const int tid = threadIdx.x; const int q = tid / PITCH_THREADS, t = tid % PITCH_THREADS; (void)q; (void)t;
 #define MPHASE_END } __syncthreads();
 #else
-#define MPHASE_BEGIN for (int tid = 0; tid < PITCH_NS * DSP_THREADS; ++tid) { const int q = tid >> 7, t = tid & 127; (void)q; (void)t;
+#define MPHASE_BEGIN for (int tid = 0; tid < PITCH_NS * PITCH_THREADS; ++tid) { const int q = tid / PITCH_THREADS, t = tid % PITCH_THREADS; (void)q; (void)t;
 #define MPHASE_END }
 #endif
 #define PSM(qq) (sm + (qq) * SM_PITCH_TOTAL)
@@ -65,11 +72,11 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
       const PitchArgs A = a[q];
       float *lp0 = PSM(q) + SM_LP0;
       const int H = PITCH_BUF_SIZE - FRAME_SIZE;
-      for (int j = t; j < FRAME_SIZE; j += DSP_THREADS) {
+      for (int j = t; j < FRAME_SIZE; j += PITCH_THREADS) {
         int p = A.ring_base + H + j; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
         A.ring[p] = A.xb[j];
       }
-      for (int i = t; i < LP_SIZE; i += DSP_THREADS) {
+      for (int i = t; i < LP_SIZE; i += PITCH_THREADS) {
         const int k = 2 * i;
         // sample k of the updated history: old ring part for k < 1248, this frame after that
         const float c = k < H ? ring_at(A.ring, A.ring_base, k) : A.xb[k - H];
@@ -105,7 +112,7 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
     if (a[q].ring) {
       const float *lp0 = PSM(q) + SM_LP0, *num = PSM(q) + SM_PITCH_END + MI_NUM;
       float *lp = PSM(q) + SM_LP;
-      for (int i = t; i < LP_SIZE; i += DSP_THREADS) {
+      for (int i = t; i < LP_SIZE; i += PITCH_THREADS) {
         float sum = lp0[i];
 #pragma unroll
         for (int k = 0; k < 5; k++) {
@@ -122,9 +129,9 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
     if (a[q].ring) {
       const float *lp = PSM(q) + SM_LP;
       float *x4 = PSM(q) + SM_X4, *y4 = PSM(q) + SM_Y4, *syy = PSM(q) + SM_SYY;
-      for (int j = t; j < 240; j += DSP_THREADS) x4[j] = lp[384 + 2 * j];
-      for (int j = t; j < 388; j += DSP_THREADS) y4[j] = j < 387 ? lp[2 * j] : 0.f;
-      for (int i = t; i < 147; i += DSP_THREADS) {
+      for (int j = t; j < 240; j += PITCH_THREADS) x4[j] = lp[384 + 2 * j];
+      for (int j = t; j < 388; j += PITCH_THREADS) y4[j] = j < 387 ? lp[2 * j] : 0.f;
+      for (int i = t; i < 147; i += PITCH_THREADS) {
         float hi = lp[2 * (i + 240)], lo = lp[2 * i];
         syy[i] = hi * hi - lo * lo;
       }
@@ -173,7 +180,7 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
     if (a[q].ring) {
       const float *lp = PSM(q) + SM_LP;
       float *xc = PSM(q) + SM_XC, *syy = PSM(q) + SM_SYY;
-      for (int i = t; i < 294; i += DSP_THREADS) {
+      for (int i = t; i < 294; i += PITCH_THREADS) {
         xc[i] = 0.f;
         float hi = lp[i + 480], lo = lp[i];
         syy[i] = hi * hi - lo * lo;
@@ -231,7 +238,7 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
     if (t >= 32 && a[q].ring) {
       float *sq = PSM(q);
       const float *x = sq + SM_LP + PITCH_MAX_PERIOD / 2;
-      for (int i = 1 + (t - 32); i <= PITCH_MAX_PERIOD / 2; i += DSP_THREADS - 32) {
+      for (int i = 1 + (t - 32); i <= PITCH_MAX_PERIOD / 2; i += PITCH_THREADS - 32) {
         float u = x[-i], v = x[PITCH_FRAME_SIZE / 2 - i];
         sq[SM_X4 + i - 1] = u * u;   // x4/y4 are dead after the coarse search: 384 floats fit in their 628
         sq[SM_YYL + i] = v * v;

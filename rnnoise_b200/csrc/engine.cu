@@ -93,11 +93,11 @@ __global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__
   if (s < a.S) { a.hp_mem[2 * s] = m0; a.hp_mem[2 * s + 1] = m1; }
 }
 
-// grid = ceil(S / PITCH_NS), block = PITCH_NS * 128, dynamic smem = PITCH_NS * SM_PITCH_TOTAL floats
+// grid = ceil(S / PITCH_NS), block = PITCH_NS * PITCH_THREADS, dynamic smem = PITCH_NS * SM_PITCH_TOTAL floats
 #ifndef PITCH_MIN_CTAS
-#define PITCH_MIN_CTAS (2048 / (PITCH_NS * DSP_THREADS))   // 32 registers/thread: 16 streams resident per SM
+#define PITCH_MIN_CTAS (2048 / (PITCH_NS * PITCH_THREADS) < 20 ? 2048 / (PITCH_NS * PITCH_THREADS) : 20)   // 32 regs/thread
 #endif
-__global__ void __launch_bounds__(PITCH_NS *DSP_THREADS, PITCH_MIN_CTAS)
+__global__ void __launch_bounds__(PITCH_NS *PITCH_THREADS, PITCH_MIN_CTAS)
 k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
   extern __shared__ float sm[];
 #if PITCH_NS == 1
@@ -507,7 +507,7 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   }
   MARK();
   const int pitch_grid = (S + PITCH_NS - 1) / PITCH_NS;
-  k_pitch<<<pitch_grid, PITCH_NS * DSP_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
+  k_pitch<<<pitch_grid, PITCH_NS * PITCH_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
   CK(cudaEventRecord(e->ev_ana[par], sf));   // xb[par] is free again
   MARK();
   if (overlap) CK(cudaStreamWaitEvent(sf, e->ev_back[par], 0));   // frame f-2 is done with slot f%3 / parity buffers
