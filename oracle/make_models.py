@@ -17,6 +17,8 @@ Models:
   hot     : same, GRU W x3, conv W x2, head W x8                        (saturating gates)
   little  : seed 4321, same dims, densities x0.5 (README:119-125 "little" = more sparsity)
   g256    : seed 99, cond128/gru256 (dimension-generality check; compared against the port only)
+  tiny    : seed 7, cond96/gru128 (conv2 K = 288 is not a whole swizzle atom -> CUDA-core conv2);
+            its state dict is kept as tiny_ckpt.npz for the exporter test
 
 Usage: python oracle/make_models.py [names...]
 """
@@ -37,7 +39,11 @@ SPECS = {
     "little": dict(seed=4321, cond=128, gru=384, density_scale=0.5, hot=False),
     # other dimensions (the engine infers them from the blob): GRU 256 -> 2 swizzle atoms, 4 unit slices per CTA
     "g256": dict(seed=99, cond=128, gru=256, density_scale=1.0, hot=False),
+    # small dims; its checkpoint is committed too (tiny_ckpt.npz) so the blob exporter
+    # (rnnoise_b200/weights.py) can be pinned against the reference pipeline where /root/reference is absent
+    "tiny": dict(seed=7, cond=96, gru=128, density_scale=1.0, hot=False),
 }
+KEEP_CKPT = {"tiny"}
 
 
 def make_ckpt(path, seed, cond, gru, density_scale, hot):
@@ -85,6 +91,11 @@ def make(name):
         subprocess.run([exe], cwd=td, check=True)
         out = os.path.join(DST, name + ".bin")
         shutil.copyfile(os.path.join(td, "weights_blob.bin"), out)
+        if name in KEEP_CKPT:
+            import numpy as np
+            import torch
+            sd = torch.load(ck, map_location="cpu")["state_dict"]
+            np.savez(os.path.join(DST, name + "_ckpt.npz"), **{k: v.numpy() for k, v in sd.items()})
         print(name, os.path.getsize(out), "bytes ->", out)
 
 

@@ -45,7 +45,7 @@ def test_sizes(L):
 
 
 def test_model_parse_and_reject(L, models_dir):
-    for name in ("default", "hot", "little", "g256"):
+    for name in ("default", "hot", "little", "g256", "tiny"):
         m = L.rnnoise_model_from_filename(os.path.join(models_dir, name + ".bin").encode())
         assert m
         L.rnnoise_model_free(m)
