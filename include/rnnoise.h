@@ -112,6 +112,19 @@ RNNOISE_EXPORT int rnnoise_process_frame_batch_s16(RNNoiseBatch *b, short *out, 
 RNNOISE_EXPORT int rnnoise_process_frame_batch_s16_async(RNNoiseBatch *b, short *out, const short *in, float *vad);
 RNNOISE_EXPORT int rnnoise_process_frame_batch_device_s16(RNNoiseBatch *b, short *d_out, const short *d_in, float *d_vad);
 
+/** Multi-frame calls: nb_frames consecutive 10 ms frames of every stream in
+ *  one call -- offline / file denoising, where the reference loops rnnoise_process_frame over a file
+ *  (examples/rnnoise_demo.c:53-64).  Each stream's audio is contiguous: in/out are
+ *  [nb_streams][nb_frames * 480] samples, vad is [nb_streams][nb_frames] (may be NULL).  out may alias
+ *  in.  The result is bit-identical to nb_frames frame-at-a-time calls.  Host forms block until out/vad
+ *  are complete; they move the audio in chunks ($RNNOISE_B200_MULTI_CHUNK frames, default 16) through
+ *  double-buffered device staging so copies overlap the kernels (pinned host memory recommended).
+ *  The _device form takes device pointers, enqueues on the batch's stream and returns. */
+RNNOISE_EXPORT int rnnoise_process_frames_batch(RNNoiseBatch *b, float *out, const float *in, float *vad, int nb_frames);
+RNNOISE_EXPORT int rnnoise_process_frames_batch_s16(RNNoiseBatch *b, short *out, const short *in, float *vad, int nb_frames);
+RNNOISE_EXPORT int rnnoise_process_frames_batch_device(RNNoiseBatch *b, float *d_out, const float *d_in, float *d_vad, int nb_frames);
+RNNOISE_EXPORT int rnnoise_process_frames_batch_device_s16(RNNoiseBatch *b, short *d_out, const short *d_in, float *d_vad, int nb_frames);
+
 /** Device-buffer call: d_in/d_out/d_vad are device pointers on the batch's device (d_out may alias
  *  d_in; d_vad may be NULL).  Enqueues the frame on the batch's stream and returns without
  *  synchronising.  0 on success, -1 on a launch error. */

@@ -52,6 +52,9 @@ def lib():
         L.rnnoise_process_frame_batch_async.restype = ip; L.rnnoise_process_frame_batch_async.argtypes = [vp, vp, vp, vp]
         for nm in ("rnnoise_process_frame_batch_s16", "rnnoise_process_frame_batch_s16_async", "rnnoise_process_frame_batch_device_s16"):
             getattr(L, nm).restype = ip; getattr(L, nm).argtypes = [vp, vp, vp, vp]
+        for nm in ("rnnoise_process_frames_batch", "rnnoise_process_frames_batch_s16", "rnnoise_process_frames_batch_device",
+                   "rnnoise_process_frames_batch_device_s16"):
+            getattr(L, nm).restype = ip; getattr(L, nm).argtypes = [vp, vp, vp, vp, ip]
         L.rnnoise_process_frame_batch_device.restype = ip; L.rnnoise_process_frame_batch_device.argtypes = [vp, vp, vp, vp]
         L.rnnoise_batch_prefilter_device.restype = ip; L.rnnoise_batch_prefilter_device.argtypes = [vp, vp]
         L.rnnoise_batch_sync.restype = ip; L.rnnoise_batch_sync.argtypes = [vp]
@@ -121,6 +124,26 @@ class Batch:
         if lib().rnnoise_process_frame_batch_s16(self.handle, out.ctypes.data, x.ctypes.data, vad.ctypes.data) != 0:
             raise RuntimeError("rnnoise_process_frame_batch_s16 failed")
         return out, vad
+
+    def process_frames(self, pcm):
+        """Multi-frame call: pcm [nb_streams][T * 480] float32 or int16 host array (each stream's audio
+        contiguous) -> (out, same shape and dtype; vad float32 [nb_streams][T])."""
+        s16 = np.asarray(pcm).dtype == np.int16
+        x = np.ascontiguousarray(pcm, np.int16 if s16 else np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.nb_streams and x.shape[1] % FRAME_SIZE == 0 and x.shape[1] > 0
+        T = x.shape[1] // FRAME_SIZE
+        out = np.empty_like(x)
+        vad = np.empty((self.nb_streams, T), np.float32)
+        fn = lib().rnnoise_process_frames_batch_s16 if s16 else lib().rnnoise_process_frames_batch
+        if fn(self.handle, out.ctypes.data, x.ctypes.data, vad.ctypes.data, T) != 0:
+            raise RuntimeError("rnnoise_process_frames_batch failed")
+        return out, vad
+
+    def process_frames_device(self, d_out, d_in, d_vad, nb_frames, s16=False):
+        """Device pointers (ints) to [nb_streams][nb_frames * 480] buffers; asynchronous."""
+        fn = lib().rnnoise_process_frames_batch_device_s16 if s16 else lib().rnnoise_process_frames_batch_device
+        if fn(self.handle, d_out, d_in, d_vad, nb_frames) != 0:
+            raise RuntimeError("rnnoise_process_frames_batch_device failed")
 
     def process_ptr_s16_async(self, out_ptr, in_ptr, vad_ptr=None):
         if lib().rnnoise_process_frame_batch_s16_async(self.handle, out_ptr, in_ptr, vad_ptr) != 0:

@@ -66,8 +66,10 @@ struct Arena {
 // High-pass biquad (rnn_biquad, denoise.c:409-419): strictly serial per stream (each step rounds
 // the state to float), so one THREAD owns one stream; a warp transposes 32x32 tiles through shared
 // memory so that global traffic stays coalesced.  grid = ceil(S/32), block = 32.
-// `in` is float PCM, or 16-bit PCM when in_s16 != 0 (widened exactly like examples/rnnoise_demo.c:56).
-__global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__ in_, int frame, int in_s16) {
+// `in` is float PCM, or 16-bit PCM when in_s16 != 0 (widened exactly like examples/rnnoise_demo.c:56);
+// stream s starts at element s * stride (FRAME_SIZE for frame-at-a-time calls, T * FRAME_SIZE inside
+// a multi-frame call whose buffers hold each stream's audio contiguously).
+__global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__ in_, int frame, int in_s16, int stride) {
   const float *in = (const float *)in_;
   const short *in16 = (const short *)in_;
   __shared__ float tile[32][33];
@@ -78,9 +80,9 @@ __global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__
   const int rows = min(32, a.S - s0);
   for (int c = 0; c < FRAME_SIZE / 32; c++) {
     if (in_s16)
-      for (int r = 0; r < rows; r++) tile[r][lane] = (float)in16[(size_t)(s0 + r) * FRAME_SIZE + c * 32 + lane];
+      for (int r = 0; r < rows; r++) tile[r][lane] = (float)in16[(size_t)(s0 + r) * stride + c * 32 + lane];
     else
-      for (int r = 0; r < rows; r++) tile[r][lane] = in[(size_t)(s0 + r) * FRAME_SIZE + c * 32 + lane];
+      for (int r = 0; r < rows; r++) tile[r][lane] = in[(size_t)(s0 + r) * stride + c * 32 + lane];
     __syncwarp();
     if (s < a.S) {
 #pragma unroll 4
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena
 }
 
 __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTables *__restrict__ T,
-                                                           void *__restrict__ out, int f, int out_s16) {
+                                                           void *__restrict__ out, int f, int out_s16, int stride) {
   extern __shared__ float sm[];
   const int s = blockIdx.x;
   pdl_wait();   // gains of this frame (k_heads)
@@ -164,8 +166,8 @@ __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTab
   g.silence = a.silence + (size_t)par * a.S + s;
   g.lastg = a.lastg + (size_t)s * NB_BANDS;
   g.synthesis_mem = a.synth_mem + (size_t)s * FRAME_SIZE;
-  g.out = out_s16 ? nullptr : (float *)out + (size_t)s * FRAME_SIZE;
-  g.out_s16 = out_s16 ? (short *)out + (size_t)s * FRAME_SIZE : nullptr;
+  g.out = out_s16 ? nullptr : (float *)out + (size_t)s * stride;
+  g.out_s16 = out_s16 ? (short *)out + (size_t)s * stride : nullptr;
   synthesis_stream(sm, g, T);
 }
 
@@ -186,6 +188,13 @@ struct B200Engine {
   cudaStream_t s_front;              // k_pitch/k_spectrum of frame f+1 overlap network + synthesis of frame f
   cudaEvent_t ev_front[2], ev_back[2];   // analysis of frame f done / network+synthesis of frame f done (by parity)
   cudaEvent_t ev_in;                 // input readiness on the caller's stream (non-prefiltered frames)
+  int io_stride, vad_stride;         // element strides between streams in the caller's PCM / VAD buffers
+  // multi-frame host calls: double-buffered chunk staging ([S][chunk*480] in, out; [S][chunk] vad)
+  void *multi_in[2], *multi_out[2];
+  float *multi_vad[2];
+  int multi_chunk;                   // frames per staged chunk (RNNOISE_B200_MULTI_CHUNK, default 16)
+  size_t multi_bytes;                // bytes allocated per PCM staging buffer
+  cudaEvent_t ev_mh2d[2], ev_mcomp[2], ev_md2h[2];
   int overlap;                       // 0: everything on one stream (RNNOISE_B200_OVERLAP=0, profiling)
   int pdl;                           // programmatic dependent launch along the network chain (RNNOISE_B200_PDL=1 enables)
   cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
@@ -308,6 +317,10 @@ extern "C" void b200_engine_destroy(B200Engine *e) {
     if (e->ev_ana[i]) cudaEventDestroy(e->ev_ana[i]);
     if (e->ev_front[i]) cudaEventDestroy(e->ev_front[i]);
     if (e->ev_back[i]) cudaEventDestroy(e->ev_back[i]);
+    if (e->ev_mh2d[i]) cudaEventDestroy(e->ev_mh2d[i]);
+    if (e->ev_mcomp[i]) cudaEventDestroy(e->ev_mcomp[i]);
+    if (e->ev_md2h[i]) cudaEventDestroy(e->ev_md2h[i]);
+    cudaFree(e->multi_in[i]); cudaFree(e->multi_out[i]); cudaFree(e->multi_vad[i]);
   }
   for (void *p : e->allocs) cudaFree(p);
   delete e;
@@ -359,6 +372,17 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   ok &= !!(a.vad = dalloc<float>(e, Ss));
   e->host_frames = 0;
   e->bq_frames = 0;
+  e->io_stride = FRAME_SIZE;
+  e->vad_stride = 1;
+  e->multi_bytes = 0;
+  {
+    const char *mc = getenv("RNNOISE_B200_MULTI_CHUNK");
+    e->multi_chunk = mc && atoi(mc) > 0 ? atoi(mc) : 16;
+  }
+  for (int i = 0; i < 2; i++) {
+    e->multi_in[i] = e->multi_out[i] = nullptr; e->multi_vad[i] = nullptr;
+    e->ev_mh2d[i] = e->ev_mcomp[i] = e->ev_md2h[i] = nullptr;
+  }
   e->s_h2d = e->s_d2h = e->s_bq = e->s_front = nullptr;
   e->ev_in = nullptr;
   const char *ov = getenv("RNNOISE_B200_OVERLAP");
@@ -391,6 +415,9 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
     ok &= cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&e->ev_mh2d[i], cudaEventDisableTiming) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&e->ev_mcomp[i], cudaEventDisableTiming) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&e->ev_md2h[i], cudaEventDisableTiming) == cudaSuccess;
   }
   DspTables *ht = new DspTables();
   b200_fill_dsp_tables(ht);
@@ -501,7 +528,7 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
       CK(cudaStreamWaitEvent(sf, e->ev_in, 0));
       CK(cudaStreamWaitEvent(sf, e->ev_bq[par ^ 1], 0));   // biquad state: after frame f-1's filter
     }
-    k_biquad<<<(S + 31) / 32, 32, 0, sf>>>(a, d_in, fr, s16);
+    k_biquad<<<(S + 31) / 32, 32, 0, sf>>>(a, d_in, fr, s16, e->io_stride);
     CK(cudaEventRecord(e->ev_bq[par], sf));
     e->bq_frames = e->frames + 1;
   }
@@ -544,9 +571,9 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   }
   const bool pdl_heads = pdl && e->use_tc == 2;   // only the k_tc2 predecessors are PDL-aware
   CK(launch_pdl(k_heads, dim3((S + HEAD_TS - 1) / HEAD_TS), dim3(160), 0, st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
-                (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad));
+                (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
   MARK();
-  CK(launch_pdl(k_synthesis, dim3(S), dim3(DSP_THREADS), SS_TOTAL * sizeof(float), st, pdl_heads, a, (const DspTables *)e->d_tables, d_out, fr, s16));
+  CK(launch_pdl(k_synthesis, dim3(S), dim3(DSP_THREADS), SS_TOTAL * sizeof(float), st, pdl_heads, a, (const DspTables *)e->d_tables, d_out, fr, s16, e->io_stride));
   CK(cudaEventRecord(e->ev_back[par], st));
   MARK();
 #undef MARK
@@ -573,7 +600,7 @@ static int issue_prefilter(B200Engine *e, const void *d_in, cudaEvent_t ready, i
   if (ready) CK(cudaStreamWaitEvent(e->s_bq, ready, 0));
   CK(cudaStreamWaitEvent(e->s_bq, e->ev_ana[slot], 0));       // frame f-2 no longer reads this xb half
   CK(cudaStreamWaitEvent(e->s_bq, e->ev_bq[slot ^ 1], 0));    // biquad state: after frame f-1's filter
-  k_biquad<<<(e->a.S + 31) / 32, 32, 0, e->s_bq>>>(e->a, d_in, (int)(f & 0x3fffffff), s16);
+  k_biquad<<<(e->a.S + 31) / 32, 32, 0, e->s_bq>>>(e->a, d_in, (int)(f & 0x3fffffff), s16, e->io_stride);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev_bq[slot], e->s_bq));
   e->bq_frames = f + 1;
@@ -615,6 +642,89 @@ extern "C" int b200_engine_frame_host_async(B200Engine *e, float *out, const flo
 }
 extern "C" int b200_engine_frame_host_async_s16(B200Engine *e, short *out, const short *in, float *vad) {
   return frame_host_async_io(e, out, in, vad, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-frame calls: T consecutive frames of every stream per call.  Buffers hold
+// each stream's audio contiguously, pcm[s][t * 480 + i] and vad[s][t] -- the layout of a decoded file --
+// so the kernels index streams with a stride of T * 480 (T for vad).  Results are bit-identical to T
+// frame-at-a-time calls: the same kernels run in the same order on the same state.
+// ------------------------------------------------------------------------------------------------
+static int frames_device_io(B200Engine *e, void *d_out, const void *d_in, float *d_vad, int T, int pcm_stride,
+                            int vad_stride, int s16) {
+  if (!e || !d_out || !d_in || T < 1 || e->bq_frames != e->frames) return -1;
+  const size_t esz = s16 ? sizeof(short) : sizeof(float);
+  const char *in = (const char *)d_in;
+  char *out = (char *)d_out;
+  e->io_stride = pcm_stride;
+  e->vad_stride = vad_stride;
+  int rc = 0;
+  // the high-pass prefilter runs up to two frames ahead on its own stream (the input is all there);
+  // it is ordered after the caller's stream once, through ev_in
+  rc = cudaEventRecord(e->ev_in, e->stream) != cudaSuccess;
+  for (int t = 0; t < 2 && t < T && !rc; t++) rc = issue_prefilter(e, in + (size_t)t * FRAME_SIZE * esz, t == 0 ? e->ev_in : nullptr, s16);
+  for (int t = 0; t < T && !rc; t++) {
+    rc = frame_device_io(e, out + (size_t)t * FRAME_SIZE * esz, in + (size_t)t * FRAME_SIZE * esz, d_vad ? d_vad + t : nullptr, s16);
+    if (!rc && t + 2 < T) rc = issue_prefilter(e, in + (size_t)(t + 2) * FRAME_SIZE * esz, nullptr, s16);
+  }
+  e->io_stride = FRAME_SIZE;
+  e->vad_stride = 1;
+  return rc ? -1 : 0;
+}
+extern "C" int b200_engine_frames_device(B200Engine *e, void *d_out, const void *d_in, float *d_vad, int T, int s16) {
+  if (!e) return -1;
+  CK(cudaSetDevice(e->device));
+  return frames_device_io(e, d_out, d_in, d_vad, T, T * FRAME_SIZE, T, s16);
+}
+
+// Host buffers: the T frames move in chunks of `multi_chunk` frames through double-buffered device
+// staging ([S][chunk * 480]), strided 2-D copies on the copy streams, so H2D(c+1), kernels(c) and
+// D2H(c-1) overlap.  Blocking: returns when `out` and `vad` are complete.
+extern "C" int b200_engine_frames_host(B200Engine *e, void *out, const void *in, float *vad, int T, int s16) {
+  if (!e || !out || !in || T < 1 || e->bq_frames != e->frames) return -1;
+  CK(cudaSetDevice(e->device));
+  const size_t S = (size_t)e->a.S, esz = s16 ? sizeof(short) : sizeof(float);
+  const int C = T < e->multi_chunk ? T : e->multi_chunk;
+  const size_t need = S * C * FRAME_SIZE * sizeof(float);   // sized for float so both sample types fit
+  if (need > e->multi_bytes) {
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < 2; i++) {
+      cudaFree(e->multi_in[i]); cudaFree(e->multi_out[i]); cudaFree(e->multi_vad[i]);
+      e->multi_in[i] = e->multi_out[i] = nullptr; e->multi_vad[i] = nullptr;
+    }
+    e->multi_bytes = 0;
+    for (int i = 0; i < 2; i++) {
+      CK(cudaMalloc(&e->multi_in[i], need));
+      CK(cudaMalloc(&e->multi_out[i], need));
+      CK(cudaMalloc(&e->multi_vad[i], S * C * sizeof(float)));
+    }
+    e->multi_bytes = need;
+  }
+  const size_t host_pitch = (size_t)T * FRAME_SIZE * esz;
+  int c = 0;
+  for (int t0 = 0; t0 < T; t0 += C, c++) {
+    const int n = T - t0 < C ? T - t0 : C, slot = c & 1;
+    const size_t dev_pitch = (size_t)n * FRAME_SIZE * esz;
+    // copy-in once chunk c-2's kernels have read this slot
+    CK(cudaStreamWaitEvent(e->s_h2d, e->ev_mcomp[slot], 0));
+    CK(cudaMemcpy2DAsync(e->multi_in[slot], dev_pitch, (const char *)in + (size_t)t0 * FRAME_SIZE * esz, host_pitch,
+                         dev_pitch, S, cudaMemcpyHostToDevice, e->s_h2d));
+    CK(cudaEventRecord(e->ev_mh2d[slot], e->s_h2d));
+    // kernels: after the copy-in, and after chunk c-2's copy-out has drained the output slot
+    CK(cudaStreamWaitEvent(e->stream, e->ev_mh2d[slot], 0));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_md2h[slot], 0));
+    if (frames_device_io(e, e->multi_out[slot], e->multi_in[slot], e->multi_vad[slot], n, n * FRAME_SIZE, n, s16)) return -1;
+    CK(cudaEventRecord(e->ev_mcomp[slot], e->stream));
+    // copy-out
+    CK(cudaStreamWaitEvent(e->s_d2h, e->ev_mcomp[slot], 0));
+    CK(cudaMemcpy2DAsync((char *)out + (size_t)t0 * FRAME_SIZE * esz, host_pitch, e->multi_out[slot], dev_pitch,
+                         dev_pitch, S, cudaMemcpyDeviceToHost, e->s_d2h));
+    if (vad)
+      CK(cudaMemcpy2DAsync(vad + t0, (size_t)T * sizeof(float), e->multi_vad[slot], (size_t)n * sizeof(float),
+                           (size_t)n * sizeof(float), S, cudaMemcpyDeviceToHost, e->s_d2h));
+    CK(cudaEventRecord(e->ev_md2h[slot], e->s_d2h));
+  }
+  return b200_engine_sync(e);
 }
 
 extern "C" int b200_engine_frame_host(B200Engine *e, float *out, const float *in, float *vad) {

@@ -22,6 +22,9 @@ int b200_engine_frame_host(B200Engine *e, float *out, const float *in, float *va
 int b200_engine_frame_host_async(B200Engine *e, float *out, const float *in, float *vad);
 int b200_engine_frame_device_s16(B200Engine *e, short *d_out, const short *d_in, float *d_vad);
 int b200_engine_frame_host_async_s16(B200Engine *e, short *out, const short *in, float *vad);
+/* T frames per stream in one call; buffers are [nb_streams][T * 480] (vad [nb_streams][T]). */
+int b200_engine_frames_device(B200Engine *e, void *d_out, const void *d_in, float *d_vad, int nb_frames, int s16);
+int b200_engine_frames_host(B200Engine *e, void *out, const void *in, float *vad, int nb_frames, int s16);
 int b200_engine_prefilter_device(B200Engine *e, const float *d_in);
 int b200_engine_sync(B200Engine *e);
 int b200_engine_set_stream(B200Engine *e, void *cuda_stream);

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(160) k_heads(int S, DevModel m, const float *_
                                                const float *__restrict__ g1, const float *__restrict__ g2,
                                                const float *__restrict__ g3, const int *__restrict__ silence,
                                                float *__restrict__ gains, float *__restrict__ vad,
-                                               float *__restrict__ vad_user) {
+                                               float *__restrict__ vad_user, int vad_stride) {
   __shared__ __align__(16) float xs[2][HEAD_TS][HEAD_XS];
   __shared__ __align__(16) float ws[2][HEAD_KC][NB_GAINS];
   __shared__ __align__(16) float wv[2][HEAD_KC];
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(160) k_heads(int S, DevModel m, const float *_
     if (s < S) {
       float v = silence[s] ? 0.f : act_sigmoid(y + m.vad_dense.bias[0]);
       vad[s] = v;
-      if (vad_user) vad_user[s] = v;
+      if (vad_user) vad_user[(size_t)s * vad_stride] = v;
     }
   }
 }

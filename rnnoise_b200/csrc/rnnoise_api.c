@@ -143,6 +143,18 @@ int rnnoise_process_frame_batch_device_s16(RNNoiseBatch *b, short *d_out, const 
   if (!b || !d_out || !d_in) return -1;
   return b200_engine_frame_device_s16(b->engine, d_out, d_in, d_vad);
 }
+int rnnoise_process_frames_batch(RNNoiseBatch *b, float *out, const float *in, float *vad, int nb_frames) {
+  return b ? b200_engine_frames_host(b->engine, out, in, vad, nb_frames, 0) : -1;
+}
+int rnnoise_process_frames_batch_s16(RNNoiseBatch *b, short *out, const short *in, float *vad, int nb_frames) {
+  return b ? b200_engine_frames_host(b->engine, out, in, vad, nb_frames, 1) : -1;
+}
+int rnnoise_process_frames_batch_device(RNNoiseBatch *b, float *d_out, const float *d_in, float *d_vad, int nb_frames) {
+  return b ? b200_engine_frames_device(b->engine, d_out, d_in, d_vad, nb_frames, 0) : -1;
+}
+int rnnoise_process_frames_batch_device_s16(RNNoiseBatch *b, short *d_out, const short *d_in, float *d_vad, int nb_frames) {
+  return b ? b200_engine_frames_device(b->engine, d_out, d_in, d_vad, nb_frames, 1) : -1;
+}
 int rnnoise_batch_prefilter_device(RNNoiseBatch *b, const float *d_in_next) {
   return b && d_in_next ? b200_engine_prefilter_device(b->engine, d_in_next) : -1;
 }

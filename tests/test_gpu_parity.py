@@ -314,3 +314,42 @@ def test_int16_pcm_io_matches_demo_semantics(rb, models_dir):
         o16, v16 = b.process_s16(pcm[f].astype(np.int16))
         assert np.array_equal(o16, of.astype(np.int32).astype(np.int16)) and np.array_equal(bits(vf), bits(v16)), f
     a.destroy(); b.destroy(); model.free()
+
+
+@pytest.mark.parametrize("chunk", [None, "5"])
+def test_multi_frame_calls_equal_frame_at_a_time(rb, models_dir, chunk, monkeypatch):
+    """rnnoise_process_frames_batch{,_s16,_device}: T frames per call over [S][T*480] buffers are
+    bit-identical to T single-frame calls, across chunk boundaries (T not a multiple of the staging
+    chunk), across consecutive multi-frame calls, and when mixed with single-frame calls."""
+    import torch
+    if chunk:
+        monkeypatch.setenv("RNNOISE_B200_MULTI_CHUNK", chunk)
+    model = rb.Model(os.path.join(models_dir, "default.bin"))
+    S, T1, T2 = 70, 23, 9
+    frames = T1 + 1 + T2
+    a, b, c, d = (rb.Batch(model, S) for _ in range(4))
+    pcm = batch_pcm(S, frames)                     # [frames][S][480], integer-valued
+    ref_out = np.empty((S, frames * 480), np.float32); ref_vad = np.empty((S, frames), np.float32)
+    for f in range(frames):
+        o, v = a.process(pcm[f])
+        ref_out[:, f * 480:(f + 1) * 480] = o; ref_vad[:, f] = v
+    by_stream = np.ascontiguousarray(pcm.transpose(1, 0, 2).reshape(S, frames * 480))
+    # host float: T1 frames, one single-frame call, T2 frames
+    o1, v1 = b.process_frames(by_stream[:, :T1 * 480])
+    om, vm = b.process(pcm[T1])
+    o2, v2 = b.process_frames(by_stream[:, (T1 + 1) * 480:])
+    got = np.concatenate([o1, om, o2], axis=1); gv = np.concatenate([v1, vm[:, None], v2], axis=1)
+    assert np.array_equal(bits(got), bits(ref_out)) and np.array_equal(bits(gv), bits(ref_vad))
+    # host int16, whole signal in one call
+    o16, v16 = c.process_frames(by_stream.astype(np.int16))
+    assert o16.dtype == np.int16 and np.array_equal(o16, ref_out.astype(np.int32).astype(np.int16))
+    assert np.array_equal(bits(v16), bits(ref_vad))
+    # device pointers, in place
+    dbuf = torch.from_numpy(by_stream).cuda(); dv = torch.empty(S, frames, device="cuda")
+    torch.cuda.synchronize()
+    d.process_frames_device(dbuf.data_ptr(), dbuf.data_ptr(), dv.data_ptr(), frames)
+    d.sync()
+    assert np.array_equal(bits(dbuf.cpu().numpy()), bits(ref_out)) and np.array_equal(bits(dv.cpu().numpy()), bits(ref_vad))
+    for x in (a, b, c, d):
+        x.destroy()
+    model.free()
