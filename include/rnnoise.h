@@ -125,6 +125,26 @@ RNNOISE_EXPORT int rnnoise_process_frames_batch_s16(RNNoiseBatch *b, short *out,
 RNNOISE_EXPORT int rnnoise_process_frames_batch_device(RNNoiseBatch *b, float *d_out, const float *d_in, float *d_vad, int nb_frames);
 RNNOISE_EXPORT int rnnoise_process_frames_batch_device_s16(RNNoiseBatch *b, short *d_out, const short *d_in, float *d_vad, int nb_frames);
 
+/** Training-feature extraction: the per-frame body of the reference's
+ *  training-data tool, src/dump_features.c:466-491 (a -DTRAINING=1 build), for every stream of the batch:
+ *    rnn_frame_analysis(clean state, Y, Ey, clean)                     (denoise.c:332-345)
+ *    quiet = rnn_compute_frame_features(noisy state, X, P, Ex, Ep, Exp, features, noisy)   (:347-398)
+ *    g[i] = min(1, sqrt((Ey[i] + 1e-3) / (Ex[i] + 1e-3))), or -1 where the target is undefined
+ *  with the TRAINING semantics: X and Y low-passed at lowpass[s] bins (:340-343), no silence
+ *  short-circuit (:389), quiet = E < 0.1 (:397).  clean/noisy are [nb_streams][480] floats, already
+ *  mixed and filtered by the caller (the tool's sequence-level filtering and mixing, :411-463, stay on the
+ *  host); rec is [nb_streams][RNNOISE_TRAIN_RECORD] = features[65] | g[32] | vad_target, the record
+ *  dump_features writes (:487-489).  vad_target [nb_streams] floats, noise_free [nb_streams] ints (non-zero:
+ *  noise_gain == 0 && fgnoise_gain == 0, :477), lowpass / band_lp [nb_streams] ints (:400-406); any of the
+ *  four may be NULL (0, 0, 481, 32).  The batch keeps the two signal histories (clean and noisy) per
+ *  stream; use a batch either for this or for denoising, not both.  0 on success, -1 on error. */
+#define RNNOISE_TRAIN_RECORD 98
+RNNOISE_EXPORT int rnnoise_batch_train_features(RNNoiseBatch *b, float *rec, const float *clean, const float *noisy,
+                                                const float *vad_target, const int *noise_free, const int *lowpass, const int *band_lp);
+RNNOISE_EXPORT int rnnoise_batch_train_features_device(RNNoiseBatch *b, float *d_rec, const float *d_clean, const float *d_noisy,
+                                                       const float *d_vad_target, const int *d_noise_free, const int *d_lowpass,
+                                                       const int *d_band_lp);
+
 /** Device-buffer call: d_in/d_out/d_vad are device pointers on the batch's device (d_out may alias
  *  d_in; d_vad may be NULL).  Enqueues the frame on the batch's stream and returns without
  *  synchronising.  0 on success, -1 on a launch error. */

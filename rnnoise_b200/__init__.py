@@ -55,6 +55,8 @@ def lib():
         for nm in ("rnnoise_process_frames_batch", "rnnoise_process_frames_batch_s16", "rnnoise_process_frames_batch_device",
                    "rnnoise_process_frames_batch_device_s16"):
             getattr(L, nm).restype = ip; getattr(L, nm).argtypes = [vp, vp, vp, vp, ip]
+        for nm in ("rnnoise_batch_train_features", "rnnoise_batch_train_features_device"):
+            getattr(L, nm).restype = ip; getattr(L, nm).argtypes = [vp] * 8
         L.rnnoise_process_frame_batch_device.restype = ip; L.rnnoise_process_frame_batch_device.argtypes = [vp, vp, vp, vp]
         L.rnnoise_batch_prefilter_device.restype = ip; L.rnnoise_batch_prefilter_device.argtypes = [vp, vp]
         L.rnnoise_batch_sync.restype = ip; L.rnnoise_batch_sync.argtypes = [vp]
@@ -144,6 +146,20 @@ class Batch:
         fn = lib().rnnoise_process_frames_batch_device_s16 if s16 else lib().rnnoise_process_frames_batch_device
         if fn(self.handle, d_out, d_in, d_vad, nb_frames) != 0:
             raise RuntimeError("rnnoise_process_frames_batch_device failed")
+
+    def train_features(self, clean, noisy, vad_target=None, noise_free=None, lowpass=None, band_lp=None):
+        """Training-feature records (include/rnnoise.h: rnnoise_batch_train_features): clean, noisy float32
+        [nb_streams][480]; optional per-stream arrays -> float32 [nb_streams][98] = features | g | vad target."""
+        c = np.ascontiguousarray(clean, np.float32); n = np.ascontiguousarray(noisy, np.float32)
+        assert c.shape == n.shape == (self.nb_streams, FRAME_SIZE)
+        keep = [None if a is None else np.ascontiguousarray(a, dt) for a, dt in
+                ((vad_target, np.float32), (noise_free, np.int32), (lowpass, np.int32), (band_lp, np.int32))]
+        assert all(a is None or a.shape == (self.nb_streams,) for a in keep)
+        rec = np.empty((self.nb_streams, 98), np.float32)
+        if lib().rnnoise_batch_train_features(self.handle, rec.ctypes.data, c.ctypes.data, n.ctypes.data,
+                                              *[None if a is None else a.ctypes.data for a in keep]) != 0:
+            raise RuntimeError("rnnoise_batch_train_features failed")
+        return rec
 
     def process_ptr_s16_async(self, out_ptr, in_ptr, vad_ptr=None):
         if lib().rnnoise_process_frame_batch_s16_async(self.handle, out_ptr, in_ptr, vad_ptr) != 0:

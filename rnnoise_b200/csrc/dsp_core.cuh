@@ -28,6 +28,7 @@
 #define FREQ_SIZE 481
 #define NB_BANDS 32
 #define NB_FEATURES 65
+#define TRAIN_RECORD (NB_FEATURES + NB_BANDS + 1)   // features | ideal gains | vad target (dump_features.c:487-489)
 #define PITCH_MIN_PERIOD 60
 #define PITCH_MAX_PERIOD 768
 #define PITCH_FRAME_SIZE 960

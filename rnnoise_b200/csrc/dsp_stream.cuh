@@ -26,6 +26,7 @@ struct SpectrumArgs {
   float *band_out;      // [3][32]  Ex, Ep, Exp
   float *features;      // [65]
   int *silence;         // [1]
+  int lowpass;          // TRAIN only: bins >= lowpass of X are zeroed (denoise.c:340-343)
 };
 
 // Pitch half of rnn_compute_frame_features (src/denoise.c:359-370): rnn_pitch_downsample /
@@ -358,6 +359,10 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
 
 // Spectral half of rnn_compute_frame_features (src/denoise.c:358, 371-397) incl. rnn_frame_analysis
 // (:332-345): X, P, band energies / correlation, log-energy features, silence test.
+// TRAIN selects the reference's -DTRAINING=1 semantics (the build src/dump_features.c uses): X is
+// low-passed at a.lowpass (:340-343), a quiet frame does NOT short-circuit the features (:389) and the
+// returned flag is E < 0.1 (:397).
+template <bool TRAIN>
 HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   float *misc = sm + SM_SPEC_END;
   int *mi = (int *)(misc + MI_INT);
@@ -377,6 +382,7 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_BEGIN
     for (int i = tid; i < FREQ_SIZE; i += nthr) {
       cpx v = F[i];
+      if (TRAIN && i >= a.lowpass) v.r = v.i = 0.f;
       XS[i] = v;
       ((cpx *)a.spec_out)[i] = v;
       if (i < 400) tx[i] = bin_term(v, v);
@@ -434,9 +440,9 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
         misc[MI_LY + i] = ly;
         E += misc[MI_E + i];
       }
-      int silent = E < 0.04;
+      int silent = !TRAIN && E < 0.04;
       mi[3] = silent;
-      a.silence[0] = silent;
+      a.silence[0] = TRAIN ? E < 0.1 : silent;
     }
   PHASE_END
   // -- features (denoise.c:378-379, 391, 394-396)
@@ -452,6 +458,59 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
       a.features[tid] = silent ? 0.f : v;
     } else if (tid == 2 * NB_BANDS) {
       a.features[tid] = silent ? 0.f : (float)(.01 * (pitch_T - 300));
+    }
+  PHASE_END
+}
+
+// Training targets (the per-frame body of src/dump_features.c:466-491, a -DTRAINING=1 build): after
+// spectrum_stream<true> of the noisy frame (features -> rec[0..65), Ex left in misc[MI_E..]), analyse the
+// clean frame (rnn_frame_analysis on the clean state: window, FFT, low-pass, band energies Ey) and derive
+// the ideal band gains g = min(1, sqrt((Ey + 1e-3) / (Ex + 1e-3))), -1 where the target is undefined.
+struct TrainArgs {
+  const float *clean;   // [480] clean speech frame
+  float *clean_mem;     // [480] previous clean frame (analysis_mem of the clean state)
+  float *rec;           // [98]  features[65] | g[32] | vad target
+  const int *quiet;     // [1]   flag written by spectrum_stream<true> (E < 0.1)
+  int lowpass, band_lp; // the sequence's low-pass bin and the first band above it (dump_features.c:400-406)
+  float vad_target;
+  int noise_free;       // noise_gain == 0 && fgnoise_gain == 0 (dump_features.c:477)
+};
+HD void train_targets_stream(float *sm, const TrainArgs a, const DspTables *T) {
+  float *misc = sm + SM_SPEC_END;
+  cpx *F = (cpx *)(sm + SM_F);
+  float *win = sm + SM_WIN, *tx = sm + SM_TX;
+  PHASE_BEGIN
+    for (int i = tid; i < FRAME_SIZE; i += nthr) { win[i] = a.clean_mem[i]; win[FRAME_SIZE + i] = a.clean[i]; }
+  PHASE_END
+  PHASE_BEGIN
+    for (int i = tid; i < FRAME_SIZE; i += nthr) a.clean_mem[i] = win[FRAME_SIZE + i];
+    fft_stage1(F, win, nullptr, T, tid, nthr);
+  PHASE_END
+  PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_radix5(F, T, tid, nthr); PHASE_END
+  PHASE_BEGIN
+    for (int i = tid; i < 400; i += nthr) {
+      cpx v = F[i];
+      if (i >= a.lowpass) v.r = v.i = 0.f;
+      tx[i] = bin_term(v, v);
+    }
+  PHASE_END
+  PHASE_BEGIN
+    if (tid < NB_BANDS + 2) misc[MI_BAND + tid] = band_sum_terms(tid, tx, T);
+  PHASE_END
+  PHASE_BEGIN
+    if (tid < NB_BANDS) {
+      const float ey = band_finish(misc + MI_BAND, tid), ex = misc[MI_E + tid];
+      float g = (float)sqrt((ey + 1e-3) / (ex + 1e-3));
+      if (g > 1) g = 1;
+      if (a.quiet[0] || tid > a.band_lp) g = -1;
+      if (ey < 5e-2 && ex < 5e-2) g = -1;
+      if (a.vad_target == 0 && a.noise_free) g = -1;
+      a.rec[NB_FEATURES + tid] = g;
+    } else if (tid == NB_BANDS) {
+      a.rec[NB_FEATURES + NB_BANDS] = a.vad_target;
     }
   PHASE_END
 }

@@ -149,7 +149,44 @@ __global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena
   g.band_out = a.band + ((size_t)slot * a.S + s) * 96;
   g.features = a.features + ((size_t)par * a.S + s) * NB_FEATURES;
   g.silence = a.silence + (size_t)par * a.S + s;
-  spectrum_stream(sm, g, T);
+  g.lowpass = FREQ_SIZE;
+  spectrum_stream<false>(sm, g, T);
+}
+
+// Training-feature extraction (src/dump_features.c:466-491): spectrum_stream<true> of the noisy frame +
+// clean-frame analysis + ideal gains; one 98-float record per stream.  Per-stream arrays may be null
+// (vad target 0, noise present, no low-pass).  grid = S, block = 128, dynamic smem = SM_SPEC_TOTAL floats
+struct TrainIo {
+  const float *clean;       // [S][480]
+  float *clean_mem;         // [S][480]
+  float *rec;               // [S][98]
+  const float *vad_target;  // [S] or null
+  const int *noise_free, *lowpass, *band_lp;   // [S] or null
+};
+__global__ void __launch_bounds__(DSP_THREADS) k_train_features(Arena a, const DspTables *__restrict__ T, int f, TrainIo io) {
+  extern __shared__ float sm[];
+  const int par = f & 1, slot = f % 3;
+  const int s = blockIdx.x;
+  SpectrumArgs g;
+  g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
+  g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+  g.pitch_state = a.pitch_state + 2 * (size_t)s;
+  g.spec_out = a.spec + ((size_t)slot * a.S + s) * (4 * FREQ_SIZE);
+  g.band_out = a.band + ((size_t)slot * a.S + s) * 96;
+  g.features = io.rec + (size_t)s * TRAIN_RECORD;
+  g.silence = a.silence + (size_t)par * a.S + s;
+  g.lowpass = io.lowpass ? io.lowpass[s] : FREQ_SIZE;
+  spectrum_stream<true>(sm, g, T);
+  TrainArgs t;
+  t.clean = io.clean + (size_t)s * FRAME_SIZE;
+  t.clean_mem = io.clean_mem + (size_t)s * FRAME_SIZE;
+  t.rec = io.rec + (size_t)s * TRAIN_RECORD;
+  t.quiet = g.silence;
+  t.lowpass = g.lowpass;
+  t.band_lp = io.band_lp ? io.band_lp[s] : NB_BANDS;
+  t.vad_target = io.vad_target ? io.vad_target[s] : 0.f;
+  t.noise_free = io.noise_free ? io.noise_free[s] : 0;
+  train_targets_stream(sm, t, T);
 }
 
 __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTables *__restrict__ T,
@@ -195,6 +232,8 @@ struct B200Engine {
   int multi_chunk;                   // frames per staged chunk (RNNOISE_B200_MULTI_CHUNK, default 16)
   size_t multi_bytes;                // bytes allocated per PCM staging buffer
   cudaEvent_t ev_mh2d[2], ev_mcomp[2], ev_md2h[2];
+  // training-feature extraction: clean-speech analysis memory and host-call staging (allocated on first use)
+  float *train_clean_mem, *train_stage;   // [S][480]; [S][2*480 + 98 + 4]
   int overlap;                       // 0: everything on one stream (RNNOISE_B200_OVERLAP=0, profiling)
   int pdl;                           // programmatic dependent launch along the network chain (RNNOISE_B200_PDL=1 enables)
   cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
@@ -374,6 +413,7 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   e->bq_frames = 0;
   e->io_stride = FRAME_SIZE;
   e->vad_stride = 1;
+  e->train_clean_mem = e->train_stage = nullptr;
   e->multi_bytes = 0;
   {
     const char *mc = getenv("RNNOISE_B200_MULTI_CHUNK");
@@ -725,6 +765,73 @@ extern "C" int b200_engine_frames_host(B200Engine *e, void *out, const void *in,
     CK(cudaEventRecord(e->ev_md2h[slot], e->s_d2h));
   }
   return b200_engine_sync(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Training-feature extraction: the frame loop of src/dump_features.c:466-491 for
+// every stream of the batch.  The noisy frame goes through the pitch + spectrum kernels with the
+// reference's TRAINING semantics (no high-pass prefilter: dump_features filters whole sequences itself,
+// :421-432), the clean frame through a window + FFT + band-energy pass; out = [S][98] records.
+// A batch used this way keeps its own signal history; do not interleave with denoising calls.
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200_engine_train_features_device(B200Engine *e, float *d_rec, const float *d_clean, const float *d_noisy,
+                                                 const float *d_vad_target, const int *d_noise_free, const int *d_lowpass,
+                                                 const int *d_band_lp) {
+  if (!e || !d_rec || !d_clean || !d_noisy || e->bq_frames != e->frames) return -1;
+  CK(cudaSetDevice(e->device));
+  const Arena &a = e->a;
+  const size_t S = (size_t)a.S;
+  cudaStream_t st = e->stream;
+  if (!e->train_clean_mem) {
+    CK(cudaMalloc(&e->train_clean_mem, S * FRAME_SIZE * sizeof(float)));
+    e->allocs.push_back(e->train_clean_mem);
+    CK(cudaMemsetAsync(e->train_clean_mem, 0, S * FRAME_SIZE * sizeof(float), st));
+  }
+  // order after whatever the analysis streams of earlier denoising calls still run
+  CK(cudaStreamWaitEvent(st, e->ev_ana[0], 0));
+  CK(cudaStreamWaitEvent(st, e->ev_ana[1], 0));
+  CK(cudaStreamWaitEvent(st, e->ev_front[0], 0));
+  CK(cudaStreamWaitEvent(st, e->ev_front[1], 0));
+  const int par = (int)(e->frames & 1), fr = (int)(e->frames & 0x3fffffff);
+  CK(cudaMemcpyAsync(a.xb + (size_t)par * S * FRAME_SIZE, d_noisy, S * FRAME_SIZE * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const int pitch_grid = (a.S + PITCH_NS - 1) / PITCH_NS;
+  k_pitch<<<pitch_grid, PITCH_NS * PITCH_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr);
+  TrainIo io;
+  io.clean = d_clean; io.clean_mem = e->train_clean_mem; io.rec = d_rec;
+  io.vad_target = d_vad_target; io.noise_free = d_noise_free; io.lowpass = d_lowpass; io.band_lp = d_band_lp;
+  k_train_features<<<a.S, DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr, io);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e->ev_ana[par], st));
+  CK(cudaEventRecord(e->ev_front[par], st));
+  e->frames++;
+  e->bq_frames = e->frames;
+  e->host_frames = e->frames;
+  return 0;
+}
+
+extern "C" int b200_engine_train_features_host(B200Engine *e, float *rec, const float *clean, const float *noisy,
+                                               const float *vad_target, const int *noise_free, const int *lowpass, const int *band_lp) {
+  if (!e || !rec || !clean || !noisy) return -1;
+  CK(cudaSetDevice(e->device));
+  const size_t S = (size_t)e->a.S, F = S * FRAME_SIZE;
+  if (!e->train_stage) {
+    CK(cudaMalloc(&e->train_stage, (2 * F + S * TRAIN_RECORD + 4 * S) * sizeof(float)));
+    e->allocs.push_back(e->train_stage);
+  }
+  float *d_clean = e->train_stage, *d_noisy = d_clean + F, *d_rec = d_noisy + F, *d_vt = d_rec + S * TRAIN_RECORD;
+  int *d_nf = (int *)(d_vt + S), *d_lp = d_nf + S, *d_bl = d_lp + S;
+  cudaStream_t st = e->stream;
+  CK(cudaMemcpyAsync(d_clean, clean, F * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_noisy, noisy, F * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (vad_target) CK(cudaMemcpyAsync(d_vt, vad_target, S * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (noise_free) CK(cudaMemcpyAsync(d_nf, noise_free, S * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (lowpass) CK(cudaMemcpyAsync(d_lp, lowpass, S * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (band_lp) CK(cudaMemcpyAsync(d_bl, band_lp, S * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (b200_engine_train_features_device(e, d_rec, d_clean, d_noisy, vad_target ? d_vt : nullptr, noise_free ? d_nf : nullptr,
+                                        lowpass ? d_lp : nullptr, band_lp ? d_bl : nullptr)) return -1;
+  CK(cudaMemcpyAsync(rec, d_rec, S * TRAIN_RECORD * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
 }
 
 extern "C" int b200_engine_frame_host(B200Engine *e, float *out, const float *in, float *vad) {

@@ -155,6 +155,14 @@ int rnnoise_process_frames_batch_device(RNNoiseBatch *b, float *d_out, const flo
 int rnnoise_process_frames_batch_device_s16(RNNoiseBatch *b, short *d_out, const short *d_in, float *d_vad, int nb_frames) {
   return b ? b200_engine_frames_device(b->engine, d_out, d_in, d_vad, nb_frames, 1) : -1;
 }
+int rnnoise_batch_train_features(RNNoiseBatch *b, float *rec, const float *clean, const float *noisy, const float *vad_target,
+                                 const int *noise_free, const int *lowpass, const int *band_lp) {
+  return b ? b200_engine_train_features_host(b->engine, rec, clean, noisy, vad_target, noise_free, lowpass, band_lp) : -1;
+}
+int rnnoise_batch_train_features_device(RNNoiseBatch *b, float *d_rec, const float *d_clean, const float *d_noisy,
+                                        const float *d_vad_target, const int *d_noise_free, const int *d_lowpass, const int *d_band_lp) {
+  return b ? b200_engine_train_features_device(b->engine, d_rec, d_clean, d_noisy, d_vad_target, d_noise_free, d_lowpass, d_band_lp) : -1;
+}
 int rnnoise_batch_prefilter_device(RNNoiseBatch *b, const float *d_in_next) {
   return b && d_in_next ? b200_engine_prefilter_device(b->engine, d_in_next) : -1;
 }

@@ -43,3 +43,23 @@ def batch_pcm(streams, frames, base_seed=20260922, first_stream=0):
     for i in range(streams):
         out[:, i, :] = stream_pcm(first_stream + i, frames, base_seed)
     return out
+
+
+def train_pair(stream, frames):
+    """Deterministic (clean, noisy) float32 [frames][480] pair for the training-feature tests: the clean
+    signal is one synthetic stream, the noisy one adds a second, scaled, stream (float32 elementwise
+    arithmetic only, so every machine produces the same bits).  Every 5th stream is noise-free."""
+    clean = stream_pcm(stream, frames) * np.float32(0.5)
+    if stream % 5 == 4:
+        return clean, clean.copy()
+    noise = stream_pcm(stream + 7919, frames) * np.float32(0.25)
+    return clean, (clean + noise).astype(np.float32)
+
+
+def train_params(stream):
+    """(lowpass bin, band_lp, noise_free) per stream, spanning the tool's range (dump_features.c:400-406)."""
+    eband = [0, 2, 4, 6, 8, 10, 12, 15, 18, 21, 24, 28, 32, 36, 41, 47, 53, 60, 68, 77, 87, 98, 110, 124, 140, 157, 176, 198, 223,
+             251, 282, 317, 356, 400]
+    lowpass = [481, 60, 120, 200, 300, 481, 90][stream % 7]
+    band_lp = next((i for i in range(32) if eband[i] > lowpass), 32)
+    return lowpass, band_lp, int(stream % 5 == 4)

@@ -15,6 +15,7 @@ struct EmuStream {
   float ring[PITCH_BUF_SIZE], synth_mem[FRAME_SIZE], hp[2];
   float spec[2][4 * FREQ_SIZE], band[2][96], lastg[NB_BANDS], pitch_state[2];
   float features[NB_FEATURES], xb[FRAME_SIZE];
+  float clean_mem[FRAME_SIZE], rec[TRAIN_RECORD];
   int silence;
 };
 struct EmuState {
@@ -64,8 +65,55 @@ void emu_analysis(void *p, const float *in, int nstreams) {
     a.band_out = s.band[par];
     a.features = s.features;
     a.silence = &s.silence;
-    spectrum_stream(e->sm, a, &e->T);
+    a.lowpass = FREQ_SIZE;
+    spectrum_stream<false>(e->sm, a, &e->T);
   }
+}
+// training-feature record of one frame (k_train_features): no prefilter, TRAINING semantics.
+// clean/noisy: [NS][480]; per-stream lowpass / band_lp / vad_target / noise_free; rec: [NS][98]; quiet: [NS]
+void emu_train(void *p, const float *clean, const float *noisy, int nstreams, const int *lowpass, const int *band_lp,
+               const float *vad_target, const int *noise_free, float *rec, int *quiet) {
+  EmuState *e = (EmuState *)p;
+  const long f = e->frames;
+  const int par = (int)(f & 1);
+  PitchArgs pa[PITCH_NS];
+  for (int q = 0; q < PITCH_NS; q++) {
+    EmuStream &s = e->st[q];
+    pa[q].ring = nullptr;
+    if (q >= nstreams) continue;
+    memcpy(s.xb, noisy + q * FRAME_SIZE, sizeof(s.xb));
+    pa[q].xb = s.xb;
+    pa[q].ring = s.ring;
+    pa[q].ring_base = (int)(((f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+    pa[q].pitch_state = s.pitch_state;
+  }
+  pitch_streams(e->sm, pa, &e->T);
+  for (int q = 0; q < nstreams; q++) {
+    EmuStream &s = e->st[q];
+    SpectrumArgs a;
+    a.ring = s.ring;
+    a.ring_base = pa[q].ring_base;
+    a.pitch_state = s.pitch_state;
+    a.spec_out = s.spec[par];
+    a.band_out = s.band[par];
+    a.features = s.rec;
+    a.silence = &s.silence;
+    a.lowpass = lowpass[q];
+    spectrum_stream<true>(e->sm, a, &e->T);
+    TrainArgs t;
+    t.clean = clean + q * FRAME_SIZE;
+    t.clean_mem = s.clean_mem;
+    t.rec = s.rec;
+    t.quiet = &s.silence;
+    t.lowpass = lowpass[q];
+    t.band_lp = band_lp[q];
+    t.vad_target = vad_target[q];
+    t.noise_free = noise_free[q];
+    train_targets_stream(e->sm, t, &e->T);
+    memcpy(rec + q * TRAIN_RECORD, s.rec, sizeof(s.rec));
+    quiet[q] = s.silence;
+  }
+  e->frames++;
 }
 // results of the last emu_analysis for stream q; returns the silence flag
 int emu_get(void *p, int q, float *xb, float *features, float *X, float *P, float *bands, float *pitch) {

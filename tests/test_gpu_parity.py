@@ -353,3 +353,41 @@ def test_multi_frame_calls_equal_frame_at_a_time(rb, models_dir, chunk, monkeypa
     for x in (a, b, c, d):
         x.destroy()
     model.free()
+
+
+def test_train_features_match_training_reference_goldens(rb, models_dir):
+    """rnnoise_batch_train_features: records bit-identical to the unmodified reference built with
+    -DTRAINING=1 running the dump_features frame loop (tests/golden/ref_train.npz, made by
+    tests/golden/make_golden_train.py); host and device entry points agree."""
+    import torch
+    from rnnoise_b200.synth_pcm import train_pair, train_params
+    g = np.load(os.path.join(GOLD, "ref_train.npz"))
+    streams, frames = [int(s) for s in g["streams"]], int(g["frames"])
+    S = len(streams)
+    model = rb.Model(os.path.join(models_dir, "default.bin"))
+    a, b = rb.Batch(model, S), rb.Batch(model, S)
+    pairs = [train_pair(s, frames) for s in streams]
+    par = [train_params(s) for s in streams]
+    lowpass = np.array([p[0] for p in par], np.int32); band_lp = np.array([p[1] for p in par], np.int32)
+    noise_free = np.array([p[2] for p in par], np.int32)
+    dl, db, dn = (torch.from_numpy(x).cuda() for x in (lowpass, band_lp, noise_free))
+    for f in range(frames):
+        clean = np.stack([p[0][f] for p in pairs]); noisy = np.stack([p[1][f] for p in pairs])
+        vad = np.array([float((f // 7 + s) % 2) for s in streams], np.float32)
+        rec = a.train_features(clean, noisy, vad, noise_free, lowpass, band_lp)
+        assert np.array_equal(bits(rec), bits(g["rec"][f])), (f, np.argwhere(bits(rec) != bits(g["rec"][f]))[:5])
+        assert np.array_equal(np.array([int(a.debug("silence", i)[0]) for i in range(S)]), g["quiet"][f]), f
+        dc, dno, dv = (torch.from_numpy(x).cuda() for x in (clean, noisy, vad))
+        drec = torch.empty(S, 98, device="cuda")
+        torch.cuda.synchronize()
+        assert rb.lib().rnnoise_batch_train_features_device(b.handle, drec.data_ptr(), dc.data_ptr(), dno.data_ptr(), dv.data_ptr(),
+                                                            dn.data_ptr(), dl.data_ptr(), db.data_ptr()) == 0
+        b.sync()
+        assert np.array_equal(bits(drec.cpu().numpy()), bits(rec)), f
+    # defaults (all optional arrays NULL): no low-pass, vad target 0, noise present
+    c = rb.Batch(model, S)
+    r0 = c.train_features(np.stack([p[0][0] for p in pairs]), np.stack([p[1][0] for p in pairs]))
+    assert r0.shape == (S, 98) and np.all(r0[:, 97] == 0)
+    for x in (a, b, c):
+        x.destroy()
+    model.free()
