@@ -22,6 +22,22 @@
 #define HD static inline
 #endif
 
+// 4-byte asynchronous global -> shared copy (LDGSTS): lets a phase start fetching the data of a later
+// phase without holding registers; async_wait_all() before the barrier that publishes it.  On the host
+// (emulation) the copy is immediate.
+HD void async_copy4(float *dst_shared, const float *src_global) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
+#else
+  *dst_shared = *src_global;
+#endif
+}
+HD void async_wait_all() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 #define DSP_THREADS 128
 #define FRAME_SIZE 480
 #define WINDOW_SIZE 960
@@ -77,8 +93,7 @@ struct DspTables {
 #define SM_XS (SM_F + 2 * WINDOW_SIZE)   // [962] X kept for the X.P correlation
 #define SM_WIN (SM_XS + 2 * FREQ_SIZE)    // [960] analysis window staged from the ring (coalesced); after the P
                                          //       transform's first stage: per-bin terms |P|^2 [0,400), Re(X conj P) [400,800)
-#define SM_TX (SM_WIN + WINDOW_SIZE)     // [400] per-bin terms |X|^2
-#define SM_SPEC_END (SM_TX + 400)
+#define SM_SPEC_END (SM_WIN + WINDOW_SIZE)
 #define SM_MISC_SIZE 288                 // small per-stream scalars / band vectors, after either plan
 #define SM_PITCH_TOTAL (SM_PITCH_END + SM_MISC_SIZE)
 #define SM_SPEC_TOTAL (SM_SPEC_END + SM_MISC_SIZE)
@@ -254,6 +269,17 @@ HD float band_sum_terms(int b, const float *t, const DspTables *T) {
     for (int k = T->eband[b - 1]; k < T->eband[b]; k++) sum += T->bin_frac[k] * t[k];
   if (b <= NB_BANDS)
     for (int k = T->eband[b]; k < T->eband[b + 1]; k++) sum += T->bin_cfrac[k] * t[k];
+  return sum;
+}
+// Same sums again with the weights already applied by the parallel lanes: w[k * stride] = bin_frac[k] * t[k]
+// and w[k * stride + coff] = bin_cfrac[k] * t[k] (the very products of the loop above), which leaves one
+// shared-memory load + FADD per step on the serial lanes and no table load at all.
+HD float band_sum_pre(int b, const float *w, int stride, int coff, const DspTables *T) {
+  float sum = 0.f;
+  if (b >= 1)
+    for (int k = T->eband[b - 1]; k < T->eband[b]; k++) sum += w[k * stride];
+  if (b <= NB_BANDS)
+    for (int k = T->eband[b]; k < T->eband[b + 1]; k++) sum += w[k * stride + coff];
   return sum;
 }
 HD float bin_term(cpx a, cpx c) {

@@ -39,12 +39,14 @@ struct SpectrumArgs {
 // packed side by side into the lanes of one or two warps -- same instructions, PITCH_NS x the useful
 // lanes.  Thread ids: q = tid / PITCH_THREADS is the stream a thread belongs to, t its local id;
 // packed phases use the first lanes of the CTA instead.
-// Measured on B200 (S = 4096): PITCH_NS = 1 -> 127 us, PITCH_NS = 4 -> 145 us: with 16 streams resident
-// per SM either way, packing removes instructions but also leaves fewer warps runnable during the
-// chain phases, and the kernel is bound by the chains' latency; the default therefore stays 1 (the
-// host emulation builds with 4 to keep the packed mapping tested).
+// Measured on B200 (S = 4096), kernel alone / whole pipelined step:
+//   128 threads per stream: PITCH_NS 1 -> 127 us / 403 us, PITCH_NS 4 -> 145 us (16 streams resident per
+//     SM either way: packing removes instructions but leaves fewer warps runnable during the chains)
+//    96 threads per stream: PITCH_NS 1 -> 132 us / 377-383 us (18 streams per SM: the 1 KB the hardware
+//     reserves per CTA costs two of the 20), PITCH_NS 2 -> 131 / 377, PITCH_NS 4 -> 124 us / 365 us
+//     (5 CTAs x 4 = 20 streams, the thread-slot limit) -> default.
 #ifndef PITCH_NS
-#define PITCH_NS 1
+#define PITCH_NS 4
 #endif
 // Threads per stream in the pitch kernel.  The chains keep one warp busy per stream, so more resident
 // streams per SM hide more latency: 96 threads (3 warps) x 20 streams fill an SM's 2048 thread slots
@@ -367,7 +369,7 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   float *misc = sm + SM_SPEC_END;
   int *mi = (int *)(misc + MI_INT);
   cpx *F = (cpx *)(sm + SM_F), *XS = (cpx *)(sm + SM_XS);
-  float *win = sm + SM_WIN, *tx = sm + SM_TX;
+  float *win = sm + SM_WIN;
   const int pitch_T = ((const int *)a.pitch_state)[0];
   // -- X = FFT(window * [previous frame | this frame]) (denoise.c:332-339); the analysis window
   //    is the last 960 samples of the updated pitch history.
@@ -375,7 +377,16 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
     for (int i = tid; i < WINDOW_SIZE; i += nthr) win[i] = ring_at(a.ring, a.ring_base, PITCH_BUF_SIZE - WINDOW_SIZE + i);
   PHASE_END
   PHASE_BEGIN fft_stage1(F, win, nullptr, T, tid, nthr); PHASE_END
-  PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
+  PHASE_BEGIN
+    // the staging buffer is dead until the second transform: start fetching the pitch-lagged window
+    // into it now (asynchronous copies), so the ring's latency hides behind the first transform
+    for (int i = tid; i < WINDOW_SIZE; i += nthr) {
+      int p = a.ring_base + PITCH_BUF_SIZE - WINDOW_SIZE - pitch_T + i;
+      if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
+      async_copy4(win + i, a.ring + p);
+    }
+    fft_radix4(F, 4, 16, 60, T, tid, nthr);
+  PHASE_END
   PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix5(F, T, tid, nthr); PHASE_END
@@ -385,10 +396,8 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
       if (TRAIN && i >= a.lowpass) v.r = v.i = 0.f;
       XS[i] = v;
       ((cpx *)a.spec_out)[i] = v;
-      if (i < 400) tx[i] = bin_term(v, v);
     }
-    // stage the pitch-lagged window for the second transform (coalesced read of the ring)
-    for (int i = tid; i < WINDOW_SIZE; i += nthr) win[i] = ring_at(a.ring, a.ring_base, PITCH_BUF_SIZE - WINDOW_SIZE - pitch_T + i);
+    async_wait_all();   // the lagged window is in `win` once this phase's barrier is passed
   PHASE_END
   // -- P = FFT(window * pitch_buf[768-T .. 768-T+960)) (denoise.c:371-374)
   PHASE_BEGIN fft_stage1(F, win, nullptr, T, tid, nthr); PHASE_END
@@ -400,14 +409,24 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
     for (int i = tid; i < FREQ_SIZE; i += nthr) {
       cpx v = F[i];
       ((cpx *)a.spec_out)[FREQ_SIZE + i] = v;
-      if (i < 400) { win[i] = bin_term(v, v); win[400 + i] = bin_term(XS[i], v); }   // staging is dead by now
+      if (i < 400) {
+        // weighted per-bin terms of the three band sums (band_sum_pre), each pair written over the
+        // complex value it came from (this thread's own slots) or into the dead window staging
+        const cpx x = XS[i];
+        const float wf = T->bin_frac[i], wc = T->bin_cfrac[i];
+        const float tx = bin_term(x, x), tp = bin_term(v, v), txp = bin_term(x, v);
+        XS[i].r = wf * tx; XS[i].i = wc * tx;
+        F[i].r = wf * tp; F[i].i = wc * tp;
+        win[i] = wf * txp; win[400 + i] = wc * txp;
+      }
     }
   PHASE_END
   // -- the three sets of 34 triangular band sums (compute_band_energy / compute_band_corr), one lane each
   PHASE_BEGIN
     if (tid < 3 * (NB_BANDS + 2)) {
       const int set = tid / (NB_BANDS + 2), b = tid % (NB_BANDS + 2);
-      misc[MI_BAND + 34 * set + b] = band_sum_terms(b, set == 0 ? tx : win + 400 * (set - 1), T);
+      misc[MI_BAND + 34 * set + b] = set == 2 ? band_sum_pre(b, win, 1, 400, T)
+                                              : band_sum_pre(b, (const float *)(set == 0 ? XS : F), 2, 1, T);
     }
   PHASE_END
   // -- Ex, Ep, Exp (denoise.c:344,375-377)
@@ -478,7 +497,7 @@ struct TrainArgs {
 HD void train_targets_stream(float *sm, const TrainArgs a, const DspTables *T) {
   float *misc = sm + SM_SPEC_END;
   cpx *F = (cpx *)(sm + SM_F);
-  float *win = sm + SM_WIN, *tx = sm + SM_TX;
+  float *win = sm + SM_WIN;
   PHASE_BEGIN
     for (int i = tid; i < FRAME_SIZE; i += nthr) { win[i] = a.clean_mem[i]; win[FRAME_SIZE + i] = a.clean[i]; }
   PHASE_END
@@ -494,11 +513,12 @@ HD void train_targets_stream(float *sm, const TrainArgs a, const DspTables *T) {
     for (int i = tid; i < 400; i += nthr) {
       cpx v = F[i];
       if (i >= a.lowpass) v.r = v.i = 0.f;
-      tx[i] = bin_term(v, v);
+      const float ty = bin_term(v, v);
+      win[i] = T->bin_frac[i] * ty; win[400 + i] = T->bin_cfrac[i] * ty;
     }
   PHASE_END
   PHASE_BEGIN
-    if (tid < NB_BANDS + 2) misc[MI_BAND + tid] = band_sum_terms(tid, tx, T);
+    if (tid < NB_BANDS + 2) misc[MI_BAND + tid] = band_sum_pre(tid, win, 1, 400, T);
   PHASE_END
   PHASE_BEGIN
     if (tid < NB_BANDS) {
@@ -532,8 +552,7 @@ struct SynthesisArgs {
 #define SS_P (SS_X + 2 * FREQ_SIZE)   // [962] delayed P
 #define SS_F (SS_P + 2 * FREQ_SIZE)   // [1920] FFT buffer
 #define SS_V (SS_F + 2 * WINDOW_SIZE) // [6][34] band vectors: r, norm, g, sums...
-#define SS_T (SS_V + 6 * 34)           // [400] per-bin |X|^2 of the pitch-filtered spectrum
-#define SS_TOTAL (SS_T + 400)
+#define SS_TOTAL (SS_V + 6 * 34)
 
 // rnn_pitch_filter (denoise.c:421-455), gain smoothing + interpolation (:479-493),
 // frame_synthesis (:400-407) with inverse_transform (:200-217).
@@ -570,11 +589,14 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
         x.r += rf * p.r;
         x.i += rf * p.i;
         X[i] = x;
-        if (i < 400) sm[SS_T + i] = bin_term(x, x);
+        if (i < 400) {   // weighted band-sum terms into the (still idle) FFT buffer
+          const float tx = bin_term(x, x);
+          sm[SS_F + i] = T->bin_frac[i] * tx; sm[SS_F + 400 + i] = T->bin_cfrac[i] * tx;
+        }
       }
     PHASE_END
     PHASE_BEGIN
-      if (tid < NB_BANDS + 2) sums[tid] = band_sum_terms(tid, sm + SS_T, T);
+      if (tid < NB_BANDS + 2) sums[tid] = band_sum_pre(tid, sm + SS_F, 1, 400, T);
     PHASE_END
     PHASE_BEGIN
       if (tid < NB_BANDS) {
