@@ -19,6 +19,7 @@
 #include "engine.h"
 #include "rnn_kernels.cuh"
 #include "gru_tc.cuh"
+#include "heads_kernel.cuh"
 
 #define CK(call)                                                                          \
   do {                                                                                    \
@@ -242,6 +243,7 @@ struct B200Engine {
   long long bq_frames;               // frames whose high-pass prefilter has been issued
   int use_tc;                       // GRU kernel: 2 = k_tc2<true> (default), 1 = k_gru_tc, 0 = dp4a cross-check
   int conv2_tc;                     // conv2 kernel: 1 = k_tc2<false> (default), 0 = dp4a cross-check
+  int heads2;                       // heads kernel: 1 = k_heads2 (default), 0 = k_heads (RNNOISE_B200_HEADS_KERNEL=cpasync)
   GruTcMaps tc_maps[2][3];          // [frame parity][layer]
   GruTcMaps conv_maps;              // x = c2in, wi = conv2 weights
   // optional per-kernel timing (rnnoise_batch_profile)
@@ -383,7 +385,13 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   e->own_stream = nullptr;
   e->profiling = 0; e->prof_frames = 0;
   for (int i = 0; i <= NKERNELS; i++) e->ev[i] = nullptr;
-  if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return nullptr; }
+  {
+    // the engine's own stream (network + synthesis) runs at the highest priority and the analysis front at
+    // the lowest (s_front below): the back half of frame f gets SM slots before the front of frame f+1
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&e->own_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { delete e; return nullptr; }
+  }
   e->stream = e->own_stream;
   Arena &a = e->a;
   a.S = S; a.cond = m->cond; a.gru = m->gru;
@@ -473,6 +481,8 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   // tensor-core GRU path: permuted weights + TMA maps for both frame parities
   // RNNOISE_B200_GRU_KERNEL = tc2 (default: persistent pipelined tcgen05) | tc1 (one tile per CTA) |
   // dp4a (CUDA-core cross-check); all three produce identical bits
+  { const char *hk = getenv("RNNOISE_B200_HEADS_KERNEL"); e->heads2 = !(hk && !strcmp(hk, "cpasync")); }
+  ok = ok && cudaFuncSetAttribute(k_heads2, cudaFuncAttributeMaxDynamicSharedMemorySize, H2_SMEM_BYTES) == cudaSuccess;
   const char *gk = getenv("RNNOISE_B200_GRU_KERNEL");
   e->use_tc = gk && !strcmp(gk, "dp4a") ? 0 : gk && !strcmp(gk, "tc1") ? 1 : 2;
   if (ok && e->use_tc) {
@@ -610,8 +620,12 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
     MARK();
   }
   const bool pdl_heads = pdl && e->use_tc == 2;   // only the k_tc2 predecessors are PDL-aware
-  CK(launch_pdl(k_heads, dim3((S + HEAD_TS - 1) / HEAD_TS), dim3(160), 0, st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
-                (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
+  if (e->heads2)
+    CK(launch_pdl(k_heads2, dim3((S + H2_TS - 1) / H2_TS), dim3(160), H2_SMEM_BYTES, st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
+                  (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
+  else
+    CK(launch_pdl(k_heads, dim3((S + HEAD_TS - 1) / HEAD_TS), dim3(160), 0, st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
+                  (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
   MARK();
   CK(launch_pdl(k_synthesis, dim3(S), dim3(DSP_THREADS), SS_TOTAL * sizeof(float), st, pdl_heads, a, (const DspTables *)e->d_tables, d_out, fr, s16, e->io_stride));
   CK(cudaEventRecord(e->ev_back[par], st));

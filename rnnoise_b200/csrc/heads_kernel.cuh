@@ -1,0 +1,127 @@
+// heads_kernel.cuh -- output heads of the network, register-tiled (default kernel; k_heads in
+// rnn_kernels.cuh is the cp.async cross-check with the same arithmetic).
+//
+//   cat = [conv2_out | gru1 | gru2 | gru3]  (rnn.c:53-57), K = 4 * gru inputs
+//   gains[32] = sigmoid(dense_out . cat + b)   each output one sequential FMA chain over K (sgemv, vec_avx.h:672)
+//   vad       = sigmoid(vad_dense . cat + b)   scalar loop: multiply, then add (vec_avx.h:731-735)
+//
+// CTA = 32 streams, 160 threads.  Warps 0..3 each own 8 streams x 32 outputs: a thread keeps 4 streams x
+// 2 adjacent outputs = 8 independent chains in registers, so one LDS.128 of activations and one LDS.64 of
+// weights feed 8 / 4 FMAs.  Warp 4 runs the 32 VAD chains (lane = stream) and is the producer: inputs and
+// weights arrive in chunks of 64 inputs (one 8 KB bulk copy of weights + 16-byte cp.async pieces of the
+// activation rows, all completing on one mbarrier) through an H2_STAGES-deep ring, so staging costs no
+// instructions on the compute warps.
+// grid = ceil(S / 32); dynamic smem = H2_STAGES * 17 KB.
+#pragma once
+#include "gru_tc.cuh"
+
+#define H2_TS 32
+#define H2_KC 64
+#define H2_XS (H2_KC + 4)   // padded row: 272 B keeps rows 16-byte aligned and LDS.128 conflict-free
+#ifndef H2_STAGES
+#define H2_STAGES 6
+#endif
+struct H2Stage {
+  float xs[H2_TS][H2_XS];
+  float ws[H2_KC][NB_GAINS];
+  float wv[H2_KC];
+};
+#define H2_SMEM_BYTES (H2_STAGES * (int)sizeof(H2Stage) + 128)
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *__restrict__ c2,
+                                                const float *__restrict__ g1, const float *__restrict__ g2,
+                                                const float *__restrict__ g3, const int *__restrict__ silence,
+                                                float *__restrict__ gains, float *__restrict__ vad,
+                                                float *__restrict__ vad_user, int vad_stride) {
+  extern __shared__ __align__(128) uint8_t h2_smem[];
+  H2Stage *st = (H2Stage *)h2_smem;
+  __shared__ __align__(8) uint64_t full[H2_STAGES];
+  const int s0 = blockIdx.x * H2_TS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gru = m.gru, nchunk = 4 * gru / H2_KC;
+  const int live_rows = min(H2_TS, S - s0);
+  if (tid == 0) {
+    for (int i = 0; i < H2_STAGES; i++) mbar_init(smem_u32(&full[i]), 33);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_trigger();
+  pdl_wait();   // GRU-3 state of this frame
+  __syncthreads();
+  // producer (warp 4): chunk c -> stage c % H2_STAGES.  gru % 64 == 0, so a chunk never straddles two sources.
+  // The 8 KB weight slab and the VAD weights are one bulk copy each; the 32 activation rows (256 B each, one
+  // per stream) go as 16-byte cp.async pieces, 16 per lane, into the padded rows -- 32 separate 256-byte bulk
+  // copies per chunk were measured at 50 us for the kernel: the per-copy cost of the bulk engine dominated.
+  // Each lane's cp.async.mbarrier.arrive.noinc fires once its pieces have landed; with lane 0's expect_tx
+  // arrival that makes 33 arrivals per phase.
+  auto produce = [&](int c) {
+    const int buf = c % H2_STAGES, c0 = c * H2_KC, src = c0 / gru, off = c0 - src * gru;
+    const uint32_t bar = smem_u32(&full[buf]);
+    if (lane == 0) {
+      mbar_expect_tx(bar, (uint32_t)(H2_KC * NB_GAINS + H2_KC) * 4u);
+      bulk_g2s(smem_u32(&st[buf].ws[0][0]), m.dense_out.w + (size_t)c0 * NB_GAINS, H2_KC * NB_GAINS * 4, bar);
+      bulk_g2s(smem_u32(&st[buf].wv[0]), m.vad_dense.w + c0, H2_KC * 4, bar);
+    }
+    const float *p = (src == 0 ? c2 : src == 1 ? g1 : src == 2 ? g2 : g3) + (size_t)s0 * gru + off;
+#pragma unroll
+    for (int i = 0; i < H2_TS * H2_KC / 4 / 32; i++) {   // piece = i * 32 + lane: row = piece / 16, 16-byte column = piece % 16
+      const int row = 2 * i + (lane >> 4), col = lane & 15;
+      cp_async16(&st[buf].xs[row][4 * col], p + (size_t)(row < live_rows ? row : 0) * gru + 4 * col, row < live_rows);
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+  };
+  if (warp == 4)
+    for (int c = 0; c < H2_STAGES - 1 && c < nchunk; c++) produce(c);
+  float acc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++) acc[i][0] = acc[i][1] = 0.f;
+  float y = 0.f;
+  const int row0 = warp * 8 + (lane >> 4) * 4, o2 = (lane & 15) * 2;
+  for (int c = 0; c < nchunk; c++) {
+    const int buf = c % H2_STAGES;
+    if (warp == 4 && c + H2_STAGES - 1 < nchunk) produce(c + H2_STAGES - 1);   // that stage was released by the barrier ending chunk c-1
+    mbar_wait(smem_u32(&full[buf]), (uint32_t)(c / H2_STAGES) & 1u);
+    const H2Stage &b = st[buf];
+    if (warp < 4) {
+#pragma unroll 4
+      for (int kk = 0; kk < H2_KC; kk += 4) {
+        const float4 x0 = *(const float4 *)&b.xs[row0 + 0][kk], x1 = *(const float4 *)&b.xs[row0 + 1][kk];
+        const float4 x2 = *(const float4 *)&b.xs[row0 + 2][kk], x3 = *(const float4 *)&b.xs[row0 + 3][kk];
+        const float2 w0 = *(const float2 *)&b.ws[kk][o2], w1 = *(const float2 *)&b.ws[kk + 1][o2];
+        const float2 w2 = *(const float2 *)&b.ws[kk + 2][o2], w3 = *(const float2 *)&b.ws[kk + 3][o2];
+#define H2_STEP(W, C)                                                                                  \
+  acc[0][0] = fmaf(W.x, x0.C, acc[0][0]); acc[0][1] = fmaf(W.y, x0.C, acc[0][1]);                      \
+  acc[1][0] = fmaf(W.x, x1.C, acc[1][0]); acc[1][1] = fmaf(W.y, x1.C, acc[1][1]);                      \
+  acc[2][0] = fmaf(W.x, x2.C, acc[2][0]); acc[2][1] = fmaf(W.y, x2.C, acc[2][1]);                      \
+  acc[3][0] = fmaf(W.x, x3.C, acc[3][0]); acc[3][1] = fmaf(W.y, x3.C, acc[3][1]);
+        H2_STEP(w0, x) H2_STEP(w1, y) H2_STEP(w2, z) H2_STEP(w3, w)
+#undef H2_STEP
+      }
+    } else {
+#pragma unroll 4
+      for (int kk = 0; kk < H2_KC; kk += 4) {
+        const float4 x = *(const float4 *)&b.xs[lane][kk], w = *(const float4 *)&b.wv[kk];
+        y = y + w.x * x.x; y = y + w.y * x.y; y = y + w.z * x.z; y = y + w.w * x.w;
+      }
+    }
+    __syncthreads();   // everyone is done with this stage before the producer refills it
+  }
+  if (warp < 4) {
+    const float b0 = m.dense_out.bias[o2], b1 = m.dense_out.bias[o2 + 1];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int s = s0 + row0 + i;
+      if (s < S) *(float2 *)&gains[(size_t)s * NB_GAINS + o2] = make_float2(act_sigmoid(acc[i][0] + b0), act_sigmoid(acc[i][1] + b1));
+    }
+  } else {
+    const int s = s0 + lane;
+    if (s < S) {
+      const float v = silence[s] ? 0.f : act_sigmoid(y + m.vad_dense.bias[0]);
+      vad[s] = v;
+      if (vad_user) vad_user[(size_t)s * vad_stride] = v;
+    }
+  }
+}

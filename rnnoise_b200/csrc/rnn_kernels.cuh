@@ -58,6 +58,12 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src, bool vali
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
 }
 
+__device__ __forceinline__ void cp_async4(void *dst, const void *src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 4 : 0;   // src-size 0 -> zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
 // Programmatic dependent launch (PDL): the network kernels of one frame form a chain on one stream.
 // pdl_trigger() lets the next kernel's CTAs be scheduled as soon as SM resources free up (its prologue
 // -- barrier init, TMEM allocation, weight prefetch -- overlaps this kernel's tail); pdl_wait() in the
@@ -93,30 +99,32 @@ __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *_
   const int s0 = blockIdx.x * RNN_TS, tid = threadIdx.x, W = m.cond / 4, cond = m.cond;
   pdl_trigger();
   constexpr int KIN = 3 * NB_FEAT, NCH = (KIN + C1_KC - 1) / C1_KC;
-  auto stage = [&](int c, int buf) {
-    const int j0 = c * C1_KC, rows = min(C1_KC, KIN - j0);
-    for (int idx = tid; idx < rows * W; idx += 128) {
-      int r = idx / W, q = idx % W;
-      cp_async16(&wsm[buf][r][4 * q], &m.conv1.w[(size_t)(j0 + r) * cond + 4 * q], true);
-    }
+  auto stage = [&](int c, int buf) {   // lane = 16-byte column, warp = row (mod 4): no index division
+    const int j0 = c * C1_KC, rows = min(C1_KC, KIN - j0), q = tid & 31;
+    if (q < W)
+      for (int r = tid >> 5; r < rows; r += 4)
+        cp_async16(&wsm[buf][r][4 * q], &m.conv1.w[(size_t)(j0 + r) * cond + 4 * q], true);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  stage(0, 0);
+  // inputs [state(2 frames) | features] and the conv2 input words to rotate: asynchronous 4-byte copies
+  // (zero fill for absent streams), all in flight together, nothing held in registers
   for (int idx = tid; idx < RNN_TS * KIN; idx += 128) {
-    int s = idx / KIN, j = idx % KIN;
-    float v = 0.f;
-    if (s0 + s < S) v = j < 2 * NB_FEAT ? conv1_state[(size_t)(s0 + s) * 2 * NB_FEAT + j]
-                                         : features[(size_t)(s0 + s) * NB_FEAT + j - 2 * NB_FEAT];
-    tmp[s][j] = v;
+    const int s = idx / KIN, j = idx % KIN;
+    const bool live = s0 + s < S;
+    const size_t row = live ? s0 + s : 0;
+    cp_async4(&tmp[s][j], j < 2 * NB_FEAT ? &conv1_state[row * 2 * NB_FEAT + j] : &features[row * NB_FEAT + j - 2 * NB_FEAT], live);
   }
-  for (int idx = tid; idx < RNN_TS * 2 * W; idx += 128) {   // words [W, 3W) of each live row
-    int s = idx / (2 * W), w = idx % (2 * W);
-    if (s0 + s < S) rot[s][w] = ((const uint32_t *)(c2in + (size_t)(s0 + s) * 3 * cond))[W + w];
+  for (int s = tid >> 6; s < RNN_TS; s += 2) {   // words [W, 3W) of each live row; 2W <= 64 words per row
+    const int w = tid & 63;
+    if (w < 2 * W) cp_async4(&rot[s][w], (const uint32_t *)(c2in + (size_t)(s0 + s < S ? s0 + s : 0) * 3 * cond) + W + w, s0 + s < S);
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  stage(0, 0);
+  asm volatile("cp.async.wait_group 1;" ::: "memory");   // inputs landed (the first weight chunk may still be in flight)
   __syncthreads();
-  for (int idx = tid; idx < RNN_TS * 2 * W; idx += 128) {
-    int s = idx / (2 * W), w = idx % (2 * W);
-    if (s0 + s < S && !silence[s0 + s]) ((uint32_t *)(c2in + (size_t)(s0 + s) * 3 * cond))[w] = rot[s][w];
+  for (int s = tid >> 6; s < RNN_TS; s += 2) {
+    const int w = tid & 63;
+    if (w < 2 * W && s0 + s < S && !silence[s0 + s]) ((uint32_t *)(c2in + (size_t)(s0 + s) * 3 * cond))[w] = rot[s][w];
   }
   const int o = tid;
   float acc[RNN_TS];

@@ -233,6 +233,17 @@ def test_gru_tensor_core_paths_equal_dp4a_path(rb, models_dir):
             for k in ("conv2_out", "conv2_state", "gru3"):
                 assert np.array_equal(bits(a.debug(k, s)), bits(b.debug(k, s))), (k, s, f)
     a.destroy(); b.destroy()
+    # output heads: register-tiled bulk-copy kernel (default) vs the cp.async kernel; S = 300 leaves a partial tile
+    os.environ["RNNOISE_B200_HEADS_KERNEL"] = "cpasync"
+    a = rb.Batch(model, S)
+    del os.environ["RNNOISE_B200_HEADS_KERNEL"]
+    b = rb.Batch(model, S)
+    for f in range(frames):
+        oa, va = a.process(pcm[f]); ob, vb = b.process(pcm[f])
+        assert np.array_equal(bits(oa), bits(ob)) and np.array_equal(bits(va), bits(vb)), f
+        for s in (0, 31, 32, 288, 299):
+            assert np.array_equal(bits(a.debug("gains", s)), bits(b.debug("gains", s))), (s, f)
+    a.destroy(); b.destroy()
     model.free()
 
 

@@ -13,7 +13,7 @@ n = sys.argv[1]
 try:
     d = json.loads(open(f"gpurun_out/ab_{n}.json").read().strip().splitlines()[-1])
     k = {a: b * 1e3 for a, b in d["roofline"]["kernel_ms_per_step"].items()}
-    print(n, "ms/step", round(d["ms_per_step"], 4), "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), {a: round(b, 1) for a, b in k.items()})
+    print(n, "ms/step", round(d["ms_per_step"], 4), "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "e2e16", round(d["e2e"]["int16_pcm"]["value"]), {a: round(b, 1) for a, b in k.items()})
 except Exception as e:
     print(n, "FAILED", e)
 PY
