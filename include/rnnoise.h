@@ -204,6 +204,12 @@ enum {
   RNNOISE_DBG_SILENCE = 15,   /* [1]   1.0 when the frame was classified silent                  */
   RNNOISE_DBG_CONV2_OUT = 16  /* [gru] conv2 output of the frame                                */
 };
+/** Pipeline timeline (diagnostics): with $RNNOISE_B200_TIMELINE=N set at batch creation, the first N frames
+ *  record timing events at the stage boundaries.  Synchronises, then writes [frames][8] milliseconds since
+ *  the first point: H2D start, H2D end, prefilter end, pitch end, spectrum end, network start, synthesis end,
+ *  D2H end (NaN where a stage did not run through this call path).  Returns the frames written, -1 on error. */
+RNNOISE_EXPORT int rnnoise_batch_timeline_read(RNNoiseBatch *b, float *ms, int capacity);
+
 /** Copies item `what` of stream `stream` into dst (capacity in floats); returns the number of
  *  floats written or -1. */
 RNNOISE_EXPORT int rnnoise_batch_debug_read(RNNoiseBatch *b, int what, int stream, float *dst, int capacity);

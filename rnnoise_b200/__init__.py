@@ -66,6 +66,7 @@ def lib():
         L.rnnoise_batch_profile.restype = ip; L.rnnoise_batch_profile.argtypes = [vp, ip]
         L.rnnoise_batch_profile_read.restype = ip
         L.rnnoise_batch_profile_read.argtypes = [vp, fp, C.POINTER(C.c_char_p), ip, C.POINTER(ip)]
+        L.rnnoise_batch_timeline_read.restype = ip; L.rnnoise_batch_timeline_read.argtypes = [vp, fp, ip]
         L.rnnoise_batch_debug_read.restype = ip; L.rnnoise_batch_debug_read.argtypes = [vp, ip, ip, fp, ip]
         _lib = L
     return _lib
@@ -179,6 +180,14 @@ class Batch:
         """Pipelining hint: start the next frame's high-pass prefilter now (see include/rnnoise.h)."""
         if lib().rnnoise_batch_prefilter_device(self.handle, d_in_next) != 0:
             raise RuntimeError("rnnoise_batch_prefilter_device failed")
+
+    def timeline(self, max_frames=256):
+        """[frames][8] stage-boundary times in ms ($RNNOISE_B200_TIMELINE must be set when the batch is created)."""
+        buf = np.zeros((max_frames, 8), np.float32)
+        n = lib().rnnoise_batch_timeline_read(self.handle, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size)
+        if n < 0:
+            raise RuntimeError("rnnoise_batch_timeline_read failed")
+        return buf[:n]
 
     def set_stream(self, cuda_stream):
         if lib().rnnoise_batch_set_stream(self.handle, cuda_stream) != 0:

@@ -250,7 +250,14 @@ struct B200Engine {
   int profiling, prof_frames;
   cudaEvent_t ev[NKERNELS + 1];
   double prof_ms[NKERNELS];
+  // optional pipeline timeline ($RNNOISE_B200_TIMELINE = frames to record): timing events at the stage
+  // boundaries of the first frames, on the streams the stages run on (rnnoise_batch_timeline_read)
+  int tl_frames;
+  std::vector<cudaEvent_t> tl;
 };
+enum { TL_H2D_START, TL_H2D_END, TL_BQ_END, TL_PITCH_END, TL_FRONT_END, TL_BACK_START, TL_BACK_END, TL_D2H_END, TL_POINTS };
+#define TL(e, frame, point, stream) \
+  do { if ((frame) < (long long)(e)->tl_frames) cudaEventRecord((e)->tl[(size_t)(frame) * TL_POINTS + (point)], (stream)); } while (0)
 static const char *const kKernelNames[NKERNELS] = {"k_biquad", "k_pitch", "k_spectrum", "k_conv1", "k_conv2", "k_gru[0]",
                                                    "k_gru[1]", "k_gru[2]", "k_heads", "k_synthesis"};
 
@@ -363,6 +370,7 @@ extern "C" void b200_engine_destroy(B200Engine *e) {
     if (e->ev_md2h[i]) cudaEventDestroy(e->ev_md2h[i]);
     cudaFree(e->multi_in[i]); cudaFree(e->multi_out[i]); cudaFree(e->multi_vad[i]);
   }
+  for (auto ev : e->tl) if (ev) cudaEventDestroy(ev);
   for (void *p : e->allocs) cudaFree(p);
   delete e;
 }
@@ -419,6 +427,12 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   ok &= !!(a.vad = dalloc<float>(e, Ss));
   e->host_frames = 0;
   e->bq_frames = 0;
+  {
+    const char *tl = getenv("RNNOISE_B200_TIMELINE");
+    e->tl_frames = tl && atoi(tl) > 0 ? atoi(tl) : 0;
+    e->tl.assign((size_t)e->tl_frames * TL_POINTS, nullptr);
+    for (auto &ev : e->tl) ok &= cudaEventCreate(&ev) == cudaSuccess;
+  }
   e->io_stride = FRAME_SIZE;
   e->vad_stride = 1;
   e->train_clean_mem = e->train_stage = nullptr;
@@ -580,19 +594,23 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
     }
     k_biquad<<<(S + 31) / 32, 32, 0, sf>>>(a, d_in, fr, s16, e->io_stride);
     CK(cudaEventRecord(e->ev_bq[par], sf));
+    TL(e, e->frames, TL_BQ_END, sf);
     e->bq_frames = e->frames + 1;
   }
   MARK();
   const int pitch_grid = (S + PITCH_NS - 1) / PITCH_NS;
   k_pitch<<<pitch_grid, PITCH_NS * PITCH_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
   CK(cudaEventRecord(e->ev_ana[par], sf));   // xb[par] is free again
+  TL(e, e->frames, TL_PITCH_END, sf);
   MARK();
   if (overlap) CK(cudaStreamWaitEvent(sf, e->ev_back[par], 0));   // frame f-2 is done with slot f%3 / parity buffers
   k_spectrum<<<S, DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
+  TL(e, e->frames, TL_FRONT_END, sf);
   if (overlap) {
     CK(cudaEventRecord(e->ev_front[par], sf));
     CK(cudaStreamWaitEvent(st, e->ev_front[par], 0));
   }
+  TL(e, e->frames, TL_BACK_START, st);
   MARK();
   const int gts = (S + RNN_TS - 1) / RNN_TS;
   k_conv1<<<gts, 128, 0, st>>>(S, e->dm, feat, a.conv1_state, sil, a.c2in);
@@ -629,6 +647,7 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   MARK();
   CK(launch_pdl(k_synthesis, dim3(S), dim3(DSP_THREADS), SS_TOTAL * sizeof(float), st, pdl_heads, a, (const DspTables *)e->d_tables, d_out, fr, s16, e->io_stride));
   CK(cudaEventRecord(e->ev_back[par], st));
+  TL(e, e->frames, TL_BACK_END, st);
   MARK();
 #undef MARK
   CK(cudaGetLastError());
@@ -657,6 +676,7 @@ static int issue_prefilter(B200Engine *e, const void *d_in, cudaEvent_t ready, i
   k_biquad<<<(e->a.S + 31) / 32, 32, 0, e->s_bq>>>(e->a, d_in, (int)(f & 0x3fffffff), s16, e->io_stride);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev_bq[slot], e->s_bq));
+  TL(e, f, TL_BQ_END, e->s_bq);
   e->bq_frames = f + 1;
   return 0;
 }
@@ -675,8 +695,10 @@ static int frame_host_async_io(B200Engine *e, void *out, const void *in, float *
   const int slot = (int)(e->host_frames & 1);
   // copy-in: the staging slot is free once the prefilter of frame n-2 has consumed it
   CK(cudaStreamWaitEvent(e->s_h2d, e->ev_bq[slot], 0));
+  TL(e, e->frames, TL_H2D_START, e->s_h2d);
   CK(cudaMemcpyAsync(e->stage_in[slot], in, n, cudaMemcpyHostToDevice, e->s_h2d));
   CK(cudaEventRecord(e->ev_h2d[slot], e->s_h2d));
+  TL(e, e->frames, TL_H2D_END, e->s_h2d);
   // high-pass prefilter on its own stream: overlaps the previous frame's kernels
   if (issue_prefilter(e, e->stage_in[slot], e->ev_h2d[slot], s16)) return -1;
   // rest of the frame: needs frame n-2's output staging drained
@@ -688,6 +710,7 @@ static int frame_host_async_io(B200Engine *e, void *out, const void *in, float *
   CK(cudaMemcpyAsync(out, e->stage_out[slot], n, cudaMemcpyDeviceToHost, e->s_d2h));
   if (vad) CK(cudaMemcpyAsync(vad, e->stage_vad[slot], (size_t)e->a.S * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
   CK(cudaEventRecord(e->ev_d2h[slot], e->s_d2h));
+  TL(e, e->frames - 1, TL_D2H_END, e->s_d2h);
   e->host_frames++;
   return 0;
 }
@@ -894,6 +917,24 @@ extern "C" int b200_engine_profile_read(B200Engine *e, float *ms, const char **n
   }
   if (frames) *frames = e->prof_frames;
   return NKERNELS;
+}
+
+// [frames recorded][TL_POINTS] milliseconds since the first recorded point; NaN where a point was not recorded
+extern "C" int b200_engine_timeline_read(B200Engine *e, float *dst, int capacity) {
+  if (!e || !dst) return -1;
+  if (b200_engine_sync(e)) return -1;
+  const int nf = (int)(e->frames < e->tl_frames ? e->frames : e->tl_frames);
+  if (capacity < nf * TL_POINTS) return -1;
+  cudaEvent_t t0 = nullptr;
+  for (int i = 0; i < TL_POINTS && !t0 && nf > 0; i++)
+    if (cudaEventQuery(e->tl[i]) == cudaSuccess) { float x; if (cudaEventElapsedTime(&x, e->tl[i], e->tl[i]) == cudaSuccess) t0 = e->tl[i]; }
+  cudaGetLastError();
+  for (int i = 0; i < nf * TL_POINTS; i++) {
+    float ms = 0.f;
+    dst[i] = t0 && cudaEventElapsedTime(&ms, t0, e->tl[i]) == cudaSuccess ? ms : nanf("");
+  }
+  cudaGetLastError();
+  return nf;
 }
 
 extern "C" int b200_engine_reset_stream(B200Engine *e, int s) {

@@ -37,6 +37,7 @@ int b200_engine_reset_stream(B200Engine *e, int stream);
 int b200_engine_launches_per_frame(const B200Engine *e);
 int b200_engine_profile(B200Engine *e, int enable);
 int b200_engine_profile_read(B200Engine *e, float *ms, const char **names, int capacity, int *frames);
+int b200_engine_timeline_read(B200Engine *e, float *dst, int capacity);
 int b200_engine_debug_read(B200Engine *e, int what, int stream, float *dst, int capacity);
 
 #ifdef __cplusplus

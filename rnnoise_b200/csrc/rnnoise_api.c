@@ -163,6 +163,9 @@ int rnnoise_batch_train_features_device(RNNoiseBatch *b, float *d_rec, const flo
                                         const float *d_vad_target, const int *d_noise_free, const int *d_lowpass, const int *d_band_lp) {
   return b ? b200_engine_train_features_device(b->engine, d_rec, d_clean, d_noisy, d_vad_target, d_noise_free, d_lowpass, d_band_lp) : -1;
 }
+int rnnoise_batch_timeline_read(RNNoiseBatch *b, float *ms, int capacity) {
+  return b ? b200_engine_timeline_read(b->engine, ms, capacity) : -1;
+}
 int rnnoise_batch_prefilter_device(RNNoiseBatch *b, const float *d_in_next) {
   return b && d_in_next ? b200_engine_prefilter_device(b->engine, d_in_next) : -1;
 }
