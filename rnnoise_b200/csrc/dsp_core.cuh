@@ -416,10 +416,24 @@ HD void lpc_taps(const float *ac_in, float *num) {
 // k = 1 stands for the initial candidate T0 itself.
 HD void rd_candidate(int k, int T0, int *T1, int *T1b) {
   const int maxperiod = PITCH_MAX_PERIOD / 2;
-  const int second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};
   if (k == 1) { *T1 = T0; *T1b = T0; return; }
+  // second_check[k] of pitch.c:420 for 2 <= k <= 15 = {3,2,3,2,5,2,3,2,3,2,3,2,5,2}: computed, so that no
+  // per-lane indexed table ends up in local memory
+  const int sc = (k & 1) ? 2 : (k == 6 || k == 12) ? 5 : 3;
+  // n / (2k), 0 <= n < 4096, 4 <= 2k <= 30, without a hardware integer division by a per-lane divisor:
+  // trunc((n + 0.5) * (1 / 2k)) in float.  The fractional part of (n + 0.5) / 2k lies in [1/60, 59/60], far
+  // beyond the rounding error (< 2^-11) of the two float operations, so the truncation is exact
+  // (checked exhaustively over the whole domain in tests/test_dsp_emulation.py).
+#ifdef RD_INT_DIV
   int t1 = (2 * T0 + k) / (2 * k);
   *T1 = t1;
   if (k == 2) *T1b = (t1 + T0 > maxperiod) ? T0 : T0 + t1;
-  else *T1b = (2 * second_check[k] * T0 + k) / (2 * k);
+  else *T1b = (2 * sc * T0 + k) / (2 * k);
+#else
+  const float inv = 1.0f / (float)(2 * k);
+  int t1 = (int)(((float)(2 * T0 + k) + 0.5f) * inv);
+  *T1 = t1;
+  if (k == 2) *T1b = (t1 + T0 > maxperiod) ? T0 : T0 + t1;
+  else *T1b = (int)(((float)(2 * sc * T0 + k) + 0.5f) * inv);
+#endif
 }

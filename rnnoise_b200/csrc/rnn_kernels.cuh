@@ -14,6 +14,21 @@
 #define NB_FEAT 65
 #define NB_GAINS 32
 
+// Correctly rounded reciprocal of the Pade denominators (the one place the contract departs from the
+// reference's _mm256_rcp_ps, DESIGN.md "Numerics").  den >= 952.7 by construction (even polynomial with
+// positive coefficients), so for den < 2^126 this is exactly the in-range path of __frcp_rn -- MUFU.RCP and
+// one FMA Newton step, the instructions the library routine executes after its exponent check -- without
+// the check and the call; anything else (overflowed or NaN input) takes the library routine.
+__device__ __forceinline__ float rcp_rn_den(float den) {
+  if (den < 8.0e37f) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+    const float e = fmaf(den, r, -1.0f);
+    return fmaf(r, -e, r);
+  }
+  return __frcp_rn(den);
+}
+
 __device__ __forceinline__ float act_tanh(float x) {   // tanh8_approx, vec_avx.h:398-416
   const float N0 = 952.52801514f, N1 = 96.39235687f, N2 = 0.60863042f;
   const float D0 = 952.72399902f, D1 = 413.36801147f, D2 = 11.88600922f;
@@ -21,7 +36,7 @@ __device__ __forceinline__ float act_tanh(float x) {   // tanh8_approx, vec_avx.
   float num = fmaf(fmaf(N2, x2, N1), x2, N0);
   float den = fmaf(fmaf(D2, x2, D1), x2, D0);
   num = num * x;
-  den = __frcp_rn(den);
+  den = rcp_rn_den(den);
   num = num * den;
   num = num < 1.f ? num : 1.f;
   return num > -1.f ? num : -1.f;
@@ -33,7 +48,7 @@ __device__ __forceinline__ float act_sigmoid(float x) { // sigmoid8_approx, vec_
   float num = fmaf(fmaf(N2, x2, N1), x2, N0);
   float den = fmaf(fmaf(D2, x2, D1), x2, D0);
   num = num * x;
-  den = __frcp_rn(den);
+  den = rcp_rn_den(den);
   num = fmaf(num, den, .5f);
   num = num < 1.f ? num : 1.f;
   return num > 0.f ? num : 0.f;

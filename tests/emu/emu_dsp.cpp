@@ -147,5 +147,7 @@ void emu_synthesis(void *p, int q, const float *gains, float *out, float *lastg)
   synthesis_stream(e->sm, a, &e->T);
   memcpy(lastg, s.lastg, sizeof(s.lastg));
 }
+// rd_candidate() exposed for an exhaustive check of its division-free arithmetic
+void emu_rd_candidate(int k, int T0, int *T1, int *T1b) { rd_candidate(k, T0, T1, T1b); }
 void emu_advance(void *p) { ((EmuState *)p)->frames++; }
 }

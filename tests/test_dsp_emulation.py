@@ -60,3 +60,20 @@ def test_device_dsp_source_is_bit_identical_to_port(emu, port_default, streams, 
     emu.emu_destroy(e)
     for st in states:
         port_default.destroy(st)
+
+
+def test_remove_doubling_candidates_exact_over_whole_domain(emu):
+    """rd_candidate() replaces the reference's integer divisions (pitch.c:462-481) by float multiply +
+    truncate and its second_check[] table by arithmetic: every (k, T0) must give the reference's integers."""
+    second_check = [0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2]
+    t1, t1b = C.c_int(), C.c_int()
+    emu.emu_rd_candidate.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    for k in range(1, 16):
+        for T0 in range(0, 385):
+            emu.emu_rd_candidate(k, T0, C.byref(t1), C.byref(t1b))
+            if k == 1:
+                want = (T0, T0)
+            else:
+                w1 = (2 * T0 + k) // (2 * k)
+                want = (w1, (T0 if w1 + T0 > 384 else T0 + w1) if k == 2 else (2 * second_check[k] * T0 + k) // (2 * k))
+            assert (t1.value, t1b.value) == want, (k, T0)
