@@ -90,6 +90,11 @@ RNNOISE_EXPORT RNNoiseBatch *rnnoise_batch_create(RNNModel *model, int nb_stream
 RNNOISE_EXPORT void rnnoise_batch_destroy(RNNoiseBatch *b);
 
 RNNOISE_EXPORT int rnnoise_batch_get_streams(const RNNoiseBatch *b);
+/** A batch is internally split into 1..4 "lanes" (contiguous stream ranges, each with its own CUDA streams)
+ *  that run side by side; streams are independent, so results do not depend on the split.  The default
+ *  (two lanes from 1024 up to 12287 streams, else one; measured on B200) can be overridden with
+ *  $RNNOISE_B200_LANES at creation time.  Returns the number of lanes. */
+RNNOISE_EXPORT int rnnoise_batch_get_lanes(const RNNoiseBatch *b);
 
 /** Host-buffer call: in/out are [nb_streams][480] floats in host memory (pinned memory makes the
  *  copies asynchronous DMA), vad is [nb_streams] (may be NULL).  Copies in, runs the frame, copies
@@ -162,7 +167,10 @@ RNNOISE_EXPORT int rnnoise_batch_prefilter_device(RNNoiseBatch *b, const float *
 RNNOISE_EXPORT int rnnoise_batch_sync(RNNoiseBatch *b);
 
 /** Use an existing CUDA stream (a cudaStream_t passed as void*) for all subsequent work of this
- *  batch, so callers can time with events on their own stream.  NULL restores the private stream. */
+ *  batch, so callers can time with events on their own stream.  NULL restores the private stream.
+ *  With several lanes the lanes keep their private streams: the kernels of a device-pointer call that read
+ *  the input or write out/vad start after the work already enqueued on the caller's stream, and the caller's
+ *  stream waits for the call's completion, so the call still behaves like work on that one stream. */
 RNNOISE_EXPORT int rnnoise_batch_set_stream(RNNoiseBatch *b, void *cuda_stream);
 
 /** Re-zero the state of one stream (what rnnoise_init() does to a DenoiseState).  0 / -1. */

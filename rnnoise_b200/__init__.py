@@ -48,6 +48,7 @@ def lib():
         L.rnnoise_batch_create.restype = vp; L.rnnoise_batch_create.argtypes = [vp, ip, ip]
         L.rnnoise_batch_destroy.argtypes = [vp]
         L.rnnoise_batch_get_streams.restype = ip; L.rnnoise_batch_get_streams.argtypes = [vp]
+        L.rnnoise_batch_get_lanes.restype = ip; L.rnnoise_batch_get_lanes.argtypes = [vp]
         L.rnnoise_process_frame_batch.restype = ip; L.rnnoise_process_frame_batch.argtypes = [vp, vp, vp, vp]
         L.rnnoise_process_frame_batch_async.restype = ip; L.rnnoise_process_frame_batch_async.argtypes = [vp, vp, vp, vp]
         for nm in ("rnnoise_process_frame_batch_s16", "rnnoise_process_frame_batch_s16_async", "rnnoise_process_frame_batch_device_s16"):
@@ -101,6 +102,7 @@ class Batch:
         self.handle = lib().rnnoise_batch_create(model.handle, nb_streams, device)
         if not self.handle:
             raise RuntimeError("rnnoise_batch_create failed (no usable CUDA device, bad model or out of memory)")
+        self.lanes = lib().rnnoise_batch_get_lanes(self.handle)
 
     def process(self, pcm, want_vad=True):
         """pcm: float32 [nb_streams][480] host array -> (out [nb_streams][480], vad [nb_streams])."""
@@ -211,9 +213,10 @@ class Batch:
 
     def profile_read(self):
         """-> (dict kernel name -> total ms, frames profiled)"""
-        n = self.launches_per_frame
-        ms = (C.c_float * n)(); names = (C.c_char_p * n)(); frames = C.c_int(0)
-        if lib().rnnoise_batch_profile_read(self.handle, ms, names, n, C.byref(frames)) != n:
+        cap = 32
+        ms = (C.c_float * cap)(); names = (C.c_char_p * cap)(); frames = C.c_int(0)
+        n = lib().rnnoise_batch_profile_read(self.handle, ms, names, cap, C.byref(frames))
+        if n <= 0:
             raise RuntimeError("rnnoise_batch_profile_read failed")
         return {names[i].decode(): float(ms[i]) for i in range(n)}, frames.value
 

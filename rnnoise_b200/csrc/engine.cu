@@ -226,6 +226,11 @@ struct B200Engine {
   cudaStream_t s_front;              // k_pitch/k_spectrum of frame f+1 overlap network + synthesis of frame f
   cudaEvent_t ev_front[2], ev_back[2];   // analysis of frame f done / network+synthesis of frame f done (by parity)
   cudaEvent_t ev_in;                 // input readiness on the caller's stream (non-prefiltered frames)
+  // lanes (rnnoise_api.c splits a batch into sub-batches that run concurrently): a lane other than the
+  // first keeps its own stream but orders every call after `parent` (the caller's stream) and makes
+  // `parent` wait for the call's completion, so the caller sees one stream's semantics
+  cudaStream_t parent;
+  cudaEvent_t ev_pin, ev_pout;
   int io_stride, vad_stride;         // element strides between streams in the caller's PCM / VAD buffers
   // multi-frame host calls: double-buffered chunk staging ([S][chunk*480] in, out; [S][chunk] vad)
   void *multi_in[2], *multi_out[2];
@@ -357,6 +362,8 @@ extern "C" void b200_engine_destroy(B200Engine *e) {
   if (e->s_bq) { cudaStreamSynchronize(e->s_bq); cudaStreamDestroy(e->s_bq); }
   if (e->s_front) { cudaStreamSynchronize(e->s_front); cudaStreamDestroy(e->s_front); }
   if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_pin) cudaEventDestroy(e->ev_pin);
+  if (e->ev_pout) cudaEventDestroy(e->ev_pout);
   for (int i = 0; i < 2; i++) {
     if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
     if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
@@ -433,6 +440,10 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
     e->tl.assign((size_t)e->tl_frames * TL_POINTS, nullptr);
     for (auto &ev : e->tl) ok &= cudaEventCreate(&ev) == cudaSuccess;
   }
+  e->parent = nullptr;
+  e->ev_pin = e->ev_pout = nullptr;
+  ok &= cudaEventCreateWithFlags(&e->ev_pin, cudaEventDisableTiming) == cudaSuccess;
+  ok &= cudaEventCreateWithFlags(&e->ev_pout, cudaEventDisableTiming) == cudaSuccess;
   e->io_stride = FRAME_SIZE;
   e->vad_stride = 1;
   e->train_clean_mem = e->train_stage = nullptr;
@@ -550,12 +561,29 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 extern "C" int b200_engine_streams(const B200Engine *e) { return e ? e->a.S : 0; }
 extern "C" int b200_engine_launches_per_frame(const B200Engine *) { return NKERNELS; }
 
+// Parent-stream bracketing of device-pointer calls (lanes).  Only the kernels that touch the caller's
+// buffers are ordered after the caller's stream -- the prefilter that reads the input, and the output heads /
+// synthesis that write vad and PCM -- so the analysis and the network of the next frame never wait for the
+// other lanes; the caller's stream waits for the call's completion (parent_leave).
+static int parent_enter(B200Engine *e) {
+  if (!e->parent) return 0;
+  CK(cudaEventRecord(e->ev_pin, e->parent));
+  return 0;
+}
+static int parent_leave(B200Engine *e) {
+  if (!e->parent) return 0;
+  CK(cudaEventRecord(e->ev_pout, e->stream));
+  CK(cudaStreamWaitEvent(e->parent, e->ev_pout, 0));
+  return 0;
+}
 static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *d_vad, int s16);
 extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float *d_in, float *d_vad) {
-  return frame_device_io(e, d_out, d_in, d_vad, 0);
+  if (!e || parent_enter(e) || frame_device_io(e, d_out, d_in, d_vad, 0)) return -1;
+  return parent_leave(e);
 }
 extern "C" int b200_engine_frame_device_s16(B200Engine *e, short *d_out, const short *d_in, float *d_vad) {
-  return frame_device_io(e, d_out, d_in, d_vad, 1);
+  if (!e || parent_enter(e) || frame_device_io(e, d_out, d_in, d_vad, 1)) return -1;
+  return parent_leave(e);
 }
 static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *d_vad, int s16) {
   if (!e || !d_out || !d_in) return -1;
@@ -592,6 +620,7 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
       CK(cudaStreamWaitEvent(sf, e->ev_in, 0));
       CK(cudaStreamWaitEvent(sf, e->ev_bq[par ^ 1], 0));   // biquad state: after frame f-1's filter
     }
+    if (e->parent) CK(cudaStreamWaitEvent(sf, e->ev_pin, 0));
     k_biquad<<<(S + 31) / 32, 32, 0, sf>>>(a, d_in, fr, s16, e->io_stride);
     CK(cudaEventRecord(e->ev_bq[par], sf));
     TL(e, e->frames, TL_BQ_END, sf);
@@ -637,6 +666,7 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
     }
     MARK();
   }
+  if (e->parent) CK(cudaStreamWaitEvent(st, e->ev_pin, 0));   // first kernel that writes the caller's buffers
   const bool pdl_heads = pdl && e->use_tc == 2;   // only the k_tc2 predecessors are PDL-aware
   if (e->heads2)
     CK(launch_pdl(k_heads2, dim3((S + H2_TS - 1) / H2_TS), dim3(160), H2_SMEM_BYTES, st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
@@ -738,8 +768,9 @@ static int frames_device_io(B200Engine *e, void *d_out, const void *d_in, float 
   int rc = 0;
   // the high-pass prefilter runs up to two frames ahead on its own stream (the input is all there);
   // it is ordered after the caller's stream once, through ev_in
-  rc = cudaEventRecord(e->ev_in, e->stream) != cudaSuccess;
-  for (int t = 0; t < 2 && t < T && !rc; t++) rc = issue_prefilter(e, in + (size_t)t * FRAME_SIZE * esz, t == 0 ? e->ev_in : nullptr, s16);
+  cudaEvent_t ready = e->parent ? e->ev_pin : e->ev_in;
+  if (!e->parent) rc = cudaEventRecord(e->ev_in, e->stream) != cudaSuccess;
+  for (int t = 0; t < 2 && t < T && !rc; t++) rc = issue_prefilter(e, in + (size_t)t * FRAME_SIZE * esz, t == 0 ? ready : nullptr, s16);
   for (int t = 0; t < T && !rc; t++) {
     rc = frame_device_io(e, out + (size_t)t * FRAME_SIZE * esz, in + (size_t)t * FRAME_SIZE * esz, d_vad ? d_vad + t : nullptr, s16);
     if (!rc && t + 2 < T) rc = issue_prefilter(e, in + (size_t)(t + 2) * FRAME_SIZE * esz, nullptr, s16);
@@ -751,13 +782,14 @@ static int frames_device_io(B200Engine *e, void *d_out, const void *d_in, float 
 extern "C" int b200_engine_frames_device(B200Engine *e, void *d_out, const void *d_in, float *d_vad, int T, int s16) {
   if (!e) return -1;
   CK(cudaSetDevice(e->device));
-  return frames_device_io(e, d_out, d_in, d_vad, T, T * FRAME_SIZE, T, s16);
+  if (parent_enter(e) || frames_device_io(e, d_out, d_in, d_vad, T, T * FRAME_SIZE, T, s16)) return -1;
+  return parent_leave(e);
 }
 
 // Host buffers: the T frames move in chunks of `multi_chunk` frames through double-buffered device
 // staging ([S][chunk * 480]), strided 2-D copies on the copy streams, so H2D(c+1), kernels(c) and
 // D2H(c-1) overlap.  Blocking: returns when `out` and `vad` are complete.
-extern "C" int b200_engine_frames_host(B200Engine *e, void *out, const void *in, float *vad, int T, int s16) {
+extern "C" int b200_engine_frames_host_enqueue(B200Engine *e, void *out, const void *in, float *vad, int T, int s16, int pitch_frames) {
   if (!e || !out || !in || T < 1 || e->bq_frames != e->frames) return -1;
   CK(cudaSetDevice(e->device));
   const size_t S = (size_t)e->a.S, esz = s16 ? sizeof(short) : sizeof(float);
@@ -777,7 +809,7 @@ extern "C" int b200_engine_frames_host(B200Engine *e, void *out, const void *in,
     }
     e->multi_bytes = need;
   }
-  const size_t host_pitch = (size_t)T * FRAME_SIZE * esz;
+  const size_t host_pitch = (size_t)pitch_frames * FRAME_SIZE * esz;   // = T for a whole buffer
   int c = 0;
   for (int t0 = 0; t0 < T; t0 += C, c++) {
     const int n = T - t0 < C ? T - t0 : C, slot = c & 1;
@@ -797,10 +829,14 @@ extern "C" int b200_engine_frames_host(B200Engine *e, void *out, const void *in,
     CK(cudaMemcpy2DAsync((char *)out + (size_t)t0 * FRAME_SIZE * esz, host_pitch, e->multi_out[slot], dev_pitch,
                          dev_pitch, S, cudaMemcpyDeviceToHost, e->s_d2h));
     if (vad)
-      CK(cudaMemcpy2DAsync(vad + t0, (size_t)T * sizeof(float), e->multi_vad[slot], (size_t)n * sizeof(float),
+      CK(cudaMemcpy2DAsync(vad + t0, (size_t)pitch_frames * sizeof(float), e->multi_vad[slot], (size_t)n * sizeof(float),
                            (size_t)n * sizeof(float), S, cudaMemcpyDeviceToHost, e->s_d2h));
     CK(cudaEventRecord(e->ev_md2h[slot], e->s_d2h));
   }
+  return 0;
+}
+extern "C" int b200_engine_frames_host(B200Engine *e, void *out, const void *in, float *vad, int T, int s16) {
+  if (b200_engine_frames_host_enqueue(e, out, in, vad, T, s16, T)) return -1;
   return b200_engine_sync(e);
 }
 
@@ -816,9 +852,11 @@ extern "C" int b200_engine_train_features_device(B200Engine *e, float *d_rec, co
                                                  const int *d_band_lp) {
   if (!e || !d_rec || !d_clean || !d_noisy || e->bq_frames != e->frames) return -1;
   CK(cudaSetDevice(e->device));
+  if (parent_enter(e)) return -1;
   const Arena &a = e->a;
   const size_t S = (size_t)a.S;
   cudaStream_t st = e->stream;
+  if (e->parent) CK(cudaStreamWaitEvent(st, e->ev_pin, 0));
   if (!e->train_clean_mem) {
     CK(cudaMalloc(&e->train_clean_mem, S * FRAME_SIZE * sizeof(float)));
     e->allocs.push_back(e->train_clean_mem);
@@ -843,7 +881,7 @@ extern "C" int b200_engine_train_features_device(B200Engine *e, float *d_rec, co
   e->frames++;
   e->bq_frames = e->frames;
   e->host_frames = e->frames;
-  return 0;
+  return parent_leave(e);
 }
 
 extern "C" int b200_engine_train_features_host(B200Engine *e, float *rec, const float *clean, const float *noisy,
@@ -893,6 +931,16 @@ extern "C" int b200_engine_set_stream(B200Engine *e, void *cuda_stream) {
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
   e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+  return 0;
+}
+
+// Lane mode: keep the engine's own stream, but bracket device-pointer calls with `parent` (NULL: off).
+extern "C" int b200_engine_set_parent(B200Engine *e, void *parent_stream) {
+  if (!e) return -1;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  e->stream = e->own_stream;
+  e->parent = (cudaStream_t)parent_stream;
   return 0;
 }
 

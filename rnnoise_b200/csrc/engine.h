@@ -25,6 +25,9 @@ int b200_engine_frame_host_async_s16(B200Engine *e, short *out, const short *in,
 /* T frames per stream in one call; buffers are [nb_streams][T * 480] (vad [nb_streams][T]). */
 int b200_engine_frames_device(B200Engine *e, void *d_out, const void *d_in, float *d_vad, int nb_frames, int s16);
 int b200_engine_frames_host(B200Engine *e, void *out, const void *in, float *vad, int nb_frames, int s16);
+/* same without the final synchronisation; pitch_frames = frames per stream row of the host buffers */
+int b200_engine_frames_host_enqueue(B200Engine *e, void *out, const void *in, float *vad, int nb_frames, int s16, int pitch_frames);
+int b200_engine_set_parent(B200Engine *e, void *parent_stream);
 /* Training-feature records [nb_streams][98] (dump_features.c:466-491); per-stream arrays may be NULL. */
 int b200_engine_train_features_device(B200Engine *e, float *d_rec, const float *d_clean, const float *d_noisy,
                                       const float *d_vad_target, const int *d_noise_free, const int *d_lowpass, const int *d_band_lp);

@@ -23,10 +23,20 @@ struct RNNModel {
   int parsed;
 };
 
+/* A batch is 1..B200_MAX_LANES engines ("lanes"), each owning a contiguous range of streams and its own
+ * CUDA streams.  Streams never interact, so lanes are independent; running them side by side fills the GPU
+ * better when one lane's grids are only a wave or two of CTAs (measured on B200 with two lanes against one,
+ * tools/lanes_experiment.py: +10 % at 1024 streams, +5 % at 2048, +13 % at 3072, +10 % at 4096, +3 % at 6144,
+ * +2 % at 8192, -1 % at 16384).
+ * $RNNOISE_B200_LANES overrides the choice. */
+#define B200_MAX_LANES 4
 struct RNNoiseBatch {
-  B200Engine *engine;
+  int lanes;
+  int first[B200_MAX_LANES + 1]; /* lane l owns streams [first[l], first[l + 1]) */
+  B200Engine *engine[B200_MAX_LANES];
   int nb_streams;
 };
+#define LANE_COUNT(b, l) ((b)->first[(l) + 1] - (b)->first[l])
 
 /* A single-stream state is a handle onto a private batch of one stream. */
 struct DenoiseState {
@@ -93,92 +103,208 @@ void rnnoise_model_free(RNNModel *model) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
+static int default_lanes(int nb_streams) {
+  const char *env = getenv("RNNOISE_B200_LANES");
+  int lanes;
+  if (env && atoi(env) > 0) lanes = atoi(env);
+  else lanes = (nb_streams >= 1024 && nb_streams < 12288) ? 2 : 1;
+  if (lanes > B200_MAX_LANES) lanes = B200_MAX_LANES;
+  while (lanes > 1 && nb_streams / lanes < 128) lanes--;
+  return lanes;
+}
+
 RNNoiseBatch *rnnoise_batch_create(RNNModel *model, int nb_streams, int device) {
   RNNoiseBatch *b;
+  int l, per;
   if (!model || !model->parsed || nb_streams < 1 || device < 0) return NULL;
   b = (RNNoiseBatch *)calloc(1, sizeof(*b));
   if (!b) return NULL;
-  b->engine = b200_engine_create(&model->host, nb_streams, device);
-  if (!b->engine) {
-    free(b);
-    return NULL;
-  }
+  b->lanes = default_lanes(nb_streams);
   b->nb_streams = nb_streams;
+  /* lane sizes: multiples of the 128-stream tensor-core tile, the last lane takes the remainder */
+  per = ((nb_streams + b->lanes - 1) / b->lanes + 127) / 128 * 128;
+  for (l = 0; l <= b->lanes; l++) b->first[l] = l * per < nb_streams ? l * per : nb_streams;
+  b->first[b->lanes] = nb_streams;
+  while (b->lanes > 1 && LANE_COUNT(b, b->lanes - 1) <= 0) b->lanes--;
+  for (l = 0; l < b->lanes; l++) {
+    b->engine[l] = b200_engine_create(&model->host, LANE_COUNT(b, l), device);
+    if (!b->engine[l]) {
+      rnnoise_batch_destroy(b);
+      return NULL;
+    }
+  }
   return b;
 }
 
 void rnnoise_batch_destroy(RNNoiseBatch *b) {
+  int l;
   if (!b) return;
-  b200_engine_destroy(b->engine);
+  for (l = 0; l < B200_MAX_LANES; l++)
+    if (b->engine[l]) b200_engine_destroy(b->engine[l]);
   free(b);
 }
 
 int rnnoise_batch_get_streams(const RNNoiseBatch *b) { return b ? b->nb_streams : 0; }
+int rnnoise_batch_get_lanes(const RNNoiseBatch *b) { return b ? b->lanes : 0; }
 
-int rnnoise_process_frame_batch(RNNoiseBatch *b, float *out, const float *in, float *vad) {
-  if (!b || !out || !in) return -1;
-  return b200_engine_frame_host(b->engine, out, in, vad);
+/* every per-frame entry point fans out over the lanes with the lane's offset into the caller's buffers */
+#define PCM_AT(p, b, l, T, type) ((type *)(p) + (size_t)(b)->first[l] * (T) * FRAME_SIZE)
+#define VAD_AT(p, b, l, T) ((p) ? (p) + (size_t)(b)->first[l] * (T) : NULL)
+#define ARR_AT(p, b, l) ((p) ? (p) + (b)->first[l] : NULL)
+#define FOR_LANES(b, l) for (l = 0; l < (b)->lanes; l++)
+
+int rnnoise_batch_sync(RNNoiseBatch *b) {
+  int l, rc = 0;
+  if (!b) return -1;
+  FOR_LANES(b, l) rc |= b200_engine_sync(b->engine[l]);
+  return rc ? -1 : 0;
 }
 
 int rnnoise_process_frame_batch_async(RNNoiseBatch *b, float *out, const float *in, float *vad) {
+  int l;
   if (!b || !out || !in) return -1;
-  return b200_engine_frame_host_async(b->engine, out, in, vad);
+  FOR_LANES(b, l)
+    if (b200_engine_frame_host_async(b->engine[l], PCM_AT(out, b, l, 1, float), PCM_AT(in, b, l, 1, const float), VAD_AT(vad, b, l, 1))) return -1;
+  return 0;
 }
-
-int rnnoise_process_frame_batch_device(RNNoiseBatch *b, float *d_out, const float *d_in, float *d_vad) {
-  if (!b || !d_out || !d_in) return -1;
-  return b200_engine_frame_device(b->engine, d_out, d_in, d_vad);
-}
-
-int rnnoise_process_frame_batch_s16(RNNoiseBatch *b, short *out, const short *in, float *vad) {
-  if (!b || !out || !in) return -1;
-  if (b200_engine_frame_host_async_s16(b->engine, out, in, vad) != 0) return -1;
-  return b200_engine_sync(b->engine);
+int rnnoise_process_frame_batch(RNNoiseBatch *b, float *out, const float *in, float *vad) {
+  if (rnnoise_process_frame_batch_async(b, out, in, vad) != 0) return -1;
+  return rnnoise_batch_sync(b);
 }
 int rnnoise_process_frame_batch_s16_async(RNNoiseBatch *b, short *out, const short *in, float *vad) {
+  int l;
   if (!b || !out || !in) return -1;
-  return b200_engine_frame_host_async_s16(b->engine, out, in, vad);
+  FOR_LANES(b, l)
+    if (b200_engine_frame_host_async_s16(b->engine[l], PCM_AT(out, b, l, 1, short), PCM_AT(in, b, l, 1, const short), VAD_AT(vad, b, l, 1))) return -1;
+  return 0;
+}
+int rnnoise_process_frame_batch_s16(RNNoiseBatch *b, short *out, const short *in, float *vad) {
+  if (rnnoise_process_frame_batch_s16_async(b, out, in, vad) != 0) return -1;
+  return rnnoise_batch_sync(b);
+}
+int rnnoise_process_frame_batch_device(RNNoiseBatch *b, float *d_out, const float *d_in, float *d_vad) {
+  int l;
+  if (!b || !d_out || !d_in) return -1;
+  FOR_LANES(b, l)
+    if (b200_engine_frame_device(b->engine[l], PCM_AT(d_out, b, l, 1, float), PCM_AT(d_in, b, l, 1, const float), VAD_AT(d_vad, b, l, 1))) return -1;
+  return 0;
 }
 int rnnoise_process_frame_batch_device_s16(RNNoiseBatch *b, short *d_out, const short *d_in, float *d_vad) {
+  int l;
   if (!b || !d_out || !d_in) return -1;
-  return b200_engine_frame_device_s16(b->engine, d_out, d_in, d_vad);
+  FOR_LANES(b, l)
+    if (b200_engine_frame_device_s16(b->engine[l], PCM_AT(d_out, b, l, 1, short), PCM_AT(d_in, b, l, 1, const short), VAD_AT(d_vad, b, l, 1))) return -1;
+  return 0;
+}
+static int frames_host(RNNoiseBatch *b, void *out, const void *in, float *vad, int T, int s16) {
+  int l;
+  if (!b || !out || !in || T < 1) return -1;
+  FOR_LANES(b, l) {
+    void *o = s16 ? (void *)PCM_AT(out, b, l, T, short) : (void *)PCM_AT(out, b, l, T, float);
+    const void *i = s16 ? (const void *)PCM_AT(in, b, l, T, const short) : (const void *)PCM_AT(in, b, l, T, const float);
+    if (b200_engine_frames_host_enqueue(b->engine[l], o, i, VAD_AT(vad, b, l, T), T, s16, T)) return -1;
+  }
+  return rnnoise_batch_sync(b);
 }
 int rnnoise_process_frames_batch(RNNoiseBatch *b, float *out, const float *in, float *vad, int nb_frames) {
-  return b ? b200_engine_frames_host(b->engine, out, in, vad, nb_frames, 0) : -1;
+  return frames_host(b, out, in, vad, nb_frames, 0);
 }
 int rnnoise_process_frames_batch_s16(RNNoiseBatch *b, short *out, const short *in, float *vad, int nb_frames) {
-  return b ? b200_engine_frames_host(b->engine, out, in, vad, nb_frames, 1) : -1;
+  return frames_host(b, out, in, vad, nb_frames, 1);
 }
 int rnnoise_process_frames_batch_device(RNNoiseBatch *b, float *d_out, const float *d_in, float *d_vad, int nb_frames) {
-  return b ? b200_engine_frames_device(b->engine, d_out, d_in, d_vad, nb_frames, 0) : -1;
+  int l;
+  if (!b || !d_out || !d_in || nb_frames < 1) return -1;
+  FOR_LANES(b, l)
+    if (b200_engine_frames_device(b->engine[l], PCM_AT(d_out, b, l, nb_frames, float), PCM_AT(d_in, b, l, nb_frames, const float),
+                                  VAD_AT(d_vad, b, l, nb_frames), nb_frames, 0)) return -1;
+  return 0;
 }
 int rnnoise_process_frames_batch_device_s16(RNNoiseBatch *b, short *d_out, const short *d_in, float *d_vad, int nb_frames) {
-  return b ? b200_engine_frames_device(b->engine, d_out, d_in, d_vad, nb_frames, 1) : -1;
+  int l;
+  if (!b || !d_out || !d_in || nb_frames < 1) return -1;
+  FOR_LANES(b, l)
+    if (b200_engine_frames_device(b->engine[l], PCM_AT(d_out, b, l, nb_frames, short), PCM_AT(d_in, b, l, nb_frames, const short),
+                                  VAD_AT(d_vad, b, l, nb_frames), nb_frames, 1)) return -1;
+  return 0;
 }
 int rnnoise_batch_train_features(RNNoiseBatch *b, float *rec, const float *clean, const float *noisy, const float *vad_target,
                                  const int *noise_free, const int *lowpass, const int *band_lp) {
-  return b ? b200_engine_train_features_host(b->engine, rec, clean, noisy, vad_target, noise_free, lowpass, band_lp) : -1;
+  int l;
+  if (!b || !rec || !clean || !noisy) return -1;
+  FOR_LANES(b, l)
+    if (b200_engine_train_features_host(b->engine[l], rec + (size_t)b->first[l] * RNNOISE_TRAIN_RECORD, PCM_AT(clean, b, l, 1, const float),
+                                        PCM_AT(noisy, b, l, 1, const float), ARR_AT(vad_target, b, l), ARR_AT(noise_free, b, l),
+                                        ARR_AT(lowpass, b, l), ARR_AT(band_lp, b, l))) return -1;
+  return 0;
 }
 int rnnoise_batch_train_features_device(RNNoiseBatch *b, float *d_rec, const float *d_clean, const float *d_noisy,
                                         const float *d_vad_target, const int *d_noise_free, const int *d_lowpass, const int *d_band_lp) {
-  return b ? b200_engine_train_features_device(b->engine, d_rec, d_clean, d_noisy, d_vad_target, d_noise_free, d_lowpass, d_band_lp) : -1;
+  int l;
+  if (!b || !d_rec || !d_clean || !d_noisy) return -1;
+  FOR_LANES(b, l)
+    if (b200_engine_train_features_device(b->engine[l], d_rec + (size_t)b->first[l] * RNNOISE_TRAIN_RECORD, PCM_AT(d_clean, b, l, 1, const float),
+                                          PCM_AT(d_noisy, b, l, 1, const float), ARR_AT(d_vad_target, b, l), ARR_AT(d_noise_free, b, l),
+                                          ARR_AT(d_lowpass, b, l), ARR_AT(d_band_lp, b, l))) return -1;
+  return 0;
 }
 int rnnoise_batch_timeline_read(RNNoiseBatch *b, float *ms, int capacity) {
-  return b ? b200_engine_timeline_read(b->engine, ms, capacity) : -1;
+  return b ? b200_engine_timeline_read(b->engine[0], ms, capacity) : -1;   /* first lane */
 }
 int rnnoise_batch_prefilter_device(RNNoiseBatch *b, const float *d_in_next) {
-  return b && d_in_next ? b200_engine_prefilter_device(b->engine, d_in_next) : -1;
+  int l;
+  if (!b || !d_in_next) return -1;
+  FOR_LANES(b, l)
+    if (b200_engine_prefilter_device(b->engine[l], PCM_AT(d_in_next, b, l, 1, const float))) return -1;
+  return 0;
 }
-int rnnoise_batch_sync(RNNoiseBatch *b) { return b ? b200_engine_sync(b->engine) : -1; }
-int rnnoise_batch_set_stream(RNNoiseBatch *b, void *s) { return b ? b200_engine_set_stream(b->engine, s) : -1; }
-int rnnoise_batch_reset_stream(RNNoiseBatch *b, int s) { return b ? b200_engine_reset_stream(b->engine, s) : -1; }
-int rnnoise_batch_launches_per_frame(const RNNoiseBatch *b) { return b ? b200_engine_launches_per_frame(b->engine) : 0; }
-int rnnoise_batch_profile(RNNoiseBatch *b, int enable) { return b ? b200_engine_profile(b->engine, enable) : -1; }
+/* One lane: the engine runs on the caller's stream itself.  Several lanes: every lane keeps its private
+ * streams and brackets each device-pointer call with the caller's stream (engine.cu: parent_enter/leave). */
+int rnnoise_batch_set_stream(RNNoiseBatch *b, void *s) {
+  int l;
+  if (!b) return -1;
+  if (b->lanes == 1) return b200_engine_set_stream(b->engine[0], s);
+  FOR_LANES(b, l)
+    if (b200_engine_set_parent(b->engine[l], s)) return -1;
+  return 0;
+}
+static int lane_of(const RNNoiseBatch *b, int s) {
+  int l;
+  for (l = 0; l < b->lanes; l++)
+    if (s < b->first[l + 1]) return l;
+  return b->lanes - 1;
+}
+int rnnoise_batch_reset_stream(RNNoiseBatch *b, int s) {
+  int l;
+  if (!b || s < 0 || s >= b->nb_streams) return -1;
+  l = lane_of(b, s);
+  return b200_engine_reset_stream(b->engine[l], s - b->first[l]);
+}
+int rnnoise_batch_launches_per_frame(const RNNoiseBatch *b) { return b ? b->lanes * b200_engine_launches_per_frame(b->engine[0]) : 0; }
+int rnnoise_batch_profile(RNNoiseBatch *b, int enable) {
+  int l, rc = 0;
+  if (!b) return -1;
+  FOR_LANES(b, l) rc |= b200_engine_profile(b->engine[l], enable);
+  return rc ? -1 : 0;
+}
+/* per-kernel times are summed over the lanes (in profiling mode the lanes run one after the other) */
 int rnnoise_batch_profile_read(RNNoiseBatch *b, float *ms, const char **names, int capacity, int *frames) {
-  return b ? b200_engine_profile_read(b->engine, ms, names, capacity, frames) : -1;
+  float lane_ms[32];
+  int l, i, n = 0;
+  if (!b || !ms) return -1;
+  FOR_LANES(b, l) {
+    n = b200_engine_profile_read(b->engine[l], l == 0 ? ms : lane_ms, names, capacity < 32 ? capacity : 32, frames);
+    if (n < 0) return -1;
+    if (l > 0)
+      for (i = 0; i < n; i++) ms[i] += lane_ms[i];
+  }
+  return n;
 }
 int rnnoise_batch_debug_read(RNNoiseBatch *b, int what, int stream, float *dst, int capacity) {
-  return b ? b200_engine_debug_read(b->engine, what, stream, dst, capacity) : -1;
+  int l;
+  if (!b || stream < 0 || stream >= b->nb_streams) return -1;
+  l = lane_of(b, stream);
+  return b200_engine_debug_read(b->engine[l], what, stream - b->first[l], dst, capacity);
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -402,3 +402,48 @@ def test_train_features_match_training_reference_goldens(rb, models_dir):
     for x in (a, b, c):
         x.destroy()
     model.free()
+
+
+@pytest.mark.parametrize("S,lanes,expect", [(300, "2", 2), (600, "4", 3)])
+def test_lanes_do_not_change_results(rb, models_dir, S, lanes, expect, monkeypatch):
+    """A batch split into lanes (sub-batches on their own CUDA streams) must be indistinguishable from a
+    single-lane batch: host float / int16 / multi-frame calls, the device-pointer call on a caller stream,
+    per-stream reset and debug reads (routed to the owning lane).  Lanes are whole 128-stream tiles except
+    the last: 300 streams -> 256 + 44; 600 streams asked for 4 lanes -> 256 + 256 + 88 (three lanes)."""
+    import torch
+    model = rb.Model(os.path.join(models_dir, "default.bin"))
+    frames = 8
+    monkeypatch.setenv("RNNOISE_B200_LANES", "1")
+    ref, ref16 = rb.Batch(model, S), rb.Batch(model, S)
+    monkeypatch.setenv("RNNOISE_B200_LANES", lanes)
+    a, a16, dev, multi = (rb.Batch(model, S) for _ in range(4))
+    assert ref.lanes == 1 and a.lanes == expect
+    pcm = batch_pcm(S, frames)
+    st = torch.cuda.Stream()
+    dev.set_stream(st.cuda_stream)
+    outs = []
+    for f in range(frames):
+        if f == 4:
+            for b in (ref, a, dev):
+                b.reset_stream(7); b.reset_stream(S - 1)
+        ro, rv = ref.process(pcm[f]); outs.append((ro, rv))
+        o, v = a.process(pcm[f])
+        assert np.array_equal(bits(o), bits(ro)) and np.array_equal(bits(v), bits(rv)), f
+        for s in (0, 127, 128, 255, 256, S - 1):
+            for k in ("features", "gains", "gru3"):
+                assert np.array_equal(bits(a.debug(k, s)), bits(ref.debug(k, s))), (k, s, f)
+        r16, rv16 = ref16.process_s16(pcm[f].astype(np.int16)); o16, v16 = a16.process_s16(pcm[f].astype(np.int16))
+        assert np.array_equal(r16, o16) and np.array_equal(bits(rv16), bits(v16)), f
+        with torch.cuda.stream(st):
+            d = torch.from_numpy(pcm[f]).cuda(non_blocking=False); dv = torch.empty(S, device="cuda")
+            dev.process_device(d.data_ptr(), d.data_ptr(), dv.data_ptr())
+            got, gotv = d.cpu().numpy(), dv.cpu().numpy()     # ordered on the caller's stream only
+        assert np.array_equal(bits(got), bits(ro)) and np.array_equal(bits(gotv), bits(rv)), f
+    # multi-frame call over the first 4 frames (before the resets)
+    by_stream = np.ascontiguousarray(pcm[:4].transpose(1, 0, 2).reshape(S, 4 * 480))
+    mo, mv = multi.process_frames(by_stream)
+    want = np.concatenate([outs[f][0] for f in range(4)], axis=1); wantv = np.stack([outs[f][1] for f in range(4)], axis=1)
+    assert np.array_equal(bits(mo), bits(want)) and np.array_equal(bits(mv), bits(wantv))
+    for b in (ref, ref16, a, a16, dev, multi):
+        b.destroy()
+    model.free()
