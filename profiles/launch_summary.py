@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Summarise an ncu launch list (`--metrics gpu__time_duration.sum --csv`): per-kernel mean duration
-and share of the step.  usage: python profiles/launch_summary.py launches.csv"""
+and share of the step.  usage: python profiles/launch_summary.py launches.csv [lanes]
+(lanes = sub-batches per step: every kernel is launched `lanes` times per step, the GRU kernel 3 x lanes)"""
 import collections
 import csv
 import sys
@@ -16,7 +17,8 @@ for r in rows[hdr + 1:]:
     v = float(r[vi].replace(',', ''))
     v = v / 1e3 if r[ui] == 'ns' else v * 1e3 if r[ui] == 'ms' else v
     d.setdefault(r[ki].split('(')[0], []).append(v)
-per_step = {k: sum(v) / len(v) * (3 if k in ('k_gru', 'k_gru_tc', 'void k_tc2<1>') else 1) for k, v in d.items() if 'k_' in k}
+lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+per_step = {k: sum(v) / len(v) * lanes * (3 if k in ('k_gru', 'k_gru_tc', 'void k_tc2<1>') else 1) for k, v in d.items() if 'k_' in k}
 tot = sum(per_step.values())
 print(f"{'kernel':16s} {'launches':>8s} {'mean us':>10s} {'us/step':>10s} {'share':>7s}")
 for k, v in d.items():
