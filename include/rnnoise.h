@@ -173,7 +173,9 @@ RNNOISE_EXPORT int rnnoise_batch_sync(RNNoiseBatch *b);
  *  stream waits for the call's completion, so the call still behaves like work on that one stream. */
 RNNOISE_EXPORT int rnnoise_batch_set_stream(RNNoiseBatch *b, void *cuda_stream);
 
-/** Re-zero the state of one stream (what rnnoise_init() does to a DenoiseState).  0 / -1. */
+/** Re-zero the state of one stream (what rnnoise_init() does to a DenoiseState): ordered after every frame
+ *  already handed to the batch, synchronises.  Fails (-1) while a rnnoise_batch_prefilter_device() hint is
+ *  pending, because that hint has already filtered the next frame with the old state.  0 / -1. */
 RNNOISE_EXPORT int rnnoise_batch_reset_stream(RNNoiseBatch *b, int stream);
 
 /** Number of kernel launches one rnnoise_process_frame_batch_device() call issues. */

@@ -987,6 +987,7 @@ extern "C" int b200_engine_timeline_read(B200Engine *e, float *dst, int capacity
 
 extern "C" int b200_engine_reset_stream(B200Engine *e, int s) {
   if (!e || s < 0 || s >= e->a.S) return -1;
+  if (e->bq_frames != e->frames) return -1;   // a prefilter hint already consumed the old filter state for the next frame
   CK(cudaSetDevice(e->device));
   const Arena &a = e->a;
   const size_t S = a.S;
