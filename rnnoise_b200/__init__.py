@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librnnoise_b200.so")
+# $RNNOISE_B200_LIB_PATH selects another build of the library (A/B measurements of two source states)
+LIB_PATH = os.environ.get("RNNOISE_B200_LIB_PATH") or os.path.join(_HERE, "librnnoise_b200.so")
 FRAME_SIZE = 480
 
 # debug-read selectors (include/rnnoise.h)
