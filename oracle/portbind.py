@@ -64,6 +64,9 @@ class Port:
         L.rp_remove_doubling.restype = C.c_float
         L.rp_remove_doubling.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int, C.c_float]
         assert L.rp_state_size() == C.sizeof(State)
+        L.rp_train_frame.restype = C.c_int
+        L.rp_train_frame.argtypes = [C.POINTER(State), C.POINTER(State), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
+                                     C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
         self.model = None
         if model_path:
             self.model = L.rp_model_from_file(model_path.encode())
@@ -74,6 +77,14 @@ class Port:
 
     def destroy(self, st):
         self.lib.rp_state_destroy(st)
+
+    def train_frame(self, clean_st, noisy_st, clean, noisy, vad_target=0.0, noise_free=0, lowpass=481, band_lp=32):
+        """Training-feature record of one frame (dump_features.c:466-491 semantics) -> (rec[98], quiet flag)."""
+        c = np.ascontiguousarray(clean, np.float32); n = np.ascontiguousarray(noisy, np.float32)
+        rec = np.zeros(98, np.float32)
+        q = self.lib.rp_train_frame(clean_st, noisy_st, fptr(c), fptr(n), float(vad_target), int(noise_free), int(lowpass),
+                                    int(band_lp), fptr(rec))
+        return rec, q
 
     def process_frame(self, st, x, trace=True):
         x = np.ascontiguousarray(x, np.float32)

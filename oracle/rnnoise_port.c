@@ -509,6 +509,73 @@ int rp_frame_features(rp_state *st, rp_cpx *X, rp_cpx *P, float *Ex, float *Ep, 
   return 0;
 }
 
+/* The frame loop of the reference's training-data tool (src/dump_features.c:466-491, a -DTRAINING=1 build of
+ * denoise.c): rnn_frame_analysis on the clean state, rnn_compute_frame_features on the noisy state with the
+ * TRAINING differences -- X and Y low-passed at `lowpass` bins (denoise.c:340-343), no silence short-circuit
+ * (:389), return value E < 0.1 (:397) -- then the ideal band gains with their masks (dump_features.c:471-478).
+ * rec[98] = features | g | vad_target.  Pinned against oracle/_ref/librnnoise_ref_training.so by
+ * tests/test_oracle_port.py::test_port_training_frame_matches_reference_training_build. */
+int rp_train_frame(rp_state *clean_st, rp_state *noisy_st, const float *clean, const float *noisy, float vad_target,
+                   int noise_free, int lowpass, int band_lp, float *rec) {
+  float w[RP_WINDOW], Ex[RP_BANDS], Ey[RP_BANDS], Ep[RP_BANDS], Exp[RP_BANDS];
+  rp_cpx X[RP_FREQ], Y[RP_FREQ], P[RP_FREQ];
+  float *features = rec, *g = rec + RP_FEATURES;
+  /* clean frame: analysis only */
+  memcpy(w, clean_st->analysis_mem, sizeof(float) * RP_FRAME);
+  memcpy(w + RP_FRAME, clean, sizeof(float) * RP_FRAME);
+  memcpy(clean_st->analysis_mem, clean, sizeof(float) * RP_FRAME);
+  window_fft(Y, w);
+  for (int i = lowpass; i < RP_FREQ; i++) Y[i].r = Y[i].i = 0;
+  rp_band_energy(Ey, Y);
+  /* noisy frame: the feature path of rp_frame_features with the TRAINING differences */
+  rp_state *st = noisy_st;
+  memcpy(w, st->analysis_mem, sizeof(float) * RP_FRAME);
+  memcpy(w + RP_FRAME, noisy, sizeof(float) * RP_FRAME);
+  memcpy(st->analysis_mem, noisy, sizeof(float) * RP_FRAME);
+  window_fft(X, w);
+  for (int i = lowpass; i < RP_FREQ; i++) X[i].r = X[i].i = 0;
+  rp_band_energy(Ex, X);
+  memmove(st->pitch_buf, st->pitch_buf + RP_FRAME, sizeof(float) * (RP_PITCH_BUF - RP_FRAME));
+  memcpy(st->pitch_buf + RP_PITCH_BUF - RP_FRAME, noisy, sizeof(float) * RP_FRAME);
+  float lp[RP_PITCH_BUF >> 1];
+  rp_pitch_downsample(st->pitch_buf, lp);
+  int pitch_index = RP_PITCH_MAX - rp_pitch_search(lp);
+  float gain = rp_remove_doubling(lp, &pitch_index, st->last_period, st->last_gain);
+  st->last_period = pitch_index;
+  st->last_gain = gain;
+  for (int i = 0; i < RP_WINDOW; i++) w[i] = st->pitch_buf[RP_PITCH_BUF - RP_WINDOW - pitch_index + i];
+  window_fft(P, w);
+  rp_band_energy(Ep, P);
+  rp_band_corr(Exp, X, P);
+  for (int i = 0; i < RP_BANDS; i++) Exp[i] = (float)(Exp[i] / sqrt(.001 + Ex[i] * Ep[i]));
+  rp_dct(&features[RP_BANDS], Exp);
+  features[2 * RP_BANDS] = (float)(.01 * (pitch_index - 300));
+  float logMax = -2, follow = -2, E = 0, Ly[RP_BANDS];
+  for (int i = 0; i < RP_BANDS; i++) {
+    float ly = (float)log10(1e-2 + Ex[i]);
+    double f15 = follow - 1.5;
+    double m1 = f15 > ly ? f15 : ly;
+    float lm7 = logMax - 7;
+    Ly[i] = (float)(lm7 > m1 ? lm7 : m1);
+    logMax = logMax > Ly[i] ? logMax : Ly[i];
+    follow = (float)(f15 > Ly[i] ? f15 : Ly[i]);
+    E += Ex[i];
+  }
+  rp_dct(features, Ly);
+  features[0] -= 12;
+  features[1] -= 4;
+  const int quiet = E < 0.1;
+  for (int i = 0; i < RP_BANDS; i++) {
+    g[i] = (float)sqrt((Ey[i] + 1e-3) / (Ex[i] + 1e-3));
+    if (g[i] > 1) g[i] = 1;
+    if (quiet || i > band_lp) g[i] = -1;
+    if (Ey[i] < 5e-2 && Ex[i] < 5e-2) g[i] = -1;
+    if (vad_target == 0 && noise_free) g[i] = -1;
+  }
+  rec[RP_FEATURES + RP_BANDS] = vad_target;
+  return quiet;
+}
+
 /* rnn_pitch_filter, denoise.c:421-455 */
 void rp_pitch_filter(rp_cpx *X, const rp_cpx *P, const float *Ex, const float *Ep, const float *Exp,
                      const float *g) {

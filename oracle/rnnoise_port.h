@@ -97,6 +97,9 @@ int rp_pitch_search(const float *lp864);               /* returns the lag in [0,
 float rp_remove_doubling(const float *lp864, int *T0, int prev_period, float prev_gain);
 int rp_frame_features(rp_state *st, rp_cpx *X, rp_cpx *P, float *Ex, float *Ep, float *Exp,
                       float *features, const float *xb);
+/* dump_features.c:466-491 frame loop with -DTRAINING=1 semantics; rec[98]; returns the quiet flag */
+int rp_train_frame(rp_state *clean_st, rp_state *noisy_st, const float *clean, const float *noisy, float vad_target,
+                   int noise_free, int lowpass, int band_lp, float *rec);
 void rp_pitch_filter(rp_cpx *X, const rp_cpx *P, const float *Ex, const float *Ep, const float *Exp,
                      const float *g);
 

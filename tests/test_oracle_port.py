@@ -113,6 +113,31 @@ def test_port_vs_live_reference_dsp_bit_exact(models_dir):
         assert np.abs(a["out"] - b["out"]).max() < 3.0
 
 
+def test_port_training_frame_matches_reference_training_build():
+    """rp_train_frame (TRAINING semantics of the feature path + ideal gains) against the unmodified reference
+    built with -DTRAINING=1 (oracle/_ref/librnnoise_ref_training.so) and against the committed goldens."""
+    from oracle import trainbind
+    from rnnoise_b200.synth_pcm import train_pair, train_params
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_train.npz"))
+    streams, frames = [int(s) for s in g["streams"]], int(g["frames"])
+    port = Port(None)
+    for q, s in enumerate(streams):
+        clean, noisy = train_pair(s, frames)
+        lp, blp, nf = train_params(s)
+        cs, ns = port.create(), port.create()
+        live = trainbind.RefTrain() if trainbind.available() else None
+        for f in range(frames):
+            vt = float((f // 7 + s) % 2)
+            rec, quiet = port.train_frame(cs, ns, clean[f], noisy[f], vt, nf, lp, blp)
+            assert rec.tobytes() == g["rec"][f, q].tobytes() and quiet == int(g["quiet"][f, q]), (s, f)
+            if live:
+                want, wq, _ = live.frame(clean[f], noisy[f], vt, nf, lp, blp)
+                assert rec.tobytes() == want.tobytes() and quiet == wq, (s, f)
+        port.destroy(cs); port.destroy(ns)
+        if live:
+            live.close()
+
+
 def test_port_rejects_malformed_blobs(models_dir):
     port = Port()
     blob = open(os.path.join(models_dir, "default.bin"), "rb").read()
