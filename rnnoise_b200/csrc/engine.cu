@@ -768,9 +768,11 @@ static int frames_device_io(B200Engine *e, void *d_out, const void *d_in, float 
   int rc = 0;
   // the high-pass prefilter runs up to two frames ahead on its own stream (the input is all there);
   // it is ordered after the caller's stream once, through ev_in
-  cudaEvent_t ready = e->parent ? e->ev_pin : e->ev_in;
-  if (!e->parent) rc = cudaEventRecord(e->ev_in, e->stream) != cudaSuccess;
-  for (int t = 0; t < 2 && t < T && !rc; t++) rc = issue_prefilter(e, in + (size_t)t * FRAME_SIZE * esz, t == 0 ? ready : nullptr, s16);
+  // (the engine's own stream may itself be waiting for a staging copy of the host path: always order after it;
+  //  with a parent stream, additionally after the caller's stream)
+  rc = cudaEventRecord(e->ev_in, e->stream) != cudaSuccess;
+  if (!rc && e->parent) rc = cudaStreamWaitEvent(e->s_bq, e->ev_pin, 0) != cudaSuccess;
+  for (int t = 0; t < 2 && t < T && !rc; t++) rc = issue_prefilter(e, in + (size_t)t * FRAME_SIZE * esz, t == 0 ? e->ev_in : nullptr, s16);
   for (int t = 0; t < T && !rc; t++) {
     rc = frame_device_io(e, out + (size_t)t * FRAME_SIZE * esz, in + (size_t)t * FRAME_SIZE * esz, d_vad ? d_vad + t : nullptr, s16);
     if (!rc && t + 2 < T) rc = issue_prefilter(e, in + (size_t)(t + 2) * FRAME_SIZE * esz, nullptr, s16);
