@@ -84,13 +84,17 @@ int b200_host_model_parse(B200HostModel *m, const void *blob, int len) {
   memset(m, 0, sizeof(*m));
   if (!blob) return -1;
   while (len > 0) {
-    const Head *h = (const Head *)p;
+    Head h;   /* copied out: a corrupted block_size must not turn into a misaligned struct access */
     if (len < BLOCK) return -1;
-    if (h->block_size < h->size || h->block_size > len - BLOCK) return -1;
-    if (h->name[sizeof(h->name) - 1] != 0 || h->size <= 0 || n >= MAX_ARRAYS) return -1;
-    arr[n].name = h->name; arr[n].size = h->size; arr[n].data = p + BLOCK; n++;
-    p += BLOCK + h->block_size;
-    len -= BLOCK + h->block_size;
+    memcpy(&h, p, sizeof(h));
+    if (h.block_size < h.size || h.block_size > len - BLOCK) return -1;
+    /* the writer pads records to 64 bytes (write_weights.c:57); anything not a multiple of 4 would leave the
+       following float / int arrays misaligned, which no valid blob does */
+    if (h.block_size & 3) return -1;
+    if (h.name[sizeof(h.name) - 1] != 0 || h.size <= 0 || n >= MAX_ARRAYS) return -1;
+    arr[n].name = ((const Head *)p)->name; arr[n].size = h.size; arr[n].data = p + BLOCK; n++;
+    p += BLOCK + h.block_size;
+    len -= BLOCK + h.block_size;
   }
   const Arr *c1 = lookup(arr, n, "conv1", "_bias"), *g1 = lookup(arr, n, "gru1_recurrent", "_bias");
   if (!c1 || !g1 || (c1->size & 3) || g1->size % 12) return -1;
