@@ -243,7 +243,7 @@ def main():
 
     # ---- end-to-end through the host-buffer C-ABI call (e2e) ----
     # rnnoise_process_frame_batch_async(): every step copies that step's PCM from pinned host memory
-    # to the device, runs the 9 kernels and copies PCM + VAD back to pinned host memory; consecutive
+    # to the device, runs the frame pipeline (10 kernels per lane) and copies PCM + VAD back to pinned host memory; consecutive
     # steps overlap on three streams.  Timed by wall clock around a fully synchronised region (covers
     # the last D2H), distinct output buffers per in-flight step.
     NBUF = 4
