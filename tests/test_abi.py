@@ -97,3 +97,29 @@ def test_reference_demo_links_unchanged(tmp_path):
                         rnnoise_b200.LIB_PATH, "-Wl,-rpath," + os.path.dirname(rnnoise_b200.LIB_PATH)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_batch_demo_compiles_links_and_fails_cleanly_without_gpu(tmp_path, models_dir):
+    """examples/rnnoise_batch_demo.c (multi-file denoiser over the multi-frame int16 call) builds against the
+    public header + library with a plain C compiler; without a GPU it must stop with the no-CPU-path message,
+    not crash."""
+    import subprocess
+    import numpy as np
+    import rnnoise_b200
+    exe = str(tmp_path / "rnnoise_batch_demo")
+    r = subprocess.run(["gcc", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "rnnoise_batch_demo.c"),
+                        "-o", exe, rnnoise_b200.LIB_PATH, "-Wl,-rpath," + os.path.dirname(rnnoise_b200.LIB_PATH)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = str(tmp_path / "a.raw")
+    (np.arange(2000) % 100).astype(np.int16).tofile(raw)
+    r = subprocess.run([exe, os.path.join(models_dir, "tiny.bin"), raw], capture_output=True, text=True)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        assert r.returncode == 0 and os.path.getsize(raw + ".denoised") == 5 * 480 * 2, r.stderr
+    else:
+        assert r.returncode == 1 and "no CPU path" in r.stderr, (r.returncode, r.stderr)
