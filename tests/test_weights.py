@@ -61,3 +61,25 @@ def test_exporter_matches_reference_pipeline_on_seeded_models(name, tmp_path):
     ref = open(os.path.join(MODELS, name + ".bin"), "rb").read()
     _diff(blob, ref)
     assert blob == ref
+
+
+def test_exported_blob_loads_in_the_product_parser_and_port(tmp_path):
+    """A blob written by the exporter is accepted by the C loader of the product (dims inferred from array
+    sizes) and by the oracle port; a blob with a perturbed weight still parses (weights are data), one with a
+    broken sparse index does not."""
+    import ctypes as C
+    import rnnoise_b200
+    from oracle.portbind import Port
+    out = str(tmp_path / "m.bin")
+    blob = weights.export_checkpoint(os.path.join(MODELS, "tiny_ckpt.npz"), out)
+    L = rnnoise_b200.lib()
+    m = L.rnnoise_model_from_filename(out.encode())
+    assert m
+    L.rnnoise_model_free(m)
+    assert Port(out).model
+    recs = weights.read_blob(blob)
+    idx = next(i for i, r in enumerate(recs) if r[0] == "gru1_input_weights_idx")
+    broken = recs[idx][2].copy(); broken[0] += 1            # first block count no longer matches the weights
+    recs[idx] = (recs[idx][0], recs[idx][1], broken)
+    bad = weights.write_blob(recs)
+    assert not L.rnnoise_model_from_buffer(bad, len(bad))
