@@ -1,0 +1,138 @@
+"""Host API layer (rnnoise_b200/csrc/rnnoise_api.c) over a mock engine (tests/mock/mock_engine.c): the split of a
+batch into lanes, the pointer offsets every entry point hands to each lane, and the routing of per-stream calls --
+for many batch sizes and lane counts, without a GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "rnnoise_b200", "csrc")
+SO = os.path.join(ROOT, "tests", "mock", "libmock_api.so")
+SRCS = [os.path.join(CSRC, "rnnoise_api.c"), os.path.join(CSRC, "model_blob.c"), os.path.join(ROOT, "tests", "mock", "mock_engine.c")]
+
+
+@pytest.fixture(scope="module")
+def M():
+    deps = SRCS + [os.path.join(CSRC, "engine.h"), os.path.join(ROOT, "include", "rnnoise.h")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.run(["gcc", "-O1", "-g", "-fPIC", "-shared", "-Wall", "-DRNNOISE_BUILD", "-I", CSRC, *SRCS, "-o", SO], check=True)
+    L = C.CDLL(SO)
+    vp, ip = C.c_void_p, C.c_int
+    L.rnnoise_model_from_filename.restype = vp; L.rnnoise_model_from_filename.argtypes = [C.c_char_p]
+    L.rnnoise_batch_create.restype = vp; L.rnnoise_batch_create.argtypes = [vp, ip, ip]
+    L.rnnoise_batch_destroy.argtypes = [vp]
+    L.rnnoise_batch_get_lanes.argtypes = [vp]; L.rnnoise_batch_get_streams.argtypes = [vp]
+    for nm in ("rnnoise_process_frame_batch", "rnnoise_process_frame_batch_async", "rnnoise_process_frame_batch_device",
+               "rnnoise_process_frame_batch_s16", "rnnoise_process_frame_batch_s16_async", "rnnoise_process_frame_batch_device_s16"):
+        getattr(L, nm).argtypes = [vp] * 4
+    for nm in ("rnnoise_process_frames_batch", "rnnoise_process_frames_batch_s16", "rnnoise_process_frames_batch_device",
+               "rnnoise_process_frames_batch_device_s16"):
+        getattr(L, nm).argtypes = [vp, vp, vp, vp, ip]
+    L.rnnoise_batch_train_features.argtypes = [vp] * 8
+    L.rnnoise_batch_prefilter_device.argtypes = [vp, vp]
+    L.rnnoise_batch_set_stream.argtypes = [vp, vp]
+    L.rnnoise_batch_reset_stream.argtypes = [vp, ip]
+    L.rnnoise_batch_debug_read.argtypes = [vp, ip, ip, C.POINTER(C.c_float), ip]
+    L.rnnoise_batch_profile_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_char_p), ip, C.POINTER(ip)]
+    L.rnnoise_batch_launches_per_frame.argtypes = [vp]
+    L.mock_hint.restype = C.c_float; L.mock_hint.argtypes = [ip]
+    L.model = L.rnnoise_model_from_filename(os.path.join(ROOT, "tests", "golden", "models", "tiny.bin").encode())
+    assert L.model
+    return L
+
+
+def owner(L, b, s):
+    buf = (C.c_float * 8)()
+    assert L.rnnoise_batch_debug_read(b, 0, s, buf, 8) == 5
+    return int(buf[0]), int(buf[1]), buf
+
+
+CASES = [(1, None), (100, None), (1023, None), (1024, None), (3000, None), (4096, None), (12287, None), (12288, None),
+         (300, "2"), (600, "4"), (129, "2"), (255, "2"), (256, "2"), (5000, "3"), (513, "4"), (70, "3")]
+
+
+@pytest.mark.parametrize("S,env", CASES)
+def test_lane_partition_and_offsets(M, monkeypatch, S, env):
+    L = M
+    if env:
+        monkeypatch.setenv("RNNOISE_B200_LANES", env)
+    else:
+        monkeypatch.delenv("RNNOISE_B200_LANES", raising=False)
+    L.mock_reset_ids()
+    b = L.rnnoise_batch_create(L.model, S, 0)
+    assert b and L.rnnoise_batch_get_streams(b) == S
+    lanes = L.rnnoise_batch_get_lanes(b)
+    own = np.array([owner(L, b, s)[:2] for s in range(S)])          # (lane id, local index) per stream
+    # contiguous ranges, local indices count up from 0, every lane non-empty, whole 128-tiles except the last lane
+    assert own[0].tolist() == [0, 0] and own[-1, 0] == lanes - 1
+    sizes = [int(np.sum(own[:, 0] == l)) for l in range(lanes)]
+    assert sum(sizes) == S and all(n > 0 for n in sizes) and all(n % 128 == 0 for n in sizes[:-1])
+    first = np.cumsum([0] + sizes)
+    for l in range(lanes):
+        assert np.array_equal(own[first[l]:first[l + 1], 1], np.arange(sizes[l])) and np.all(own[first[l]:first[l + 1], 0] == l)
+    if env is None:
+        assert lanes == (2 if 1024 <= S < 12288 else 1)
+    else:
+        assert 1 <= lanes <= int(env) and (lanes == 1 or S // lanes >= 128 or sizes[-1] < 128)
+    assert L.rnnoise_batch_launches_per_frame(b) == 10 * lanes
+    lane_of = own[:, 0].astype(np.float32); local = own[:, 1].astype(np.float32)
+
+    # single-frame float / int16 entry points
+    x = np.arange(S * 480, dtype=np.float32).reshape(S, 480) % 977
+    for fn in (L.rnnoise_process_frame_batch, L.rnnoise_process_frame_batch_async, L.rnnoise_process_frame_batch_device):
+        out = np.zeros_like(x); vad = np.zeros(S, np.float32)
+        assert fn(b, out.ctypes.data, x.ctypes.data, vad.ctypes.data) == 0
+        assert np.array_equal(out, 2 * x + (1000 * lane_of + local)[:, None]) and np.array_equal(vad, 100 * lane_of + local)
+    x16 = (np.arange(S * 480).reshape(S, 480) % 501).astype(np.int16)
+    for fn in (L.rnnoise_process_frame_batch_s16, L.rnnoise_process_frame_batch_s16_async, L.rnnoise_process_frame_batch_device_s16):
+        out = np.zeros_like(x16); vad = np.zeros(S, np.float32)
+        assert fn(b, out.ctypes.data, x16.ctypes.data, None if fn is L.rnnoise_process_frame_batch_s16_async else vad.ctypes.data) == 0
+        assert np.array_equal(out.astype(np.int64), x16.astype(np.int64) + (1000 * own[:, 0] + own[:, 1])[:, None])
+    # multi-frame: [S][T * 480] buffers, vad [S][T]
+    T = 3
+    xm = (np.arange(S * T * 480, dtype=np.float32) % 601).reshape(S, T * 480)
+    for fn in (L.rnnoise_process_frames_batch, L.rnnoise_process_frames_batch_device):
+        out = np.zeros_like(xm); vad = np.zeros((S, T), np.float32)
+        assert fn(b, out.ctypes.data, xm.ctypes.data, vad.ctypes.data, T) == 0
+        want = 2 * xm.reshape(S, T, 480) + (1000 * lane_of + local)[:, None, None] + 0.25 * np.arange(T, dtype=np.float32)[None, :, None]
+        assert np.array_equal(out.reshape(S, T, 480), want.astype(np.float32))
+        assert np.array_equal(vad, (100 * lane_of + local)[:, None] + (np.arange(T, dtype=np.float32) / np.float32(1000))[None, :])
+    xm16 = (np.arange(S * T * 480) % 301).astype(np.int16).reshape(S, T * 480)
+    for fn in (L.rnnoise_process_frames_batch_s16, L.rnnoise_process_frames_batch_device_s16):
+        out = np.zeros_like(xm16)
+        assert fn(b, out.ctypes.data, xm16.ctypes.data, None, T) == 0
+        want = xm16.reshape(S, T, 480).astype(np.int64) + (1000 * own[:, 0] + own[:, 1])[:, None, None] + np.arange(T)[None, :, None]
+        assert np.array_equal(out.reshape(S, T, 480).astype(np.int64), want)
+    # training records with per-stream arrays (and with all of them NULL)
+    clean = (np.arange(S * 480, dtype=np.float32) % 211).reshape(S, 480); noisy = clean[::-1].copy()
+    vt = (np.arange(S) % 2).astype(np.float32); nf = (np.arange(S) % 3 == 0).astype(np.int32)
+    lp = (100 + np.arange(S) % 300).astype(np.int32); bl = (np.arange(S) % 33).astype(np.int32)
+    rec = np.zeros((S, 98), np.float32)
+    assert L.rnnoise_batch_train_features(b, rec.ctypes.data, clean.ctypes.data, noisy.ctypes.data, vt.ctypes.data, nf.ctypes.data,
+                                          lp.ctypes.data, bl.ctypes.data) == 0
+    assert np.array_equal(rec[:, :96], clean[:, :96] + noisy[:, :96]) and np.array_equal(rec[:, 96], 1000 * lane_of + local)
+    assert np.array_equal(rec[:, 97], (vt + 2 * nf + 4 * lp + 4096 * bl).astype(np.float32))
+    assert L.rnnoise_batch_train_features(b, rec.ctypes.data, clean.ctypes.data, noisy.ctypes.data, None, None, None, None) == 0
+    assert np.all(rec[:, 97] == 4 * 481 + 4096 * 32)
+    # prefilter hint: every lane receives the start of its own slice
+    assert L.rnnoise_batch_prefilter_device(b, x.ctypes.data) == 0
+    for l in range(min(lanes, 16)):
+        assert L.mock_hint(l) == x[first[l], 0]
+    # per-stream routing: reset and debug; stream handling: one lane runs on the caller's stream, several are bracketed
+    for s in {0, S - 1, S // 2, int(first[lanes - 1])}:
+        assert L.rnnoise_batch_reset_stream(b, s) == 0
+        lane, loc, buf = owner(L, b, s)
+        assert int(buf[2]) == loc
+    assert L.rnnoise_batch_reset_stream(b, S) == -1 and L.rnnoise_batch_reset_stream(b, -1) == -1
+    assert L.rnnoise_batch_set_stream(b, C.c_void_p(0x1234)) == 0
+    for l in range(lanes):
+        _, _, buf = owner(L, b, int(first[l]))
+        assert (buf[3], buf[4]) == ((0.0, 1.0) if lanes == 1 else (1.0, 0.0))
+    # profile: per-kernel times summed over the lanes
+    ms = (C.c_float * 32)(); names = (C.c_char_p * 32)(); fr = C.c_int(0)
+    assert L.rnnoise_batch_profile_read(b, ms, names, 32, C.byref(fr)) == 2 and fr.value == 7
+    assert ms[0] == sum(1.0 + l for l in range(lanes)) and ms[1] == 10.0 * lanes and names[0] == b"k_a"
+    L.rnnoise_batch_destroy(b)
