@@ -49,10 +49,15 @@ def pool_frames(S):
     return int(max(4, min(POOL_FRAMES, (1 << 30) // (S * FRAME * 4))))
 
 
-def make_pool(S):
-    """float32 [pool_frames(S)][S][480]: POOL_STREAMS distinct synthetic streams tiled to S."""
+def base_pool(S):
+    """float32 [pool_frames(S)][min(POOL_STREAMS, S)][480]: the distinct synthetic streams of the input pool."""
     from rnnoise_b200.synth_pcm import batch_pcm
-    base = batch_pcm(min(POOL_STREAMS, S), pool_frames(S))
+    return batch_pcm(min(POOL_STREAMS, S), pool_frames(S))
+
+
+def make_pool(S):
+    """float32 [pool_frames(S)][S][480]: POOL_STREAMS distinct synthetic streams tiled to S (stream s = pool stream s % 128)."""
+    base = base_pool(S)
     reps = (S + base.shape[1] - 1) // base.shape[1]
     return np.ascontiguousarray(np.tile(base, (1, reps, 1))[:, :S])
 
@@ -96,14 +101,44 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def run_reference(S, steps, warmup, threads=None):
+REF_REPEATS = 5     # repeat the CPU measurement >= 5 times, report median and best
+
+
+def has_vnni():
+    try:
+        return any(l.startswith("flags") and " avx_vnni" in l for l in open("/proc/cpuinfo"))
+    except Exception:
+        return False
+
+
+_pool_file = {}
+
+
+def pool_file(S):
+    """The GPU arm's input pool written once for the CPU arm (same PCM on both sides): [frames][streams][480] float32."""
+    if S not in _pool_file:
+        base = base_pool(S)
+        d = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        path = os.path.join(d, f"rnnoise_b200_pool_{os.getpid()}_{S}.f32")
+        base.astype(np.float32).tofile(path)
+        import atexit
+        atexit.register(lambda: os.path.exists(path) and os.remove(path))
+        _pool_file[S] = (path, base.shape[1], base.shape[0])
+    return _pool_file[S]
+
+
+def run_reference(S, steps, warmup, threads=None, repeats=1, vnni=False, model=None, pool_S=None):
     """Times the unmodified reference (oracle/_ref) on the host cores; returns dict or None."""
     from oracle import refbind
-    exe = refbind.bench_path()
+    exe = refbind.bench_path(vnni=vnni)
     if not os.path.exists(exe):
         return None
     threads = threads or len(os.sched_getaffinity(0))
-    r = subprocess.run([exe, MODEL, str(S), str(steps), str(warmup), str(threads)], capture_output=True, text=True, timeout=1500)
+    cmd = [exe, model or MODEL, str(S), str(steps), str(warmup), str(threads), str(repeats)]
+    if pool_S:
+        path, ps, pf = pool_file(pool_S)
+        cmd += [path, str(ps), str(pf)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
     if r.returncode != 0:
         return None
     d = json.loads(r.stdout.strip().splitlines()[-1])
@@ -111,16 +146,44 @@ def run_reference(S, steps, warmup, threads=None):
     return d
 
 
-def best_reference_threads(S):
+def best_reference_threads(S, model=None):
     """Quick sweep: containers often expose more logical CPUs than their CPU quota; pick the thread
     count that gives the reference its best throughput on this box."""
     n = len(os.sched_getaffinity(0))
     best, best_t = None, n
     for t in sorted({n, max(1, n // 2), max(1, n // 4), max(1, n // 8)}, reverse=True):
-        r = run_reference(min(S, 8 * t), 12, 3, threads=t)
+        r = run_reference(min(S, 8 * t), 12, 3, threads=t, model=model)
         if r and (best is None or r["frames_per_s"] > best):
             best, best_t = r["frames_per_s"], t
     return best_t, best
+
+
+def reference_baseline(S, budget_s, model=None, warmup=5):
+    """BASELINE.md section 3 protocol: the unmodified reference (RTCD/AVX2 build), the thread count that is best
+    on this box, the SAME PCM pool as the GPU arm, REF_REPEATS back-to-back repeats -> median (the value) and
+    best; plus the AVX-VNNI build of the same sources when the host has the instruction.  `budget_s` bounds the
+    CPU work of the main run."""
+    threads, rate = best_reference_threads(S, model)
+    if not rate:
+        return None
+    steps = int(max(3, min(400, budget_s / REF_REPEATS * rate / S)))
+    ref = run_reference(S, steps, warmup, threads=threads, repeats=REF_REPEATS, model=model, pool_S=S)
+    if ref is None:
+        return None
+    ref["steps_per_repeat"] = steps
+    if has_vnni():
+        v = run_reference(S, steps, warmup, threads=threads, repeats=3, vnni=True, model=model, pool_S=S)
+        if v:
+            ref["vnni"] = {"value": v["frames_per_s"], "best": v["best_frames_per_s"], "build": "same sources, nnet_avx2.c with -mavxvnni (vec_avx.h:623 branch)"}
+    return ref
+
+
+def cpu_baseline_dict(ref, S):
+    return {"value": ref["frames_per_s"], "best": ref["best_frames_per_s"], "repeats": ref["repeat_frames_per_s"], "unit": "frames/s",
+            "cores": ref["threads"], "kind": "reference", "vnni": ref.get("vnni"),
+            "sample": f"{S} streams x {ref['steps_per_repeat']} frames x {REF_REPEATS} repeats (value = median, best beside it), same PCM pool as the "
+                      f"GPU arm, unmodified xiph/rnnoise RTCD/AVX2 build via oracle/_ref, {ref['threads']} threads (best of a thread sweep "
+                      f"over the {len(os.sched_getaffinity(0))} logical CPUs the container exposes), {cpu_model()}"}
 
 
 def cpu_model():
@@ -156,21 +219,18 @@ def main():
         if rank != 0:
             return
         total_S = S * max(a.gpus, 1)
-        threads, rate = best_reference_threads(total_S)
         # every step = one frame of all streams on the host cores; the sample is bounded to about a minute of
-        # CPU work (the rate does not depend on how many frames are run)
-        frames_run = int(max(3, min(K, 60.0 * (rate or 2e5) / total_S)))
-        ref = run_reference(total_S, frames_run, min(Wm, 5), threads=threads)
+        # CPU work in total (the rate does not depend on how many frames are run)
+        ref = reference_baseline(total_S, 60.0, model=MODEL, warmup=min(Wm, 5))
         if ref is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_bench not built (needs /root/reference at build time)"}))
             return
         v = ref["frames_per_s"]
         print(json.dumps({"impl": "reference", "metric": "10ms frames/sec", "value": v, "unit": "frames/s", "n_gpus": a.gpus,
-                          "steps": K, "warmup": Wm, "ms_per_step": 1e3 * ref["elapsed_s"] / frames_run, "higher_is_better": True,
+                          "steps": K, "warmup": Wm, "ms_per_step": 1e3 * ref["elapsed_s"] / ref["steps_per_repeat"], "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "int8+fp32 (AVX2)", "data": "synthetic",
                           "config": dict(cfg, streams_total=total_S),
-                          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": ref["threads"], "kind": "reference",
-                                           "sample": f"{total_S} streams x {frames_run} frames (steps actually run), unmodified xiph/rnnoise RTCD/AVX2 build, {cpu_model()}"},
+                          "cpu_baseline": cpu_baseline_dict(ref, total_S),
                           "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -180,7 +240,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     if W > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: one JSON line only
+        # NCCL's log (version banner, INFO lines when the caller sets NCCL_DEBUG=INFO to check the ranks) goes to
+        # stderr, so that stdout carries the one JSON line only; NCCL_DEBUG itself is left to the caller
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -189,7 +251,6 @@ def main():
         build.build()
     model = rnnoise_b200.Model(MODEL)
     batch = rnnoise_b200.Batch(model, S, local)
-    cfg["lanes"] = batch.lanes   # the library's default split of the batch into concurrently running sub-batches
     pool_h = torch.from_numpy(make_pool(S)).pin_memory()           # [POOL][S][480] pinned host
     POOL_FRAMES = pool_h.shape[0]
     pool_d = pool_h.to(dev)                                        # device-resident inputs
@@ -331,19 +392,15 @@ def main():
         cpu = None
         if W == 1 and not a.no_cpu_baseline:
             try:
-                threads, rate = best_reference_threads(S)           # calibration ~ a second
-                if rate:
-                    steps_cpu = int(max(10, min(400, 15.0 * rate / S)))
-                    ref = run_reference(S, steps_cpu, 5, threads=threads)
-                    cpu = {"value": ref["frames_per_s"], "unit": "frames/s", "cores": ref["threads"], "kind": "reference",
-                           "sample": f"{S} streams x {steps_cpu} frames, unmodified xiph/rnnoise RTCD/AVX2 build via oracle/_ref, {cpu_model()}"}
+                ref = reference_baseline(S, 20.0, model=MODEL)
+                cpu = cpu_baseline_dict(ref, S) if ref else None
             except Exception as ex:  # noqa: BLE001
                 cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
         line = {"metric": "10ms frames/sec", "value": value, "unit": "frames/s", "n_gpus": W, "steps": K, "warmup": Wm,
                 "ms_per_step": ms / K, "wall_ms_per_step": wall_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int8 (u8 x s8 -> s32) + fp32", "data": "synthetic", "config": dict(cfg, streams_total=W * S),
                 "realtime_streams_per_gpu": value / W / 100.0, "clocks": clocks, "e2e": e2e,
-                "gpu_launches": K * batch.launches_per_frame, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": K * batch.launches_per_frame, "lanes": lanes, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line))
     batch.destroy()
     model.free()

@@ -87,7 +87,31 @@ RNNOISE_EXPORT void rnnoise_model_free(RNNModel *model);
  *  NULL on failure (bad model, nb_streams < 1, no such device, out of memory). */
 RNNOISE_EXPORT RNNoiseBatch *rnnoise_batch_create(RNNModel *model, int nb_streams, int device);
 
+/** Multi-device batch: nb_streams stream states sharded over the nb_devices CUDA devices
+ *  listed in devices[] as contiguous stream ranges (shard k = streams [k*S/G, (k+1)*S/G), remainders to the
+ *  first shards), one host thread driving all of them.  Streams never interact, so there is no collective:
+ *  every per-frame call fans out over the devices asynchronously and rnnoise_batch_sync() joins them.  The
+ *  host-buffer entry points (rnnoise_process_frame_batch{,_async,_s16,...}, rnnoise_process_frames_batch*,
+ *  rnnoise_batch_train_features) work unchanged on [nb_streams][...] host buffers; device-resident audio goes
+ *  through the *_multi forms below, one pointer per device.  NULL on failure. */
+RNNOISE_EXPORT RNNoiseBatch *rnnoise_batch_create_multi(RNNModel *model, int nb_streams, const int *devices, int nb_devices);
+/** Number of devices of a batch, and shard k: its CUDA device, first stream and stream count.  0 / -1. */
+RNNOISE_EXPORT int rnnoise_batch_get_devices(const RNNoiseBatch *b);
+RNNOISE_EXPORT int rnnoise_batch_get_shard(const RNNoiseBatch *b, int k, int *device, int *first_stream, int *nb_streams);
+/** Device-pointer frame call of a multi-device batch: d_in[k] / d_out[k] ([shard streams][480]) and d_vad[k]
+ *  ([shard streams]; the array or single entries may be NULL) live on device k.  Enqueues and returns.
+ *  rnnoise_batch_prefilter_device_multi / rnnoise_batch_set_stream_multi are the per-device forms of the
+ *  calls below (streams[k] = a cudaStream_t of device k).  All also accept a single-device batch. */
+RNNOISE_EXPORT int rnnoise_process_frame_batch_device_multi(RNNoiseBatch *b, float *const *d_out, const float *const *d_in, float *const *d_vad);
+RNNOISE_EXPORT int rnnoise_batch_prefilter_device_multi(RNNoiseBatch *b, const float *const *d_in_next);
+RNNOISE_EXPORT int rnnoise_batch_set_stream_multi(RNNoiseBatch *b, void *const *streams);
+
 RNNOISE_EXPORT void rnnoise_batch_destroy(RNNoiseBatch *b);
+
+/* Error discipline of every per-frame call below: arguments and call-order preconditions are checked on the
+ * whole batch before anything is enqueued -- such a -1 leaves the batch untouched.  A -1 caused by a CUDA error
+ * while the frame was being enqueued cannot be undone (parts of the batch are a frame ahead): the batch is
+ * poisoned, every later per-frame call returns -1, and the only valid operation is rnnoise_batch_destroy(). */
 
 RNNOISE_EXPORT int rnnoise_batch_get_streams(const RNNoiseBatch *b);
 /** A batch is internally split into 1..4 "lanes" (contiguous stream ranges, each with its own CUDA streams)
@@ -219,6 +243,10 @@ enum {
  *  the first point: H2D start, H2D end, prefilter end, pitch end, spectrum end, network start, synthesis end,
  *  D2H end (NaN where a stage did not run through this call path).  Returns the frames written, -1 on error. */
 RNNOISE_EXPORT int rnnoise_batch_timeline_read(RNNoiseBatch *b, float *ms, int capacity);
+
+/** Test hook: start a fresh batch (nothing processed yet) at frame index `frames`, so that tests can cross the
+ *  wrap of the internal frame counter within a few frames.  0 / -1. */
+RNNOISE_EXPORT int rnnoise_batch_debug_set_frame_counter(RNNoiseBatch *b, long long frames);
 
 /** Copies item `what` of stream `stream` into dst (capacity in floats); returns the number of
  *  floats written or -1. */

@@ -59,8 +59,8 @@ def lib_path(kind="rtcd", cond=128, gru=384):
     return os.path.join(HERE, "_ref", name % (cond, gru))
 
 
-def bench_path(cond=128, gru=384):
-    return os.path.join(HERE, "_ref", "ref_bench_c%d_g%d" % (cond, gru))
+def bench_path(cond=128, gru=384, vnni=False):
+    return os.path.join(HERE, "_ref", "ref_bench_%sc%d_g%d" % ("vnni_" if vnni else "", cond, gru))
 
 
 def available(kind="rtcd", cond=128, gru=384):

@@ -48,6 +48,14 @@ def lib():
         L.rnnoise_process_frame.restype = C.c_float; L.rnnoise_process_frame.argtypes = [vp, fp, fp]
         L.rnnoise_batch_create.restype = vp; L.rnnoise_batch_create.argtypes = [vp, ip, ip]
         L.rnnoise_batch_destroy.argtypes = [vp]
+        L.rnnoise_batch_create_multi.restype = vp; L.rnnoise_batch_create_multi.argtypes = [vp, ip, C.POINTER(C.c_int), ip]
+        L.rnnoise_batch_get_devices.restype = ip; L.rnnoise_batch_get_devices.argtypes = [vp]
+        L.rnnoise_batch_get_shard.restype = ip; L.rnnoise_batch_get_shard.argtypes = [vp, ip] + [C.POINTER(C.c_int)] * 3
+        L.rnnoise_process_frame_batch_device_multi.restype = ip
+        L.rnnoise_process_frame_batch_device_multi.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        L.rnnoise_batch_prefilter_device_multi.restype = ip; L.rnnoise_batch_prefilter_device_multi.argtypes = [vp, C.POINTER(vp)]
+        L.rnnoise_batch_set_stream_multi.restype = ip; L.rnnoise_batch_set_stream_multi.argtypes = [vp, C.POINTER(vp)]
+        L.rnnoise_batch_debug_set_frame_counter.restype = ip; L.rnnoise_batch_debug_set_frame_counter.argtypes = [vp, C.c_longlong]
         L.rnnoise_batch_get_streams.restype = ip; L.rnnoise_batch_get_streams.argtypes = [vp]
         L.rnnoise_batch_get_lanes.restype = ip; L.rnnoise_batch_get_lanes.argtypes = [vp]
         L.rnnoise_process_frame_batch.restype = ip; L.rnnoise_process_frame_batch.argtypes = [vp, vp, vp, vp]
@@ -95,15 +103,49 @@ class Model:
 
 
 class Batch:
-    """RNNoiseBatch*: nb_streams independent denoiser states resident on one GPU."""
+    """RNNoiseBatch*: nb_streams independent denoiser states resident on one GPU, or -- with `devices`, a list
+    of CUDA device indices -- sharded over several GPUs of one box (rnnoise_batch_create_multi)."""
 
-    def __init__(self, model, nb_streams, device=0):
+    def __init__(self, model, nb_streams, device=0, devices=None):
         self.model = model
         self.nb_streams = nb_streams
-        self.handle = lib().rnnoise_batch_create(model.handle, nb_streams, device)
+        if devices is None:
+            self.handle = lib().rnnoise_batch_create(model.handle, nb_streams, device)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            self.handle = lib().rnnoise_batch_create_multi(model.handle, nb_streams, arr, len(devices))
         if not self.handle:
             raise RuntimeError("rnnoise_batch_create failed (no usable CUDA device, bad model or out of memory)")
         self.lanes = lib().rnnoise_batch_get_lanes(self.handle)
+        self.nb_devices = lib().rnnoise_batch_get_devices(self.handle)
+
+    def shard(self, k):
+        """-> (cuda device, first stream, stream count) of shard k."""
+        d, f, n = C.c_int(), C.c_int(), C.c_int()
+        if lib().rnnoise_batch_get_shard(self.handle, k, C.byref(d), C.byref(f), C.byref(n)) != 0:
+            raise IndexError(k)
+        return d.value, f.value, n.value
+
+    @staticmethod
+    def _ptrs(lst):
+        return None if lst is None else (C.c_void_p * len(lst))(*lst)
+
+    def process_device_multi(self, d_out, d_in, d_vad=None):
+        """Lists of device pointers (ints), one per device of the batch; asynchronous."""
+        if lib().rnnoise_process_frame_batch_device_multi(self.handle, self._ptrs(d_out), self._ptrs(d_in), self._ptrs(d_vad)) != 0:
+            raise RuntimeError("rnnoise_process_frame_batch_device_multi failed")
+
+    def prefilter_device_multi(self, d_in_next):
+        if lib().rnnoise_batch_prefilter_device_multi(self.handle, self._ptrs(d_in_next)) != 0:
+            raise RuntimeError("rnnoise_batch_prefilter_device_multi failed")
+
+    def set_stream_multi(self, streams):
+        if lib().rnnoise_batch_set_stream_multi(self.handle, self._ptrs(streams)) != 0:
+            raise RuntimeError("rnnoise_batch_set_stream_multi failed")
+
+    def debug_set_frame_counter(self, frames):
+        if lib().rnnoise_batch_debug_set_frame_counter(self.handle, int(frames)) != 0:
+            raise RuntimeError("rnnoise_batch_debug_set_frame_counter failed (batch not fresh)")
 
     def process(self, pcm, want_vad=True):
         """pcm: float32 [nb_streams][480] host array -> (out [nb_streams][480], vad [nb_streams])."""

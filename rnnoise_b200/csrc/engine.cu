@@ -266,12 +266,19 @@ enum { TL_H2D_START, TL_H2D_END, TL_BQ_END, TL_PITCH_END, TL_FRONT_END, TL_BACK_
 static const char *const kKernelNames[NKERNELS] = {"k_biquad", "k_pitch", "k_spectrum", "k_conv1", "k_conv2", "k_gru[0]",
                                                    "k_gru[1]", "k_gru[2]", "k_heads", "k_synthesis"};
 
+// The kernels derive three things from the frame index they are handed: the ping-pong parity f & 1, the
+// spectrum slot f % 3 and the pitch-ring base ((f + 1) * 480) % 1728, which has period 18 in f.  The 64-bit
+// host counter is therefore reduced modulo a multiple of lcm(2, 3, 18) = 18 that fits an int: all three stay
+// continuous for ever (a plain power-of-two mask would make the slot and the ring base jump at the wrap).
+#define FRAME_WRAP (18LL << 24)
+static inline int frame_arg(long long f) { return (int)(f % FRAME_WRAP); }
+
 template <typename T>
 static T *dalloc(B200Engine *e, size_t n, bool zero = true) {
   void *p = nullptr;
   if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+  e->allocs.push_back(p);   // owned from here on: freed by b200_engine_destroy even when the memset below fails
   if (zero && cudaMemset(p, 0, n * sizeof(T)) != cudaSuccess) return nullptr;
-  e->allocs.push_back(p);
   return (T *)p;
 }
 template <typename T>
@@ -606,7 +613,7 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   cudaStream_t sf = overlap ? e->s_front : st;
   int ki = 0;
 #define MARK() do { if (e->profiling) cudaEventRecord(e->ev[ki++], st); } while (0)
-  const int fr = (int)(e->frames & 0x3fffffff);
+  const int fr = frame_arg(e->frames);
   const int *sil = a.silence + (size_t)par * S;
   const float *feat = a.features + (size_t)par * S * NB_FEATURES;
   MARK();
@@ -703,7 +710,7 @@ static int issue_prefilter(B200Engine *e, const void *d_in, cudaEvent_t ready, i
   if (ready) CK(cudaStreamWaitEvent(e->s_bq, ready, 0));
   CK(cudaStreamWaitEvent(e->s_bq, e->ev_ana[slot], 0));       // frame f-2 no longer reads this xb half
   CK(cudaStreamWaitEvent(e->s_bq, e->ev_bq[slot ^ 1], 0));    // biquad state: after frame f-1's filter
-  k_biquad<<<(e->a.S + 31) / 32, 32, 0, e->s_bq>>>(e->a, d_in, (int)(f & 0x3fffffff), s16, e->io_stride);
+  k_biquad<<<(e->a.S + 31) / 32, 32, 0, e->s_bq>>>(e->a, d_in, frame_arg(f), s16, e->io_stride);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev_bq[slot], e->s_bq));
   TL(e, f, TL_BQ_END, e->s_bq);
@@ -711,6 +718,7 @@ static int issue_prefilter(B200Engine *e, const void *d_in, cudaEvent_t ready, i
   return 0;
 }
 
+extern "C" int b200_engine_prefilter_ahead(const B200Engine *e) { return e ? (int)(e->bq_frames - e->frames) : 0; }
 extern "C" int b200_engine_prefilter_device(B200Engine *e, const float *d_in) {
   if (!e || !d_in) return -1;
   CK(cudaSetDevice(e->device));
@@ -869,7 +877,7 @@ extern "C" int b200_engine_train_features_device(B200Engine *e, float *d_rec, co
   CK(cudaStreamWaitEvent(st, e->ev_ana[1], 0));
   CK(cudaStreamWaitEvent(st, e->ev_front[0], 0));
   CK(cudaStreamWaitEvent(st, e->ev_front[1], 0));
-  const int par = (int)(e->frames & 1), fr = (int)(e->frames & 0x3fffffff);
+  const int par = (int)(e->frames & 1), fr = frame_arg(e->frames);
   CK(cudaMemcpyAsync(a.xb + (size_t)par * S * FRAME_SIZE, d_noisy, S * FRAME_SIZE * sizeof(float), cudaMemcpyDeviceToDevice, st));
   const int pitch_grid = (a.S + PITCH_NS - 1) / PITCH_NS;
   k_pitch<<<pitch_grid, PITCH_NS * PITCH_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr);
@@ -1007,13 +1015,22 @@ extern "C" int b200_engine_reset_stream(B200Engine *e, int s) {
   return 0;
 }
 
+// Test hook: start a FRESH engine (all state zero, nothing enqueued) at an arbitrary frame index, so the
+// counter wrap can be crossed in a few frames.  Fails once a frame has been processed.
+extern "C" int b200_engine_debug_set_frames(B200Engine *e, long long frames) {
+  if (!e || frames < 0 || e->frames != 0 || e->bq_frames != 0 || e->host_frames != 0) return -1;
+  e->frames = e->bq_frames = e->host_frames = frames;
+  return 0;
+}
+
 extern "C" int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst, int cap) {
   if (!e || !dst || s < 0 || s >= e->a.S || e->frames < 1) return -1;
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
   const Arena &a = e->a;
   const size_t S = a.S;
-  const int par = (int)((e->frames - 1) & 1), slot = (int)((e->frames - 1) % 3);
+  const int fl = frame_arg(e->frames - 1);   // the index the kernels of the last frame were handed
+  const int par = fl & 1, slot = fl % 3;
   const float *src = nullptr;
   int n = 0;
   switch (what) {

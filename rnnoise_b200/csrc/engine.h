@@ -34,6 +34,10 @@ int b200_engine_train_features_device(B200Engine *e, float *d_rec, const float *
 int b200_engine_train_features_host(B200Engine *e, float *rec, const float *clean, const float *noisy,
                                     const float *vad_target, const int *noise_free, const int *lowpass, const int *band_lp);
 int b200_engine_prefilter_device(B200Engine *e, const float *d_in);
+/* frames whose high-pass prefilter has been issued ahead of processing (0, 1 or 2) */
+int b200_engine_prefilter_ahead(const B200Engine *e);
+/* test hook: start a fresh engine at an arbitrary frame index (counter-wrap tests) */
+int b200_engine_debug_set_frames(B200Engine *e, long long frames);
 int b200_engine_sync(B200Engine *e);
 int b200_engine_set_stream(B200Engine *e, void *cuda_stream);
 int b200_engine_reset_stream(B200Engine *e, int stream);

@@ -60,10 +60,17 @@ static int int8_layer(B200Layer *l, const Arr *a, int n, const char *name, int n
   int remain = ix->size / 4, tiles = 0, rows_left = nb_out;
   for (int ob = 0; remain > 0; ob++) {
     int nb = *idx++;
-    if (nb < 0 || remain < nb + 1 || rows_left <= 0) return -1;
+    /* nb >= remain (not remain < nb + 1: nb + 1 overflows for nb == INT_MAX) */
+    if (nb < 0 || nb >= remain || rows_left <= 0) return -1;
+    int last_pos = -4;
     for (int b = 0; b < nb; b++) {
       int pos = *idx++;
-      if (pos < 0 || pos + 3 >= nb_in || (pos & 3)) return -1;
+      if (pos < 0 || pos > nb_in - 4 || (pos & 3)) return -1;
+      /* positions inside one output block must increase: a repeated position would ACCUMULATE in the
+         reference's sparse kernel (vec_avx.h:778-828) but overwrite in this dense expansion; the exporter
+         never emits one (wexchange/c_export/common.py), so it is rejected instead of mis-read */
+      if (pos <= last_pos) return -1;
+      last_pos = pos;
       if ((tiles + 1) * 32 > w->size) return -1;
       const signed char *t = src + (size_t)tiles * 32;
       for (int o = 0; o < 8; o++)

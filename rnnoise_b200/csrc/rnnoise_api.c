@@ -29,12 +29,22 @@ struct RNNModel {
  * tools/lanes_experiment.py: +10 % at 1024 streams, +5 % at 2048, +13 % at 3072, +10 % at 4096, +3 % at 6144,
  * +2 % at 8192, -1 % at 16384).
  * $RNNOISE_B200_LANES overrides the choice. */
-#define B200_MAX_LANES 4
+#define B200_MAX_LANES 4      /* per device */
+#define B200_MAX_DEVICES 16
+#define B200_MAX_ENGINES (B200_MAX_LANES * B200_MAX_DEVICES)
 struct RNNoiseBatch {
-  int lanes;
-  int first[B200_MAX_LANES + 1]; /* lane l owns streams [first[l], first[l + 1]) */
-  B200Engine *engine[B200_MAX_LANES];
+  int lanes;                       /* engines in total, over all devices */
+  int first[B200_MAX_ENGINES + 1]; /* lane l owns streams [first[l], first[l + 1]) */
+  B200Engine *engine[B200_MAX_ENGINES];
   int nb_streams;
+  /* devices (rnnoise_batch_create_multi): device k runs lanes [dev_lane[k], dev_lane[k + 1]) over the contiguous
+   * shard of streams [first[dev_lane[k]], first[dev_lane[k + 1]]) */
+  int nb_devices;
+  int device[B200_MAX_DEVICES];
+  int dev_lane[B200_MAX_DEVICES + 1];
+  /* set when a per-frame call failed after some lanes had already enqueued the frame: the lanes are then out
+   * of step with each other for good, so every later call fails cleanly instead of producing skewed audio */
+  int poisoned;
 };
 #define LANE_COUNT(b, l) ((b)->first[(l) + 1] - (b)->first[l])
 
@@ -113,35 +123,63 @@ static int default_lanes(int nb_streams) {
   return lanes;
 }
 
-RNNoiseBatch *rnnoise_batch_create(RNNModel *model, int nb_streams, int device) {
+/* Streams are independent (no cross-stream term anywhere in rnnoise_process_frame, denoise.c:457-504), so a
+ * batch shards over devices as contiguous stream ranges (stream i -> device floor(i * G / S)) with
+ * no collective; each device's shard is then split into lanes as for a single device. */
+RNNoiseBatch *rnnoise_batch_create_multi(RNNModel *model, int nb_streams, const int *devices, int nb_devices) {
   RNNoiseBatch *b;
-  int l, per;
-  if (!model || !model->parsed || nb_streams < 1 || device < 0) return NULL;
+  int k, l, per, lanes, s0, cnt, base, rem;
+  if (!model || !model->parsed || nb_streams < 1 || !devices || nb_devices < 1 || nb_devices > B200_MAX_DEVICES) return NULL;
+  if (nb_devices > nb_streams) nb_devices = nb_streams;
+  for (k = 0; k < nb_devices; k++)
+    if (devices[k] < 0) return NULL;
   b = (RNNoiseBatch *)calloc(1, sizeof(*b));
   if (!b) return NULL;
-  b->lanes = default_lanes(nb_streams);
   b->nb_streams = nb_streams;
-  /* lane sizes: multiples of the 128-stream tensor-core tile, the last lane takes the remainder */
-  per = ((nb_streams + b->lanes - 1) / b->lanes + 127) / 128 * 128;
-  for (l = 0; l <= b->lanes; l++) b->first[l] = l * per < nb_streams ? l * per : nb_streams;
-  b->first[b->lanes] = nb_streams;
-  while (b->lanes > 1 && LANE_COUNT(b, b->lanes - 1) <= 0) b->lanes--;
-  for (l = 0; l < b->lanes; l++) {
-    b->engine[l] = b200_engine_create(&model->host, LANE_COUNT(b, l), device);
-    if (!b->engine[l]) {
-      rnnoise_batch_destroy(b);
-      return NULL;
+  b->nb_devices = nb_devices;
+  base = nb_streams / nb_devices; rem = nb_streams % nb_devices;
+  s0 = 0;
+  for (k = 0; k < nb_devices; k++, s0 += cnt) {
+    cnt = base + (k < rem ? 1 : 0);
+    b->device[k] = devices[k];
+    b->dev_lane[k] = b->lanes;
+    lanes = default_lanes(cnt);
+    /* lane sizes: multiples of the 128-stream tensor-core tile, the last lane takes the remainder */
+    per = ((cnt + lanes - 1) / lanes + 127) / 128 * 128;
+    for (l = 0; l < lanes && l * per < cnt; l++) {
+      b->first[b->lanes] = s0 + l * per;
+      b->first[b->lanes + 1] = s0 + ((l + 1) * per < cnt ? (l + 1) * per : cnt);
+      b->engine[b->lanes] = b200_engine_create(&model->host, LANE_COUNT(b, b->lanes), devices[k]);
+      if (!b->engine[b->lanes]) {
+        rnnoise_batch_destroy(b);
+        return NULL;
+      }
+      b->lanes++;
     }
   }
+  b->dev_lane[nb_devices] = b->lanes;
   return b;
+}
+
+RNNoiseBatch *rnnoise_batch_create(RNNModel *model, int nb_streams, int device) {
+  return rnnoise_batch_create_multi(model, nb_streams, &device, 1);
 }
 
 void rnnoise_batch_destroy(RNNoiseBatch *b) {
   int l;
   if (!b) return;
-  for (l = 0; l < B200_MAX_LANES; l++)
+  for (l = 0; l < B200_MAX_ENGINES; l++)
     if (b->engine[l]) b200_engine_destroy(b->engine[l]);
   free(b);
+}
+
+int rnnoise_batch_get_devices(const RNNoiseBatch *b) { return b ? b->nb_devices : 0; }
+int rnnoise_batch_get_shard(const RNNoiseBatch *b, int k, int *device, int *first_stream, int *nb_streams) {
+  if (!b || k < 0 || k >= b->nb_devices) return -1;
+  if (device) *device = b->device[k];
+  if (first_stream) *first_stream = b->first[b->dev_lane[k]];
+  if (nb_streams) *nb_streams = b->first[b->dev_lane[k + 1]] - b->first[b->dev_lane[k]];
+  return 0;
 }
 
 int rnnoise_batch_get_streams(const RNNoiseBatch *b) { return b ? b->nb_streams : 0; }
@@ -160,11 +198,33 @@ int rnnoise_batch_sync(RNNoiseBatch *b) {
   return rc ? -1 : 0;
 }
 
+/* Error discipline of the per-frame entry points: everything that can be checked is checked on EVERY lane before
+ * anything is enqueued (arguments, a pending prefilter hint); such a failure returns -1 and leaves the batch as
+ * it was.  A failure after that point (a CUDA error in some lane) leaves earlier lanes one frame ahead of later
+ * ones, which cannot be repaired: the batch is marked poisoned and every following per-frame call returns -1;
+ * destroy it.  need_idle: the entry point refuses to run across a pending rnnoise_batch_prefilter_device() hint. */
+static int frame_call_ok(RNNoiseBatch *b, int need_idle, int single_device) {
+  int l;
+  if (!b || b->poisoned) return 0;
+  if (single_device && b->nb_devices != 1) return 0;   /* one device pointer cannot address several devices */
+  if (need_idle)
+    FOR_LANES(b, l)
+      if (b200_engine_prefilter_ahead(b->engine[l]) != 0) return 0;
+  return 1;
+}
+#define FAN_OUT(b, l, call)          \
+  do {                               \
+    FOR_LANES(b, l)                  \
+      if (call) {                    \
+        (b)->poisoned = 1;           \
+        return -1;                   \
+      }                              \
+  } while (0)
+
 int rnnoise_process_frame_batch_async(RNNoiseBatch *b, float *out, const float *in, float *vad) {
   int l;
-  if (!b || !out || !in) return -1;
-  FOR_LANES(b, l)
-    if (b200_engine_frame_host_async(b->engine[l], PCM_AT(out, b, l, 1, float), PCM_AT(in, b, l, 1, const float), VAD_AT(vad, b, l, 1))) return -1;
+  if (!out || !in || !frame_call_ok(b, 1, 0)) return -1;
+  FAN_OUT(b, l, b200_engine_frame_host_async(b->engine[l], PCM_AT(out, b, l, 1, float), PCM_AT(in, b, l, 1, const float), VAD_AT(vad, b, l, 1)));
   return 0;
 }
 int rnnoise_process_frame_batch(RNNoiseBatch *b, float *out, const float *in, float *vad) {
@@ -173,9 +233,8 @@ int rnnoise_process_frame_batch(RNNoiseBatch *b, float *out, const float *in, fl
 }
 int rnnoise_process_frame_batch_s16_async(RNNoiseBatch *b, short *out, const short *in, float *vad) {
   int l;
-  if (!b || !out || !in) return -1;
-  FOR_LANES(b, l)
-    if (b200_engine_frame_host_async_s16(b->engine[l], PCM_AT(out, b, l, 1, short), PCM_AT(in, b, l, 1, const short), VAD_AT(vad, b, l, 1))) return -1;
+  if (!out || !in || !frame_call_ok(b, 1, 0)) return -1;
+  FAN_OUT(b, l, b200_engine_frame_host_async_s16(b->engine[l], PCM_AT(out, b, l, 1, short), PCM_AT(in, b, l, 1, const short), VAD_AT(vad, b, l, 1)));
   return 0;
 }
 int rnnoise_process_frame_batch_s16(RNNoiseBatch *b, short *out, const short *in, float *vad) {
@@ -184,25 +243,61 @@ int rnnoise_process_frame_batch_s16(RNNoiseBatch *b, short *out, const short *in
 }
 int rnnoise_process_frame_batch_device(RNNoiseBatch *b, float *d_out, const float *d_in, float *d_vad) {
   int l;
-  if (!b || !d_out || !d_in) return -1;
-  FOR_LANES(b, l)
-    if (b200_engine_frame_device(b->engine[l], PCM_AT(d_out, b, l, 1, float), PCM_AT(d_in, b, l, 1, const float), VAD_AT(d_vad, b, l, 1))) return -1;
+  if (!d_out || !d_in || !frame_call_ok(b, 0, 1)) return -1;
+  FAN_OUT(b, l, b200_engine_frame_device(b->engine[l], PCM_AT(d_out, b, l, 1, float), PCM_AT(d_in, b, l, 1, const float), VAD_AT(d_vad, b, l, 1)));
   return 0;
 }
 int rnnoise_process_frame_batch_device_s16(RNNoiseBatch *b, short *d_out, const short *d_in, float *d_vad) {
   int l;
-  if (!b || !d_out || !d_in) return -1;
+  if (!d_out || !d_in || !frame_call_ok(b, 0, 1)) return -1;
+  FAN_OUT(b, l, b200_engine_frame_device_s16(b->engine[l], PCM_AT(d_out, b, l, 1, short), PCM_AT(d_in, b, l, 1, const short), VAD_AT(d_vad, b, l, 1)));
+  return 0;
+}
+/* Multi-device form of the device-pointer call: d_in[k] / d_out[k] / d_vad[k] live on device k of the batch
+ * (rnnoise_batch_get_shard) and hold that device's shard, [shard streams][480] / [shard streams]. */
+#define DEV_OF_LANE(b, l, k) do { while ((l) >= (b)->dev_lane[(k) + 1]) (k)++; } while (0)
+#define SHARD_OFF(b, l, k) ((size_t)((b)->first[l] - (b)->first[(b)->dev_lane[k]]))
+int rnnoise_process_frame_batch_device_multi(RNNoiseBatch *b, float *const *d_out, const float *const *d_in, float *const *d_vad) {
+  int l, k = 0;
+  if (!d_out || !d_in || !frame_call_ok(b, 0, 0)) return -1;
+  for (l = 0; l < b->nb_devices; l++)
+    if (!d_out[l] || !d_in[l]) return -1;
+  FOR_LANES(b, l) {
+    DEV_OF_LANE(b, l, k);
+    if (b200_engine_frame_device(b->engine[l], d_out[k] + SHARD_OFF(b, l, k) * FRAME_SIZE, d_in[k] + SHARD_OFF(b, l, k) * FRAME_SIZE,
+                                 d_vad && d_vad[k] ? d_vad[k] + SHARD_OFF(b, l, k) : NULL)) {
+      b->poisoned = 1;
+      return -1;
+    }
+  }
+  return 0;
+}
+int rnnoise_batch_prefilter_device_multi(RNNoiseBatch *b, const float *const *d_in_next) {
+  int l, k = 0;
+  if (!d_in_next || !frame_call_ok(b, 0, 0)) return -1;
+  for (l = 0; l < b->nb_devices; l++)
+    if (!d_in_next[l]) return -1;
   FOR_LANES(b, l)
-    if (b200_engine_frame_device_s16(b->engine[l], PCM_AT(d_out, b, l, 1, short), PCM_AT(d_in, b, l, 1, const short), VAD_AT(d_vad, b, l, 1))) return -1;
+    if (b200_engine_prefilter_ahead(b->engine[l]) >= 2) return -1;
+  FOR_LANES(b, l) {
+    DEV_OF_LANE(b, l, k);
+    if (b200_engine_prefilter_device(b->engine[l], d_in_next[k] + SHARD_OFF(b, l, k) * FRAME_SIZE)) {
+      b->poisoned = 1;
+      return -1;
+    }
+  }
   return 0;
 }
 static int frames_host(RNNoiseBatch *b, void *out, const void *in, float *vad, int T, int s16) {
   int l;
-  if (!b || !out || !in || T < 1) return -1;
+  if (!out || !in || T < 1 || !frame_call_ok(b, 1, 0)) return -1;
   FOR_LANES(b, l) {
     void *o = s16 ? (void *)PCM_AT(out, b, l, T, short) : (void *)PCM_AT(out, b, l, T, float);
     const void *i = s16 ? (const void *)PCM_AT(in, b, l, T, const short) : (const void *)PCM_AT(in, b, l, T, const float);
-    if (b200_engine_frames_host_enqueue(b->engine[l], o, i, VAD_AT(vad, b, l, T), T, s16, T)) return -1;
+    if (b200_engine_frames_host_enqueue(b->engine[l], o, i, VAD_AT(vad, b, l, T), T, s16, T)) {
+      b->poisoned = 1;
+      return -1;
+    }
   }
   return rnnoise_batch_sync(b);
 }
@@ -214,38 +309,34 @@ int rnnoise_process_frames_batch_s16(RNNoiseBatch *b, short *out, const short *i
 }
 int rnnoise_process_frames_batch_device(RNNoiseBatch *b, float *d_out, const float *d_in, float *d_vad, int nb_frames) {
   int l;
-  if (!b || !d_out || !d_in || nb_frames < 1) return -1;
-  FOR_LANES(b, l)
-    if (b200_engine_frames_device(b->engine[l], PCM_AT(d_out, b, l, nb_frames, float), PCM_AT(d_in, b, l, nb_frames, const float),
-                                  VAD_AT(d_vad, b, l, nb_frames), nb_frames, 0)) return -1;
+  if (!d_out || !d_in || nb_frames < 1 || !frame_call_ok(b, 1, 1)) return -1;
+  FAN_OUT(b, l, b200_engine_frames_device(b->engine[l], PCM_AT(d_out, b, l, nb_frames, float), PCM_AT(d_in, b, l, nb_frames, const float),
+                                          VAD_AT(d_vad, b, l, nb_frames), nb_frames, 0));
   return 0;
 }
 int rnnoise_process_frames_batch_device_s16(RNNoiseBatch *b, short *d_out, const short *d_in, float *d_vad, int nb_frames) {
   int l;
-  if (!b || !d_out || !d_in || nb_frames < 1) return -1;
-  FOR_LANES(b, l)
-    if (b200_engine_frames_device(b->engine[l], PCM_AT(d_out, b, l, nb_frames, short), PCM_AT(d_in, b, l, nb_frames, const short),
-                                  VAD_AT(d_vad, b, l, nb_frames), nb_frames, 1)) return -1;
+  if (!d_out || !d_in || nb_frames < 1 || !frame_call_ok(b, 1, 1)) return -1;
+  FAN_OUT(b, l, b200_engine_frames_device(b->engine[l], PCM_AT(d_out, b, l, nb_frames, short), PCM_AT(d_in, b, l, nb_frames, const short),
+                                          VAD_AT(d_vad, b, l, nb_frames), nb_frames, 1));
   return 0;
 }
 int rnnoise_batch_train_features(RNNoiseBatch *b, float *rec, const float *clean, const float *noisy, const float *vad_target,
                                  const int *noise_free, const int *lowpass, const int *band_lp) {
   int l;
-  if (!b || !rec || !clean || !noisy) return -1;
-  FOR_LANES(b, l)
-    if (b200_engine_train_features_host(b->engine[l], rec + (size_t)b->first[l] * RNNOISE_TRAIN_RECORD, PCM_AT(clean, b, l, 1, const float),
-                                        PCM_AT(noisy, b, l, 1, const float), ARR_AT(vad_target, b, l), ARR_AT(noise_free, b, l),
-                                        ARR_AT(lowpass, b, l), ARR_AT(band_lp, b, l))) return -1;
+  if (!rec || !clean || !noisy || !frame_call_ok(b, 1, 0)) return -1;
+  FAN_OUT(b, l, b200_engine_train_features_host(b->engine[l], rec + (size_t)b->first[l] * RNNOISE_TRAIN_RECORD, PCM_AT(clean, b, l, 1, const float),
+                                                PCM_AT(noisy, b, l, 1, const float), ARR_AT(vad_target, b, l), ARR_AT(noise_free, b, l),
+                                                ARR_AT(lowpass, b, l), ARR_AT(band_lp, b, l)));
   return 0;
 }
 int rnnoise_batch_train_features_device(RNNoiseBatch *b, float *d_rec, const float *d_clean, const float *d_noisy,
                                         const float *d_vad_target, const int *d_noise_free, const int *d_lowpass, const int *d_band_lp) {
   int l;
-  if (!b || !d_rec || !d_clean || !d_noisy) return -1;
-  FOR_LANES(b, l)
-    if (b200_engine_train_features_device(b->engine[l], d_rec + (size_t)b->first[l] * RNNOISE_TRAIN_RECORD, PCM_AT(d_clean, b, l, 1, const float),
-                                          PCM_AT(d_noisy, b, l, 1, const float), ARR_AT(d_vad_target, b, l), ARR_AT(d_noise_free, b, l),
-                                          ARR_AT(d_lowpass, b, l), ARR_AT(d_band_lp, b, l))) return -1;
+  if (!d_rec || !d_clean || !d_noisy || !frame_call_ok(b, 1, 1)) return -1;
+  FAN_OUT(b, l, b200_engine_train_features_device(b->engine[l], d_rec + (size_t)b->first[l] * RNNOISE_TRAIN_RECORD, PCM_AT(d_clean, b, l, 1, const float),
+                                                  PCM_AT(d_noisy, b, l, 1, const float), ARR_AT(d_vad_target, b, l), ARR_AT(d_noise_free, b, l),
+                                                  ARR_AT(d_lowpass, b, l), ARR_AT(d_band_lp, b, l)));
   return 0;
 }
 int rnnoise_batch_timeline_read(RNNoiseBatch *b, float *ms, int capacity) {
@@ -253,19 +344,41 @@ int rnnoise_batch_timeline_read(RNNoiseBatch *b, float *ms, int capacity) {
 }
 int rnnoise_batch_prefilter_device(RNNoiseBatch *b, const float *d_in_next) {
   int l;
-  if (!b || !d_in_next) return -1;
+  if (!d_in_next || !frame_call_ok(b, 0, 1)) return -1;
   FOR_LANES(b, l)
-    if (b200_engine_prefilter_device(b->engine[l], PCM_AT(d_in_next, b, l, 1, const float))) return -1;
+    if (b200_engine_prefilter_ahead(b->engine[l]) >= 2) return -1;   /* at most two frames ahead: nothing enqueued yet */
+  FAN_OUT(b, l, b200_engine_prefilter_device(b->engine[l], PCM_AT(d_in_next, b, l, 1, const float)));
   return 0;
 }
 /* One lane: the engine runs on the caller's stream itself.  Several lanes: every lane keeps its private
  * streams and brackets each device-pointer call with the caller's stream (engine.cu: parent_enter/leave). */
 int rnnoise_batch_set_stream(RNNoiseBatch *b, void *s) {
   int l;
-  if (!b) return -1;
+  if (!b || b->nb_devices != 1) return -1;
   if (b->lanes == 1) return b200_engine_set_stream(b->engine[0], s);
   FOR_LANES(b, l)
     if (b200_engine_set_parent(b->engine[l], s)) return -1;
+  return 0;
+}
+/* streams[k] = a cudaStream_t of device k of the batch (NULL entries / NULL array restore the private streams) */
+int rnnoise_batch_set_stream_multi(RNNoiseBatch *b, void *const *streams) {
+  int l, k = 0;
+  if (!b) return -1;
+  FOR_LANES(b, l) {
+    void *s;
+    DEV_OF_LANE(b, l, k);
+    s = streams ? streams[k] : NULL;
+    if (b->dev_lane[k + 1] - b->dev_lane[k] == 1 ? b200_engine_set_stream(b->engine[l], s) : b200_engine_set_parent(b->engine[l], s)) return -1;
+  }
+  return 0;
+}
+int rnnoise_batch_debug_set_frame_counter(RNNoiseBatch *b, long long frames) {
+  int l;
+  if (!b) return -1;
+  FOR_LANES(b, l)
+    if (b200_engine_prefilter_ahead(b->engine[l]) != 0) return -1;
+  FOR_LANES(b, l)
+    if (b200_engine_debug_set_frames(b->engine[l], frames)) return -1;
   return 0;
 }
 static int lane_of(const RNNoiseBatch *b, int s) {
@@ -276,7 +389,7 @@ static int lane_of(const RNNoiseBatch *b, int s) {
 }
 int rnnoise_batch_reset_stream(RNNoiseBatch *b, int s) {
   int l;
-  if (!b || s < 0 || s >= b->nb_streams) return -1;
+  if (!b || b->poisoned || s < 0 || s >= b->nb_streams) return -1;
   l = lane_of(b, s);
   return b200_engine_reset_stream(b->engine[l], s - b->first[l]);
 }

@@ -9,15 +9,15 @@
 #include "engine.h"
 
 #define FRAME 480
-struct B200Engine { int S, id, last_reset, profiling; void *stream, *parent; };
+struct B200Engine { int S, id, last_reset, profiling, device, ahead, fail_frames; long long frames; void *stream, *parent; };
 static int g_next_id = 0;
 void mock_reset_ids(void) { g_next_id = 0; }
 
 B200Engine *b200_engine_create(const B200HostModel *m, int nb_streams, int device) {
   B200Engine *e;
-  if (!m || nb_streams < 1 || device != 0) return NULL;
+  if (!m || nb_streams < 1 || device < 0 || device >= 8) return NULL;
   e = (B200Engine *)calloc(1, sizeof(*e));
-  e->S = nb_streams; e->id = g_next_id++; e->last_reset = -1;
+  e->S = nb_streams; e->id = g_next_id++; e->last_reset = -1; e->device = device;
   return e;
 }
 void b200_engine_destroy(B200Engine *e) { free(e); }
@@ -44,9 +44,13 @@ static void fill_s(B200Engine *e, short *out, const short *in, float *vad, int T
       if (vad) vad[(size_t)s * T + t] = 100 * e->id + s + t / 1000.f;
     }
 }
-int b200_engine_frame_device(B200Engine *e, float *o, const float *i, float *v) { fill_f(e, o, i, v, 1); return 0; }
+/* test hooks: engine `id` fails its next per-frame call; frames handled / device of an engine */
+static int g_fail_id = -1;
+void mock_fail_next(int id) { g_fail_id = id; }
+static int failing(B200Engine *e) { if (e->id == g_fail_id) { g_fail_id = -1; return 1; } e->frames++; e->ahead = 0; return 0; }
+int b200_engine_frame_device(B200Engine *e, float *o, const float *i, float *v) { if (failing(e)) return -1; fill_f(e, o, i, v, 1); return 0; }
 int b200_engine_frame_host(B200Engine *e, float *o, const float *i, float *v) { fill_f(e, o, i, v, 1); return 0; }
-int b200_engine_frame_host_async(B200Engine *e, float *o, const float *i, float *v) { fill_f(e, o, i, v, 1); return 0; }
+int b200_engine_frame_host_async(B200Engine *e, float *o, const float *i, float *v) { if (failing(e)) return -1; fill_f(e, o, i, v, 1); return 0; }
 int b200_engine_frame_device_s16(B200Engine *e, short *o, const short *i, float *v) { fill_s(e, o, i, v, 1); return 0; }
 int b200_engine_frame_host_async_s16(B200Engine *e, short *o, const short *i, float *v) { fill_s(e, o, i, v, 1); return 0; }
 int b200_engine_frames_device(B200Engine *e, void *o, const void *i, float *v, int T, int s16) {
@@ -73,7 +77,9 @@ int b200_engine_train_features_host(B200Engine *e, float *rec, const float *c, c
                                     const int *lp, const int *bl) { return b200_engine_train_features_device(e, rec, c, n, vt, nf, lp, bl); }
 /* the "hint" is recorded by writing nothing; it only has to receive the lane's slice: remember its first sample */
 static float g_hint[16];
-int b200_engine_prefilter_device(B200Engine *e, const float *d_in) { if (e->id < 16) g_hint[e->id] = d_in[0]; return 0; }
+int b200_engine_prefilter_device(B200Engine *e, const float *d_in) { if (e->id < 16) g_hint[e->id] = d_in[0]; e->ahead++; return 0; }
+int b200_engine_prefilter_ahead(const B200Engine *e) { return e->ahead; }
+int b200_engine_debug_set_frames(B200Engine *e, long long f) { if (e->frames) return -1; e->frames = f; return 0; }
 float mock_hint(int id) { return g_hint[id]; }
 int b200_engine_sync(B200Engine *e) { (void)e; return 0; }
 int b200_engine_reset_stream(B200Engine *e, int s) { if (s < 0 || s >= e->S) return -1; e->last_reset = s; return 0; }
@@ -93,5 +99,6 @@ int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst, int cap) 
   (void)what;
   if (s < 0 || s >= e->S || cap < 5) return -1;
   dst[0] = (float)e->id; dst[1] = (float)s; dst[2] = (float)e->last_reset; dst[3] = e->parent ? 1.f : 0.f; dst[4] = e->stream ? 1.f : 0.f;
+  if (cap >= 7) { dst[5] = (float)e->device; dst[6] = (float)e->frames; }
   return 5;
 }

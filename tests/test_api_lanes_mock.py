@@ -39,6 +39,15 @@ def M():
     L.rnnoise_batch_profile_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_char_p), ip, C.POINTER(ip)]
     L.rnnoise_batch_launches_per_frame.argtypes = [vp]
     L.mock_hint.restype = C.c_float; L.mock_hint.argtypes = [ip]
+    L.rnnoise_batch_create_multi.restype = vp; L.rnnoise_batch_create_multi.argtypes = [vp, ip, C.POINTER(ip), ip]
+    L.rnnoise_batch_get_devices.argtypes = [vp]
+    L.rnnoise_batch_get_shard.argtypes = [vp, ip] + [C.POINTER(ip)] * 3
+    L.rnnoise_process_frame_batch_device_multi.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.rnnoise_batch_prefilter_device_multi.argtypes = [vp, C.POINTER(vp)]
+    L.rnnoise_batch_set_stream_multi.argtypes = [vp, C.POINTER(vp)]
+    L.rnnoise_batch_debug_set_frame_counter.argtypes = [vp, C.c_longlong]
+    L.rnnoise_batch_sync.argtypes = [vp]
+    L.mock_fail_next.argtypes = [ip]
     L.model = L.rnnoise_model_from_filename(os.path.join(ROOT, "tests", "golden", "models", "tiny.bin").encode())
     assert L.model
     return L
@@ -135,4 +144,110 @@ def test_lane_partition_and_offsets(M, monkeypatch, S, env):
     ms = (C.c_float * 32)(); names = (C.c_char_p * 32)(); fr = C.c_int(0)
     assert L.rnnoise_batch_profile_read(b, ms, names, 32, C.byref(fr)) == 2 and fr.value == 7
     assert ms[0] == sum(1.0 + l for l in range(lanes)) and ms[1] == 10.0 * lanes and names[0] == b"k_a"
+    L.rnnoise_batch_destroy(b)
+
+
+@pytest.mark.parametrize("S,devs", [(8192, [0, 1]), (10001, [3, 1, 2]), (65536, list(range(8))), (5, [0, 1, 2, 3, 4, 5, 6, 7]), (300, [2, 0])])
+def test_multi_device_shards_lanes_and_pointer_offsets(M, monkeypatch, S, devs):
+    """rnnoise_batch_create_multi: contiguous shards per device (stream i -> device floor(i * G / S) up to the
+    remainder rule), lanes inside each shard, per-device pointers of the *_multi device call, host-buffer calls
+    over the whole batch."""
+    L = M
+    monkeypatch.delenv("RNNOISE_B200_LANES", raising=False)
+    L.mock_reset_ids()
+    arr = (C.c_int * len(devs))(*devs)
+    b = L.rnnoise_batch_create_multi(L.model, S, arr, len(devs))
+    assert b and L.rnnoise_batch_get_streams(b) == S
+    G = L.rnnoise_batch_get_devices(b)
+    assert G == min(len(devs), S)
+    shards = []
+    for k in range(G):
+        d, f, n = C.c_int(), C.c_int(), C.c_int()
+        assert L.rnnoise_batch_get_shard(b, k, C.byref(d), C.byref(f), C.byref(n)) == 0
+        shards.append((d.value, f.value, n.value))
+    assert L.rnnoise_batch_get_shard(b, G, None, None, None) == -1
+    base, rem = divmod(S, G)
+    assert [n for _, _, n in shards] == [base + (1 if k < rem else 0) for k in range(G)]
+    assert [d for d, _, _ in shards] == devs[:G] and shards[0][1] == 0
+    assert all(shards[k][1] + shards[k][2] == shards[k + 1][1] for k in range(G - 1)) and shards[-1][1] + shards[-1][2] == S
+    # every stream is handled by an engine on its shard's device
+    buf = (C.c_float * 8)()
+    probe = sorted({0, S - 1, S // 2} | {f for _, f, _ in shards} | {f + n - 1 for _, f, n in shards})
+    eng = {}
+    for s in probe:
+        assert L.rnnoise_batch_debug_read(b, 0, s, buf, 8) == 5
+        k = max(i for i in range(G) if shards[i][1] <= s)
+        assert int(buf[5]) == shards[k][0], (s, k)
+        eng[s] = (int(buf[0]), int(buf[1]))
+    # host-buffer call over the whole batch
+    x = (np.arange(S * 480, dtype=np.float32) % 977).reshape(S, 480)
+    out = np.zeros_like(x); vad = np.zeros(S, np.float32)
+    assert L.rnnoise_process_frame_batch(b, out.ctypes.data, x.ctypes.data, vad.ctypes.data) == 0
+    for s in probe:
+        assert np.array_equal(out[s], 2 * x[s] + 1000 * eng[s][0] + eng[s][1]) and vad[s] == 100 * eng[s][0] + eng[s][1]
+    # per-device pointers: each device's buffers hold only its shard
+    xs = [np.ascontiguousarray(x[f:f + n]) for _, f, n in shards]
+    outs = [np.zeros_like(a) for a in xs]; vads = [np.zeros(len(a), np.float32) for a in xs]
+    P = lambda lst: (C.c_void_p * G)(*[a.ctypes.data for a in lst])
+    assert L.rnnoise_process_frame_batch_device_multi(b, P(outs), P(xs), P(vads)) == 0
+    assert np.array_equal(np.concatenate(outs), out) and np.array_equal(np.concatenate(vads), vad)
+    assert L.rnnoise_process_frame_batch_device_multi(b, P(outs), P(xs), None) == 0
+    assert L.rnnoise_batch_prefilter_device_multi(b, P(xs)) == 0
+    # single-pointer device calls cannot address several devices
+    if G > 1:
+        assert L.rnnoise_process_frame_batch_device(b, out.ctypes.data, x.ctypes.data, None) == -1
+        assert L.rnnoise_batch_set_stream(b, C.c_void_p(0x10)) == -1
+    st = (C.c_void_p * G)(*[0x100 + k for k in range(G)])
+    assert L.rnnoise_batch_set_stream_multi(b, st) == 0
+    L.rnnoise_batch_destroy(b)
+
+
+def test_call_order_errors_leave_the_batch_intact_and_enqueue_errors_poison_it(M, monkeypatch):
+    L = M
+    monkeypatch.setenv("RNNOISE_B200_LANES", "3")
+    L.mock_reset_ids()
+    S = 600
+    b = L.rnnoise_batch_create(L.model, S, 0)
+    assert L.rnnoise_batch_get_lanes(b) == 3
+    x = np.ones((S, 480), np.float32); out = np.zeros_like(x)
+    buf = (C.c_float * 8)()
+
+    def frames_of_lanes():
+        res = []
+        for s in (0, 256, 599):
+            L.rnnoise_batch_debug_read(b, 0, s, buf, 8)
+            res.append(int(buf[6]))
+        return res
+    # a pending prefilter hint: host-buffer and multi-frame calls are refused before ANY lane is touched
+    assert L.rnnoise_batch_prefilter_device(b, x.ctypes.data) == 0
+    assert L.rnnoise_process_frame_batch(b, out.ctypes.data, x.ctypes.data, None) == -1
+    assert L.rnnoise_process_frames_batch(b, out.ctypes.data, x.ctypes.data, None, 1) == -1
+    assert L.rnnoise_batch_debug_set_frame_counter(b, 5) == -1
+    assert frames_of_lanes() == [0, 0, 0]
+    assert L.rnnoise_process_frame_batch_device(b, out.ctypes.data, x.ctypes.data, None) == 0   # consumes the hint
+    assert L.rnnoise_process_frame_batch(b, out.ctypes.data, x.ctypes.data, None) == 0
+    assert frames_of_lanes() == [2, 2, 2]
+    # third hint in a row is refused without touching any lane
+    assert L.rnnoise_batch_prefilter_device(b, x.ctypes.data) == 0 and L.rnnoise_batch_prefilter_device(b, x.ctypes.data) == 0
+    assert L.rnnoise_batch_prefilter_device(b, x.ctypes.data) == -1
+    assert L.rnnoise_process_frame_batch_device(b, out.ctypes.data, x.ctypes.data, None) == 0
+    # NULL arguments: refused, nothing enqueued
+    assert L.rnnoise_process_frame_batch_device(b, None, x.ctypes.data, None) == -1
+    assert frames_of_lanes() == [3, 3, 3]
+    # an enqueue error in the middle lane: lanes are out of step -> poisoned, every later call fails
+    L.mock_fail_next(1)
+    assert L.rnnoise_process_frame_batch_device(b, out.ctypes.data, x.ctypes.data, None) == -1
+    assert frames_of_lanes() == [4, 3, 3]
+    for _ in range(2):
+        assert L.rnnoise_process_frame_batch_device(b, out.ctypes.data, x.ctypes.data, None) == -1
+        assert L.rnnoise_process_frame_batch(b, out.ctypes.data, x.ctypes.data, None) == -1
+        assert L.rnnoise_process_frames_batch(b, out.ctypes.data, x.ctypes.data, None, 1) == -1
+        assert L.rnnoise_batch_reset_stream(b, 0) == -1
+    assert frames_of_lanes() == [4, 3, 3]
+    L.rnnoise_batch_destroy(b)
+    # frame-counter hook works on a fresh batch only
+    b = L.rnnoise_batch_create(L.model, 10, 0)
+    assert L.rnnoise_batch_debug_set_frame_counter(b, (1 << 30) - 3) == 0
+    assert L.rnnoise_process_frame_batch(b, out.ctypes.data, x.ctypes.data, None) == 0
+    assert L.rnnoise_batch_debug_set_frame_counter(b, 7) == -1
     L.rnnoise_batch_destroy(b)

@@ -83,3 +83,27 @@ def test_exported_blob_loads_in_the_product_parser_and_port(tmp_path):
     recs[idx] = (recs[idx][0], recs[idx][1], broken)
     bad = weights.write_blob(recs)
     assert not L.rnnoise_model_from_buffer(bad, len(bad))
+
+
+def test_sparse_index_overflow_and_repeated_positions_are_rejected():
+    """a block count of INT_MAX must not overflow the parser's bounds check, and a position repeated
+    inside one output block (which the reference's sparse kernel would ACCUMULATE, vec_avx.h:778-828, while a
+    dense expansion overwrites) is refused instead of being mis-read."""
+    import rnnoise_b200
+    L = rnnoise_b200.lib()
+    blob = open(os.path.join(MODELS, "tiny.bin"), "rb").read()
+    assert L.rnnoise_model_from_buffer(blob, len(blob))
+    for mutate in ("intmax", "repeat", "descending"):
+        recs = weights.read_blob(blob)
+        i = next(k for k, r in enumerate(recs) if r[0] == "gru2_recurrent_weights_idx")
+        idx = recs[i][2].copy()
+        assert idx[0] >= 2
+        if mutate == "intmax":
+            idx[0] = 2**31 - 1
+        elif mutate == "repeat":
+            idx[2] = idx[1]
+        else:
+            idx[1], idx[2] = idx[2], idx[1]
+        recs[i] = (recs[i][0], recs[i][1], idx)
+        bad = weights.write_blob(recs)
+        assert not L.rnnoise_model_from_buffer(bad, len(bad)), mutate
