@@ -15,6 +15,7 @@
 
 #include "../../include/rnnoise.h"
 #include "dsp_stream.cuh"
+#include "dsp_pitch.cuh"
 #include "dsp_tables.hpp"
 #include "engine.h"
 #include "rnn_kernels.cuh"
@@ -135,6 +136,21 @@ k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
 #endif
 }
 
+// Default pitch kernel (dsp_pitch.cuh): CTA = PG streams, one home warp per stream + three chain warps.
+// grid = ceil(S / PG), block = PG_THREADS, dynamic smem = PG * P2_STRIDE floats
+#define PITCH2_SMEM_BYTES (PG * P2_STRIDE * (int)sizeof(float))
+__global__ void __launch_bounds__(PG_THREADS, PG <= 8 ? 2 : 1) k_pitch2(Arena a, int f) {
+  extern __shared__ float sm[];
+  const int s0 = blockIdx.x * PG;
+  PitchGroup g;
+  g.n = min(PG, a.S - s0);
+  g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+  g.xb = a.xb + ((size_t)(f & 1) * a.S + s0) * FRAME_SIZE;
+  g.ring = a.ring + (size_t)s0 * PITCH_BUF_SIZE;
+  g.pitch_state = a.pitch_state + 2 * (size_t)s0;
+  pitch_group(sm, g);
+}
+
 #ifndef SPEC_MIN_BLOCKS
 #define SPEC_MIN_BLOCKS 12
 #endif
@@ -248,6 +264,7 @@ struct B200Engine {
   long long bq_frames;               // frames whose high-pass prefilter has been issued
   int use_tc;                       // GRU kernel: 2 = k_tc2<true> (default), 1 = k_gru_tc, 0 = dp4a cross-check
   int conv2_tc;                     // conv2 kernel: 1 = k_tc2<false> (default), 0 = dp4a cross-check
+  int pitch2;                       // pitch kernel: 1 = k_pitch2 (default), 0 = k_pitch (RNNOISE_B200_PITCH_KERNEL=v1 cross-check)
   int heads2;                       // heads kernel: 1 = k_heads2 (default), 0 = k_heads (RNNOISE_B200_HEADS_KERNEL=cpasync)
   GruTcMaps tc_maps[2][3];          // [frame parity][layer]
   GruTcMaps conv_maps;              // x = c2in, wi = conv2 weights
@@ -514,6 +531,8 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   // RNNOISE_B200_GRU_KERNEL = tc2 (default: persistent pipelined tcgen05) | tc1 (one tile per CTA) |
   // dp4a (CUDA-core cross-check); all three produce identical bits
   { const char *hk = getenv("RNNOISE_B200_HEADS_KERNEL"); e->heads2 = !(hk && !strcmp(hk, "cpasync")); }
+  { const char *pk = getenv("RNNOISE_B200_PITCH_KERNEL"); e->pitch2 = !(pk && !strcmp(pk, "v1")); }
+  ok = ok && cudaFuncSetAttribute(k_pitch2, cudaFuncAttributeMaxDynamicSharedMemorySize, PITCH2_SMEM_BYTES) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(k_heads2, cudaFuncAttributeMaxDynamicSharedMemorySize, H2_SMEM_BYTES) == cudaSuccess;
   const char *gk = getenv("RNNOISE_B200_GRU_KERNEL");
   e->use_tc = gk && !strcmp(gk, "dp4a") ? 0 : gk && !strcmp(gk, "tc1") ? 1 : 2;
@@ -583,6 +602,13 @@ static int parent_leave(B200Engine *e) {
   CK(cudaStreamWaitEvent(e->parent, e->ev_pout, 0));
   return 0;
 }
+static void launch_pitch(B200Engine *e, cudaStream_t st, int fr) {
+  const int S = e->a.S;
+  if (e->pitch2)
+    k_pitch2<<<(S + PG - 1) / PG, PG_THREADS, PITCH2_SMEM_BYTES, st>>>(e->a, fr);
+  else
+    k_pitch<<<(S + PITCH_NS - 1) / PITCH_NS, PITCH_NS * PITCH_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), st>>>(e->a, e->d_tables, fr);
+}
 static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *d_vad, int s16);
 extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float *d_in, float *d_vad) {
   if (!e || parent_enter(e) || frame_device_io(e, d_out, d_in, d_vad, 0)) return -1;
@@ -634,8 +660,7 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
     e->bq_frames = e->frames + 1;
   }
   MARK();
-  const int pitch_grid = (S + PITCH_NS - 1) / PITCH_NS;
-  k_pitch<<<pitch_grid, PITCH_NS * PITCH_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
+  launch_pitch(e, sf, fr);
   CK(cudaEventRecord(e->ev_ana[par], sf));   // xb[par] is free again
   TL(e, e->frames, TL_PITCH_END, sf);
   MARK();
@@ -879,8 +904,7 @@ extern "C" int b200_engine_train_features_device(B200Engine *e, float *d_rec, co
   CK(cudaStreamWaitEvent(st, e->ev_front[1], 0));
   const int par = (int)(e->frames & 1), fr = frame_arg(e->frames);
   CK(cudaMemcpyAsync(a.xb + (size_t)par * S * FRAME_SIZE, d_noisy, S * FRAME_SIZE * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  const int pitch_grid = (a.S + PITCH_NS - 1) / PITCH_NS;
-  k_pitch<<<pitch_grid, PITCH_NS * PITCH_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr);
+  launch_pitch(e, st, fr);
   TrainIo io;
   io.clean = d_clean; io.clean_mem = e->train_clean_mem; io.rec = d_rec;
   io.vad_target = d_vad_target; io.noise_free = d_noise_free; io.lowpass = d_lowpass; io.band_lp = d_band_lp;

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include "dsp_stream.cuh"
+#include "dsp_pitch.cuh"
 #include "dsp_tables.hpp"
 
 struct EmuStream {
@@ -146,6 +147,49 @@ void emu_synthesis(void *p, int q, const float *gains, float *out, float *lastg)
   a.out_s16 = nullptr;
   synthesis_stream(e->sm, a, &e->T);
   memcpy(lastg, s.lastg, sizeof(s.lastg));
+}
+// ---- the default pitch kernel's body (dsp_pitch.cuh: pitch_group, PG streams per CTA) + spectrum_stream ----
+struct EmuGroup {
+  DspTables T;
+  float xb[PG][FRAME_SIZE], ring[PG][PITCH_BUF_SIZE], pitch_state[PG][2], hp[PG][2];
+  float spec[PG][4 * FREQ_SIZE], band[PG][96], features[PG][NB_FEATURES];
+  int silence[PG];
+  long frames;
+  alignas(16) float sm[PG * P2_STRIDE > 8192 ? PG * P2_STRIDE : 8192];
+};
+int emu_group_streams(void) { return PG; }
+void *emu_group_create(void) {
+  EmuGroup *e = (EmuGroup *)calloc(1, sizeof(EmuGroup));
+  b200_fill_dsp_tables(&e->T);
+  return e;
+}
+void emu_group_destroy(void *p) { free(p); }
+// biquad + pitch_group + spectrum of one frame for n <= PG streams (in: [n][480]); outputs per stream:
+// features [n][65], pitch [n][2] = {period, gain}, silence [n]
+void emu_group_analysis(void *p, const float *in, int n, float *features, float *pitch, int *silence) {
+  EmuGroup *e = (EmuGroup *)p;
+  const long f = e->frames++;
+  for (int q = 0; q < n; q++) {
+    float m0 = e->hp[q][0], m1 = e->hp[q][1];
+    for (int i = 0; i < FRAME_SIZE; i++) e->xb[q][i] = biquad_step(in[q * FRAME_SIZE + i], m0, m1);
+    e->hp[q][0] = m0; e->hp[q][1] = m1;
+  }
+  PitchGroup g;
+  g.xb = &e->xb[0][0]; g.ring = &e->ring[0][0]; g.pitch_state = &e->pitch_state[0][0];
+  g.n = n;
+  g.ring_base = (int)(((f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
+  pitch_group(e->sm, g);
+  for (int q = 0; q < n; q++) {
+    SpectrumArgs a;
+    a.ring = e->ring[q]; a.ring_base = g.ring_base; a.pitch_state = e->pitch_state[q];
+    a.spec_out = e->spec[q]; a.band_out = e->band[q]; a.features = e->features[q]; a.silence = &e->silence[q];
+    a.lowpass = FREQ_SIZE;
+    spectrum_stream<false>(e->sm, a, &e->T);
+    memcpy(features + q * NB_FEATURES, e->features[q], sizeof(e->features[q]));
+    int period; memcpy(&period, &e->pitch_state[q][0], 4);
+    pitch[2 * q] = (float)period; pitch[2 * q + 1] = e->pitch_state[q][1];
+    silence[q] = e->silence[q];
+  }
 }
 // rd_candidate() exposed for an exhaustive check of its division-free arithmetic
 void emu_rd_candidate(int k, int T0, int *T1, int *T1b) { rd_candidate(k, T0, T1, T1b); }

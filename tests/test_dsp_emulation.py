@@ -18,7 +18,7 @@ EMU_SO = os.path.join(ROOT, "tests", "emu", "libemu_dsp.so")
 
 @pytest.fixture(scope="module")
 def emu():
-    deps = [EMU_SRC] + [os.path.join(ROOT, "rnnoise_b200", "csrc", f) for f in ("dsp_core.cuh", "dsp_stream.cuh", "dsp_tables.hpp")]
+    deps = [EMU_SRC] + [os.path.join(ROOT, "rnnoise_b200", "csrc", f) for f in ("dsp_core.cuh", "dsp_stream.cuh", "dsp_pitch.cuh", "dsp_tables.hpp")]
     if not os.path.exists(EMU_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMU_SO) for d in deps):
         subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-DPITCH_NS=4",
                         "-I", os.path.join(ROOT, "rnnoise_b200", "csrc"), EMU_SRC, "-o", EMU_SO], check=True)
@@ -29,6 +29,9 @@ def emu():
     E.emu_get.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_float)] * 6
     E.emu_synthesis.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_float)] * 3
     E.emu_advance.argtypes = [C.c_void_p]
+    E.emu_group_create.restype = C.c_void_p
+    E.emu_group_destroy.argtypes = [C.c_void_p]
+    E.emu_group_analysis.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]
     return E
 
 
@@ -77,3 +80,28 @@ def test_remove_doubling_candidates_exact_over_whole_domain(emu):
                 w1 = (2 * T0 + k) // (2 * k)
                 want = (w1, (T0 if w1 + T0 > 384 else T0 + w1) if k == 2 else (2 * second_check[k] * T0 + k) // (2 * k))
             assert (t1.value, t1b.value) == want, (k, T0)
+
+
+@pytest.mark.parametrize("first,n,frames", [(0, 16, 80), (16, 16, 40), (40, 5, 40), (15, 1, 150), (100, 11, 30)])
+def test_pitch_group_kernel_source_is_bit_identical_to_port(emu, port_default, first, n, frames):
+    """The default pitch kernel's body (dsp_pitch.cuh: PG streams per CTA, home warps + chain warps, refinement
+    correlations after the decision) executed thread id by thread id: pitch period, pitch gain, silence flag and
+    all 65 features (which carry the pitch-lagged spectrum) must equal the port's bits; full and partial groups,
+    streams with digital silence (every 16th), 150-frame run for the continuity prior."""
+    assert emu.emu_group_streams() >= n
+    ids = list(range(first, first + n))
+    pcm = np.stack([stream_pcm(s, frames) for s in ids], axis=1)
+    states = [port_default.create() for _ in ids]
+    e = emu.emu_group_create()
+    feat = np.zeros((n, 65), np.float32); pitch = np.zeros((n, 2), np.float32); sil = np.zeros(n, np.int32)
+    for f in range(frames):
+        emu.emu_group_analysis(e, fptr(np.ascontiguousarray(pcm[f])), n, fptr(feat), fptr(pitch), sil.ctypes.data_as(C.POINTER(C.c_int)))
+        for q, s in enumerate(ids):
+            b = port_default.process_frame(states[q], pcm[f, q])
+            assert int(pitch[q, 0]) == b["pitch"], (f, s, int(pitch[q, 0]), b["pitch"])
+            assert pitch[q, 1:].tobytes() == np.float32(b["pitch_gain"]).tobytes(), (f, s)
+            assert sil[q] == b["silence"], (f, s)
+            assert feat[q].tobytes() == b["features"].tobytes(), (f, s)
+    emu.emu_group_destroy(e)
+    for st in states:
+        port_default.destroy(st)

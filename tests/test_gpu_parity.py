@@ -244,6 +244,20 @@ def test_gru_tensor_core_paths_equal_dp4a_path(rb, models_dir):
         for s in (0, 31, 32, 288, 299):
             assert np.array_equal(bits(a.debug("gains", s)), bits(b.debug("gains", s))), (s, f)
     a.destroy(); b.destroy()
+    # pitch: group kernel (default: 16 streams per CTA, home + chain warps) vs the round-1 kernel (4 streams per CTA);
+    # S = 300 leaves a partial group (12 of 16 streams) in the last CTA
+    os.environ["RNNOISE_B200_PITCH_KERNEL"] = "v1"
+    a = rb.Batch(model, S)
+    del os.environ["RNNOISE_B200_PITCH_KERNEL"]
+    b = rb.Batch(model, S)
+    for f in range(3 * frames):
+        x = pcm[f % frames]
+        oa, va = a.process(x); ob, vb = b.process(x)
+        assert np.array_equal(bits(oa), bits(ob)) and np.array_equal(bits(va), bits(vb)), f
+        for s in (0, 15, 16, 143, 287, 288, 299):
+            for k in ("pitch", "features", "P"):
+                assert np.array_equal(bits(a.debug(k, s)), bits(b.debug(k, s))), (k, s, f)
+    a.destroy(); b.destroy()
     model.free()
 
 
