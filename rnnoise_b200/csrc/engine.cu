@@ -21,6 +21,7 @@
 #include "rnn_kernels.cuh"
 #include "gru_tc.cuh"
 #include "heads_kernel.cuh"
+#include "net_kernel.cuh"
 
 #define CK(call)                                                                          \
   do {                                                                                    \
@@ -268,6 +269,9 @@ struct B200Engine {
   int heads2;                       // heads kernel: 1 = k_heads2 (default), 0 = k_heads (RNNOISE_B200_HEADS_KERNEL=cpasync)
   GruTcMaps tc_maps[2][3];          // [frame parity][layer]
   GruTcMaps conv_maps;              // x = c2in, wi = conv2 weights
+  int net_fused;                    // 1 = k_net: conv2 + 3 GRU layers in one cluster kernel (default); 0 = one launch per layer
+  NetMaps net_maps[2];              // [frame parity]
+  NetPtrs net_ptrs[2];
   // optional per-kernel timing (rnnoise_batch_profile)
   int profiling, prof_frames;
   cudaEvent_t ev[NKERNELS + 1];
@@ -564,6 +568,30 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
     e->conv_maps.h = e->conv_maps.x; e->conv_maps.wr = e->conv_maps.wi;
     ok = ok && cudaFuncSetAttribute(k_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<false>(3 * m->cond, m->gru)) == cudaSuccess;
   }
+  // fused network kernel (net_kernel.cuh): needs the persistent tcgen05 GRU path and conv2 on the tensor cores
+  { const char *nk = getenv("RNNOISE_B200_NET_KERNEL"); e->net_fused = !(nk && !strcmp(nk, "layers")) && e->use_tc == 2 && e->conv2_tc; }
+  if (ok && e->net_fused) {
+    const size_t hs = Ss * m->gru;
+    for (int par = 0; par < 2; par++) {
+      NetMaps &nm = e->net_maps[par];
+      NetPtrs &np = e->net_ptrs[par];
+      memset(&np, 0, sizeof(np));
+      nm.x[0] = e->conv_maps.x; nm.wi[0] = e->conv_maps.wi; nm.h[0] = e->conv_maps.x; nm.wr[0] = e->conv_maps.wi;
+      np.scale_i[0] = dm.conv2.scale; np.subias_i[0] = dm.conv2.subias;
+      np.out_f32[0] = a.conv2_out; np.out_u8[0] = a.conv2_out_u8;
+      for (int l = 0; l < 3; l++) {
+        const GruTcMaps &mp = e->tc_maps[par][l];
+        nm.x[l + 1] = mp.x; nm.h[l + 1] = mp.h; nm.wi[l + 1] = mp.wi; nm.wr[l + 1] = mp.wr;
+        np.scale_i[l + 1] = dm.gru_in[l].scale; np.subias_i[l + 1] = dm.gru_in[l].subias;
+        np.scale_r[l + 1] = dm.gru_rec[l].scale; np.subias_r[l + 1] = dm.gru_rec[l].subias; np.diag[l + 1] = dm.gru_rec[l].diag;
+        np.h_old[l + 1] = a.hbuf + ((size_t)(par ^ 1) * 3 + l) * hs;
+        np.out_f32[l + 1] = a.hbuf + ((size_t)par * 3 + l) * hs;
+        np.out_u8[l + 1] = a.hbuf_u8 + ((size_t)par * 3 + l) * hs;
+      }
+    }
+    ok = cudaFuncSetAttribute(k_net, cudaFuncAttributeMaxDynamicSharedMemorySize, net_smem_bytes(3 * m->cond, m->gru)) == cudaSuccess;
+    if (!ok) fprintf(stderr, "[rnnoise_b200] fused network kernel setup failed\n");
+  }
   if (!ok || cudaDeviceSynchronize() != cudaSuccess) {
     fprintf(stderr, "[rnnoise_b200] engine allocation/upload failed: %s\n", cudaGetErrorString(cudaGetLastError()));
     b200_engine_destroy(e);
@@ -585,7 +613,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 extern "C" int b200_engine_streams(const B200Engine *e) { return e ? e->a.S : 0; }
-extern "C" int b200_engine_launches_per_frame(const B200Engine *) { return NKERNELS; }
+extern "C" int b200_engine_launches_per_frame(const B200Engine *e) { return e && e->net_fused ? NKERNELS - 3 : NKERNELS; }
 
 // Parent-stream bracketing of device-pointer calls (lanes).  Only the kernels that touch the caller's
 // buffers are ordered after the caller's stream -- the prefilter that reads the input, and the output heads /
@@ -677,6 +705,10 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   k_conv1<<<gts, 128, 0, st>>>(S, e->dm, feat, a.conv1_state, sil, a.c2in);
   MARK();
   const bool pdl = e->pdl && !e->profiling;
+  if (e->net_fused) {
+    k_net<<<dim3((S + TC_M - 1) / TC_M, 4), P_THREADS, net_smem_bytes(3 * cond, gru), st>>>(S, 3 * cond, gru, e->net_maps[par], e->net_ptrs[par], sil);
+    MARK(); MARK(); MARK(); MARK();   // one launch covers the conv2 and GRU slots of the per-kernel profile
+  } else {
   if (e->conv2_tc)
     CK(launch_pdl(k_tc2<false>, dim3((S + TC_M - 1) / TC_M, 4), dim3(P_THREADS), tc2_smem_bytes<false>(3 * cond, gru), st, pdl,
                   S, 3 * cond, gru, e->conv_maps, e->dm.conv2, e->dm.conv2, (const float *)nullptr, a.conv2_out, a.conv2_out_u8, sil));
@@ -698,8 +730,9 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
     }
     MARK();
   }
+  }
   if (e->parent) CK(cudaStreamWaitEvent(st, e->ev_pin, 0));   // first kernel that writes the caller's buffers
-  const bool pdl_heads = pdl && e->use_tc == 2;   // only the k_tc2 predecessors are PDL-aware
+  const bool pdl_heads = pdl && e->use_tc == 2 && !e->net_fused;   // only the k_tc2 predecessors are PDL-aware
   if (e->heads2)
     CK(launch_pdl(k_heads2, dim3((S + H2_TS - 1) / H2_TS), dim3(160), H2_SMEM_BYTES, st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
                   (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
@@ -995,7 +1028,7 @@ extern "C" int b200_engine_profile_read(B200Engine *e, float *ms, const char **n
   if (!e || !ms || capacity < NKERNELS) return -1;
   for (int i = 0; i < NKERNELS; i++) {
     ms[i] = (float)e->prof_ms[i];
-    if (names) names[i] = kKernelNames[i];
+    if (names) names[i] = e->net_fused && i == 4 ? "k_net" : e->net_fused && i >= 5 && i <= 7 ? "-" : kKernelNames[i];
   }
   if (frames) *frames = e->prof_frames;
   return NKERNELS;

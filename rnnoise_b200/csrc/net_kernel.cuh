@@ -1,0 +1,281 @@
+// net_kernel.cuh -- conv2 -> GRU1 -> GRU2 -> GRU3 of compute_rnn() (reference src/rnn.c:44-60) as ONE persistent
+// tcgen05 kernel over a 4-CTA thread-block cluster per 128-stream tile (the default network path; the per-layer
+// kernels k_tc2<> of gru_tc.cuh run the same arithmetic one layer per launch and are kept as cross-checks).
+//
+//   cluster = 4 CTAs = one tile of 128 streams; CTA r of the cluster owns output units [r*N/4, (r+1)*N/4) of
+//   EVERY layer.  Per layer a CTA needs the whole u8 activation rows of the previous layer (K = N bytes per
+//   stream): each CTA writes its unit quarter (fp32 state + u8 operand mirror) to global memory, the cluster
+//   synchronises (barrier.cluster release/acquire + proxy fence), and every CTA TMA-loads the full 128 x K tile
+//   back from L2.  The recurrent operand Hu8 of the NEXT layer does not depend on this frame, so its TMA load is
+//   issued as soon as the current layer's MMAs have retired and hides behind the epilogue tail; the weight-slice
+//   ring (3 stages) and the TMEM accumulator ring (2 stages) simply run on across layer boundaries, so the weights
+//   of the next layer's first slices are already in shared memory when its activations arrive.
+//
+//   warp 16 (one elected thread): TMA producer + tcgen05.mma issuer      (as in k_tc2)
+//   warps 0..15                 : epilogue, warp w -> TMEM lane quarter w & 3, units 4 * (w >> 2) .. + 4 of a slice
+//
+// Against one launch per layer this removes four kernel boundaries (drain, launch latency, barrier/TMEM/parameter
+// prologue, cold TMA pipeline) per frame and lane.  Arithmetic: identical to k_tc2 / the dp4a kernels, bit for bit
+// (exact s32 accumulators; (float)acc*scale + subias; fma(diag,h,.); Pade sigmoid/tanh; h' = z*h + (1-z)*n).
+// grid = (ceil(S/128), 4), cluster (1,4,1), block = 544, dynamic smem = net_smem_bytes(), 1 CTA / SM.
+#pragma once
+#include "gru_tc.cuh"
+
+#define NET_LAYERS 4   // conv2 + 3 GRU
+
+struct NetMaps {       // TMA descriptors of one frame parity
+  CUtensorMap x[NET_LAYERS], h[NET_LAYERS], wi[NET_LAYERS], wr[NET_LAYERS];   // h / wr unused for layer 0 (conv2)
+};
+struct NetPtrs {
+  const float *scale_i[NET_LAYERS], *subias_i[NET_LAYERS];   // input matrix (conv2: the only matrix)
+  const float *scale_r[NET_LAYERS], *subias_r[NET_LAYERS], *diag[NET_LAYERS];
+  const float *h_old[NET_LAYERS];     // fp32 state of the previous frame (GRU layers)
+  float *out_f32[NET_LAYERS];         // conv2_out / new fp32 state
+  uint8_t *out_u8[NET_LAYERS];        // their u8 operand mirrors
+};
+
+__host__ __device__ constexpr int net_stage_bytes(int K) { return 2 * (K / TC_KATOM) * (3 * P_SLICE * TC_KATOM); }
+__host__ __device__ constexpr int net_prm_floats(int N) { return (2 + 3 * 16) * (N / 4); }
+__host__ __device__ constexpr int net_smem_bytes(int Kc, int N) {
+  // A tiles: X (max(Kc, N) bytes per row) + H (N); B ring; parameters of all layers; barriers
+  return 1024 + ((Kc > N ? Kc : N) / TC_KATOM + N / TC_KATOM) * TC_A_ATOM_BYTES + P_STAGES * net_stage_bytes(N) +
+         net_prm_floats(N) * 4 + 24 * 8 + 64;
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Kc = conv2's contraction length (3 * cond), N = gru; both multiples of 128.
+__global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(P_THREADS, 1)
+k_net(int S, int Kc, int N, const __grid_constant__ NetMaps maps, const __grid_constant__ NetPtrs p, const int *__restrict__ silence) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int upc = N / 4, nslice = upc / P_SLICE;
+  const int atoms_c = Kc / TC_KATOM, atoms_n = N / TC_KATOM, atoms_x = atoms_c > atoms_n ? atoms_c : atoms_n;
+  const int m0 = blockIdx.x * TC_M, jq = blockIdx.y * upc;
+  uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t *sAx = base, *sAh = sAx + atoms_x * TC_A_ATOM_BYTES;
+  uint8_t *sB = sAh + atoms_n * TC_A_ATOM_BYTES;
+  const int stage_bytes = net_stage_bytes(N);
+  float *prm = (float *)(sB + P_STAGES * stage_bytes);   // conv: [2][upc]; then per GRU layer [upc][16]
+  uint64_t *bars = (uint64_t *)(prm + net_prm_floats(N));
+  uint32_t *tmem_slot = (uint32_t *)(bars + 24);
+  const uint32_t bar_x = smem_u32(&bars[0]), bar_h = smem_u32(&bars[1]), bar_adone = smem_u32(&bars[2]);
+  auto bar_bfull = [&](int i) { return smem_u32(&bars[4 + i]); };
+  auto bar_bempty = [&](int i) { return smem_u32(&bars[8 + i]); };
+  auto bar_tfull = [&](int i) { return smem_u32(&bars[12 + i]); };
+  auto bar_tempty = [&](int i) { return smem_u32(&bars[14 + i]); };
+
+  if (tid == 0) {
+    mbar_init(bar_x, 1); mbar_init(bar_h, 1); mbar_init(bar_adone, 1);
+    for (int i = 0; i < P_STAGES; i++) { mbar_init(bar_bfull(i), 1); mbar_init(bar_bempty(i), 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(bar_tfull(i), 1); mbar_init(bar_tempty(i), P_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // epilogue parameters of this CTA's unit quarter, all layers
+  for (int i = tid; i < 2 * upc; i += blockDim.x) prm[i] = (i < upc ? p.scale_i[0] : p.subias_i[0])[jq + i % upc];
+  for (int L = 1; L < NET_LAYERS; L++) {
+    float *pl = prm + 2 * upc + (L - 1) * 16 * upc;
+    for (int i = tid; i < 16 * upc; i += blockDim.x) {
+      // per unit u: {sc_i, sb_i, sc_r, sb_r} for z, r, n, then {diag_z, diag_r, diag_n, 0}: four LDS.128
+      const int u = i >> 4, c = i & 15;
+      float v = 0.f;
+      if (c < 12) {
+        const int g = c >> 2, w = c & 3;
+        v = (w == 0 ? p.scale_i[L] : w == 1 ? p.subias_i[L] : w == 2 ? p.scale_r[L] : p.subias_r[L])[g * N + jq + u];
+      } else if (c < 15) {
+        v = p.diag[L][(c - 12) * N + jq + u];
+      }
+      pl[i] = v;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  cluster_sync_all();   // every CTA of the cluster is up (barriers initialised) before the first cross-CTA dependency
+
+  if (warp == P_EPI_WARPS) {
+    // ------------------------------------------------------------------------------------------------
+    // producer / MMA issuer: lane 0 works, the whole warp takes part in the cluster barriers
+    // ------------------------------------------------------------------------------------------------
+    int job = 0;   // global slice index over all layers: weight stage job % P_STAGES, TMEM stage job & 1
+    auto load_B = [&](int j) {
+      const int L = j / nslice, s = j - L * nslice, st = j % P_STAGES;
+      uint8_t *dst = sB + st * stage_bytes;
+      if (L == 0) {
+        const int batom = P_SLICE * TC_KATOM;
+        mbar_expect_tx(bar_bfull(st), (uint32_t)(atoms_c * batom));
+        for (int a = 0; a < atoms_c; a++)
+          tma_load_2d(smem_u32(dst + a * batom), &maps.wi[0], bar_bfull(st), a * TC_KATOM, jq + s * P_SLICE);
+      } else {
+        const int batom = 3 * P_SLICE * TC_KATOM, row = (blockIdx.y * nslice + s) * 3 * P_SLICE;
+        mbar_expect_tx(bar_bfull(st), (uint32_t)(2 * atoms_n * batom));
+        for (int a = 0; a < atoms_n; a++) {
+          tma_load_2d(smem_u32(dst + a * batom), &maps.wi[L], bar_bfull(st), a * TC_KATOM, row);
+          tma_load_2d(smem_u32(dst + (atoms_n + a) * batom), &maps.wr[L], bar_bfull(st), a * TC_KATOM, row);
+        }
+      }
+    };
+    const int njobs = NET_LAYERS * nslice;
+    if (lane == 0) {
+      for (int j = 0; j < P_STAGES && j < njobs; j++) load_B(j);
+      mbar_expect_tx(bar_x, (uint32_t)(atoms_c * TC_A_ATOM_BYTES));
+      for (int a = 0; a < atoms_c; a++) tma_load_2d(smem_u32(sAx + a * TC_A_ATOM_BYTES), &maps.x[0], bar_x, a * TC_KATOM, m0);
+      mbar_expect_tx(bar_h, (uint32_t)(atoms_n * TC_A_ATOM_BYTES));   // recurrent operand of GRU1: previous frame's state
+      for (int a = 0; a < atoms_n; a++) tma_load_2d(smem_u32(sAh + a * TC_A_ATOM_BYTES), &maps.h[1], bar_h, a * TC_KATOM, m0);
+    }
+    for (int L = 0; L < NET_LAYERS; L++) {
+      if (lane == 0) {
+        const int natoms = L == 0 ? atoms_c : atoms_n, nmat = L == 0 ? 1 : 2;
+        const int kN = L == 0 ? P_SLICE : 3 * P_SLICE, batom = kN * TC_KATOM;
+        const uint32_t idesc = umma_idesc_i8(TC_M, kN);
+        mbar_wait(bar_x, (uint32_t)(L & 1));
+        if (L >= 1) mbar_wait(bar_h, (uint32_t)((L - 1) & 1));
+        for (int s = 0; s < nslice; s++, job++) {
+          const int st = job % P_STAGES, ts = job & 1;
+          mbar_wait(bar_bfull(st), (uint32_t)((job / P_STAGES) & 1));
+          mbar_wait(bar_tempty(ts), (uint32_t)(((job >> 1) & 1) ^ 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint8_t *Bs = sB + st * stage_bytes;
+          for (int g = 0; g < nmat; g++) {
+            const uint8_t *A = g ? sAh : sAx;
+            for (int a = 0; a < natoms; a++) {
+              const uint64_t ad = umma_desc_sw128(smem_u32(A + a * TC_A_ATOM_BYTES));
+              const uint64_t bd = umma_desc_sw128(smem_u32(Bs + (g * natoms + a) * batom));
+#pragma unroll
+              for (int k = 0; k < TC_KATOM / 32; k++)
+                umma_i8(tmem + ts * (6 * P_SLICE) + g * kN, ad + (uint64_t)(k * 32 >> 4), bd + (uint64_t)(k * 32 >> 4), idesc, (a | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(bar_bempty(st));
+          umma_commit(bar_tfull(ts));
+          if (job >= 1 && job - 1 + P_STAGES < njobs) {   // refill the stage the previous job used
+            mbar_wait(bar_bempty((job - 1) % P_STAGES), (uint32_t)(((job - 1) / P_STAGES) & 1));
+            load_B(job - 1 + P_STAGES);
+          }
+        }
+        if (L + 1 < NET_LAYERS) {
+          // the activation tiles are reusable once this layer's MMAs have retired: fetch the next layer's recurrent
+          // operand right away (it only depends on the previous frame)
+          umma_commit(bar_adone);
+          mbar_wait(bar_adone, (uint32_t)(L & 1));
+          if (L + 1 >= 2) {   // (GRU1's was loaded in the prologue: conv2 does not use the tile)
+            mbar_expect_tx(bar_h, (uint32_t)(atoms_n * TC_A_ATOM_BYTES));
+            for (int a = 0; a < atoms_n; a++) tma_load_2d(smem_u32(sAh + a * TC_A_ATOM_BYTES), &maps.h[L + 1], bar_h, a * TC_KATOM, m0);
+          }
+        }
+      }
+      if (L + 1 < NET_LAYERS) {
+        __syncwarp();
+        cluster_sync_all();   // all four unit quarters of layer L are in global memory
+        if (lane == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(bar_x, (uint32_t)(atoms_n * TC_A_ATOM_BYTES));
+          for (int a = 0; a < atoms_n; a++) tma_load_2d(smem_u32(sAx + a * TC_A_ATOM_BYTES), &maps.x[L + 1], bar_x, a * TC_KATOM, m0);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------------
+    // epilogue warps
+    // ------------------------------------------------------------------------------------------------
+    const int lq = warp & 3, ch = warp >> 2;
+    const int srow = m0 + lq * 32 + lane;
+    const bool live = srow < S;
+    const bool silent = live ? silence[srow] != 0 : true;
+    const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
+    int job = 0;
+    for (int L = 0; L < NET_LAYERS; L++) {
+      const float *h_old = p.h_old[L];
+      float *out_f32 = p.out_f32[L];
+      uint8_t *out_u8 = p.out_u8[L];
+      const float *pl = prm + (L == 0 ? 0 : 2 * upc + (L - 1) * 16 * upc);
+      float hcur[P_UPT], hnext[P_UPT];
+      auto load_h = [&](int s, float (&dst)[P_UPT]) {
+        if (L > 0 && live && s < nslice) {
+          float4 a = __ldg((const float4 *)&h_old[(size_t)srow * N + jq + s * P_SLICE + ch * P_UPT]);
+          dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < P_UPT; q++) dst[q] = 0.f;
+        }
+      };
+      load_h(0, hcur);
+      for (int s = 0; s < nslice; s++, job++) {
+        const int ts = job & 1;
+        load_h(s + 1, hnext);
+        mbar_wait(bar_tfull(ts), (uint32_t)((job >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t t0 = trow + ts * (6 * P_SLICE) + ch * P_UPT;
+        const int ub = s * P_SLICE + ch * P_UPT;     // unit index inside this CTA's quarter
+        float outv[P_UPT];
+        if (L > 0) {
+          int az[P_UPT], ar[P_UPT], an[P_UPT], bz[P_UPT], br[P_UPT], bn[P_UPT];
+          tmem_ld4(t0 + 0 * P_SLICE, az); tmem_ld4(t0 + 1 * P_SLICE, ar); tmem_ld4(t0 + 2 * P_SLICE, an);
+          tmem_ld4(t0 + 3 * P_SLICE, bz); tmem_ld4(t0 + 4 * P_SLICE, br); tmem_ld4(t0 + 5 * P_SLICE, bn);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty(ts));
+#pragma unroll
+          for (int q = 0; q < P_UPT; q++) {
+            const int u = ub + q;
+            const float h = hcur[q];
+            float out = h;
+            if (!silent) {
+              const float4 pz = *(const float4 *)&pl[16 * u], pr = *(const float4 *)&pl[16 * u + 4];
+              const float4 pn = *(const float4 *)&pl[16 * u + 8], pd = *(const float4 *)&pl[16 * u + 12];
+              float zi = (float)az[q] * pz.x + pz.y;
+              float ri = (float)ar[q] * pr.x + pr.y;
+              float ni = (float)an[q] * pn.x + pn.y;
+              float zr = fmaf(pd.x, h, (float)bz[q] * pz.z + pz.w);
+              float rr = fmaf(pd.y, h, (float)br[q] * pr.z + pr.w);
+              float nr = fmaf(pd.z, h, (float)bn[q] * pn.z + pn.w);
+              float z = act_sigmoid(zi + zr);
+              float r = act_sigmoid(ri + rr);
+              float n = act_tanh(ni + nr * r);
+              out = z * h + (1 - z) * n;
+            }
+            outv[q] = out;
+          }
+        } else {
+          int acc[P_UPT];
+          tmem_ld4(t0, acc);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty(ts));
+#pragma unroll
+          for (int q = 0; q < P_UPT; q++) outv[q] = act_tanh((float)acc[q] * pl[ub + q] + pl[upc + ub + q]);
+        }
+        if (live) {
+          *(float4 *)&out_f32[(size_t)srow * N + jq + ub] = make_float4(outv[0], outv[1], outv[2], outv[3]);
+          *(uint32_t *)&out_u8[(size_t)srow * N + jq + ub] = quant4(outv[0], outv[1], outv[2], outv[3]);
+        }
+#pragma unroll
+        for (int q = 0; q < P_UPT; q++) hcur[q] = hnext[q];
+      }
+      if (L + 1 < NET_LAYERS) {
+        // this thread's part of layer L is written: make it visible to the TMA (async proxy) reads of the whole
+        // cluster, then wait until every CTA has done the same
+        fence_proxy_async();
+        cluster_sync_all();
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P_TMEM_COLS) : "memory");
+  }
+  cluster_sync_all();   // no CTA of the cluster exits while a peer could still be arriving on the cluster barrier
+}

@@ -244,6 +244,19 @@ def test_gru_tensor_core_paths_equal_dp4a_path(rb, models_dir):
         for s in (0, 31, 32, 288, 299):
             assert np.array_equal(bits(a.debug("gains", s)), bits(b.debug("gains", s))), (s, f)
     a.destroy(); b.destroy()
+    # network: one fused cluster kernel for conv2 + 3 GRU layers (default) vs one launch per layer
+    os.environ["RNNOISE_B200_NET_KERNEL"] = "layers"
+    a = rb.Batch(model, S)
+    del os.environ["RNNOISE_B200_NET_KERNEL"]
+    b = rb.Batch(model, S)
+    for f in range(2 * frames):
+        x = pcm[f % frames]
+        oa, va = a.process(x); ob, vb = b.process(x)
+        for s in (0, 127, 128, 255, 256, 299):
+            for k in ("conv2_out", "gru1", "gru2", "gru3", "gains"):
+                assert np.array_equal(bits(a.debug(k, s)), bits(b.debug(k, s))), (k, s, f)
+        assert np.array_equal(bits(oa), bits(ob)) and np.array_equal(bits(va), bits(vb)), f
+    a.destroy(); b.destroy()
     # pitch: group kernel (default: 16 streams per CTA, home + chain warps) vs the round-1 kernel (4 streams per CTA);
     # S = 300 leaves a partial group (12 of 16 streams) in the last CTA
     os.environ["RNNOISE_B200_PITCH_KERNEL"] = "v1"

@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
-"""Same-box A/B of the two pitch kernels: per-kernel CUDA-event times (serialised profile pass) and the pipelined
-device-resident step, default model.  usage: python tools/ab_pitch.py [streams]"""
+"""Same-box A/B of engine variants selected by environment variables at batch creation: per-kernel CUDA-event times
+(serialised profile pass) and the pipelined device-resident step, default model.  Every configuration is run
+twice, interleaved.
+usage: python tools/ab_env.py [--streams S] "VAR=a;VAR2=b" "VAR=c" ""      (one argument per configuration)"""
 import json
 import os
 import sys
@@ -14,16 +16,29 @@ import torch  # noqa: E402
 import rnnoise_b200  # noqa: E402
 from bench import make_pool  # noqa: E402
 
-S = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+args = sys.argv[1:]
+S = 4096
+if args and args[0] == "--streams":
+    S = int(args[1]); args = args[2:]
+configs = args or [""]
+VARS = sorted({kv.split("=")[0] for c in configs for kv in c.split(";") if kv})
 dev = torch.device("cuda", 0)
 pool = torch.from_numpy(make_pool(S)).to(dev)
 F = pool.shape[0]
 out = torch.empty(S, 480, device=dev); vad = torch.empty(S, device=dev)
 model = rnnoise_b200.Model(os.path.join(ROOT, "tests", "golden", "models", "default.bin"))
 res = {}
-for mode in ("v1", "v2", "v1", "v2"):
-    os.environ["RNNOISE_B200_PITCH_KERNEL"] = mode
-    b = rnnoise_b200.Batch(model, S, 0)
+for mode in configs + configs:
+    for v in VARS:
+        os.environ.pop(v, None)
+    for kv in mode.split(";"):
+        if kv:
+            os.environ[kv.split("=")[0]] = kv.split("=", 1)[1]
+    try:
+        b = rnnoise_b200.Batch(model, S, 0)
+    except Exception as ex:  # noqa: BLE001
+        res.setdefault(mode, []).append({"error": str(ex)})
+        continue
     st = torch.cuda.Stream(dev); torch.cuda.set_stream(st); b.set_stream(st.cuda_stream)
     b.prefilter_device(pool[0].data_ptr())
     def step(i):
