@@ -196,6 +196,83 @@ def cpu_model():
     return "unknown"
 
 
+def single_process(a, cfg, S, K, Wm):
+    """One host thread, G GPUs: rnnoise_batch_create_multi shards G * S streams contiguously over the devices; the
+    device-resident arm times every device with its own CUDA events (value = all streams / max over devices), the
+    e2e arm goes through the ordinary host-buffer call on one [G * S][480] pinned buffer."""
+    import torch
+    import rnnoise_b200
+    G = a.gpus
+    model = rnnoise_b200.Model(MODEL)
+    batch = rnnoise_b200.Batch(model, G * S, devices=list(range(G)))
+    assert batch.nb_devices == G and all(batch.shard(k) == (k, k * S, S) for k in range(G))
+    base = torch.from_numpy(make_pool(S))
+    F = base.shape[0]
+    pool_d = [base.to(f"cuda:{k}") for k in range(G)]
+    out_d = [torch.empty(S, FRAME, device=f"cuda:{k}") for k in range(G)]
+    vad_d = [torch.empty(S, device=f"cuda:{k}") for k in range(G)]
+    streams = [torch.cuda.Stream(torch.device("cuda", k)) for k in range(G)]
+    batch.set_stream_multi([s.cuda_stream for s in streams])
+
+    def step(i):
+        batch.prefilter_device_multi([p[(i + 1) % F].data_ptr() for p in pool_d])
+        batch.process_device_multi([o.data_ptr() for o in out_d], [p[i % F].data_ptr() for p in pool_d], [v.data_ptr() for v in vad_d])
+
+    def sync_all():
+        for k in range(G):
+            torch.cuda.synchronize(k)
+
+    batch.prefilter_device_multi([p[0].data_ptr() for p in pool_d])
+    for i in range(Wm):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(0)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(G)]
+    t0 = time.perf_counter()
+    for k in range(G):
+        with torch.cuda.device(k):
+            ev[k][0].record(streams[k])
+    for i in range(K):
+        step(Wm + i)
+    for k in range(G):
+        with torch.cuda.device(k):
+            ev[k][1].record(streams[k])
+    sync_all()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = max(e0.elapsed_time(e1) for e0, e1 in ev)
+    clocks = sampler.stop()
+    batch.process_device_multi([o.data_ptr() for o in out_d], [p[(Wm + K) % F].data_ptr() for p in pool_d], [v.data_ptr() for v in vad_d])
+    batch.sync()
+    value = G * S * K / (ms * 1e-3)
+    # e2e: one [G * S][480] pinned buffer per pool frame, host-buffer call of the whole batch
+    Fh = min(F, max(2, (1 << 30) // (G * S * FRAME * 4)))
+    pool_h = torch.cat([base[:Fh]] * G, dim=1).contiguous().pin_memory()
+    NBUF = 4
+    out_h = [torch.empty(G * S, FRAME).pin_memory() for _ in range(NBUF)]
+    vad_h = [torch.empty(G * S).pin_memory() for _ in range(NBUF)]
+    for i in range(4):
+        batch.process_ptr_async(out_h[i % NBUF].data_ptr(), pool_h[i % Fh].data_ptr(), vad_h[i % NBUF].data_ptr())
+    batch.sync()
+    t0 = time.perf_counter()
+    for i in range(K):
+        batch.process_ptr_async(out_h[i % NBUF].data_ptr(), pool_h[i % Fh].data_ptr(), vad_h[i % NBUF].data_ptr())
+    batch.sync()
+    ms_e = (time.perf_counter() - t0) * 1e3
+    line = {"metric": "10ms frames/sec", "value": value, "unit": "frames/s", "n_gpus": G, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
+            "wall_ms_per_step": wall_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 (u8 x s8 -> s32) + fp32", "data": "synthetic", "config": dict(cfg, streams_total=G * S),
+            "launch": "single process: one host thread drives all GPUs through rnnoise_batch_create_multi (no torchrun, no NCCL)",
+            "realtime_streams_per_gpu": value / G / 100.0, "clocks": clocks, "lanes": batch.lanes,
+            "e2e": {"value": G * S * K / (ms_e * 1e-3), "unit": "frames/s", "steps": K, "ms_per_step": ms_e / K,
+                    "h2d_bytes_per_step": G * S * FRAME * 4, "d2h_bytes_per_step": G * S * FRAME * 4 + G * S * 4,
+                    "api": "rnnoise_process_frame_batch_async on a multi-device batch + rnnoise_batch_sync"},
+            "gpu_launches": K * batch.launches_per_frame}
+    print(json.dumps(line))
+    batch.destroy()
+    model.free()
+
+
 def main():
     global POOL_FRAMES
     ap = argparse.ArgumentParser()
@@ -205,12 +282,18 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="default", help="model name under tests/golden/models (default, little, ...) or a blob path")
+    ap.add_argument("--single-process", action="store_true",
+                    help="with --gpus N and no torchrun: ONE process drives N GPUs through rnnoise_batch_create_multi (C ABI sharding)")
     a = ap.parse_args()
+    global MODEL
+    if a.model != "default":
+        MODEL = a.model if os.path.exists(a.model) else os.path.join(ROOT, "tests", "golden", "models", a.model + ".bin")
     W, rank, local = world()
     S, K, Wm = a.streams, a.steps, max(a.warmup, 3)
-    cfg = {"workload": f"{S} concurrent 48 kHz mono streams per GPU, default synthetic model (cond128/GRU384 int8 block-sparse), "
+    cfg = {"workload": f"{S} concurrent 48 kHz mono streams per GPU, {a.model} synthetic model (int8 block-sparse GRUs), "
                        f"one 480-sample frame per stream per step", "streams_per_gpu": S, "frame": FRAME,
-           "model": "tests/golden/models/default.bin",
+           "model": os.path.relpath(MODEL, ROOT),
            "l2": f"per-step state+I/O working set {S * 43344 / 1e6:.0f} MB vs 126 MB L2; input rotates through a "
                  f"{pool_frames(S)}-frame device pool ({pool_frames(S) * S * FRAME * 4 / 1e6:.0f} MB)"}
 
@@ -238,6 +321,8 @@ def main():
     import rnnoise_b200
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    if a.single_process and W == 1 and a.gpus > 1:
+        return single_process(a, cfg, S, K, Wm)
     if W > 1:
         import torch.distributed as dist
         # NCCL's log (version banner, INFO lines when the caller sets NCCL_DEBUG=INFO to check the ranks) goes to

@@ -266,6 +266,7 @@ struct B200Engine {
   int use_tc;                       // GRU kernel: 2 = k_tc2<true> (default), 1 = k_gru_tc, 0 = dp4a cross-check
   int conv2_tc;                     // conv2 kernel: 1 = k_tc2<false> (default), 0 = dp4a cross-check
   int pitch2;                       // pitch kernel: 1 = k_pitch2 (default), 0 = k_pitch (RNNOISE_B200_PITCH_KERNEL=v1 cross-check)
+  int heads_ns;                     // k_heads2<NS>: streams per thread, 2 (16 streams per CTA, default) or 4 ($RNNOISE_B200_HEADS_TILE=32)
   int heads2;                       // heads kernel: 1 = k_heads2 (default), 0 = k_heads (RNNOISE_B200_HEADS_KERNEL=cpasync)
   GruTcMaps tc_maps[2][3];          // [frame parity][layer]
   GruTcMaps conv_maps;              // x = c2in, wi = conv2 weights
@@ -537,7 +538,9 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   { const char *hk = getenv("RNNOISE_B200_HEADS_KERNEL"); e->heads2 = !(hk && !strcmp(hk, "cpasync")); }
   { const char *pk = getenv("RNNOISE_B200_PITCH_KERNEL"); e->pitch2 = !(pk && !strcmp(pk, "v1")); }
   ok = ok && cudaFuncSetAttribute(k_pitch2, cudaFuncAttributeMaxDynamicSharedMemorySize, PITCH2_SMEM_BYTES) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(k_heads2, cudaFuncAttributeMaxDynamicSharedMemorySize, H2_SMEM_BYTES) == cudaSuccess;
+  { const char *ht = getenv("RNNOISE_B200_HEADS_TILE"); e->heads_ns = ht && !strcmp(ht, "32") ? 4 : 2; }
+  ok = ok && cudaFuncSetAttribute(k_heads2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<4>()) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_heads2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<2>()) == cudaSuccess;
   const char *gk = getenv("RNNOISE_B200_GRU_KERNEL");
   e->use_tc = gk && !strcmp(gk, "dp4a") ? 0 : gk && !strcmp(gk, "tc1") ? 1 : 2;
   if (ok && e->use_tc) {
@@ -733,8 +736,11 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   }
   if (e->parent) CK(cudaStreamWaitEvent(st, e->ev_pin, 0));   // first kernel that writes the caller's buffers
   const bool pdl_heads = pdl && e->use_tc == 2 && !e->net_fused;   // only the k_tc2 predecessors are PDL-aware
-  if (e->heads2)
-    CK(launch_pdl(k_heads2, dim3((S + H2_TS - 1) / H2_TS), dim3(160), H2_SMEM_BYTES, st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
+  if (e->heads2 && e->heads_ns == 2)
+    CK(launch_pdl(k_heads2<2>, dim3((S + 15) / 16), dim3(160), h2_smem_bytes<2>(), st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
+                  (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
+  else if (e->heads2)
+    CK(launch_pdl(k_heads2<4>, dim3((S + 31) / 32), dim3(160), h2_smem_bytes<4>(), st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
                   (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
   else
     CK(launch_pdl(k_heads, dim3((S + HEAD_TS - 1) / HEAD_TS), dim3(160), 0, st, pdl_heads, S, e->dm, (const float *)a.conv2_out,

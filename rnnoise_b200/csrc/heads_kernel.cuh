@@ -5,9 +5,11 @@
 //   gains[32] = sigmoid(dense_out . cat + b)   each output one sequential FMA chain over K (sgemv, vec_avx.h:672)
 //   vad       = sigmoid(vad_dense . cat + b)   scalar loop: multiply, then add (vec_avx.h:731-735)
 //
-// CTA = 32 streams, 160 threads.  Warps 0..3 each own 8 streams x 32 outputs: a thread keeps 4 streams x
-// 2 adjacent outputs = 8 independent chains in registers, so one LDS.128 of activations and one LDS.64 of
-// weights feed 8 / 4 FMAs.  Warp 4 runs the 32 VAD chains (lane = stream) and is the producer: inputs and
+// CTA = 8 * NS streams, 160 threads.  Warps 0..3 each own 2 * NS streams x 32 outputs: a thread keeps NS streams x
+// 2 adjacent outputs = 2 * NS independent chains in registers, so one LDS.128 of activations and one LDS.64 of
+// weights feed 8 / NS FMAs.  NS = 4 (32 streams per CTA) has the best load : FMA ratio, NS = 2 (16 streams per
+// CTA, the default) launches twice the CTAs: a 2048-stream lane then covers 128 SMs instead of 64 and each
+// thread's chain work is halved -- the kernel is bound by the latency of its serial FMA chains, not by loads.  Warp 4 runs the 32 VAD chains (lane = stream) and is the producer: inputs and
 // weights arrive in chunks of 64 inputs (one 8 KB bulk copy of weights + 16-byte cp.async pieces of the
 // activation rows, all completing on one mbarrier) through an H2_STAGES-deep ring, so staging costs no
 // instructions on the compute warps.
@@ -21,29 +23,33 @@
 #ifndef H2_STAGES
 #define H2_STAGES 6
 #endif
-struct H2Stage {
-  float xs[H2_TS][H2_XS];
+template <int NS> struct H2StageT {
+  float xs[8 * NS][H2_XS];
   float ws[H2_KC][NB_GAINS];
   float wv[H2_KC];
 };
-#define H2_SMEM_BYTES (H2_STAGES * (int)sizeof(H2Stage) + 128)
+template <int NS> constexpr int h2_smem_bytes() { return H2_STAGES * (int)sizeof(H2StageT<NS>) + 128; }
+#define H2_SMEM_BYTES h2_smem_bytes<4>()
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+template <int NS>
 __global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *__restrict__ c2,
                                                 const float *__restrict__ g1, const float *__restrict__ g2,
                                                 const float *__restrict__ g3, const int *__restrict__ silence,
                                                 float *__restrict__ gains, float *__restrict__ vad,
                                                 float *__restrict__ vad_user, int vad_stride) {
   extern __shared__ __align__(128) uint8_t h2_smem[];
+  typedef H2StageT<NS> H2Stage;
+  constexpr int TS = 8 * NS;
   H2Stage *st = (H2Stage *)h2_smem;
   __shared__ __align__(8) uint64_t full[H2_STAGES];
-  const int s0 = blockIdx.x * H2_TS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s0 = blockIdx.x * TS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gru = m.gru, nchunk = 4 * gru / H2_KC;
-  const int live_rows = min(H2_TS, S - s0);
+  const int live_rows = min(TS, S - s0);
   if (tid == 0) {
     for (int i = 0; i < H2_STAGES; i++) mbar_init(smem_u32(&full[i]), 33);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -67,7 +73,7 @@ __global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *
     }
     const float *p = (src == 0 ? c2 : src == 1 ? g1 : src == 2 ? g2 : g3) + (size_t)s0 * gru + off;
 #pragma unroll
-    for (int i = 0; i < H2_TS * H2_KC / 4 / 32; i++) {   // piece = i * 32 + lane: row = piece / 16, 16-byte column = piece % 16
+    for (int i = 0; i < TS * H2_KC / 4 / 32; i++) {   // piece = i * 32 + lane: row = piece / 16, 16-byte column = piece % 16
       const int row = 2 * i + (lane >> 4), col = lane & 15;
       cp_async16(&st[buf].xs[row][4 * col], p + (size_t)(row < live_rows ? row : 0) * gru + 4 * col, row < live_rows);
     }
@@ -75,11 +81,11 @@ __global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *
   };
   if (warp == 4)
     for (int c = 0; c < H2_STAGES - 1 && c < nchunk; c++) produce(c);
-  float acc[4][2];
+  float acc[NS][2];
 #pragma unroll
-  for (int i = 0; i < 4; i++) acc[i][0] = acc[i][1] = 0.f;
+  for (int i = 0; i < NS; i++) acc[i][0] = acc[i][1] = 0.f;
   float y = 0.f;
-  const int row0 = warp * 8 + (lane >> 4) * 4, o2 = (lane & 15) * 2;
+  const int row0 = warp * (2 * NS) + (lane >> 4) * NS, o2 = (lane & 15) * 2;
   for (int c = 0; c < nchunk; c++) {
     const int buf = c % H2_STAGES;
     if (warp == 4 && c + H2_STAGES - 1 < nchunk) produce(c + H2_STAGES - 1);   // that stage was released by the barrier ending chunk c-1
@@ -88,22 +94,24 @@ __global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *
     if (warp < 4) {
 #pragma unroll 4
       for (int kk = 0; kk < H2_KC; kk += 4) {
-        const float4 x0 = *(const float4 *)&b.xs[row0 + 0][kk], x1 = *(const float4 *)&b.xs[row0 + 1][kk];
-        const float4 x2 = *(const float4 *)&b.xs[row0 + 2][kk], x3 = *(const float4 *)&b.xs[row0 + 3][kk];
+        float4 x[NS];
+#pragma unroll
+        for (int i = 0; i < NS; i++) x[i] = *(const float4 *)&b.xs[row0 + i][kk];
         const float2 w0 = *(const float2 *)&b.ws[kk][o2], w1 = *(const float2 *)&b.ws[kk + 1][o2];
         const float2 w2 = *(const float2 *)&b.ws[kk + 2][o2], w3 = *(const float2 *)&b.ws[kk + 3][o2];
-#define H2_STEP(W, C)                                                                                  \
-  acc[0][0] = fmaf(W.x, x0.C, acc[0][0]); acc[0][1] = fmaf(W.y, x0.C, acc[0][1]);                      \
-  acc[1][0] = fmaf(W.x, x1.C, acc[1][0]); acc[1][1] = fmaf(W.y, x1.C, acc[1][1]);                      \
-  acc[2][0] = fmaf(W.x, x2.C, acc[2][0]); acc[2][1] = fmaf(W.y, x2.C, acc[2][1]);                      \
-  acc[3][0] = fmaf(W.x, x3.C, acc[3][0]); acc[3][1] = fmaf(W.y, x3.C, acc[3][1]);
-        H2_STEP(w0, x) H2_STEP(w1, y) H2_STEP(w2, z) H2_STEP(w3, w)
-#undef H2_STEP
+#pragma unroll
+        for (int i = 0; i < NS; i++) { acc[i][0] = fmaf(w0.x, x[i].x, acc[i][0]); acc[i][1] = fmaf(w0.y, x[i].x, acc[i][1]); }
+#pragma unroll
+        for (int i = 0; i < NS; i++) { acc[i][0] = fmaf(w1.x, x[i].y, acc[i][0]); acc[i][1] = fmaf(w1.y, x[i].y, acc[i][1]); }
+#pragma unroll
+        for (int i = 0; i < NS; i++) { acc[i][0] = fmaf(w2.x, x[i].z, acc[i][0]); acc[i][1] = fmaf(w2.y, x[i].z, acc[i][1]); }
+#pragma unroll
+        for (int i = 0; i < NS; i++) { acc[i][0] = fmaf(w3.x, x[i].w, acc[i][0]); acc[i][1] = fmaf(w3.y, x[i].w, acc[i][1]); }
       }
     } else {
 #pragma unroll 4
       for (int kk = 0; kk < H2_KC; kk += 4) {
-        const float4 x = *(const float4 *)&b.xs[lane][kk], w = *(const float4 *)&b.wv[kk];
+        const float4 x = *(const float4 *)&b.xs[lane < TS ? lane : 0][kk], w = *(const float4 *)&b.wv[kk];
         y = y + w.x * x.x; y = y + w.y * x.y; y = y + w.z * x.z; y = y + w.w * x.w;
       }
     }
@@ -112,13 +120,13 @@ __global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *
   if (warp < 4) {
     const float b0 = m.dense_out.bias[o2], b1 = m.dense_out.bias[o2 + 1];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < NS; i++) {
       const int s = s0 + row0 + i;
       if (s < S) *(float2 *)&gains[(size_t)s * NB_GAINS + o2] = make_float2(act_sigmoid(acc[i][0] + b0), act_sigmoid(acc[i][1] + b1));
     }
   } else {
     const int s = s0 + lane;
-    if (s < S) {
+    if (lane < TS && s < S) {
       const float v = silence[s] ? 0.f : act_sigmoid(y + m.vad_dense.bias[0]);
       vad[s] = v;
       if (vad_user) vad_user[(size_t)s * vad_stride] = v;
