@@ -130,7 +130,9 @@ def pool_file(S):
 def run_reference(S, steps, warmup, threads=None, repeats=1, vnni=False, model=None, pool_S=None):
     """Times the unmodified reference (oracle/_ref) on the host cores; returns dict or None."""
     from oracle import refbind
-    exe = refbind.bench_path(vnni=vnni)
+    from rnnoise_b200 import weights
+    d = weights.describe(open(model or MODEL, "rb").read())    # the reference's model dims are compile-time: one build per (cond, gru)
+    exe = refbind.bench_path(d["cond"], d["gru"], vnni=vnni)
     if not os.path.exists(exe):
         return None
     threads = threads or len(os.sched_getaffinity(0))

@@ -17,8 +17,9 @@ Models:
   hot     : same, GRU W x3, conv W x2, head W x8                        (saturating gates)
   little  : seed 4321, same dims, densities x0.5 (README:119-125 "little" = more sparsity)
   g256    : seed 99, cond128/gru256 (dimension-generality check; compared against the port only)
-  tiny    : seed 7, cond96/gru128 (conv2 K = 288 is not a whole swizzle atom -> CUDA-core conv2);
+  tiny    : seed 7, cond96/gru128 (conv2 K = 288 is not a whole swizzle atom -> rows padded to 384);
             its state dict is kept as tiny_ckpt.npz for the exporter test
+  little_b: seed 4322, cond128/gru192 (BASELINE configs[3] read literally: half-width GRUs; K = 192 padded to 256)
 
 Usage: python oracle/make_models.py [names...]
 """
@@ -42,6 +43,9 @@ SPECS = {
     # small dims; its checkpoint is committed too (tiny_ckpt.npz) so the blob exporter
     # (rnnoise_b200/weights.py) can be pinned against the reference pipeline where /root/reference is absent
     "tiny": dict(seed=7, cond=96, gru=128, density_scale=1.0, hot=False),
+    # the literal half-width reading of BASELINE configs[3] ("'little' half-size model"): GRU 192.  K = 192 is 1.5 swizzle
+    # atoms (rows padded to 256 with zero weights), 48 units per CTA = 3 slices
+    "little_b": dict(seed=4322, cond=128, gru=192, density_scale=1.0, hot=False),
 }
 KEEP_CKPT = {"tiny"}
 

@@ -38,6 +38,8 @@
 // ------------------------------------------------------------------------------------------------
 struct Arena {
   int S, cond, gru;
+  int Kp, Kcp;         // byte row strides of the u8 operand rows: gru and 3 * cond rounded up to the 128-byte swizzle atom
+                       // (the pad bytes meet zero weights in the GEMMs, so they never contribute)
   // DSP state
   float *ring;         // [S][1728] pitch history ring (analysis_mem is its newest 480 samples)
   float *synth_mem;    // [S][480]
@@ -49,10 +51,10 @@ struct Arena {
   float *pitch_state;  // [S][2] {last_period (int bits), last_gain}
   // network state
   float *conv1_state;  // [S][130]
-  uint8_t *c2in;       // [S][3*cond] u8 operand row of conv2: [memory (2 frames of conv1 output) | newest]
+  uint8_t *c2in;       // [S][Kcp] u8 operand row of conv2: [memory (2 frames of conv1 output) | newest | pad]
   float *hbuf;         // [2][3][S][gru] ping-pong GRU states
-  uint8_t *hbuf_u8;    // [2][3][S][gru] their u8 = 127 + rne(127 h) mirrors (tensor-core A operands)
-  uint8_t *conv2_out_u8; // [S][gru]
+  uint8_t *hbuf_u8;    // [2][3][S][Kp] their u8 = 127 + rne(127 h) mirrors (tensor-core A operands)
+  uint8_t *conv2_out_u8; // [S][Kp]
   // per-frame scratch
   float *xb;           // [2][S][480] high-passed input, double-buffered by frame parity
   float *features;     // [2][S][65] by frame parity (frame f+1's analysis overlaps frame f's network)
@@ -371,13 +373,19 @@ static int make_map_u8(CUtensorMap *m, const void *base, uint64_t rows, uint64_t
 }
 // dense s8 [3*gru][K] (rows = z|r|n outputs) -> [gru/32 slices][3 gates][32 units][K]: the 96 B-operand
 // rows of one unit slice become contiguous
-static const signed char *upload_permuted(B200Engine *e, const B200Layer *l, int gru, int units) {
+// K is padded with zero weights up to Kp bytes per row.
+static const signed char *upload_permuted(B200Engine *e, const B200Layer *l, int gru, int units, int Kp) {
   const int K = l->nb_in;
-  std::vector<signed char> p((size_t)3 * gru * K);
+  std::vector<signed char> p((size_t)3 * gru * Kp, 0);
   for (int sl = 0; sl < gru / units; sl++)
     for (int g = 0; g < 3; g++)
       for (int u = 0; u < units; u++)
-        memcpy(&p[(((size_t)sl * 3 + g) * units + u) * K], l->w8 + (size_t)(g * gru + sl * units + u) * K, K);
+        memcpy(&p[(((size_t)sl * 3 + g) * units + u) * Kp], l->w8 + (size_t)(g * gru + sl * units + u) * K, K);
+  return upload<signed char>(e, p.data(), p.size());
+}
+static const signed char *upload_padded_rows(B200Engine *e, const signed char *w, int rows, int K, int Kp) {
+  std::vector<signed char> p((size_t)rows * Kp, 0);
+  for (int r = 0; r < rows; r++) memcpy(&p[(size_t)r * Kp], w + (size_t)r * K, K);
   return upload<signed char>(e, p.data(), p.size());
 }
 
@@ -418,8 +426,11 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
     return nullptr;
   }
   if (!m || S < 1 || device < 0 || device >= ndev) return nullptr;
-  if (m->gru % 128 || m->cond % 4 || m->gru > 1024 || m->cond > 128) {
-    fprintf(stderr, "[rnnoise_b200] unsupported model dims cond=%d gru=%d (need gru %% 128 == 0, cond <= 128)\n", m->cond, m->gru);
+  // gru: a CTA of the tensor-core kernels owns gru / 4 units in slices of 16, the heads stream 64-input chunks that
+  // must not straddle two layers; cond: one conv1 output per thread of a 128-thread CTA.  The contraction lengths
+  // themselves (gru, 3 * cond) are free: rows are padded to the 128-byte swizzle atom with zero weights.
+  if (m->gru % 64 || m->cond % 4 || m->gru > 1024 || m->cond > 128 || m->gru < 64 || m->cond < 4) {
+    fprintf(stderr, "[rnnoise_b200] unsupported model dims cond=%d gru=%d (need gru %% 64 == 0, gru <= 1024, cond %% 4 == 0, cond <= 128)\n", m->cond, m->gru);
     return nullptr;
   }
   if (cudaSetDevice(device) != cudaSuccess) return nullptr;
@@ -439,6 +450,8 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   e->stream = e->own_stream;
   Arena &a = e->a;
   a.S = S; a.cond = m->cond; a.gru = m->gru;
+  a.Kp = (m->gru + TC_KATOM - 1) / TC_KATOM * TC_KATOM;
+  a.Kcp = (3 * m->cond + TC_KATOM - 1) / TC_KATOM * TC_KATOM;
   const size_t Ss = (size_t)S;
   bool ok = true;
   ok &= !!(a.ring = dalloc<float>(e, Ss * PITCH_BUF_SIZE));
@@ -449,12 +462,13 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   ok &= !!(a.lastg = dalloc<float>(e, Ss * NB_BANDS));
   ok &= !!(a.pitch_state = dalloc<float>(e, Ss * 2));
   ok &= !!(a.conv1_state = dalloc<float>(e, Ss * 2 * NB_FEATURES));
-  ok &= !!(a.c2in = dalloc<uint8_t>(e, Ss * 3 * m->cond));
-  if (ok) ok = cudaMemset(a.c2in, 127, Ss * 3 * m->cond) == cudaSuccess;   // u8 image of zeros
+  ok &= !!(a.c2in = dalloc<uint8_t>(e, Ss * a.Kcp));
+  if (ok) ok = cudaMemset(a.c2in, 127, Ss * a.Kcp) == cudaSuccess;   // u8 image of zeros
   ok &= !!(a.hbuf = dalloc<float>(e, 2 * 3 * Ss * m->gru));
-  ok &= !!(a.hbuf_u8 = dalloc<uint8_t>(e, 2 * 3 * Ss * m->gru));
-  ok &= !!(a.conv2_out_u8 = dalloc<uint8_t>(e, Ss * m->gru));
-  if (ok) ok = cudaMemset(a.hbuf_u8, 127, 2 * 3 * Ss * m->gru) == cudaSuccess;   // u8 image of h = 0
+  ok &= !!(a.hbuf_u8 = dalloc<uint8_t>(e, 2 * 3 * Ss * a.Kp));
+  ok &= !!(a.conv2_out_u8 = dalloc<uint8_t>(e, Ss * a.Kp));
+  if (ok) ok = cudaMemset(a.hbuf_u8, 127, 2 * 3 * Ss * a.Kp) == cudaSuccess;   // u8 image of h = 0
+  if (ok) ok = cudaMemset(a.conv2_out_u8, 127, Ss * a.Kp) == cudaSuccess;
   ok &= !!(a.xb = dalloc<float>(e, 2 * Ss * FRAME_SIZE));
   ok &= !!(a.features = dalloc<float>(e, 2 * Ss * NB_FEATURES));
   ok &= !!(a.silence = dalloc<int>(e, 2 * Ss));
@@ -542,39 +556,39 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   ok = ok && cudaFuncSetAttribute(k_heads2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<4>()) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(k_heads2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<2>()) == cudaSuccess;
   const char *gk = getenv("RNNOISE_B200_GRU_KERNEL");
-  e->use_tc = gk && !strcmp(gk, "dp4a") ? 0 : gk && !strcmp(gk, "tc1") ? 1 : 2;
+  e->use_tc = gk && !strcmp(gk, "dp4a") ? 0 : gk && !strcmp(gk, "tc1") && m->gru % 128 == 0 ? 1 : 2;
   if (ok && e->use_tc) {
-    const size_t hs = Ss * m->gru;
+    const size_t hs = Ss * a.Kp;
     const int units = e->use_tc == 1 ? TC_UNITS : P_SLICE;
     for (int l = 0; l < 3 && ok; l++) {
-      const signed char *wi = upload_permuted(e, &m->gru_in[l], m->gru, units), *wr = upload_permuted(e, &m->gru_rec[l], m->gru, units);
+      const signed char *wi = upload_permuted(e, &m->gru_in[l], m->gru, units, a.Kp), *wr = upload_permuted(e, &m->gru_rec[l], m->gru, units, a.Kp);
       ok = wi && wr;
       for (int par = 0; par < 2 && ok; par++) {
         GruTcMaps &mp = e->tc_maps[par][l];
         const uint8_t *x = l == 0 ? a.conv2_out_u8 : a.hbuf_u8 + ((size_t)par * 3 + l - 1) * hs;
         const uint8_t *h = a.hbuf_u8 + ((size_t)(par ^ 1) * 3 + l) * hs;
-        ok = make_map_u8(&mp.x, x, S, m->gru, TC_M) == 0 && make_map_u8(&mp.h, h, S, m->gru, TC_M) == 0 &&
-             make_map_u8(&mp.wi, wi, 3 * m->gru, m->gru, 3 * units) == 0 && make_map_u8(&mp.wr, wr, 3 * m->gru, m->gru, 3 * units) == 0;
+        ok = make_map_u8(&mp.x, x, S, a.Kp, TC_M) == 0 && make_map_u8(&mp.h, h, S, a.Kp, TC_M) == 0 &&
+             make_map_u8(&mp.wi, wi, 3 * m->gru, a.Kp, 3 * units) == 0 && make_map_u8(&mp.wr, wr, 3 * m->gru, a.Kp, 3 * units) == 0;
       }
     }
     ok = ok && cudaFuncSetAttribute(k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, gru_tc_smem_bytes(m->gru)) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<true>(m->gru, m->gru)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<true>(a.Kp, m->gru)) == cudaSuccess;
     if (!ok) fprintf(stderr, "[rnnoise_b200] tensor-core GRU setup failed\n");
   }
-  // conv2 on the tensor cores needs its K = 3*cond to be whole 128-byte swizzle atoms
+  // conv2 on the tensor cores: K = 3 * cond padded to whole 128-byte swizzle atoms
   const char *ck = getenv("RNNOISE_B200_CONV2_KERNEL");
-  e->conv2_tc = !(ck && !strcmp(ck, "dp4a")) && (3 * m->cond) % TC_KATOM == 0;
+  e->conv2_tc = !(ck && !strcmp(ck, "dp4a"));
   if (ok && e->conv2_tc) {
-    const signed char *w2 = upload<signed char>(e, m->conv2.w8, (size_t)m->gru * 3 * m->cond);   // natural [unit][K]
-    ok = w2 && make_map_u8(&e->conv_maps.x, a.c2in, S, 3 * m->cond, TC_M) == 0 &&
-         make_map_u8(&e->conv_maps.wi, w2, m->gru, 3 * m->cond, P_SLICE) == 0;
+    const signed char *w2 = upload_padded_rows(e, m->conv2.w8, m->gru, 3 * m->cond, a.Kcp);   // natural [unit][K]
+    ok = w2 && make_map_u8(&e->conv_maps.x, a.c2in, S, a.Kcp, TC_M) == 0 &&
+         make_map_u8(&e->conv_maps.wi, w2, m->gru, a.Kcp, P_SLICE) == 0;
     e->conv_maps.h = e->conv_maps.x; e->conv_maps.wr = e->conv_maps.wi;
-    ok = ok && cudaFuncSetAttribute(k_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<false>(3 * m->cond, m->gru)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<false>(a.Kcp, m->gru)) == cudaSuccess;
   }
   // fused network kernel (net_kernel.cuh): needs the persistent tcgen05 GRU path and conv2 on the tensor cores
   { const char *nk = getenv("RNNOISE_B200_NET_KERNEL"); e->net_fused = !(nk && !strcmp(nk, "layers")) && e->use_tc == 2 && e->conv2_tc; }
   if (ok && e->net_fused) {
-    const size_t hs = Ss * m->gru;
+    const size_t hs = Ss * m->gru, hs8 = Ss * a.Kp;
     for (int par = 0; par < 2; par++) {
       NetMaps &nm = e->net_maps[par];
       NetPtrs &np = e->net_ptrs[par];
@@ -589,10 +603,10 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
         np.scale_r[l + 1] = dm.gru_rec[l].scale; np.subias_r[l + 1] = dm.gru_rec[l].subias; np.diag[l + 1] = dm.gru_rec[l].diag;
         np.h_old[l + 1] = a.hbuf + ((size_t)(par ^ 1) * 3 + l) * hs;
         np.out_f32[l + 1] = a.hbuf + ((size_t)par * 3 + l) * hs;
-        np.out_u8[l + 1] = a.hbuf_u8 + ((size_t)par * 3 + l) * hs;
+        np.out_u8[l + 1] = a.hbuf_u8 + ((size_t)par * 3 + l) * hs8;
       }
     }
-    ok = cudaFuncSetAttribute(k_net, cudaFuncAttributeMaxDynamicSharedMemorySize, net_smem_bytes(3 * m->cond, m->gru)) == cudaSuccess;
+    ok = cudaFuncSetAttribute(k_net, cudaFuncAttributeMaxDynamicSharedMemorySize, net_smem_bytes(a.Kcp, a.Kp, m->gru)) == cudaSuccess;
     if (!ok) fprintf(stderr, "[rnnoise_b200] fused network kernel setup failed\n");
   }
   if (!ok || cudaDeviceSynchronize() != cudaSuccess) {
@@ -656,7 +670,7 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   const int S = a.S, gru = a.gru, cond = a.cond;
   cudaStream_t st = e->stream;
   const int par = (int)(e->frames & 1);
-  const size_t hstride = (size_t)S * gru;
+  const size_t hstride = (size_t)S * gru, hstride8 = (size_t)S * a.Kp;
   float *h_new[3], *h_old[3];
   for (int l = 0; l < 3; l++) {
     h_new[l] = a.hbuf + ((size_t)par * 3 + l) * hstride;
@@ -705,31 +719,31 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   TL(e, e->frames, TL_BACK_START, st);
   MARK();
   const int gts = (S + RNN_TS - 1) / RNN_TS;
-  k_conv1<<<gts, 128, 0, st>>>(S, e->dm, feat, a.conv1_state, sil, a.c2in);
+  k_conv1<<<gts, 128, 0, st>>>(S, e->dm, feat, a.conv1_state, sil, a.c2in, a.Kcp);
   MARK();
   const bool pdl = e->pdl && !e->profiling;
   if (e->net_fused) {
-    k_net<<<dim3((S + TC_M - 1) / TC_M, 4), P_THREADS, net_smem_bytes(3 * cond, gru), st>>>(S, 3 * cond, gru, e->net_maps[par], e->net_ptrs[par], sil);
+    k_net<<<dim3((S + TC_M - 1) / TC_M, 4), P_THREADS, net_smem_bytes(a.Kcp, a.Kp, gru), st>>>(S, a.Kcp, a.Kp, gru, e->net_maps[par], e->net_ptrs[par], sil);
     MARK(); MARK(); MARK(); MARK();   // one launch covers the conv2 and GRU slots of the per-kernel profile
   } else {
   if (e->conv2_tc)
-    CK(launch_pdl(k_tc2<false>, dim3((S + TC_M - 1) / TC_M, 4), dim3(P_THREADS), tc2_smem_bytes<false>(3 * cond, gru), st, pdl,
-                  S, 3 * cond, gru, e->conv_maps, e->dm.conv2, e->dm.conv2, (const float *)nullptr, a.conv2_out, a.conv2_out_u8, sil));
+    CK(launch_pdl(k_tc2<false>, dim3((S + TC_M - 1) / TC_M, 4), dim3(P_THREADS), tc2_smem_bytes<false>(a.Kcp, gru), st, pdl,
+                  S, a.Kcp, gru, a.Kp, e->conv_maps, e->dm.conv2, e->dm.conv2, (const float *)nullptr, a.conv2_out, a.conv2_out_u8, sil));
   else
-    k_conv2<<<gts, 128, RNN_TS * (3 * cond / 4) * sizeof(uint32_t), st>>>(S, e->dm, a.c2in, a.conv2_out, a.conv2_out_u8);
+    k_conv2<<<gts, 128, RNN_TS * (3 * cond / 4) * sizeof(uint32_t), st>>>(S, e->dm, a.c2in, a.Kcp, a.conv2_out, a.conv2_out_u8, a.Kp);
   MARK();
   const size_t gsm = 2 * RNN_TS * (gru / 4) * sizeof(uint32_t);
   for (int l = 0; l < 3; l++) {
-    uint8_t *hu8_new = a.hbuf_u8 + ((size_t)par * 3 + l) * hstride;
+    uint8_t *hu8_new = a.hbuf_u8 + ((size_t)par * 3 + l) * hstride8;
     if (e->use_tc == 2) {
-      CK(launch_pdl(k_tc2<true>, dim3((S + TC_M - 1) / TC_M, 4), dim3(P_THREADS), tc2_smem_bytes<true>(gru, gru), st, pdl,
-                    S, gru, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], (const float *)h_old[l], h_new[l], hu8_new, sil));
+      CK(launch_pdl(k_tc2<true>, dim3((S + TC_M - 1) / TC_M, 4), dim3(P_THREADS), tc2_smem_bytes<true>(a.Kp, gru), st, pdl,
+                    S, a.Kp, gru, a.Kp, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], (const float *)h_old[l], h_new[l], hu8_new, sil));
     } else if (e->use_tc == 1) {
       k_gru_tc<<<dim3((S + TC_M - 1) / TC_M, gru / TC_UNITS), 160, gru_tc_smem_bytes(gru), st>>>(
           S, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, sil);
     } else {
       const float *x = l == 0 ? a.conv2_out : h_new[l - 1];
-      k_gru<<<dim3(gts, gru / 128), 128, gsm, st>>>(S, gru, e->dm.gru_in[l], e->dm.gru_rec[l], x, h_old[l], h_new[l], hu8_new, sil);
+      k_gru<<<dim3(gts, (gru + 127) / 128), 128, gsm, st>>>(S, gru, e->dm.gru_in[l], e->dm.gru_rec[l], x, h_old[l], h_new[l], hu8_new, a.Kp, sil);
     }
     MARK();
   }
@@ -1072,8 +1086,8 @@ extern "C" int b200_engine_reset_stream(B200Engine *e, int s) {
   ZERO(a.spec, 4 * FREQ_SIZE, 3) ZERO(a.band, 96, 3) ZERO(a.lastg, NB_BANDS, 1) ZERO(a.pitch_state, 2, 1)
   ZERO(a.conv1_state, 2 * NB_FEATURES, 1) ZERO(a.hbuf, a.gru, 6)
 #undef ZERO
-  for (int c = 0; c < 6; c++) CK(cudaMemsetAsync(a.hbuf_u8 + ((size_t)c * S + s) * a.gru, 127, a.gru, st));
-  CK(cudaMemsetAsync(a.c2in + (size_t)s * 3 * a.cond, 127, 3 * a.cond, st));
+  for (int c = 0; c < 6; c++) CK(cudaMemsetAsync(a.hbuf_u8 + ((size_t)c * S + s) * a.Kp, 127, a.Kp, st));
+  CK(cudaMemsetAsync(a.c2in + (size_t)s * a.Kcp, 127, a.Kcp, st));
   CK(cudaStreamSynchronize(st));
   return 0;
 }
@@ -1113,7 +1127,7 @@ extern "C" int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst
       n = 2 * a.cond;
       if (cap < n) return -1;
       std::vector<uint8_t> tmp(n);
-      CK(cudaMemcpy(tmp.data(), a.c2in + (size_t)s * 3 * a.cond, n, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(tmp.data(), a.c2in + (size_t)s * a.Kcp, n, cudaMemcpyDeviceToHost));
       for (int i = 0; i < n; i++) dst[i] = (float)tmp[i];
       return n;
     }

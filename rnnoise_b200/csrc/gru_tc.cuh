@@ -281,12 +281,13 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, int (&v)[4]) {
                : "memory");
 }
 
-// K = contraction length (bytes of one activation row), N = number of output units (gru).
+// K = contraction length = bytes of one (zero-weight padded) activation row, a multiple of 128; N = number of output
+// units (gru, a multiple of 64); ldo = row stride of the u8 output mirror (the padded K of its consumer).
 // GRU : maps.x/h = Xu8/Hu8 [S][K]; maps.wi/wr = s8 [(N/16) x 48][K];  out = h_new (+u8), aux = h_old
 // conv: maps.x = conv2 input u8 [S][K]; maps.wi = s8 [N][K] (unit-major); out = conv2_out (+u8)
 template <bool kGru>
 __global__ void __launch_bounds__(P_THREADS, 1)
-k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, DevLayerQ wr,
+k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, DevLayerQ wr,
       const float *__restrict__ h_old, float *__restrict__ out_f32, uint8_t *__restrict__ out_u8,
       const int *__restrict__ silence) {
   using C = TcCfg<kGru>;
@@ -453,7 +454,7 @@ k_tc2(int S, int K, int N, const __grid_constant__ GruTcMaps maps, DevLayerQ wi,
       }
       if (live) {
         *(float4 *)&out_f32[(size_t)srow * N + jq + ub] = make_float4(outv[0], outv[1], outv[2], outv[3]);
-        *(uint32_t *)&out_u8[(size_t)srow * N + jq + ub] = quant4(outv[0], outv[1], outv[2], outv[3]);
+        *(uint32_t *)&out_u8[(size_t)srow * ldo + jq + ub] = quant4(outv[0], outv[1], outv[2], outv[3]);
       }
 #pragma unroll
       for (int q = 0; q < P_UPT; q++) hcur[q] = hnext[q];

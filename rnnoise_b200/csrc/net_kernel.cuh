@@ -36,9 +36,9 @@ struct NetPtrs {
 
 __host__ __device__ constexpr int net_stage_bytes(int K) { return 2 * (K / TC_KATOM) * (3 * P_SLICE * TC_KATOM); }
 __host__ __device__ constexpr int net_prm_floats(int N) { return (2 + 3 * 16) * (N / 4); }
-__host__ __device__ constexpr int net_smem_bytes(int Kc, int N) {
-  // A tiles: X (max(Kc, N) bytes per row) + H (N); B ring; parameters of all layers; barriers
-  return 1024 + ((Kc > N ? Kc : N) / TC_KATOM + N / TC_KATOM) * TC_A_ATOM_BYTES + P_STAGES * net_stage_bytes(N) +
+__host__ __device__ constexpr int net_smem_bytes(int Kc, int Kn, int N) {
+  // A tiles: X (max(Kc, Kn) bytes per row) + H (Kn); B ring; parameters of all layers; barriers
+  return 1024 + ((Kc > Kn ? Kc : Kn) / TC_KATOM + Kn / TC_KATOM) * TC_A_ATOM_BYTES + P_STAGES * net_stage_bytes(Kn) +
          net_prm_floats(N) * 4 + 24 * 8 + 64;
 }
 
@@ -48,18 +48,19 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// Kc = conv2's contraction length (3 * cond), N = gru; both multiples of 128.
+// Kc = conv2's contraction length (3 * cond) and Kn = the GRU layers' (gru), both padded up to multiples of 128 with
+// zero weights; N = gru (a multiple of 64).  Kn is also the row stride of every u8 activation mirror.
 __global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(P_THREADS, 1)
-k_net(int S, int Kc, int N, const __grid_constant__ NetMaps maps, const __grid_constant__ NetPtrs p, const int *__restrict__ silence) {
+k_net(int S, int Kc, int Kn, int N, const __grid_constant__ NetMaps maps, const __grid_constant__ NetPtrs p, const int *__restrict__ silence) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int upc = N / 4, nslice = upc / P_SLICE;
-  const int atoms_c = Kc / TC_KATOM, atoms_n = N / TC_KATOM, atoms_x = atoms_c > atoms_n ? atoms_c : atoms_n;
+  const int atoms_c = Kc / TC_KATOM, atoms_n = Kn / TC_KATOM, atoms_x = atoms_c > atoms_n ? atoms_c : atoms_n;
   const int m0 = blockIdx.x * TC_M, jq = blockIdx.y * upc;
   uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t *sAx = base, *sAh = sAx + atoms_x * TC_A_ATOM_BYTES;
   uint8_t *sB = sAh + atoms_n * TC_A_ATOM_BYTES;
-  const int stage_bytes = net_stage_bytes(N);
+  const int stage_bytes = net_stage_bytes(Kn);
   float *prm = (float *)(sB + P_STAGES * stage_bytes);   // conv: [2][upc]; then per GRU layer [upc][16]
   uint64_t *bars = (uint64_t *)(prm + net_prm_floats(N));
   uint32_t *tmem_slot = (uint32_t *)(bars + 24);
@@ -258,7 +259,7 @@ k_net(int S, int Kc, int N, const __grid_constant__ NetMaps maps, const __grid_c
         }
         if (live) {
           *(float4 *)&out_f32[(size_t)srow * N + jq + ub] = make_float4(outv[0], outv[1], outv[2], outv[3]);
-          *(uint32_t *)&out_u8[(size_t)srow * N + jq + ub] = quant4(outv[0], outv[1], outv[2], outv[3]);
+          *(uint32_t *)&out_u8[(size_t)srow * Kn + jq + ub] = quant4(outv[0], outv[1], outv[2], outv[3]);
         }
 #pragma unroll
         for (int q = 0; q < P_UPT; q++) hcur[q] = hnext[q];

@@ -107,7 +107,7 @@ struct DevModel {
 #define C1_XS 196   // row stride of the staged inputs (195 + 1: keeps rows 16-byte aligned)
 __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *__restrict__ features,
                                                float *conv1_state, const int *__restrict__ silence,
-                                               uint8_t *c2in) {
+                                               uint8_t *c2in, int ldc /* row stride of c2in: 3 * cond padded to 128 */) {
   __shared__ __align__(16) float tmp[RNN_TS][C1_XS];
   __shared__ __align__(16) float wsm[2][C1_KC][128];   // weight chunks, double-buffered (cond <= 128)
   __shared__ uint32_t rot[RNN_TS][64];                  // 2*cond/4 words per stream
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *_
   }
   for (int s = tid >> 6; s < RNN_TS; s += 2) {   // words [W, 3W) of each live row; 2W <= 64 words per row
     const int w = tid & 63;
-    if (w < 2 * W) cp_async4(&rot[s][w], (const uint32_t *)(c2in + (size_t)(s0 + s < S ? s0 + s : 0) * 3 * cond) + W + w, s0 + s < S);
+    if (w < 2 * W) cp_async4(&rot[s][w], (const uint32_t *)(c2in + (size_t)(s0 + s < S ? s0 + s : 0) * ldc) + W + w, s0 + s < S);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   stage(0, 0);
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *_
   __syncthreads();
   for (int s = tid >> 6; s < RNN_TS; s += 2) {
     const int w = tid & 63;
-    if (w < 2 * W && s0 + s < S && !silence[s0 + s]) ((uint32_t *)(c2in + (size_t)(s0 + s) * 3 * cond))[w] = rot[s][w];
+    if (w < 2 * W && s0 + s < S && !silence[s0 + s]) ((uint32_t *)(c2in + (size_t)(s0 + s) * ldc))[w] = rot[s][w];
   }
   const int o = tid;
   float acc[RNN_TS];
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *_
 #pragma unroll
     for (int s = 0; s < RNN_TS; s++)
       if (s0 + s < S && !silence[s0 + s])
-        c2in[(size_t)(s0 + s) * 3 * cond + 2 * cond + o] = (uint8_t)quant_u8(act_tanh(acc[s] + b));
+        c2in[(size_t)(s0 + s) * ldc + 2 * cond + o] = (uint8_t)quant_u8(act_tanh(acc[s] + b));
   }
   // memory update: mem = tmp[65:195]; silent frames leave the state untouched (denoise.c:474)
   for (int idx = tid; idx < RNN_TS * 2 * NB_FEAT; idx += 128) {
@@ -191,13 +191,13 @@ __global__ void __launch_bounds__(128) k_conv1(int S, DevModel m, const float *_
 // conv2 on CUDA cores (cross-check kernel for k_tc2<false>): c2in (3*cond u8) -> gru, tanh
 // (cgemv8x4 vec_avx.h:829).  grid = ceil(S / RNN_TS), block = 128, dynamic smem = RNN_TS*(3*cond/4)*4
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_conv2(int S, DevModel m, const uint8_t *__restrict__ c2in,
-                                               float *__restrict__ conv2_out, uint8_t *__restrict__ conv2_out_u8) {
+__global__ void __launch_bounds__(128) k_conv2(int S, DevModel m, const uint8_t *__restrict__ c2in, int ldc,
+                                               float *__restrict__ conv2_out, uint8_t *__restrict__ conv2_out_u8, int ldo) {
   extern __shared__ uint32_t u_sm[];   // [RNN_TS][K/4]
   const int K = 3 * m.cond, K4 = K / 4, s0 = blockIdx.x * RNN_TS, tid = threadIdx.x;
   for (int idx = tid; idx < RNN_TS * K4; idx += 128) {
     int s = idx / K4;
-    u_sm[idx] = s0 + s < S ? ((const uint32_t *)(c2in + (size_t)(s0 + s) * K))[idx % K4] : 0u;
+    u_sm[idx] = s0 + s < S ? ((const uint32_t *)(c2in + (size_t)(s0 + s) * ldc))[idx % K4] : 0u;
   }
   __syncthreads();
   for (int o = tid; o < m.gru; o += 128) {
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128) k_conv2(int S, DevModel m, const uint8_t 
       if (s0 + s < S) {
         float v = act_tanh((float)acc[s] * sc + sb);
         conv2_out[(size_t)(s0 + s) * m.gru + o] = v;
-        conv2_out_u8[(size_t)(s0 + s) * m.gru + o] = (uint8_t)quant_u8(v);   // operand of the GRU-1 GEMM
+        conv2_out_u8[(size_t)(s0 + s) * ldo + o] = (uint8_t)quant_u8(v);   // operand of the GRU-1 GEMM
       }
   }
 }
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128) k_conv2(int S, DevModel m, const uint8_t 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_gru(int S, int gru, DevLayerQ wi, DevLayerQ wr,
                                              const float *__restrict__ x, const float *__restrict__ h_old,
-                                             float *__restrict__ h_new, uint8_t *__restrict__ h_new_u8,
+                                             float *__restrict__ h_new, uint8_t *__restrict__ h_new_u8, int ldo,
                                              const int *__restrict__ silence) {
   extern __shared__ uint32_t u_sm[];
   const int K4 = gru / 4, s0 = blockIdx.x * RNN_TS, tid = threadIdx.x;
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(128) k_gru(int S, int gru, DevLayerQ wi, DevLa
       out = z * h + (1 - z) * n;
     }
     h_new[(size_t)(s0 + s) * gru + j] = out;
-    h_new_u8[(size_t)(s0 + s) * gru + j] = (uint8_t)quant_u8(out);
+    h_new_u8[(size_t)(s0 + s) * ldo + j] = (uint8_t)quant_u8(out);
   }
 }
 

@@ -77,7 +77,7 @@ def test_default_model_bit_exact_vs_port(rb, port_default, models_dir):
     print("max |gpu - port|:", worst)
 
 
-@pytest.mark.parametrize("name", ["hot", "little", "g256", "tiny"])
+@pytest.mark.parametrize("name", ["hot", "little", "g256", "tiny", "little_b"])
 def test_other_models_bit_exact_vs_port(rb, models_dir, name):
     from oracle.portbind import Port
     port = Port(os.path.join(models_dir, name + ".bin"))

@@ -49,7 +49,7 @@ def test_exporter_matches_reference_pipeline_on_committed_checkpoint(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/torch/rnnoise"), reason="needs the reference model definition")
-@pytest.mark.parametrize("name", ["default", "hot", "little", "g256"])
+@pytest.mark.parametrize("name", ["default", "hot", "little", "g256", "little_b"])
 def test_exporter_matches_reference_pipeline_on_seeded_models(name, tmp_path):
     """Rebuild the seeded checkpoint with the reference's model class (as oracle/make_models.py did)
     and export it directly: same bytes as the committed blob made through the C detour."""
