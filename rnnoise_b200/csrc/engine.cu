@@ -272,6 +272,7 @@ struct B200Engine {
   int heads2;                       // heads kernel: 1 = k_heads2 (default), 0 = k_heads (RNNOISE_B200_HEADS_KERNEL=cpasync)
   GruTcMaps tc_maps[2][3];          // [frame parity][layer]
   GruTcMaps conv_maps;              // x = c2in, wi = conv2 weights
+  int net_conv1;                    // 1 = conv1 runs as k_net's prologue (default with net_fused); 0 = k_conv1 launch
   int net_fused;                    // 1 = k_net: conv2 + 3 GRU layers in one cluster kernel (default); 0 = one launch per layer
   NetMaps net_maps[2];              // [frame parity]
   NetPtrs net_ptrs[2];
@@ -587,6 +588,7 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   }
   // fused network kernel (net_kernel.cuh): needs the persistent tcgen05 GRU path and conv2 on the tensor cores
   { const char *nk = getenv("RNNOISE_B200_NET_KERNEL"); e->net_fused = !(nk && !strcmp(nk, "layers")) && e->use_tc == 2 && e->conv2_tc; }
+  { const char *c1 = getenv("RNNOISE_B200_NET_CONV1"); e->net_conv1 = e->net_fused && !(c1 && !strcmp(c1, "0")); }
   if (ok && e->net_fused) {
     const size_t hs = Ss * m->gru, hs8 = Ss * a.Kp;
     for (int par = 0; par < 2; par++) {
@@ -596,6 +598,11 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
       nm.x[0] = e->conv_maps.x; nm.wi[0] = e->conv_maps.wi; nm.h[0] = e->conv_maps.x; nm.wr[0] = e->conv_maps.wi;
       np.scale_i[0] = dm.conv2.scale; np.subias_i[0] = dm.conv2.subias;
       np.out_f32[0] = a.conv2_out; np.out_u8[0] = a.conv2_out_u8;
+      if (e->net_conv1) {
+        np.conv1_w = dm.conv1.w; np.conv1_b = dm.conv1.bias;
+        np.features = a.features + (size_t)par * Ss * NB_FEATURES;
+        np.conv1_state = a.conv1_state; np.c2in = a.c2in; np.cond = m->cond;
+      }
       for (int l = 0; l < 3; l++) {
         const GruTcMaps &mp = e->tc_maps[par][l];
         nm.x[l + 1] = mp.x; nm.h[l + 1] = mp.h; nm.wi[l + 1] = mp.wi; nm.wr[l + 1] = mp.wr;
@@ -630,7 +637,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 extern "C" int b200_engine_streams(const B200Engine *e) { return e ? e->a.S : 0; }
-extern "C" int b200_engine_launches_per_frame(const B200Engine *e) { return e && e->net_fused ? NKERNELS - 3 : NKERNELS; }
+extern "C" int b200_engine_launches_per_frame(const B200Engine *e) { return !e ? NKERNELS : NKERNELS - (e->net_fused ? 3 : 0) - (e->net_conv1 ? 1 : 0); }
 
 // Parent-stream bracketing of device-pointer calls (lanes).  Only the kernels that touch the caller's
 // buffers are ordered after the caller's stream -- the prefilter that reads the input, and the output heads /
@@ -719,7 +726,7 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   TL(e, e->frames, TL_BACK_START, st);
   MARK();
   const int gts = (S + RNN_TS - 1) / RNN_TS;
-  k_conv1<<<gts, 128, 0, st>>>(S, e->dm, feat, a.conv1_state, sil, a.c2in, a.Kcp);
+  if (!e->net_conv1) k_conv1<<<gts, 128, 0, st>>>(S, e->dm, feat, a.conv1_state, sil, a.c2in, a.Kcp);
   MARK();
   const bool pdl = e->pdl && !e->profiling;
   if (e->net_fused) {
@@ -1048,7 +1055,7 @@ extern "C" int b200_engine_profile_read(B200Engine *e, float *ms, const char **n
   if (!e || !ms || capacity < NKERNELS) return -1;
   for (int i = 0; i < NKERNELS; i++) {
     ms[i] = (float)e->prof_ms[i];
-    if (names) names[i] = e->net_fused && i == 4 ? "k_net" : e->net_fused && i >= 5 && i <= 7 ? "-" : kKernelNames[i];
+    if (names) names[i] = e->net_fused && i == 4 ? "k_net" : (e->net_fused && i >= 5 && i <= 7) || (e->net_conv1 && i == 3) ? "-" : kKernelNames[i];
   }
   if (frames) *frames = e->prof_frames;
   return NKERNELS;

@@ -1,4 +1,4 @@
-// net_kernel.cuh -- conv2 -> GRU1 -> GRU2 -> GRU3 of compute_rnn() (reference src/rnn.c:44-60) as ONE persistent
+// net_kernel.cuh -- conv1 -> conv2 -> GRU1 -> GRU2 -> GRU3 of compute_rnn() (reference src/rnn.c:44-60) as ONE persistent
 // tcgen05 kernel over a 4-CTA thread-block cluster per 128-stream tile (the default network path; the per-layer
 // kernels k_tc2<> of gru_tc.cuh run the same arithmetic one layer per launch and are kept as cross-checks).
 //
@@ -10,6 +10,12 @@
 //   issued as soon as the current layer's MMAs have retired and hides behind the epilogue tail; the weight-slice
 //   ring (3 stages) and the TMEM accumulator ring (2 stages) simply run on across layer boundaries, so the weights
 //   of the next layer's first slices are already in shared memory when its activations arrive.
+//
+//   conv1 (fp32, 195 -> cond, one sequential FMA chain per output: nnet.c:113-123, sgemv vec_avx.h:672) runs as a
+//   prologue on the epilogue warps while the producer prefetches weights: CTA r computes it for streams
+//   [32 r, 32 r + 32) of the tile (thread = output x 8 streams, inputs transposed in shared memory), updates the
+//   conv1 memory and conv2's u8 operand rows in global memory, and the cluster barrier that starts conv2 publishes
+//   them.  (k_conv1 of rnn_kernels.cuh is the stand-alone cross-check.)
 //
 //   warp 16 (one elected thread): TMA producer + tcgen05.mma issuer      (as in k_tc2)
 //   warps 0..15                 : epilogue, warp w -> TMEM lane quarter w & 3, units 4 * (w >> 2) .. + 4 of a slice
@@ -32,7 +38,14 @@ struct NetPtrs {
   const float *h_old[NET_LAYERS];     // fp32 state of the previous frame (GRU layers)
   float *out_f32[NET_LAYERS];         // conv2_out / new fp32 state
   uint8_t *out_u8[NET_LAYERS];        // their u8 operand mirrors
+  // conv1 prologue (conv1_w == nullptr: conv2's operand rows were prepared by k_conv1)
+  const float *conv1_w, *conv1_b;     // [195][cond], [cond]
+  const float *features;              // [S][65] of this frame
+  float *conv1_state;                 // [S][130]
+  uint8_t *c2in;                      // [S][Kc] conv2 operand rows: [memory (2 x cond) | newest (cond) | pad]
+  int cond;
 };
+#define NET_C1_IN (3 * NB_FEAT)       // 195
 
 __host__ __device__ constexpr int net_stage_bytes(int K) { return 2 * (K / TC_KATOM) * (3 * P_SLICE * TC_KATOM); }
 __host__ __device__ constexpr int net_prm_floats(int N) { return (2 + 3 * 16) * (N / 4); }
@@ -101,7 +114,57 @@ k_net(int S, int Kc, int Kn, int N, const __grid_constant__ NetMaps maps, const 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  cluster_sync_all();   // every CTA of the cluster is up (barriers initialised) before the first cross-CTA dependency
+
+  if (p.conv1_w && warp < P_EPI_WARPS) {
+    // ---- conv1 prologue for streams [m0 + 32 r, + 32), r = this CTA's rank; the X tile region is still free ----
+    float *tmpT = (float *)sAx;                      // [195][32]: input j of the 32 streams (conflict-free, LDS.128 broadcast)
+    const int cond = p.cond, W = cond / 4, r0 = m0 + 32 * (int)blockIdx.y;
+    for (int idx = tid; idx < 32 * NET_C1_IN; idx += 32 * P_EPI_WARPS) {
+      const int sl = idx & 31, j = idx >> 5, row = r0 + sl;
+      float v = 0.f;
+      if (row < S) v = j < 2 * NB_FEAT ? p.conv1_state[(size_t)row * 2 * NB_FEAT + j] : p.features[(size_t)row * NB_FEAT + j - 2 * NB_FEAT];
+      tmpT[idx] = v;
+    }
+    // the words of the operand rows that the memory update moves down (read everything before anything is written)
+    uint32_t rot[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int idx = tid + k * 32 * P_EPI_WARPS, sl = idx / (2 * W), w = idx - sl * 2 * W, row = r0 + sl;
+      rot[k] = (sl < 32 && row < S) ? ((const uint32_t *)(p.c2in + (size_t)row * Kc))[W + w] : 0u;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");
+    const int o = tid & 127, sg = tid >> 7;          // output, group of 8 streams
+    if (o < cond) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] = 0.f;
+      const float *wp = p.conv1_w + o;
+#pragma unroll 5
+      for (int j = 0; j < NET_C1_IN; j++) {          // sequential FMA chain over the inputs (sgemv order)
+        const float w = __ldg(wp + (size_t)j * cond);
+        const float4 a = *(const float4 *)&tmpT[j * 32 + sg * 8], b = *(const float4 *)&tmpT[j * 32 + sg * 8 + 4];
+        acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+        acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+      }
+      const float bias = p.conv1_b[o];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int row = r0 + sg * 8 + i;
+        if (row < S && !silence[row]) p.c2in[(size_t)row * Kc + 2 * cond + o] = (uint8_t)quant_u8(act_tanh(acc[i] + bias));
+      }
+    }
+    // memory updates; silent frames leave both memories untouched (denoise.c:474)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int idx = tid + k * 32 * P_EPI_WARPS, sl = idx / (2 * W), w = idx - sl * 2 * W, row = r0 + sl;
+      if (sl < 32 && row < S && !silence[row]) ((uint32_t *)(p.c2in + (size_t)row * Kc))[w] = rot[k];
+    }
+    for (int idx = tid; idx < 32 * 2 * NB_FEAT; idx += 32 * P_EPI_WARPS) {
+      const int sl = idx / (2 * NB_FEAT), j = idx - sl * 2 * NB_FEAT, row = r0 + sl;
+      if (row < S && !silence[row]) p.conv1_state[(size_t)row * 2 * NB_FEAT + j] = tmpT[(NB_FEAT + j) * 32 + sl];
+    }
+    fence_proxy_async();   // the operand rows are read back by TMA after the cluster barrier
+  }
 
   if (warp == P_EPI_WARPS) {
     // ------------------------------------------------------------------------------------------------
@@ -127,11 +190,17 @@ k_net(int S, int Kc, int Kn, int N, const __grid_constant__ NetMaps maps, const 
     };
     const int njobs = NET_LAYERS * nslice;
     if (lane == 0) {
+      // weights and GRU1's recurrent operand (previous frame's state) do not depend on conv1: fetched beside it
       for (int j = 0; j < P_STAGES && j < njobs; j++) load_B(j);
+      mbar_expect_tx(bar_h, (uint32_t)(atoms_n * TC_A_ATOM_BYTES));
+      for (int a = 0; a < atoms_n; a++) tma_load_2d(smem_u32(sAh + a * TC_A_ATOM_BYTES), &maps.h[1], bar_h, a * TC_KATOM, m0);
+    }
+    __syncwarp();
+    cluster_sync_all();   // every CTA is up (barriers initialised) and the conv1 prologues of the whole tile are in global memory
+    if (lane == 0) {
+      fence_proxy_async();
       mbar_expect_tx(bar_x, (uint32_t)(atoms_c * TC_A_ATOM_BYTES));
       for (int a = 0; a < atoms_c; a++) tma_load_2d(smem_u32(sAx + a * TC_A_ATOM_BYTES), &maps.x[0], bar_x, a * TC_KATOM, m0);
-      mbar_expect_tx(bar_h, (uint32_t)(atoms_n * TC_A_ATOM_BYTES));   // recurrent operand of GRU1: previous frame's state
-      for (int a = 0; a < atoms_n; a++) tma_load_2d(smem_u32(sAh + a * TC_A_ATOM_BYTES), &maps.h[1], bar_h, a * TC_KATOM, m0);
     }
     for (int L = 0; L < NET_LAYERS; L++) {
       if (lane == 0) {
@@ -188,6 +257,7 @@ k_net(int S, int Kc, int Kn, int N, const __grid_constant__ NetMaps maps, const 
     // ------------------------------------------------------------------------------------------------
     // epilogue warps
     // ------------------------------------------------------------------------------------------------
+    cluster_sync_all();   // (pairs with the producer warp's: conv1 of the whole tile is published)
     const int lq = warp & 3, ch = warp >> 2;
     const int srow = m0 + lq * 32 + lane;
     const bool live = srow < S;

@@ -244,19 +244,26 @@ def test_gru_tensor_core_paths_equal_dp4a_path(rb, models_dir):
         for s in (0, 31, 32, 288, 299):
             assert np.array_equal(bits(a.debug("gains", s)), bits(b.debug("gains", s))), (s, f)
     a.destroy(); b.destroy()
-    # network: one fused cluster kernel for conv2 + 3 GRU layers (default) vs one launch per layer
+    # network: one fused cluster kernel for conv1 + conv2 + 3 GRU layers (default) vs the same without the conv1
+    # prologue vs one launch per layer
     os.environ["RNNOISE_B200_NET_KERNEL"] = "layers"
     a = rb.Batch(model, S)
     del os.environ["RNNOISE_B200_NET_KERNEL"]
+    os.environ["RNNOISE_B200_NET_CONV1"] = "0"
+    c = rb.Batch(model, S)
+    del os.environ["RNNOISE_B200_NET_CONV1"]
     b = rb.Batch(model, S)
+    assert (a.launches_per_frame, c.launches_per_frame, b.launches_per_frame) == (10, 7, 6)
     for f in range(2 * frames):
         x = pcm[f % frames]
-        oa, va = a.process(x); ob, vb = b.process(x)
-        for s in (0, 127, 128, 255, 256, 299):
-            for k in ("conv2_out", "gru1", "gru2", "gru3", "gains"):
-                assert np.array_equal(bits(a.debug(k, s)), bits(b.debug(k, s))), (k, s, f)
+        oa, va = a.process(x); oc, vc = c.process(x); ob, vb = b.process(x)
+        for s in (0, 31, 32, 127, 128, 255, 256, 299):
+            for k in ("conv1_state", "conv2_state", "conv2_out", "gru1", "gru2", "gru3", "gains"):
+                assert np.array_equal(bits(a.debug(k, s)), bits(c.debug(k, s))), ("k_net without conv1", k, s, f)
+                assert np.array_equal(bits(a.debug(k, s)), bits(b.debug(k, s))), ("k_net", k, s, f)
+        assert np.array_equal(bits(oa), bits(oc)) and np.array_equal(bits(va), bits(vc)), f
         assert np.array_equal(bits(oa), bits(ob)) and np.array_equal(bits(va), bits(vb)), f
-    a.destroy(); b.destroy()
+    a.destroy(); b.destroy(); c.destroy()
     # pitch: group kernel (default: 16 streams per CTA, home + chain warps) vs the round-1 kernel (4 streams per CTA);
     # S = 300 leaves a partial group (12 of 16 streams) in the last CTA
     os.environ["RNNOISE_B200_PITCH_KERNEL"] = "v1"
