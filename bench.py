@@ -37,6 +37,9 @@ KERNEL_BYTES = {
     "k_pitch": (480 + 1248 + 480 + 4) * 4,                          # xb, ring history read, new frame appended, pitch state
     "k_spectrum": (1728 + 2 * 962 + 96 + 65 + 1 + 2) * 4,           # ring (both windows), X+P, bands, features, flags
     "k_synthesis": (2 * 962 + 96 + 32 + 32 + 2 * 32 + 2 * 480 + 480) * 4,
+    # conv1 (features, conv1 memory r/w, conv2 operand row r/w) + conv2 + 3 GRU layers (fp32 state r/w, u8 mirrors), default dims
+    "k_net": 1292 + 2688 + 3 * 6144,
+    "k_heads": 6276,
 }
 
 
@@ -447,7 +450,7 @@ def main():
     times, nprof = batch.profile_read()
     batch.profile(False)
     lanes = batch.lanes                                            # sub-batches run side by side (include/rnnoise.h)
-    kernels = {k: v / nprof for k, v in times.items()}             # ms per step and kernel, summed over the lanes' launches
+    kernels = {k: v / nprof for k, v in times.items() if k != "-"}   # ms per step and kernel, summed over the lanes' launches
     top = max(kernels, key=kernels.get)
     peaks = {}
     try:
@@ -459,7 +462,7 @@ def main():
     try:   # dram__bytes_read+write per launch of that kernel from the committed ncu --set full capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         key = "k_gru" if top.startswith("k_gru") else top
-        if S == 4096 and key in tj and tj.get("lanes", 1) == lanes:
+        if S == 4096 and key in tj and tj.get("lanes", 1) == lanes and a.model == "default":
             traffic = tj[key]["dram_bytes_per_launch"]
     except Exception:
         pass
