@@ -252,6 +252,11 @@ RNNOISE_EXPORT int rnnoise_batch_debug_set_frame_counter(RNNoiseBatch *b, long l
  *  floats written or -1. */
 RNNOISE_EXPORT int rnnoise_batch_debug_read(RNNoiseBatch *b, int what, int stream, float *dst, int capacity);
 
+/** Bulk form for long parity statistics: item `what` (RNNOISE_DBG_PITCH, _SILENCE, _FEATURES or _GAINS) of every
+ *  stream into dst as [nb_streams][n] floats; capacity must be exactly nb_streams * n (n = 2, 1, 65, 32).
+ *  Returns n or -1. */
+RNNOISE_EXPORT int rnnoise_batch_debug_read_all(RNNoiseBatch *b, int what, float *dst, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

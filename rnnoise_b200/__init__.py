@@ -78,6 +78,7 @@ def lib():
         L.rnnoise_batch_profile_read.argtypes = [vp, fp, C.POINTER(C.c_char_p), ip, C.POINTER(ip)]
         L.rnnoise_batch_timeline_read.restype = ip; L.rnnoise_batch_timeline_read.argtypes = [vp, fp, ip]
         L.rnnoise_batch_debug_read.restype = ip; L.rnnoise_batch_debug_read.argtypes = [vp, ip, ip, fp, ip]
+        L.rnnoise_batch_debug_read_all.restype = ip; L.rnnoise_batch_debug_read_all.argtypes = [vp, ip, fp, ip]
         _lib = L
     return _lib
 
@@ -269,6 +270,14 @@ class Batch:
         if n < 0:
             raise RuntimeError("debug_read failed")
         return buf[:n].copy()
+
+    def debug_all(self, what):
+        """Item `what` (pitch, silence, features, gains) of every stream -> float32 [nb_streams][n]."""
+        n = dict(pitch=2, silence=1, features=65, gains=32)[what]
+        buf = np.empty((self.nb_streams, n), np.float32)
+        if lib().rnnoise_batch_debug_read_all(self.handle, DBG[what], buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size) != n:
+            raise RuntimeError("debug_read_all failed")
+        return buf
 
     def destroy(self):
         if self.handle:

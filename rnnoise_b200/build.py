@@ -11,6 +11,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "librnnoise_b200.so")
+# Tolerance-build experiment: the same sources with FMA contraction allowed in the DSP code.
+# NOT the product: it breaks the bit-exact contract (DESIGN.md "Numerics"); tools/tolerance_experiment.py loads it
+# through $RNNOISE_B200_LIB_PATH to measure what the contract costs and what contraction does to pitch parity.
+SO_FMAD = os.path.join(HERE, "librnnoise_b200_fmad.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -31,10 +35,11 @@ def sources():
     return out
 
 
-def build(force=False, verbose=False):
-    if not force and not _newer(SO, sources() + [os.path.abspath(__file__)]):
-        return SO
-    obj = os.path.join(HERE, "build")
+def build(force=False, verbose=False, fmad=False):
+    so = SO_FMAD if fmad else SO
+    if not force and not _newer(so, sources() + [os.path.abspath(__file__)]):
+        return so
+    obj = os.path.join(HERE, "build_fmad" if fmad else "build")
     os.makedirs(obj, exist_ok=True)
     cmds = []
     cobjs = []
@@ -44,17 +49,17 @@ def build(force=False, verbose=False):
         cobjs.append(o)
     eo = os.path.join(obj, "engine.cu.o")
     extra = os.environ.get("RNNOISE_B200_NVCC_FLAGS", "").split()
-    cmds.append([NVCC, *ARCH, *extra, "-O3", "-lineinfo", "--fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-DRNNOISE_BUILD",
+    cmds.append([NVCC, *ARCH, *extra, "-O3", "-lineinfo", "--fmad=true" if fmad else "--fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-DRNNOISE_BUILD",
                  "-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, "engine.cu"), "-o", eo])
-    cmds.append([NVCC, *ARCH, "-shared", "-o", SO, *cobjs, eo, "-cudart", "static"])
+    cmds.append([NVCC, *ARCH, "-shared", "-o", so, *cobjs, eo, "-cudart", "static"])
     for cmd in cmds:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode:
             raise RuntimeError("build of librnnoise_b200.so failed")
-    return SO
+    return so
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, fmad="--fmad" in sys.argv))

@@ -1107,6 +1107,30 @@ extern "C" int b200_engine_debug_set_frames(B200Engine *e, long long frames) {
   return 0;
 }
 
+// Bulk form for long parity statistics: item `what` of EVERY stream, [S][n] floats (pitch: {period, gain};
+// silence: 0/1; features: 65).  Returns n or -1.
+extern "C" int b200_engine_debug_read_all(B200Engine *e, int what, float *dst, int cap) {
+  if (!e || !dst || e->frames < 1) return -1;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  const Arena &a = e->a;
+  const size_t S = a.S;
+  const int par = frame_arg(e->frames - 1) & 1;
+  const void *src; int n;
+  switch (what) {
+    case RNNOISE_DBG_PITCH: src = a.pitch_state; n = 2; break;
+    case RNNOISE_DBG_SILENCE: src = a.silence + (size_t)par * S; n = 1; break;
+    case RNNOISE_DBG_FEATURES: src = a.features + (size_t)par * S * NB_FEATURES; n = NB_FEATURES; break;
+    case RNNOISE_DBG_GAINS: src = a.gains; n = NB_BANDS; break;
+    default: return -1;
+  }
+  if ((size_t)cap < S * n) return -1;
+  CK(cudaMemcpy(dst, src, S * n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (what == RNNOISE_DBG_PITCH) for (size_t s = 0; s < S; s++) { int p; memcpy(&p, dst + 2 * s, 4); dst[2 * s] = (float)p; }
+  if (what == RNNOISE_DBG_SILENCE) for (size_t s = 0; s < S; s++) { int p; memcpy(&p, dst + s, 4); dst[s] = (float)p; }
+  return n;
+}
+
 extern "C" int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst, int cap) {
   if (!e || !dst || s < 0 || s >= e->a.S || e->frames < 1) return -1;
   CK(cudaSetDevice(e->device));

@@ -46,6 +46,7 @@ int b200_engine_profile(B200Engine *e, int enable);
 int b200_engine_profile_read(B200Engine *e, float *ms, const char **names, int capacity, int *frames);
 int b200_engine_timeline_read(B200Engine *e, float *dst, int capacity);
 int b200_engine_debug_read(B200Engine *e, int what, int stream, float *dst, int capacity);
+int b200_engine_debug_read_all(B200Engine *e, int what, float *dst, int capacity);
 
 #ifdef __cplusplus
 }

@@ -413,6 +413,16 @@ int rnnoise_batch_profile_read(RNNoiseBatch *b, float *ms, const char **names, i
   }
   return n;
 }
+int rnnoise_batch_debug_read_all(RNNoiseBatch *b, int what, float *dst, int capacity) {
+  int l, n = -1, per;
+  if (!b || !dst || b->nb_streams < 1 || capacity % b->nb_streams) return -1;
+  per = capacity / b->nb_streams; /* the caller's row length; must equal the item's length */
+  FOR_LANES(b, l) {
+    n = b200_engine_debug_read_all(b->engine[l], what, dst + (size_t)b->first[l] * per, LANE_COUNT(b, l) * per);
+    if (n != per) return -1;
+  }
+  return n;
+}
 int rnnoise_batch_debug_read(RNNoiseBatch *b, int what, int stream, float *dst, int capacity) {
   int l;
   if (!b || stream < 0 || stream >= b->nb_streams) return -1;

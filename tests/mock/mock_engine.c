@@ -102,3 +102,9 @@ int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst, int cap) 
   if (cap >= 7) { dst[5] = (float)e->device; dst[6] = (float)e->frames; }
   return 5;
 }
+int b200_engine_debug_read_all(B200Engine *e, int what, float *dst, int cap) {
+  (void)what;
+  if (cap < e->S * 2) return -1;
+  for (int s = 0; s < e->S; s++) { dst[2 * s] = (float)e->id; dst[2 * s + 1] = (float)s; }
+  return 2;
+}
