@@ -35,11 +35,13 @@ def sources():
     return out
 
 
-def build(force=False, verbose=False, fmad=False):
-    so = SO_FMAD if fmad else SO
+def build(force=False, verbose=False, fmad=False, variant=None, flags=()):
+    """variant / flags: an experimental build librnnoise_b200_<variant>.so with extra nvcc flags (compile-time knobs
+    such as -DPG=8), loaded through $RNNOISE_B200_LIB_PATH by the A/B tools; never the product library."""
+    so = SO_FMAD if fmad else os.path.join(HERE, f"librnnoise_b200_{variant}.so") if variant else SO
     if not force and not _newer(so, sources() + [os.path.abspath(__file__)]):
         return so
-    obj = os.path.join(HERE, "build_fmad" if fmad else "build")
+    obj = os.path.join(HERE, "build_fmad" if fmad else f"build_{variant}" if variant else "build")
     os.makedirs(obj, exist_ok=True)
     cmds = []
     cobjs = []
@@ -48,7 +50,7 @@ def build(force=False, verbose=False, fmad=False):
         cmds.append(["gcc", "-O2", "-fPIC", "-Wall", "-fvisibility=hidden", "-DRNNOISE_BUILD", "-c", os.path.join(CSRC, c), "-o", o])
         cobjs.append(o)
     eo = os.path.join(obj, "engine.cu.o")
-    extra = os.environ.get("RNNOISE_B200_NVCC_FLAGS", "").split()
+    extra = os.environ.get("RNNOISE_B200_NVCC_FLAGS", "").split() + list(flags)
     cmds.append([NVCC, *ARCH, *extra, "-O3", "-lineinfo", "--fmad=true" if fmad else "--fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-DRNNOISE_BUILD",
                  "-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, "engine.cu"), "-o", eo])
     cmds.append([NVCC, *ARCH, "-shared", "-o", so, *cobjs, eo, "-cudart", "static"])
@@ -62,4 +64,6 @@ def build(force=False, verbose=False, fmad=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, fmad="--fmad" in sys.argv))
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    fl = sys.argv[sys.argv.index("--flags") + 1].split() if "--flags" in sys.argv else []
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, fmad="--fmad" in sys.argv, variant=var, flags=fl))

@@ -57,7 +57,14 @@ struct PitchGroup {
   int ring_base;        // physical index of logical sample 0 AFTER this frame's 480-sample shift
 };
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__) && defined(PITCH_TIMING)
+// diagnostics build (-DPITCH_TIMING=<cta>): that CTA's thread 0 records clock64() after every phase barrier
+__device__ long long g_pitch_t[32];
+#endif
+#if defined(__CUDA_ARCH__) && defined(PITCH_TIMING)
+#define GPHASE_BEGIN { const int tid = threadIdx.x; const int w = tid >> 5, ln = tid & 31; (void)w; (void)ln;
+#define GPHASE_END } __syncthreads(); if (blockIdx.x == PITCH_TIMING && threadIdx.x == 0 && phase_no < 32) g_pitch_t[phase_no] = clock64(); phase_no++;
+#elif defined(__CUDA_ARCH__)
 #define GPHASE_BEGIN { const int tid = threadIdx.x; const int w = tid >> 5, ln = tid & 31; (void)w; (void)ln;
 #define GPHASE_END } __syncthreads();
 #else
@@ -76,6 +83,10 @@ HD float dot_seq(const float *x, const float *y, int n) {
 
 HD void pitch_group(float *sm, const PitchGroup g) {
   const int H = PITCH_BUF_SIZE - FRAME_SIZE;
+#if defined(__CUDA_ARCH__) && defined(PITCH_TIMING)
+  int phase_no = 1;
+  if (blockIdx.x == PITCH_TIMING && threadIdx.x == 0) g_pitch_t[0] = clock64();
+#endif
   // -- P1: append the new frame to the history ring (denoise.c:359-360; a ring instead of the memmove) and
   //    decimate by 2 straight from HBM/L2 (pitch.c:171-173).  The 480 ring slots being overwritten hold the
   //    oldest samples, which the decimation never reads.
@@ -170,41 +181,67 @@ HD void pitch_group(float *sm, const PitchGroup g) {
         for (int c = 0; c < 5; c++) if (5 * ln + c < 147) xc[5 * ln + c] = acc[c];
       }
     } else if (ln < g.n) {
+      // Each chain consumes its inputs in register blocks of CB: the loads of a block are issued together (and,
+      // in program order, before the previous block's stores, which the compiler must assume to alias), so the
+      // shared-memory latency is paid once per block instead of once per step.
       float *sq = GSM(ln);
       const float *lp = sq + P2_LP;
-      if (w == PG) {                         // quarter rate: y4[j] = lp[2j]
+      constexpr int CB = 7;
+      if (w == PG) {                         // quarter rate: y4[j] = lp[2j]; 147 = 21 * 7 lags
         float S = 1.f;
-#pragma unroll 4
+#pragma unroll 8
         for (int j = 0; j < 240; j++) { const float v = lp[2 * j]; S = S + v * v; }
-#pragma unroll 4
-        for (int i = 0; i < 147; i++) {
-          sq[P2_SYY4 + i] = S;
-          const float hi = lp[2 * (i + 240)], lo = lp[2 * i];
-          S = S + (hi * hi - lo * lo); S = RMAX(1, S);
+        float hi[CB], lo[CB], o[CB];
+#pragma unroll
+        for (int t = 0; t < CB; t++) { hi[t] = lp[2 * (t + 240)]; lo[t] = lp[2 * t]; }
+        for (int i0 = 0; i0 < 147; i0 += CB) {
+#pragma unroll
+          for (int t = 0; t < CB; t++) { o[t] = S; S = S + (hi[t] * hi[t] - lo[t] * lo[t]); S = RMAX(1, S); }
+          if (i0 + CB < 147) {
+#pragma unroll
+            for (int t = 0; t < CB; t++) { hi[t] = lp[2 * (i0 + CB + t + 240)]; lo[t] = lp[2 * (i0 + CB + t)]; }
+          }
+#pragma unroll
+          for (int t = 0; t < CB; t++) sq[P2_SYY4 + i0 + t] = o[t];
         }
-      } else if (w == PG + 1) {              // half rate
+      } else if (w == PG + 1) {              // half rate; 294 = 42 * 7 lags
         float S = 1.f;
-#pragma unroll 4
+#pragma unroll 8
         for (int j = 0; j < 480; j++) { const float v = lp[j]; S = S + v * v; }
-#pragma unroll 4
-        for (int i = 0; i < 294; i++) {
-          sq[P2_SYY2 + i] = S;
-          const float hi = lp[i + 480], lo = lp[i];
-          S = S + (hi * hi - lo * lo); S = RMAX(1, S);
+        float hi[CB], lo[CB], o[CB];
+#pragma unroll
+        for (int t = 0; t < CB; t++) { hi[t] = lp[t + 480]; lo[t] = lp[t]; }
+        for (int i0 = 0; i0 < 294; i0 += CB) {
+#pragma unroll
+          for (int t = 0; t < CB; t++) { o[t] = S; S = S + (hi[t] * hi[t] - lo[t] * lo[t]); S = RMAX(1, S); }
+          if (i0 + CB < 294) {
+#pragma unroll
+            for (int t = 0; t < CB; t++) { hi[t] = lp[i0 + CB + t + 480]; lo[t] = lp[i0 + CB + t]; }
+          }
+#pragma unroll
+          for (int t = 0; t < CB; t++) sq[P2_SYY2 + i0 + t] = o[t];
         }
-      } else {                               // yy_lookup; yyl[0] = xx
+      } else {                               // yy_lookup; yyl[0] = xx; 384 = 48 * 8 lags
         const int N = PITCH_FRAME_SIZE / 2;
         const float *x = lp + PITCH_MAX_PERIOD / 2;
         float yy = 0.f;
-#pragma unroll 4
+#pragma unroll 8
         for (int j = 0; j < N; j++) { const float v = x[j]; yy = yy + v * v; }
         sq[P2_YYL] = yy;
         sq[P2_DOT + 0] = yy;                 // xx: the same products added in the same order (pitch.c:449-451)
-#pragma unroll 4
-        for (int i = 1; i <= PITCH_MAX_PERIOD / 2; i++) {
-          const float u = x[-i], v = x[N - i];
-          yy = yy + u * u - v * v;
-          sq[P2_YYL + i] = RMAX(0, yy);
+        constexpr int YB = 8;
+        float u[YB], v[YB], o[YB];
+#pragma unroll
+        for (int t = 0; t < YB; t++) { u[t] = x[-(1 + t)]; v[t] = x[N - (1 + t)]; }
+        for (int i0 = 1; i0 <= PITCH_MAX_PERIOD / 2; i0 += YB) {
+#pragma unroll
+          for (int t = 0; t < YB; t++) { yy = yy + u[t] * u[t] - v[t] * v[t]; o[t] = RMAX(0, yy); }
+          if (i0 + YB <= PITCH_MAX_PERIOD / 2) {
+#pragma unroll
+            for (int t = 0; t < YB; t++) { u[t] = x[-(i0 + YB + t)]; v[t] = x[N - (i0 + YB + t)]; }
+          }
+#pragma unroll
+          for (int t = 0; t < YB; t++) sq[P2_YYL + i0 + t] = o[t];
         }
       }
     }
@@ -218,7 +255,13 @@ HD void pitch_group(float *sm, const PitchGroup g) {
       float *sq = GSM(tid);
       int *mi = (int *)(sq + P2_MISC + PM_INT);
       Best2 b2; best2_init(b2);
-      for (int i = 0; i < 147; i++) best2_visit(b2, i, sq[P2_XC4 + i], sq[P2_SYY4 + i]);
+      for (int i0 = 0; i0 < 147; i0 += 7) {   // 147 = 21 * 7: inputs of a block loaded together, then visited in order
+        float xc[7], sy[7];
+#pragma unroll
+        for (int t = 0; t < 7; t++) { xc[t] = sq[P2_XC4 + i0 + t]; sy[t] = sq[P2_SYY4 + i0 + t]; }
+#pragma unroll
+        for (int t = 0; t < 7; t++) best2_visit(b2, i0 + t, xc[t], sy[t]);
+      }
       mi[0] = b2.p0; mi[1] = b2.p1;
     }
   GPHASE_END

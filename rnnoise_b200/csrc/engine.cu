@@ -1099,6 +1099,15 @@ extern "C" int b200_engine_reset_stream(B200Engine *e, int s) {
   return 0;
 }
 
+#ifdef PITCH_TIMING
+// diagnostics build only: clock64() stamps of one CTA of the last k_pitch2 launch (start, then after each phase)
+extern "C" __attribute__((visibility("default"))) int b200_debug_pitch_timing(long long *dst, int n) {
+  if (n > 32) n = 32;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(dst, g_pitch_t, n * sizeof(long long)) == cudaSuccess ? n : -1;
+}
+#endif
+
 // Test hook: start a FRESH engine (all state zero, nothing enqueued) at an arbitrary frame index, so the
 // counter wrap can be crossed in a few frames.  Fails once a frame has been processed.
 extern "C" int b200_engine_debug_set_frames(B200Engine *e, long long frames) {
@@ -1154,11 +1163,13 @@ extern "C" int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst
     case RNNOISE_DBG_GRU1: case RNNOISE_DBG_GRU2: case RNNOISE_DBG_GRU3:
       src = a.hbuf + (((size_t)par * 3 + (what - RNNOISE_DBG_GRU1)) * S + s) * a.gru; n = a.gru; break;
     case RNNOISE_DBG_CONV1_STATE: src = a.conv1_state + (size_t)s * 2 * NB_FEATURES; n = 2 * NB_FEATURES; break;
-    case RNNOISE_DBG_CONV2_STATE: {   // kept as u8 (the only form conv2 consumes): returned as floats 0..255
+    case RNNOISE_DBG_CONV2_STATE: {   // kept as u8 (the only form conv2 consumes): returned as floats 0..255.
+      // After a frame the operand row is [memory the frame saw (2 x cond) | the frame's conv1 output (cond)]; the
+      // reference's conv2_state at that point (nnet.c:122: mem = tmp[in_size:]) is the LAST 2 x cond entries.
       n = 2 * a.cond;
       if (cap < n) return -1;
       std::vector<uint8_t> tmp(n);
-      CK(cudaMemcpy(tmp.data(), a.c2in + (size_t)s * a.Kcp, n, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(tmp.data(), a.c2in + (size_t)s * a.Kcp + a.cond, n, cudaMemcpyDeviceToHost));
       for (int i = 0; i < n; i++) dst[i] = (float)tmp[i];
       return n;
     }
