@@ -272,6 +272,7 @@ struct B200Engine {
   int heads2;                       // heads kernel: 1 = k_heads2 (default), 0 = k_heads (RNNOISE_B200_HEADS_KERNEL=cpasync)
   GruTcMaps tc_maps[2][3];          // [frame parity][layer]
   GruTcMaps conv_maps;              // x = c2in, wi = conv2 weights
+  int net_cluster;                  // CTAs per cluster of k_net: 4 (default) or 8 ($RNNOISE_B200_NET_CLUSTER; needs gru % 128 == 0)
   int net_conv1;                    // 1 = conv1 runs as k_net's prologue (default with net_fused); 0 = k_conv1 launch
   int net_fused;                    // 1 = k_net: conv2 + 3 GRU layers in one cluster kernel (default); 0 = one launch per layer
   NetMaps net_maps[2];              // [frame parity]
@@ -588,6 +589,7 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   }
   // fused network kernel (net_kernel.cuh): needs the persistent tcgen05 GRU path and conv2 on the tensor cores
   { const char *nk = getenv("RNNOISE_B200_NET_KERNEL"); e->net_fused = !(nk && !strcmp(nk, "layers")) && e->use_tc == 2 && e->conv2_tc; }
+  { const char *nc = getenv("RNNOISE_B200_NET_CLUSTER"); e->net_cluster = nc && !strcmp(nc, "8") && m->gru % (8 * P_SLICE) == 0 ? 8 : 4; }
   { const char *c1 = getenv("RNNOISE_B200_NET_CONV1"); e->net_conv1 = e->net_fused && !(c1 && !strcmp(c1, "0")); }
   if (ok && e->net_fused) {
     const size_t hs = Ss * m->gru, hs8 = Ss * a.Kp;
@@ -730,7 +732,16 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   MARK();
   const bool pdl = e->pdl && !e->profiling;
   if (e->net_fused) {
-    k_net<<<dim3((S + TC_M - 1) / TC_M, 4), P_THREADS, net_smem_bytes(a.Kcp, a.Kp, gru), st>>>(S, a.Kcp, a.Kp, gru, e->net_maps[par], e->net_ptrs[par], sil);
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((S + TC_M - 1) / TC_M, e->net_cluster); cfg.blockDim = dim3(P_THREADS);
+      cfg.dynamicSmemBytes = net_smem_bytes(a.Kcp, a.Kp, gru); cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = e->net_cluster; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, k_net, S, a.Kcp, a.Kp, gru, e->net_maps[par], e->net_ptrs[par], sil));
+    }
     MARK(); MARK(); MARK(); MARK();   // one launch covers the conv2 and GRU slots of the per-kernel profile
   } else {
   if (e->conv2_tc)

@@ -23,7 +23,7 @@
 // Against one launch per layer this removes four kernel boundaries (drain, launch latency, barrier/TMEM/parameter
 // prologue, cold TMA pipeline) per frame and lane.  Arithmetic: identical to k_tc2 / the dp4a kernels, bit for bit
 // (exact s32 accumulators; (float)acc*scale + subias; fma(diag,h,.); Pade sigmoid/tanh; h' = z*h + (1-z)*n).
-// grid = (ceil(S/128), 4), cluster (1,4,1), block = 544, dynamic smem = net_smem_bytes(), 1 CTA / SM.
+// grid = (ceil(S/128), R), cluster (1,R,1) with R = 4 or 8, block = 544, dynamic smem = net_smem_bytes(), 1 CTA / SM.
 #pragma once
 #include "gru_tc.cuh"
 
@@ -48,7 +48,7 @@ struct NetPtrs {
 #define NET_C1_IN (3 * NB_FEAT)       // 195
 
 __host__ __device__ constexpr int net_stage_bytes(int K) { return 2 * (K / TC_KATOM) * (3 * P_SLICE * TC_KATOM); }
-__host__ __device__ constexpr int net_prm_floats(int N) { return (2 + 3 * 16) * (N / 4); }
+__host__ __device__ constexpr int net_prm_floats(int N) { return (2 + 3 * 16) * (N / 4); }   // sized for the smallest cluster (4)
 __host__ __device__ constexpr int net_smem_bytes(int Kc, int Kn, int N) {
   // A tiles: X (max(Kc, Kn) bytes per row) + H (Kn); B ring; parameters of all layers; barriers
   return 1024 + ((Kc > Kn ? Kc : Kn) / TC_KATOM + Kn / TC_KATOM) * TC_A_ATOM_BYTES + P_STAGES * net_stage_bytes(Kn) +
@@ -63,11 +63,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // Kc = conv2's contraction length (3 * cond) and Kn = the GRU layers' (gru), both padded up to multiples of 128 with
 // zero weights; N = gru (a multiple of 64).  Kn is also the row stride of every u8 activation mirror.
-__global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(P_THREADS, 1)
+// The cluster size R = gridDim.y (4 or 8, set by the launch attribute) splits every layer's units R ways: R = 8 halves
+// each CTA's share (and the kernel's latency) at the price of twice the SMs per tile.
+__global__ void __launch_bounds__(P_THREADS, 1)
 k_net(int S, int Kc, int Kn, int N, const __grid_constant__ NetMaps maps, const __grid_constant__ NetPtrs p, const int *__restrict__ silence) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int upc = N / 4, nslice = upc / P_SLICE;
+  const int R = (int)gridDim.y, upc = N / R, nslice = upc / P_SLICE;   // units / slices per CTA
   const int atoms_c = Kc / TC_KATOM, atoms_n = Kn / TC_KATOM, atoms_x = atoms_c > atoms_n ? atoms_c : atoms_n;
   const int m0 = blockIdx.x * TC_M, jq = blockIdx.y * upc;
   uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -118,11 +120,11 @@ k_net(int S, int Kc, int Kn, int N, const __grid_constant__ NetMaps maps, const 
   if (p.conv1_w && warp < P_EPI_WARPS) {
     // ---- conv1 prologue for streams [m0 + 32 r, + 32), r = this CTA's rank; the X tile region is still free ----
     float *tmpT = (float *)sAx;                      // [195][32]: input j of the 32 streams (conflict-free, LDS.128 broadcast)
-    const int cond = p.cond, W = cond / 4, r0 = m0 + 32 * (int)blockIdx.y;
+    const int cond = p.cond, W = cond / 4, nrow = TC_M / R, r0 = m0 + nrow * (int)blockIdx.y;   // this CTA's 32 (R = 4) or 16 streams
     for (int idx = tid; idx < 32 * NET_C1_IN; idx += 32 * P_EPI_WARPS) {
       const int sl = idx & 31, j = idx >> 5, row = r0 + sl;
       float v = 0.f;
-      if (row < S) v = j < 2 * NB_FEAT ? p.conv1_state[(size_t)row * 2 * NB_FEAT + j] : p.features[(size_t)row * NB_FEAT + j - 2 * NB_FEAT];
+      if (sl < nrow && row < S) v = j < 2 * NB_FEAT ? p.conv1_state[(size_t)row * 2 * NB_FEAT + j] : p.features[(size_t)row * NB_FEAT + j - 2 * NB_FEAT];
       tmpT[idx] = v;
     }
     // the words of the operand rows that the memory update moves down (read everything before anything is written)
@@ -130,11 +132,11 @@ k_net(int S, int Kc, int Kn, int N, const __grid_constant__ NetMaps maps, const 
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int idx = tid + k * 32 * P_EPI_WARPS, sl = idx / (2 * W), w = idx - sl * 2 * W, row = r0 + sl;
-      rot[k] = (sl < 32 && row < S) ? ((const uint32_t *)(p.c2in + (size_t)row * Kc))[W + w] : 0u;
+      rot[k] = (sl < nrow && row < S) ? ((const uint32_t *)(p.c2in + (size_t)row * Kc))[W + w] : 0u;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");
     const int o = tid & 127, sg = tid >> 7;          // output, group of 8 streams
-    if (o < cond) {
+    if (o < cond && sg * 8 < nrow) {
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) acc[i] = 0.f;
@@ -157,11 +159,11 @@ k_net(int S, int Kc, int Kn, int N, const __grid_constant__ NetMaps maps, const 
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int idx = tid + k * 32 * P_EPI_WARPS, sl = idx / (2 * W), w = idx - sl * 2 * W, row = r0 + sl;
-      if (sl < 32 && row < S && !silence[row]) ((uint32_t *)(p.c2in + (size_t)row * Kc))[w] = rot[k];
+      if (sl < nrow && row < S && !silence[row]) ((uint32_t *)(p.c2in + (size_t)row * Kc))[w] = rot[k];
     }
     for (int idx = tid; idx < 32 * 2 * NB_FEAT; idx += 32 * P_EPI_WARPS) {
       const int sl = idx / (2 * NB_FEAT), j = idx - sl * 2 * NB_FEAT, row = r0 + sl;
-      if (row < S && !silence[row]) p.conv1_state[(size_t)row * 2 * NB_FEAT + j] = tmpT[(NB_FEAT + j) * 32 + sl];
+      if (sl < nrow && row < S && !silence[row]) p.conv1_state[(size_t)row * 2 * NB_FEAT + j] = tmpT[(NB_FEAT + j) * 32 + sl];
     }
     fence_proxy_async();   // the operand rows are read back by TMA after the cluster barrier
   }

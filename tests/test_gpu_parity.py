@@ -253,17 +253,21 @@ def test_gru_tensor_core_paths_equal_dp4a_path(rb, models_dir):
     c = rb.Batch(model, S)
     del os.environ["RNNOISE_B200_NET_CONV1"]
     b = rb.Batch(model, S)
+    os.environ["RNNOISE_B200_NET_CLUSTER"] = "8"
+    d = rb.Batch(model, S)
+    del os.environ["RNNOISE_B200_NET_CLUSTER"]
     assert (a.launches_per_frame, c.launches_per_frame, b.launches_per_frame) == (10, 7, 6)
     for f in range(2 * frames):
         x = pcm[f % frames]
-        oa, va = a.process(x); oc, vc = c.process(x); ob, vb = b.process(x)
+        oa, va = a.process(x); oc, vc = c.process(x); ob, vb = b.process(x); od, vd = d.process(x)
+        assert np.array_equal(bits(oa), bits(od)) and np.array_equal(bits(va), bits(vd)), ("8-CTA clusters", f)
         for s in (0, 31, 32, 127, 128, 255, 256, 299):
             for k in ("conv1_state", "conv2_state", "conv2_out", "gru1", "gru2", "gru3", "gains"):
                 assert np.array_equal(bits(a.debug(k, s)), bits(c.debug(k, s))), ("k_net without conv1", k, s, f)
                 assert np.array_equal(bits(a.debug(k, s)), bits(b.debug(k, s))), ("k_net", k, s, f)
         assert np.array_equal(bits(oa), bits(oc)) and np.array_equal(bits(va), bits(vc)), f
         assert np.array_equal(bits(oa), bits(ob)) and np.array_equal(bits(va), bits(vb)), f
-    a.destroy(); b.destroy(); c.destroy()
+    a.destroy(); b.destroy(); c.destroy(); d.destroy()
     # pitch: group kernel (default: 16 streams per CTA, home + chain warps) vs the round-1 kernel (4 streams per CTA);
     # S = 300 leaves a partial group (12 of 16 streams) in the last CTA
     os.environ["RNNOISE_B200_PITCH_KERNEL"] = "v1"
