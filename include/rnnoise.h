@@ -190,11 +190,11 @@ RNNOISE_EXPORT int rnnoise_batch_prefilter_device(RNNoiseBatch *b, const float *
 /** Block until everything enqueued on the batch's stream has finished.  0 / -1. */
 RNNOISE_EXPORT int rnnoise_batch_sync(RNNoiseBatch *b);
 
-/** Use an existing CUDA stream (a cudaStream_t passed as void*) for all subsequent work of this
- *  batch, so callers can time with events on their own stream.  NULL restores the private stream.
- *  With several lanes the lanes keep their private streams: the kernels of a device-pointer call that read
- *  the input or write out/vad start after the work already enqueued on the caller's stream, and the caller's
- *  stream waits for the call's completion, so the call still behaves like work on that one stream. */
+/** Order the batch's device-pointer calls with an existing CUDA stream (a cudaStream_t passed as void*), so callers
+ *  can pipeline their own work and time with events on that stream.  The batch keeps its private streams (analysis
+ *  front, network, output tail run side by side across consecutive frames): the kernels of a call that read the input
+ *  or write out/vad start after the work already enqueued on the caller's stream, and the caller's stream waits for the
+ *  call's completion, so the call behaves like work on that one stream.  NULL detaches. */
 RNNOISE_EXPORT int rnnoise_batch_set_stream(RNNoiseBatch *b, void *cuda_stream);
 
 /** Re-zero the state of one stream (what rnnoise_init() does to a DenoiseState): ordered after every frame

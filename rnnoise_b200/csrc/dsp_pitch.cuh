@@ -36,7 +36,8 @@ static_assert(PG >= 4 && PG <= 29 && 10 * PG <= PG_THREADS, "narrow phases are l
 #define P2_X4 P2_B
 #define P2_Y4 (P2_B + 240)
 #define P2_XC2 P2_B
-#define P2_XC4 (P2_B + LP_SIZE)      // [148] coarse correlations
+#define P2_XC4 (P2_B + LP_SIZE)      // [148] coarse correlations; after the coarse scan: candidate gains / xy / yy [3][16]
+#define P2_CAND P2_XC4
 #define P2_SYY4 (P2_XC4 + 148)       // [148] running energy seen by the coarse scan
 #define P2_SYY2 (P2_SYY4 + 148)      // [296] running energy seen by the fine scan
 #define P2_YYL (P2_SYY2 + 296)       // [388] yy_lookup
@@ -73,12 +74,51 @@ __device__ long long g_pitch_t[32];
 #endif
 #define GSM(q) (sm + (q) * P2_STRIDE)
 
-// one serial dot product <x[0..n), y[0..n)>, summed in index order (xcorr_kernel / celt_inner_prod order)
+// One serial dot product <x[0..n), y[0..n)>, summed in index order (xcorr_kernel / celt_inner_prod order).
+// The chain of n dependent additions is the critical path of the narrow phases, and a single warp does not hide
+// its own shared-memory latency: the operands are fetched in register blocks of 8, the next block's loads issued
+// before the current block's additions (measured: 14.6 -> ~6 cycles per step for a lone warp).
 HD float dot_seq(const float *x, const float *y, int n) {
   float s = 0.f;
-#pragma unroll 8
-  for (int i = 0; i < n; i++) s = s + x[i] * y[i];
+  const int nb = n & ~7;
+  float a[8], b[8];
+  if (nb) {
+#pragma unroll
+    for (int t = 0; t < 8; t++) { a[t] = x[t]; b[t] = y[t]; }
+  }
+  for (int i = 0; i < nb; i += 8) {
+    float na[8], nb2[8];
+    const bool more = i + 8 < nb;
+    if (more) {
+#pragma unroll
+      for (int t = 0; t < 8; t++) { na[t] = x[i + 8 + t]; nb2[t] = y[i + 8 + t]; }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; t++) s = s + a[t] * b[t];
+    if (more) {
+#pragma unroll
+      for (int t = 0; t < 8; t++) { a[t] = na[t]; b[t] = nb2[t]; }
+    }
+  }
+  for (int i = nb; i < n; i++) s = s + x[i] * y[i];
   return s;
+}
+
+// find_best_pitch's update for one examined lag (pitch.c:71-98; best2_visit of dsp_core.cuh) without branches: lanes of
+// a warp hold different streams here, and three nested divergent branches per lag cost ~200 cycles per step.  The
+// products are formed unconditionally (no side effects) and the reference's conditions select the updates.
+HD void best2_visit_sel(Best2 &b, int i, float xcorr, float Syy) {
+  float x16 = xcorr;
+  x16 *= 1e-12f;
+  const float num = x16 * x16;
+  const bool c1 = xcorr > 0 && (num * b.den1 > b.num1 * Syy);
+  const bool c0 = c1 && (num * b.den0 > b.num0 * Syy);
+  b.num1 = c0 ? b.num0 : c1 ? num : b.num1;
+  b.den1 = c0 ? b.den0 : c1 ? Syy : b.den1;
+  b.p1 = c0 ? b.p0 : c1 ? i : b.p1;
+  b.num0 = c0 ? num : b.num0;
+  b.den0 = c0 ? Syy : b.den0;
+  b.p0 = c0 ? i : b.p0;
 }
 
 HD void pitch_group(float *sm, const PitchGroup g) {
@@ -95,19 +135,32 @@ HD void pitch_group(float *sm, const PitchGroup g) {
       const float *xb = g.xb + (size_t)w * FRAME_SIZE;
       float *ring = g.ring + (size_t)w * PITCH_BUF_SIZE;
       float *lp0 = GSM(w) + P2_B;
-      for (int j = ln; j < FRAME_SIZE; j += 32) {
-        int p = g.ring_base + H + j; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
-        ring[p] = xb[j];
+      // global loads in batches of independent requests (a warp walks its stream alone: without the batching the
+      // 27 + 15 round trips to L2 / HBM were 19 k cycles of the phase)
+      {
+        float v[15];
+#pragma unroll
+        for (int u = 0; u < 15; u++) v[u] = xb[ln + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 15; u++) {
+          int p = g.ring_base + H + ln + 32 * u; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
+          ring[p] = v[u];
+        }
       }
-      for (int i = ln; i < LP_SIZE; i += 32) {
-        const int k = 2 * i;
-        const float c = k < H ? ring_at(ring, g.ring_base, k) : xb[k - H];
-        const float r = k + 1 < H ? ring_at(ring, g.ring_base, k + 1) : xb[k + 1 - H];
-        if (i) {
-          const float l = k - 1 < H ? ring_at(ring, g.ring_base, k - 1) : xb[k - 1 - H];
-          lp0[i] = .5f * (.5f * (l + r) + c);
-        } else {
-          lp0[i] = .5f * (.5f * r + c);
+#pragma unroll
+      for (int b0 = 0; b0 < 27; b0 += 9) {
+        float c[9], r[9], l[9];
+#pragma unroll
+        for (int u = 0; u < 9; u++) {
+          const int i = ln + 32 * (b0 + u), k = 2 * i;
+          c[u] = k < H ? ring_at(ring, g.ring_base, k) : xb[k - H];
+          r[u] = k + 1 < H ? ring_at(ring, g.ring_base, k + 1) : xb[k + 1 - H];
+          l[u] = i == 0 ? 0.f : k - 1 < H ? ring_at(ring, g.ring_base, k - 1) : xb[k - 1 - H];
+        }
+#pragma unroll
+        for (int u = 0; u < 9; u++) {
+          const int i = ln + 32 * (b0 + u);
+          lp0[i] = i ? .5f * (.5f * (l[u] + r[u]) + c[u]) : .5f * (.5f * r[u] + c[u]);
         }
       }
     }
@@ -260,7 +313,7 @@ HD void pitch_group(float *sm, const PitchGroup g) {
 #pragma unroll
         for (int t = 0; t < 7; t++) { xc[t] = sq[P2_XC4 + i0 + t]; sy[t] = sq[P2_SYY4 + i0 + t]; }
 #pragma unroll
-        for (int t = 0; t < 7; t++) best2_visit(b2, i0 + t, xc[t], sy[t]);
+        for (int t = 0; t < 7; t++) best2_visit_sel(b2, i0 + t, xc[t], sy[t]);
       }
       mi[0] = b2.p0; mi[1] = b2.p1;
     }
@@ -292,8 +345,8 @@ HD void pitch_group(float *sm, const PitchGroup g) {
       const int c0 = 2 * mi[0], c1 = 2 * mi[1];
       const int lo = c0 < c1 ? c0 : c1, hi = c0 < c1 ? c1 : c0;
       Best2 b2; best2_init(b2);
-      for (int i = lo - 2; i <= lo + 2; i++) if (i >= 0 && i < 294) best2_visit(b2, i, xc[i], syy[i]);
-      for (int i = hi - 2; i <= hi + 2; i++) if (i > lo + 2 && i >= 0 && i < 294) best2_visit(b2, i, xc[i], syy[i]);
+      for (int i = lo - 2; i <= lo + 2; i++) if (i >= 0 && i < 294) best2_visit_sel(b2, i, xc[i], syy[i]);
+      for (int i = hi - 2; i <= hi + 2; i++) if (i > lo + 2 && i >= 0 && i < 294) best2_visit_sel(b2, i, xc[i], syy[i]);
       int offset = 0;
       if (b2.p0 > 0 && b2.p0 < 293) {
         float aa = xc[b2.p0 - 1], bb = xc[b2.p0], cc = xc[b2.p0 + 1];
@@ -323,30 +376,46 @@ HD void pitch_group(float *sm, const PitchGroup g) {
       if (ok) sq[P2_DOT + ln] = dot_seq(x, x - off, PITCH_FRAME_SIZE / 2);
     }
   GPHASE_END
-  // -- P11: decision logic of rnn_remove_doubling (pitch.c:457-510), lane = stream
+  // -- P11a: every candidate's pitch gain (pitch.c:458, 483-485: a double-precision sqrt and division each) is
+  //    independent of the others: one lane per (stream, k), k = 1 (the initial candidate T0) .. 15
+  GPHASE_BEGIN
+    if (tid < 15 * PG && tid % PG < g.n) {
+      const int q = tid % PG, k = 1 + tid / PG;
+      float *sq = GSM(q);
+      const float *dot = sq + P2_DOT, *yyl = sq + P2_YYL;
+      const int T0 = ((const int *)(sq + P2_MISC + PM_INT))[2];
+      int T1, T1b;
+      rd_candidate(k, T0, &T1, &T1b);
+      if (k == 1 || T1 >= PITCH_MIN_PERIOD / 2) {
+        const float xy = k == 1 ? dot[1] : .5f * (dot[2 + 2 * (k - 2)] + dot[3 + 2 * (k - 2)]);
+        const float yy = k == 1 ? yyl[T0] : .5f * (yyl[T1] + yyl[T1b]);
+        sq[P2_CAND + k] = pitch_gain(xy, dot[0], yy);
+        sq[P2_CAND + 16 + k] = xy;
+        sq[P2_CAND + 32 + k] = yy;
+      }
+    }
+  GPHASE_END
+  // -- P11b: decision logic of rnn_remove_doubling (pitch.c:457-510) over the precomputed gains, lane = stream.  An
+  //    accepted candidate only overwrites the running best and no threshold depends on an earlier acceptance, so
+  //    walking k upwards with the gains at hand is the reference's loop.
   GPHASE_BEGIN
     if (tid < g.n) {
       float *sq = GSM(tid);
-      const float *dot = sq + P2_DOT, *yyl = sq + P2_YYL;
+      const float *cg = sq + P2_CAND, *cxy = sq + P2_CAND + 16, *cyy = sq + P2_CAND + 32;
       int *mi = (int *)(sq + P2_MISC + PM_INT);
       const float *ps = g.pitch_state + 2 * (size_t)tid;
       const int T0 = mi[2], minperiod = PITCH_MIN_PERIOD / 2;
       const int prev_period = ((const int *)ps)[0] / 2;
       const float prev_gain = ps[1];
-      const float xx = dot[0];
-      float xy = dot[1];
-      float yy = yyl[T0];
-      float best_xy = xy, best_yy = yy;
-      const float g0 = pitch_gain(xy, xx, yy);
+      float best_xy = cxy[1], best_yy = cyy[1];
+      const float g0 = cg[1];
       float gg = g0;
       int Tb = T0, kbest = 1;
       for (int k = 2; k <= 15; k++) {
         int T1, T1b;
         rd_candidate(k, T0, &T1, &T1b);
         if (T1 < minperiod) break;
-        xy = .5f * (dot[2 + 2 * (k - 2)] + dot[3 + 2 * (k - 2)]);
-        yy = .5f * (yyl[T1] + yyl[T1b]);
-        float g1 = pitch_gain(xy, xx, yy);
+        const float g1 = cg[k];
         int d = T1 - prev_period; if (d < 0) d = -d;
         float cont;
         if (d <= 1) cont = prev_gain;
@@ -355,7 +424,7 @@ HD void pitch_group(float *sm, const PitchGroup g) {
         float thresh = RMAX(.3f, .7f * g0 - cont);
         if (T1 < 3 * minperiod) thresh = RMAX(.4f, .85f * g0 - cont);
         else if (T1 < 2 * minperiod) thresh = RMAX(.5f, .9f * g0 - cont);
-        if (g1 > thresh) { best_xy = xy; best_yy = yy; Tb = T1; gg = g1; kbest = k; }
+        if (g1 > thresh) { best_xy = cxy[k]; best_yy = cyy[k]; Tb = T1; gg = g1; kbest = k; }
       }
       best_xy = RMAX(0, best_xy);
       float pg;

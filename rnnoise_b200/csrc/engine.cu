@@ -59,7 +59,7 @@ struct Arena {
   float *xb;           // [2][S][480] high-passed input, double-buffered by frame parity
   float *features;     // [2][S][65] by frame parity (frame f+1's analysis overlaps frame f's network)
   int *silence;        // [2][S]
-  float *conv2_out;    // [S][gru]
+  float *conv2_out;    // [2][S][gru] by frame parity (the output heads of frame f run beside the network of frame f+1)
   float *gains;        // [S][32]
   float *vad;          // [S]
 };
@@ -243,6 +243,9 @@ struct B200Engine {
   float *stage_in[2], *stage_out[2], *stage_vad[2];
   cudaStream_t s_h2d, s_d2h, s_bq;
   cudaStream_t s_front;              // k_pitch/k_spectrum of frame f+1 overlap network + synthesis of frame f
+  cudaStream_t s_tail;               // output heads + synthesis of frame f overlap the network of frame f+1 (third pipeline stage)
+  cudaEvent_t ev_net[2];             // network of frame f done (by parity): the tail may start
+  int tail_overlap;                  // 0: heads + synthesis stay on the network's stream ($RNNOISE_B200_TAIL_OVERLAP=0)
   cudaEvent_t ev_front[2], ev_back[2];   // analysis of frame f done / network+synthesis of frame f done (by parity)
   cudaEvent_t ev_in;                 // input readiness on the caller's stream (non-prefiltered frames)
   // lanes (rnnoise_api.c splits a batch into sub-batches that run concurrently): a lane other than the
@@ -400,6 +403,7 @@ extern "C" void b200_engine_destroy(B200Engine *e) {
   if (e->s_d2h) { cudaStreamSynchronize(e->s_d2h); cudaStreamDestroy(e->s_d2h); }
   if (e->s_bq) { cudaStreamSynchronize(e->s_bq); cudaStreamDestroy(e->s_bq); }
   if (e->s_front) { cudaStreamSynchronize(e->s_front); cudaStreamDestroy(e->s_front); }
+  if (e->s_tail) { cudaStreamSynchronize(e->s_tail); cudaStreamDestroy(e->s_tail); }
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_pin) cudaEventDestroy(e->ev_pin);
   if (e->ev_pout) cudaEventDestroy(e->ev_pout);
@@ -411,6 +415,7 @@ extern "C" void b200_engine_destroy(B200Engine *e) {
     if (e->ev_ana[i]) cudaEventDestroy(e->ev_ana[i]);
     if (e->ev_front[i]) cudaEventDestroy(e->ev_front[i]);
     if (e->ev_back[i]) cudaEventDestroy(e->ev_back[i]);
+    if (e->ev_net[i]) cudaEventDestroy(e->ev_net[i]);
     if (e->ev_mh2d[i]) cudaEventDestroy(e->ev_mh2d[i]);
     if (e->ev_mcomp[i]) cudaEventDestroy(e->ev_mcomp[i]);
     if (e->ev_md2h[i]) cudaEventDestroy(e->ev_md2h[i]);
@@ -474,7 +479,7 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   ok &= !!(a.xb = dalloc<float>(e, 2 * Ss * FRAME_SIZE));
   ok &= !!(a.features = dalloc<float>(e, 2 * Ss * NB_FEATURES));
   ok &= !!(a.silence = dalloc<int>(e, 2 * Ss));
-  ok &= !!(a.conv2_out = dalloc<float>(e, Ss * m->gru));
+  ok &= !!(a.conv2_out = dalloc<float>(e, 2 * Ss * m->gru));
   ok &= !!(a.gains = dalloc<float>(e, Ss * NB_BANDS));
   ok &= !!(a.vad = dalloc<float>(e, Ss));
   e->host_frames = 0;
@@ -501,7 +506,13 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
     e->multi_in[i] = e->multi_out[i] = nullptr; e->multi_vad[i] = nullptr;
     e->ev_mh2d[i] = e->ev_mcomp[i] = e->ev_md2h[i] = nullptr;
   }
-  e->s_h2d = e->s_d2h = e->s_bq = e->s_front = nullptr;
+  e->s_h2d = e->s_d2h = e->s_bq = e->s_front = e->s_tail = nullptr;
+  { const char *to = getenv("RNNOISE_B200_TAIL_OVERLAP"); e->tail_overlap = !(to && !strcmp(to, "0")); }
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    ok &= cudaStreamCreateWithPriority(&e->s_tail, cudaStreamNonBlocking, hi) == cudaSuccess;   // oldest frame first
+  }
   e->ev_in = nullptr;
   const char *ov = getenv("RNNOISE_B200_OVERLAP");
   e->overlap = !(ov && !strcmp(ov, "0"));
@@ -528,6 +539,8 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
     e->ev_h2d[i] = e->ev_comp[i] = e->ev_d2h[i] = e->ev_bq[i] = e->ev_ana[i] = e->ev_front[i] = e->ev_back[i] = nullptr;
     ok &= cudaEventCreateWithFlags(&e->ev_front[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_back[i], cudaEventDisableTiming) == cudaSuccess;
+    e->ev_net[i] = nullptr;
+    ok &= cudaEventCreateWithFlags(&e->ev_net[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_bq[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_ana[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess;
@@ -589,7 +602,16 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   }
   // fused network kernel (net_kernel.cuh): needs the persistent tcgen05 GRU path and conv2 on the tensor cores
   { const char *nk = getenv("RNNOISE_B200_NET_KERNEL"); e->net_fused = !(nk && !strcmp(nk, "layers")) && e->use_tc == 2 && e->conv2_tc; }
-  { const char *nc = getenv("RNNOISE_B200_NET_CLUSTER"); e->net_cluster = nc && !strcmp(nc, "8") && m->gru % (8 * P_SLICE) == 0 ? 8 : 4; }
+  {
+    // CTAs per cluster of k_net.  8 halves every CTA's share of a layer (and the kernel's latency) but takes twice
+    // the SMs per 128-stream tile: it wins while all tiles of the lane still fit the GPU in one wave (measured on
+    // B200: S = 64: 59 vs 88 us, S = 1024: 125 vs 187 us per frame of network time; S = 4096: 268 vs 213 us), so it
+    // is the default up to 16 tiles (2048 streams) per lane.  $RNNOISE_B200_NET_CLUSTER = 4 | 8 overrides.
+    const char *nc = getenv("RNNOISE_B200_NET_CLUSTER");
+    const int tiles = (S + TC_M - 1) / TC_M;
+    int want = nc ? atoi(nc) : tiles * 8 <= 128 ? 8 : 4;
+    e->net_cluster = want == 8 && m->gru % (8 * P_SLICE) == 0 ? 8 : 4;
+  }
   { const char *c1 = getenv("RNNOISE_B200_NET_CONV1"); e->net_conv1 = e->net_fused && !(c1 && !strcmp(c1, "0")); }
   if (ok && e->net_fused) {
     const size_t hs = Ss * m->gru, hs8 = Ss * a.Kp;
@@ -599,7 +621,7 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
       memset(&np, 0, sizeof(np));
       nm.x[0] = e->conv_maps.x; nm.wi[0] = e->conv_maps.wi; nm.h[0] = e->conv_maps.x; nm.wr[0] = e->conv_maps.wi;
       np.scale_i[0] = dm.conv2.scale; np.subias_i[0] = dm.conv2.subias;
-      np.out_f32[0] = a.conv2_out; np.out_u8[0] = a.conv2_out_u8;
+      np.out_f32[0] = a.conv2_out + (size_t)par * hs; np.out_u8[0] = a.conv2_out_u8;
       if (e->net_conv1) {
         np.conv1_w = dm.conv1.w; np.conv1_b = dm.conv1.bias;
         np.features = a.features + (size_t)par * Ss * NB_FEATURES;
@@ -650,9 +672,10 @@ static int parent_enter(B200Engine *e) {
   CK(cudaEventRecord(e->ev_pin, e->parent));
   return 0;
 }
+static cudaStream_t tail_stream(const B200Engine *e) { return e->tail_overlap && e->overlap && !e->profiling ? e->s_tail : e->stream; }
 static int parent_leave(B200Engine *e) {
   if (!e->parent) return 0;
-  CK(cudaEventRecord(e->ev_pout, e->stream));
+  CK(cudaEventRecord(e->ev_pout, tail_stream(e)));
   CK(cudaStreamWaitEvent(e->parent, e->ev_pout, 0));
   return 0;
 }
@@ -685,12 +708,15 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
     h_new[l] = a.hbuf + ((size_t)par * 3 + l) * hstride;
     h_old[l] = a.hbuf + ((size_t)(par ^ 1) * 3 + l) * hstride;
   }
-  // Two-stream software pipeline: the analysis front (biquad -> k_pitch -> k_spectrum) of frame f runs
-  // on s_front and only waits for what it really depends on, so it overlaps the network + synthesis
-  // of frame f-1 still running on the caller's stream `st`.  Hazards: xb[par] (ev_ana), the spectrum
-  // slot f%3 and features/silence[par], last read by frame f-2's back half (ev_back[par]).
+  // Three-stage software pipeline over streams: the analysis front (biquad -> k_pitch -> k_spectrum) of frame f+1
+  // on s_front, the network of frame f on `st`, and the tail (output heads -> synthesis) of frame f-1 on s_tail run
+  // side by side; each stage only waits for what it really depends on.  Hazards: xb[par] (ev_ana); the spectrum
+  // slot f%3, features/silence[par], the GRU states and conv2 output of parity par, all last read by the tail of
+  // frame f-2 (ev_back[par], recorded on the tail's stream).
   const bool overlap = e->overlap && !e->profiling;
   cudaStream_t sf = overlap ? e->s_front : st;
+  cudaStream_t stl = tail_stream(e);
+  float *c2o = a.conv2_out + (size_t)par * hstride;
   int ki = 0;
 #define MARK() do { if (e->profiling) cudaEventRecord(e->ev[ki++], st); } while (0)
   const int fr = frame_arg(e->frames);
@@ -728,6 +754,7 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   TL(e, e->frames, TL_BACK_START, st);
   MARK();
   const int gts = (S + RNN_TS - 1) / RNN_TS;
+  if (stl != st) CK(cudaStreamWaitEvent(st, e->ev_back[par], 0));   // the tail of frame f-2 has read the states of this parity
   if (!e->net_conv1) k_conv1<<<gts, 128, 0, st>>>(S, e->dm, feat, a.conv1_state, sil, a.c2in, a.Kcp);
   MARK();
   const bool pdl = e->pdl && !e->profiling;
@@ -746,9 +773,9 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   } else {
   if (e->conv2_tc)
     CK(launch_pdl(k_tc2<false>, dim3((S + TC_M - 1) / TC_M, 4), dim3(P_THREADS), tc2_smem_bytes<false>(a.Kcp, gru), st, pdl,
-                  S, a.Kcp, gru, a.Kp, e->conv_maps, e->dm.conv2, e->dm.conv2, (const float *)nullptr, a.conv2_out, a.conv2_out_u8, sil));
+                  S, a.Kcp, gru, a.Kp, e->conv_maps, e->dm.conv2, e->dm.conv2, (const float *)nullptr, c2o, a.conv2_out_u8, sil));
   else
-    k_conv2<<<gts, 128, RNN_TS * (3 * cond / 4) * sizeof(uint32_t), st>>>(S, e->dm, a.c2in, a.Kcp, a.conv2_out, a.conv2_out_u8, a.Kp);
+    k_conv2<<<gts, 128, RNN_TS * (3 * cond / 4) * sizeof(uint32_t), st>>>(S, e->dm, a.c2in, a.Kcp, c2o, a.conv2_out_u8, a.Kp);
   MARK();
   const size_t gsm = 2 * RNN_TS * (gru / 4) * sizeof(uint32_t);
   for (int l = 0; l < 3; l++) {
@@ -760,27 +787,33 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
       k_gru_tc<<<dim3((S + TC_M - 1) / TC_M, gru / TC_UNITS), 160, gru_tc_smem_bytes(gru), st>>>(
           S, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, sil);
     } else {
-      const float *x = l == 0 ? a.conv2_out : h_new[l - 1];
+      const float *x = l == 0 ? c2o : h_new[l - 1];
       k_gru<<<dim3(gts, (gru + 127) / 128), 128, gsm, st>>>(S, gru, e->dm.gru_in[l], e->dm.gru_rec[l], x, h_old[l], h_new[l], hu8_new, a.Kp, sil);
     }
     MARK();
   }
   }
-  if (e->parent) CK(cudaStreamWaitEvent(st, e->ev_pin, 0));   // first kernel that writes the caller's buffers
-  const bool pdl_heads = pdl && e->use_tc == 2 && !e->net_fused;   // only the k_tc2 predecessors are PDL-aware
+  if (stl != st) {
+    CK(cudaEventRecord(e->ev_net[par], st));
+    CK(cudaStreamWaitEvent(stl, e->ev_net[par], 0));
+  }
+  if (e->parent) CK(cudaStreamWaitEvent(stl, e->ev_pin, 0));   // first kernel that writes the caller's buffers
+  const bool pdl_heads = pdl && e->use_tc == 2 && !e->net_fused && stl == st;   // only the k_tc2 predecessors are PDL-aware
   if (e->heads2 && e->heads_ns == 2)
-    CK(launch_pdl(k_heads2<2>, dim3((S + 15) / 16), dim3(160), h2_smem_bytes<2>(), st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
+    CK(launch_pdl(k_heads2<2>, dim3((S + 15) / 16), dim3(160), h2_smem_bytes<2>(), stl, pdl_heads, S, e->dm, (const float *)c2o,
                   (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
   else if (e->heads2)
-    CK(launch_pdl(k_heads2<4>, dim3((S + 31) / 32), dim3(160), h2_smem_bytes<4>(), st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
+    CK(launch_pdl(k_heads2<4>, dim3((S + 31) / 32), dim3(160), h2_smem_bytes<4>(), stl, pdl_heads, S, e->dm, (const float *)c2o,
                   (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
   else
-    CK(launch_pdl(k_heads, dim3((S + HEAD_TS - 1) / HEAD_TS), dim3(160), 0, st, pdl_heads, S, e->dm, (const float *)a.conv2_out,
+    CK(launch_pdl(k_heads, dim3((S + HEAD_TS - 1) / HEAD_TS), dim3(160), 0, stl, pdl_heads, S, e->dm, (const float *)c2o,
                   (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
   MARK();
-  CK(launch_pdl(k_synthesis, dim3(S), dim3(DSP_THREADS), SS_TOTAL * sizeof(float), st, pdl_heads, a, (const DspTables *)e->d_tables, d_out, fr, s16, e->io_stride));
-  CK(cudaEventRecord(e->ev_back[par], st));
-  TL(e, e->frames, TL_BACK_END, st);
+  CK(launch_pdl(k_synthesis, dim3(S), dim3(DSP_THREADS), SS_TOTAL * sizeof(float), stl, pdl_heads, a, (const DspTables *)e->d_tables, d_out, fr, s16, e->io_stride));
+  CK(cudaEventRecord(e->ev_back[par], stl));
+  TL(e, e->frames, TL_BACK_END, stl);
+  // an engine driven directly on a caller's stream (no parent bracket): that stream sees the call complete
+  if (stl != st && st != e->own_stream) CK(cudaStreamWaitEvent(st, e->ev_back[par], 0));
   MARK();
 #undef MARK
   CK(cudaGetLastError());
@@ -836,9 +869,9 @@ static int frame_host_async_io(B200Engine *e, void *out, const void *in, float *
   // high-pass prefilter on its own stream: overlaps the previous frame's kernels
   if (issue_prefilter(e, e->stage_in[slot], e->ev_h2d[slot], s16)) return -1;
   // rest of the frame: needs frame n-2's output staging drained
-  CK(cudaStreamWaitEvent(e->stream, e->ev_d2h[slot], 0));
+  CK(cudaStreamWaitEvent(tail_stream(e), e->ev_d2h[slot], 0));   // the tail writes the output staging
   if (frame_device_io(e, e->stage_out[slot], e->stage_in[slot], e->stage_vad[slot], s16)) return -1;
-  CK(cudaEventRecord(e->ev_comp[slot], e->stream));
+  CK(cudaEventRecord(e->ev_comp[slot], tail_stream(e)));
   // copy-out
   CK(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[slot], 0));
   CK(cudaMemcpyAsync(out, e->stage_out[slot], n, cudaMemcpyDeviceToHost, e->s_d2h));
@@ -927,9 +960,9 @@ extern "C" int b200_engine_frames_host_enqueue(B200Engine *e, void *out, const v
     CK(cudaEventRecord(e->ev_mh2d[slot], e->s_h2d));
     // kernels: after the copy-in, and after chunk c-2's copy-out has drained the output slot
     CK(cudaStreamWaitEvent(e->stream, e->ev_mh2d[slot], 0));
-    CK(cudaStreamWaitEvent(e->stream, e->ev_md2h[slot], 0));
+    CK(cudaStreamWaitEvent(tail_stream(e), e->ev_md2h[slot], 0));
     if (frames_device_io(e, e->multi_out[slot], e->multi_in[slot], e->multi_vad[slot], n, n * FRAME_SIZE, n, s16)) return -1;
-    CK(cudaEventRecord(e->ev_mcomp[slot], e->stream));
+    CK(cudaEventRecord(e->ev_mcomp[slot], tail_stream(e)));
     // copy-out
     CK(cudaStreamWaitEvent(e->s_d2h, e->ev_mcomp[slot], 0));
     CK(cudaMemcpy2DAsync((char *)out + (size_t)t0 * FRAME_SIZE * esz, host_pitch, e->multi_out[slot], dev_pitch,
@@ -973,6 +1006,8 @@ extern "C" int b200_engine_train_features_device(B200Engine *e, float *d_rec, co
   CK(cudaStreamWaitEvent(st, e->ev_ana[1], 0));
   CK(cudaStreamWaitEvent(st, e->ev_front[0], 0));
   CK(cudaStreamWaitEvent(st, e->ev_front[1], 0));
+  CK(cudaStreamWaitEvent(st, e->ev_back[0], 0));
+  CK(cudaStreamWaitEvent(st, e->ev_back[1], 0));
   const int par = (int)(e->frames & 1), fr = frame_arg(e->frames);
   CK(cudaMemcpyAsync(a.xb + (size_t)par * S * FRAME_SIZE, d_noisy, S * FRAME_SIZE * sizeof(float), cudaMemcpyDeviceToDevice, st));
   launch_pitch(e, st, fr);
@@ -1027,6 +1062,7 @@ extern "C" int b200_engine_sync(B200Engine *e) {
   CK(cudaStreamSynchronize(e->s_bq));
   CK(cudaStreamSynchronize(e->s_front));
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->s_tail));
   CK(cudaStreamSynchronize(e->s_d2h));
   return 0;
 }
@@ -1035,6 +1071,7 @@ extern "C" int b200_engine_set_stream(B200Engine *e, void *cuda_stream) {
   if (!e) return -1;
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->s_tail));
   e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
   return 0;
 }
@@ -1044,6 +1081,7 @@ extern "C" int b200_engine_set_parent(B200Engine *e, void *parent_stream) {
   if (!e) return -1;
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->s_tail));
   e->stream = e->own_stream;
   e->parent = (cudaStream_t)parent_stream;
   return 0;
@@ -1052,7 +1090,7 @@ extern "C" int b200_engine_set_parent(B200Engine *e, void *parent_stream) {
 extern "C" int b200_engine_profile(B200Engine *e, int enable) {
   if (!e) return -1;
   CK(cudaSetDevice(e->device));
-  CK(cudaStreamSynchronize(e->stream));
+  if (b200_engine_sync(e)) return -1;   // the stream roles change with the profiling flag: drain every stage first
   if (enable) {
     for (int i = 0; i <= NKERNELS; i++) if (!e->ev[i]) CK(cudaEventCreate(&e->ev[i]));
     for (int i = 0; i < NKERNELS; i++) e->prof_ms[i] = 0.0;
@@ -1097,6 +1135,7 @@ extern "C" int b200_engine_reset_stream(B200Engine *e, int s) {
   const Arena &a = e->a;
   const size_t S = a.S;
   cudaStream_t st = e->stream;
+  CK(cudaStreamSynchronize(e->s_tail));   // the tail of the last frame still reads / writes this stream's state
 #define ZERO(ptr, per, copies)                                                                          \
   for (int c_ = 0; c_ < (copies); c_++)                                                                 \
     CK(cudaMemsetAsync((ptr) + ((size_t)c_ * S + s) * (per), 0, (size_t)(per) * sizeof(*(ptr)), st));
@@ -1133,6 +1172,7 @@ extern "C" int b200_engine_debug_read_all(B200Engine *e, int what, float *dst, i
   if (!e || !dst || e->frames < 1) return -1;
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->s_tail));
   const Arena &a = e->a;
   const size_t S = a.S;
   const int par = frame_arg(e->frames - 1) & 1;
@@ -1155,6 +1195,7 @@ extern "C" int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst
   if (!e || !dst || s < 0 || s >= e->a.S || e->frames < 1) return -1;
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->s_tail));
   const Arena &a = e->a;
   const size_t S = a.S;
   const int fl = frame_arg(e->frames - 1);   // the index the kernels of the last frame were handed
@@ -1186,7 +1227,7 @@ extern "C" int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst
     }
     case RNNOISE_DBG_PITCH: src = a.pitch_state + 2 * (size_t)s; n = 2; break;
     case RNNOISE_DBG_SILENCE: src = (const float *)(a.silence + (size_t)par * S + s); n = 1; break;
-    case RNNOISE_DBG_CONV2_OUT: src = a.conv2_out + (size_t)s * a.gru; n = a.gru; break;
+    case RNNOISE_DBG_CONV2_OUT: src = a.conv2_out + ((size_t)par * S + s) * a.gru; n = a.gru; break;
     default: return -1;
   }
   if (cap < n) return -1;

@@ -121,11 +121,21 @@ k_net(int S, int Kc, int Kn, int N, const __grid_constant__ NetMaps maps, const 
     // ---- conv1 prologue for streams [m0 + 32 r, + 32), r = this CTA's rank; the X tile region is still free ----
     float *tmpT = (float *)sAx;                      // [195][32]: input j of the 32 streams (conflict-free, LDS.128 broadcast)
     const int cond = p.cond, W = cond / 4, nrow = TC_M / R, r0 = m0 + nrow * (int)blockIdx.y;   // this CTA's 32 (R = 4) or 16 streams
-    for (int idx = tid; idx < 32 * NET_C1_IN; idx += 32 * P_EPI_WARPS) {
-      const int sl = idx & 31, j = idx >> 5, row = r0 + sl;
-      float v = 0.f;
-      if (sl < nrow && row < S) v = j < 2 * NB_FEAT ? p.conv1_state[(size_t)row * 2 * NB_FEAT + j] : p.features[(size_t)row * NB_FEAT + j - 2 * NB_FEAT];
-      tmpT[idx] = v;
+    {
+      // 32 x 195 inputs, 13 per thread (idx = tid + 512 u): all global loads in flight together, then the stores
+      float v[13];
+#pragma unroll
+      for (int u = 0; u < 13; u++) {
+        const int idx = tid + u * 32 * P_EPI_WARPS, sl = idx & 31, j = idx >> 5, row = r0 + sl;
+        v[u] = 0.f;
+        if (idx < 32 * NET_C1_IN && sl < nrow && row < S)
+          v[u] = j < 2 * NB_FEAT ? p.conv1_state[(size_t)row * 2 * NB_FEAT + j] : p.features[(size_t)row * NB_FEAT + j - 2 * NB_FEAT];
+      }
+#pragma unroll
+      for (int u = 0; u < 13; u++) {
+        const int idx = tid + u * 32 * P_EPI_WARPS;
+        if (idx < 32 * NET_C1_IN) tmpT[idx] = v[u];
+      }
     }
     // the words of the operand rows that the memory update moves down (read everything before anything is written)
     uint32_t rot[4];
@@ -141,12 +151,27 @@ k_net(int S, int Kc, int Kn, int N, const __grid_constant__ NetMaps maps, const 
 #pragma unroll
       for (int i = 0; i < 8; i++) acc[i] = 0.f;
       const float *wp = p.conv1_w + o;
-#pragma unroll 5
-      for (int j = 0; j < NET_C1_IN; j++) {          // sequential FMA chain over the inputs (sgemv order)
-        const float w = __ldg(wp + (size_t)j * cond);
-        const float4 a = *(const float4 *)&tmpT[j * 32 + sg * 8], b = *(const float4 *)&tmpT[j * 32 + sg * 8 + 4];
-        acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
-        acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+      // sequential FMA chain over the 195 inputs (sgemv order); the weights come from L2 / L1 in blocks of 13
+      // independent loads, the next block requested before the current one is consumed (195 = 15 x 13)
+      float wn[13];
+#pragma unroll
+      for (int u = 0; u < 13; u++) wn[u] = __ldg(wp + (size_t)u * cond);
+      for (int j0 = 0; j0 < NET_C1_IN; j0 += 13) {
+        float wc[13];
+#pragma unroll
+        for (int u = 0; u < 13; u++) wc[u] = wn[u];
+        if (j0 + 13 < NET_C1_IN) {
+#pragma unroll
+          for (int u = 0; u < 13; u++) wn[u] = __ldg(wp + (size_t)(j0 + 13 + u) * cond);
+        }
+#pragma unroll
+        for (int u = 0; u < 13; u++) {
+          const int j = j0 + u;
+          const float w = wc[u];
+          const float4 a = *(const float4 *)&tmpT[j * 32 + sg * 8], b = *(const float4 *)&tmpT[j * 32 + sg * 8 + 4];
+          acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+          acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+        }
       }
       const float bias = p.conv1_b[o];
 #pragma unroll

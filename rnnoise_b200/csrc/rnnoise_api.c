@@ -350,12 +350,12 @@ int rnnoise_batch_prefilter_device(RNNoiseBatch *b, const float *d_in_next) {
   FAN_OUT(b, l, b200_engine_prefilter_device(b->engine[l], PCM_AT(d_in_next, b, l, 1, const float)));
   return 0;
 }
-/* One lane: the engine runs on the caller's stream itself.  Several lanes: every lane keeps its private
- * streams and brackets each device-pointer call with the caller's stream (engine.cu: parent_enter/leave). */
+/* Every lane keeps its private streams (the three pipeline stages of engine.cu) and brackets each device-pointer
+ * call with the caller's stream (engine.cu: parent_enter/leave): the kernels that read the caller's input or write
+ * its output start after the work already enqueued on that stream, and the stream waits for the call's completion. */
 int rnnoise_batch_set_stream(RNNoiseBatch *b, void *s) {
   int l;
   if (!b || b->nb_devices != 1) return -1;
-  if (b->lanes == 1) return b200_engine_set_stream(b->engine[0], s);
   FOR_LANES(b, l)
     if (b200_engine_set_parent(b->engine[l], s)) return -1;
   return 0;
@@ -368,7 +368,7 @@ int rnnoise_batch_set_stream_multi(RNNoiseBatch *b, void *const *streams) {
     void *s;
     DEV_OF_LANE(b, l, k);
     s = streams ? streams[k] : NULL;
-    if (b->dev_lane[k + 1] - b->dev_lane[k] == 1 ? b200_engine_set_stream(b->engine[l], s) : b200_engine_set_parent(b->engine[l], s)) return -1;
+    if (b200_engine_set_parent(b->engine[l], s)) return -1;
   }
   return 0;
 }

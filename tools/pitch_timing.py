@@ -23,7 +23,7 @@ pcm = np.ascontiguousarray(np.tile(base, (1, S // 32, 1)))
 model = rnnoise_b200.Model(os.path.join(ROOT, "tests", "golden", "models", "default.bin"))
 b = rnnoise_b200.Batch(model, S)
 names = ["P1 append+decimate", "P2 autocorr", "P3 lpc", "P4 fir", "P5 decimate2", "P6 coarse|chains", "P7 scan", "P8 fine", "P9 pick",
-         "P10 rd dots", "P11 decision", "P12 refine", "P13 final"]
+         "P10 rd dots", "P11a gains", "P11b decision", "P12 refine", "P13 final"]
 acc = np.zeros(len(names))
 n = 0
 for f in range(12):
