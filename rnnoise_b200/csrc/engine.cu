@@ -426,7 +426,10 @@ extern "C" void b200_engine_destroy(B200Engine *e) {
   delete e;
 }
 
-extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int device) {
+extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int device) { return b200_engine_create_on(m, S, device, S); }
+// device_streams = streams of the whole batch that live on this device (all lanes): the kernel choices that depend on
+// how full the GPU is are made on that figure, not on the lane's share.
+extern "C" B200Engine *b200_engine_create_on(const B200HostModel *m, int S, int device, int device_streams) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
     fprintf(stderr, "[rnnoise_b200] no CUDA device available -- this library has no CPU path\n");
@@ -565,7 +568,10 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
   // RNNOISE_B200_GRU_KERNEL = tc2 (default: persistent pipelined tcgen05) | tc1 (one tile per CTA) |
   // dp4a (CUDA-core cross-check); all three produce identical bits
   { const char *hk = getenv("RNNOISE_B200_HEADS_KERNEL"); e->heads2 = !(hk && !strcmp(hk, "cpasync")); }
-  { const char *pk = getenv("RNNOISE_B200_PITCH_KERNEL"); e->pitch2 = !(pk && !strcmp(pk, "v1")); }
+  // Pitch kernel: v1 (4 streams x 96 threads per CTA, 20 streams resident per SM) is the default; v2 (k_pitch2, 16
+  // streams per CTA, far fewer instructions but one CTA per SM) has the same throughput per SM and only wins when a
+  // lane is exactly one wave of its CTAs (profiles/README.md "Pitch kernels"); $RNNOISE_B200_PITCH_KERNEL = v1 | v2.
+  { const char *pk = getenv("RNNOISE_B200_PITCH_KERNEL"); e->pitch2 = pk && !strcmp(pk, "v2"); }
   ok = ok && cudaFuncSetAttribute(k_pitch2, cudaFuncAttributeMaxDynamicSharedMemorySize, PITCH2_SMEM_BYTES) == cudaSuccess;
   { const char *ht = getenv("RNNOISE_B200_HEADS_TILE"); e->heads_ns = ht && !strcmp(ht, "32") ? 4 : 2; }
   ok = ok && cudaFuncSetAttribute(k_heads2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<4>()) == cudaSuccess;
@@ -601,15 +607,23 @@ extern "C" B200Engine *b200_engine_create(const B200HostModel *m, int S, int dev
     ok = ok && cudaFuncSetAttribute(k_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<false>(a.Kcp, m->gru)) == cudaSuccess;
   }
   // fused network kernel (net_kernel.cuh): needs the persistent tcgen05 GRU path and conv2 on the tensor cores
-  { const char *nk = getenv("RNNOISE_B200_NET_KERNEL"); e->net_fused = !(nk && !strcmp(nk, "layers")) && e->use_tc == 2 && e->conv2_tc; }
+  // The fused kernel removes five launches and their drain/fill gaps per frame: it wins while the batch is latency-bound
+  // (S = 64: 0.064 vs 0.080 ms per frame) and loses once the GPU is full, where its CTAs idle through the cluster barriers
+  // on SMs nothing else can share (S = 4096: 0.34 vs 0.32 ms): default up to 512 streams per device.
+  // $RNNOISE_B200_NET_KERNEL = fused | layers overrides.
+  {
+    const char *nk = getenv("RNNOISE_B200_NET_KERNEL");
+    const bool want = nk ? !strcmp(nk, "fused") : device_streams <= 512;
+    e->net_fused = want && e->use_tc == 2 && e->conv2_tc;
+  }
   {
     // CTAs per cluster of k_net.  8 halves every CTA's share of a layer (and the kernel's latency) but takes twice
-    // the SMs per 128-stream tile: it wins while all tiles of the lane still fit the GPU in one wave (measured on
-    // B200: S = 64: 59 vs 88 us, S = 1024: 125 vs 187 us per frame of network time; S = 4096: 268 vs 213 us), so it
-    // is the default up to 16 tiles (2048 streams) per lane.  $RNNOISE_B200_NET_CLUSTER = 4 | 8 overrides.
+    // the SMs per 128-stream tile (measured on B200, network time per frame: S = 64: 59 vs 88 us, S = 1024: 125 vs
+    // 187 us; S = 2048: step 0.206 vs 0.195 ms; S = 4096: 268 vs 213 us): default 8 up to 8 tiles (1024 streams) on the
+    // device.  $RNNOISE_B200_NET_CLUSTER = 4 | 8 overrides.
     const char *nc = getenv("RNNOISE_B200_NET_CLUSTER");
-    const int tiles = (S + TC_M - 1) / TC_M;
-    int want = nc ? atoi(nc) : tiles * 8 <= 128 ? 8 : 4;
+    const int tiles = (device_streams + TC_M - 1) / TC_M;
+    int want = nc ? atoi(nc) : tiles <= 8 ? 8 : 4;
     e->net_cluster = want == 8 && m->gru % (8 * P_SLICE) == 0 ? 8 : 4;
   }
   { const char *c1 = getenv("RNNOISE_B200_NET_CONV1"); e->net_conv1 = e->net_fused && !(c1 && !strcmp(c1, "0")); }

@@ -13,6 +13,8 @@ typedef struct B200Engine B200Engine;
 
 /* Creates device state for nb_streams streams on `device`; uploads the model. NULL on failure. */
 B200Engine *b200_engine_create(const B200HostModel *m, int nb_streams, int device);
+/* same for one lane of a batch that keeps device_streams streams on this device in total */
+B200Engine *b200_engine_create_on(const B200HostModel *m, int nb_streams, int device, int device_streams);
 void b200_engine_destroy(B200Engine *e);
 int b200_engine_streams(const B200Engine *e);
 /* One frame for every stream, device pointers, asynchronous on the engine's stream. */

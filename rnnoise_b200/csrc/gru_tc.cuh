@@ -421,26 +421,25 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty(ts));
+        if (silent) {
 #pragma unroll
-        for (int q = 0; q < P_UPT; q++) {
-          const int u = ub + q;
-          const float h = hcur[q];
-          float out = h;
-          if (!silent) {
+          for (int q = 0; q < P_UPT; q++) outv[q] = hcur[q];
+        } else {
+          float zi[P_UPT], ri[P_UPT], ni[P_UPT], zr[P_UPT], rr[P_UPT], nr[P_UPT];
+#pragma unroll
+          for (int q = 0; q < P_UPT; q++) {
+            const int u = ub + q;
+            const float h = hcur[q];
             const float4 pz = *(const float4 *)&prm[16 * u], pr = *(const float4 *)&prm[16 * u + 4];
             const float4 pn = *(const float4 *)&prm[16 * u + 8], pd = *(const float4 *)&prm[16 * u + 12];
-            float zi = (float)az[q] * pz.x + pz.y;
-            float ri = (float)ar[q] * pr.x + pr.y;
-            float ni = (float)an[q] * pn.x + pn.y;
-            float zr = fmaf(pd.x, h, (float)bz[q] * pz.z + pz.w);
-            float rr = fmaf(pd.y, h, (float)br[q] * pr.z + pr.w);
-            float nr = fmaf(pd.z, h, (float)bn[q] * pn.z + pn.w);
-            float z = act_sigmoid(zi + zr);
-            float r = act_sigmoid(ri + rr);
-            float n = act_tanh(ni + nr * r);
-            out = z * h + (1 - z) * n;
+            zi[q] = (float)az[q] * pz.x + pz.y;
+            ri[q] = (float)ar[q] * pr.x + pr.y;
+            ni[q] = (float)an[q] * pn.x + pn.y;
+            zr[q] = fmaf(pd.x, h, (float)bz[q] * pz.z + pz.w);
+            rr[q] = fmaf(pd.y, h, (float)br[q] * pr.z + pr.w);
+            nr[q] = fmaf(pd.z, h, (float)bn[q] * pn.z + pn.w);
           }
-          outv[q] = out;
+          gru_units<P_UPT>(zi, ri, ni, zr, rr, nr, hcur, outv);
         }
       } else {
         int acc[P_UPT];
@@ -450,7 +449,14 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty(ts));
 #pragma unroll
-        for (int q = 0; q < P_UPT; q++) outv[q] = act_tanh((float)acc[q] * prm[ub + q] + prm[upc + ub + q]);
+        for (int q = 0; q < P_UPT; q++) outv[q] = (float)acc[q] * prm[ub + q] + prm[upc + ub + q];
+          if (fabsf(outv[0]) < ACT_FAST_LIMIT && fabsf(outv[1]) < ACT_FAST_LIMIT && fabsf(outv[2]) < ACT_FAST_LIMIT && fabsf(outv[3]) < ACT_FAST_LIMIT) {
+#pragma unroll
+            for (int q = 0; q < P_UPT; q++) outv[q] = act_tanh_inrange(outv[q]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < P_UPT; q++) outv[q] = act_tanh(outv[q]);
+          }
       }
       if (live) {
         *(float4 *)&out_f32[(size_t)srow * N + jq + ub] = make_float4(outv[0], outv[1], outv[2], outv[3]);

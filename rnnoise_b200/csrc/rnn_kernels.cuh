@@ -53,6 +53,73 @@ __device__ __forceinline__ float act_sigmoid(float x) { // sigmoid8_approx, vec_
   num = num < 1.f ? num : 1.f;
   return num > 0.f ? num : 0.f;
 }
+// Straight-line forms for the tensor-core epilogues.  rcp_rn_den's range test is a (potentially divergent) branch plus
+// a call per activation: twelve per thread and 16-unit slice, which also keeps the compiler from interleaving the
+// independent dependency chains of a thread's units.  For |x| < ACT_FAST_LIMIT the Pade denominators stay below 8e37
+// (11.886 * 1e36 + ...), i.e. inside the branch-free path, whose instructions are exactly those of rcp_rn_den's in-range
+// path: the epilogues test all of a slice's pre-activations once and fall back to act_tanh / act_sigmoid otherwise.
+#define ACT_FAST_LIMIT 1.0e9f
+__device__ __forceinline__ float rcp_den_inrange(float den) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+  const float e = fmaf(den, r, -1.0f);
+  return fmaf(r, -e, r);
+}
+__device__ __forceinline__ float act_tanh_inrange(float x) {
+  const float N0 = 952.52801514f, N1 = 96.39235687f, N2 = 0.60863042f;
+  const float D0 = 952.72399902f, D1 = 413.36801147f, D2 = 11.88600922f;
+  float x2 = x * x;
+  float num = fmaf(fmaf(N2, x2, N1), x2, N0);
+  float den = fmaf(fmaf(D2, x2, D1), x2, D0);
+  num = num * x;
+  den = rcp_den_inrange(den);
+  num = num * den;
+  num = num < 1.f ? num : 1.f;
+  return num > -1.f ? num : -1.f;
+}
+__device__ __forceinline__ float act_sigmoid_inrange(float x) {
+  const float N0 = 238.13200378f, N1 = 6.02452230f, N2 = 0.00950985f;
+  const float D0 = 952.72399902f, D1 = 103.34200287f, D2 = 0.74287558f;
+  float x2 = x * x;
+  float num = fmaf(fmaf(N2, x2, N1), x2, N0);
+  float den = fmaf(fmaf(D2, x2, D1), x2, D0);
+  num = num * x;
+  den = rcp_den_inrange(den);
+  num = fmaf(num, den, .5f);
+  num = num < 1.f ? num : 1.f;
+  return num > 0.f ? num : 0.f;
+}
+// One GRU unit update (compute_generic_gru, nnet.c:65-94) from the six dequantised pre-activations of a unit and its
+// old state, for P units of a thread at once: sums first, one range test, then the branch-free block.
+template <int P>
+__device__ __forceinline__ void gru_units(const float (&zi)[P], const float (&ri)[P], const float (&ni)[P], const float (&zr)[P],
+                                          const float (&rr)[P], const float (&nr)[P], const float (&h)[P], float (&out)[P]) {
+  float zs[P], rs[P];
+  bool ok = true;
+#pragma unroll
+  for (int q = 0; q < P; q++) {
+    zs[q] = zi[q] + zr[q];
+    rs[q] = ri[q] + rr[q];
+    ok = ok && fabsf(zs[q]) < ACT_FAST_LIMIT && fabsf(rs[q]) < ACT_FAST_LIMIT && fabsf(ni[q]) + fabsf(nr[q]) < ACT_FAST_LIMIT;
+  }
+  if (ok) {
+#pragma unroll
+    for (int q = 0; q < P; q++) {
+      const float z = act_sigmoid_inrange(zs[q]);
+      const float r = act_sigmoid_inrange(rs[q]);
+      const float n = act_tanh_inrange(ni[q] + nr[q] * r);
+      out[q] = z * h[q] + (1 - z) * n;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < P; q++) {
+      const float z = act_sigmoid(zs[q]);
+      const float r = act_sigmoid(rs[q]);
+      const float n = act_tanh(ni[q] + nr[q] * r);
+      out[q] = z * h[q] + (1 - z) * n;
+    }
+  }
+}
 __device__ __forceinline__ uint32_t quant_u8(float x) { // vector_ps_to_epi8, vec_avx.h:326-341
   int v = __float2int_rn(fmaf(x, 127.f, 127.f));
   v = v < 0 ? 0 : v;

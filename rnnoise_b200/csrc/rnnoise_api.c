@@ -149,7 +149,7 @@ RNNoiseBatch *rnnoise_batch_create_multi(RNNModel *model, int nb_streams, const 
     for (l = 0; l < lanes && l * per < cnt; l++) {
       b->first[b->lanes] = s0 + l * per;
       b->first[b->lanes + 1] = s0 + ((l + 1) * per < cnt ? (l + 1) * per : cnt);
-      b->engine[b->lanes] = b200_engine_create(&model->host, LANE_COUNT(b, b->lanes), devices[k]);
+      b->engine[b->lanes] = b200_engine_create_on(&model->host, LANE_COUNT(b, b->lanes), devices[k], cnt);
       if (!b->engine[b->lanes]) {
         rnnoise_batch_destroy(b);
         return NULL;

@@ -20,6 +20,9 @@ B200Engine *b200_engine_create(const B200HostModel *m, int nb_streams, int devic
   e->S = nb_streams; e->id = g_next_id++; e->last_reset = -1; e->device = device;
   return e;
 }
+B200Engine *b200_engine_create_on(const B200HostModel *m, int nb_streams, int device, int device_streams) {
+  return device_streams >= nb_streams ? b200_engine_create(m, nb_streams, device) : NULL;
+}
 void b200_engine_destroy(B200Engine *e) { free(e); }
 int b200_engine_streams(const B200Engine *e) { return e->S; }
 
