@@ -26,9 +26,9 @@
 template <int NS> struct H2StageT {
   float xs[8 * NS][H2_XS];
   float ws[H2_KC][NB_GAINS];
-  float wv[H2_KC];
 };
-template <int NS> constexpr int h2_smem_bytes() { return H2_STAGES * (int)sizeof(H2StageT<NS>) + 128; }
+#define H2_MAX_K 4096   // 4 * gru, gru <= 1024: the VAD weight vector is staged whole, once
+template <int NS> constexpr int h2_smem_bytes() { return H2_STAGES * (int)sizeof(H2StageT<NS>) + H2_MAX_K * 4 + 128; }
 #define H2_SMEM_BYTES h2_smem_bytes<4>()
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -46,30 +46,33 @@ __global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *
   typedef H2StageT<NS> H2Stage;
   constexpr int TS = 8 * NS;
   H2Stage *st = (H2Stage *)h2_smem;
+  float *wv_all = (float *)(h2_smem + H2_STAGES * sizeof(H2Stage));   // [4 * gru] vad_dense weights
   __shared__ __align__(8) uint64_t full[H2_STAGES];
   const int s0 = blockIdx.x * TS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gru = m.gru, nchunk = 4 * gru / H2_KC;
   const int live_rows = min(TS, S - s0);
   if (tid == 0) {
-    for (int i = 0; i < H2_STAGES; i++) mbar_init(smem_u32(&full[i]), 33);
+    for (int i = 0; i < H2_STAGES; i++) mbar_init(smem_u32(&full[i]), 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   pdl_trigger();
+  for (int i = tid; i < gru; i += 160) cp_async16(&wv_all[4 * i], m.vad_dense.w + 4 * i, true);   // 4 * gru floats
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   pdl_wait();   // GRU-3 state of this frame
   __syncthreads();
   // producer (warp 4): chunk c -> stage c % H2_STAGES.  gru % 64 == 0, so a chunk never straddles two sources.
-  // The 8 KB weight slab and the VAD weights are one bulk copy each; the 32 activation rows (256 B each, one
-  // per stream) go as 16-byte cp.async pieces, 16 per lane, into the padded rows -- 32 separate 256-byte bulk
-  // copies per chunk were measured at 50 us for the kernel: the per-copy cost of the bulk engine dominated.
-  // Each lane's cp.async.mbarrier.arrive.noinc fires once its pieces have landed; with lane 0's expect_tx
-  // arrival that makes 33 arrivals per phase.
+  // Everything travels as 16-byte cp.async pieces issued by the 32 lanes (activation rows of 256 B per stream into
+  // the padded rows, the 8 KB weight slab): bulk copies cost ~0.5 us EACH on the SM's copy engine whatever their
+  // size -- with two per chunk (weights + VAD weights) the kernel sat at 1.2 us per chunk, 29 us in all, for a
+  // 10 us chain.  Each lane's cp.async.mbarrier.arrive.noinc fires once its pieces have landed: 32 arrivals per phase.
   auto produce = [&](int c) {
     const int buf = c % H2_STAGES, c0 = c * H2_KC, src = c0 / gru, off = c0 - src * gru;
     const uint32_t bar = smem_u32(&full[buf]);
-    if (lane == 0) {
-      mbar_expect_tx(bar, (uint32_t)(H2_KC * NB_GAINS + H2_KC) * 4u);
-      bulk_g2s(smem_u32(&st[buf].ws[0][0]), m.dense_out.w + (size_t)c0 * NB_GAINS, H2_KC * NB_GAINS * 4, bar);
-      bulk_g2s(smem_u32(&st[buf].wv[0]), m.vad_dense.w + c0, H2_KC * 4, bar);
+    const float *wsrc = m.dense_out.w + (size_t)c0 * NB_GAINS;
+#pragma unroll
+    for (int i = 0; i < H2_KC * NB_GAINS / 4 / 32; i++) {   // 512 pieces of the [64][32] weight slab, contiguous in memory
+      const int piece = i * 32 + lane;
+      cp_async16(&st[buf].ws[0][0] + 4 * piece, wsrc + 4 * piece, true);
     }
     const float *p = (src == 0 ? c2 : src == 1 ? g1 : src == 2 ? g2 : g3) + (size_t)s0 * gru + off;
 #pragma unroll
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *
     } else {
 #pragma unroll 4
       for (int kk = 0; kk < H2_KC; kk += 4) {
-        const float4 x = *(const float4 *)&b.xs[lane < TS ? lane : 0][kk], w = *(const float4 *)&b.wv[kk];
+        const float4 x = *(const float4 *)&b.xs[lane < TS ? lane : 0][kk], w = *(const float4 *)&wv_all[c * H2_KC + kk];
         y = y + w.x * x.x; y = y + w.y * x.y; y = y + w.z * x.z; y = y + w.w * x.w;
       }
     }
