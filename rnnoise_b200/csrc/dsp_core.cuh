@@ -100,7 +100,7 @@ struct DspTables {
 // misc slots (float indices relative to the misc base)
 #define MI_AC 0     // [5] autocorrelation
 #define MI_NUM 8    // [5] whitening FIR taps
-#define MI_INT 16   // ints: [0]=best0 [1]=best1 [2]=T (pitch index) [3]=silence [4]=T0 half-rate
+#define MI_INT 16   // ints: [0]=best0 [1]=best1 [2]=T (pitch index) [3]=silence [4]=T0 half-rate [5]=Tb [6]=kbest
 #define MI_BAND 32  // [3][34] band sums (X, P, X.P)
 #define MI_E 136    // [3][32] Ex, Ep, Exp
 #define MI_LY 232   // [32] log band energies
@@ -373,6 +373,23 @@ HD void best2_visit(Best2 &b, int i, float xcorr, float Syy) {
       }
     }
   }
+}
+
+// find_best_pitch's update for one examined lag (pitch.c:71-98; best2_visit of dsp_core.cuh) without branches: lanes of
+// a warp hold different streams here, and three nested divergent branches per lag cost ~200 cycles per step.  The
+// products are formed unconditionally (no side effects) and the reference's conditions select the updates.
+HD void best2_visit_sel(Best2 &b, int i, float xcorr, float Syy) {
+  float x16 = xcorr;
+  x16 *= 1e-12f;
+  const float num = x16 * x16;
+  const bool c1 = xcorr > 0 && (num * b.den1 > b.num1 * Syy);
+  const bool c0 = c1 && (num * b.den0 > b.num0 * Syy);
+  b.num1 = c0 ? b.num0 : c1 ? num : b.num1;
+  b.den1 = c0 ? b.den0 : c1 ? Syy : b.den1;
+  b.p1 = c0 ? b.p0 : c1 ? i : b.p1;
+  b.num0 = c0 ? num : b.num0;
+  b.den0 = c0 ? Syy : b.den0;
+  b.p0 = c0 ? i : b.p0;
 }
 
 // Order-4 whitening filter design (src/pitch.c:181-212, src/celt_lpc.c:38-89): ac[5] -> taps[5]

@@ -104,23 +104,6 @@ HD float dot_seq(const float *x, const float *y, int n) {
   return s;
 }
 
-// find_best_pitch's update for one examined lag (pitch.c:71-98; best2_visit of dsp_core.cuh) without branches: lanes of
-// a warp hold different streams here, and three nested divergent branches per lag cost ~200 cycles per step.  The
-// products are formed unconditionally (no side effects) and the reference's conditions select the updates.
-HD void best2_visit_sel(Best2 &b, int i, float xcorr, float Syy) {
-  float x16 = xcorr;
-  x16 *= 1e-12f;
-  const float num = x16 * x16;
-  const bool c1 = xcorr > 0 && (num * b.den1 > b.num1 * Syy);
-  const bool c0 = c1 && (num * b.den0 > b.num0 * Syy);
-  b.num1 = c0 ? b.num0 : c1 ? num : b.num1;
-  b.den1 = c0 ? b.den0 : c1 ? Syy : b.den1;
-  b.p1 = c0 ? b.p0 : c1 ? i : b.p1;
-  b.num0 = c0 ? num : b.num0;
-  b.den0 = c0 ? Syy : b.den0;
-  b.p0 = c0 ? i : b.p0;
-}
-
 HD void pitch_group(float *sm, const PitchGroup g) {
   const int H = PITCH_BUF_SIZE - FRAME_SIZE;
 #if defined(__CUDA_ARCH__) && defined(PITCH_TIMING)

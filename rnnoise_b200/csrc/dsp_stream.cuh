@@ -174,7 +174,13 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
       float *sq = PSM(tid);
       int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       Best2 b2; best2_init(b2);
-      for (int i = 0; i < 147; i++) best2_visit(b2, i, sq[SM_XC + i], sq[SM_SYY + i]);
+      for (int i0 = 0; i0 < 147; i0 += 3) {   // 147 = 49 * 3: a block's inputs loaded together, then visited in order, branch-free
+        float xc3[3], sy3[3];                  // (32 registers per thread in this kernel: small blocks)
+#pragma unroll
+        for (int u = 0; u < 3; u++) { xc3[u] = sq[SM_XC + i0 + u]; sy3[u] = sq[SM_SYY + i0 + u]; }
+#pragma unroll
+        for (int u = 0; u < 3; u++) best2_visit_sel(b2, i0 + u, xc3[u], sy3[u]);
+      }
       mi[0] = b2.p0; mi[1] = b2.p1;
     }
   MPHASE_END
@@ -225,8 +231,8 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
       const int c0 = 2 * mi[0], c1 = 2 * mi[1];
       const int lo = c0 < c1 ? c0 : c1, hi = c0 < c1 ? c1 : c0;
       Best2 b2; best2_init(b2);
-      for (int i = lo - 2; i <= lo + 2; i++) if (i >= 0 && i < 294) best2_visit(b2, i, xc[i], syy[i]);
-      for (int i = hi - 2; i <= hi + 2; i++) if (i > lo + 2 && i >= 0 && i < 294) best2_visit(b2, i, xc[i], syy[i]);
+      for (int i = lo - 2; i <= lo + 2; i++) if (i >= 0 && i < 294) best2_visit_sel(b2, i, xc[i], syy[i]);
+      for (int i = hi - 2; i <= hi + 2; i++) if (i > lo + 2 && i >= 0 && i < 294) best2_visit_sel(b2, i, xc[i], syy[i]);
       int offset = 0;
       if (b2.p0 > 0 && b2.p0 < 293) {
         float aa = xc[b2.p0 - 1], bb = xc[b2.p0], cc = xc[b2.p0 + 1];
@@ -291,43 +297,49 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
           for (int i = 0; i < N; i++) s = s + x[i] * x[i - off];
           dot[t] = s;
         }
-      } else if (t >= 32 && t < 62) {
-        int c = (t - 32) / 2, k = c + 1, T1, T1b;
-        rd_candidate(k, T0, &T1, &T1b);
-        if (k == 1 || T1 >= PITCH_MIN_PERIOD / 2) {
-          int off = ((t - 32) & 1) ? T1 + 1 : T1 - 1;
-          float s = 0.f;
-#pragma unroll 8
-          for (int i = 0; i < N; i++) s = s + x[i] * x[i - off];
-          dot[t] = s;
-        }
       }
     }
   MPHASE_END
-  // -- decision logic of rnn_remove_doubling (pitch.c:457-527) + state update (denoise.c:369-370)
+  // -- every candidate's pitch gain (pitch.c:458, 483-485: a double-precision sqrt and division each) is independent
+  //    of the others: one lane per (stream, k), k = 1 (the initial candidate T0) .. 15; results in the dead xcorr array
+  MPHASE_BEGIN
+    if (tid < 15 * PITCH_NS && a[tid % PITCH_NS].ring) {
+      const int qq = tid % PITCH_NS, k = 1 + tid / PITCH_NS;
+      float *sq = PSM(qq);
+      const float *dot = sq + SM_DOT, *yyl = sq + SM_YYL;
+      const int T0 = ((const int *)(sq + SM_PITCH_END + MI_INT))[4];
+      int T1, T1b;
+      rd_candidate(k, T0, &T1, &T1b);
+      if (k == 1 || T1 >= PITCH_MIN_PERIOD / 2) {
+        const float xy = k == 1 ? dot[1] : .5f * (dot[2 + 2 * (k - 2)] + dot[3 + 2 * (k - 2)]);
+        const float yy = k == 1 ? yyl[T0] : .5f * (yyl[T1] + yyl[T1b]);
+        sq[SM_XC + k] = pitch_gain(xy, dot[0], yy);
+        sq[SM_XC + 16 + k] = xy;
+        sq[SM_XC + 32 + k] = yy;
+      }
+    }
+  MPHASE_END
+  // -- decision logic of rnn_remove_doubling (pitch.c:457-510) over the precomputed gains.  An accepted candidate only
+  //    overwrites the running best and no threshold depends on an earlier acceptance, so walking k upwards with the
+  //    gains at hand is the reference's loop.
   MPHASE_BEGIN
     if (tid < PITCH_NS && a[tid].ring) {
       const PitchArgs A = a[tid];
       float *sq = PSM(tid);
-      const float *dot = sq + SM_DOT, *yyl = sq + SM_YYL;
+      const float *cg = sq + SM_XC, *cxy = sq + SM_XC + 16, *cyy = sq + SM_XC + 32;
       int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       const int T0 = mi[4], minperiod = PITCH_MIN_PERIOD / 2;
       int prev_period = ((const int *)A.pitch_state)[0] / 2;
       const float prev_gain = A.pitch_state[1];
-      const float xx = dot[0];
-      float xy = dot[1];
-      float yy = yyl[T0];
-      float best_xy = xy, best_yy = yy;
-      const float g0 = pitch_gain(xy, xx, yy);
+      float best_xy = cxy[1], best_yy = cyy[1];
+      const float g0 = cg[1];
       float g = g0;
       int Tb = T0, kbest = 1;
       for (int k = 2; k <= 15; k++) {
         int T1, T1b;
         rd_candidate(k, T0, &T1, &T1b);
         if (T1 < minperiod) break;
-        xy = .5f * (dot[2 + 2 * (k - 2)] + dot[3 + 2 * (k - 2)]);
-        yy = .5f * (yyl[T1] + yyl[T1b]);
-        float g1 = pitch_gain(xy, xx, yy);
+        const float g1 = cg[k];
         int d = T1 - prev_period; if (d < 0) d = -d;
         float cont;
         if (d <= 1) cont = prev_gain;
@@ -336,25 +348,51 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
         float thresh = RMAX(.3f, .7f * g0 - cont);
         if (T1 < 3 * minperiod) thresh = RMAX(.4f, .85f * g0 - cont);
         else if (T1 < 2 * minperiod) thresh = RMAX(.5f, .9f * g0 - cont);
-        if (g1 > thresh) { best_xy = xy; best_yy = yy; Tb = T1; g = g1; kbest = k; }
+        if (g1 > thresh) { best_xy = cxy[k]; best_yy = cyy[k]; Tb = T1; g = g1; kbest = k; }
       }
       best_xy = RMAX(0, best_xy);
       float pg;
       if (best_yy <= best_xy) pg = 1.f;
       else pg = best_xy / (best_yy + 1);
-      // xcorr[k] = <x, x-(T+k-1)>, k = 0..2; the centre lag was summed above in the same order
-      float xc0 = dot[32 + 2 * (kbest - 1)], xc2 = dot[33 + 2 * (kbest - 1)];
-      float xc1 = kbest == 1 ? dot[1] : dot[2 + 2 * (kbest - 2)];
+      if (pg > g) pg = g;
+      mi[5] = Tb; mi[6] = kbest;
+      sq[SM_PITCH_END + MI_AC] = pg;   // the autocorrelation slots are long dead
+    }
+  MPHASE_END
+  // -- the two refinement correlations around the chosen period (pitch.c:513-514: xcorr[k] = <x, x-(T+k-1)>, k = 0, 2;
+  //    the centre lag was summed with the candidates in the same order) -- 2 instead of 30 speculative ones
+  MPHASE_BEGIN
+    if (tid < 2 * PITCH_NS && a[tid % PITCH_NS].ring) {
+      const int qq = tid % PITCH_NS, side = tid / PITCH_NS;
+      float *sq = PSM(qq);
+      const float *x = sq + SM_LP + PITCH_MAX_PERIOD / 2;
+      const int Tb = ((const int *)(sq + SM_PITCH_END + MI_INT))[5];
+      const int off = side ? Tb + 1 : Tb - 1;
+      float s2 = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < PITCH_FRAME_SIZE / 2; i++) s2 = s2 + x[i] * x[i - off];
+      sq[SM_DOT + 32 + side] = s2;
+    }
+  MPHASE_END
+  // -- final offset (pitch.c:515-524) + state update (denoise.c:369-370)
+  MPHASE_BEGIN
+    if (tid < PITCH_NS && a[tid].ring) {
+      const PitchArgs A = a[tid];
+      float *sq = PSM(tid);
+      const float *dot = sq + SM_DOT;
+      int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
+      const int Tb = mi[5], kbest = mi[6];
+      const float xc0 = dot[32], xc2 = dot[33];
+      const float xc1 = kbest == 1 ? dot[1] : dot[2 + 2 * (kbest - 2)];
       int offset;
       if ((xc2 - xc0) > .7f * (xc1 - xc0)) offset = 1;
       else if ((xc0 - xc2) > .7f * (xc1 - xc2)) offset = -1;
       else offset = 0;
-      if (pg > g) pg = g;
       int Tout = 2 * Tb + offset;
       if (Tout < PITCH_MIN_PERIOD) Tout = PITCH_MIN_PERIOD;
       mi[2] = Tout;
       ((int *)A.pitch_state)[0] = Tout;
-      A.pitch_state[1] = pg;
+      A.pitch_state[1] = sq[SM_PITCH_END + MI_AC];
     }
   MPHASE_END
 }
