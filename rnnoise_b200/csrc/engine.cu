@@ -573,7 +573,8 @@ extern "C" B200Engine *b200_engine_create_on(const B200HostModel *m, int S, int 
   // lane is exactly one wave of its CTAs (profiles/README.md "Pitch kernels"); $RNNOISE_B200_PITCH_KERNEL = v1 | v2.
   { const char *pk = getenv("RNNOISE_B200_PITCH_KERNEL"); e->pitch2 = pk && !strcmp(pk, "v2"); }
   ok = ok && cudaFuncSetAttribute(k_pitch2, cudaFuncAttributeMaxDynamicSharedMemorySize, PITCH2_SMEM_BYTES) == cudaSuccess;
-  { const char *ht = getenv("RNNOISE_B200_HEADS_TILE"); e->heads_ns = ht && !strcmp(ht, "32") ? 4 : 2; }
+  { const char *ht = getenv("RNNOISE_B200_HEADS_TILE"); e->heads_ns = ht && !strcmp(ht, "32") ? 4 : ht && !strcmp(ht, "8") ? 1 : 2; }
+  ok = ok && cudaFuncSetAttribute(k_heads2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<1>()) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(k_heads2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<4>()) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(k_heads2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<2>()) == cudaSuccess;
   const char *gk = getenv("RNNOISE_B200_GRU_KERNEL");
@@ -813,7 +814,10 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   }
   if (e->parent) CK(cudaStreamWaitEvent(stl, e->ev_pin, 0));   // first kernel that writes the caller's buffers
   const bool pdl_heads = pdl && e->use_tc == 2 && !e->net_fused && stl == st;   // only the k_tc2 predecessors are PDL-aware
-  if (e->heads2 && e->heads_ns == 2)
+  if (e->heads2 && e->heads_ns == 1)
+    CK(launch_pdl(k_heads2<1>, dim3((S + 7) / 8), dim3(160), h2_smem_bytes<1>(), stl, pdl_heads, S, e->dm, (const float *)c2o,
+                  (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
+  else if (e->heads2 && e->heads_ns == 2)
     CK(launch_pdl(k_heads2<2>, dim3((S + 15) / 16), dim3(160), h2_smem_bytes<2>(), stl, pdl_heads, S, e->dm, (const float *)c2o,
                   (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
   else if (e->heads2)

@@ -242,13 +242,21 @@ def test_gru_tensor_core_paths_equal_dp4a_path(rb, models_dir):
     os.environ["RNNOISE_B200_HEADS_KERNEL"] = "cpasync"
     a = rb.Batch(model, S)
     del os.environ["RNNOISE_B200_HEADS_KERNEL"]
-    b = rb.Batch(model, S)
+    tiles = {}
+    for t in ("8", "16", "32"):           # streams per CTA of the register-tiled kernel (1, 2 or 4 streams per thread)
+        os.environ["RNNOISE_B200_HEADS_TILE"] = t
+        tiles[t] = rb.Batch(model, S)
+    del os.environ["RNNOISE_B200_HEADS_TILE"]
     for f in range(frames):
-        oa, va = a.process(pcm[f]); ob, vb = b.process(pcm[f])
-        assert np.array_equal(bits(oa), bits(ob)) and np.array_equal(bits(va), bits(vb)), f
-        for s in (0, 31, 32, 288, 299):
-            assert np.array_equal(bits(a.debug("gains", s)), bits(b.debug("gains", s))), (s, f)
-    a.destroy(); b.destroy()
+        oa, va = a.process(pcm[f])
+        for t, b in tiles.items():
+            ob, vb = b.process(pcm[f])
+            assert np.array_equal(bits(oa), bits(ob)) and np.array_equal(bits(va), bits(vb)), (t, f)
+            for s in (0, 7, 8, 31, 32, 288, 295, 296, 299):
+                assert np.array_equal(bits(a.debug("gains", s)), bits(b.debug("gains", s))), (t, s, f)
+    a.destroy()
+    for b in tiles.values():
+        b.destroy()
     # network: one fused cluster kernel for conv1 + conv2 + 3 GRU layers (default) vs the same without the conv1
     # prologue vs one launch per layer
     os.environ["RNNOISE_B200_NET_KERNEL"] = "layers"
