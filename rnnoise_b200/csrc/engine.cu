@@ -74,22 +74,24 @@ struct Arena {
 // `in` is float PCM, or 16-bit PCM when in_s16 != 0 (widened exactly like examples/rnnoise_demo.c:56);
 // stream s starts at element s * stride (FRAME_SIZE for frame-at-a-time calls, T * FRAME_SIZE inside
 // a multi-frame call whose buffers hold each stream's audio contiguously).
-__global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__ in_, int frame, int in_s16, int stride) {
+// Every DSP kernel works on a RANGE [r0, r1) of the batch's streams (engine.cu "ranges": the front and the tail of the
+// frame pipeline run as several sub-grids on their own CUDA streams, the network over the whole batch).
+__global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__ in_, int frame, int in_s16, int stride, int r0, int r1) {
   const float *in = (const float *)in_;
   const short *in16 = (const short *)in_;
   __shared__ float tile[32][33];
-  const int lane = threadIdx.x, s0 = blockIdx.x * 32, s = s0 + lane;
+  const int lane = threadIdx.x, s0 = r0 + blockIdx.x * 32, s = s0 + lane;
   float *xb = a.xb + (size_t)(frame & 1) * a.S * FRAME_SIZE;
   float m0 = 0.f, m1 = 0.f;
-  if (s < a.S) { m0 = a.hp_mem[2 * s]; m1 = a.hp_mem[2 * s + 1]; }
-  const int rows = min(32, a.S - s0);
+  if (s < r1) { m0 = a.hp_mem[2 * s]; m1 = a.hp_mem[2 * s + 1]; }
+  const int rows = min(32, r1 - s0);
   for (int c = 0; c < FRAME_SIZE / 32; c++) {
     if (in_s16)
       for (int r = 0; r < rows; r++) tile[r][lane] = (float)in16[(size_t)(s0 + r) * stride + c * 32 + lane];
     else
       for (int r = 0; r < rows; r++) tile[r][lane] = in[(size_t)(s0 + r) * stride + c * 32 + lane];
     __syncwarp();
-    if (s < a.S) {
+    if (s < r1) {
 #pragma unroll 4
       for (int t = 0; t < 32; t++) tile[lane][t] = biquad_step(tile[lane][t], m0, m1);
     }
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__
     for (int r = 0; r < rows; r++) xb[(size_t)(s0 + r) * FRAME_SIZE + c * 32 + lane] = tile[r][lane];
     __syncwarp();
   }
-  if (s < a.S) { a.hp_mem[2 * s] = m0; a.hp_mem[2 * s + 1] = m1; }
+  if (s < r1) { a.hp_mem[2 * s] = m0; a.hp_mem[2 * s + 1] = m1; }
 }
 
 // grid = ceil(S / PITCH_NS), block = PITCH_NS * PITCH_THREADS, dynamic smem = PITCH_NS * SM_PITCH_TOTAL floats
@@ -105,11 +107,11 @@ __global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__
 #define PITCH_MIN_CTAS (2048 / (PITCH_NS * PITCH_THREADS) < 20 ? 2048 / (PITCH_NS * PITCH_THREADS) : 20)   // 32 regs/thread
 #endif
 __global__ void __launch_bounds__(PITCH_NS *PITCH_THREADS, PITCH_MIN_CTAS)
-k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
+k_pitch(Arena a, const DspTables *__restrict__ T, int f, int r0, int r1) {
   extern __shared__ float sm[];
 #if PITCH_NS == 1
   {
-    const int s = blockIdx.x;
+    const int s = r0 + blockIdx.x;
     PitchArgs g;   // in registers: pointers keep their (global) address space
     g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
     g.xb = a.xb + ((size_t)(f & 1) * a.S + s) * FRAME_SIZE;
@@ -122,11 +124,11 @@ k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
   {
     const int grp = blockIdx.x;
     if (threadIdx.x < PITCH_NS) {
-      const int s = grp * PITCH_NS + threadIdx.x;
+      const int s = r0 + grp * PITCH_NS + threadIdx.x;
       PitchArgs g;
       g.ring = nullptr; g.xb = nullptr; g.pitch_state = nullptr;
       g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
-      if (s < a.S) {
+      if (s < r1) {
         g.xb = a.xb + ((size_t)(f & 1) * a.S + s) * FRAME_SIZE;
         g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
         g.pitch_state = a.pitch_state + 2 * (size_t)s;
@@ -142,11 +144,11 @@ k_pitch(Arena a, const DspTables *__restrict__ T, int f) {
 // Default pitch kernel (dsp_pitch.cuh): CTA = PG streams, one home warp per stream + three chain warps.
 // grid = ceil(S / PG), block = PG_THREADS, dynamic smem = PG * P2_STRIDE floats
 #define PITCH2_SMEM_BYTES (PG * P2_STRIDE * (int)sizeof(float))
-__global__ void __launch_bounds__(PG_THREADS, PG <= 8 ? 2 : 1) k_pitch2(Arena a, int f) {
+__global__ void __launch_bounds__(PG_THREADS, PG <= 8 ? 2 : 1) k_pitch2(Arena a, int f, int r0, int r1) {
   extern __shared__ float sm[];
-  const int s0 = blockIdx.x * PG;
+  const int s0 = r0 + blockIdx.x * PG;
   PitchGroup g;
-  g.n = min(PG, a.S - s0);
+  g.n = min(PG, r1 - s0);
   g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
   g.xb = a.xb + ((size_t)(f & 1) * a.S + s0) * FRAME_SIZE;
   g.ring = a.ring + (size_t)s0 * PITCH_BUF_SIZE;
@@ -157,10 +159,10 @@ __global__ void __launch_bounds__(PG_THREADS, PG <= 8 ? 2 : 1) k_pitch2(Arena a,
 #ifndef SPEC_MIN_BLOCKS
 #define SPEC_MIN_BLOCKS 12
 #endif
-__global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena a, const DspTables *__restrict__ T, int f) {
+__global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena a, const DspTables *__restrict__ T, int f, int r0) {
   extern __shared__ float sm[];
   const int par = f & 1, slot = f % 3;
-  const int s = blockIdx.x;
+  const int s = r0 + blockIdx.x;
   SpectrumArgs g;
   g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
   g.ring_base = (int)(((long long)(f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
@@ -210,9 +212,9 @@ __global__ void __launch_bounds__(DSP_THREADS) k_train_features(Arena a, const D
 }
 
 __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTables *__restrict__ T,
-                                                           void *__restrict__ out, int f, int out_s16, int stride) {
+                                                           void *__restrict__ out, int f, int out_s16, int stride, int r0) {
   extern __shared__ float sm[];
-  const int s = blockIdx.x;
+  const int s = r0 + blockIdx.x;
   pdl_wait();   // gains of this frame (k_heads)
   const int par = f & 1, slot = f % 3, dslot = (f + 2) % 3;   // dslot = (f - 1) mod 3
   SynthesisArgs g;
@@ -230,6 +232,7 @@ __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTab
 
 // ------------------------------------------------------------------------------------------------
 #define NKERNELS 10
+#define B200_MAX_RANGES 4
 struct B200Engine {
   int device;
   Arena a;
@@ -241,12 +244,20 @@ struct B200Engine {
   // host-buffer calls: double-buffered device staging, copy streams and the events that chain
   // H2D(n) -> compute(n) -> D2H(n) while protecting slot reuse two frames later
   float *stage_in[2], *stage_out[2], *stage_vad[2];
-  cudaStream_t s_h2d, s_d2h, s_bq;
-  cudaStream_t s_front;              // k_pitch/k_spectrum of frame f+1 overlap network + synthesis of frame f
-  cudaStream_t s_tail;               // output heads + synthesis of frame f overlap the network of frame f+1 (third pipeline stage)
-  cudaEvent_t ev_net[2];             // network of frame f done (by parity): the tail may start
+  cudaStream_t s_h2d, s_d2h;
+  // Ranges ("lanes"): the DSP stages of a frame -- analysis front (biquad -> pitch -> spectrum) and tail (output heads ->
+  // synthesis) -- run as 1..4 sub-grids over contiguous stream ranges, each on its own CUDA streams, so that kernels of
+  // about one wave overlap with each other and with the other pipeline stages; the network kernels, whose CTAs are
+  // latency-bound whatever the grid size, run ONCE over the whole batch on `stream`.
+  int nr;
+  struct Range {
+    int r0, r1;                      // streams [r0, r1)
+    cudaStream_t s_bq, s_front, s_tail;
+    cudaEvent_t ev_bq[2], ev_ana[2]; // biquad of frame f done / pitch of frame f done (xb slot free), by frame parity
+    cudaEvent_t ev_front[2], ev_back[2];   // analysis of frame f done / tail (heads + synthesis) of frame f done
+  } rg[B200_MAX_RANGES];
+  cudaEvent_t ev_net[2];             // network of frame f done (by parity): the tails may start
   int tail_overlap;                  // 0: heads + synthesis stay on the network's stream ($RNNOISE_B200_TAIL_OVERLAP=0)
-  cudaEvent_t ev_front[2], ev_back[2];   // analysis of frame f done / network+synthesis of frame f done (by parity)
   cudaEvent_t ev_in;                 // input readiness on the caller's stream (non-prefiltered frames)
   // lanes (rnnoise_api.c splits a batch into sub-batches that run concurrently): a lane other than the
   // first keeps its own stream but orders every call after `parent` (the caller's stream) and makes
@@ -264,8 +275,7 @@ struct B200Engine {
   float *train_clean_mem, *train_stage;   // [S][480]; [S][2*480 + 98 + 4]
   int overlap;                       // 0: everything on one stream (RNNOISE_B200_OVERLAP=0, profiling)
   int pdl;                           // programmatic dependent launch along the network chain (RNNOISE_B200_PDL=1 enables)
-  cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
-  cudaEvent_t ev_bq[2], ev_ana[2];   // biquad of frame f done / analysis of frame f done (xb slot free)
+  cudaEvent_t ev_h2d[2], ev_d2h[2];
   long long host_frames;
   long long bq_frames;               // frames whose high-pass prefilter has been issued
   int use_tc;                       // GRU kernel: 2 = k_tc2<true> (default), 1 = k_gru_tc, 0 = dp4a cross-check
@@ -401,20 +411,24 @@ extern "C" void b200_engine_destroy(B200Engine *e) {
   for (int i = 0; i <= NKERNELS; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->s_h2d) { cudaStreamSynchronize(e->s_h2d); cudaStreamDestroy(e->s_h2d); }
   if (e->s_d2h) { cudaStreamSynchronize(e->s_d2h); cudaStreamDestroy(e->s_d2h); }
-  if (e->s_bq) { cudaStreamSynchronize(e->s_bq); cudaStreamDestroy(e->s_bq); }
-  if (e->s_front) { cudaStreamSynchronize(e->s_front); cudaStreamDestroy(e->s_front); }
-  if (e->s_tail) { cudaStreamSynchronize(e->s_tail); cudaStreamDestroy(e->s_tail); }
+  for (int r = 0; r < B200_MAX_RANGES; r++) {
+    B200Engine::Range &R = e->rg[r];
+    if (R.s_bq) { cudaStreamSynchronize(R.s_bq); cudaStreamDestroy(R.s_bq); }
+    if (R.s_front) { cudaStreamSynchronize(R.s_front); cudaStreamDestroy(R.s_front); }
+    if (R.s_tail) { cudaStreamSynchronize(R.s_tail); cudaStreamDestroy(R.s_tail); }
+    for (int i = 0; i < 2; i++) {
+      if (R.ev_bq[i]) cudaEventDestroy(R.ev_bq[i]);
+      if (R.ev_ana[i]) cudaEventDestroy(R.ev_ana[i]);
+      if (R.ev_front[i]) cudaEventDestroy(R.ev_front[i]);
+      if (R.ev_back[i]) cudaEventDestroy(R.ev_back[i]);
+    }
+  }
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_pin) cudaEventDestroy(e->ev_pin);
   if (e->ev_pout) cudaEventDestroy(e->ev_pout);
   for (int i = 0; i < 2; i++) {
     if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
-    if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
     if (e->ev_d2h[i]) cudaEventDestroy(e->ev_d2h[i]);
-    if (e->ev_bq[i]) cudaEventDestroy(e->ev_bq[i]);
-    if (e->ev_ana[i]) cudaEventDestroy(e->ev_ana[i]);
-    if (e->ev_front[i]) cudaEventDestroy(e->ev_front[i]);
-    if (e->ev_back[i]) cudaEventDestroy(e->ev_back[i]);
     if (e->ev_net[i]) cudaEventDestroy(e->ev_net[i]);
     if (e->ev_mh2d[i]) cudaEventDestroy(e->ev_mh2d[i]);
     if (e->ev_mcomp[i]) cudaEventDestroy(e->ev_mcomp[i]);
@@ -509,13 +523,9 @@ extern "C" B200Engine *b200_engine_create_on(const B200HostModel *m, int S, int 
     e->multi_in[i] = e->multi_out[i] = nullptr; e->multi_vad[i] = nullptr;
     e->ev_mh2d[i] = e->ev_mcomp[i] = e->ev_md2h[i] = nullptr;
   }
-  e->s_h2d = e->s_d2h = e->s_bq = e->s_front = e->s_tail = nullptr;
+  e->s_h2d = e->s_d2h = nullptr;
+  memset(e->rg, 0, sizeof(e->rg));
   { const char *to = getenv("RNNOISE_B200_TAIL_OVERLAP"); e->tail_overlap = !(to && !strcmp(to, "0")); }
-  {
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    ok &= cudaStreamCreateWithPriority(&e->s_tail, cudaStreamNonBlocking, hi) == cudaSuccess;   // oldest frame first
-  }
   e->ev_in = nullptr;
   const char *ov = getenv("RNNOISE_B200_OVERLAP");
   e->overlap = !(ov && !strcmp(ov, "0"));
@@ -523,31 +533,50 @@ extern "C" B200Engine *b200_engine_create_on(const B200HostModel *m, int S, int 
   // kernels could use: 10.05 M frames/s without vs 9.0-9.3 M with PDL -> opt-in only
   { const char *pd = getenv("RNNOISE_B200_PDL"); e->pdl = pd && !strcmp(pd, "1"); }
   {
-    // the analysis front runs at the lowest stream priority: the network kernels of the previous frame
-    // (caller's stream) get SM slots first.  (Capping the front kernels' grid to leave room was measured
+    // Ranges of the DSP stages (measured on B200 with whole sub-batches, tools/lanes_experiment.py: two against one
+    // +10 % at 1024 streams, +5 % at 2048, +13 % at 3072, +10 % at 4096, +3 % at 6144, +2 % at 8192, -1 % at 16384; four
+    // are slower than two at 4096): two from 1024 to 12287 streams, else one; whole 128-stream tiles except the last.
+    // $RNNOISE_B200_LANES overrides.
+    const char *ln = getenv("RNNOISE_B200_LANES");
+    int nr = ln && atoi(ln) > 0 ? atoi(ln) : (S >= 1024 && S < 12288) ? 2 : 1;
+    if (nr > B200_MAX_RANGES) nr = B200_MAX_RANGES;
+    while (nr > 1 && S / nr < 128) nr--;
+    const int per = ((S + nr - 1) / nr + 127) / 128 * 128;
+    e->nr = 0;
+    for (int r = 0; r < nr && r * per < S; r++) {
+      e->rg[r].r0 = r * per;
+      e->rg[r].r1 = (r + 1) * per < S ? (r + 1) * per : S;
+      e->nr++;
+    }
+    // stream priorities: the tails (oldest frame) and the network first, the analysis fronts last -- the front of frame
+    // f+1 only fills what the back of frame f leaves free.  (Capping the front kernels' grid to leave room was measured
     // and is worse than the plain one-CTA-per-stream grid: profiles/README.md.)
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = lowest priority (largest value)
     const char *pr = getenv("RNNOISE_B200_FRONT_PRIORITY");
-    ok &= cudaStreamCreateWithPriority(&e->s_front, cudaStreamNonBlocking, pr && !strcmp(pr, "high") ? hi : lo) == cudaSuccess;
+    for (int r = 0; r < e->nr; r++) {
+      B200Engine::Range &R = e->rg[r];
+      ok &= cudaStreamCreateWithPriority(&R.s_tail, cudaStreamNonBlocking, hi) == cudaSuccess;
+      ok &= cudaStreamCreateWithPriority(&R.s_front, cudaStreamNonBlocking, pr && !strcmp(pr, "high") ? hi : lo) == cudaSuccess;
+      ok &= cudaStreamCreateWithFlags(&R.s_bq, cudaStreamNonBlocking) == cudaSuccess;
+      for (int i = 0; i < 2; i++) {
+        ok &= cudaEventCreateWithFlags(&R.ev_bq[i], cudaEventDisableTiming) == cudaSuccess;
+        ok &= cudaEventCreateWithFlags(&R.ev_ana[i], cudaEventDisableTiming) == cudaSuccess;
+        ok &= cudaEventCreateWithFlags(&R.ev_front[i], cudaEventDisableTiming) == cudaSuccess;
+        ok &= cudaEventCreateWithFlags(&R.ev_back[i], cudaEventDisableTiming) == cudaSuccess;
+      }
+    }
   }
   ok &= cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) == cudaSuccess;
-  ok &= cudaStreamCreateWithFlags(&e->s_bq, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 2; i++) {
     ok &= !!(e->stage_in[i] = dalloc<float>(e, Ss * FRAME_SIZE));
     ok &= !!(e->stage_out[i] = dalloc<float>(e, Ss * FRAME_SIZE));
     ok &= !!(e->stage_vad[i] = dalloc<float>(e, Ss));
-    e->ev_h2d[i] = e->ev_comp[i] = e->ev_d2h[i] = e->ev_bq[i] = e->ev_ana[i] = e->ev_front[i] = e->ev_back[i] = nullptr;
-    ok &= cudaEventCreateWithFlags(&e->ev_front[i], cudaEventDisableTiming) == cudaSuccess;
-    ok &= cudaEventCreateWithFlags(&e->ev_back[i], cudaEventDisableTiming) == cudaSuccess;
-    e->ev_net[i] = nullptr;
+    e->ev_h2d[i] = e->ev_d2h[i] = e->ev_net[i] = nullptr;
     ok &= cudaEventCreateWithFlags(&e->ev_net[i], cudaEventDisableTiming) == cudaSuccess;
-    ok &= cudaEventCreateWithFlags(&e->ev_bq[i], cudaEventDisableTiming) == cudaSuccess;
-    ok &= cudaEventCreateWithFlags(&e->ev_ana[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess;
-    ok &= cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_mh2d[i], cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&e->ev_mcomp[i], cudaEventDisableTiming) == cudaSuccess;
@@ -676,7 +705,11 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 extern "C" int b200_engine_streams(const B200Engine *e) { return e ? e->a.S : 0; }
-extern "C" int b200_engine_launches_per_frame(const B200Engine *e) { return !e ? NKERNELS : NKERNELS - (e->net_fused ? 3 : 0) - (e->net_conv1 ? 1 : 0); }
+extern "C" int b200_engine_ranges(const B200Engine *e) { return e ? e->nr : 0; }
+// kernel launches of one frame: the five DSP kernels once per range, the network once for the whole batch
+extern "C" int b200_engine_launches_per_frame(const B200Engine *e) {
+  return !e ? NKERNELS : 5 * e->nr + (e->net_fused ? (e->net_conv1 ? 1 : 2) : 5);
+}
 
 // Parent-stream bracketing of device-pointer calls (lanes).  Only the kernels that touch the caller's
 // buffers are ordered after the caller's stream -- the prefilter that reads the input, and the output heads /
@@ -687,19 +720,21 @@ static int parent_enter(B200Engine *e) {
   CK(cudaEventRecord(e->ev_pin, e->parent));
   return 0;
 }
-static cudaStream_t tail_stream(const B200Engine *e) { return e->tail_overlap && e->overlap && !e->profiling ? e->s_tail : e->stream; }
+static bool tail_separate(const B200Engine *e) { return e->tail_overlap && e->overlap && !e->profiling; }
+static cudaStream_t tail_stream(const B200Engine *e, int r) { return tail_separate(e) ? e->rg[r].s_tail : e->stream; }
+// the caller's stream waits for the tails of the last frame handed to the engine
 static int parent_leave(B200Engine *e) {
-  if (!e->parent) return 0;
-  CK(cudaEventRecord(e->ev_pout, tail_stream(e)));
-  CK(cudaStreamWaitEvent(e->parent, e->ev_pout, 0));
+  if (!e->parent || e->frames < 1) return 0;
+  const int par = (int)((e->frames - 1) & 1);
+  for (int r = 0; r < e->nr; r++) CK(cudaStreamWaitEvent(e->parent, e->rg[r].ev_back[par], 0));
   return 0;
 }
-static void launch_pitch(B200Engine *e, cudaStream_t st, int fr) {
-  const int S = e->a.S;
+static void launch_pitch(B200Engine *e, cudaStream_t st, int fr, int r0, int r1) {
+  const int n = r1 - r0;
   if (e->pitch2)
-    k_pitch2<<<(S + PG - 1) / PG, PG_THREADS, PITCH2_SMEM_BYTES, st>>>(e->a, fr);
+    k_pitch2<<<(n + PG - 1) / PG, PG_THREADS, PITCH2_SMEM_BYTES, st>>>(e->a, fr, r0, r1);
   else
-    k_pitch<<<(S + PITCH_NS - 1) / PITCH_NS, PITCH_NS * PITCH_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), st>>>(e->a, e->d_tables, fr);
+    k_pitch<<<(n + PITCH_NS - 1) / PITCH_NS, PITCH_NS * PITCH_THREADS, PITCH_NS * SM_PITCH_TOTAL * sizeof(float), st>>>(e->a, e->d_tables, fr, r0, r1);
 }
 static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *d_vad, int s16);
 extern "C" int b200_engine_frame_device(B200Engine *e, float *d_out, const float *d_in, float *d_vad) {
@@ -723,53 +758,66 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
     h_new[l] = a.hbuf + ((size_t)par * 3 + l) * hstride;
     h_old[l] = a.hbuf + ((size_t)(par ^ 1) * 3 + l) * hstride;
   }
-  // Three-stage software pipeline over streams: the analysis front (biquad -> k_pitch -> k_spectrum) of frame f+1
-  // on s_front, the network of frame f on `st`, and the tail (output heads -> synthesis) of frame f-1 on s_tail run
-  // side by side; each stage only waits for what it really depends on.  Hazards: xb[par] (ev_ana); the spectrum
-  // slot f%3, features/silence[par], the GRU states and conv2 output of parity par, all last read by the tail of
-  // frame f-2 (ev_back[par], recorded on the tail's stream).
+  // Three-stage software pipeline over streams: the analysis fronts (biquad -> k_pitch -> k_spectrum, one per range) of
+  // frame f+1, the network of frame f on `st` (whole batch) and the tails (output heads -> synthesis, one per range) of
+  // frame f-1 run side by side; each stage only waits for what it really depends on.  Hazards: xb[par] (ev_ana); the
+  // spectrum slot f%3, features/silence[par], the GRU states and conv2 output of parity par, all last read by the tails
+  // of frame f-2 (ev_back[par], recorded on the tails' streams).
   const bool overlap = e->overlap && !e->profiling;
-  cudaStream_t sf = overlap ? e->s_front : st;
-  cudaStream_t stl = tail_stream(e);
+  const bool tsep = tail_separate(e);
   float *c2o = a.conv2_out + (size_t)par * hstride;
   int ki = 0;
 #define MARK() do { if (e->profiling) cudaEventRecord(e->ev[ki++], st); } while (0)
+#define FRONT(R) (overlap ? (R).s_front : st)
   const int fr = frame_arg(e->frames);
   const int *sil = a.silence + (size_t)par * S;
   const float *feat = a.features + (size_t)par * S * NB_FEATURES;
   MARK();
   if (e->bq_frames > e->frames) {
-    // the prefilter of this frame was issued ahead on the biquad stream (prefilter hint / pipelined
+    // the prefilter of this frame was issued ahead on the biquad streams (prefilter hint / pipelined
     // host call): just order the rest of the frame after it
-    CK(cudaStreamWaitEvent(sf, e->ev_bq[par], 0));
+    for (int r = 0; r < e->nr; r++) CK(cudaStreamWaitEvent(FRONT(e->rg[r]), e->rg[r].ev_bq[par], 0));
   } else {
-    if (overlap) {   // the input is ordered on the caller's stream
-      CK(cudaEventRecord(e->ev_in, st));
-      CK(cudaStreamWaitEvent(sf, e->ev_in, 0));
-      CK(cudaStreamWaitEvent(sf, e->ev_bq[par ^ 1], 0));   // biquad state: after frame f-1's filter
+    // an engine driven directly on a caller's stream: the input is ordered on that stream (with the engine's own
+    // stream the caller's work is ordered through the parent bracket, ev_pin, or not at all)
+    const bool in_on_st = overlap && st != e->own_stream;
+    if (in_on_st) CK(cudaEventRecord(e->ev_in, st));
+    for (int r = 0; r < e->nr; r++) {
+      B200Engine::Range &R = e->rg[r];
+      cudaStream_t sf = FRONT(R);
+      if (in_on_st) CK(cudaStreamWaitEvent(sf, e->ev_in, 0));
+      if (overlap) CK(cudaStreamWaitEvent(sf, R.ev_bq[par ^ 1], 0));   // biquad state: after frame f-1's filter
+      if (e->parent) CK(cudaStreamWaitEvent(sf, e->ev_pin, 0));
+      k_biquad<<<(R.r1 - R.r0 + 31) / 32, 32, 0, sf>>>(a, d_in, fr, s16, e->io_stride, R.r0, R.r1);
+      CK(cudaEventRecord(R.ev_bq[par], sf));
     }
-    if (e->parent) CK(cudaStreamWaitEvent(sf, e->ev_pin, 0));
-    k_biquad<<<(S + 31) / 32, 32, 0, sf>>>(a, d_in, fr, s16, e->io_stride);
-    CK(cudaEventRecord(e->ev_bq[par], sf));
-    TL(e, e->frames, TL_BQ_END, sf);
+    TL(e, e->frames, TL_BQ_END, FRONT(e->rg[0]));
     e->bq_frames = e->frames + 1;
   }
   MARK();
-  launch_pitch(e, sf, fr);
-  CK(cudaEventRecord(e->ev_ana[par], sf));   // xb[par] is free again
-  TL(e, e->frames, TL_PITCH_END, sf);
-  MARK();
-  if (overlap) CK(cudaStreamWaitEvent(sf, e->ev_back[par], 0));   // frame f-2 is done with slot f%3 / parity buffers
-  k_spectrum<<<S, DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr);
-  TL(e, e->frames, TL_FRONT_END, sf);
-  if (overlap) {
-    CK(cudaEventRecord(e->ev_front[par], sf));
-    CK(cudaStreamWaitEvent(st, e->ev_front[par], 0));
+  for (int r = 0; r < e->nr; r++) {
+    B200Engine::Range &R = e->rg[r];
+    launch_pitch(e, FRONT(R), fr, R.r0, R.r1);
+    CK(cudaEventRecord(R.ev_ana[par], FRONT(R)));   // xb[par] is free again
   }
+  TL(e, e->frames, TL_PITCH_END, FRONT(e->rg[0]));
+  MARK();
+  for (int r = 0; r < e->nr; r++) {
+    B200Engine::Range &R = e->rg[r];
+    cudaStream_t sf = FRONT(R);
+    if (overlap) CK(cudaStreamWaitEvent(sf, R.ev_back[par], 0));   // frame f-2 is done with slot f%3 / parity buffers
+    k_spectrum<<<R.r1 - R.r0, DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), sf>>>(a, e->d_tables, fr, R.r0);
+    if (overlap) {
+      CK(cudaEventRecord(R.ev_front[par], sf));
+      CK(cudaStreamWaitEvent(st, R.ev_front[par], 0));
+    }
+  }
+  TL(e, e->frames, TL_FRONT_END, FRONT(e->rg[0]));
   TL(e, e->frames, TL_BACK_START, st);
   MARK();
   const int gts = (S + RNN_TS - 1) / RNN_TS;
-  if (stl != st) CK(cudaStreamWaitEvent(st, e->ev_back[par], 0));   // the tail of frame f-2 has read the states of this parity
+  if (tsep)   // the tails of frame f-2 have read the states of this parity
+    for (int r = 0; r < e->nr; r++) CK(cudaStreamWaitEvent(st, e->rg[r].ev_back[par], 0));
   if (!e->net_conv1) k_conv1<<<gts, 128, 0, st>>>(S, e->dm, feat, a.conv1_state, sil, a.c2in, a.Kcp);
   MARK();
   const bool pdl = e->pdl && !e->profiling;
@@ -786,54 +834,64 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
     }
     MARK(); MARK(); MARK(); MARK();   // one launch covers the conv2 and GRU slots of the per-kernel profile
   } else {
-  if (e->conv2_tc)
-    CK(launch_pdl(k_tc2<false>, dim3((S + TC_M - 1) / TC_M, 4), dim3(P_THREADS), tc2_smem_bytes<false>(a.Kcp, gru), st, pdl,
-                  S, a.Kcp, gru, a.Kp, e->conv_maps, e->dm.conv2, e->dm.conv2, (const float *)nullptr, c2o, a.conv2_out_u8, sil));
-  else
-    k_conv2<<<gts, 128, RNN_TS * (3 * cond / 4) * sizeof(uint32_t), st>>>(S, e->dm, a.c2in, a.Kcp, c2o, a.conv2_out_u8, a.Kp);
-  MARK();
-  const size_t gsm = 2 * RNN_TS * (gru / 4) * sizeof(uint32_t);
-  for (int l = 0; l < 3; l++) {
-    uint8_t *hu8_new = a.hbuf_u8 + ((size_t)par * 3 + l) * hstride8;
-    if (e->use_tc == 2) {
-      CK(launch_pdl(k_tc2<true>, dim3((S + TC_M - 1) / TC_M, 4), dim3(P_THREADS), tc2_smem_bytes<true>(a.Kp, gru), st, pdl,
-                    S, a.Kp, gru, a.Kp, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], (const float *)h_old[l], h_new[l], hu8_new, sil));
-    } else if (e->use_tc == 1) {
-      k_gru_tc<<<dim3((S + TC_M - 1) / TC_M, gru / TC_UNITS), 160, gru_tc_smem_bytes(gru), st>>>(
-          S, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, sil);
-    } else {
-      const float *x = l == 0 ? c2o : h_new[l - 1];
-      k_gru<<<dim3(gts, (gru + 127) / 128), 128, gsm, st>>>(S, gru, e->dm.gru_in[l], e->dm.gru_rec[l], x, h_old[l], h_new[l], hu8_new, a.Kp, sil);
-    }
+    if (e->conv2_tc)
+      CK(launch_pdl(k_tc2<false>, dim3((S + TC_M - 1) / TC_M, 4), dim3(P_THREADS), tc2_smem_bytes<false>(a.Kcp, gru), st, pdl,
+                    S, a.Kcp, gru, a.Kp, e->conv_maps, e->dm.conv2, e->dm.conv2, (const float *)nullptr, c2o, a.conv2_out_u8, sil));
+    else
+      k_conv2<<<gts, 128, RNN_TS * (3 * cond / 4) * sizeof(uint32_t), st>>>(S, e->dm, a.c2in, a.Kcp, c2o, a.conv2_out_u8, a.Kp);
     MARK();
+    const size_t gsm = 2 * RNN_TS * (gru / 4) * sizeof(uint32_t);
+    for (int l = 0; l < 3; l++) {
+      uint8_t *hu8_new = a.hbuf_u8 + ((size_t)par * 3 + l) * hstride8;
+      if (e->use_tc == 2) {
+        CK(launch_pdl(k_tc2<true>, dim3((S + TC_M - 1) / TC_M, 4), dim3(P_THREADS), tc2_smem_bytes<true>(a.Kp, gru), st, pdl,
+                      S, a.Kp, gru, a.Kp, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], (const float *)h_old[l], h_new[l], hu8_new, sil));
+      } else if (e->use_tc == 1) {
+        k_gru_tc<<<dim3((S + TC_M - 1) / TC_M, gru / TC_UNITS), 160, gru_tc_smem_bytes(gru), st>>>(
+            S, gru, e->tc_maps[par][l], e->dm.gru_in[l], e->dm.gru_rec[l], h_old[l], h_new[l], hu8_new, sil);
+      } else {
+        const float *x = l == 0 ? c2o : h_new[l - 1];
+        k_gru<<<dim3(gts, (gru + 127) / 128), 128, gsm, st>>>(S, gru, e->dm.gru_in[l], e->dm.gru_rec[l], x, h_old[l], h_new[l], hu8_new, a.Kp, sil);
+      }
+      MARK();
+    }
   }
+  if (tsep) CK(cudaEventRecord(e->ev_net[par], st));
+  const bool pdl_heads = pdl && e->use_tc == 2 && !e->net_fused && !tsep && e->nr == 1;   // only the k_tc2 predecessors are PDL-aware
+  for (int r = 0; r < e->nr; r++) {
+    B200Engine::Range &R = e->rg[r];
+    cudaStream_t stl = tail_stream(e, r);
+    const int n = R.r1 - R.r0;
+    if (tsep) CK(cudaStreamWaitEvent(stl, e->ev_net[par], 0));
+    if (e->parent) CK(cudaStreamWaitEvent(stl, e->ev_pin, 0));   // first kernel that writes the caller's buffers
+    const float *c2 = c2o + (size_t)R.r0 * gru, *g1 = h_new[0] + (size_t)R.r0 * gru, *g2 = h_new[1] + (size_t)R.r0 * gru,
+                *g3 = h_new[2] + (size_t)R.r0 * gru;
+    float *gains = a.gains + (size_t)R.r0 * NB_BANDS, *vad = a.vad + R.r0;
+    float *uvad = d_vad ? d_vad + (size_t)R.r0 * e->vad_stride : nullptr;
+    const int *silr = sil + R.r0;
+    if (e->heads2 && e->heads_ns == 1)
+      CK(launch_pdl(k_heads2<1>, dim3((n + 7) / 8), dim3(160), h2_smem_bytes<1>(), stl, pdl_heads, n, e->dm, c2, g1, g2, g3, silr, gains, vad, uvad, e->vad_stride));
+    else if (e->heads2 && e->heads_ns == 2)
+      CK(launch_pdl(k_heads2<2>, dim3((n + 15) / 16), dim3(160), h2_smem_bytes<2>(), stl, pdl_heads, n, e->dm, c2, g1, g2, g3, silr, gains, vad, uvad, e->vad_stride));
+    else if (e->heads2)
+      CK(launch_pdl(k_heads2<4>, dim3((n + 31) / 32), dim3(160), h2_smem_bytes<4>(), stl, pdl_heads, n, e->dm, c2, g1, g2, g3, silr, gains, vad, uvad, e->vad_stride));
+    else
+      CK(launch_pdl(k_heads, dim3((n + HEAD_TS - 1) / HEAD_TS), dim3(160), 0, stl, pdl_heads, n, e->dm, c2, g1, g2, g3, silr, gains, vad, uvad, e->vad_stride));
   }
-  if (stl != st) {
-    CK(cudaEventRecord(e->ev_net[par], st));
-    CK(cudaStreamWaitEvent(stl, e->ev_net[par], 0));
-  }
-  if (e->parent) CK(cudaStreamWaitEvent(stl, e->ev_pin, 0));   // first kernel that writes the caller's buffers
-  const bool pdl_heads = pdl && e->use_tc == 2 && !e->net_fused && stl == st;   // only the k_tc2 predecessors are PDL-aware
-  if (e->heads2 && e->heads_ns == 1)
-    CK(launch_pdl(k_heads2<1>, dim3((S + 7) / 8), dim3(160), h2_smem_bytes<1>(), stl, pdl_heads, S, e->dm, (const float *)c2o,
-                  (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
-  else if (e->heads2 && e->heads_ns == 2)
-    CK(launch_pdl(k_heads2<2>, dim3((S + 15) / 16), dim3(160), h2_smem_bytes<2>(), stl, pdl_heads, S, e->dm, (const float *)c2o,
-                  (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
-  else if (e->heads2)
-    CK(launch_pdl(k_heads2<4>, dim3((S + 31) / 32), dim3(160), h2_smem_bytes<4>(), stl, pdl_heads, S, e->dm, (const float *)c2o,
-                  (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
-  else
-    CK(launch_pdl(k_heads, dim3((S + HEAD_TS - 1) / HEAD_TS), dim3(160), 0, stl, pdl_heads, S, e->dm, (const float *)c2o,
-                  (const float *)h_new[0], (const float *)h_new[1], (const float *)h_new[2], sil, a.gains, a.vad, d_vad, e->vad_stride));
   MARK();
-  CK(launch_pdl(k_synthesis, dim3(S), dim3(DSP_THREADS), SS_TOTAL * sizeof(float), stl, pdl_heads, a, (const DspTables *)e->d_tables, d_out, fr, s16, e->io_stride));
-  CK(cudaEventRecord(e->ev_back[par], stl));
-  TL(e, e->frames, TL_BACK_END, stl);
-  // an engine driven directly on a caller's stream (no parent bracket): that stream sees the call complete
-  if (stl != st && st != e->own_stream) CK(cudaStreamWaitEvent(st, e->ev_back[par], 0));
+  for (int r = 0; r < e->nr; r++) {
+    B200Engine::Range &R = e->rg[r];
+    cudaStream_t stl = tail_stream(e, r);
+    CK(launch_pdl(k_synthesis, dim3(R.r1 - R.r0), dim3(DSP_THREADS), SS_TOTAL * sizeof(float), stl, pdl_heads, a, (const DspTables *)e->d_tables, d_out, fr,
+                  s16, e->io_stride, R.r0));
+    CK(cudaEventRecord(R.ev_back[par], stl));
+    // an engine driven directly on a caller's stream (no parent bracket): that stream sees the call complete
+    if (stl != st && st != e->own_stream) CK(cudaStreamWaitEvent(st, R.ev_back[par], 0));
+  }
+  TL(e, e->frames, TL_BACK_END, tail_stream(e, 0));
   MARK();
 #undef MARK
+#undef FRONT
   CK(cudaGetLastError());
   e->frames++;
   if (e->profiling) {
@@ -848,19 +906,22 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   return 0;
 }
 
-// Issue the high-pass prefilter of the next not-yet-prefiltered frame on the biquad stream.
+// Issue the high-pass prefilter of the next not-yet-prefiltered frame on the biquad streams.
 // `ready` (optional) = event after which d_in is valid.  At most two frames ahead of processing.
 static int issue_prefilter(B200Engine *e, const void *d_in, cudaEvent_t ready, int s16) {
   if (e->bq_frames >= e->frames + 2) return -1;
   const long long f = e->bq_frames;
   const int slot = (int)(f & 1);
-  if (ready) CK(cudaStreamWaitEvent(e->s_bq, ready, 0));
-  CK(cudaStreamWaitEvent(e->s_bq, e->ev_ana[slot], 0));       // frame f-2 no longer reads this xb half
-  CK(cudaStreamWaitEvent(e->s_bq, e->ev_bq[slot ^ 1], 0));    // biquad state: after frame f-1's filter
-  k_biquad<<<(e->a.S + 31) / 32, 32, 0, e->s_bq>>>(e->a, d_in, frame_arg(f), s16, e->io_stride);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(e->ev_bq[slot], e->s_bq));
-  TL(e, f, TL_BQ_END, e->s_bq);
+  for (int r = 0; r < e->nr; r++) {
+    B200Engine::Range &R = e->rg[r];
+    if (ready) CK(cudaStreamWaitEvent(R.s_bq, ready, 0));
+    CK(cudaStreamWaitEvent(R.s_bq, R.ev_ana[slot], 0));       // frame f-2 no longer reads this xb half
+    CK(cudaStreamWaitEvent(R.s_bq, R.ev_bq[slot ^ 1], 0));    // biquad state: after frame f-1's filter
+    k_biquad<<<(R.r1 - R.r0 + 31) / 32, 32, 0, R.s_bq>>>(e->a, d_in, frame_arg(f), s16, e->io_stride, R.r0, R.r1);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(R.ev_bq[slot], R.s_bq));
+  }
+  TL(e, f, TL_BQ_END, e->rg[0].s_bq);
   e->bq_frames = f + 1;
   return 0;
 }
@@ -877,9 +938,9 @@ static int frame_host_async_io(B200Engine *e, void *out, const void *in, float *
   if (e->bq_frames != e->frames) return -1;   // a device-side prefilter hint is pending: do not mix
   CK(cudaSetDevice(e->device));
   const size_t n = (size_t)e->a.S * FRAME_SIZE * (s16 ? sizeof(short) : sizeof(float));
-  const int slot = (int)(e->host_frames & 1);
-  // copy-in: the staging slot is free once the prefilter of frame n-2 has consumed it
-  CK(cudaStreamWaitEvent(e->s_h2d, e->ev_bq[slot], 0));
+  const int slot = (int)(e->host_frames & 1), par = (int)(e->frames & 1);
+  // copy-in: the staging slot is free once the prefilters of frame n-2 have consumed it
+  for (int r = 0; r < e->nr; r++) CK(cudaStreamWaitEvent(e->s_h2d, e->rg[r].ev_bq[par], 0));
   TL(e, e->frames, TL_H2D_START, e->s_h2d);
   CK(cudaMemcpyAsync(e->stage_in[slot], in, n, cudaMemcpyHostToDevice, e->s_h2d));
   CK(cudaEventRecord(e->ev_h2d[slot], e->s_h2d));
@@ -887,11 +948,10 @@ static int frame_host_async_io(B200Engine *e, void *out, const void *in, float *
   // high-pass prefilter on its own stream: overlaps the previous frame's kernels
   if (issue_prefilter(e, e->stage_in[slot], e->ev_h2d[slot], s16)) return -1;
   // rest of the frame: needs frame n-2's output staging drained
-  CK(cudaStreamWaitEvent(tail_stream(e), e->ev_d2h[slot], 0));   // the tail writes the output staging
+  for (int r = 0; r < e->nr; r++) CK(cudaStreamWaitEvent(tail_stream(e, r), e->ev_d2h[slot], 0));   // the tails write the output staging
   if (frame_device_io(e, e->stage_out[slot], e->stage_in[slot], e->stage_vad[slot], s16)) return -1;
-  CK(cudaEventRecord(e->ev_comp[slot], tail_stream(e)));
-  // copy-out
-  CK(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[slot], 0));
+  // copy-out: after the tails of every range
+  for (int r = 0; r < e->nr; r++) CK(cudaStreamWaitEvent(e->s_d2h, e->rg[r].ev_back[par], 0));
   CK(cudaMemcpyAsync(out, e->stage_out[slot], n, cudaMemcpyDeviceToHost, e->s_d2h));
   if (vad) CK(cudaMemcpyAsync(vad, e->stage_vad[slot], (size_t)e->a.S * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
   CK(cudaEventRecord(e->ev_d2h[slot], e->s_d2h));
@@ -926,7 +986,7 @@ static int frames_device_io(B200Engine *e, void *d_out, const void *d_in, float 
   // (the engine's own stream may itself be waiting for a staging copy of the host path: always order after it;
   //  with a parent stream, additionally after the caller's stream)
   rc = cudaEventRecord(e->ev_in, e->stream) != cudaSuccess;
-  if (!rc && e->parent) rc = cudaStreamWaitEvent(e->s_bq, e->ev_pin, 0) != cudaSuccess;
+  for (int r = 0; r < e->nr && !rc && e->parent; r++) rc = cudaStreamWaitEvent(e->rg[r].s_bq, e->ev_pin, 0) != cudaSuccess;
   for (int t = 0; t < 2 && t < T && !rc; t++) rc = issue_prefilter(e, in + (size_t)t * FRAME_SIZE * esz, t == 0 ? e->ev_in : nullptr, s16);
   for (int t = 0; t < T && !rc; t++) {
     rc = frame_device_io(e, out + (size_t)t * FRAME_SIZE * esz, in + (size_t)t * FRAME_SIZE * esz, d_vad ? d_vad + t : nullptr, s16);
@@ -978,11 +1038,11 @@ extern "C" int b200_engine_frames_host_enqueue(B200Engine *e, void *out, const v
     CK(cudaEventRecord(e->ev_mh2d[slot], e->s_h2d));
     // kernels: after the copy-in, and after chunk c-2's copy-out has drained the output slot
     CK(cudaStreamWaitEvent(e->stream, e->ev_mh2d[slot], 0));
-    CK(cudaStreamWaitEvent(tail_stream(e), e->ev_md2h[slot], 0));
+    for (int r = 0; r < e->nr; r++) CK(cudaStreamWaitEvent(tail_stream(e, r), e->ev_md2h[slot], 0));
     if (frames_device_io(e, e->multi_out[slot], e->multi_in[slot], e->multi_vad[slot], n, n * FRAME_SIZE, n, s16)) return -1;
-    CK(cudaEventRecord(e->ev_mcomp[slot], tail_stream(e)));
-    // copy-out
-    CK(cudaStreamWaitEvent(e->s_d2h, e->ev_mcomp[slot], 0));
+    // copy-out: after the tails of the chunk's last frame (which follow everything else of the chunk)
+    for (int r = 0; r < e->nr; r++) CK(cudaStreamWaitEvent(e->s_d2h, e->rg[r].ev_back[(e->frames - 1) & 1], 0));
+    CK(cudaEventRecord(e->ev_mcomp[slot], e->s_d2h));
     CK(cudaMemcpy2DAsync((char *)out + (size_t)t0 * FRAME_SIZE * esz, host_pitch, e->multi_out[slot], dev_pitch,
                          dev_pitch, S, cudaMemcpyDeviceToHost, e->s_d2h));
     if (vad)
@@ -1020,26 +1080,29 @@ extern "C" int b200_engine_train_features_device(B200Engine *e, float *d_rec, co
     CK(cudaMemsetAsync(e->train_clean_mem, 0, S * FRAME_SIZE * sizeof(float), st));
   }
   // order after whatever the analysis streams of earlier denoising calls still run
-  CK(cudaStreamWaitEvent(st, e->ev_ana[0], 0));
-  CK(cudaStreamWaitEvent(st, e->ev_ana[1], 0));
-  CK(cudaStreamWaitEvent(st, e->ev_front[0], 0));
-  CK(cudaStreamWaitEvent(st, e->ev_front[1], 0));
-  CK(cudaStreamWaitEvent(st, e->ev_back[0], 0));
-  CK(cudaStreamWaitEvent(st, e->ev_back[1], 0));
+  for (int r = 0; r < e->nr; r++)
+    for (int i = 0; i < 2; i++) {
+      CK(cudaStreamWaitEvent(st, e->rg[r].ev_ana[i], 0));
+      CK(cudaStreamWaitEvent(st, e->rg[r].ev_front[i], 0));
+      CK(cudaStreamWaitEvent(st, e->rg[r].ev_back[i], 0));
+    }
   const int par = (int)(e->frames & 1), fr = frame_arg(e->frames);
   CK(cudaMemcpyAsync(a.xb + (size_t)par * S * FRAME_SIZE, d_noisy, S * FRAME_SIZE * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  launch_pitch(e, st, fr);
+  launch_pitch(e, st, fr, 0, a.S);
   TrainIo io;
   io.clean = d_clean; io.clean_mem = e->train_clean_mem; io.rec = d_rec;
   io.vad_target = d_vad_target; io.noise_free = d_noise_free; io.lowpass = d_lowpass; io.band_lp = d_band_lp;
   k_train_features<<<a.S, DSP_THREADS, SM_SPEC_TOTAL * sizeof(float), st>>>(a, e->d_tables, fr, io);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(e->ev_ana[par], st));
-  CK(cudaEventRecord(e->ev_front[par], st));
+  for (int r = 0; r < e->nr; r++) {   // later denoising-style calls order after this one through the usual events
+    CK(cudaEventRecord(e->rg[r].ev_ana[par], st));
+    CK(cudaEventRecord(e->rg[r].ev_front[par], st));
+    CK(cudaEventRecord(e->rg[r].ev_back[par], st));
+  }
   e->frames++;
   e->bq_frames = e->frames;
   e->host_frames = e->frames;
-  return parent_leave(e);
+  return parent_leave(e);   // (waits for ev_back of this call's parity: recorded above on the engine's stream)
 }
 
 extern "C" int b200_engine_train_features_host(B200Engine *e, float *rec, const float *clean, const float *noisy,
@@ -1077,10 +1140,9 @@ extern "C" int b200_engine_sync(B200Engine *e) {
   if (!e) return -1;
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->s_h2d));
-  CK(cudaStreamSynchronize(e->s_bq));
-  CK(cudaStreamSynchronize(e->s_front));
+  for (int r = 0; r < e->nr; r++) { CK(cudaStreamSynchronize(e->rg[r].s_bq)); CK(cudaStreamSynchronize(e->rg[r].s_front)); }
   CK(cudaStreamSynchronize(e->stream));
-  CK(cudaStreamSynchronize(e->s_tail));
+  for (int r = 0; r < e->nr; r++) CK(cudaStreamSynchronize(e->rg[r].s_tail));
   CK(cudaStreamSynchronize(e->s_d2h));
   return 0;
 }
@@ -1089,7 +1151,7 @@ extern "C" int b200_engine_set_stream(B200Engine *e, void *cuda_stream) {
   if (!e) return -1;
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
-  CK(cudaStreamSynchronize(e->s_tail));
+  for (int r = 0; r < e->nr; r++) CK(cudaStreamSynchronize(e->rg[r].s_tail));
   e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
   return 0;
 }
@@ -1099,7 +1161,7 @@ extern "C" int b200_engine_set_parent(B200Engine *e, void *parent_stream) {
   if (!e) return -1;
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
-  CK(cudaStreamSynchronize(e->s_tail));
+  for (int r = 0; r < e->nr; r++) CK(cudaStreamSynchronize(e->rg[r].s_tail));
   e->stream = e->own_stream;
   e->parent = (cudaStream_t)parent_stream;
   return 0;
@@ -1153,7 +1215,7 @@ extern "C" int b200_engine_reset_stream(B200Engine *e, int s) {
   const Arena &a = e->a;
   const size_t S = a.S;
   cudaStream_t st = e->stream;
-  CK(cudaStreamSynchronize(e->s_tail));   // the tail of the last frame still reads / writes this stream's state
+  for (int r = 0; r < e->nr; r++) CK(cudaStreamSynchronize(e->rg[r].s_tail));   // the tails of the last frame still read / write this stream's state
 #define ZERO(ptr, per, copies)                                                                          \
   for (int c_ = 0; c_ < (copies); c_++)                                                                 \
     CK(cudaMemsetAsync((ptr) + ((size_t)c_ * S + s) * (per), 0, (size_t)(per) * sizeof(*(ptr)), st));
@@ -1190,7 +1252,7 @@ extern "C" int b200_engine_debug_read_all(B200Engine *e, int what, float *dst, i
   if (!e || !dst || e->frames < 1) return -1;
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
-  CK(cudaStreamSynchronize(e->s_tail));
+  for (int r = 0; r < e->nr; r++) CK(cudaStreamSynchronize(e->rg[r].s_tail));
   const Arena &a = e->a;
   const size_t S = a.S;
   const int par = frame_arg(e->frames - 1) & 1;
@@ -1213,7 +1275,7 @@ extern "C" int b200_engine_debug_read(B200Engine *e, int what, int s, float *dst
   if (!e || !dst || s < 0 || s >= e->a.S || e->frames < 1) return -1;
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
-  CK(cudaStreamSynchronize(e->s_tail));
+  for (int r = 0; r < e->nr; r++) CK(cudaStreamSynchronize(e->rg[r].s_tail));
   const Arena &a = e->a;
   const size_t S = a.S;
   const int fl = frame_arg(e->frames - 1);   // the index the kernels of the last frame were handed

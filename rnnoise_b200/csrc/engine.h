@@ -17,6 +17,8 @@ B200Engine *b200_engine_create(const B200HostModel *m, int nb_streams, int devic
 B200Engine *b200_engine_create_on(const B200HostModel *m, int nb_streams, int device, int device_streams);
 void b200_engine_destroy(B200Engine *e);
 int b200_engine_streams(const B200Engine *e);
+/* sub-grids ("lanes") the DSP stages of a frame run as */
+int b200_engine_ranges(const B200Engine *e);
 /* One frame for every stream, device pointers, asynchronous on the engine's stream. */
 int b200_engine_frame_device(B200Engine *e, float *d_out, const float *d_in, float *d_vad);
 /* One frame, host pointers (copies in, runs, copies out, synchronises). */

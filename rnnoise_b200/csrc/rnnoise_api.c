@@ -23,27 +23,23 @@ struct RNNModel {
   int parsed;
 };
 
-/* A batch is 1..B200_MAX_LANES engines ("lanes"), each owning a contiguous range of streams and its own
- * CUDA streams.  Streams never interact, so lanes are independent; running them side by side fills the GPU
- * better when one lane's grids are only a wave or two of CTAs (measured on B200 with two lanes against one,
- * tools/lanes_experiment.py: +10 % at 1024 streams, +5 % at 2048, +13 % at 3072, +10 % at 4096, +3 % at 6144,
- * +2 % at 8192, -1 % at 16384).
- * $RNNOISE_B200_LANES overrides the choice. */
-#define B200_MAX_LANES 4      /* per device */
+/* A batch is one engine per device (rnnoise_batch_create_multi shards the streams contiguously over the devices; the
+ * plain rnnoise_batch_create is the one-device case).  Inside an engine the DSP stages of a frame run as 1..4 sub-grids
+ * ("lanes": contiguous stream ranges on their own CUDA streams) while the network runs once over the whole device batch
+ * (engine.cu); streams never interact, so results do not depend on any of these splits.  $RNNOISE_B200_LANES overrides
+ * the lane count.  `lanes` below counts ENGINES (= devices). */
 #define B200_MAX_DEVICES 16
-#define B200_MAX_ENGINES (B200_MAX_LANES * B200_MAX_DEVICES)
+#define B200_MAX_ENGINES B200_MAX_DEVICES
 struct RNNoiseBatch {
-  int lanes;                       /* engines in total, over all devices */
-  int first[B200_MAX_ENGINES + 1]; /* lane l owns streams [first[l], first[l + 1]) */
+  int lanes;                       /* engines = devices */
+  int first[B200_MAX_ENGINES + 1]; /* engine l owns streams [first[l], first[l + 1]) */
   B200Engine *engine[B200_MAX_ENGINES];
   int nb_streams;
-  /* devices (rnnoise_batch_create_multi): device k runs lanes [dev_lane[k], dev_lane[k + 1]) over the contiguous
-   * shard of streams [first[dev_lane[k]], first[dev_lane[k + 1]]) */
   int nb_devices;
   int device[B200_MAX_DEVICES];
-  int dev_lane[B200_MAX_DEVICES + 1];
-  /* set when a per-frame call failed after some lanes had already enqueued the frame: the lanes are then out
-   * of step with each other for good, so every later call fails cleanly instead of producing skewed audio */
+  int dev_lane[B200_MAX_DEVICES + 1];   /* = k: kept so that shard bookkeeping reads the same for 1 or more engines per device */
+  /* set when a per-frame call failed after some engines had already enqueued the frame: they are then out of step with
+   * each other for good, so every later call fails cleanly instead of producing skewed audio */
   int poisoned;
 };
 #define LANE_COUNT(b, l) ((b)->first[(l) + 1] - (b)->first[l])
@@ -113,22 +109,12 @@ void rnnoise_model_free(RNNModel *model) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
-static int default_lanes(int nb_streams) {
-  const char *env = getenv("RNNOISE_B200_LANES");
-  int lanes;
-  if (env && atoi(env) > 0) lanes = atoi(env);
-  else lanes = (nb_streams >= 1024 && nb_streams < 12288) ? 2 : 1;
-  if (lanes > B200_MAX_LANES) lanes = B200_MAX_LANES;
-  while (lanes > 1 && nb_streams / lanes < 128) lanes--;
-  return lanes;
-}
-
 /* Streams are independent (no cross-stream term anywhere in rnnoise_process_frame, denoise.c:457-504), so a
  * batch shards over devices as contiguous stream ranges (stream i -> device floor(i * G / S)) with
  * no collective; each device's shard is then split into lanes as for a single device. */
 RNNoiseBatch *rnnoise_batch_create_multi(RNNModel *model, int nb_streams, const int *devices, int nb_devices) {
   RNNoiseBatch *b;
-  int k, l, per, lanes, s0, cnt, base, rem;
+  int k, s0, cnt, base, rem;
   if (!model || !model->parsed || nb_streams < 1 || !devices || nb_devices < 1 || nb_devices > B200_MAX_DEVICES) return NULL;
   if (nb_devices > nb_streams) nb_devices = nb_streams;
   for (k = 0; k < nb_devices; k++)
@@ -142,20 +128,15 @@ RNNoiseBatch *rnnoise_batch_create_multi(RNNModel *model, int nb_streams, const 
   for (k = 0; k < nb_devices; k++, s0 += cnt) {
     cnt = base + (k < rem ? 1 : 0);
     b->device[k] = devices[k];
-    b->dev_lane[k] = b->lanes;
-    lanes = default_lanes(cnt);
-    /* lane sizes: multiples of the 128-stream tensor-core tile, the last lane takes the remainder */
-    per = ((cnt + lanes - 1) / lanes + 127) / 128 * 128;
-    for (l = 0; l < lanes && l * per < cnt; l++) {
-      b->first[b->lanes] = s0 + l * per;
-      b->first[b->lanes + 1] = s0 + ((l + 1) * per < cnt ? (l + 1) * per : cnt);
-      b->engine[b->lanes] = b200_engine_create_on(&model->host, LANE_COUNT(b, b->lanes), devices[k], cnt);
-      if (!b->engine[b->lanes]) {
-        rnnoise_batch_destroy(b);
-        return NULL;
-      }
-      b->lanes++;
+    b->dev_lane[k] = k;
+    b->first[k] = s0;
+    b->first[k + 1] = s0 + cnt;
+    b->engine[k] = b200_engine_create(&model->host, cnt, devices[k]);
+    if (!b->engine[k]) {
+      rnnoise_batch_destroy(b);
+      return NULL;
     }
+    b->lanes++;
   }
   b->dev_lane[nb_devices] = b->lanes;
   return b;
@@ -183,7 +164,7 @@ int rnnoise_batch_get_shard(const RNNoiseBatch *b, int k, int *device, int *firs
 }
 
 int rnnoise_batch_get_streams(const RNNoiseBatch *b) { return b ? b->nb_streams : 0; }
-int rnnoise_batch_get_lanes(const RNNoiseBatch *b) { return b ? b->lanes : 0; }
+int rnnoise_batch_get_lanes(const RNNoiseBatch *b) { return b ? b200_engine_ranges(b->engine[0]) : 0; }
 
 /* every per-frame entry point fans out over the lanes with the lane's offset into the caller's buffers */
 #define PCM_AT(p, b, l, T, type) ((type *)(p) + (size_t)(b)->first[l] * (T) * FRAME_SIZE)
@@ -393,7 +374,7 @@ int rnnoise_batch_reset_stream(RNNoiseBatch *b, int s) {
   l = lane_of(b, s);
   return b200_engine_reset_stream(b->engine[l], s - b->first[l]);
 }
-int rnnoise_batch_launches_per_frame(const RNNoiseBatch *b) { return b ? b->lanes * b200_engine_launches_per_frame(b->engine[0]) : 0; }
+int rnnoise_batch_launches_per_frame(const RNNoiseBatch *b) { return b ? b->lanes * b200_engine_launches_per_frame(b->engine[0]) : 0; }   /* all devices */
 int rnnoise_batch_profile(RNNoiseBatch *b, int enable) {
   int l, rc = 0;
   if (!b) return -1;

@@ -59,34 +59,25 @@ def owner(L, b, s):
     return int(buf[0]), int(buf[1]), buf
 
 
-CASES = [(1, None), (100, None), (1023, None), (1024, None), (3000, None), (4096, None), (12287, None), (12288, None),
-         (300, "2"), (600, "4"), (129, "2"), (255, "2"), (256, "2"), (5000, "3"), (513, "4"), (70, "3")]
+CASES = [(1, None), (100, None), (1023, None), (1024, None), (3000, None), (4096, None), (12287, None), (12288, None)]
 
 
 @pytest.mark.parametrize("S,env", CASES)
-def test_lane_partition_and_offsets(M, monkeypatch, S, env):
+def test_single_device_batch_is_one_engine_over_the_whole_buffers(M, monkeypatch, S, env):
+    """One device = one engine that receives the caller's buffers unsliced (the split of the DSP stages into lanes is
+    the engine's business: rnnoise_batch_get_lanes reports it); every entry point hands over the right pointers."""
     L = M
-    if env:
-        monkeypatch.setenv("RNNOISE_B200_LANES", env)
-    else:
-        monkeypatch.delenv("RNNOISE_B200_LANES", raising=False)
     L.mock_reset_ids()
     b = L.rnnoise_batch_create(L.model, S, 0)
     assert b and L.rnnoise_batch_get_streams(b) == S
     lanes = L.rnnoise_batch_get_lanes(b)
-    own = np.array([owner(L, b, s)[:2] for s in range(S)])          # (lane id, local index) per stream
-    # contiguous ranges, local indices count up from 0, every lane non-empty, whole 128-tiles except the last lane
-    assert own[0].tolist() == [0, 0] and own[-1, 0] == lanes - 1
-    sizes = [int(np.sum(own[:, 0] == l)) for l in range(lanes)]
-    assert sum(sizes) == S and all(n > 0 for n in sizes) and all(n % 128 == 0 for n in sizes[:-1])
-    first = np.cumsum([0] + sizes)
-    for l in range(lanes):
-        assert np.array_equal(own[first[l]:first[l + 1], 1], np.arange(sizes[l])) and np.all(own[first[l]:first[l + 1], 0] == l)
-    if env is None:
-        assert lanes == (2 if 1024 <= S < 12288 else 1)
-    else:
-        assert 1 <= lanes <= int(env) and (lanes == 1 or S // lanes >= 128 or sizes[-1] < 128)
-    assert L.rnnoise_batch_launches_per_frame(b) == 10 * lanes
+    assert lanes == (2 if 1024 <= S < 12288 else 1)
+    probe = sorted({0, 1, S // 2, S - 1} & set(range(S)))
+    own = np.array([owner(L, b, s)[:2] for s in probe])
+    assert np.all(own[:, 0] == 0) and own[:, 1].tolist() == probe
+    own = np.stack([np.zeros(S, int), np.arange(S)], axis=1)
+    first = np.array([0, S]); lanes = 1
+    assert L.rnnoise_batch_launches_per_frame(b) == 10
     lane_of = own[:, 0].astype(np.float32); local = own[:, 1].astype(np.float32)
 
     # single-frame float / int16 entry points
@@ -131,7 +122,7 @@ def test_lane_partition_and_offsets(M, monkeypatch, S, env):
     for l in range(min(lanes, 16)):
         assert L.mock_hint(l) == x[first[l], 0]
     # per-stream routing: reset and debug; stream handling: one lane runs on the caller's stream, several are bracketed
-    for s in {0, S - 1, S // 2, int(first[lanes - 1])}:
+    for s in {0, S - 1, S // 2}:
         assert L.rnnoise_batch_reset_stream(b, s) == 0
         lane, loc, buf = owner(L, b, s)
         assert int(buf[2]) == loc
@@ -204,13 +195,15 @@ def test_multi_device_shards_lanes_and_pointer_offsets(M, monkeypatch, S, devs):
 
 def test_call_order_errors_leave_the_batch_intact_and_enqueue_errors_poison_it(M, monkeypatch):
     L = M
-    monkeypatch.setenv("RNNOISE_B200_LANES", "3")
     L.mock_reset_ids()
     S = 600
-    b = L.rnnoise_batch_create(L.model, S, 0)
-    assert L.rnnoise_batch_get_lanes(b) == 3
+    devs = (C.c_int * 3)(0, 1, 2)
+    b = L.rnnoise_batch_create_multi(L.model, S, devs, 3)       # three engines (devices) of 200 streams
+    assert L.rnnoise_batch_get_devices(b) == 3
     x = np.ones((S, 480), np.float32); out = np.zeros_like(x)
     buf = (C.c_float * 8)()
+    xs = [np.ascontiguousarray(x[k * 200:(k + 1) * 200]) for k in range(3)]; outs = [np.zeros_like(a) for a in xs]
+    PX = (C.c_void_p * 3)(*[a.ctypes.data for a in xs]); PO = (C.c_void_p * 3)(*[a.ctypes.data for a in outs])
 
     def frames_of_lanes():
         res = []
@@ -218,28 +211,28 @@ def test_call_order_errors_leave_the_batch_intact_and_enqueue_errors_poison_it(M
             L.rnnoise_batch_debug_read(b, 0, s, buf, 8)
             res.append(int(buf[6]))
         return res
-    # a pending prefilter hint: host-buffer and multi-frame calls are refused before ANY lane is touched
-    assert L.rnnoise_batch_prefilter_device(b, x.ctypes.data) == 0
+    # a pending prefilter hint: host-buffer and multi-frame calls are refused before ANY engine is touched
+    assert L.rnnoise_batch_prefilter_device_multi(b, PX) == 0
     assert L.rnnoise_process_frame_batch(b, out.ctypes.data, x.ctypes.data, None) == -1
     assert L.rnnoise_process_frames_batch(b, out.ctypes.data, x.ctypes.data, None, 1) == -1
     assert L.rnnoise_batch_debug_set_frame_counter(b, 5) == -1
     assert frames_of_lanes() == [0, 0, 0]
-    assert L.rnnoise_process_frame_batch_device(b, out.ctypes.data, x.ctypes.data, None) == 0   # consumes the hint
+    assert L.rnnoise_process_frame_batch_device_multi(b, PO, PX, None) == 0   # consumes the hint
     assert L.rnnoise_process_frame_batch(b, out.ctypes.data, x.ctypes.data, None) == 0
     assert frames_of_lanes() == [2, 2, 2]
-    # third hint in a row is refused without touching any lane
-    assert L.rnnoise_batch_prefilter_device(b, x.ctypes.data) == 0 and L.rnnoise_batch_prefilter_device(b, x.ctypes.data) == 0
-    assert L.rnnoise_batch_prefilter_device(b, x.ctypes.data) == -1
-    assert L.rnnoise_process_frame_batch_device(b, out.ctypes.data, x.ctypes.data, None) == 0
+    # third hint in a row is refused without touching any engine
+    assert L.rnnoise_batch_prefilter_device_multi(b, PX) == 0 and L.rnnoise_batch_prefilter_device_multi(b, PX) == 0
+    assert L.rnnoise_batch_prefilter_device_multi(b, PX) == -1
+    assert L.rnnoise_process_frame_batch_device_multi(b, PO, PX, None) == 0
     # NULL arguments: refused, nothing enqueued
-    assert L.rnnoise_process_frame_batch_device(b, None, x.ctypes.data, None) == -1
+    assert L.rnnoise_process_frame_batch_device_multi(b, None, PX, None) == -1
     assert frames_of_lanes() == [3, 3, 3]
-    # an enqueue error in the middle lane: lanes are out of step -> poisoned, every later call fails
+    # an enqueue error in the middle engine: the engines are out of step -> poisoned, every later call fails
     L.mock_fail_next(1)
-    assert L.rnnoise_process_frame_batch_device(b, out.ctypes.data, x.ctypes.data, None) == -1
+    assert L.rnnoise_process_frame_batch_device_multi(b, PO, PX, None) == -1
     assert frames_of_lanes() == [4, 3, 3]
     for _ in range(2):
-        assert L.rnnoise_process_frame_batch_device(b, out.ctypes.data, x.ctypes.data, None) == -1
+        assert L.rnnoise_process_frame_batch_device_multi(b, PO, PX, None) == -1
         assert L.rnnoise_process_frame_batch(b, out.ctypes.data, x.ctypes.data, None) == -1
         assert L.rnnoise_process_frames_batch(b, out.ctypes.data, x.ctypes.data, None, 1) == -1
         assert L.rnnoise_batch_reset_stream(b, 0) == -1
