@@ -15,7 +15,7 @@ tscale = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nse
 acc = collections.OrderedDict()
 for r in rows[2:]:
     name = r[ki].split("(")[0].replace("void ", "")
-    key = {"k_tc2<1>": "k_gru", "k_tc2<0>": "k_conv2", "k_heads2": "k_heads"}.get(name, name)
+    key = {"k_tc2<1>": "k_gru", "k_tc2<0>": "k_conv2"}.get(name, "k_heads" if name.startswith("k_heads2") else name)
     b = float(r[ri].replace(",", "")) * scale[U[ri]] + float(r[wi].replace(",", "")) * scale[U[wi]]
     acc.setdefault(key, []).append((b, float(r[di].replace(",", "")) * tscale[U[di]]))
 out = {"lanes": int(sys.argv[2])}
