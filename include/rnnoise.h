@@ -114,10 +114,10 @@ RNNOISE_EXPORT void rnnoise_batch_destroy(RNNoiseBatch *b);
  * poisoned, every later per-frame call returns -1, and the only valid operation is rnnoise_batch_destroy(). */
 
 RNNOISE_EXPORT int rnnoise_batch_get_streams(const RNNoiseBatch *b);
-/** A batch is internally split into 1..4 "lanes" (contiguous stream ranges, each with its own CUDA streams)
- *  that run side by side; streams are independent, so results do not depend on the split.  The default
- *  (two lanes from 1024 up to 12287 streams, else one; measured on B200) can be overridden with
- *  $RNNOISE_B200_LANES at creation time.  Returns the number of lanes. */
+/** Inside a device batch the DSP stages of a frame (analysis front, output tail) run as 1..4 "lanes" -- sub-grids over
+ *  contiguous stream ranges on their own CUDA streams -- while the network runs once over the whole batch; streams are
+ *  independent, so results do not depend on the split.  The default (two lanes from 1024 up to 32767 streams, else one;
+ *  measured on B200) can be overridden with $RNNOISE_B200_LANES at creation time.  Returns the number of lanes. */
 RNNOISE_EXPORT int rnnoise_batch_get_lanes(const RNNoiseBatch *b);
 
 /** Host-buffer call: in/out are [nb_streams][480] floats in host memory (pinned memory makes the

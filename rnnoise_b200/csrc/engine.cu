@@ -533,12 +533,12 @@ extern "C" B200Engine *b200_engine_create_on(const B200HostModel *m, int S, int 
   // kernels could use: 10.05 M frames/s without vs 9.0-9.3 M with PDL -> opt-in only
   { const char *pd = getenv("RNNOISE_B200_PDL"); e->pdl = pd && !strcmp(pd, "1"); }
   {
-    // Ranges of the DSP stages (measured on B200 with whole sub-batches, tools/lanes_experiment.py: two against one
-    // +10 % at 1024 streams, +5 % at 2048, +13 % at 3072, +10 % at 4096, +3 % at 6144, +2 % at 8192, -1 % at 16384; four
-    // are slower than two at 4096): two from 1024 to 12287 streams, else one; whole 128-stream tiles except the last.
-    // $RNNOISE_B200_LANES overrides.
+    // Ranges of the DSP stages (measured on B200, profiles/r2f_ab_matrix.json, ms per step with 1 / 2 / 3 ranges:
+    // 1024 streams 0.113 / 0.113 / 0.195, 2048: 0.190 / 0.177-0.186 / 0.243, 4096: 0.320-0.330 / 0.305 / 0.352,
+    // 8192: 0.606 / 0.593 / 0.622, 16384: 1.144 / 1.136 / 1.153): two from 1024 to 32767 streams, else one; whole
+    // 128-stream tiles except the last.  $RNNOISE_B200_LANES overrides.
     const char *ln = getenv("RNNOISE_B200_LANES");
-    int nr = ln && atoi(ln) > 0 ? atoi(ln) : (S >= 1024 && S < 12288) ? 2 : 1;
+    int nr = ln && atoi(ln) > 0 ? atoi(ln) : (S >= 1024 && S < 32768) ? 2 : 1;
     if (nr > B200_MAX_RANGES) nr = B200_MAX_RANGES;
     while (nr > 1 && S / nr < 128) nr--;
     const int per = ((S + nr - 1) / nr + 127) / 128 * 128;
@@ -602,7 +602,9 @@ extern "C" B200Engine *b200_engine_create_on(const B200HostModel *m, int S, int 
   // lane is exactly one wave of its CTAs (profiles/README.md "Pitch kernels"); $RNNOISE_B200_PITCH_KERNEL = v1 | v2.
   { const char *pk = getenv("RNNOISE_B200_PITCH_KERNEL"); e->pitch2 = pk && !strcmp(pk, "v2"); }
   ok = ok && cudaFuncSetAttribute(k_pitch2, cudaFuncAttributeMaxDynamicSharedMemorySize, PITCH2_SMEM_BYTES) == cudaSuccess;
-  { const char *ht = getenv("RNNOISE_B200_HEADS_TILE"); e->heads_ns = ht && !strcmp(ht, "32") ? 4 : ht && !strcmp(ht, "8") ? 1 : 2; }
+  // streams per CTA of the heads kernel: 16 while the batch is small (twice the CTAs: lower latency), 32 once the GPU is
+  // full (fewer, fatter CTAs disturb the other stages less: 4096 streams 0.3008 vs 0.3055 ms per step; 8: 0.3245)
+  { const char *ht = getenv("RNNOISE_B200_HEADS_TILE"); e->heads_ns = ht ? (!strcmp(ht, "32") ? 4 : !strcmp(ht, "8") ? 1 : 2) : device_streams >= 4096 ? 4 : 2; }
   ok = ok && cudaFuncSetAttribute(k_heads2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<1>()) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(k_heads2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<4>()) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(k_heads2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<2>()) == cudaSuccess;

@@ -25,7 +25,7 @@ B200Engine *b200_engine_create_on(const B200HostModel *m, int nb_streams, int de
 }
 void b200_engine_destroy(B200Engine *e) { free(e); }
 int b200_engine_streams(const B200Engine *e) { return e->S; }
-int b200_engine_ranges(const B200Engine *e) { return e->S >= 1024 && e->S < 12288 ? 2 : 1; }
+int b200_engine_ranges(const B200Engine *e) { return e->S >= 1024 && e->S < 32768 ? 2 : 1; }
 
 /* out = 2 * in + 1000 * engine id + local stream (+ frame index / 4); vad = 100 * id + local stream + frame / 1000 */
 static void fill_f(B200Engine *e, float *out, const float *in, float *vad, int T) {

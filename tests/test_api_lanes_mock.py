@@ -71,7 +71,7 @@ def test_single_device_batch_is_one_engine_over_the_whole_buffers(M, monkeypatch
     b = L.rnnoise_batch_create(L.model, S, 0)
     assert b and L.rnnoise_batch_get_streams(b) == S
     lanes = L.rnnoise_batch_get_lanes(b)
-    assert lanes == (2 if 1024 <= S < 12288 else 1)
+    assert lanes == (2 if 1024 <= S < 32768 else 1)
     probe = sorted({0, 1, S // 2, S - 1} & set(range(S)))
     own = np.array([owner(L, b, s)[:2] for s in probe])
     assert np.all(own[:, 0] == 0) and own[:, 1].tolist() == probe
