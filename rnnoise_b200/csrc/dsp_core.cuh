@@ -32,6 +32,23 @@ HD void async_copy4(float *dst_shared, const float *src_global) {
   *dst_shared = *src_global;
 #endif
 }
+// Streaming loads / stores for the bulk per-stream arrays (spectra, ring, overlap memory, PCM): evict-first, so that
+// they do not push the few KB of shared tables (twiddles, window, band weights, DCT) out of the small L1 these kernels
+// leave beside their shared memory.  Plain accesses in the host emulation.
+HD float ld_stream(const float *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+HD void st_stream(float *p, float v) {
+#if defined(__CUDA_ARCH__)
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
 HD void async_wait_all() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -308,6 +325,14 @@ HD float interp_bin(const float *band, int k, const DspTables *T) {
 HD float dct_one(const float *in, int i, const DspTables *T) {
   float sum = 0.f;
   for (int j = 0; j < NB_BANDS; j++) sum += in[j] * T->dct[j * NB_BANDS + i];
+  return (float)(sum * sqrt(2. / 22));
+}
+
+// same with the table already staged (row-major [j][i], as T->dct)
+HD float dct_one_tab(const float *in, int i, const float *tab) {
+  float sum = 0.f;
+#pragma unroll 8
+  for (int j = 0; j < NB_BANDS; j++) sum += in[j] * tab[j * NB_BANDS + i];
   return (float)(sum * sqrt(2. / 22));
 }
 

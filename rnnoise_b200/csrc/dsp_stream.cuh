@@ -412,7 +412,10 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   // -- X = FFT(window * [previous frame | this frame]) (denoise.c:332-339); the analysis window
   //    is the last 960 samples of the updated pitch history.
   PHASE_BEGIN
-    for (int i = tid; i < WINDOW_SIZE; i += nthr) win[i] = ring_at(a.ring, a.ring_base, PITCH_BUF_SIZE - WINDOW_SIZE + i);
+    for (int i = tid; i < WINDOW_SIZE; i += nthr) {
+      int p = a.ring_base + PITCH_BUF_SIZE - WINDOW_SIZE + i; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
+      win[i] = ld_stream(a.ring + p);
+    }
   PHASE_END
   PHASE_BEGIN fft_stage1(F, win, nullptr, T, tid, nthr); PHASE_END
   PHASE_BEGIN
@@ -433,7 +436,7 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
       cpx v = F[i];
       if (TRAIN && i >= a.lowpass) v.r = v.i = 0.f;
       XS[i] = v;
-      ((cpx *)a.spec_out)[i] = v;
+      st_stream(a.spec_out + 2 * i, v.r); st_stream(a.spec_out + 2 * i + 1, v.i);
     }
     async_wait_all();   // the lagged window is in `win` once this phase's barrier is passed
   PHASE_END
@@ -446,7 +449,7 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_BEGIN
     for (int i = tid; i < FREQ_SIZE; i += nthr) {
       cpx v = F[i];
-      ((cpx *)a.spec_out)[FREQ_SIZE + i] = v;
+      st_stream(a.spec_out + 2 * (FREQ_SIZE + i), v.r); st_stream(a.spec_out + 2 * (FREQ_SIZE + i) + 1, v.i);
       if (i < 400) {
         // weighted per-bin terms of the three band sums (band_sum_pre), each pair written over the
         // complex value it came from (this thread's own slots) or into the dead window staging
@@ -468,6 +471,9 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
     }
   PHASE_END
   // -- Ex, Ep, Exp (denoise.c:344,375-377)
+  // (the FFT buffer is dead from here on: the three warps that have nothing to do in this phase copy the 32 x 32 DCT
+  //  table into it, so that the two DCTs at the end read shared memory instead of 32 dependent L1/L2 round trips)
+  float *dct_sm = sm + SM_F;
   PHASE_BEGIN
     if (tid < NB_BANDS) {
       float ex = band_finish(misc + MI_BAND, tid);
@@ -476,6 +482,8 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
       exp_ = (float)(exp_ / sqrt(.001 + ex * ep));
       misc[MI_E + tid] = ex; misc[MI_E + 32 + tid] = ep; misc[MI_E + 64 + tid] = exp_;
       a.band_out[tid] = ex; a.band_out[32 + tid] = ep; a.band_out[64 + tid] = exp_;
+    } else {
+      for (int i = tid - NB_BANDS; i < NB_BANDS * NB_BANDS; i += nthr - NB_BANDS) dct_sm[i] = T->dct[i];
     }
   PHASE_END
   // -- log-energy floor follower + silence test (denoise.c:380-393): the 32 log10() are independent
@@ -506,12 +514,12 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_BEGIN
     const int silent = mi[3];
     if (tid < NB_BANDS) {
-      float v = dct_one(misc + MI_LY, tid, T);
+      float v = dct_one_tab(misc + MI_LY, tid, dct_sm);
       if (tid == 0) v -= 12;
       if (tid == 1) v -= 4;
       a.features[tid] = silent ? 0.f : v;
     } else if (tid < 2 * NB_BANDS) {
-      float v = dct_one(misc + MI_E + 64, tid - NB_BANDS, T);
+      float v = dct_one_tab(misc + MI_E + 64, tid - NB_BANDS, dct_sm);
       a.features[tid] = silent ? 0.f : v;
     } else if (tid == 2 * NB_BANDS) {
       a.features[tid] = silent ? 0.f : (float)(.01 * (pitch_T - 300));
@@ -600,8 +608,10 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
   const int silent = a.silence[0];
   PHASE_BEGIN
     for (int i = tid; i < FREQ_SIZE; i += nthr) {
-      X[i] = ((const cpx *)a.spec_delayed)[i];
-      P[i] = ((const cpx *)a.spec_delayed)[FREQ_SIZE + i];
+      cpx x, p;
+      x.r = ld_stream(a.spec_delayed + 2 * i); x.i = ld_stream(a.spec_delayed + 2 * i + 1);
+      p.r = ld_stream(a.spec_delayed + 2 * (FREQ_SIZE + i)); p.i = ld_stream(a.spec_delayed + 2 * (FREQ_SIZE + i) + 1);
+      X[i] = x; P[i] = p;
     }
     if (!silent && tid < NB_BANDS) {
       const float Ex = a.band_delayed[tid], Ep = a.band_delayed[32 + tid], Exp = a.band_delayed[64 + tid];
@@ -661,22 +671,31 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       }
     PHASE_END
   }
-  PHASE_BEGIN fft_stage1(F, nullptr, X, T, tid, nthr); PHASE_END
+  // P is dead once the pitch filter has run: fetch the overlap memory and the synthesis window into its place with
+  // asynchronous copies now, so that the output phase does not wait on HBM / L2 for them
+  float *ola = sm + SS_P, *hw = sm + SS_P + FRAME_SIZE;
+  PHASE_BEGIN
+    for (int i = tid; i < FRAME_SIZE; i += nthr) { async_copy4(ola + i, a.synthesis_mem + i); async_copy4(hw + i, T->half_window + i); }
+    fft_stage1(F, nullptr, X, T, tid, nthr);
+  PHASE_END
   PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
-  PHASE_BEGIN fft_radix5(F, T, tid, nthr); PHASE_END
+  PHASE_BEGIN
+    fft_radix5(F, T, tid, nthr);
+    async_wait_all();   // overlap memory + window are in shared memory once this phase's barrier is passed
+  PHASE_END
   PHASE_BEGIN
     for (int i = tid; i < FRAME_SIZE; i += nthr) {
       // t[i] = 960 * y[(960 - i) % 960].re, windowed; out = first half + overlap memory
       float t0 = WINDOW_SIZE * F[i ? WINDOW_SIZE - i : 0].r;
       float t1 = WINDOW_SIZE * F[WINDOW_SIZE - (FRAME_SIZE + i)].r;   // index 480+i -> y[480-i]
-      t0 *= T->half_window[i];
-      t1 *= T->half_window[FRAME_SIZE - 1 - i];
-      const float o = t0 + a.synthesis_mem[i];
+      t0 *= hw[i];
+      t1 *= hw[FRAME_SIZE - 1 - i];
+      const float o = t0 + ola[i];
       if (a.out_s16) a.out_s16[i] = (short)(int)o;   // truncation toward zero, low 16 bits (x86 cvttss2si + narrowing)
-      else a.out[i] = o;
-      a.synthesis_mem[i] = t1;
+      else st_stream(a.out + i, o);
+      st_stream(a.synthesis_mem + i, t1);
     }
   PHASE_END
 }

@@ -311,11 +311,31 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
   auto bar_tempty = [&](int i) { return smem_u32(&bars[9 + i]); };
 
   pdl_trigger();
-  if (tid == 0) {
+  // The producer thread initialises the barriers ITSELF and starts the weight and operand-tile loads right away:
+  // they overlap the TMEM allocation and the (scattered) parameter staging below instead of following them (the
+  // other threads touch the barriers only after the __syncthreads that ends the prologue).
+  auto load_B0 = [&](int s) {
+    const int st = s % P_STAGES;
+    uint8_t *dst = sB + st * stage_bytes;
+    const int row = (blockIdx.y * nslice + s) * C::kN;
+    mbar_expect_tx(bar_bfull(st), (uint32_t)stage_bytes);
+    for (int a = 0; a < natoms; a++) {
+      tma_load_2d(smem_u32(dst + a * C::kBAtom), &maps.wi, bar_bfull(st), a * TC_KATOM, row);
+      if (kGru) tma_load_2d(smem_u32(dst + (natoms + a) * C::kBAtom), &maps.wr, bar_bfull(st), a * TC_KATOM, row);
+    }
+  };
+  if (warp == P_EPI_WARPS && lane == 0) {
     mbar_init(bar_a, 1);
     for (int i = 0; i < P_STAGES; i++) { mbar_init(bar_bfull(i), 1); mbar_init(bar_bempty(i), 1); }
     for (int i = 0; i < 2; i++) { mbar_init(bar_tfull(i), 1); mbar_init(bar_tempty(i), P_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < P_STAGES && s < nslice; s++) load_B0(s);   // weights: independent of the previous kernel
+    pdl_wait();                                                    // activations of this frame are complete
+    mbar_expect_tx(bar_a, (uint32_t)(C::kMats * natoms * TC_A_ATOM_BYTES));
+    for (int a = 0; a < natoms; a++) {
+      tma_load_2d(smem_u32(sAx + a * TC_A_ATOM_BYTES), &maps.x, bar_a, a * TC_KATOM, m0);
+      if (kGru) tma_load_2d(smem_u32(sAh + a * TC_A_ATOM_BYTES), &maps.h, bar_a, a * TC_KATOM, m0);
+    }
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P_TMEM_COLS) : "memory");
@@ -354,14 +374,7 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
           if (kGru) tma_load_2d(smem_u32(dst + (natoms + a) * C::kBAtom), &maps.wr, bar_bfull(st), a * TC_KATOM, row);
         }
       };
-      for (int s = 0; s < P_STAGES && s < nslice; s++) load_B(s);   // weights: independent of the previous kernel
-      pdl_wait();                                                   // activations of this frame are complete
-      mbar_expect_tx(bar_a, (uint32_t)(C::kMats * natoms * TC_A_ATOM_BYTES));
-      for (int a = 0; a < natoms; a++) {
-        tma_load_2d(smem_u32(sAx + a * TC_A_ATOM_BYTES), &maps.x, bar_a, a * TC_KATOM, m0);
-        if (kGru) tma_load_2d(smem_u32(sAh + a * TC_A_ATOM_BYTES), &maps.h, bar_a, a * TC_KATOM, m0);
-      }
-      mbar_wait(bar_a, 0);
+      mbar_wait(bar_a, 0);   // (weights and operand tiles were requested in the prologue)
       const uint32_t idesc = umma_idesc_i8(TC_M, C::kN);
       for (int s = 0; s < nslice; s++) {
         const int st = s % P_STAGES, ts = s & 1;
