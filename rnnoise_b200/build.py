@@ -47,13 +47,13 @@ def build(force=False, verbose=False, fmad=False, variant=None, flags=()):
     cobjs = []
     for c in ("rnnoise_api.c", "model_blob.c"):
         o = os.path.join(obj, c + ".o")
-        cmds.append(["gcc", "-O2", "-fPIC", "-Wall", "-fvisibility=hidden", "-DRNNOISE_BUILD", "-c", os.path.join(CSRC, c), "-o", o])
+        cmds.append(["gcc", "-O2", "-fPIC", "-pthread", "-Wall", "-fvisibility=hidden", "-DRNNOISE_BUILD", "-c", os.path.join(CSRC, c), "-o", o])
         cobjs.append(o)
     eo = os.path.join(obj, "engine.cu.o")
     extra = os.environ.get("RNNOISE_B200_NVCC_FLAGS", "").split() + list(flags)
     cmds.append([NVCC, *ARCH, *extra, "-O3", "-lineinfo", "--fmad=true" if fmad else "--fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-DRNNOISE_BUILD",
                  "-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, "engine.cu"), "-o", eo])
-    cmds.append([NVCC, *ARCH, "-shared", "-o", so, *cobjs, eo, "-cudart", "static"])
+    cmds.append([NVCC, *ARCH, "-shared", "-o", so, *cobjs, eo, "-cudart", "static", "-lpthread"])
     for cmd in cmds:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:

@@ -4,6 +4,7 @@
  * point; the arithmetic itself lives in the CUDA kernels (engine.cu).  There is no CPU path: every
  * creation call fails when the engine cannot be brought up on a GPU.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -41,7 +42,84 @@ struct RNNoiseBatch {
   /* set when a per-frame call failed after some engines had already enqueued the frame: they are then out of step with
    * each other for good, so every later call fails cleanly instead of producing skewed audio */
   int poisoned;
+  /* multi-device batches: one host worker thread per device, so that the enqueue cost of a frame (copies, launches,
+   * event operations: ~60 us of CPU time per device and frame on the host-buffer path) is paid in parallel instead of
+   * G times in a row by the caller's thread -- measured with 8 GPUs from one thread: 0.80 ms per step of enqueueing
+   * against a 0.30 ms GPU step.  A call posts one job per device and returns when all of them are ENQUEUED. */
+  struct Worker *workers;
 };
+
+typedef struct Job {
+  int kind;                 /* J_* */
+  void *out; const void *in; float *vad;
+  int T, s16;
+} Job;
+enum { J_HOST_ASYNC = 1, J_DEVICE, J_PREFILTER, J_SYNC, J_FRAMES_HOST };
+typedef struct Worker {
+  pthread_t th;
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  int state;                /* 0 idle, 1 job posted, 2 done, -1 quit */
+  Job job;
+  int rc;
+  B200Engine *e;
+} Worker;
+
+static int run_job(B200Engine *e, const Job *j) {
+  switch (j->kind) {
+    case J_HOST_ASYNC:
+      return j->s16 ? b200_engine_frame_host_async_s16(e, (short *)j->out, (const short *)j->in, j->vad)
+                    : b200_engine_frame_host_async(e, (float *)j->out, (const float *)j->in, j->vad);
+    case J_DEVICE:
+      return j->s16 ? b200_engine_frame_device_s16(e, (short *)j->out, (const short *)j->in, j->vad)
+                    : b200_engine_frame_device(e, (float *)j->out, (const float *)j->in, j->vad);
+    case J_PREFILTER: return b200_engine_prefilter_device(e, (const float *)j->in);
+    case J_SYNC: return b200_engine_sync(e);
+    case J_FRAMES_HOST: return b200_engine_frames_host_enqueue(e, j->out, j->in, j->vad, j->T, j->s16, j->T);
+  }
+  return -1;
+}
+static void *worker_main(void *arg) {
+  Worker *w = (Worker *)arg;
+  pthread_mutex_lock(&w->mu);
+  for (;;) {
+    while (w->state != 1 && w->state != -1) pthread_cond_wait(&w->cv, &w->mu);
+    if (w->state == -1) break;
+    pthread_mutex_unlock(&w->mu);
+    w->rc = run_job(w->e, &w->job);
+    pthread_mutex_lock(&w->mu);
+    w->state = 2;
+    pthread_cond_broadcast(&w->cv);
+  }
+  pthread_mutex_unlock(&w->mu);
+  return NULL;
+}
+/* runs jobs[l] on engine l for every engine: on the worker threads when the batch has them, else in place.
+ * Returns 0, or -1 if any job failed (all jobs are always run to completion). */
+static int run_jobs(RNNoiseBatch *b, const Job *jobs) {
+  int l, rc = 0;
+  if (!b->workers) {
+    for (l = 0; l < b->lanes; l++) rc |= run_job(b->engine[l], &jobs[l]);
+    return rc ? -1 : 0;
+  }
+  for (l = 0; l < b->lanes; l++) {
+    Worker *w = &b->workers[l];
+    pthread_mutex_lock(&w->mu);
+    w->job = jobs[l];
+    w->state = 1;
+    pthread_cond_broadcast(&w->cv);
+    pthread_mutex_unlock(&w->mu);
+  }
+  for (l = 0; l < b->lanes; l++) {
+    Worker *w = &b->workers[l];
+    pthread_mutex_lock(&w->mu);
+    while (w->state != 2) pthread_cond_wait(&w->cv, &w->mu);
+    w->state = 0;
+    rc |= w->rc;
+    pthread_mutex_unlock(&w->mu);
+  }
+  return rc ? -1 : 0;
+}
 #define LANE_COUNT(b, l) ((b)->first[(l) + 1] - (b)->first[l])
 
 /* A single-stream state is a handle onto a private batch of one stream. */
@@ -139,6 +217,21 @@ RNNoiseBatch *rnnoise_batch_create_multi(RNNModel *model, int nb_streams, const 
     b->lanes++;
   }
   b->dev_lane[nb_devices] = b->lanes;
+  if (nb_devices > 1) {
+    b->workers = (Worker *)calloc((size_t)nb_devices, sizeof(Worker));
+    if (!b->workers) { rnnoise_batch_destroy(b); return NULL; }
+    for (k = 0; k < nb_devices; k++) {
+      Worker *w = &b->workers[k];
+      w->e = b->engine[k];
+      pthread_mutex_init(&w->mu, NULL);
+      pthread_cond_init(&w->cv, NULL);
+      if (pthread_create(&w->th, NULL, worker_main, w) != 0) {
+        w->e = NULL;   /* marks "no thread" for the destructor */
+        rnnoise_batch_destroy(b);
+        return NULL;
+      }
+    }
+  }
   return b;
 }
 
@@ -149,6 +242,21 @@ RNNoiseBatch *rnnoise_batch_create(RNNModel *model, int nb_streams, int device) 
 void rnnoise_batch_destroy(RNNoiseBatch *b) {
   int l;
   if (!b) return;
+  if (b->workers) {
+    for (l = 0; l < b->nb_devices; l++) {
+      Worker *w = &b->workers[l];
+      if (!w->e) continue;
+      pthread_mutex_lock(&w->mu);
+      w->state = -1;
+      pthread_cond_broadcast(&w->cv);
+      pthread_mutex_unlock(&w->mu);
+      pthread_join(w->th, NULL);
+      pthread_mutex_destroy(&w->mu);
+      pthread_cond_destroy(&w->cv);
+    }
+    free(b->workers);
+    b->workers = NULL;
+  }
   for (l = 0; l < B200_MAX_ENGINES; l++)
     if (b->engine[l]) b200_engine_destroy(b->engine[l]);
   free(b);
@@ -173,10 +281,11 @@ int rnnoise_batch_get_lanes(const RNNoiseBatch *b) { return b ? b200_engine_rang
 #define FOR_LANES(b, l) for (l = 0; l < (b)->lanes; l++)
 
 int rnnoise_batch_sync(RNNoiseBatch *b) {
-  int l, rc = 0;
+  Job jobs[B200_MAX_ENGINES];
+  int l;
   if (!b) return -1;
-  FOR_LANES(b, l) rc |= b200_engine_sync(b->engine[l]);
-  return rc ? -1 : 0;
+  FOR_LANES(b, l) { memset(&jobs[l], 0, sizeof(Job)); jobs[l].kind = J_SYNC; }
+  return run_jobs(b, jobs);
 }
 
 /* Error discipline of the per-frame entry points: everything that can be checked is checked on EVERY lane before
@@ -202,21 +311,36 @@ static int frame_call_ok(RNNoiseBatch *b, int need_idle, int single_device) {
       }                              \
   } while (0)
 
+static int fan_out_jobs(RNNoiseBatch *b, const Job *jobs) {
+  if (run_jobs(b, jobs) != 0) {
+    b->poisoned = 1;
+    return -1;
+  }
+  return 0;
+}
 int rnnoise_process_frame_batch_async(RNNoiseBatch *b, float *out, const float *in, float *vad) {
+  Job jobs[B200_MAX_ENGINES];
   int l;
   if (!out || !in || !frame_call_ok(b, 1, 0)) return -1;
-  FAN_OUT(b, l, b200_engine_frame_host_async(b->engine[l], PCM_AT(out, b, l, 1, float), PCM_AT(in, b, l, 1, const float), VAD_AT(vad, b, l, 1)));
-  return 0;
+  FOR_LANES(b, l) {
+    Job j = {J_HOST_ASYNC, PCM_AT(out, b, l, 1, float), PCM_AT(in, b, l, 1, const float), VAD_AT(vad, b, l, 1), 1, 0};
+    jobs[l] = j;
+  }
+  return fan_out_jobs(b, jobs);
 }
 int rnnoise_process_frame_batch(RNNoiseBatch *b, float *out, const float *in, float *vad) {
   if (rnnoise_process_frame_batch_async(b, out, in, vad) != 0) return -1;
   return rnnoise_batch_sync(b);
 }
 int rnnoise_process_frame_batch_s16_async(RNNoiseBatch *b, short *out, const short *in, float *vad) {
+  Job jobs[B200_MAX_ENGINES];
   int l;
   if (!out || !in || !frame_call_ok(b, 1, 0)) return -1;
-  FAN_OUT(b, l, b200_engine_frame_host_async_s16(b->engine[l], PCM_AT(out, b, l, 1, short), PCM_AT(in, b, l, 1, const short), VAD_AT(vad, b, l, 1)));
-  return 0;
+  FOR_LANES(b, l) {
+    Job j = {J_HOST_ASYNC, PCM_AT(out, b, l, 1, short), PCM_AT(in, b, l, 1, const short), VAD_AT(vad, b, l, 1), 1, 1};
+    jobs[l] = j;
+  }
+  return fan_out_jobs(b, jobs);
 }
 int rnnoise_process_frame_batch_s16(RNNoiseBatch *b, short *out, const short *in, float *vad) {
   if (rnnoise_process_frame_batch_s16_async(b, out, in, vad) != 0) return -1;
@@ -239,21 +363,23 @@ int rnnoise_process_frame_batch_device_s16(RNNoiseBatch *b, short *d_out, const 
 #define DEV_OF_LANE(b, l, k) do { while ((l) >= (b)->dev_lane[(k) + 1]) (k)++; } while (0)
 #define SHARD_OFF(b, l, k) ((size_t)((b)->first[l] - (b)->first[(b)->dev_lane[k]]))
 int rnnoise_process_frame_batch_device_multi(RNNoiseBatch *b, float *const *d_out, const float *const *d_in, float *const *d_vad) {
+  Job jobs[B200_MAX_ENGINES];
   int l, k = 0;
   if (!d_out || !d_in || !frame_call_ok(b, 0, 0)) return -1;
   for (l = 0; l < b->nb_devices; l++)
     if (!d_out[l] || !d_in[l]) return -1;
   FOR_LANES(b, l) {
     DEV_OF_LANE(b, l, k);
-    if (b200_engine_frame_device(b->engine[l], d_out[k] + SHARD_OFF(b, l, k) * FRAME_SIZE, d_in[k] + SHARD_OFF(b, l, k) * FRAME_SIZE,
-                                 d_vad && d_vad[k] ? d_vad[k] + SHARD_OFF(b, l, k) : NULL)) {
-      b->poisoned = 1;
-      return -1;
+    {
+      Job j = {J_DEVICE, d_out[k] + SHARD_OFF(b, l, k) * FRAME_SIZE, d_in[k] + SHARD_OFF(b, l, k) * FRAME_SIZE,
+               d_vad && d_vad[k] ? d_vad[k] + SHARD_OFF(b, l, k) : NULL, 1, 0};
+      jobs[l] = j;
     }
   }
-  return 0;
+  return fan_out_jobs(b, jobs);
 }
 int rnnoise_batch_prefilter_device_multi(RNNoiseBatch *b, const float *const *d_in_next) {
+  Job jobs[B200_MAX_ENGINES];
   int l, k = 0;
   if (!d_in_next || !frame_call_ok(b, 0, 0)) return -1;
   for (l = 0; l < b->nb_devices; l++)
@@ -262,23 +388,25 @@ int rnnoise_batch_prefilter_device_multi(RNNoiseBatch *b, const float *const *d_
     if (b200_engine_prefilter_ahead(b->engine[l]) >= 2) return -1;
   FOR_LANES(b, l) {
     DEV_OF_LANE(b, l, k);
-    if (b200_engine_prefilter_device(b->engine[l], d_in_next[k] + SHARD_OFF(b, l, k) * FRAME_SIZE)) {
-      b->poisoned = 1;
-      return -1;
+    {
+      Job j = {J_PREFILTER, NULL, d_in_next[k] + SHARD_OFF(b, l, k) * FRAME_SIZE, NULL, 1, 0};
+      jobs[l] = j;
     }
   }
-  return 0;
+  return fan_out_jobs(b, jobs);
 }
 static int frames_host(RNNoiseBatch *b, void *out, const void *in, float *vad, int T, int s16) {
   int l;
   if (!out || !in || T < 1 || !frame_call_ok(b, 1, 0)) return -1;
-  FOR_LANES(b, l) {
-    void *o = s16 ? (void *)PCM_AT(out, b, l, T, short) : (void *)PCM_AT(out, b, l, T, float);
-    const void *i = s16 ? (const void *)PCM_AT(in, b, l, T, const short) : (const void *)PCM_AT(in, b, l, T, const float);
-    if (b200_engine_frames_host_enqueue(b->engine[l], o, i, VAD_AT(vad, b, l, T), T, s16, T)) {
-      b->poisoned = 1;
-      return -1;
+  {
+    Job jobs[B200_MAX_ENGINES];
+    FOR_LANES(b, l) {
+      void *o = s16 ? (void *)PCM_AT(out, b, l, T, short) : (void *)PCM_AT(out, b, l, T, float);
+      const void *i = s16 ? (const void *)PCM_AT(in, b, l, T, const short) : (const void *)PCM_AT(in, b, l, T, const float);
+      Job j = {J_FRAMES_HOST, o, i, VAD_AT(vad, b, l, T), T, s16};
+      jobs[l] = j;
     }
+    if (fan_out_jobs(b, jobs) != 0) return -1;
   }
   return rnnoise_batch_sync(b);
 }
