@@ -353,6 +353,37 @@ HD float pitch_gain(float xy, float xx, float yy) { return (float)(xy / sqrt((do
 // 16-byte vector view for single-lane chains (one LDS.128 / STS.128 per four elements)
 struct alignas(16) f4 { float x, y, z, w; };
 
+// s + x[0]*y[0] + x[1]*y[1] + ... + x[n-1]*y[n-1], added strictly in index order (the reference's summation order),
+// n % 4 == 0, n >= 4.  The n dependent additions are the critical path of the narrow pitch phases and one warp does
+// not hide its own shared-memory latency, so the operands travel in two register sets of four: the loads of block
+// b+1 are in flight while block b is added (software pipelining by hand, unrolled twice so that no register copies
+// are needed; same instruction count as the plain loop).
+#define DC_LOAD(xr, yr, i0) { xr[0] = x[(i0)]; xr[1] = x[(i0) + 1]; xr[2] = x[(i0) + 2]; xr[3] = x[(i0) + 3]; \
+                              yr[0] = y[(i0)]; yr[1] = y[(i0) + 1]; yr[2] = y[(i0) + 2]; yr[3] = y[(i0) + 3]; }
+#define DC_ACC(xr, yr) { s = s + xr[0] * yr[0]; s = s + xr[1] * yr[1]; s = s + xr[2] * yr[2]; s = s + xr[3] * yr[3]; }
+HD float dot_chain4(float s, const float *x, const float *y, int n) {
+  const int B = n >> 2;
+  float xa[4], ya[4], xb[4], yb[4];
+  DC_LOAD(xa, ya, 0)
+  int b = 0;
+  for (; b + 2 < B; b += 2) {
+    DC_LOAD(xb, yb, 4 * b + 4)
+    DC_ACC(xa, ya)
+    DC_LOAD(xa, ya, 4 * b + 8)
+    DC_ACC(xb, yb)
+  }
+  if (B - b == 2) {
+    DC_LOAD(xb, yb, 4 * b + 4)
+    DC_ACC(xa, ya)
+    DC_ACC(xb, yb)
+  } else {
+    DC_ACC(xa, ya)
+  }
+  return s;
+}
+#undef DC_LOAD
+#undef DC_ACC
+
 // Running energy chain of find_best_pitch (pitch.c:67-68, 99-100), split so that only the truly
 // serial part runs on one lane:
 //   prefix : S = 1 + sum_{j<len} y[j]^2, added in index order (len % 4 == 0, y 16-byte aligned)

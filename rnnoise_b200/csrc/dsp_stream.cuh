@@ -27,6 +27,7 @@ struct SpectrumArgs {
   float *features;      // [65]
   int *silence;         // [1]
   int lowpass;          // TRAIN only: bins >= lowpass of X are zeroed (denoise.c:340-343)
+  int rot;              // 0..3: which warp runs the one-warp phases (see pitch_streams; never changes a result)
 };
 
 // Pitch half of rnn_compute_frame_features (src/denoise.c:359-370): rnn_pitch_downsample /
@@ -55,18 +56,33 @@ struct SpectrumArgs {
 #define PITCH_THREADS 96
 #endif
 static_assert(PITCH_THREADS >= 96 && PITCH_THREADS % 32 == 0, "phases use local thread ids up to 64 + PITCH_NS");
+#define MPHASE_RTID const int rtid = tid >= rot_lanes ? tid - rot_lanes : tid - rot_lanes + PITCH_NS * PITCH_THREADS; (void)rtid;
 #if defined(__CUDA_ARCH__)
-#define MPHASE_BEGIN { const int tid = threadIdx.x; const int q = tid / PITCH_THREADS, t = tid % PITCH_THREADS; (void)q; (void)t;
+#define MPHASE_BEGIN { const int tid = threadIdx.x; const int q = tid / PITCH_THREADS, t = tid % PITCH_THREADS; (void)q; (void)t; MPHASE_RTID
 #define MPHASE_END } __syncthreads();
 #else
-#define MPHASE_BEGIN for (int tid = 0; tid < PITCH_NS * PITCH_THREADS; ++tid) { const int q = tid / PITCH_THREADS, t = tid % PITCH_THREADS; (void)q; (void)t;
+#define MPHASE_BEGIN for (int tid = 0; tid < PITCH_NS * PITCH_THREADS; ++tid) { const int q = tid / PITCH_THREADS, t = tid % PITCH_THREADS; (void)q; (void)t; MPHASE_RTID
 #define MPHASE_END }
 #endif
 #define PSM(qq) (sm + (qq) * SM_PITCH_TOTAL)
+#ifndef PITCH_CHAIN4
+#define PITCH_CHAIN4 1
+#endif
 
 // a[q].ring == nullptr marks an absent stream (batch size not a multiple of PITCH_NS)
-HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
+HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot) {
   (void)T;
+  // `rot` (0..3) moves the narrow phases -- a few lanes of ONE warp working while the CTA waits -- to another warp of
+  // the CTA.  Co-resident CTAs run the phases in lock-step (same work, same start), and a warp's scheduler is its
+  // index modulo 4: without the rotation the lone warps of all five CTAs of an SM would share one scheduler while
+  // the other three idle.  Which thread does the work never changes a result.
+#if PITCH_NS < 3
+  rot = 0;
+#endif
+  const int rot_lanes = 32 * (rot & 3);
+  const int w_energy = 32 * (rot == 0 ? 1 : rot == 1 ? 2 : rot == 2 ? 4 : 5);   // not a stream's first warp (0, 3, 6, 9)
+  const int w_yy = 32 * (rot == 0 ? 2 : rot == 1 ? 4 : rot == 2 ? 1 : 7);
+  (void)w_energy; (void)w_yy;
   // -- append the new frame to the history ring (denoise.c:359-360; a ring instead of the memmove) and
   //    decimate by 2 straight from HBM/L2 (pitch.c:171-173).  The 480 ring slots being overwritten hold
   //    the oldest samples, which the decimation never reads: no hazard inside the phase.
@@ -96,19 +112,23 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
   // -- autocorrelation lags 0..4 (celt_lpc.c:92-174: first n-4 samples, then the tail): 5 lanes per
   //    stream, all streams packed into warp 0 (lane = 8 * stream + lag)
   MPHASE_BEGIN
-    if (tid < 8 * PITCH_NS && (tid & 7) < 5 && a[tid >> 3].ring) {
-      const int qq = tid >> 3, k = tid & 7, fastN = LP_SIZE - 4;
+    if (rtid < 8 * PITCH_NS && (rtid & 7) < 5 && a[rtid >> 3].ring) {
+      const int qq = rtid >> 3, k = rtid & 7, fastN = LP_SIZE - 4;
       const float *lp0 = PSM(qq) + SM_LP0;
+#if PITCH_CHAIN4
+      const float s = dot_chain4(0.f, lp0, lp0 + k, fastN);
+#else
       float s = 0.f;
 #pragma unroll 4
       for (int j = 0; j < fastN; j++) s = s + lp0[j] * lp0[j + k];
+#endif
       float d = 0.f;
       for (int i = k + fastN; i < LP_SIZE; i++) d = d + lp0[i] * lp0[i - k];
       PSM(qq)[SM_PITCH_END + MI_AC + k] = s + d;
     }
   MPHASE_END
   MPHASE_BEGIN
-    if (tid < PITCH_NS && a[tid].ring) lpc_taps(PSM(tid) + SM_PITCH_END + MI_AC, PSM(tid) + SM_PITCH_END + MI_NUM);
+    if (rtid < PITCH_NS && a[rtid].ring) lpc_taps(PSM(rtid) + SM_PITCH_END + MI_AC, PSM(rtid) + SM_PITCH_END + MI_NUM);
   MPHASE_END
   // -- 5-tap whitening FIR with zero history (celt_fir5, pitch.c:104-143)
   MPHASE_BEGIN
@@ -164,14 +184,14 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
       }
 #pragma unroll
       for (int c = 0; c < 5; c++) if (5 * t + c < 147) xc[5 * t + c] = acc[c];
-    } else if (tid >= 32 && tid < 32 + PITCH_NS && a[tid - 32].ring) {
-      float *sq = PSM(tid - 32);
+    } else if (tid >= w_energy && tid < w_energy + PITCH_NS && a[tid - w_energy].ring) {
+      float *sq = PSM(tid - w_energy);
       syy_running_inplace(sq + SM_SYY, sq_prefix(1.f, sq + SM_Y4, 240), 147);
     }
   MPHASE_END
   MPHASE_BEGIN
-    if (tid < PITCH_NS && a[tid].ring) {
-      float *sq = PSM(tid);
+    if (rtid < PITCH_NS && a[rtid].ring) {
+      float *sq = PSM(rtid);
       int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       Best2 b2; best2_init(b2);
       for (int i0 = 0; i0 < 147; i0 += 3) {   // 147 = 49 * 3: a block's inputs loaded together, then visited in order, branch-free
@@ -199,8 +219,8 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
   // -- fine search around the two coarse winners (pitch.c:344-361): 10 lanes per stream packed from
   //    lane 0 on; the energy chains of all streams in the lanes of another warp
   MPHASE_BEGIN
-    if (tid < 10 * PITCH_NS && a[tid / 10].ring) {
-      const int qq = tid / 10, c = tid % 10;
+    if (rtid < 10 * PITCH_NS && a[rtid / 10].ring) {
+      const int qq = rtid / 10, c = rtid % 10;
       float *sq = PSM(qq);
       const int *mi = (const int *)(sq + SM_PITCH_END + MI_INT);
       const int c0 = 2 * mi[0], c1 = 2 * mi[1];
@@ -209,13 +229,17 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
       if (c >= 5) { int d = i - c0; if (d < 0) d = -d; if (d <= 2) ok = false; }
       if (ok) {
         const float *xl = sq + SM_LP + 384, *y = sq + SM_LP + i;
+#if PITCH_CHAIN4
+        const float sum = dot_chain4(0.f, xl, y, 480);
+#else
         float sum = 0.f;
 #pragma unroll 8
         for (int j = 0; j < 480; j++) sum = sum + xl[j] * y[j];
+#endif
         sq[SM_XC + i] = RMAX(-1, sum);
       }
-    } else if (tid >= 64 && tid < 64 + PITCH_NS && a[tid - 64].ring) {
-      float *sq = PSM(tid - 64);
+    } else if (rtid >= 64 && rtid < 64 + PITCH_NS && a[rtid - 64].ring) {
+      float *sq = PSM(rtid - 64);
       syy_running_inplace(sq + SM_SYY, sq_prefix(1.f, sq + SM_LP, 480), 294);
     }
   MPHASE_END
@@ -224,8 +248,8 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
   //    visit those in ascending order.  Each stream's other warps meanwhile square the samples the
   //    yy_lookup chain of rnn_remove_doubling will need (pitch.c:454): a[i-1] = x[-i]^2, yyl[i] := x[N-i]^2.
   MPHASE_BEGIN
-    if (tid < PITCH_NS && a[tid].ring) {
-      float *sq = PSM(tid);
+    if (rtid < PITCH_NS && a[rtid].ring) {
+      float *sq = PSM(rtid);
       const float *xc = sq + SM_XC, *syy = sq + SM_SYY;
       int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       const int c0 = 2 * mi[0], c1 = 2 * mi[1];
@@ -260,9 +284,9 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
   //    lanes 64..64+NS-1 of the CTA: the yy_lookup energy chains of all streams (pitch.c:450-456)
   MPHASE_BEGIN
     const int N = PITCH_FRAME_SIZE / 2;
-    if (tid >= 64 && tid < 64 + PITCH_NS) {
-      if (a[tid - 64].ring) {
-        float *sq = PSM(tid - 64);
+    if (tid >= w_yy && tid < w_yy + PITCH_NS) {
+      if (a[tid - w_yy].ring) {
+        float *sq = PSM(tid - w_yy);
         const float *x = sq + SM_LP + PITCH_MAX_PERIOD / 2;
         float *yyl = sq + SM_YYL;
         float yy = sq_prefix(0.f, x, N);   // == xx, summed in the same order (pitch.c:449-451)
@@ -292,10 +316,14 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
           off = ((t - 2) & 1) ? T1b : T1;
         }
         if (ok) {
+#if PITCH_CHAIN4
+          dot[t] = dot_chain4(0.f, x, x - off, N);
+#else
           float s = 0.f;
 #pragma unroll 8
           for (int i = 0; i < N; i++) s = s + x[i] * x[i - off];
           dot[t] = s;
+#endif
         }
       }
     }
@@ -303,8 +331,8 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
   // -- every candidate's pitch gain (pitch.c:458, 483-485: a double-precision sqrt and division each) is independent
   //    of the others: one lane per (stream, k), k = 1 (the initial candidate T0) .. 15; results in the dead xcorr array
   MPHASE_BEGIN
-    if (tid < 15 * PITCH_NS && a[tid % PITCH_NS].ring) {
-      const int qq = tid % PITCH_NS, k = 1 + tid / PITCH_NS;
+    if (rtid < 15 * PITCH_NS && a[rtid % PITCH_NS].ring) {
+      const int qq = rtid % PITCH_NS, k = 1 + rtid / PITCH_NS;
       float *sq = PSM(qq);
       const float *dot = sq + SM_DOT, *yyl = sq + SM_YYL;
       const int T0 = ((const int *)(sq + SM_PITCH_END + MI_INT))[4];
@@ -323,9 +351,9 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
   //    overwrites the running best and no threshold depends on an earlier acceptance, so walking k upwards with the
   //    gains at hand is the reference's loop.
   MPHASE_BEGIN
-    if (tid < PITCH_NS && a[tid].ring) {
-      const PitchArgs A = a[tid];
-      float *sq = PSM(tid);
+    if (rtid < PITCH_NS && a[rtid].ring) {
+      const PitchArgs A = a[rtid];
+      float *sq = PSM(rtid);
       const float *cg = sq + SM_XC, *cxy = sq + SM_XC + 16, *cyy = sq + SM_XC + 32;
       int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       const int T0 = mi[4], minperiod = PITCH_MIN_PERIOD / 2;
@@ -362,23 +390,27 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
   // -- the two refinement correlations around the chosen period (pitch.c:513-514: xcorr[k] = <x, x-(T+k-1)>, k = 0, 2;
   //    the centre lag was summed with the candidates in the same order) -- 2 instead of 30 speculative ones
   MPHASE_BEGIN
-    if (tid < 2 * PITCH_NS && a[tid % PITCH_NS].ring) {
-      const int qq = tid % PITCH_NS, side = tid / PITCH_NS;
+    if (rtid < 2 * PITCH_NS && a[rtid % PITCH_NS].ring) {
+      const int qq = rtid % PITCH_NS, side = rtid / PITCH_NS;
       float *sq = PSM(qq);
       const float *x = sq + SM_LP + PITCH_MAX_PERIOD / 2;
       const int Tb = ((const int *)(sq + SM_PITCH_END + MI_INT))[5];
       const int off = side ? Tb + 1 : Tb - 1;
+#if PITCH_CHAIN4
+      sq[SM_DOT + 32 + side] = dot_chain4(0.f, x, x - off, PITCH_FRAME_SIZE / 2);
+#else
       float s2 = 0.f;
 #pragma unroll 8
       for (int i = 0; i < PITCH_FRAME_SIZE / 2; i++) s2 = s2 + x[i] * x[i - off];
       sq[SM_DOT + 32 + side] = s2;
+#endif
     }
   MPHASE_END
   // -- final offset (pitch.c:515-524) + state update (denoise.c:369-370)
   MPHASE_BEGIN
-    if (tid < PITCH_NS && a[tid].ring) {
-      const PitchArgs A = a[tid];
-      float *sq = PSM(tid);
+    if (rtid < PITCH_NS && a[rtid].ring) {
+      const PitchArgs A = a[rtid];
+      float *sq = PSM(rtid);
       const float *dot = sq + SM_DOT;
       int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       const int Tb = mi[5], kbest = mi[6];
@@ -474,34 +506,40 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   // (the FFT buffer is dead from here on: the three warps that have nothing to do in this phase copy the 32 x 32 DCT
   //  table into it, so that the two DCTs at the end read shared memory instead of 32 dependent L1/L2 round trips)
   float *dct_sm = sm + SM_F;
-  PHASE_BEGIN
-    if (tid < NB_BANDS) {
-      float ex = band_finish(misc + MI_BAND, tid);
-      float ep = band_finish(misc + MI_BAND + 34, tid);
-      float exp_ = band_finish(misc + MI_BAND + 68, tid);
+  PHASE_BEGIN const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
+    if (rt < NB_BANDS) {
+      float ex = band_finish(misc + MI_BAND, rt);
+      float ep = band_finish(misc + MI_BAND + 34, rt);
+      float exp_ = band_finish(misc + MI_BAND + 68, rt);
       exp_ = (float)(exp_ / sqrt(.001 + ex * ep));
-      misc[MI_E + tid] = ex; misc[MI_E + 32 + tid] = ep; misc[MI_E + 64 + tid] = exp_;
-      a.band_out[tid] = ex; a.band_out[32 + tid] = ep; a.band_out[64 + tid] = exp_;
+      misc[MI_E + rt] = ex; misc[MI_E + 32 + rt] = ep; misc[MI_E + 64 + rt] = exp_;
+      a.band_out[rt] = ex; a.band_out[32 + rt] = ep; a.band_out[64 + rt] = exp_;
     } else {
-      for (int i = tid - NB_BANDS; i < NB_BANDS * NB_BANDS; i += nthr - NB_BANDS) dct_sm[i] = T->dct[i];
+      for (int i = rt - NB_BANDS; i < NB_BANDS * NB_BANDS; i += nthr - NB_BANDS) dct_sm[i] = T->dct[i];
     }
   PHASE_END
   // -- log-energy floor follower + silence test (denoise.c:380-393): the 32 log10() are independent
   //    (one lane each); only the follower itself is a serial chain.
-  PHASE_BEGIN
-    if (tid < NB_BANDS) misc[MI_LY + tid] = (float)log10(1e-2 + misc[MI_E + tid]);
+  PHASE_BEGIN const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
+    if (rt < NB_BANDS) misc[MI_LY + rt] = (float)log10(1e-2 + misc[MI_E + rt]);
   PHASE_END
-  PHASE_BEGIN
-    if (tid == 0) {
+  PHASE_BEGIN const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
+    if (rt == 0) {
       float logMax = -2, follow = -2, E = 0;
+      // The reference evaluates follow - 1.5 and both maxima in double and rounds on the stores to ly[i] and follow
+      // (denoise.c:384-386).  follow - 1.5 is exact in double (24-bit operands a few binades apart), rounding is
+      // monotonic -- float(max(a, b)) == max(float(a), float(b)) -- and the other operands are floats already, so the
+      // same values come out of float arithmetic: follow - 1.5f is the single correct rounding of the exact
+      // difference.  32 dependent steps of 3 float ops instead of conversions and FP64 ops on one thread
+      // (tests/test_dsp_emulation.py holds this source against the literal restatement in oracle/rnnoise_port.c).
       for (int i = 0; i < NB_BANDS; i++) {
         float ly = misc[MI_LY + i];
-        double f15 = follow - 1.5;
-        double m1 = RMAX(f15, ly);
-        float lm7 = logMax - 7;
-        ly = (float)RMAX(lm7, m1);
+        const float f15 = follow - 1.5f;
+        const float m1 = RMAX(f15, ly);
+        const float lm7 = logMax - 7;
+        ly = RMAX(lm7, m1);
         logMax = RMAX(logMax, ly);
-        follow = (float)RMAX(f15, ly);
+        follow = RMAX(f15, ly);
         misc[MI_LY + i] = ly;
         E += misc[MI_E + i];
       }
@@ -511,18 +549,18 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
     }
   PHASE_END
   // -- features (denoise.c:378-379, 391, 394-396)
-  PHASE_BEGIN
+  PHASE_BEGIN const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
     const int silent = mi[3];
-    if (tid < NB_BANDS) {
-      float v = dct_one_tab(misc + MI_LY, tid, dct_sm);
-      if (tid == 0) v -= 12;
-      if (tid == 1) v -= 4;
-      a.features[tid] = silent ? 0.f : v;
-    } else if (tid < 2 * NB_BANDS) {
-      float v = dct_one_tab(misc + MI_E + 64, tid - NB_BANDS, dct_sm);
-      a.features[tid] = silent ? 0.f : v;
-    } else if (tid == 2 * NB_BANDS) {
-      a.features[tid] = silent ? 0.f : (float)(.01 * (pitch_T - 300));
+    if (rt < NB_BANDS) {
+      float v = dct_one_tab(misc + MI_LY, rt, dct_sm);
+      if (rt == 0) v -= 12;
+      if (rt == 1) v -= 4;
+      a.features[rt] = silent ? 0.f : v;
+    } else if (rt < 2 * NB_BANDS) {
+      float v = dct_one_tab(misc + MI_E + 64, rt - NB_BANDS, dct_sm);
+      a.features[rt] = silent ? 0.f : v;
+    } else if (rt == 2 * NB_BANDS) {
+      a.features[rt] = silent ? 0.f : (float)(.01 * (pitch_T - 300));
     }
   PHASE_END
 }
@@ -591,6 +629,7 @@ struct SynthesisArgs {
   float *synthesis_mem;     // [480]
   float *out;               // [480] float PCM, or
   short *out_s16;           // [480] 16-bit PCM (non-null selects it): the C cast of examples/rnnoise_demo.c:58
+  int rot;                  // 0..3: which warp runs the one-warp phases (see pitch_streams)
 };
 
 // shared-memory plan of the synthesis CTA (floats)
@@ -613,9 +652,10 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       p.r = ld_stream(a.spec_delayed + 2 * (FREQ_SIZE + i)); p.i = ld_stream(a.spec_delayed + 2 * (FREQ_SIZE + i) + 1);
       X[i] = x; P[i] = p;
     }
-    if (!silent && tid < NB_BANDS) {
-      const float Ex = a.band_delayed[tid], Ep = a.band_delayed[32 + tid], Exp = a.band_delayed[64 + tid];
-      const float gg = a.gains[tid];
+    const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
+    if (!silent && rt < NB_BANDS) {
+      const float Ex = a.band_delayed[rt], Ep = a.band_delayed[32 + rt], Exp = a.band_delayed[64 + rt];
+      const float gg = a.gains[rt];
       float rr;
       if (Exp > gg) rr = 1;
       else {
@@ -626,7 +666,7 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       c = RMIN(1, c);
       rr = (float)sqrt((double)c);
       rr = (float)(rr * sqrt(Ex / (1e-8 + Ep)));
-      r[tid] = rr;
+      r[rt] = rr;
     }
   PHASE_END
   if (!silent) {
@@ -644,20 +684,22 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       }
     PHASE_END
     PHASE_BEGIN
-      if (tid < NB_BANDS + 2) sums[tid] = band_sum_pre(tid, sm + SS_F, 1, 400, T);
+      const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
+      if (rt < NB_BANDS + 2) sums[rt] = band_sum_pre(rt, sm + SS_F, 1, 400, T);
     PHASE_END
     PHASE_BEGIN
-      if (tid < NB_BANDS) {
-        float newE = band_finish(sums, tid);
-        norm[tid] = (float)sqrt(a.band_delayed[tid] / (1e-8 + newE));
+      const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
+      if (rt < NB_BANDS) {
+        float newE = band_finish(sums, rt);
+        norm[rt] = (float)sqrt(a.band_delayed[rt] / (1e-8 + newE));
         // gain smoothing (denoise.c:479-487)
-        float gg = a.gains[tid];
-        float lg = a.lastg[tid];
+        float gg = a.gains[rt];
+        float lg = a.lastg[rt];
         float al = .6f * lg;
         gg = RMAX(gg, al);
-        double t = gg * (a.band_delayed[tid] + 1e-3) / (a.band_cur[tid] + 1e-3);
-        a.lastg[tid] = (float)RMIN(1.f, t);
-        g[tid] = gg;
+        double t = gg * (a.band_delayed[rt] + 1e-3) / (a.band_cur[rt] + 1e-3);
+        a.lastg[rt] = (float)RMIN(1.f, t);
+        g[rt] = gg;
       }
     PHASE_END
     PHASE_BEGIN

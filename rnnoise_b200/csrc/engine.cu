@@ -102,6 +102,18 @@ __global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__
   if (s < r1) { a.hp_mem[2 * s] = m0; a.hp_mem[2 * s + 1] = m1; }
 }
 
+// Which warp of a DSP CTA runs its one-warp phases (dsp_stream.cuh pitch_streams `rot`; also spectrum / synthesis).  Blocks are handed to the SMs round
+// robin, so the co-resident CTAs of an SM are about gridDim-independent multiples of the SM count apart.
+__device__ __forceinline__ int warp_rotation() {
+#ifdef PITCH_NO_ROTATION
+  return 0;
+#else
+  unsigned nsm;
+  asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+  return (int)((blockIdx.x / nsm) & 3);
+#endif
+}
+
 // grid = ceil(S / PITCH_NS), block = PITCH_NS * PITCH_THREADS, dynamic smem = PITCH_NS * SM_PITCH_TOTAL floats
 #ifndef PITCH_MIN_CTAS
 #define PITCH_MIN_CTAS (2048 / (PITCH_NS * PITCH_THREADS) < 20 ? 2048 / (PITCH_NS * PITCH_THREADS) : 20)   // 32 regs/thread
@@ -117,7 +129,7 @@ k_pitch(Arena a, const DspTables *__restrict__ T, int f, int r0, int r1) {
     g.xb = a.xb + ((size_t)(f & 1) * a.S + s) * FRAME_SIZE;
     g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
     g.pitch_state = a.pitch_state + 2 * (size_t)s;
-    pitch_streams(sm, &g, T);
+    pitch_streams(sm, &g, T, 0);
   }
 #else
   __shared__ PitchArgs pa[PITCH_NS];
@@ -136,7 +148,7 @@ k_pitch(Arena a, const DspTables *__restrict__ T, int f, int r0, int r1) {
       pa[threadIdx.x] = g;
     }
     __syncthreads();
-    pitch_streams(sm, pa, T);
+    pitch_streams(sm, pa, T, warp_rotation());
   }
 #endif
 }
@@ -172,6 +184,7 @@ __global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena
   g.features = a.features + ((size_t)par * a.S + s) * NB_FEATURES;
   g.silence = a.silence + (size_t)par * a.S + s;
   g.lowpass = FREQ_SIZE;
+  g.rot = warp_rotation();
   spectrum_stream<false>(sm, g, T);
 }
 
@@ -198,6 +211,7 @@ __global__ void __launch_bounds__(DSP_THREADS) k_train_features(Arena a, const D
   g.features = io.rec + (size_t)s * TRAIN_RECORD;
   g.silence = a.silence + (size_t)par * a.S + s;
   g.lowpass = io.lowpass ? io.lowpass[s] : FREQ_SIZE;
+  g.rot = warp_rotation();
   spectrum_stream<true>(sm, g, T);
   TrainArgs t;
   t.clean = io.clean + (size_t)s * FRAME_SIZE;
@@ -227,6 +241,7 @@ __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTab
   g.synthesis_mem = a.synth_mem + (size_t)s * FRAME_SIZE;
   g.out = out_s16 ? nullptr : (float *)out + (size_t)s * stride;
   g.out_s16 = out_s16 ? (short *)out + (size_t)s * stride : nullptr;
+  g.rot = warp_rotation();
   synthesis_stream(sm, g, T);
 }
 

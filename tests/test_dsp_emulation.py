@@ -105,3 +105,39 @@ def test_pitch_group_kernel_source_is_bit_identical_to_port(emu, port_default, f
     emu.emu_group_destroy(e)
     for st in states:
         port_default.destroy(st)
+
+
+def test_log_energy_follower_in_float_equals_the_reference_double_form():
+    """spectrum_stream runs the floor follower of denoise.c:380-387 in float (dsp_stream.cuh); the reference evaluates
+    follow - 1.5 and the maxima in double.  Both forms over 200k random band vectors, ties and near-ties included."""
+    rng = np.random.default_rng(5)
+    n = 200_000
+    ly = rng.uniform(-2.2, 9.0, size=(n, 32)).astype(np.float32)
+    # near-ties: a band exactly 1.5 (or 7) below its predecessor / the running maximum, +- one ulp
+    k = rng.integers(1, 32, size=n)
+    rows = np.arange(n)
+    tie = ly[rows, k - 1] - np.float32(1.5)
+    ly[rows, k] = np.where(rows % 3 == 0, tie, np.where(rows % 3 == 1, np.nextafter(tie, np.float32(np.inf)), ly[rows, k]))
+    with np.errstate(invalid="ignore"):
+        def run(double_form):
+            out = np.empty_like(ly)
+            logmax = np.full(n, -2, np.float32); follow = np.full(n, -2, np.float32)
+            for i in range(32):
+                if double_form:
+                    f15 = follow.astype(np.float64) - 1.5
+                    m1 = np.where(f15 > ly[:, i], f15, ly[:, i].astype(np.float64))
+                    lm7 = (logmax - np.float32(7)).astype(np.float32)
+                    v = np.where(lm7 > m1, lm7.astype(np.float64), m1).astype(np.float32)
+                    logmax = np.where(logmax > v, logmax, v)
+                    follow = np.where(f15 > v, f15, v.astype(np.float64)).astype(np.float32)
+                else:
+                    f15 = (follow - np.float32(1.5)).astype(np.float32)
+                    m1 = np.where(f15 > ly[:, i], f15, ly[:, i])
+                    lm7 = (logmax - np.float32(7)).astype(np.float32)
+                    v = np.where(lm7 > m1, lm7, m1)
+                    logmax = np.where(logmax > v, logmax, v)
+                    follow = np.where(f15 > v, f15, v)
+                out[:, i] = v
+            return out
+        a, b = run(True), run(False)
+    assert a.tobytes() == b.tobytes()
