@@ -107,20 +107,26 @@ struct DspTables {
 #define SM_PITCH_END (SM_DOT + 64)
 //   spectrum kernel
 #define SM_F 0                           // [1920] FFT work buffer (interleaved complex)
-#define SM_XS (SM_F + 2 * WINDOW_SIZE)   // [962] X kept for the X.P correlation
-#define SM_WIN (SM_XS + 2 * FREQ_SIZE)    // [960] analysis window staged from the ring (coalesced); after the P
+#define SM_XS (SM_F + 2 * WINDOW_SIZE)   // [800] bins 0..399 of X kept for the X.P correlation (the band sums end at bin 400)
+#define SM_WIN (SM_XS + 2 * 400)         // [960] analysis window staged from the ring (coalesced); after the P
                                          //       transform's first stage: per-bin terms |P|^2 [0,400), Re(X conj P) [400,800)
 #define SM_SPEC_END (SM_WIN + WINDOW_SIZE)
-#define SM_MISC_SIZE 288                 // small per-stream scalars / band vectors, after either plan
+#define SM_MISC_SIZE 288                 // pitch kernel: small per-stream scalars / vectors after its plan (MI_*)
+#define SM_SPEC_MISC 208                 // spectrum kernel: its own, tighter misc block (SMI_*)
 #define SM_PITCH_TOTAL (SM_PITCH_END + SM_MISC_SIZE)
-#define SM_SPEC_TOTAL (SM_SPEC_END + SM_MISC_SIZE)
+// 3888 floats = 15.2 KB: with the 1 KB the system reserves per CTA, 14 CTAs fit the 228 KB of an SM (13 with the
+// round-1 plan of 4130 floats), so the 2048 one-stream CTAs of a 4096-stream batch's range are ONE wave (2072 slots)
+#define SM_SPEC_TOTAL (SM_SPEC_END + SM_SPEC_MISC)
+static_assert((SM_SPEC_TOTAL * 4 + 1024) * 14 <= 228 * 1024, "spectrum kernel: 14 CTAs per SM");
 // misc slots (float indices relative to the misc base)
 #define MI_AC 0     // [5] autocorrelation
 #define MI_NUM 8    // [5] whitening FIR taps
 #define MI_INT 16   // ints: [0]=best0 [1]=best1 [2]=T (pitch index) [3]=silence [4]=T0 half-rate [5]=Tb [6]=kbest
-#define MI_BAND 32  // [3][34] band sums (X, P, X.P)
-#define MI_E 136    // [3][32] Ex, Ep, Exp
-#define MI_LY 232   // [32] log band energies
+// spectrum kernel's misc block
+#define SMI_INT 0    // ints: [3]=silence
+#define SMI_BAND 8   // [3][34] band sums (X, P, X.P)
+#define SMI_LY 8     // [32] log band energies -- written after the band sums are consumed, in their place
+#define SMI_E 112    // [3][32] Ex, Ep, Exp
 static_assert(SM_LP0 + LP_SIZE <= SM_PITCH_END, "lp0 overlay");
 static_assert(SM_LP % 4 == 0 && SM_X4 % 4 == 0 && SM_Y4 % 4 == 0 && SM_SYY % 4 == 0 && (SM_LP + 384) % 4 == 0,
               "single-lane chains use 16-byte vector loads");

@@ -437,7 +437,7 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
 template <bool TRAIN>
 HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   float *misc = sm + SM_SPEC_END;
-  int *mi = (int *)(misc + MI_INT);
+  int *mi = (int *)(misc + SMI_INT);
   cpx *F = (cpx *)(sm + SM_F), *XS = (cpx *)(sm + SM_XS);
   float *win = sm + SM_WIN;
   const int pitch_T = ((const int *)a.pitch_state)[0];
@@ -467,7 +467,7 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
     for (int i = tid; i < FREQ_SIZE; i += nthr) {
       cpx v = F[i];
       if (TRAIN && i >= a.lowpass) v.r = v.i = 0.f;
-      XS[i] = v;
+      if (i < 400) XS[i] = v;
       st_stream(a.spec_out + 2 * i, v.r); st_stream(a.spec_out + 2 * i + 1, v.i);
     }
     async_wait_all();   // the lagged window is in `win` once this phase's barrier is passed
@@ -498,7 +498,7 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_BEGIN
     if (tid < 3 * (NB_BANDS + 2)) {
       const int set = tid / (NB_BANDS + 2), b = tid % (NB_BANDS + 2);
-      misc[MI_BAND + 34 * set + b] = set == 2 ? band_sum_pre(b, win, 1, 400, T)
+      misc[SMI_BAND + 34 * set + b] = set == 2 ? band_sum_pre(b, win, 1, 400, T)
                                               : band_sum_pre(b, (const float *)(set == 0 ? XS : F), 2, 1, T);
     }
   PHASE_END
@@ -508,11 +508,11 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   float *dct_sm = sm + SM_F;
   PHASE_BEGIN const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
     if (rt < NB_BANDS) {
-      float ex = band_finish(misc + MI_BAND, rt);
-      float ep = band_finish(misc + MI_BAND + 34, rt);
-      float exp_ = band_finish(misc + MI_BAND + 68, rt);
+      float ex = band_finish(misc + SMI_BAND, rt);
+      float ep = band_finish(misc + SMI_BAND + 34, rt);
+      float exp_ = band_finish(misc + SMI_BAND + 68, rt);
       exp_ = (float)(exp_ / sqrt(.001 + ex * ep));
-      misc[MI_E + rt] = ex; misc[MI_E + 32 + rt] = ep; misc[MI_E + 64 + rt] = exp_;
+      misc[SMI_E + rt] = ex; misc[SMI_E + 32 + rt] = ep; misc[SMI_E + 64 + rt] = exp_;
       a.band_out[rt] = ex; a.band_out[32 + rt] = ep; a.band_out[64 + rt] = exp_;
     } else {
       for (int i = rt - NB_BANDS; i < NB_BANDS * NB_BANDS; i += nthr - NB_BANDS) dct_sm[i] = T->dct[i];
@@ -521,7 +521,7 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   // -- log-energy floor follower + silence test (denoise.c:380-393): the 32 log10() are independent
   //    (one lane each); only the follower itself is a serial chain.
   PHASE_BEGIN const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
-    if (rt < NB_BANDS) misc[MI_LY + rt] = (float)log10(1e-2 + misc[MI_E + rt]);
+    if (rt < NB_BANDS) misc[SMI_LY + rt] = (float)log10(1e-2 + misc[SMI_E + rt]);
   PHASE_END
   PHASE_BEGIN const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
     if (rt == 0) {
@@ -531,17 +531,17 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
       // monotonic -- float(max(a, b)) == max(float(a), float(b)) -- and the other operands are floats already, so the
       // same values come out of float arithmetic: follow - 1.5f is the single correct rounding of the exact
       // difference.  32 dependent steps of 3 float ops instead of conversions and FP64 ops on one thread
-      // (tests/test_dsp_emulation.py holds this source against the literal restatement in oracle/rnnoise_port.c).
+      // (tests/test_dsp_emulation.py holds this source against the literal double form).
       for (int i = 0; i < NB_BANDS; i++) {
-        float ly = misc[MI_LY + i];
+        float ly = misc[SMI_LY + i];
         const float f15 = follow - 1.5f;
         const float m1 = RMAX(f15, ly);
         const float lm7 = logMax - 7;
         ly = RMAX(lm7, m1);
         logMax = RMAX(logMax, ly);
         follow = RMAX(f15, ly);
-        misc[MI_LY + i] = ly;
-        E += misc[MI_E + i];
+        misc[SMI_LY + i] = ly;
+        E += misc[SMI_E + i];
       }
       int silent = !TRAIN && E < 0.04;
       mi[3] = silent;
@@ -552,12 +552,12 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_BEGIN const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
     const int silent = mi[3];
     if (rt < NB_BANDS) {
-      float v = dct_one_tab(misc + MI_LY, rt, dct_sm);
+      float v = dct_one_tab(misc + SMI_LY, rt, dct_sm);
       if (rt == 0) v -= 12;
       if (rt == 1) v -= 4;
       a.features[rt] = silent ? 0.f : v;
     } else if (rt < 2 * NB_BANDS) {
-      float v = dct_one_tab(misc + MI_E + 64, rt - NB_BANDS, dct_sm);
+      float v = dct_one_tab(misc + SMI_E + 64, rt - NB_BANDS, dct_sm);
       a.features[rt] = silent ? 0.f : v;
     } else if (rt == 2 * NB_BANDS) {
       a.features[rt] = silent ? 0.f : (float)(.01 * (pitch_T - 300));
@@ -566,7 +566,7 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
 }
 
 // Training targets (the per-frame body of src/dump_features.c:466-491, a -DTRAINING=1 build): after
-// spectrum_stream<true> of the noisy frame (features -> rec[0..65), Ex left in misc[MI_E..]), analyse the
+// spectrum_stream<true> of the noisy frame (features -> rec[0..65), Ex left in misc[SMI_E..]), analyse the
 // clean frame (rnn_frame_analysis on the clean state: window, FFT, low-pass, band energies Ey) and derive
 // the ideal band gains g = min(1, sqrt((Ey + 1e-3) / (Ex + 1e-3))), -1 where the target is undefined.
 struct TrainArgs {
@@ -602,11 +602,11 @@ HD void train_targets_stream(float *sm, const TrainArgs a, const DspTables *T) {
     }
   PHASE_END
   PHASE_BEGIN
-    if (tid < NB_BANDS + 2) misc[MI_BAND + tid] = band_sum_pre(tid, win, 1, 400, T);
+    if (tid < NB_BANDS + 2) misc[SMI_BAND + tid] = band_sum_pre(tid, win, 1, 400, T);
   PHASE_END
   PHASE_BEGIN
     if (tid < NB_BANDS) {
-      const float ey = band_finish(misc + MI_BAND, tid), ex = misc[MI_E + tid];
+      const float ey = band_finish(misc + SMI_BAND, tid), ex = misc[SMI_E + tid];
       float g = (float)sqrt((ey + 1e-3) / (ex + 1e-3));
       if (g > 1) g = 1;
       if (a.quiet[0] || tid > a.band_lp) g = -1;
@@ -634,10 +634,12 @@ struct SynthesisArgs {
 
 // shared-memory plan of the synthesis CTA (floats)
 #define SS_X 0                        // [962] delayed X
-#define SS_P (SS_X + 2 * FREQ_SIZE)   // [962] delayed P
-#define SS_F (SS_P + 2 * FREQ_SIZE)   // [1920] FFT buffer
+#define SS_P (SS_X + 2 * FREQ_SIZE)   // [800] bins 0..399 of the delayed P (the pitch filter's gain is 0 from bin 400 on)
+#define SS_F (SS_P + 2 * 400)         // [1920] FFT buffer
 #define SS_V (SS_F + 2 * WINDOW_SIZE) // [6][34] band vectors: r, norm, g, sums...
 #define SS_TOTAL (SS_V + 6 * 34)
+// 3886 floats: 14 CTAs per SM (13 with all 481 bins of P resident), see SM_SPEC_TOTAL
+static_assert((SS_TOTAL * 4 + 1024) * 14 <= 228 * 1024, "synthesis kernel: 14 CTAs per SM");
 
 // rnn_pitch_filter (denoise.c:421-455), gain smoothing + interpolation (:479-493),
 // frame_synthesis (:400-407) with inverse_transform (:200-217).
@@ -650,7 +652,14 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       cpx x, p;
       x.r = ld_stream(a.spec_delayed + 2 * i); x.i = ld_stream(a.spec_delayed + 2 * i + 1);
       p.r = ld_stream(a.spec_delayed + 2 * (FREQ_SIZE + i)); p.i = ld_stream(a.spec_delayed + 2 * (FREQ_SIZE + i) + 1);
-      X[i] = x; P[i] = p;
+      if (i < 400) P[i] = p;
+      else if (!silent) {
+        // the pitch filter of the bins the band interpolation leaves at gain 0 (denoise.c:140-154, 432-438), done here
+        // so that P's tail need not stay resident: the same multiply and add as in the filter phase below
+        x.r += 0.f * p.r;
+        x.i += 0.f * p.i;
+      }
+      X[i] = x;
     }
     const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
     if (!silent && rt < NB_BANDS) {
@@ -671,16 +680,15 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
   PHASE_END
   if (!silent) {
     PHASE_BEGIN
-      for (int i = tid; i < FREQ_SIZE; i += nthr) {
+      for (int i = tid; i < 400; i += nthr) {   // bins 400..480: done at load time
         float rf = interp_bin(r, i, T);
         cpx x = X[i], p = P[i];
         x.r += rf * p.r;
         x.i += rf * p.i;
         X[i] = x;
-        if (i < 400) {   // weighted band-sum terms into the (still idle) FFT buffer
-          const float tx = bin_term(x, x);
-          sm[SS_F + i] = T->bin_frac[i] * tx; sm[SS_F + 400 + i] = T->bin_cfrac[i] * tx;
-        }
+        // weighted band-sum terms into the (still idle) FFT buffer
+        const float tx = bin_term(x, x);
+        sm[SS_F + i] = T->bin_frac[i] * tx; sm[SS_F + 400 + i] = T->bin_cfrac[i] * tx;
       }
     PHASE_END
     PHASE_BEGIN
@@ -713,11 +721,12 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       }
     PHASE_END
   }
-  // P is dead once the pitch filter has run: fetch the overlap memory and the synthesis window into its place with
-  // asynchronous copies now, so that the output phase does not wait on HBM / L2 for them
-  float *ola = sm + SS_P, *hw = sm + SS_P + FRAME_SIZE;
+  // P is dead once the pitch filter has run: fetch the overlap memory into its place with asynchronous copies now, so
+  // that the output phase does not wait on HBM for it (the window is a table every CTA reads: L1 / L2 hits)
+  float *ola = sm + SS_P;
+  const float *hw = T->half_window;
   PHASE_BEGIN
-    for (int i = tid; i < FRAME_SIZE; i += nthr) { async_copy4(ola + i, a.synthesis_mem + i); async_copy4(hw + i, T->half_window + i); }
+    for (int i = tid; i < FRAME_SIZE; i += nthr) async_copy4(ola + i, a.synthesis_mem + i);
     fft_stage1(F, nullptr, X, T, tid, nthr);
   PHASE_END
   PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END

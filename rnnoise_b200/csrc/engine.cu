@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(PG_THREADS, PG <= 8 ? 2 : 1) k_pitch2(Arena a,
 }
 
 #ifndef SPEC_MIN_BLOCKS
-#define SPEC_MIN_BLOCKS 12
+#define SPEC_MIN_BLOCKS 14
 #endif
 __global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena a, const DspTables *__restrict__ T, int f, int r0) {
   extern __shared__ float sm[];
