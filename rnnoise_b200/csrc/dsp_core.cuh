@@ -32,12 +32,29 @@ HD void async_copy4(float *dst_shared, const float *src_global) {
   *dst_shared = *src_global;
 #endif
 }
+HD void async_copy8(void *dst_shared, const void *src_global) {   // both 8-byte aligned
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
+#else
+  ((float *)dst_shared)[0] = ((const float *)src_global)[0];
+  ((float *)dst_shared)[1] = ((const float *)src_global)[1];
+#endif
+}
 // Streaming loads / stores for the bulk per-stream arrays (spectra, ring, overlap memory, PCM): evict-first, so that
 // they do not push the few KB of shared tables (twiddles, window, band weights, DCT) out of the small L1 these kernels
 // leave beside their shared memory.  Plain accesses in the host emulation.
 HD float ld_stream(const float *p) {
 #if defined(__CUDA_ARCH__)
   return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+// plain global load that bypasses L1 (the history ring: read here once, re-read from L2 by the next kernel).  Like
+// ld_stream it names the global space, which lets the compiler move it above shared-memory stores.
+HD float ld_global(const float *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);
 #else
   return *p;
 #endif
@@ -114,10 +131,7 @@ struct DspTables {
 #define SM_MISC_SIZE 288                 // pitch kernel: small per-stream scalars / vectors after its plan (MI_*)
 #define SM_SPEC_MISC 208                 // spectrum kernel: its own, tighter misc block (SMI_*)
 #define SM_PITCH_TOTAL (SM_PITCH_END + SM_MISC_SIZE)
-// 3888 floats = 15.2 KB: with the 1 KB the system reserves per CTA, 14 CTAs fit the 228 KB of an SM (13 with the
-// round-1 plan of 4130 floats), so the 2048 one-stream CTAs of a 4096-stream batch's range are ONE wave (2072 slots)
-#define SM_SPEC_TOTAL (SM_SPEC_END + SM_SPEC_MISC)
-static_assert((SM_SPEC_TOTAL * 4 + 1024) * 14 <= 228 * 1024, "spectrum kernel: 14 CTAs per SM");
+#define SM_SPEC_TOTAL (SM_SPEC_END + SM_SPEC_MISC)   // 3888 floats = 15.2 KB (registers, not shared memory, set the CTAs per SM: engine.cu)
 // misc slots (float indices relative to the misc base)
 #define MI_AC 0     // [5] autocorrelation
 #define MI_NUM 8    // [5] whitening FIR taps
@@ -132,6 +146,11 @@ static_assert(SM_LP % 4 == 0 && SM_X4 % 4 == 0 && SM_Y4 % 4 == 0 && SM_SYY % 4 =
               "single-lane chains use 16-byte vector loads");
 
 // logical sample k of the updated 1728-sample pitch history (after this frame's shift)
+HD int ring_pos(int ring_base, int k) {
+  int p = ring_base + k;
+  if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
+  return p;
+}
 HD float ring_at(const float *ring, int ring_base, int k) {
   int p = ring_base + k;
   if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;

@@ -27,7 +27,6 @@ struct SpectrumArgs {
   float *features;      // [65]
   int *silence;         // [1]
   int lowpass;          // TRAIN only: bins >= lowpass of X are zeroed (denoise.c:340-343)
-  int rot;              // 0..3: which warp runs the one-warp phases (see pitch_streams; never changes a result)
 };
 
 // Pitch half of rnn_compute_frame_features (src/denoise.c:359-370): rnn_pitch_downsample /
@@ -56,12 +55,11 @@ struct SpectrumArgs {
 #define PITCH_THREADS 96
 #endif
 static_assert(PITCH_THREADS >= 96 && PITCH_THREADS % 32 == 0, "phases use local thread ids up to 64 + PITCH_NS");
-#define MPHASE_RTID const int rtid = tid >= rot_lanes ? tid - rot_lanes : tid - rot_lanes + PITCH_NS * PITCH_THREADS; (void)rtid;
 #if defined(__CUDA_ARCH__)
-#define MPHASE_BEGIN { const int tid = threadIdx.x; const int q = tid / PITCH_THREADS, t = tid % PITCH_THREADS; (void)q; (void)t; MPHASE_RTID
+#define MPHASE_BEGIN { const int tid = threadIdx.x; const int q = tid / PITCH_THREADS, t = tid % PITCH_THREADS; (void)q; (void)t;
 #define MPHASE_END } __syncthreads();
 #else
-#define MPHASE_BEGIN for (int tid = 0; tid < PITCH_NS * PITCH_THREADS; ++tid) { const int q = tid / PITCH_THREADS, t = tid % PITCH_THREADS; (void)q; (void)t; MPHASE_RTID
+#define MPHASE_BEGIN for (int tid = 0; tid < PITCH_NS * PITCH_THREADS; ++tid) { const int q = tid / PITCH_THREADS, t = tid % PITCH_THREADS; (void)q; (void)t;
 #define MPHASE_END }
 #endif
 #define PSM(qq) (sm + (qq) * SM_PITCH_TOTAL)
@@ -70,19 +68,8 @@ static_assert(PITCH_THREADS >= 96 && PITCH_THREADS % 32 == 0, "phases use local 
 #endif
 
 // a[q].ring == nullptr marks an absent stream (batch size not a multiple of PITCH_NS)
-HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot) {
+HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
   (void)T;
-  // `rot` (0..3) moves the narrow phases -- a few lanes of ONE warp working while the CTA waits -- to another warp of
-  // the CTA.  Co-resident CTAs run the phases in lock-step (same work, same start), and a warp's scheduler is its
-  // index modulo 4: without the rotation the lone warps of all five CTAs of an SM would share one scheduler while
-  // the other three idle.  Which thread does the work never changes a result.
-#if PITCH_NS < 3
-  rot = 0;
-#endif
-  const int rot_lanes = 32 * (rot & 3);
-  const int w_energy = 32 * (rot == 0 ? 1 : rot == 1 ? 2 : rot == 2 ? 4 : 5);   // not a stream's first warp (0, 3, 6, 9)
-  const int w_yy = 32 * (rot == 0 ? 2 : rot == 1 ? 4 : rot == 2 ? 1 : 7);
-  (void)w_energy; (void)w_yy;
   // -- append the new frame to the history ring (denoise.c:359-360; a ring instead of the memmove) and
   //    decimate by 2 straight from HBM/L2 (pitch.c:171-173).  The 480 ring slots being overwritten hold
   //    the oldest samples, which the decimation never reads: no hazard inside the phase.
@@ -91,20 +78,38 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
       const PitchArgs A = a[q];
       float *lp0 = PSM(q) + SM_LP0;
       const int H = PITCH_BUF_SIZE - FRAME_SIZE;
-      for (int j = t; j < FRAME_SIZE; j += PITCH_THREADS) {
-        int p = A.ring_base + H + j; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
-        A.ring[p] = A.xb[j];
+      // A thread's loads are issued in batches before their first use (5 frame samples; 3 x 3 history samples): the CTAs
+      // of an SM run this phase in lock-step, so nothing else hides an HBM / L2 round trip per loop iteration
+      // (14 exposed round trips per thread before, 4 now).
+      {
+        constexpr int NA = (FRAME_SIZE + PITCH_THREADS - 1) / PITCH_THREADS;
+        float v[NA];
+#pragma unroll
+        for (int u = 0; u < NA; u++) { const int j = t + u * PITCH_THREADS; v[u] = j < FRAME_SIZE ? ld_stream(A.xb + j) : 0.f; }
+#pragma unroll
+        for (int u = 0; u < NA; u++) {
+          const int j = t + u * PITCH_THREADS;
+          int p = A.ring_base + H + j; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
+          if (j < FRAME_SIZE) A.ring[p] = v[u];
+        }
       }
-      for (int i = t; i < LP_SIZE; i += PITCH_THREADS) {
-        const int k = 2 * i;
-        // sample k of the updated history: old ring part for k < 1248, this frame after that
-        const float c = k < H ? ring_at(A.ring, A.ring_base, k) : A.xb[k - H];
-        const float r = k + 1 < H ? ring_at(A.ring, A.ring_base, k + 1) : A.xb[k + 1 - H];
-        if (i) {
-          const float l = k - 1 < H ? ring_at(A.ring, A.ring_base, k - 1) : A.xb[k - 1 - H];
-          lp0[i] = .5f * (.5f * (l + r) + c);
-        } else {
-          lp0[i] = .5f * (.5f * r + c);
+      for (int i0 = t; i0 < LP_SIZE; i0 += 3 * PITCH_THREADS) {
+        float l[3], c[3], r[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+          const int i = i0 + u * PITCH_THREADS, k = 2 * i;
+          l[u] = c[u] = r[u] = 0.f;
+          if (i < LP_SIZE) {
+            // sample k of the updated history: old ring part for k < 1248, this frame after that
+            c[u] = k < H ? ld_global(A.ring + ring_pos(A.ring_base, k)) : ld_stream(A.xb + (k - H));
+            r[u] = k + 1 < H ? ld_global(A.ring + ring_pos(A.ring_base, k + 1)) : ld_stream(A.xb + (k + 1 - H));
+            if (i) l[u] = k - 1 < H ? ld_global(A.ring + ring_pos(A.ring_base, k - 1)) : ld_stream(A.xb + (k - 1 - H));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+          const int i = i0 + u * PITCH_THREADS;
+          if (i < LP_SIZE) lp0[i] = i ? .5f * (.5f * (l[u] + r[u]) + c[u]) : .5f * (.5f * r[u] + c[u]);
         }
       }
     }
@@ -112,8 +117,8 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
   // -- autocorrelation lags 0..4 (celt_lpc.c:92-174: first n-4 samples, then the tail): 5 lanes per
   //    stream, all streams packed into warp 0 (lane = 8 * stream + lag)
   MPHASE_BEGIN
-    if (rtid < 8 * PITCH_NS && (rtid & 7) < 5 && a[rtid >> 3].ring) {
-      const int qq = rtid >> 3, k = rtid & 7, fastN = LP_SIZE - 4;
+    if (tid < 8 * PITCH_NS && (tid & 7) < 5 && a[tid >> 3].ring) {
+      const int qq = tid >> 3, k = tid & 7, fastN = LP_SIZE - 4;
       const float *lp0 = PSM(qq) + SM_LP0;
 #if PITCH_CHAIN4
       const float s = dot_chain4(0.f, lp0, lp0 + k, fastN);
@@ -128,7 +133,7 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
     }
   MPHASE_END
   MPHASE_BEGIN
-    if (rtid < PITCH_NS && a[rtid].ring) lpc_taps(PSM(rtid) + SM_PITCH_END + MI_AC, PSM(rtid) + SM_PITCH_END + MI_NUM);
+    if (tid < PITCH_NS && a[tid].ring) lpc_taps(PSM(tid) + SM_PITCH_END + MI_AC, PSM(tid) + SM_PITCH_END + MI_NUM);
   MPHASE_END
   // -- 5-tap whitening FIR with zero history (celt_fir5, pitch.c:104-143)
   MPHASE_BEGIN
@@ -184,14 +189,14 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
       }
 #pragma unroll
       for (int c = 0; c < 5; c++) if (5 * t + c < 147) xc[5 * t + c] = acc[c];
-    } else if (tid >= w_energy && tid < w_energy + PITCH_NS && a[tid - w_energy].ring) {
-      float *sq = PSM(tid - w_energy);
+    } else if (tid >= 32 && tid < 32 + PITCH_NS && a[tid - 32].ring) {
+      float *sq = PSM(tid - 32);
       syy_running_inplace(sq + SM_SYY, sq_prefix(1.f, sq + SM_Y4, 240), 147);
     }
   MPHASE_END
   MPHASE_BEGIN
-    if (rtid < PITCH_NS && a[rtid].ring) {
-      float *sq = PSM(rtid);
+    if (tid < PITCH_NS && a[tid].ring) {
+      float *sq = PSM(tid);
       int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       Best2 b2; best2_init(b2);
       for (int i0 = 0; i0 < 147; i0 += 3) {   // 147 = 49 * 3: a block's inputs loaded together, then visited in order, branch-free
@@ -219,8 +224,8 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
   // -- fine search around the two coarse winners (pitch.c:344-361): 10 lanes per stream packed from
   //    lane 0 on; the energy chains of all streams in the lanes of another warp
   MPHASE_BEGIN
-    if (rtid < 10 * PITCH_NS && a[rtid / 10].ring) {
-      const int qq = rtid / 10, c = rtid % 10;
+    if (tid < 10 * PITCH_NS && a[tid / 10].ring) {
+      const int qq = tid / 10, c = tid % 10;
       float *sq = PSM(qq);
       const int *mi = (const int *)(sq + SM_PITCH_END + MI_INT);
       const int c0 = 2 * mi[0], c1 = 2 * mi[1];
@@ -238,8 +243,8 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
 #endif
         sq[SM_XC + i] = RMAX(-1, sum);
       }
-    } else if (rtid >= 64 && rtid < 64 + PITCH_NS && a[rtid - 64].ring) {
-      float *sq = PSM(rtid - 64);
+    } else if (tid >= 64 && tid < 64 + PITCH_NS && a[tid - 64].ring) {
+      float *sq = PSM(tid - 64);
       syy_running_inplace(sq + SM_SYY, sq_prefix(1.f, sq + SM_LP, 480), 294);
     }
   MPHASE_END
@@ -248,8 +253,8 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
   //    visit those in ascending order.  Each stream's other warps meanwhile square the samples the
   //    yy_lookup chain of rnn_remove_doubling will need (pitch.c:454): a[i-1] = x[-i]^2, yyl[i] := x[N-i]^2.
   MPHASE_BEGIN
-    if (rtid < PITCH_NS && a[rtid].ring) {
-      float *sq = PSM(rtid);
+    if (tid < PITCH_NS && a[tid].ring) {
+      float *sq = PSM(tid);
       const float *xc = sq + SM_XC, *syy = sq + SM_SYY;
       int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       const int c0 = 2 * mi[0], c1 = 2 * mi[1];
@@ -284,9 +289,9 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
   //    lanes 64..64+NS-1 of the CTA: the yy_lookup energy chains of all streams (pitch.c:450-456)
   MPHASE_BEGIN
     const int N = PITCH_FRAME_SIZE / 2;
-    if (tid >= w_yy && tid < w_yy + PITCH_NS) {
-      if (a[tid - w_yy].ring) {
-        float *sq = PSM(tid - w_yy);
+    if (tid >= 64 && tid < 64 + PITCH_NS) {
+      if (a[tid - 64].ring) {
+        float *sq = PSM(tid - 64);
         const float *x = sq + SM_LP + PITCH_MAX_PERIOD / 2;
         float *yyl = sq + SM_YYL;
         float yy = sq_prefix(0.f, x, N);   // == xx, summed in the same order (pitch.c:449-451)
@@ -331,8 +336,8 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
   // -- every candidate's pitch gain (pitch.c:458, 483-485: a double-precision sqrt and division each) is independent
   //    of the others: one lane per (stream, k), k = 1 (the initial candidate T0) .. 15; results in the dead xcorr array
   MPHASE_BEGIN
-    if (rtid < 15 * PITCH_NS && a[rtid % PITCH_NS].ring) {
-      const int qq = rtid % PITCH_NS, k = 1 + rtid / PITCH_NS;
+    if (tid < 15 * PITCH_NS && a[tid % PITCH_NS].ring) {
+      const int qq = tid % PITCH_NS, k = 1 + tid / PITCH_NS;
       float *sq = PSM(qq);
       const float *dot = sq + SM_DOT, *yyl = sq + SM_YYL;
       const int T0 = ((const int *)(sq + SM_PITCH_END + MI_INT))[4];
@@ -351,9 +356,9 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
   //    overwrites the running best and no threshold depends on an earlier acceptance, so walking k upwards with the
   //    gains at hand is the reference's loop.
   MPHASE_BEGIN
-    if (rtid < PITCH_NS && a[rtid].ring) {
-      const PitchArgs A = a[rtid];
-      float *sq = PSM(rtid);
+    if (tid < PITCH_NS && a[tid].ring) {
+      const PitchArgs A = a[tid];
+      float *sq = PSM(tid);
       const float *cg = sq + SM_XC, *cxy = sq + SM_XC + 16, *cyy = sq + SM_XC + 32;
       int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       const int T0 = mi[4], minperiod = PITCH_MIN_PERIOD / 2;
@@ -390,8 +395,8 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
   // -- the two refinement correlations around the chosen period (pitch.c:513-514: xcorr[k] = <x, x-(T+k-1)>, k = 0, 2;
   //    the centre lag was summed with the candidates in the same order) -- 2 instead of 30 speculative ones
   MPHASE_BEGIN
-    if (rtid < 2 * PITCH_NS && a[rtid % PITCH_NS].ring) {
-      const int qq = rtid % PITCH_NS, side = rtid / PITCH_NS;
+    if (tid < 2 * PITCH_NS && a[tid % PITCH_NS].ring) {
+      const int qq = tid % PITCH_NS, side = tid / PITCH_NS;
       float *sq = PSM(qq);
       const float *x = sq + SM_LP + PITCH_MAX_PERIOD / 2;
       const int Tb = ((const int *)(sq + SM_PITCH_END + MI_INT))[5];
@@ -408,9 +413,9 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T, int rot
   MPHASE_END
   // -- final offset (pitch.c:515-524) + state update (denoise.c:369-370)
   MPHASE_BEGIN
-    if (rtid < PITCH_NS && a[rtid].ring) {
-      const PitchArgs A = a[rtid];
-      float *sq = PSM(rtid);
+    if (tid < PITCH_NS && a[tid].ring) {
+      const PitchArgs A = a[tid];
+      float *sq = PSM(tid);
       const float *dot = sq + SM_DOT;
       int *mi = (int *)(sq + SM_PITCH_END + MI_INT);
       const int Tb = mi[5], kbest = mi[6];
@@ -444,10 +449,13 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   // -- X = FFT(window * [previous frame | this frame]) (denoise.c:332-339); the analysis window
   //    is the last 960 samples of the updated pitch history.
   PHASE_BEGIN
+    // asynchronous copies: a thread's 8 requests are in flight together (a load -> store loop pays one L2 / HBM
+    // round trip per iteration, and the CTAs of an SM reach this phase together)
     for (int i = tid; i < WINDOW_SIZE; i += nthr) {
       int p = a.ring_base + PITCH_BUF_SIZE - WINDOW_SIZE + i; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
-      win[i] = ld_stream(a.ring + p);
+      async_copy4(win + i, a.ring + p);
     }
+    async_wait_all();
   PHASE_END
   PHASE_BEGIN fft_stage1(F, win, nullptr, T, tid, nthr); PHASE_END
   PHASE_BEGIN
@@ -506,25 +514,25 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   // (the FFT buffer is dead from here on: the three warps that have nothing to do in this phase copy the 32 x 32 DCT
   //  table into it, so that the two DCTs at the end read shared memory instead of 32 dependent L1/L2 round trips)
   float *dct_sm = sm + SM_F;
-  PHASE_BEGIN const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
-    if (rt < NB_BANDS) {
-      float ex = band_finish(misc + SMI_BAND, rt);
-      float ep = band_finish(misc + SMI_BAND + 34, rt);
-      float exp_ = band_finish(misc + SMI_BAND + 68, rt);
+  PHASE_BEGIN
+    if (tid < NB_BANDS) {
+      float ex = band_finish(misc + SMI_BAND, tid);
+      float ep = band_finish(misc + SMI_BAND + 34, tid);
+      float exp_ = band_finish(misc + SMI_BAND + 68, tid);
       exp_ = (float)(exp_ / sqrt(.001 + ex * ep));
-      misc[SMI_E + rt] = ex; misc[SMI_E + 32 + rt] = ep; misc[SMI_E + 64 + rt] = exp_;
-      a.band_out[rt] = ex; a.band_out[32 + rt] = ep; a.band_out[64 + rt] = exp_;
+      misc[SMI_E + tid] = ex; misc[SMI_E + 32 + tid] = ep; misc[SMI_E + 64 + tid] = exp_;
+      a.band_out[tid] = ex; a.band_out[32 + tid] = ep; a.band_out[64 + tid] = exp_;
     } else {
-      for (int i = rt - NB_BANDS; i < NB_BANDS * NB_BANDS; i += nthr - NB_BANDS) dct_sm[i] = T->dct[i];
+      for (int i = tid - NB_BANDS; i < NB_BANDS * NB_BANDS; i += nthr - NB_BANDS) dct_sm[i] = T->dct[i];
     }
   PHASE_END
   // -- log-energy floor follower + silence test (denoise.c:380-393): the 32 log10() are independent
   //    (one lane each); only the follower itself is a serial chain.
-  PHASE_BEGIN const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
-    if (rt < NB_BANDS) misc[SMI_LY + rt] = (float)log10(1e-2 + misc[SMI_E + rt]);
+  PHASE_BEGIN
+    if (tid < NB_BANDS) misc[SMI_LY + tid] = (float)log10(1e-2 + misc[SMI_E + tid]);
   PHASE_END
-  PHASE_BEGIN const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
-    if (rt == 0) {
+  PHASE_BEGIN
+    if (tid == 0) {
       float logMax = -2, follow = -2, E = 0;
       // The reference evaluates follow - 1.5 and both maxima in double and rounds on the stores to ly[i] and follow
       // (denoise.c:384-386).  follow - 1.5 is exact in double (24-bit operands a few binades apart), rounding is
@@ -549,18 +557,18 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
     }
   PHASE_END
   // -- features (denoise.c:378-379, 391, 394-396)
-  PHASE_BEGIN const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
+  PHASE_BEGIN
     const int silent = mi[3];
-    if (rt < NB_BANDS) {
-      float v = dct_one_tab(misc + SMI_LY, rt, dct_sm);
-      if (rt == 0) v -= 12;
-      if (rt == 1) v -= 4;
-      a.features[rt] = silent ? 0.f : v;
-    } else if (rt < 2 * NB_BANDS) {
-      float v = dct_one_tab(misc + SMI_E + 64, rt - NB_BANDS, dct_sm);
-      a.features[rt] = silent ? 0.f : v;
-    } else if (rt == 2 * NB_BANDS) {
-      a.features[rt] = silent ? 0.f : (float)(.01 * (pitch_T - 300));
+    if (tid < NB_BANDS) {
+      float v = dct_one_tab(misc + SMI_LY, tid, dct_sm);
+      if (tid == 0) v -= 12;
+      if (tid == 1) v -= 4;
+      a.features[tid] = silent ? 0.f : v;
+    } else if (tid < 2 * NB_BANDS) {
+      float v = dct_one_tab(misc + SMI_E + 64, tid - NB_BANDS, dct_sm);
+      a.features[tid] = silent ? 0.f : v;
+    } else if (tid == 2 * NB_BANDS) {
+      a.features[tid] = silent ? 0.f : (float)(.01 * (pitch_T - 300));
     }
   PHASE_END
 }
@@ -629,16 +637,18 @@ struct SynthesisArgs {
   float *synthesis_mem;     // [480]
   float *out;               // [480] float PCM, or
   short *out_s16;           // [480] 16-bit PCM (non-null selects it): the C cast of examples/rnnoise_demo.c:58
-  int rot;                  // 0..3: which warp runs the one-warp phases (see pitch_streams)
 };
 
 // shared-memory plan of the synthesis CTA (floats)
 #define SS_X 0                        // [962] delayed X
-#define SS_P (SS_X + 2 * FREQ_SIZE)   // [800] bins 0..399 of the delayed P (the pitch filter's gain is 0 from bin 400 on)
+#define SS_P (SS_X + 2 * FREQ_SIZE)   // [800] bins 0..399 of the delayed P (the pitch filter's gain is 0 from bin 400 on); once P is dead,
+                                      //       the overlap memory is prefetched into its place
 #define SS_F (SS_P + 2 * 400)         // [1920] FFT buffer
 #define SS_V (SS_F + 2 * WINDOW_SIZE) // [6][34] band vectors: r, norm, g, sums...
 #define SS_TOTAL (SS_V + 6 * 34)
-// 3886 floats: 14 CTAs per SM (13 with all 481 bins of P resident), see SM_SPEC_TOTAL
+// 3886 floats: 14 CTAs per SM (13 with all 481 bins of P resident; measured r2j: 0.2900 -> 0.2875 ms per step at 4096
+// streams, 1.098 -> 1.095 at 16 384).  Prefetching the synthesis window next to the overlap memory would need 960
+// floats there and cost that 14th CTA; the window is a table every CTA reads (L1 / L2 hits).
 static_assert((SS_TOTAL * 4 + 1024) * 14 <= 228 * 1024, "synthesis kernel: 14 CTAs per SM");
 
 // rnn_pitch_filter (denoise.c:421-455), gain smoothing + interpolation (:479-493),
@@ -648,23 +658,24 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
   float *r = sm + SS_V, *sums = sm + SS_V + 34, *norm = sm + SS_V + 68, *g = sm + SS_V + 102;
   const int silent = a.silence[0];
   PHASE_BEGIN
+    // X (all bins) and bins 0..399 of P arrive by asynchronous copies, all of a thread's requests in flight together.
+    // The pitch filter's gain is 0 from bin 400 on (interp_band_gain leaves those bins at 0, denoise.c:140-154,
+    // 432-438): their update x += 0 * p is done here, with P's tail in registers, so that it need not stay resident --
+    // the same multiply and add as in the filter phase below.
+    static_assert(FREQ_SIZE - 400 <= DSP_THREADS, "one tail bin per thread");
+    int itail = -1;
+    cpx ptail; ptail.r = ptail.i = 0.f;
     for (int i = tid; i < FREQ_SIZE; i += nthr) {
-      cpx x, p;
-      x.r = ld_stream(a.spec_delayed + 2 * i); x.i = ld_stream(a.spec_delayed + 2 * i + 1);
-      p.r = ld_stream(a.spec_delayed + 2 * (FREQ_SIZE + i)); p.i = ld_stream(a.spec_delayed + 2 * (FREQ_SIZE + i) + 1);
-      if (i < 400) P[i] = p;
+      async_copy8(&X[i], a.spec_delayed + 2 * i);
+      if (i < 400) async_copy8(&P[i], a.spec_delayed + 2 * (FREQ_SIZE + i));
       else if (!silent) {
-        // the pitch filter of the bins the band interpolation leaves at gain 0 (denoise.c:140-154, 432-438), done here
-        // so that P's tail need not stay resident: the same multiply and add as in the filter phase below
-        x.r += 0.f * p.r;
-        x.i += 0.f * p.i;
+        itail = i;
+        ptail.r = ld_stream(a.spec_delayed + 2 * (FREQ_SIZE + i)); ptail.i = ld_stream(a.spec_delayed + 2 * (FREQ_SIZE + i) + 1);
       }
-      X[i] = x;
     }
-    const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
-    if (!silent && rt < NB_BANDS) {
-      const float Ex = a.band_delayed[rt], Ep = a.band_delayed[32 + rt], Exp = a.band_delayed[64 + rt];
-      const float gg = a.gains[rt];
+    if (!silent && tid < NB_BANDS) {
+      const float Ex = a.band_delayed[tid], Ep = a.band_delayed[32 + tid], Exp = a.band_delayed[64 + tid];
+      const float gg = a.gains[tid];
       float rr;
       if (Exp > gg) rr = 1;
       else {
@@ -675,7 +686,14 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       c = RMIN(1, c);
       rr = (float)sqrt((double)c);
       rr = (float)(rr * sqrt(Ex / (1e-8 + Ep)));
-      r[rt] = rr;
+      r[tid] = rr;
+    }
+    async_wait_all();   // a thread sees its own copies: the tail bin below was fetched by this thread
+    if (itail >= 0) {
+      cpx x = X[itail];
+      x.r += 0.f * ptail.r;
+      x.i += 0.f * ptail.i;
+      X[itail] = x;
     }
   PHASE_END
   if (!silent) {
@@ -692,22 +710,20 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       }
     PHASE_END
     PHASE_BEGIN
-      const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
-      if (rt < NB_BANDS + 2) sums[rt] = band_sum_pre(rt, sm + SS_F, 1, 400, T);
+        if (tid < NB_BANDS + 2) sums[tid] = band_sum_pre(tid, sm + SS_F, 1, 400, T);
     PHASE_END
     PHASE_BEGIN
-      const int rt = (tid + DSP_THREADS - 32 * (a.rot & 3)) % DSP_THREADS;
-      if (rt < NB_BANDS) {
-        float newE = band_finish(sums, rt);
-        norm[rt] = (float)sqrt(a.band_delayed[rt] / (1e-8 + newE));
+        if (tid < NB_BANDS) {
+        float newE = band_finish(sums, tid);
+        norm[tid] = (float)sqrt(a.band_delayed[tid] / (1e-8 + newE));
         // gain smoothing (denoise.c:479-487)
-        float gg = a.gains[rt];
-        float lg = a.lastg[rt];
+        float gg = a.gains[tid];
+        float lg = a.lastg[tid];
         float al = .6f * lg;
         gg = RMAX(gg, al);
-        double t = gg * (a.band_delayed[rt] + 1e-3) / (a.band_cur[rt] + 1e-3);
-        a.lastg[rt] = (float)RMIN(1.f, t);
-        g[rt] = gg;
+        double t = gg * (a.band_delayed[tid] + 1e-3) / (a.band_cur[tid] + 1e-3);
+        a.lastg[tid] = (float)RMIN(1.f, t);
+        g[tid] = gg;
       }
     PHASE_END
     PHASE_BEGIN
@@ -722,7 +738,7 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
     PHASE_END
   }
   // P is dead once the pitch filter has run: fetch the overlap memory into its place with asynchronous copies now, so
-  // that the output phase does not wait on HBM for it (the window is a table every CTA reads: L1 / L2 hits)
+  // that the output phase does not wait on HBM for it
   float *ola = sm + SS_P;
   const float *hw = T->half_window;
   PHASE_BEGIN

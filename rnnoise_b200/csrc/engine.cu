@@ -102,18 +102,6 @@ __global__ void __launch_bounds__(32) k_biquad(Arena a, const void *__restrict__
   if (s < r1) { a.hp_mem[2 * s] = m0; a.hp_mem[2 * s + 1] = m1; }
 }
 
-// Which warp of a DSP CTA runs its one-warp phases (dsp_stream.cuh pitch_streams `rot`; also spectrum / synthesis).  Blocks are handed to the SMs round
-// robin, so the co-resident CTAs of an SM are about gridDim-independent multiples of the SM count apart.
-__device__ __forceinline__ int warp_rotation() {
-#ifdef PITCH_NO_ROTATION
-  return 0;
-#else
-  unsigned nsm;
-  asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
-  return (int)((blockIdx.x / nsm) & 3);
-#endif
-}
-
 // grid = ceil(S / PITCH_NS), block = PITCH_NS * PITCH_THREADS, dynamic smem = PITCH_NS * SM_PITCH_TOTAL floats
 #ifndef PITCH_MIN_CTAS
 #define PITCH_MIN_CTAS (2048 / (PITCH_NS * PITCH_THREADS) < 20 ? 2048 / (PITCH_NS * PITCH_THREADS) : 20)   // 32 regs/thread
@@ -129,7 +117,7 @@ k_pitch(Arena a, const DspTables *__restrict__ T, int f, int r0, int r1) {
     g.xb = a.xb + ((size_t)(f & 1) * a.S + s) * FRAME_SIZE;
     g.ring = a.ring + (size_t)s * PITCH_BUF_SIZE;
     g.pitch_state = a.pitch_state + 2 * (size_t)s;
-    pitch_streams(sm, &g, T, 0);
+    pitch_streams(sm, &g, T);
   }
 #else
   __shared__ PitchArgs pa[PITCH_NS];
@@ -148,7 +136,7 @@ k_pitch(Arena a, const DspTables *__restrict__ T, int f, int r0, int r1) {
       pa[threadIdx.x] = g;
     }
     __syncthreads();
-    pitch_streams(sm, pa, T, warp_rotation());
+    pitch_streams(sm, pa, T);
   }
 #endif
 }
@@ -168,8 +156,11 @@ __global__ void __launch_bounds__(PG_THREADS, PG <= 8 ? 2 : 1) k_pitch2(Arena a,
   pitch_group(sm, g);
 }
 
+// 12 CTAs per SM = 40 registers per thread without spills.  The shared-memory plan would admit 14, but 32 registers
+// spill in the radix-5 stage and the pipelined step gets slower (r2j: 0.2900 -> 0.2965 ms at 4096 streams, 1.098 ->
+// 1.123 at 16 384) although a range's grid then is a single wave.
 #ifndef SPEC_MIN_BLOCKS
-#define SPEC_MIN_BLOCKS 14
+#define SPEC_MIN_BLOCKS 12
 #endif
 __global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena a, const DspTables *__restrict__ T, int f, int r0) {
   extern __shared__ float sm[];
@@ -184,7 +175,6 @@ __global__ void __launch_bounds__(DSP_THREADS, SPEC_MIN_BLOCKS) k_spectrum(Arena
   g.features = a.features + ((size_t)par * a.S + s) * NB_FEATURES;
   g.silence = a.silence + (size_t)par * a.S + s;
   g.lowpass = FREQ_SIZE;
-  g.rot = warp_rotation();
   spectrum_stream<false>(sm, g, T);
 }
 
@@ -211,7 +201,6 @@ __global__ void __launch_bounds__(DSP_THREADS) k_train_features(Arena a, const D
   g.features = io.rec + (size_t)s * TRAIN_RECORD;
   g.silence = a.silence + (size_t)par * a.S + s;
   g.lowpass = io.lowpass ? io.lowpass[s] : FREQ_SIZE;
-  g.rot = warp_rotation();
   spectrum_stream<true>(sm, g, T);
   TrainArgs t;
   t.clean = io.clean + (size_t)s * FRAME_SIZE;
@@ -241,7 +230,6 @@ __global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTab
   g.synthesis_mem = a.synth_mem + (size_t)s * FRAME_SIZE;
   g.out = out_s16 ? nullptr : (float *)out + (size_t)s * stride;
   g.out_s16 = out_s16 ? (short *)out + (size_t)s * stride : nullptr;
-  g.rot = warp_rotation();
   synthesis_stream(sm, g, T);
 }
 
@@ -296,7 +284,8 @@ struct B200Engine {
   int use_tc;                       // GRU kernel: 2 = k_tc2<true> (default), 1 = k_gru_tc, 0 = dp4a cross-check
   int conv2_tc;                     // conv2 kernel: 1 = k_tc2<false> (default), 0 = dp4a cross-check
   int pitch2;                       // pitch kernel: 1 = k_pitch2 (default), 0 = k_pitch (RNNOISE_B200_PITCH_KERNEL=v1 cross-check)
-  int heads_ns;                     // k_heads2<NS>: streams per thread, 2 (16 streams per CTA, default) or 4 ($RNNOISE_B200_HEADS_TILE=32)
+  int heads_ns;                     // k_heads2<NS, NW> tile: 1 = <1,4> 8 streams per CTA, 2 = <2,4> 16, 4 = <4,4> 32, 8 = <2,8> 32 streams on
+                                    // 8 compute warps ($RNNOISE_B200_HEADS_TILE = 8 | 16 | 32 | 32w)
   int heads2;                       // heads kernel: 1 = k_heads2 (default), 0 = k_heads (RNNOISE_B200_HEADS_KERNEL=cpasync)
   GruTcMaps tc_maps[2][3];          // [frame parity][layer]
   GruTcMaps conv_maps;              // x = c2in, wi = conv2 weights
@@ -619,10 +608,11 @@ extern "C" B200Engine *b200_engine_create_on(const B200HostModel *m, int S, int 
   ok = ok && cudaFuncSetAttribute(k_pitch2, cudaFuncAttributeMaxDynamicSharedMemorySize, PITCH2_SMEM_BYTES) == cudaSuccess;
   // streams per CTA of the heads kernel: 16 while the batch is small (twice the CTAs: lower latency), 32 once the GPU is
   // full (fewer, fatter CTAs disturb the other stages less: 4096 streams 0.3008 vs 0.3055 ms per step; 8: 0.3245)
-  { const char *ht = getenv("RNNOISE_B200_HEADS_TILE"); e->heads_ns = ht ? (!strcmp(ht, "32") ? 4 : !strcmp(ht, "8") ? 1 : 2) : device_streams >= 4096 ? 4 : 2; }
-  ok = ok && cudaFuncSetAttribute(k_heads2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<1>()) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(k_heads2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<4>()) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(k_heads2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<2>()) == cudaSuccess;
+  { const char *ht = getenv("RNNOISE_B200_HEADS_TILE"); e->heads_ns = ht ? (!strcmp(ht, "32w") ? 8 : !strcmp(ht, "32") ? 4 : !strcmp(ht, "8") ? 1 : 2) : device_streams >= 4096 ? 4 : 2; }
+  ok = ok && cudaFuncSetAttribute(k_heads2<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<1>()) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_heads2<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<4>()) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_heads2<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<2>()) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_heads2<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2_smem_bytes<2, 8>()) == cudaSuccess;
   const char *gk = getenv("RNNOISE_B200_GRU_KERNEL");
   e->use_tc = gk && !strcmp(gk, "dp4a") ? 0 : gk && !strcmp(gk, "tc1") && m->gru % 128 == 0 ? 1 : 2;
   if (ok && e->use_tc) {
@@ -887,11 +877,13 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
     float *uvad = d_vad ? d_vad + (size_t)R.r0 * e->vad_stride : nullptr;
     const int *silr = sil + R.r0;
     if (e->heads2 && e->heads_ns == 1)
-      CK(launch_pdl(k_heads2<1>, dim3((n + 7) / 8), dim3(160), h2_smem_bytes<1>(), stl, pdl_heads, n, e->dm, c2, g1, g2, g3, silr, gains, vad, uvad, e->vad_stride));
+      CK(launch_pdl(k_heads2<1, 4>, dim3((n + 7) / 8), dim3(160), h2_smem_bytes<1>(), stl, pdl_heads, n, e->dm, c2, g1, g2, g3, silr, gains, vad, uvad, e->vad_stride));
     else if (e->heads2 && e->heads_ns == 2)
-      CK(launch_pdl(k_heads2<2>, dim3((n + 15) / 16), dim3(160), h2_smem_bytes<2>(), stl, pdl_heads, n, e->dm, c2, g1, g2, g3, silr, gains, vad, uvad, e->vad_stride));
+      CK(launch_pdl(k_heads2<2, 4>, dim3((n + 15) / 16), dim3(160), h2_smem_bytes<2>(), stl, pdl_heads, n, e->dm, c2, g1, g2, g3, silr, gains, vad, uvad, e->vad_stride));
+    else if (e->heads2 && e->heads_ns == 8)
+      CK(launch_pdl(k_heads2<2, 8>, dim3((n + 31) / 32), dim3(288), h2_smem_bytes<2, 8>(), stl, pdl_heads, n, e->dm, c2, g1, g2, g3, silr, gains, vad, uvad, e->vad_stride));
     else if (e->heads2)
-      CK(launch_pdl(k_heads2<4>, dim3((n + 31) / 32), dim3(160), h2_smem_bytes<4>(), stl, pdl_heads, n, e->dm, c2, g1, g2, g3, silr, gains, vad, uvad, e->vad_stride));
+      CK(launch_pdl(k_heads2<4, 4>, dim3((n + 31) / 32), dim3(160), h2_smem_bytes<4>(), stl, pdl_heads, n, e->dm, c2, g1, g2, g3, silr, gains, vad, uvad, e->vad_stride));
     else
       CK(launch_pdl(k_heads, dim3((n + HEAD_TS - 1) / HEAD_TS), dim3(160), 0, stl, pdl_heads, n, e->dm, c2, g1, g2, g3, silr, gains, vad, uvad, e->vad_stride));
   }

@@ -5,15 +5,16 @@
 //   gains[32] = sigmoid(dense_out . cat + b)   each output one sequential FMA chain over K (sgemv, vec_avx.h:672)
 //   vad       = sigmoid(vad_dense . cat + b)   scalar loop: multiply, then add (vec_avx.h:731-735)
 //
-// CTA = 8 * NS streams, 160 threads.  Warps 0..3 each own 2 * NS streams x 32 outputs: a thread keeps NS streams x
-// 2 adjacent outputs = 2 * NS independent chains in registers, so one LDS.128 of activations and one LDS.64 of
-// weights feed 8 / NS FMAs.  NS = 4 (32 streams per CTA) has the best load : FMA ratio, NS = 2 (16 streams per
-// CTA, the default) launches twice the CTAs: a 2048-stream lane then covers 128 SMs instead of 64 and each
-// thread's chain work is halved -- the kernel is bound by the latency of its serial FMA chains, not by loads.  Warp 4 runs the 32 VAD chains (lane = stream) and is the producer: inputs and
-// weights arrive in chunks of 64 inputs (one 8 KB bulk copy of weights + 16-byte cp.async pieces of the
-// activation rows, all completing on one mbarrier) through an H2_STAGES-deep ring, so staging costs no
-// instructions on the compute warps.
-// grid = ceil(S / 32); dynamic smem = H2_STAGES * 17 KB.
+// CTA = 2 * NS * NW streams, NW compute warps + 1.  Compute warp w owns 2 * NS streams x 32 outputs: a thread keeps NS
+// streams x 2 adjacent outputs = 2 * NS independent chains in registers, so one LDS.128 of activations and one LDS.64
+// of weights feed 8 / NS FMAs.  The kernel is bound by the latency of its serial FMA chains, not by loads: with one
+// compute warp per scheduler (NW = 4) nothing hides a warp's shared-memory and dependent-issue stalls, so the
+// 32-stream tile comes in two shapes -- <4, 4> (8 chains per thread) and <2, 8> (4 chains per thread, two warps per
+// scheduler: same streams per CTA, same number of SMs taken, half the work per warp).  <2, 4> (16 streams per CTA)
+// launches twice the CTAs.  The last warp runs the VAD chains (lane = stream) and is the producer: inputs and
+// weights arrive in chunks of 64 inputs (16-byte cp.async pieces of the weight slab and of the activation rows, all
+// completing on one mbarrier) through an H2_STAGES-deep ring, so staging costs no instructions on the compute warps.
+// grid = ceil(S / TS); dynamic smem = H2_STAGES * (TS * 272 + 8192) B + 16 KB.
 #pragma once
 #include "gru_tc.cuh"
 
@@ -23,28 +24,27 @@
 #ifndef H2_STAGES
 #define H2_STAGES 6
 #endif
-template <int NS> struct H2StageT {
-  float xs[8 * NS][H2_XS];
+template <int TS> struct H2StageT {
+  float xs[TS][H2_XS];
   float ws[H2_KC][NB_GAINS];
 };
 #define H2_MAX_K 4096   // 4 * gru, gru <= 1024: the VAD weight vector is staged whole, once
-template <int NS> constexpr int h2_smem_bytes() { return H2_STAGES * (int)sizeof(H2StageT<NS>) + H2_MAX_K * 4 + 128; }
-#define H2_SMEM_BYTES h2_smem_bytes<4>()
+template <int NS, int NW = 4> constexpr int h2_smem_bytes() { return H2_STAGES * (int)sizeof(H2StageT<2 * NS * NW>) + H2_MAX_K * 4 + 128; }
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int NS>
-__global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *__restrict__ c2,
+template <int NS, int NW>
+__global__ void __launch_bounds__(32 * NW + 32) k_heads2(int S, DevModel m, const float *__restrict__ c2,
                                                 const float *__restrict__ g1, const float *__restrict__ g2,
                                                 const float *__restrict__ g3, const int *__restrict__ silence,
                                                 float *__restrict__ gains, float *__restrict__ vad,
                                                 float *__restrict__ vad_user, int vad_stride) {
   extern __shared__ __align__(128) uint8_t h2_smem[];
-  typedef H2StageT<NS> H2Stage;
-  constexpr int TS = 8 * NS;
+  constexpr int TS = 2 * NS * NW, NT = 32 * NW + 32;
+  typedef H2StageT<TS> H2Stage;
   H2Stage *st = (H2Stage *)h2_smem;
   float *wv_all = (float *)(h2_smem + H2_STAGES * sizeof(H2Stage));   // [4 * gru] vad_dense weights
   __shared__ __align__(8) uint64_t full[H2_STAGES];
@@ -56,11 +56,11 @@ __global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   pdl_trigger();
-  for (int i = tid; i < gru; i += 160) cp_async16(&wv_all[4 * i], m.vad_dense.w + 4 * i, true);   // 4 * gru floats
+  for (int i = tid; i < gru; i += NT) cp_async16(&wv_all[4 * i], m.vad_dense.w + 4 * i, true);   // 4 * gru floats
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   pdl_wait();   // GRU-3 state of this frame
   __syncthreads();
-  // producer (warp 4): chunk c -> stage c % H2_STAGES.  gru % 64 == 0, so a chunk never straddles two sources.
+  // producer (warp NW): chunk c -> stage c % H2_STAGES.  gru % 64 == 0, so a chunk never straddles two sources.
   // Everything travels as 16-byte cp.async pieces issued by the 32 lanes (activation rows of 256 B per stream into
   // the padded rows, the 8 KB weight slab): bulk copies cost ~0.5 us EACH on the SM's copy engine whatever their
   // size -- with two per chunk (weights + VAD weights) the kernel sat at 1.2 us per chunk, 29 us in all, for a
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *
     }
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
   };
-  if (warp == 4)
+  if (warp == NW)
     for (int c = 0; c < H2_STAGES - 1 && c < nchunk; c++) produce(c);
   float acc[NS][2];
 #pragma unroll
@@ -91,10 +91,10 @@ __global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *
   const int row0 = warp * (2 * NS) + (lane >> 4) * NS, o2 = (lane & 15) * 2;
   for (int c = 0; c < nchunk; c++) {
     const int buf = c % H2_STAGES;
-    if (warp == 4 && c + H2_STAGES - 1 < nchunk) produce(c + H2_STAGES - 1);   // that stage was released by the barrier ending chunk c-1
+    if (warp == NW && c + H2_STAGES - 1 < nchunk) produce(c + H2_STAGES - 1);   // that stage was released by the barrier ending chunk c-1
     mbar_wait(smem_u32(&full[buf]), (uint32_t)(c / H2_STAGES) & 1u);
     const H2Stage &b = st[buf];
-    if (warp < 4) {
+    if (warp < NW) {
 #pragma unroll 4
       for (int kk = 0; kk < H2_KC; kk += 4) {
         float4 x[NS];
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(160) k_heads2(int S, DevModel m, const float *
     }
     __syncthreads();   // everyone is done with this stage before the producer refills it
   }
-  if (warp < 4) {
+  if (warp < NW) {
     const float b0 = m.dense_out.bias[o2], b1 = m.dense_out.bias[o2 + 1];
 #pragma unroll
     for (int i = 0; i < NS; i++) {

@@ -55,7 +55,7 @@ void emu_analysis(void *p, const float *in, int nstreams) {
     pa[q].ring_base = (int)(((f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
     pa[q].pitch_state = s.pitch_state;
   }
-  pitch_streams(e->sm, pa, &e->T, (int)(f & 3));   // every warp rotation of the narrow phases gets exercised
+  pitch_streams(e->sm, pa, &e->T);
   for (int q = 0; q < nstreams; q++) {
     EmuStream &s = e->st[q];
     SpectrumArgs a;
@@ -67,7 +67,6 @@ void emu_analysis(void *p, const float *in, int nstreams) {
     a.features = s.features;
     a.silence = &s.silence;
     a.lowpass = FREQ_SIZE;
-    a.rot = (int)((f + q) & 3);
     spectrum_stream<false>(e->sm, a, &e->T);
   }
 }
@@ -89,7 +88,7 @@ void emu_train(void *p, const float *clean, const float *noisy, int nstreams, co
     pa[q].ring_base = (int)(((f + 1) * FRAME_SIZE) % PITCH_BUF_SIZE);
     pa[q].pitch_state = s.pitch_state;
   }
-  pitch_streams(e->sm, pa, &e->T, (int)((f + 1) & 3));
+  pitch_streams(e->sm, pa, &e->T);
   for (int q = 0; q < nstreams; q++) {
     EmuStream &s = e->st[q];
     SpectrumArgs a;
@@ -101,7 +100,6 @@ void emu_train(void *p, const float *clean, const float *noisy, int nstreams, co
     a.features = s.rec;
     a.silence = &s.silence;
     a.lowpass = lowpass[q];
-    a.rot = (int)((f + q + 1) & 3);
     spectrum_stream<true>(e->sm, a, &e->T);
     TrainArgs t;
     t.clean = clean + q * FRAME_SIZE;
@@ -147,7 +145,6 @@ void emu_synthesis(void *p, int q, const float *gains, float *out, float *lastg)
   a.synthesis_mem = s.synth_mem;
   a.out = out;
   a.out_s16 = nullptr;
-  a.rot = (int)((e->frames + q + 2) & 3);
   synthesis_stream(e->sm, a, &e->T);
   memcpy(lastg, s.lastg, sizeof(s.lastg));
 }
@@ -187,7 +184,6 @@ void emu_group_analysis(void *p, const float *in, int n, float *features, float 
     a.ring = e->ring[q]; a.ring_base = g.ring_base; a.pitch_state = e->pitch_state[q];
     a.spec_out = e->spec[q]; a.band_out = e->band[q]; a.features = e->features[q]; a.silence = &e->silence[q];
     a.lowpass = FREQ_SIZE;
-    a.rot = (int)((f + q) & 3);
     spectrum_stream<false>(e->sm, a, &e->T);
     memcpy(features + q * NB_FEATURES, e->features[q], sizeof(e->features[q]));
     int period; memcpy(&period, &e->pitch_state[q][0], 4);

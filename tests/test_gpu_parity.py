@@ -243,7 +243,7 @@ def test_gru_tensor_core_paths_equal_dp4a_path(rb, models_dir):
     a = rb.Batch(model, S)
     del os.environ["RNNOISE_B200_HEADS_KERNEL"]
     tiles = {}
-    for t in ("8", "16", "32"):           # streams per CTA of the register-tiled kernel (1, 2 or 4 streams per thread)
+    for t in ("8", "16", "32", "32w"):    # streams per CTA of the register-tiled kernel (1, 2 or 4 streams per thread on 4 compute warps; 2 on 8)
         os.environ["RNNOISE_B200_HEADS_TILE"] = t
         tiles[t] = rb.Batch(model, S)
     del os.environ["RNNOISE_B200_HEADS_TILE"]
