@@ -13,6 +13,9 @@
 #include <string.h>
 #include <vector>
 
+// NVTX v3 is header-only: the ranges cost a relaxed load each unless a tool (nsys, ncu --nvtx) is attached.
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/rnnoise.h"
 #include "dsp_stream.cuh"
 #include "dsp_pitch.cuh"
@@ -32,6 +35,20 @@
       return -1;                                                                          \
     }                                                                                     \
   } while (0)
+
+// Host-side trace ranges (SURVEY section 5 "tracing"): one per public engine call and one per pipeline stage of a frame
+// (front = biquad/pitch/spectrum enqueue, network, tail = heads/synthesis), so a timeline shows the enqueue cost of
+// every stage next to the kernels it launched.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define NVTX_SCOPE(name) NvtxRange nvtx_scope_(name)
+struct NvtxStages {   // consecutive ranges inside one function; closed on every return path
+  bool open = false;
+  void next(const char *name) { if (open) nvtxRangePop(); nvtxRangePushA(name); open = true; }
+  ~NvtxStages() { if (open) nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Per-stream state in HBM (all [S][len], stream-major so one CTA reads its stream contiguously)
@@ -779,6 +796,8 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   const int fr = frame_arg(e->frames);
   const int *sil = a.silence + (size_t)par * S;
   const float *feat = a.features + (size_t)par * S * NB_FEATURES;
+  NvtxStages nv;
+  nv.next("rnnoise_b200 frame: front (biquad, pitch, spectrum)");
   MARK();
   if (e->bq_frames > e->frames) {
     // the prefilter of this frame was issued ahead on the biquad streams (prefilter hint / pipelined
@@ -821,6 +840,7 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
   }
   TL(e, e->frames, TL_FRONT_END, FRONT(e->rg[0]));
   TL(e, e->frames, TL_BACK_START, st);
+  nv.next("rnnoise_b200 frame: network (conv1, conv2, GRU x3)");
   MARK();
   const int gts = (S + RNN_TS - 1) / RNN_TS;
   if (tsep)   // the tails of frame f-2 have read the states of this parity
@@ -864,6 +884,7 @@ static int frame_device_io(B200Engine *e, void *d_out, const void *d_in, float *
     }
   }
   if (tsep) CK(cudaEventRecord(e->ev_net[par], st));
+  nv.next("rnnoise_b200 frame: tail (heads, synthesis)");
   const bool pdl_heads = pdl && e->use_tc == 2 && !e->net_fused && !tsep && e->nr == 1;   // only the k_tc2 predecessors are PDL-aware
   for (int r = 0; r < e->nr; r++) {
     B200Engine::Range &R = e->rg[r];
@@ -945,6 +966,7 @@ extern "C" int b200_engine_prefilter_device(B200Engine *e, const float *d_in) {
 static int frame_host_async_io(B200Engine *e, void *out, const void *in, float *vad, int s16) {
   if (!e || !out || !in) return -1;
   if (e->bq_frames != e->frames) return -1;   // a device-side prefilter hint is pending: do not mix
+  NVTX_SCOPE("rnnoise_b200 host frame (H2D, frame, D2H enqueue)");
   CK(cudaSetDevice(e->device));
   const size_t n = (size_t)e->a.S * FRAME_SIZE * (s16 ? sizeof(short) : sizeof(float));
   const int slot = (int)(e->host_frames & 1), par = (int)(e->frames & 1);
@@ -987,6 +1009,7 @@ static int frames_device_io(B200Engine *e, void *d_out, const void *d_in, float 
   const size_t esz = s16 ? sizeof(short) : sizeof(float);
   const char *in = (const char *)d_in;
   char *out = (char *)d_out;
+  NVTX_SCOPE("rnnoise_b200 multi-frame call");
   e->io_stride = pcm_stride;
   e->vad_stride = vad_stride;
   int rc = 0;
@@ -1147,6 +1170,7 @@ extern "C" int b200_engine_frame_host(B200Engine *e, float *out, const float *in
 
 extern "C" int b200_engine_sync(B200Engine *e) {
   if (!e) return -1;
+  NVTX_SCOPE("rnnoise_b200 sync");
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->s_h2d));
   for (int r = 0; r < e->nr; r++) { CK(cudaStreamSynchronize(e->rg[r].s_bq)); CK(cudaStreamSynchronize(e->rg[r].s_front)); }
