@@ -29,7 +29,7 @@ HD void async_copy4(float *dst_shared, const float *src_global) {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
 #else
-  *dst_shared = *src_global;
+  __builtin_memcpy(dst_shared, src_global, 4);   // raw bytes (the band-edge table travels through this as shorts)
 #endif
 }
 HD void async_copy8(void *dst_shared, const void *src_global) {   // both 8-byte aligned
@@ -38,6 +38,15 @@ HD void async_copy8(void *dst_shared, const void *src_global) {   // both 8-byte
 #else
   ((float *)dst_shared)[0] = ((const float *)src_global)[0];
   ((float *)dst_shared)[1] = ((const float *)src_global)[1];
+#endif
+}
+// 16-byte variant (both addresses 16-byte aligned): a quarter of the instructions, and .cg keeps the streamed data out
+// of the small L1 these kernels leave beside their shared memory (the 4- and 8-byte forms only exist as .ca).
+HD void async_copy16(float *dst_shared, const float *src_global) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
+#else
+  dst_shared[0] = src_global[0]; dst_shared[1] = src_global[1]; dst_shared[2] = src_global[2]; dst_shared[3] = src_global[3];
 #endif
 }
 // Streaming loads / stores for the bulk per-stream arrays (spectra, ring, overlap memory, PCM): evict-first, so that
@@ -64,6 +73,13 @@ HD void st_stream(float *p, float v) {
   __stcs(p, v);
 #else
   *p = v;
+#endif
+}
+HD void st_stream2(float *p, float a, float b) {   // p 8-byte aligned
+#if defined(__CUDA_ARCH__)
+  __stcs((float2 *)p, make_float2(a, b));
+#else
+  p[0] = a; p[1] = b;
 #endif
 }
 HD void async_wait_all() {
@@ -125,11 +141,12 @@ struct DspTables {
 //   spectrum kernel
 #define SM_F 0                           // [1920] FFT work buffer (interleaved complex)
 #define SM_XS (SM_F + 2 * WINDOW_SIZE)   // [800] bins 0..399 of X kept for the X.P correlation (the band sums end at bin 400)
-#define SM_WIN (SM_XS + 2 * 400)         // [960] analysis window staged from the ring (coalesced); after the P
-                                         //       transform's first stage: per-bin terms |P|^2 [0,400), Re(X conj P) [400,800)
-#define SM_SPEC_END (SM_WIN + WINDOW_SIZE)
+#define SM_WIN (SM_XS + 2 * 400)         // [964] analysis window staged from the ring in 16-byte pieces (the pitch-lagged one starts
+                                         //       0..3 floats into the first piece); after the P transform's first stage: per-bin
+                                         //       terms |P|^2 [0,400), Re(X conj P) [400,800)
+#define SM_SPEC_END (SM_WIN + WINDOW_SIZE + 4)
 #define SM_MISC_SIZE 288                 // pitch kernel: small per-stream scalars / vectors after its plan (MI_*)
-#define SM_SPEC_MISC 208                 // spectrum kernel: its own, tighter misc block (SMI_*)
+#define SM_SPEC_MISC 228                 // spectrum kernel: its own, tighter misc block (SMI_*)
 #define SM_PITCH_TOTAL (SM_PITCH_END + SM_MISC_SIZE)
 #define SM_SPEC_TOTAL (SM_SPEC_END + SM_SPEC_MISC)   // 3888 floats = 15.2 KB (registers, not shared memory, set the CTAs per SM: engine.cu)
 // misc slots (float indices relative to the misc base)
@@ -141,6 +158,8 @@ struct DspTables {
 #define SMI_BAND 8   // [3][34] band sums (X, P, X.P)
 #define SMI_LY 8     // [32] log band energies -- written after the band sums are consumed, in their place
 #define SMI_E 112    // [3][32] Ex, Ep, Exp
+#define SMI_EBAND 208 // [34] shorts: band edges staged from the table (the band-sum lanes' loop bounds)
+static_assert(SM_WIN % 4 == 0 && SM_XS % 4 == 0 && SM_SPEC_END % 4 == 0 && SMI_LY % 4 == 0 && SMI_E % 4 == 0, "16-byte pieces / vector loads");
 static_assert(SM_LP0 + LP_SIZE <= SM_PITCH_END, "lp0 overlay");
 static_assert(SM_LP % 4 == 0 && SM_X4 % 4 == 0 && SM_Y4 % 4 == 0 && SM_SYY % 4 == 0 && (SM_LP + 384) % 4 == 0,
               "single-lane chains use 16-byte vector loads");
@@ -173,7 +192,9 @@ HD cpx csub(cpx a, cpx b) { cpx m; m.r = a.r - b.r; m.i = a.i - b.i; return m; }
 // its four inputs straight from `src` (kiss_fft.c:577-584 + kf_bfly4 m==1 branch :112-130).
 // Input element i of the transform is win(i) * src[i] (imag 0) when `herm` is null, or the
 // Hermitian extension of herm[0..480] (inverse_transform, denoise.c:200-211).
-HD void fft_stage1(cpx *F, const float *src, const cpx *herm, const DspTables *T, int tid, int nthr) {
+// `hw` = the half window (the table itself, or a copy a kernel staged into shared memory).
+HD void fft_stage1(cpx *F, const float *src, const cpx *herm, const DspTables *T, int tid, int nthr, const float *hw = nullptr) {
+  if (!hw) hw = T->half_window;
   for (int g = tid; g < 240; g += nthr) {
     int j0 = g / 48, j1 = (g / 16) % 3, j2 = (g / 4) % 4, j3 = g % 4;
     int base = j0 + 5 * j1 + 15 * j2 + 60 * j3;
@@ -187,7 +208,7 @@ HD void fft_stage1(cpx *F, const float *src, const cpx *herm, const DspTables *T
         else { v.r = herm[WINDOW_SIZE - i].r; v.i = -herm[WINDOW_SIZE - i].i; }
       } else {
         int wi = i < FRAME_SIZE ? i : WINDOW_SIZE - 1 - i;
-        v.r = src[i] * T->half_window[wi];
+        v.r = src[i] * hw[wi];
         v.i = 0.f;
       }
       a[q].r = T->fft_scale * v.r;
@@ -316,12 +337,33 @@ HD float band_sum_terms(int b, const float *t, const DspTables *T) {
 // Same sums again with the weights already applied by the parallel lanes: w[k * stride] = bin_frac[k] * t[k]
 // and w[k * stride + coff] = bin_cfrac[k] * t[k] (the very products of the loop above), which leaves one
 // shared-memory load + FADD per step on the serial lanes and no table load at all.
-HD float band_sum_pre(int b, const float *w, int stride, int coff, const DspTables *T) {
+// The sums are serial float chains of up to 83 terms on one lane each: the terms are loaded eight at a time (all in
+// flight together) and then added in order, so that a lane pays one shared-memory latency per eight steps instead of
+// one per step.  `eb` = band edges (the table, or a staged copy).
+HD float band_chain8(float sum, const float *p, int stride, int n) {
+  for (; n >= 8; n -= 8, p += 8 * stride) {
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) t[u] = p[u * stride];
+#pragma unroll
+    for (int u = 0; u < 8; u++) sum += t[u];
+  }
+  if (n >= 4) {
+    float t[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) t[u] = p[u * stride];
+#pragma unroll
+    for (int u = 0; u < 4; u++) sum += t[u];
+    n -= 4; p += 4 * stride;
+  }
+  for (; n > 0; n--, p += stride) sum += p[0];
+  return sum;
+}
+HD float band_sum_pre(int b, const float *w, int stride, int coff, const short *eb) {
   float sum = 0.f;
-  if (b >= 1)
-    for (int k = T->eband[b - 1]; k < T->eband[b]; k++) sum += w[k * stride];
-  if (b <= NB_BANDS)
-    for (int k = T->eband[b]; k < T->eband[b + 1]; k++) sum += w[k * stride + coff];
+  const int k1 = eb[b];
+  if (b >= 1) { const int k0 = eb[b - 1]; sum = band_chain8(sum, w + k0 * stride, stride, k1 - k0); }
+  if (b <= NB_BANDS) { const int k2 = eb[b + 1]; sum = band_chain8(sum, w + k1 * stride + coff, stride, k2 - k1); }
   return sum;
 }
 HD float bin_term(cpx a, cpx c) {

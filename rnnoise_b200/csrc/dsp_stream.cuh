@@ -446,25 +446,36 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   cpx *F = (cpx *)(sm + SM_F), *XS = (cpx *)(sm + SM_XS);
   float *win = sm + SM_WIN;
   const int pitch_T = ((const int *)a.pitch_state)[0];
+  short *eb = (short *)(misc + SMI_EBAND);
+  float *hws = sm + SM_XS;   // the half window, staged for the first transform (bins of X live here afterwards)
+  // the pitch-lagged window starts at ring position q0 (any alignment): it is fetched as the 241 aligned 16-byte pieces
+  // that cover it and read from `lag` floats into the staging buffer
+  int q0 = a.ring_base + PITCH_BUF_SIZE - WINDOW_SIZE - pitch_T;
+  if (q0 >= PITCH_BUF_SIZE) q0 -= PITCH_BUF_SIZE;
+  if (q0 < 0) q0 += PITCH_BUF_SIZE;
+  const int lag = q0 & 3;
   // -- X = FFT(window * [previous frame | this frame]) (denoise.c:332-339); the analysis window
   //    is the last 960 samples of the updated pitch history.
   PHASE_BEGIN
-    // asynchronous copies: a thread's 8 requests are in flight together (a load -> store loop pays one L2 / HBM
-    // round trip per iteration, and the CTAs of an SM reach this phase together)
-    for (int i = tid; i < WINDOW_SIZE; i += nthr) {
-      int p = a.ring_base + PITCH_BUF_SIZE - WINDOW_SIZE + i; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
-      async_copy4(win + i, a.ring + p);
+    // asynchronous 16-byte copies (ring base and window start are multiples of 4 floats; a piece never straddles the
+    // ring's end), all of a thread's requests in flight together, L1 bypassed; the half window and the band edges
+    // come along, so that stage 1 and the band sums read shared memory instead of waiting on the L2 for the tables
+    static_assert(PITCH_BUF_SIZE % 4 == 0 && FRAME_SIZE % 4 == 0 && (PITCH_BUF_SIZE - WINDOW_SIZE) % 4 == 0, "aligned pieces");
+    for (int c = tid; c < WINDOW_SIZE / 4; c += nthr) {
+      int p = a.ring_base + PITCH_BUF_SIZE - WINDOW_SIZE + 4 * c; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
+      async_copy16(win + 4 * c, a.ring + p);
     }
+    for (int c = tid; c < FRAME_SIZE / 4; c += nthr) async_copy16(hws + 4 * c, T->half_window + 4 * c);
+    if (tid < (NB_BANDS + 2) / 2) async_copy4((float *)eb + tid, (const float *)T->eband + tid);
     async_wait_all();
   PHASE_END
-  PHASE_BEGIN fft_stage1(F, win, nullptr, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_stage1(F, win, nullptr, T, tid, nthr, hws); PHASE_END
   PHASE_BEGIN
     // the staging buffer is dead until the second transform: start fetching the pitch-lagged window
     // into it now (asynchronous copies), so the ring's latency hides behind the first transform
-    for (int i = tid; i < WINDOW_SIZE; i += nthr) {
-      int p = a.ring_base + PITCH_BUF_SIZE - WINDOW_SIZE - pitch_T + i;
-      if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
-      async_copy4(win + i, a.ring + p);
+    for (int c = tid; c < WINDOW_SIZE / 4 + 1; c += nthr) {
+      int p = q0 - lag + 4 * c; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
+      async_copy16(win + 4 * c, a.ring + p);
     }
     fft_radix4(F, 4, 16, 60, T, tid, nthr);
   PHASE_END
@@ -476,12 +487,12 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
       cpx v = F[i];
       if (TRAIN && i >= a.lowpass) v.r = v.i = 0.f;
       if (i < 400) XS[i] = v;
-      st_stream(a.spec_out + 2 * i, v.r); st_stream(a.spec_out + 2 * i + 1, v.i);
+      st_stream2(a.spec_out + 2 * i, v.r, v.i);
     }
     async_wait_all();   // the lagged window is in `win` once this phase's barrier is passed
   PHASE_END
   // -- P = FFT(window * pitch_buf[768-T .. 768-T+960)) (denoise.c:371-374)
-  PHASE_BEGIN fft_stage1(F, win, nullptr, T, tid, nthr); PHASE_END
+  PHASE_BEGIN fft_stage1(F, win + lag, nullptr, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
@@ -489,7 +500,7 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_BEGIN
     for (int i = tid; i < FREQ_SIZE; i += nthr) {
       cpx v = F[i];
-      st_stream(a.spec_out + 2 * (FREQ_SIZE + i), v.r); st_stream(a.spec_out + 2 * (FREQ_SIZE + i) + 1, v.i);
+      st_stream2(a.spec_out + 2 * (FREQ_SIZE + i), v.r, v.i);
       if (i < 400) {
         // weighted per-bin terms of the three band sums (band_sum_pre), each pair written over the
         // complex value it came from (this thread's own slots) or into the dead window staging
@@ -506,15 +517,17 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_BEGIN
     if (tid < 3 * (NB_BANDS + 2)) {
       const int set = tid / (NB_BANDS + 2), b = tid % (NB_BANDS + 2);
-      misc[SMI_BAND + 34 * set + b] = set == 2 ? band_sum_pre(b, win, 1, 400, T)
-                                              : band_sum_pre(b, (const float *)(set == 0 ? XS : F), 2, 1, T);
+      misc[SMI_BAND + 34 * set + b] = set == 2 ? band_sum_pre(b, win, 1, 400, eb)
+                                              : band_sum_pre(b, (const float *)(set == 0 ? XS : F), 2, 1, eb);
     }
   PHASE_END
   // -- Ex, Ep, Exp (denoise.c:344,375-377)
-  // (the FFT buffer is dead from here on: the three warps that have nothing to do in this phase copy the 32 x 32 DCT
-  //  table into it, so that the two DCTs at the end read shared memory instead of 32 dependent L1/L2 round trips)
+  // (the FFT buffer is dead from here on: the 32 x 32 DCT table is fetched into it with asynchronous 16-byte copies --
+  //  no thread waits for them before the follower phase -- so that the two DCTs at the end read shared memory
+  //  instead of 32 dependent L1/L2 round trips)
   float *dct_sm = sm + SM_F;
   PHASE_BEGIN
+    for (int c = tid; c < NB_BANDS * NB_BANDS / 4; c += nthr) async_copy16(dct_sm + 4 * c, T->dct + 4 * c);
     if (tid < NB_BANDS) {
       float ex = band_finish(misc + SMI_BAND, tid);
       float ep = band_finish(misc + SMI_BAND + 34, tid);
@@ -522,8 +535,6 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
       exp_ = (float)(exp_ / sqrt(.001 + ex * ep));
       misc[SMI_E + tid] = ex; misc[SMI_E + 32 + tid] = ep; misc[SMI_E + 64 + tid] = exp_;
       a.band_out[tid] = ex; a.band_out[32 + tid] = ep; a.band_out[64 + tid] = exp_;
-    } else {
-      for (int i = tid - NB_BANDS; i < NB_BANDS * NB_BANDS; i += nthr - NB_BANDS) dct_sm[i] = T->dct[i];
     }
   PHASE_END
   // -- log-energy floor follower + silence test (denoise.c:380-393): the 32 log10() are independent
@@ -533,28 +544,52 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_END
   PHASE_BEGIN
     if (tid == 0) {
-      float logMax = -2, follow = -2, E = 0;
+      float logMax = -2, follow = -2;
       // The reference evaluates follow - 1.5 and both maxima in double and rounds on the stores to ly[i] and follow
       // (denoise.c:384-386).  follow - 1.5 is exact in double (24-bit operands a few binades apart), rounding is
       // monotonic -- float(max(a, b)) == max(float(a), float(b)) -- and the other operands are floats already, so the
       // same values come out of float arithmetic: follow - 1.5f is the single correct rounding of the exact
       // difference.  32 dependent steps of 3 float ops instead of conversions and FP64 ops on one thread
       // (tests/test_dsp_emulation.py holds this source against the literal double form).
-      for (int i = 0; i < NB_BANDS; i++) {
-        float ly = misc[SMI_LY + i];
-        const float f15 = follow - 1.5f;
-        const float m1 = RMAX(f15, ly);
-        const float lm7 = logMax - 7;
-        ly = RMAX(lm7, m1);
-        logMax = RMAX(logMax, ly);
-        follow = RMAX(f15, ly);
-        misc[SMI_LY + i] = ly;
-        E += misc[SMI_E + i];
+      // The chain runs on registers: 16 inputs per 16-byte vector loads, 16 steps, 16 outputs per vector stores (one
+      // shared-memory round trip per step made this phase 11 % of the CTA's lifetime, profiles/r2p).
+#pragma unroll
+      for (int hb = 0; hb < NB_BANDS; hb += 16) {
+        f4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = *(const f4 *)(misc + SMI_LY + hb + 4 * u);
+        float l[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
+                       v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          float ly = l[i];
+          const float f15 = follow - 1.5f;
+          const float m1 = RMAX(f15, ly);
+          const float lm7 = logMax - 7;
+          ly = RMAX(lm7, m1);
+          logMax = RMAX(logMax, ly);
+          follow = RMAX(f15, ly);
+          l[i] = ly;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          f4 o; o.x = l[4 * u]; o.y = l[4 * u + 1]; o.z = l[4 * u + 2]; o.w = l[4 * u + 3];
+          *(f4 *)(misc + SMI_LY + hb + 4 * u) = o;
+        }
       }
+    } else if (tid == 32) {
+      // the frame energy (denoise.c:387) is its own chain: a lane of another warp adds it beside the follower
+      float E = 0;
+      f4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = *(const f4 *)(misc + SMI_E + 4 * u);
+#pragma unroll
+      for (int u = 0; u < 8; u++) { E += v[u].x; E += v[u].y; E += v[u].z; E += v[u].w; }
       int silent = !TRAIN && E < 0.04;
       mi[3] = silent;
       a.silence[0] = TRAIN ? E < 0.1 : silent;
     }
+    async_wait_all();   // the DCT table is in shared memory once this phase's barrier is passed
   PHASE_END
   // -- features (denoise.c:378-379, 391, 394-396)
   PHASE_BEGIN
@@ -610,7 +645,7 @@ HD void train_targets_stream(float *sm, const TrainArgs a, const DspTables *T) {
     }
   PHASE_END
   PHASE_BEGIN
-    if (tid < NB_BANDS + 2) misc[SMI_BAND + tid] = band_sum_pre(tid, win, 1, 400, T);
+    if (tid < NB_BANDS + 2) misc[SMI_BAND + tid] = band_sum_pre(tid, win, 1, 400, T->eband);
   PHASE_END
   PHASE_BEGIN
     if (tid < NB_BANDS) {
@@ -658,20 +693,30 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
   float *r = sm + SS_V, *sums = sm + SS_V + 34, *norm = sm + SS_V + 68, *g = sm + SS_V + 102;
   const int silent = a.silence[0];
   PHASE_BEGIN
-    // X (all bins) and bins 0..399 of P arrive by asynchronous copies, all of a thread's requests in flight together.
+    // X (all bins) and bins 0..399 of P arrive by asynchronous copies, all of a thread's requests in flight together:
+    // 16-byte pieces (L1 bypassed) for bins 0..399 of X and bins 1..400 of P -- floats [0, 800) and [964, 1764) of the
+    // spectrum slot, which is laid out exactly like SS_X | SS_P (the last piece's second half, P bin 400, lands on the
+    // idle FFT buffer) -- and 8-byte pieces for the 81 tail bins of X and bin 0 of P.
     // The pitch filter's gain is 0 from bin 400 on (interp_band_gain leaves those bins at 0, denoise.c:140-154,
-    // 432-438): their update x += 0 * p is done here, with P's tail in registers, so that it need not stay resident --
-    // the same multiply and add as in the filter phase below.
-    static_assert(FREQ_SIZE - 400 <= DSP_THREADS, "one tail bin per thread");
+    // 432-438): their update x += 0 * p is done here by the thread that fetched the bin, with P's tail in registers, so
+    // that it need not stay resident -- the same multiply and add as in the filter phase below.
+    static_assert(FREQ_SIZE - 400 < DSP_THREADS, "one tail bin per thread, one more thread for bin 0 of P");
+    static_assert(SS_P == 2 * FREQ_SIZE && (SS_P + 2) % 4 == 0, "slot layout == shared layout; P bin 1 is 16-byte aligned");
+    for (int c = tid; c < 200; c += nthr) {
+      async_copy16(sm + SS_X + 4 * c, a.spec_delayed + 4 * c);
+      async_copy16(sm + SS_P + 2 + 4 * c, a.spec_delayed + SS_P + 2 + 4 * c);
+    }
     int itail = -1;
     cpx ptail; ptail.r = ptail.i = 0.f;
-    for (int i = tid; i < FREQ_SIZE; i += nthr) {
+    if (tid < FREQ_SIZE - 400) {
+      const int i = 400 + tid;
       async_copy8(&X[i], a.spec_delayed + 2 * i);
-      if (i < 400) async_copy8(&P[i], a.spec_delayed + 2 * (FREQ_SIZE + i));
-      else if (!silent) {
+      if (!silent) {
         itail = i;
         ptail.r = ld_stream(a.spec_delayed + 2 * (FREQ_SIZE + i)); ptail.i = ld_stream(a.spec_delayed + 2 * (FREQ_SIZE + i) + 1);
       }
+    } else if (tid == FREQ_SIZE - 400) {
+      async_copy8(&P[0], a.spec_delayed + 2 * FREQ_SIZE);
     }
     if (!silent && tid < NB_BANDS) {
       const float Ex = a.band_delayed[tid], Ep = a.band_delayed[32 + tid], Exp = a.band_delayed[64 + tid];
@@ -710,7 +755,7 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       }
     PHASE_END
     PHASE_BEGIN
-        if (tid < NB_BANDS + 2) sums[tid] = band_sum_pre(tid, sm + SS_F, 1, 400, T);
+        if (tid < NB_BANDS + 2) sums[tid] = band_sum_pre(tid, sm + SS_F, 1, 400, T->eband);
     PHASE_END
     PHASE_BEGIN
         if (tid < NB_BANDS) {
@@ -737,15 +782,20 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
       }
     PHASE_END
   }
-  // P is dead once the pitch filter has run: fetch the overlap memory into its place with asynchronous copies now, so
-  // that the output phase does not wait on HBM for it
-  float *ola = sm + SS_P;
-  const float *hw = T->half_window;
+  // P is dead once the pitch filter has run: fetch the overlap memory into its place with asynchronous copies now, and --
+  // X being dead once stage 1 has gathered it -- the synthesis window into X's place during the next phase, so that the
+  // output phase waits neither on HBM nor on the L2 for them (it was 30 % of this CTA's lifetime: four dependent
+  // round trips per thread for the window, profiles/r2p)
+  float *ola = sm + SS_P + 2;   // 16-byte aligned
+  float *hws = sm + SS_X;
   PHASE_BEGIN
-    for (int i = tid; i < FRAME_SIZE; i += nthr) async_copy4(ola + i, a.synthesis_mem + i);
+    for (int c = tid; c < FRAME_SIZE / 4; c += nthr) async_copy16(ola + 4 * c, a.synthesis_mem + 4 * c);
     fft_stage1(F, nullptr, X, T, tid, nthr);
   PHASE_END
-  PHASE_BEGIN fft_radix4(F, 4, 16, 60, T, tid, nthr); PHASE_END
+  PHASE_BEGIN
+    for (int c = tid; c < FRAME_SIZE / 4; c += nthr) async_copy16(hws + 4 * c, T->half_window + 4 * c);
+    fft_radix4(F, 4, 16, 60, T, tid, nthr);
+  PHASE_END
   PHASE_BEGIN fft_radix4(F, 16, 64, 15, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
   PHASE_BEGIN
@@ -753,16 +803,37 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
     async_wait_all();   // overlap memory + window are in shared memory once this phase's barrier is passed
   PHASE_END
   PHASE_BEGIN
-    for (int i = tid; i < FRAME_SIZE; i += nthr) {
-      // t[i] = 960 * y[(960 - i) % 960].re, windowed; out = first half + overlap memory
-      float t0 = WINDOW_SIZE * F[i ? WINDOW_SIZE - i : 0].r;
-      float t1 = WINDOW_SIZE * F[WINDOW_SIZE - (FRAME_SIZE + i)].r;   // index 480+i -> y[480-i]
-      t0 *= hw[i];
-      t1 *= hw[FRAME_SIZE - 1 - i];
-      const float o = t0 + ola[i];
-      if (a.out_s16) a.out_s16[i] = (short)(int)o;   // truncation toward zero, low 16 bits (x86 cvttss2si + narrowing)
-      else st_stream(a.out + i, o);
-      st_stream(a.synthesis_mem + i, t1);
+    // t[i] = 960 * y[(960 - i) % 960].re, windowed; out = first half + overlap memory.  A thread's operands are
+    // loaded for all of its samples first, then combined
+    // (two samples at a time: the kernel keeps 14 CTAs per SM with 36 registers per thread)
+    constexpr int NI = (FRAME_SIZE + DSP_THREADS - 1) / DSP_THREADS;
+    static_assert(NI % 2 == 0, "pairs");
+#pragma unroll
+    for (int u0 = 0; u0 < NI; u0 += 2) {
+      float y0[2], y1[2], w0[2], w1[2], ol[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int i = tid + (u0 + u) * DSP_THREADS, ii = i < FRAME_SIZE ? i : 0;
+        y0[u] = F[ii ? WINDOW_SIZE - ii : 0].r;
+        y1[u] = F[WINDOW_SIZE - (FRAME_SIZE + ii)].r;   // index 480+i -> y[480-i]
+        w0[u] = hws[ii];
+        w1[u] = hws[FRAME_SIZE - 1 - ii];
+        ol[u] = ola[ii];
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int i = tid + (u0 + u) * DSP_THREADS;
+        if (i < FRAME_SIZE) {
+          float t0 = WINDOW_SIZE * y0[u];
+          float t1 = WINDOW_SIZE * y1[u];
+          t0 *= w0[u];
+          t1 *= w1[u];
+          const float o = t0 + ol[u];
+          if (a.out_s16) a.out_s16[i] = (short)(int)o;   // truncation toward zero, low 16 bits (x86 cvttss2si + narrowing)
+          else st_stream(a.out + i, o);
+          st_stream(a.synthesis_mem + i, t1);
+        }
+      }
     }
   PHASE_END
 }

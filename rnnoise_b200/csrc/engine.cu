@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(DSP_THREADS) k_train_features(Arena a, const D
   train_targets_stream(sm, t, T);
 }
 
-__global__ void __launch_bounds__(DSP_THREADS) k_synthesis(Arena a, const DspTables *__restrict__ T,
+__global__ void __launch_bounds__(DSP_THREADS, 14) k_synthesis(Arena a, const DspTables *__restrict__ T,
                                                            void *__restrict__ out, int f, int out_s16, int stride, int r0) {
   extern __shared__ float sm[];
   const int s = r0 + blockIdx.x;
@@ -367,7 +367,21 @@ static int upload_q(B200Engine *e, DevLayerQ *d, const B200Layer *l) {
   d->scale = upload<float>(e, l->scale, l->nb_out);
   d->subias = upload<float>(e, l->subias, l->nb_out);
   d->diag = l->diag ? upload<float>(e, l->diag, l->nb_out) : nullptr;
+  d->packed = nullptr;
   return (d->wp && d->scale && d->subias && (!l->diag || d->diag)) ? 0 : -1;
+}
+// epilogue parameter records of one GRU layer (DevLayerQ::packed), from the host copies of its two matrices
+static int upload_gru_params(B200Engine *e, DevLayerQ *rec, const B200Layer *li, const B200Layer *lr, int gru) {
+  std::vector<float> p((size_t)gru * 16, 0.f);
+  for (int u = 0; u < gru; u++)
+    for (int g = 0; g < 3; g++) {
+      float *q = &p[(size_t)u * 16 + 4 * g];
+      q[0] = li->scale[g * gru + u]; q[1] = li->subias[g * gru + u];
+      q[2] = lr->scale[g * gru + u]; q[3] = lr->subias[g * gru + u];
+      p[(size_t)u * 16 + 12 + g] = lr->diag[g * gru + u];
+    }
+  rec->packed = upload<float>(e, p.data(), p.size());
+  return rec->packed ? 0 : -1;
 }
 static int upload_f(B200Engine *e, DevLayerF *d, const B200Layer *l) {
   d->w = upload<float>(e, l->wf, (size_t)l->nb_in * l->nb_out);
@@ -613,7 +627,8 @@ extern "C" B200Engine *b200_engine_create_on(const B200HostModel *m, int S, int 
   ok = ok && upload_f(e, &dm.conv1, &m->conv1) == 0 && upload_f(e, &dm.dense_out, &m->dense_out) == 0 &&
        upload_f(e, &dm.vad_dense, &m->vad_dense) == 0 && upload_q(e, &dm.conv2, &m->conv2) == 0;
   for (int k = 0; k < 3 && ok; k++)
-    ok = upload_q(e, &dm.gru_in[k], &m->gru_in[k]) == 0 && upload_q(e, &dm.gru_rec[k], &m->gru_rec[k]) == 0;
+    ok = upload_q(e, &dm.gru_in[k], &m->gru_in[k]) == 0 && upload_q(e, &dm.gru_rec[k], &m->gru_rec[k]) == 0 &&
+         m->gru_rec[k].diag && upload_gru_params(e, &dm.gru_rec[k], &m->gru_in[k], &m->gru_rec[k], m->gru) == 0;
   // tensor-core GRU path: permuted weights + TMA maps for both frame parities
   // RNNOISE_B200_GRU_KERNEL = tc2 (default: persistent pipelined tcgen05) | tc1 (one tile per CTA) |
   // dp4a (CUDA-core cross-check); all three produce identical bits
@@ -700,6 +715,7 @@ extern "C" B200Engine *b200_engine_create_on(const B200HostModel *m, int S, int 
         nm.x[l + 1] = mp.x; nm.h[l + 1] = mp.h; nm.wi[l + 1] = mp.wi; nm.wr[l + 1] = mp.wr;
         np.scale_i[l + 1] = dm.gru_in[l].scale; np.subias_i[l + 1] = dm.gru_in[l].subias;
         np.scale_r[l + 1] = dm.gru_rec[l].scale; np.subias_r[l + 1] = dm.gru_rec[l].subias; np.diag[l + 1] = dm.gru_rec[l].diag;
+        np.packed[l + 1] = dm.gru_rec[l].packed;
         np.h_old[l + 1] = a.hbuf + ((size_t)(par ^ 1) * 3 + l) * hs;
         np.out_f32[l + 1] = a.hbuf + ((size_t)par * 3 + l) * hs;
         np.out_u8[l + 1] = a.hbuf_u8 + ((size_t)par * 3 + l) * hs8;

@@ -238,11 +238,11 @@ k_gru_tc(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, D
 //
 //   kGru = true : one GRU layer (k_gru_tc2).   kGru = false: conv2 (k_conv2_tc), a single GEMM + tanh.
 //
-// CTA = 128 streams x (N/4) output units, processed as slices of 16 units through a three-deep TMA ring
-// for the weight slices and a two-deep TMEM ring for the accumulators:
+// CTA = 128 streams x (N/4) output units, processed as slices of 16 units through a two-deep TMA ring
+// (TC2_STAGES) for the weight slices and a two-deep TMEM ring for the accumulators:
 //     warp 16 (one elected thread): TMA producer + tcgen05.mma issuer
 //     warps 0..15 (512 threads)   : epilogue -- warp w reads TMEM lane quarter (w & 3), units 4*(w>>2)..+4
-// so that  TMA(slice s+2) || MMA(slice s+1) || epilogue(slice s).  The u8 activation tiles (128 x K;
+// so that  TMA / MMA(slice s+1) || epilogue(slice s).  The u8 activation tiles (128 x K;
 // GRU: Xu8 and Hu8) are loaded once per CTA and stay resident.  Per slice and matrix one
 // tcgen05.mma.kind::i8 chain of K/32 instructions, M128 x N48 (GRU: z|r|n of 16 units) or N16 (conv2);
 // accumulators: GRU [in z|r|n (48) | rec z|r|n (48)] = 96 TMEM columns per stage, conv2 16.
@@ -251,7 +251,17 @@ k_gru_tc(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, D
 // ================================================================================================
 #define P_SLICE 16
 #ifndef P_STAGES
-#define P_STAGES 3
+#define P_STAGES 3                        // weight ring of the fused network kernel (net_kernel.cuh)
+#endif
+// Weight ring of the per-layer kernels: TWO stages.  The epilogue of a slice (2.7 us) is far longer than a slice's TMA +
+// MMAs, so the third stage never ran ahead usefully, while its 37 KB are what lets three CTAs of the DSP kernels share
+// an SM with a GRU CTA (same-box A/B at 4096 streams, profiles/r2p: 0.2804 -> 0.2775 ms per step, twice).
+#ifndef TC2_STAGES
+#define TC2_STAGES 2
+#endif
+// How many slices ahead the epilogue fetches the old state (1 or 2; 2 costs 8 registers per thread)
+#ifndef TC2_HAHEAD
+#define TC2_HAHEAD 2
 #endif
 #define P_TMEM_COLS 256                   // >= 2 stages x 96 columns, power of two
 
@@ -265,7 +275,7 @@ template <bool kGru> struct TcCfg {
 template <bool kGru>
 __host__ __device__ constexpr int tc2_smem_bytes(int K, int N) {
   return 1024 + TcCfg<kGru>::kMats * (K / TC_KATOM) * TC_A_ATOM_BYTES +
-         P_STAGES * TcCfg<kGru>::kMats * (K / TC_KATOM) * TcCfg<kGru>::kBAtom + TcCfg<kGru>::kPrm * (N / 4) * 4 + 16 * 8 + 64;
+         TC2_STAGES * TcCfg<kGru>::kMats * (K / TC_KATOM) * TcCfg<kGru>::kBAtom + TcCfg<kGru>::kPrm * (N / 4) * 4 + 16 * 8 + 64;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -301,7 +311,7 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
   uint8_t *sAx = base, *sAh = sAx + natoms * TC_A_ATOM_BYTES;
   uint8_t *sB = sAx + C::kMats * natoms * TC_A_ATOM_BYTES;
   const int stage_bytes = C::kMats * natoms * C::kBAtom;
-  float *prm = (float *)(sB + P_STAGES * stage_bytes);            // [kPrm][upc]
+  float *prm = (float *)(sB + TC2_STAGES * stage_bytes);            // [kPrm][upc]
   uint64_t *bars = (uint64_t *)(prm + C::kPrm * upc);
   uint32_t *tmem_slot = (uint32_t *)(bars + 16);
   const uint32_t bar_a = smem_u32(&bars[0]);
@@ -315,7 +325,7 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
   // they overlap the TMEM allocation and the (scattered) parameter staging below instead of following them (the
   // other threads touch the barriers only after the __syncthreads that ends the prologue).
   auto load_B0 = [&](int s) {
-    const int st = s % P_STAGES;
+    const int st = s % TC2_STAGES;
     uint8_t *dst = sB + st * stage_bytes;
     const int row = (blockIdx.y * nslice + s) * C::kN;
     mbar_expect_tx(bar_bfull(st), (uint32_t)stage_bytes);
@@ -326,36 +336,35 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
   };
   if (warp == P_EPI_WARPS && lane == 0) {
     mbar_init(bar_a, 1);
-    for (int i = 0; i < P_STAGES; i++) { mbar_init(bar_bfull(i), 1); mbar_init(bar_bempty(i), 1); }
+    for (int i = 0; i < TC2_STAGES; i++) { mbar_init(bar_bfull(i), 1); mbar_init(bar_bempty(i), 1); }
     for (int i = 0; i < 2; i++) { mbar_init(bar_tfull(i), 1); mbar_init(bar_tempty(i), P_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int s = 0; s < P_STAGES && s < nslice; s++) load_B0(s);   // weights: independent of the previous kernel
+    // first what the first slice needs (its weights, then the operand tiles), then the second weight stage: every CTA
+    // of the grid starts here at the same time and the burst is bound by L2 bandwidth (17 MB at 4096 streams)
+    load_B0(0);                                                    // weights: independent of the previous kernel
     pdl_wait();                                                    // activations of this frame are complete
     mbar_expect_tx(bar_a, (uint32_t)(C::kMats * natoms * TC_A_ATOM_BYTES));
     for (int a = 0; a < natoms; a++) {
       tma_load_2d(smem_u32(sAx + a * TC_A_ATOM_BYTES), &maps.x, bar_a, a * TC_KATOM, m0);
       if (kGru) tma_load_2d(smem_u32(sAh + a * TC_A_ATOM_BYTES), &maps.h, bar_a, a * TC_KATOM, m0);
     }
+    for (int s = 1; s < TC2_STAGES && s < nslice; s++) load_B0(s);
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < C::kPrm * upc; i += blockDim.x) {
-    if (kGru) {
-      // per unit u: {sc_i, sb_i, sc_r, sb_r} for z, r, n, then {diag_z, diag_r, diag_n, 0}: four LDS.128
-      const int u = i >> 4, c = i & 15;
-      float v = 0.f;
-      if (c < 12) {
-        const int g = c >> 2, w = c & 3;
-        v = (w == 0 ? wi.scale : w == 1 ? wi.subias : w == 2 ? wr.scale : wr.subias)[g * N + jq + u];
-      } else if (c < 15) {
-        v = wr.diag[(c - 12) * N + jq + u];
-      }
-      prm[i] = v;
-    } else {
-      prm[i] = (i < upc ? wi.scale : wi.subias)[jq + i % upc];
-    }
+  if (kGru) {
+    // per unit u: {sc_i, sb_i, sc_r, sb_r} for z, r, n, then {diag_z, diag_r, diag_n, 0} (four LDS.128 in the epilogue):
+    // this CTA's slice of the layer's packed records (DevLayerQ::packed) is contiguous -- 16-byte asynchronous copies
+    // issued by the epilogue warps, which wait for them only right before their first slice (the three dependent
+    // scattered loads per thread of the earlier staging loop were 8-14 % of this kernel's warp time, profiles/r2p)
+    const float *src = wr.packed + (size_t)jq * 16;
+    if (warp < P_EPI_WARPS)
+      for (int c = tid; c < 4 * upc; c += 32 * P_EPI_WARPS) cp_async16(prm + 4 * c, src + 4 * c, true);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  } else {
+    for (int i = tid; i < C::kPrm * upc; i += blockDim.x) prm[i] = (i < upc ? wi.scale : wi.subias)[jq + i % upc];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -365,7 +374,7 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
   if (warp == P_EPI_WARPS) {
     if (lane == 0) {
       auto load_B = [&](int s) {
-        const int st = s % P_STAGES;
+        const int st = s % TC2_STAGES;
         uint8_t *dst = sB + st * stage_bytes;
         const int row = (blockIdx.y * nslice + s) * C::kN;
         mbar_expect_tx(bar_bfull(st), (uint32_t)stage_bytes);
@@ -377,8 +386,8 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
       mbar_wait(bar_a, 0);   // (weights and operand tiles were requested in the prologue)
       const uint32_t idesc = umma_idesc_i8(TC_M, C::kN);
       for (int s = 0; s < nslice; s++) {
-        const int st = s % P_STAGES, ts = s & 1;
-        mbar_wait(bar_bfull(st), (uint32_t)((s / P_STAGES) & 1));
+        const int st = s % TC2_STAGES, ts = s & 1;
+        mbar_wait(bar_bfull(st), (uint32_t)((s / TC2_STAGES) & 1));
         mbar_wait(bar_tempty(ts), (uint32_t)(((s >> 1) & 1) ^ 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint8_t *Bs = sB + st * stage_bytes;
@@ -394,9 +403,9 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
         }
         umma_commit(bar_bempty(st));   // weight stage reusable once these MMAs retire
         umma_commit(bar_tfull(ts));    // accumulators of slice s ready for the epilogue
-        if (s >= 1 && s - 1 + P_STAGES < nslice) {   // refill the stage slice s-1 used
-          mbar_wait(bar_bempty((s - 1) % P_STAGES), (uint32_t)(((s - 1) / P_STAGES) & 1));
-          load_B(s - 1 + P_STAGES);
+        if (s >= 1 && s - 1 + TC2_STAGES < nslice) {   // refill the stage slice s-1 used
+          mbar_wait(bar_bempty((s - 1) % TC2_STAGES), (uint32_t)(((s - 1) / TC2_STAGES) & 1));
+          load_B(s - 1 + TC2_STAGES);
         }
       }
     }
@@ -406,7 +415,7 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
     const bool live = srow < S;
     const bool silent = live ? silence[srow] != 0 : true;
     const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
-    float hcur[P_UPT], hnext[P_UPT];
+    float hcur[P_UPT], hnext[P_UPT], hnext2[P_UPT];   // old state: fetched two slices ahead (a strided 16-byte gather from HBM)
     auto load_h = [&](int s, float (&dst)[P_UPT]) {
       if (kGru && live && s < nslice) {
         float4 a = __ldg((const float4 *)&h_old[(size_t)srow * N + jq + s * P_SLICE + ch * P_UPT]);
@@ -417,9 +426,14 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
       }
     };
     load_h(0, hcur);
+    if (TC2_HAHEAD == 2) load_h(1, hnext);
+    if (kGru) {   // the parameter records requested in the prologue: own copies landed, then visible to all epilogue warps
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");
+    }
     for (int s = 0; s < nslice; s++) {
       const int ts = s & 1;
-      load_h(s + 1, hnext);
+      if (TC2_HAHEAD == 2) load_h(s + 2, hnext2); else load_h(s + 1, hnext);
       mbar_wait(bar_tfull(ts), (uint32_t)((s >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t t0 = trow + ts * C::kCols + ch * P_UPT;
@@ -476,7 +490,7 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
         *(uint32_t *)&out_u8[(size_t)srow * ldo + jq + ub] = quant4(outv[0], outv[1], outv[2], outv[3]);
       }
 #pragma unroll
-      for (int q = 0; q < P_UPT; q++) hcur[q] = hnext[q];
+      for (int q = 0; q < P_UPT; q++) { hcur[q] = hnext[q]; if (TC2_HAHEAD == 2) hnext[q] = hnext2[q]; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }

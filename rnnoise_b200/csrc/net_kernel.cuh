@@ -35,6 +35,7 @@ struct NetMaps {       // TMA descriptors of one frame parity
 struct NetPtrs {
   const float *scale_i[NET_LAYERS], *subias_i[NET_LAYERS];   // input matrix (conv2: the only matrix)
   const float *scale_r[NET_LAYERS], *subias_r[NET_LAYERS], *diag[NET_LAYERS];
+  const float *packed[NET_LAYERS];    // GRU layers: DevLayerQ::packed, [N][16] epilogue parameter records
   const float *h_old[NET_LAYERS];     // fp32 state of the previous frame (GRU layers)
   float *out_f32[NET_LAYERS];         // conv2_out / new fp32 state
   uint8_t *out_u8[NET_LAYERS];        // their u8 operand mirrors
@@ -97,21 +98,14 @@ k_net(int S, int Kc, int Kn, int N, const __grid_constant__ NetMaps maps, const 
   }
   // epilogue parameters of this CTA's unit quarter, all layers
   for (int i = tid; i < 2 * upc; i += blockDim.x) prm[i] = (i < upc ? p.scale_i[0] : p.subias_i[0])[jq + i % upc];
+  // GRU layers: this CTA's unit slice of the packed parameter records, contiguous in memory and in shared memory:
+  // 16-byte asynchronous copies, all in flight together (six dependent scattered loads per thread before)
   for (int L = 1; L < NET_LAYERS; L++) {
     float *pl = prm + 2 * upc + (L - 1) * 16 * upc;
-    for (int i = tid; i < 16 * upc; i += blockDim.x) {
-      // per unit u: {sc_i, sb_i, sc_r, sb_r} for z, r, n, then {diag_z, diag_r, diag_n, 0}: four LDS.128
-      const int u = i >> 4, c = i & 15;
-      float v = 0.f;
-      if (c < 12) {
-        const int g = c >> 2, w = c & 3;
-        v = (w == 0 ? p.scale_i[L] : w == 1 ? p.subias_i[L] : w == 2 ? p.scale_r[L] : p.subias_r[L])[g * N + jq + u];
-      } else if (c < 15) {
-        v = p.diag[L][(c - 12) * N + jq + u];
-      }
-      pl[i] = v;
-    }
+    const float *src = p.packed[L] + (size_t)jq * 16;
+    for (int c = tid; c < 4 * upc; c += blockDim.x) cp_async16(pl + 4 * c, src + 4 * c, true);
   }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -156,7 +156,14 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // Device-resident model (built by engine.cu from the parsed blob).
 struct DevLayerF { const float *w, *bias; };                               // w[in][out]
-struct DevLayerQ { const int *wp; const float *scale, *subias, *diag; };   // wp[in/4][out] packed s8x4
+struct DevLayerQ {
+  const int *wp;                          // wp[in/4][out] packed s8x4
+  const float *scale, *subias, *diag;
+  // recurrent GRU matrices only: the epilogue parameters of the LAYER, one 64-byte record per unit in the order the
+  // tensor-core epilogues read them -- {scale_in, subias_in, scale_rec, subias_rec} for z, r, n, then {diag_z, diag_r,
+  // diag_n, 0} -- so that a CTA stages its unit slice with contiguous 16-byte asynchronous copies
+  const float *packed;                    // [gru][16]
+};
 struct DevModel {
   int cond, gru;
   DevLayerF conv1, dense_out, vad_dense;
