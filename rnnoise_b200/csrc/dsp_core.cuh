@@ -138,6 +138,9 @@ struct DspTables {
 #define SM_YYL (SM_SYY + 296)            // [392] yy_lookup
 #define SM_DOT (SM_YYL + 392)            // [64]  remove_doubling dot products
 #define SM_PITCH_END (SM_DOT + 64)
+#define SM_LP0N (SM_LP0 + LP_SIZE)       // [864] k_pitch: the decimated signal before whitening lives behind the raw history that
+                                         //       lp | lp0 stage at first -- over the (then idle) tail of the search scratch and
+                                         //       the first 52 floats of the misc block, whose slots (MI_*) start at 64
 //   spectrum kernel
 #define SM_F 0                           // [1920] FFT work buffer (interleaved complex)
 #define SM_XS (SM_F + 2 * WINDOW_SIZE)   // [800] bins 0..399 of X kept for the X.P correlation (the band sums end at bin 400)
@@ -150,9 +153,9 @@ struct DspTables {
 #define SM_PITCH_TOTAL (SM_PITCH_END + SM_MISC_SIZE)
 #define SM_SPEC_TOTAL (SM_SPEC_END + SM_SPEC_MISC)   // 3888 floats = 15.2 KB (registers, not shared memory, set the CTAs per SM: engine.cu)
 // misc slots (float indices relative to the misc base)
-#define MI_AC 0     // [5] autocorrelation
-#define MI_NUM 8    // [5] whitening FIR taps
-#define MI_INT 16   // ints: [0]=best0 [1]=best1 [2]=T (pitch index) [3]=silence [4]=T0 half-rate [5]=Tb [6]=kbest
+#define MI_AC 64    // [5] autocorrelation
+#define MI_NUM 72   // [5] whitening FIR taps
+#define MI_INT 80   // ints: [0]=best0 [1]=best1 [2]=T (pitch index) [3]=silence [4]=T0 half-rate [5]=Tb [6]=kbest
 // spectrum kernel's misc block
 #define SMI_INT 0    // ints: [3]=silence
 #define SMI_BAND 8   // [3][34] band sums (X, P, X.P)
@@ -161,6 +164,7 @@ struct DspTables {
 #define SMI_EBAND 208 // [34] shorts: band edges staged from the table (the band-sum lanes' loop bounds)
 static_assert(SM_WIN % 4 == 0 && SM_XS % 4 == 0 && SM_SPEC_END % 4 == 0 && SMI_LY % 4 == 0 && SMI_E % 4 == 0, "16-byte pieces / vector loads");
 static_assert(SM_LP0 + LP_SIZE <= SM_PITCH_END, "lp0 overlay");
+static_assert(SM_LP0N % 4 == 0 && SM_LP0N + LP_SIZE <= SM_PITCH_END + 64, "k_pitch: decimated signal ends before the misc slots");
 static_assert(SM_LP % 4 == 0 && SM_X4 % 4 == 0 && SM_Y4 % 4 == 0 && SM_SYY % 4 == 0 && (SM_LP + 384) % 4 == 0,
               "single-lane chains use 16-byte vector loads");
 

@@ -70,47 +70,40 @@ static_assert(PITCH_THREADS >= 96 && PITCH_THREADS % 32 == 0, "phases use local 
 // a[q].ring == nullptr marks an absent stream (batch size not a multiple of PITCH_NS)
 HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
   (void)T;
-  // -- append the new frame to the history ring (denoise.c:359-360; a ring instead of the memmove) and
-  //    decimate by 2 straight from HBM/L2 (pitch.c:171-173).  The 480 ring slots being overwritten hold
-  //    the oldest samples, which the decimation never reads: no hazard inside the phase.
+  // -- the updated 1728-sample history [old ring part | this frame] (denoise.c:359-360; a ring instead of the memmove)
+  //    is fetched ONCE, in logical order, into the space of the two half-rate signals (dead until the decimation has
+  //    run): 432 aligned 16-byte asynchronous copies per stream, all of a thread's requests in flight together, L1
+  //    bypassed -- one HBM / L2 round trip for the phase (the CTAs of an SM run it in lock-step, so nothing else hides
+  //    the latency; the register version paid four dependent round trips and 32 load instructions per thread).
   MPHASE_BEGIN
     if (a[q].ring) {
       const PitchArgs A = a[q];
-      float *lp0 = PSM(q) + SM_LP0;
+      float *raw = PSM(q) + SM_LP;
       const int H = PITCH_BUF_SIZE - FRAME_SIZE;
-      // A thread's loads are issued in batches before their first use (5 frame samples; 3 x 3 history samples): the CTAs
-      // of an SM run this phase in lock-step, so nothing else hides an HBM / L2 round trip per loop iteration
-      // (14 exposed round trips per thread before, 4 now).
-      {
-        constexpr int NA = (FRAME_SIZE + PITCH_THREADS - 1) / PITCH_THREADS;
-        float v[NA];
-#pragma unroll
-        for (int u = 0; u < NA; u++) { const int j = t + u * PITCH_THREADS; v[u] = j < FRAME_SIZE ? ld_stream(A.xb + j) : 0.f; }
-#pragma unroll
-        for (int u = 0; u < NA; u++) {
-          const int j = t + u * PITCH_THREADS;
-          int p = A.ring_base + H + j; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
-          if (j < FRAME_SIZE) A.ring[p] = v[u];
-        }
+      static_assert(SM_LP == 0 && SM_LP0 == LP_SIZE && 2 * LP_SIZE == PITCH_BUF_SIZE && SM_PITCH_TOTAL % 4 == 0, "raw history over lp | lp0");
+      static_assert((PITCH_BUF_SIZE - FRAME_SIZE) % 4 == 0, "a piece is either old history or new frame");
+      for (int c = t; c < PITCH_BUF_SIZE / 4; c += PITCH_THREADS) {
+        const int k = 4 * c;   // ring base and ring length are multiples of 4 floats: a piece never straddles the ring's end
+        async_copy16(raw + k, k < H ? A.ring + ring_pos(A.ring_base, k) : A.xb + (k - H));
       }
-      for (int i0 = t; i0 < LP_SIZE; i0 += 3 * PITCH_THREADS) {
-        float l[3], c[3], r[3];
-#pragma unroll
-        for (int u = 0; u < 3; u++) {
-          const int i = i0 + u * PITCH_THREADS, k = 2 * i;
-          l[u] = c[u] = r[u] = 0.f;
-          if (i < LP_SIZE) {
-            // sample k of the updated history: old ring part for k < 1248, this frame after that
-            c[u] = k < H ? ld_global(A.ring + ring_pos(A.ring_base, k)) : ld_stream(A.xb + (k - H));
-            r[u] = k + 1 < H ? ld_global(A.ring + ring_pos(A.ring_base, k + 1)) : ld_stream(A.xb + (k + 1 - H));
-            if (i) l[u] = k - 1 < H ? ld_global(A.ring + ring_pos(A.ring_base, k - 1)) : ld_stream(A.xb + (k - 1 - H));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 3; u++) {
-          const int i = i0 + u * PITCH_THREADS;
-          if (i < LP_SIZE) lp0[i] = i ? .5f * (.5f * (l[u] + r[u]) + c[u]) : .5f * (.5f * r[u] + c[u]);
-        }
+    }
+    async_wait_all();
+  MPHASE_END
+  // -- append the new frame to the ring (the 480 slots being overwritten hold the oldest samples, which nothing reads
+  //    any more) and decimate by 2 (pitch.c:171-173) into the scratch that the searches use later
+  MPHASE_BEGIN
+    if (a[q].ring) {
+      const PitchArgs A = a[q];
+      const float *raw = PSM(q) + SM_LP;
+      float *lp0 = PSM(q) + SM_LP0N;
+      const int H = PITCH_BUF_SIZE - FRAME_SIZE;
+      for (int j = t; j < FRAME_SIZE; j += PITCH_THREADS) {
+        int p = A.ring_base + H + j; if (p >= PITCH_BUF_SIZE) p -= PITCH_BUF_SIZE;
+        A.ring[p] = raw[H + j];
+      }
+      for (int i = t; i < LP_SIZE; i += PITCH_THREADS) {
+        const float c = raw[2 * i], r = raw[2 * i + 1];
+        lp0[i] = i ? .5f * (.5f * (raw[2 * i - 1] + r) + c) : .5f * (.5f * r + c);
       }
     }
   MPHASE_END
@@ -119,7 +112,7 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
   MPHASE_BEGIN
     if (tid < 8 * PITCH_NS && (tid & 7) < 5 && a[tid >> 3].ring) {
       const int qq = tid >> 3, k = tid & 7, fastN = LP_SIZE - 4;
-      const float *lp0 = PSM(qq) + SM_LP0;
+      const float *lp0 = PSM(qq) + SM_LP0N;
 #if PITCH_CHAIN4
       const float s = dot_chain4(0.f, lp0, lp0 + k, fastN);
 #else
@@ -138,7 +131,7 @@ HD void pitch_streams(float *sm, const PitchArgs *a, const DspTables *T) {
   // -- 5-tap whitening FIR with zero history (celt_fir5, pitch.c:104-143)
   MPHASE_BEGIN
     if (a[q].ring) {
-      const float *lp0 = PSM(q) + SM_LP0, *num = PSM(q) + SM_PITCH_END + MI_NUM;
+      const float *lp0 = PSM(q) + SM_LP0N, *num = PSM(q) + SM_PITCH_END + MI_NUM;
       float *lp = PSM(q) + SM_LP;
       for (int i = t; i < LP_SIZE; i += PITCH_THREADS) {
         float sum = lp0[i];

@@ -259,9 +259,11 @@ k_gru_tc(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, D
 #ifndef TC2_STAGES
 #define TC2_STAGES 2
 #endif
-// How many slices ahead the epilogue fetches the old state (1 or 2; 2 costs 8 registers per thread)
+// How many slices ahead the epilogue fetches the old state (1 or 2).  Two slices ahead take a layer from 22.3 to 21.0 us
+// at 4096 streams but cost 8 registers per thread (94 instead of 86), which leaves room for one CTA less of the DSP
+// kernels beside a GRU CTA: the pipelined step is slower with it (0.2790 vs 0.2770 ms, profiles/r2q_ab_4096.txt).
 #ifndef TC2_HAHEAD
-#define TC2_HAHEAD 2
+#define TC2_HAHEAD 1
 #endif
 #define P_TMEM_COLS 256                   // >= 2 stages x 96 columns, power of two
 
