@@ -192,6 +192,17 @@ HD cpx cmul(cpx a, cpx b) {
 HD cpx cadd(cpx a, cpx b) { cpx m; m.r = a.r + b.r; m.i = a.i + b.i; return m; }
 HD cpx csub(cpx a, cpx b) { cpx m; m.r = a.r - b.r; m.i = a.i - b.i; return m; }
 
+// The work buffer F is addressed through an XOR swizzle inside its 16-element blocks: element idx lives at
+//   fsw(idx) = idx ^ (((idx >> 4) & 3) << 2),
+// a permutation of each aligned block of 16 that moves the four 4-element groups of block B by B mod 4 places.  The
+// second stage (radix 4, m = 4) reads elements 16 g + j + 4 q with (g, j) = lane: unswizzled, the 16 lanes of a half
+// warp hit only 4 of the 16 8-byte bank pairs (a 4-way conflict on all 8 accesses of a butterfly: 3x the wavefronts
+// of that stage, a quarter of all shared-memory wavefronts of the spectrum and synthesis kernels, profiles/r2p);
+// swizzled, bank = j + 4 (q ^ (g & 3)) takes all 16 values.  The other stages walk j or u linearly inside a block
+// (the XOR is then a constant per half warp) and stay conflict-free; stage 1 still writes 4 contiguous elements.
+// Arithmetic and results are untouched: only where an element is parked between stages changes.
+HD int fsw(int idx) { return idx ^ (((idx >> 4) & 3) << 2); }
+
 // Stage 1 (radix 4, m = 1) fused with the bit-reversed, scaled, windowed load: group g gathers
 // its four inputs straight from `src` (kiss_fft.c:577-584 + kf_bfly4 m==1 branch :112-130).
 // Input element i of the transform is win(i) * src[i] (imag 0) when `herm` is null, or the
@@ -226,28 +237,38 @@ HD void fft_stage1(cpx *F, const float *src, const cpx *herm, const DspTables *T
     s1 = csub(a[1], a[3]);
     a[1].r = s0.r + s1.i; a[1].i = s0.i - s1.r;
     a[3].r = s0.r - s1.i; a[3].i = s0.i + s1.r;
-    F[4 * g + 0] = a[0]; F[4 * g + 1] = a[1]; F[4 * g + 2] = a[2]; F[4 * g + 3] = a[3];
+    cpx *Fo = F + 16 * (g >> 2) + 4 * ((g & 3) ^ ((g >> 2) & 3));   // fsw(4 g .. 4 g + 3): still 4 contiguous elements
+    Fo[0] = a[0]; Fo[1] = a[1]; Fo[2] = a[2]; Fo[3] = a[3];
   }
 }
-// generic radix-4 stage: `m` butterflies per group, groups `gstride` apart, twiddle stride fs
+// radix-4 stages 2 and 3: m = 4 (groups 16 apart, twiddle stride 60) or m = 16 (groups 64 apart, stride 15).
+// Element q of butterfly (g, j) is F[g * gstride + j + q * m]; its swizzled place is
+//   m = 4 : 16 g + j + 4 (q ^ (g & 3))          m = 16 : 64 g + 16 q + (j ^ 4 q)
 HD void fft_radix4(cpx *F0, int m, int gstride, int fs, const DspTables *T, int tid, int nthr) {
   for (int b = tid; b < 240; b += nthr) {
     int g = b / m, j = b % m;
-    cpx *F = F0 + g * gstride + j;
-    cpx s0 = cmul(F[m], T->tw[j * fs]);
-    cpx s1 = cmul(F[2 * m], T->tw[2 * j * fs]);
-    cpx s2 = cmul(F[3 * m], T->tw[3 * j * fs]);
-    cpx f0 = F[0];
+    cpx *F = F0 + g * gstride;
+    int i0, i1, i2, i3;
+    if (m == 4) {
+      const int s = (g & 3) << 2;
+      i0 = j + s; i1 = j + (4 ^ s); i2 = j + (8 ^ s); i3 = j + (12 ^ s);
+    } else {
+      i0 = j; i1 = 16 + (j ^ 4); i2 = 32 + (j ^ 8); i3 = 48 + (j ^ 12);
+    }
+    cpx s0 = cmul(F[i1], T->tw[j * fs]);
+    cpx s1 = cmul(F[i2], T->tw[2 * j * fs]);
+    cpx s2 = cmul(F[i3], T->tw[3 * j * fs]);
+    cpx f0 = F[i0];
     cpx s5 = csub(f0, s1);
     f0 = cadd(f0, s1);
     cpx s3 = cadd(s0, s2);
     cpx s4 = csub(s0, s2);
-    F[2 * m] = csub(f0, s3);
-    F[0] = cadd(f0, s3);
+    F[i2] = csub(f0, s3);
+    F[i0] = cadd(f0, s3);
     cpx o1, o3;
     o1.r = s5.r + s4.i; o1.i = s5.i - s4.r;
     o3.r = s5.r - s4.i; o3.i = s5.i + s4.r;
-    F[m] = o1; F[3 * m] = o3;
+    F[i1] = o1; F[i3] = o3;
   }
 }
 HD void fft_radix3(cpx *F0, const DspTables *T, int tid, int nthr) { // m = 64, 5 groups of 192
@@ -255,7 +276,7 @@ HD void fft_radix3(cpx *F0, const DspTables *T, int tid, int nthr) { // m = 64, 
   const float epi3 = T->tw[fs * m].i;
   for (int b = tid; b < 320; b += nthr) {
     int g = b / m, j = b % m;
-    cpx *F = F0 + g * 192 + j;
+    cpx *F = F0 + g * 192 + fsw(j);   // 192 g and 64 q leave (idx >> 4) & 3 unchanged: the swizzle is that of j
     cpx s1 = cmul(F[m], T->tw[j * fs]);
     cpx s2 = cmul(F[2 * m], T->tw[2 * j * fs]);
     cpx s3 = cadd(s1, s2);
@@ -275,29 +296,30 @@ HD void fft_radix5(cpx *F, const DspTables *T, int tid, int nthr) { // m = 192, 
   const int m = 192;
   const cpx ya = T->tw[m], yb = T->tw[2 * m];
   for (int u = tid; u < m; u += nthr) {
-    cpx s0 = F[u];
-    cpx s1 = cmul(F[u + m], T->tw[u]);
-    cpx s2 = cmul(F[u + 2 * m], T->tw[2 * u]);
-    cpx s3 = cmul(F[u + 3 * m], T->tw[3 * u]);
-    cpx s4 = cmul(F[u + 4 * m], T->tw[4 * u]);
+    const int v = fsw(u);   // 192 q leaves (idx >> 4) & 3 unchanged
+    cpx s0 = F[v];
+    cpx s1 = cmul(F[v + m], T->tw[u]);
+    cpx s2 = cmul(F[v + 2 * m], T->tw[2 * u]);
+    cpx s3 = cmul(F[v + 3 * m], T->tw[3 * u]);
+    cpx s4 = cmul(F[v + 4 * m], T->tw[4 * u]);
     cpx s7 = cadd(s1, s4), s10 = csub(s1, s4), s8 = cadd(s2, s3), s9 = csub(s2, s3);
     cpx o0;
     o0.r = s0.r + (s7.r + s8.r);
     o0.i = s0.i + (s7.i + s8.i);
-    F[u] = o0;
+    F[v] = o0;
     cpx s5, s6, s11, s12;
     s5.r = s0.r + (s7.r * ya.r + s8.r * yb.r);
     s5.i = s0.i + (s7.i * ya.r + s8.i * yb.r);
     s6.r = s10.i * ya.i + s9.i * yb.i;
     s6.i = -(s10.r * ya.i + s9.r * yb.i);
-    F[u + m] = csub(s5, s6);
-    F[u + 4 * m] = cadd(s5, s6);
+    F[v + m] = csub(s5, s6);
+    F[v + 4 * m] = cadd(s5, s6);
     s11.r = s0.r + (s7.r * yb.r + s8.r * ya.r);
     s11.i = s0.i + (s7.i * yb.r + s8.i * ya.r);
     s12.r = s9.i * ya.i - s10.i * yb.i;
     s12.i = s10.r * yb.i - s9.r * ya.i;
-    F[u + 2 * m] = cadd(s11, s12);
-    F[u + 3 * m] = csub(s11, s12);
+    F[v + 2 * m] = cadd(s11, s12);
+    F[v + 3 * m] = csub(s11, s12);
   }
 }
 

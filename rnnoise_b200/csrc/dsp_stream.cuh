@@ -477,7 +477,7 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_BEGIN fft_radix5(F, T, tid, nthr); PHASE_END
   PHASE_BEGIN
     for (int i = tid; i < FREQ_SIZE; i += nthr) {
-      cpx v = F[i];
+      cpx v = F[fsw(i)];
       if (TRAIN && i >= a.lowpass) v.r = v.i = 0.f;
       if (i < 400) XS[i] = v;
       st_stream2(a.spec_out + 2 * i, v.r, v.i);
@@ -491,27 +491,32 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
   PHASE_BEGIN fft_radix3(F, T, tid, nthr); PHASE_END
   PHASE_BEGIN fft_radix5(F, T, tid, nthr); PHASE_END
   PHASE_BEGIN
+    cpx *PT = F + 512;   // |P|^2 terms: the upper half of the work buffer (bins 0..480 park below element 496)
     for (int i = tid; i < FREQ_SIZE; i += nthr) {
-      cpx v = F[i];
+      cpx v = F[fsw(i)];
       st_stream2(a.spec_out + 2 * (FREQ_SIZE + i), v.r, v.i);
       if (i < 400) {
-        // weighted per-bin terms of the three band sums (band_sum_pre), each pair written over the
-        // complex value it came from (this thread's own slots) or into the dead window staging
+        // weighted per-bin terms of the three band sums (band_sum_pre): X's over the complex value they came from (this
+        // thread's own slot), P's into the dead upper half of the work buffer, X.P's into the dead window staging
         const cpx x = XS[i];
         const float wf = T->bin_frac[i], wc = T->bin_cfrac[i];
         const float tx = bin_term(x, x), tp = bin_term(v, v), txp = bin_term(x, v);
         XS[i].r = wf * tx; XS[i].i = wc * tx;
-        F[i].r = wf * tp; F[i].i = wc * tp;
+        PT[i].r = wf * tp; PT[i].i = wc * tp;
         win[i] = wf * txp; win[400 + i] = wc * txp;
       }
     }
   PHASE_END
   // -- the three sets of 34 triangular band sums (compute_band_energy / compute_band_corr), one lane each
   PHASE_BEGIN
+    // Chain lengths run from 2 terms (band 0) to 83 (band 32) and a warp takes as long as its longest lane: the 102
+    // chains are dealt to the lanes longest first (lane L: band 33 - L / 3, set L % 3), so that warp 0 holds the eleven
+    // widest bands of all three sets and the other warps finish after 30, 8 and 4 steps -- 125 warp-steps instead of
+    // 4 x 80 with the sets laid out one after the other (this phase was a fifth of the kernel's instructions).
     if (tid < 3 * (NB_BANDS + 2)) {
-      const int set = tid / (NB_BANDS + 2), b = tid % (NB_BANDS + 2);
+      const int b = NB_BANDS + 1 - tid / 3, set = tid % 3;
       misc[SMI_BAND + 34 * set + b] = set == 2 ? band_sum_pre(b, win, 1, 400, eb)
-                                              : band_sum_pre(b, (const float *)(set == 0 ? XS : F), 2, 1, eb);
+                                              : band_sum_pre(b, (const float *)(set == 0 ? XS : F + 512), 2, 1, eb);
     }
   PHASE_END
   // -- Ex, Ep, Exp (denoise.c:344,375-377)
@@ -631,7 +636,7 @@ HD void train_targets_stream(float *sm, const TrainArgs a, const DspTables *T) {
   PHASE_BEGIN fft_radix5(F, T, tid, nthr); PHASE_END
   PHASE_BEGIN
     for (int i = tid; i < 400; i += nthr) {
-      cpx v = F[i];
+      cpx v = F[fsw(i)];
       if (i >= a.lowpass) v.r = v.i = 0.f;
       const float ty = bin_term(v, v);
       win[i] = T->bin_frac[i] * ty; win[400 + i] = T->bin_cfrac[i] * ty;
@@ -807,8 +812,8 @@ HD void synthesis_stream(float *sm, const SynthesisArgs a, const DspTables *T) {
 #pragma unroll
       for (int u = 0; u < 2; u++) {
         const int i = tid + (u0 + u) * DSP_THREADS, ii = i < FRAME_SIZE ? i : 0;
-        y0[u] = F[ii ? WINDOW_SIZE - ii : 0].r;
-        y1[u] = F[WINDOW_SIZE - (FRAME_SIZE + ii)].r;   // index 480+i -> y[480-i]
+        y0[u] = F[fsw(ii ? WINDOW_SIZE - ii : 0)].r;
+        y1[u] = F[fsw(WINDOW_SIZE - (FRAME_SIZE + ii))].r;   // index 480+i -> y[480-i]
         w0[u] = hws[ii];
         w1[u] = hws[FRAME_SIZE - 1 - ii];
         ol[u] = ola[ii];
