@@ -145,8 +145,8 @@ struct DspTables {
 #define SM_F 0                           // [1920] FFT work buffer (interleaved complex)
 #define SM_XS (SM_F + 2 * WINDOW_SIZE)   // [800] bins 0..399 of X kept for the X.P correlation (the band sums end at bin 400)
 #define SM_WIN (SM_XS + 2 * 400)         // [964] analysis window staged from the ring in 16-byte pieces (the pitch-lagged one starts
-                                         //       0..3 floats into the first piece); after the P transform's first stage: per-bin
-                                         //       terms |P|^2 [0,400), Re(X conj P) [400,800)
+                                         //       0..3 floats into the first piece); after the P transform: the weighted per-bin terms
+                                         //       of Re(X conj P), interleaved (frac, 1 - frac) pairs [0,800)
 #define SM_SPEC_END (SM_WIN + WINDOW_SIZE + 4)
 #define SM_MISC_SIZE 288                 // pitch kernel: small per-stream scalars / vectors after its plan (MI_*)
 #define SM_SPEC_MISC 228                 // spectrum kernel: its own, tighter misc block (SMI_*)

@@ -497,13 +497,14 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
       st_stream2(a.spec_out + 2 * (FREQ_SIZE + i), v.r, v.i);
       if (i < 400) {
         // weighted per-bin terms of the three band sums (band_sum_pre): X's over the complex value they came from (this
-        // thread's own slot), P's into the dead upper half of the work buffer, X.P's into the dead window staging
+        // thread's own slot), P's into the dead upper half of the work buffer, X.P's into the dead window staging; all
+        // three as (frac term, 1 - frac term) pairs
         const cpx x = XS[i];
         const float wf = T->bin_frac[i], wc = T->bin_cfrac[i];
         const float tx = bin_term(x, x), tp = bin_term(v, v), txp = bin_term(x, v);
         XS[i].r = wf * tx; XS[i].i = wc * tx;
         PT[i].r = wf * tp; PT[i].i = wc * tp;
-        win[i] = wf * txp; win[400 + i] = wc * txp;
+        win[2 * i] = wf * txp; win[2 * i + 1] = wc * txp;
       }
     }
   PHASE_END
@@ -514,9 +515,12 @@ HD void spectrum_stream(float *sm, const SpectrumArgs a, const DspTables *T) {
     // widest bands of all three sets and the other warps finish after 30, 8 and 4 steps -- 125 warp-steps instead of
     // 4 x 80 with the sets laid out one after the other (this phase was a fifth of the kernel's instructions).
     if (tid < 3 * (NB_BANDS + 2)) {
+      // (the three sets' terms have the same interleaved layout -- frac term, 1 - frac term per bin -- so that the lanes of
+      //  a warp, which hold all three sets, run ONE instruction stream; with a different layout for the X.P terms the sets
+      //  were three divergent paths executed one after the other)
       const int b = NB_BANDS + 1 - tid / 3, set = tid % 3;
-      misc[SMI_BAND + 34 * set + b] = set == 2 ? band_sum_pre(b, win, 1, 400, eb)
-                                              : band_sum_pre(b, (const float *)(set == 0 ? XS : F + 512), 2, 1, eb);
+      const float *terms = set == 0 ? (const float *)XS : set == 1 ? (const float *)(F + 512) : (const float *)win;
+      misc[SMI_BAND + 34 * set + b] = band_sum_pre(b, terms, 2, 1, eb);
     }
   PHASE_END
   // -- Ex, Ep, Exp (denoise.c:344,375-377)

@@ -265,6 +265,11 @@ k_gru_tc(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, D
 #ifndef TC2_HAHEAD
 #define TC2_HAHEAD 1
 #endif
+// L2 prefetch of the CTA's old-state rows at kernel start (no registers held): the state was written a whole frame ago
+// and has left the L2 at large batch sizes, so the per-slice gathers of the epilogue otherwise wait on HBM
+#ifndef TC2_H_L2PF
+#define TC2_H_L2PF 0
+#endif
 #define P_TMEM_COLS 256                   // >= 2 stages x 96 columns, power of two
 
 template <bool kGru> struct TcCfg {
@@ -427,6 +432,9 @@ k_tc2(int S, int K, int N, int ldo, const __grid_constant__ GruTcMaps maps, DevL
         for (int q = 0; q < P_UPT; q++) dst[q] = 0.f;
       }
     };
+    if (TC2_H_L2PF && kGru && live)   // the row's upc floats = upc / 32 lines of 128 bytes, one per column group of the warp quartet
+      for (int l = ch; l * 32 < upc; l += P_EPI_WARPS / 4)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(&h_old[(size_t)srow * N + jq + l * 32]) : "memory");
     load_h(0, hcur);
     if (TC2_HAHEAD == 2) load_h(1, hnext);
     if (kGru) {   // the parameter records requested in the prologue: own copies landed, then visible to all epilogue warps
