@@ -266,9 +266,11 @@ k_gru_tc(int S, int gru, const __grid_constant__ GruTcMaps maps, DevLayerQ wi, D
 #define TC2_HAHEAD 1
 #endif
 // L2 prefetch of the CTA's old-state rows at kernel start (no registers held): the state was written a whole frame ago
-// and has left the L2 at large batch sizes, so the per-slice gathers of the epilogue otherwise wait on HBM
+// and has left the L2 at large batch sizes, so the per-slice gathers of the epilogue otherwise wait on HBM.  Same-box
+// A/B at 4096 streams (profiles/r2t_ab_4096.txt): 0.2570 -> 0.2564 ms per step -- inside the noise, kept on because it
+// costs nothing; it is the build the r2t evidence was measured with.
 #ifndef TC2_H_L2PF
-#define TC2_H_L2PF 0
+#define TC2_H_L2PF 1
 #endif
 #define P_TMEM_COLS 256                   // >= 2 stages x 96 columns, power of two
 
