@@ -28,6 +28,8 @@ struct EmuState {
 
 extern "C" {
 int emu_streams(void) { return PITCH_NS; }
+// the FFT work buffer's address swizzle (dsp_core.cuh: fsw), for the structural test of its bank mapping
+int emu_fsw(int idx) { return fsw(idx); }
 void *emu_create(void) {
   EmuState *e = (EmuState *)calloc(1, sizeof(EmuState));
   b200_fill_dsp_tables(&e->T);

@@ -141,3 +141,34 @@ def test_log_energy_follower_in_float_equals_the_reference_double_form():
             return out
         a, b = run(True), run(False)
     assert a.tobytes() == b.tobytes()
+
+
+def test_fft_buffer_swizzle_is_a_block_permutation_without_bank_conflicts(emu):
+    """dsp_core.cuh `fsw`: a permutation (involution) of every aligned block of 16 complex elements under which every
+    FFT stage's half warp (16 lanes x 8-byte elements = one shared-memory wavefront) touches 16 different bank pairs --
+    and the radix-4 m = 4 stage, unswizzled, only 4 (the conflict the swizzle removes, profiles/README.md)."""
+    f = [emu.emu_fsw(i) for i in range(960)]
+    assert sorted(f) == list(range(960))
+    assert all(f[f[i]] == i and f[i] // 16 == i // 16 for i in range(960))
+
+    def banks(idx):          # 8-byte elements: 16 bank pairs
+        return {i % 16 for i in idx}
+
+    for b0 in range(0, 240, 16):                      # radix-4 stages: butterfly b = 16 consecutive lanes
+        for q in range(4):
+            m4 = [16 * (b // 4) + b % 4 + 4 * q for b in range(b0, b0 + 16)]
+            assert len(banks(m4)) == 4                 # the unswizzled layout: 4-way conflict
+            assert len(banks(f[i] for i in m4)) == 16
+            m16 = [64 * (b // 16) + b % 16 + 16 * q for b in range(b0, b0 + 16)]
+            assert len(banks(f[i] for i in m16)) == 16
+    for b0 in range(0, 320, 16):                      # radix 3: m = 64
+        for q in range(3):
+            assert len(banks(f[192 * (b // 64) + b % 64 + 64 * q] for b in range(b0, b0 + 16))) == 16
+    for u0 in range(0, 192, 16):                      # radix 5: m = 192
+        for q in range(5):
+            assert len(banks(f[u + 192 * q] for u in range(u0, u0 + 16))) == 16
+    for i0 in range(0, 480, 16):                      # linear consumers (spectrum stores, per-bin terms)
+        assert len(banks(f[i] for i in range(i0, i0 + 16))) == 16
+    for g0 in range(0, 240, 4):                       # stage 1 writes 4 contiguous elements per group
+        for g in range(g0, g0 + 4):
+            assert [f[4 * g + q] for q in range(4)] == list(range(f[4 * g], f[4 * g] + 4))
