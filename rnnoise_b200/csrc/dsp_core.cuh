@@ -125,12 +125,13 @@ struct DspTables {
 // Shared-memory plans (floats).  The analysis of one frame is two kernels, each CTA = one stream:
 //   pitch kernel    : whitened half-rate signal + search scratch          (SM_PITCH_END + SM_MISC_SIZE)
 //   spectrum kernel : FFT work buffer + a copy of X for the X.P correlation (SM_SPEC_END + SM_MISC_SIZE)
-// The pitch history itself stays in HBM/L2 (ring): it is read once, in order, by the decimation and
-// gathered once per FFT by stage 1.
+// The pitch history itself stays in HBM/L2 (ring): the pitch kernel stages it once (aligned 16-byte asynchronous
+// copies, logical order) for the decimation, the spectrum kernel fetches its two analysis windows the same way.
 // ------------------------------------------------------------------------------------------------
 //   pitch kernel
 #define SM_LP 0                          // [864] whitened half-rate signal
-#define SM_LP0 (SM_LP + LP_SIZE)         // [864] decimated signal before whitening (dies after FIR)
+#define SM_LP0 (SM_LP + LP_SIZE)         // [864] second half of the raw-history staging [SM_LP, SM_LP + 1728) of the first phase (the decimated
+                                         //       signal before whitening is SM_LP0N); x4 / y4 / xcorr ... overlay it afterwards
 #define SM_X4 (SM_LP0)                   // [240]   (reuses LP0 once the FIR is done)
 #define SM_Y4 (SM_X4 + 240)              // [388]
 #define SM_XC (SM_Y4 + 388)              // [296] coarse / fine correlations
@@ -151,7 +152,7 @@ struct DspTables {
 #define SM_MISC_SIZE 288                 // pitch kernel: small per-stream scalars / vectors after its plan (MI_*)
 #define SM_SPEC_MISC 228                 // spectrum kernel: its own, tighter misc block (SMI_*)
 #define SM_PITCH_TOTAL (SM_PITCH_END + SM_MISC_SIZE)
-#define SM_SPEC_TOTAL (SM_SPEC_END + SM_SPEC_MISC)   // 3888 floats = 15.2 KB (registers, not shared memory, set the CTAs per SM: engine.cu)
+#define SM_SPEC_TOTAL (SM_SPEC_END + SM_SPEC_MISC)   // 3912 floats = 15.3 KB (registers, not shared memory, set the CTAs per SM: engine.cu)
 // misc slots (float indices relative to the misc base)
 #define MI_AC 64    // [5] autocorrelation
 #define MI_NUM 72   // [5] whitening FIR taps
