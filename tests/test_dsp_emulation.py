@@ -172,3 +172,57 @@ def test_fft_buffer_swizzle_is_a_block_permutation_without_bank_conflicts(emu):
     for g0 in range(0, 240, 4):                       # stage 1 writes 4 contiguous elements per group
         for g in range(g0, g0 + 4):
             assert [f[4 * g + q] for q in range(4)] == list(range(f[4 * g], f[4 * g] + 4))
+
+
+def _edge_signals(frames):
+    n = frames * 480
+    t = np.arange(n)
+    rng = np.random.default_rng(1)
+    yield "fullscale_square", (32767 * np.sign(np.sin(2 * np.pi * 440 * t / 48000))).astype(np.float32)
+    x = np.zeros(n, np.float32); x[::997] = 30000
+    yield "impulses", x
+    yield "dc", np.full(n, 12345.0, np.float32)
+    yield "tiny_noise", (rng.standard_normal(n) * 1e-30).astype(np.float32)
+    yield "denormal_noise", (rng.standard_normal(n) * 1e-41).astype(np.float32)
+    yield "clipping_noise", np.clip(rng.standard_normal(n) * 40000, -32768, 32767).astype(np.float32)
+    x = (rng.standard_normal(n) * 3000).astype(np.float32); x[5000:5480] = 0; x[9600:14400] = 0
+    yield "gaps_of_silence", x
+    x = (rng.standard_normal(n) * 3000).astype(np.float32); x[7000] = np.nan
+    yield "one_nan", x
+    x = (rng.standard_normal(n) * 3000).astype(np.float32); x[7000] = np.inf
+    yield "one_inf", x
+
+
+@pytest.mark.parametrize("name,sig", list(_edge_signals(40)), ids=[n for n, _ in _edge_signals(40)])
+def test_device_dsp_source_on_edge_case_signals(emu, port_default, name, sig):
+    """Full-scale, impulsive, constant, vanishing (incl. denormal), clipped and gapped input: the device DSP source stays
+    bit-identical to the port.  A non-finite sample poisons the state of the reference for good (every later output sample is
+    NaN); the device source does the same, sample for sample -- only the sign bit of those NaNs (which operand of a
+    commutative x86 instruction came first) is outside the contract."""
+    frames = len(sig) // 480
+    pcm = sig.reshape(frames, 480)
+    st = port_default.create()
+    e = emu.emu_create()
+    finite = np.isfinite(sig).all()
+    for f in range(frames):
+        emu.emu_analysis(e, fptr(np.ascontiguousarray(pcm[f][None])), 1)
+        b = port_default.process_frame(st, pcm[f])
+        xb = np.zeros(480, np.float32); feat = np.zeros(65, np.float32)
+        X = np.zeros(962, np.float32); P = np.zeros(962, np.float32)
+        bands = np.zeros(96, np.float32); pitch = np.zeros(2, np.float32)
+        sil = emu.emu_get(e, 0, fptr(xb), fptr(feat), fptr(X), fptr(P), fptr(bands), fptr(pitch))
+        out = np.zeros(480, np.float32); lastg = np.zeros(32, np.float32)
+        emu.emu_synthesis(e, 0, fptr(b["g_raw"]), fptr(out), fptr(lastg))
+        for k, u, v in (("xb", xb, b["xb"]), ("features", feat, b["features"]), ("X", X, b["X"]), ("P", P, b["P"]),
+                        ("Ex", bands[:32], b["Ex"]), ("Ep", bands[32:64], b["Ep"]), ("Exp", bands[64:], b["Exp"]),
+                        ("out", out, b["out"]), ("lastg", lastg, b["lastg"])):
+            if finite:
+                assert u.tobytes() == v.tobytes(), (name, k, f)
+            else:
+                assert np.array_equal(np.isnan(u), np.isnan(v)), (name, k, f)
+                m = ~np.isnan(u)
+                assert u[m].tobytes() == v[m].tobytes(), (name, k, f)
+        if finite:
+            assert sil == b["silence"] and int(pitch[0]) == b["pitch"], (name, f)
+        emu.emu_advance(e)
+    emu.emu_destroy(e)

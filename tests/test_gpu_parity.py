@@ -502,3 +502,39 @@ def test_lanes_do_not_change_results(rb, models_dir, S, lanes, expect, monkeypat
     for b in (ref, ref16, a, a16, dev, multi):
         b.destroy()
     model.free()
+
+
+def test_edge_case_signals_and_poisoned_neighbours(rb, port_default, models_dir):
+    """Full-scale square wave, impulses, DC, vanishing (incl. denormal) noise, clipped noise and gaps of digital silence as
+    streams of one batch: every DSP quantity, the PCM and the VAD stay bit-identical to the port.  Two more streams carry
+    one NaN / one Inf sample (the reference's state is poisoned for good by either): their NaNs must not reach any other
+    stream of the batch -- the ordinary stream next to them stays bit-exact."""
+    from test_dsp_emulation import _edge_signals
+    frames = 40
+    sigs = list(_edge_signals(frames))
+    names = [n for n, _ in sigs] + ["ordinary"]
+    pcm = np.stack([x.reshape(frames, 480) for _, x in sigs] + [stream_pcm(3, frames)], axis=1)   # [frames][S][480]
+    S = pcm.shape[1]
+    finite = [bool(np.isfinite(pcm[:, i]).all()) for i in range(S)]
+    model = rb.Model(os.path.join(models_dir, "default.bin"))
+    batch = rb.Batch(model, S)
+    states = [port_default.create() for _ in range(S)]
+    nan_pos_mismatch = 0
+    for f in range(frames):
+        out, vad = batch.process(pcm[f])
+        for i in range(S):
+            r = port_default.process_frame(states[i], pcm[f, i])
+            tag = f"frame {f} stream {names[i]}"
+            if finite[i]:
+                assert int(batch.debug("silence", i)[0]) == r["silence"] and int(batch.debug("pitch", i)[0]) == r["pitch"], tag
+                for key in ("xb", "X", "P", "Ex", "Ep", "Exp", "features"):
+                    assert np.array_equal(bits(batch.debug(key, i)), bits(r[key])), f"{key} not bit-exact, {tag}"
+                assert np.array_equal(bits(out[i]), bits(r["out"])), f"pcm, {tag}"
+                assert np.array_equal(bits(vad[i:i + 1]), bits(np.float32([r["vad"]]))), f"vad, {tag}"
+            else:
+                nan_pos_mismatch += int((np.isnan(out[i]) != np.isnan(r["out"])).sum())
+    print("NaN-position differences on the poisoned streams (informative):", nan_pos_mismatch)
+    for st in states:
+        port_default.destroy(st)
+    batch.destroy()
+    model.free()
